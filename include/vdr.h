@@ -1,0 +1,172 @@
+/*
+ * vdr.h -- C ABI of libvdr.so, the B200 (sm_100a) kernels behind the vit-deep-radiomics hot path.
+ *
+ * The reference (larosi/vit-deep-radiomics) has no FFI: every GPU op is a stock PyTorch or
+ * third-party module call made from Python.  Each entry point below
+ * therefore cites the reference *call site* it replaces (file:line under /root/reference/src).
+ * The Python drop-in modules in vit_deep_radiomics_b200/ bind these with ctypes (see
+ * INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory (incl. workspaces) and keeps it alive until `stream` reaches the op;
+ *   - the library never allocates device memory, never synchronises, never changes the device;
+ *   - return 0 on success, a negative VDR_E* for argument errors, a positive cudaError_t otherwise;
+ *     vdr_last_error_string() gives a thread-local description of the last non-zero return;
+ *   - matrices are row-major; "ld*" are leading dimensions in ELEMENTS;
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t), f32 = float.
+ */
+#ifndef VDR_H_
+#define VDR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* vdr_stream_t;
+
+#define VDR_OK            0
+#define VDR_EINVAL       -1   /* bad shape / null pointer / unsupported value */
+#define VDR_EALIGN       -2   /* pointer or leading dimension not 16-byte aligned */
+#define VDR_EWORKSPACE   -3   /* workspace too small */
+#define VDR_EUNSUPPORTED -4   /* valid request this build does not implement */
+#define VDR_EDRIVER      -5   /* could not obtain a driver entry point (TMA descriptor encode) */
+
+#define VDR_DTYPE_BF16 0
+#define VDR_DTYPE_F32  1
+
+/* epilogue selectors for vdr_gemm */
+#define VDR_EPI_BIAS          0   /* C = A W^T + b                                         */
+#define VDR_EPI_BIAS_GELU     1   /* C = gelu_erf(A W^T + b)                                */
+#define VDR_EPI_BIAS_RESIDUAL 2   /* C = A W^T + b + R                                      */
+
+int         vdr_version(void);
+const char* vdr_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t    vdr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM on tcgen05 tensor cores: C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N] (+ R)).
+ * A, W bf16 (K contiguous), fp32 accumulation in TMEM, bias f32 (may be NULL), C bf16 or f32.
+ * Replaces: torch.nn.Linear inside the backbone (tfds_dense_descriptor.py:123, K3 in SURVEY 2.4)
+ * and inside nn.TransformerEncoderLayer / MLPLayer (models_archs.py:130-137,146,193-199).
+ *
+ * Row remapping (used to write patch tokens behind the CLS token and to add pos-embed):
+ *   out_row(m) = (out_group > 0) ? (m / out_group) * out_group_stride + out_offset + m % out_group : m
+ *   res_row(m) = (res_mod   > 0) ? res_offset + m % res_mod : out_row(m)
+ * Requirements: N % 8 == 0, lda/ldw/ldc/ldr % 8 == 0, 16-byte aligned pointers.  K is arbitrary
+ *   (the K tail is zero-filled by TMA), e.g. K = 588 for 14x14 patches with lda = ldw = 592.
+ */
+typedef struct {
+  const void* A;  int64_t lda;
+  const void* W;  int64_t ldw;
+  const float* bias;
+  const void* R;  int64_t ldr;  int r_dtype;      /* residual (bf16 or f32), only for EPI_BIAS_RESIDUAL */
+  void* C;        int64_t ldc;  int c_dtype;
+  int M, N, K;
+  int epilogue;
+  int out_group, out_group_stride, out_offset;    /* 0,0,0 = identity */
+  int res_mod, res_offset;                        /* 0,0 = same row as the output */
+} vdr_gemm_args;
+
+int vdr_gemm(const vdr_gemm_args* args, vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch extraction (im2col) fused with the reference's host-side image preparation.
+ * Replaces: prepare_image (tfds_dense_descriptor.py:30-48: gray2rgb + HWC->NCHW + float32 cast)
+ * and the data movement of the patch-embedding conv (K1).  Output A[(b,py,px), (c,iy,ix)] bf16,
+ * i.e. the K-major operand of vdr_gemm with W = conv weight viewed as (d, 3*p*p).
+ *   src: f32, element strides (in elements) for batch/channel/row/col; channel stride 0 = gray
+ *   image replicated to 3 channels (gray2rgb, :41).
+ */
+int vdr_im2col_patches(const float* src, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                       int B, int H, int W, int patch, void* A_bf16, vdr_stream_t stream);
+
+/* CLS rows of the token matrix: X[b*N + 0, :] = cls[:] + pos[0, :]   (f32 params -> bf16 tokens) */
+int vdr_write_cls_rows(const float* cls, const float* pos0, void* X_bf16, int B, int N, int d,
+                       vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim, one warp per row, 16-byte vector loads, fp32 statistics.
+ * Replaces: Block.norm1/norm2 + final norm of the backbone (K2) and nn.LayerNorm in the
+ * classifier (models_archs.py:145 and the post-norms inside nn.TransformerEncoderLayer).
+ * x bf16 (rows, d) -> y (bf16 or f32).  d % 8 == 0, d <= 4096.  Optional mean/rstd (f32, rows)
+ * are written when non-NULL (saved for the backward pass).
+ */
+int vdr_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta,
+                      void* y, int64_t ldy, int y_dtype, float* mean, float* rstd,
+                      int rows, int d, float eps, vdr_stream_t stream);
+
+/* dx, dgamma, dbeta of the LayerNorm above.  dgamma/dbeta are ACCUMULATED (+=) into f32 buffers. */
+int vdr_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                      const float* gamma, const float* mean, const float* rstd,
+                      void* dx, int64_t lddx, float* dgamma, float* dbeta,
+                      int rows, int d, vdr_stream_t stream);
+
+/* CLS concat + LayerNorm in one pass: Y[0] = LN(cls), Y[1+i] = LN(X[i]).
+ * Replaces: torch.cat([cls, x]) + self.norm(x)  (models_archs.py:143-145).
+ * X f32 (n, d) tokens as produced by the gather; Y bf16 (n+1, d); mean/rstd (n+1) optional. */
+int vdr_cls_concat_layernorm_fwd(const float* X, const float* cls, const float* gamma,
+                                 const float* beta, void* Y_bf16, float* mean, float* rstd,
+                                 int n, int d, float eps, vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused flash-style self-attention forward on tcgen05 (head_dim 64).
+ * Replaces: Attention.forward of the backbone (K4) and the SDPA inside
+ * nn.TransformerEncoderLayer (models_archs.py:146).
+ * qkv bf16 (B*N, 3*d) as written by the QKV GEMM: [q(h,64) | k(h,64) | v(h,64)] per token;
+ * out bf16 (B*N, d).  lse (B, h, N) f32 optional (log-sum-exp, for the backward pass).
+ */
+int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse,
+                       int B, int N, int heads, float scale, vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * G1: tumour-mask gather of ViT descriptors into a per-patient point cloud.
+ * Replaces: PETCTDataset3D._get_features (train_models.py:143-182): nearest mask resize (:151),
+ * (h,w,S) flatten order (:159-163), boolean row gather (:180) and, optionally, the 3-D
+ * sinusoidal positional encoding added as PE/4 (:30-44,178-180; computed in f64).
+ *
+ *   feat      (S, h, w, D) descriptors, slice-major as the backbone writes them (bf16 or f32),
+ *             row stride ld_feat elements between consecutive (s,a,b) tokens
+ *   mask      (S, hm, wm) u8 pixel masks; row_map[h], col_map[w] (int32) give the source pixel
+ *             row/col of each feature-grid row/col (the order-0 resize index maps)
+ *   out_tok   (cap, D) f32 packed tokens in ascending n = a*(w*S) + b*S + k   (stable)
+ *   out_src   (cap, 3) int32 (slice k, row a, col b) per token
+ *   out_count int32[1] number selected (may exceed cap: rows beyond cap are not written)
+ *   pe        if pe_scale != 0: tokens = f32(f64(token) + pe_scale * PE3D(x,y,z)) with
+ *             x = (xi/w)*w_orig*res[0] - mean_x + noise[0] ... exactly as :166-176, in f64;
+ *             pe_div (device, f64[D/6]) = 10000^(6i/D) as computed by the host (:34);
+ *             coef_host (HOST, f64[11]) = {w_orig, h_orig, res0, res1, res2,
+ *                                          noise0, noise1, noise2, mean_x, mean_y, mean_z}
+ *   workspace >= vdr_mask_gather_workspace_bytes(S,h,w)
+ */
+size_t vdr_mask_gather_workspace_bytes(int S, int h, int w);
+int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat,
+                    const uint8_t* mask, int hm, int wm, const int32_t* row_map, const int32_t* col_map,
+                    int S, int h, int w, int D,
+                    float* out_tok, int32_t* out_src, int32_t* out_count, int cap,
+                    double pe_scale, const double* pe_div, const double* coef_host,
+                    void* workspace, size_t workspace_bytes, vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * G2: voxel point cloud.  Replaces: to_pointcloud_df + the caller's mask_box filter
+ * (create_pointcloud_dataframe.py:15-31,78).
+ *   img f32 (H,W,S), mask u8 (H,W,S).  Pass 1 reduces the index-space bounding box of mask>0
+ *   (bbox int32[6] = xi_min,xi_max,yi_min,yi_max,zi_min,zi_max with the reference's xy-meshgrid
+ *   index convention xi=(n/S)%H, yi=n/(H*S), zi=n%S; empty mask -> min>max).  Pass 2 compacts
+ *   every voxel inside the box: out_flat int32 (flat index n), out_raw f32, out_mask u8,
+ *   out_count int32[1].  Order is ascending n (stable).  A box in (yi, xi, zi) is ordered exactly
+ *   like n = (yi*H + xi)*S + zi, so pass 2 needs no scan: output row j maps to its voxel in closed form.
+ */
+int vdr_voxel_bbox(const uint8_t* mask, int H, int W, int S, int32_t* bbox, vdr_stream_t stream);
+int vdr_voxel_gather(const float* img, const uint8_t* mask, int H, int W, int S, const int32_t* bbox,
+                     int32_t* out_flat, float* out_raw, uint8_t* out_mask, int32_t* out_count, int cap,
+                     vdr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDR_H_ */

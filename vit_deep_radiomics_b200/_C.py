@@ -1,0 +1,96 @@
+"""ctypes binding of libvdr.so (C ABI declared in include/vdr.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  The
+library is built in-tree by ``__graft_entry__.build()`` / ``make -C vit_deep_radiomics_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvdr.so")
+
+VDR_DTYPE_BF16, VDR_DTYPE_F32 = 0, 1
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+
+#: every symbol include/vdr.h declares (checked by tests/test_abi.py)
+EXPORTS = (
+    "vdr_version", "vdr_last_error_string", "vdr_launch_count",
+    "vdr_gemm", "vdr_im2col_patches", "vdr_write_cls_rows",
+    "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd",
+    "vdr_flash_attn_fwd",
+    "vdr_mask_gather_workspace_bytes", "vdr_mask_gather",
+    "vdr_voxel_bbox", "vdr_voxel_gather",
+)
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p),
+        ("R", C.c_void_p), ("ldr", C.c_int64), ("r_dtype", C.c_int),
+        ("C", C.c_void_p), ("ldc", C.c_int64), ("c_dtype", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("epilogue", C.c_int),
+        ("out_group", C.c_int), ("out_group_stride", C.c_int), ("out_offset", C.c_int),
+        ("res_mod", C.c_int), ("res_offset", C.c_int),
+    ]
+
+
+class VdrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libvdr.so once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise VdrError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C vit_deep_radiomics_b200/csrc`.  There is no CPU/PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+    L.vdr_version.restype = i32
+    L.vdr_last_error_string.restype = C.c_char_p
+    L.vdr_launch_count.restype = C.c_uint64
+    L.vdr_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+    L.vdr_im2col_patches.argtypes = [vp, i64, i64, i64, i64, i32, i32, i32, i32, vp, vp]
+    L.vdr_write_cls_rows.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.vdr_layernorm_fwd.argtypes = [vp, i64, vp, vp, vp, i64, i32, vp, vp, i32, i32, f32, vp]
+    L.vdr_layernorm_bwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp]
+    L.vdr_cls_concat_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]
+    L.vdr_flash_attn_fwd.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, f32, vp]
+    L.vdr_mask_gather_workspace_bytes.argtypes = [i32, i32, i32]
+    L.vdr_mask_gather_workspace_bytes.restype = sz
+    L.vdr_mask_gather.argtypes = [vp, i32, i64, vp, i32, i32, vp, vp, i32, i32, i32, i32,
+                                  vp, vp, vp, i32, f64, vp, C.POINTER(f64), vp, sz, vp]
+    L.vdr_voxel_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.vdr_voxel_gather.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("vdr_version", "vdr_last_error_string", "vdr_launch_count",
+                        "vdr_mask_gather_workspace_bytes"):
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    """Map the C return code to a Python exception (reference convention: plain exceptions)."""
+    if rc == 0:
+        return
+    msg = lib().vdr_last_error_string().decode("utf-8", "replace")
+    if rc in (-1, -2, -3):
+        raise ValueError(f"{what}: {msg} (VDR code {rc})")
+    raise VdrError(f"{what}: {msg} (code {rc})")
+
+
+def launch_count() -> int:
+    return int(lib().vdr_launch_count())

@@ -1,0 +1,353 @@
+// Tumour-mask gathers.
+//   G1  vdr_mask_gather : stable stream compaction of in-mask ViT tokens into a point cloud
+//       (warp ballot + popc ranks inside a tile, tile counts -> exclusive scan -> scatter),
+//       rows copied warp-wide with 16-byte accesses, optional fp64 3-D sinusoidal PE epilogue.
+//   G2  vdr_voxel_bbox / vdr_voxel_gather : bounding box of the mask, then every voxel inside it.
+// Index contracts are in SURVEY.md Appendix A1/A2/A6 and restated in oracle/gather_np.py.
+#include "common.cuh"
+
+namespace vdr {
+
+constexpr int kTile = 2048;      // candidates per block
+constexpr int kGThreads = 256;   // 8 warps
+constexpr int kIters = kTile / kGThreads;
+
+struct G1Geom {
+  const uint8_t* mask;
+  const int32_t* row_map;
+  const int32_t* col_map;
+  int S, h, w, hm, wm;
+  int64_t total;
+};
+
+// candidate n = a*(w*S) + b*S + k  (slice fastest)  ->  resized-mask value
+__device__ __forceinline__ bool g1_pred(const G1Geom& g, int64_t n) {
+  const int k = static_cast<int>(n % g.S);
+  const int64_t q = n / g.S;
+  const int b = static_cast<int>(q % g.w);
+  const int a = static_cast<int>(q / g.w);
+  const int64_t off = (static_cast<int64_t>(k) * g.hm + __ldg(g.row_map + a)) * g.wm + __ldg(g.col_map + b);
+  return __ldg(g.mask + off) != 0;
+}
+
+__global__ void __launch_bounds__(kGThreads) g1_count_kernel(G1Geom g, int32_t* __restrict__ tile_counts) {
+  __shared__ int s_warp[kGThreads / 32];
+  const int64_t tile_base = static_cast<int64_t>(blockIdx.x) * kTile;
+  int cnt = 0;
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    const int64_t n = tile_base + it * kGThreads + threadIdx.x;
+    const bool p = (n < g.total) && g1_pred(g, n);
+    cnt += __popc(__ballot_sync(0xffffffffu, p));
+  }
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;  // every lane holds the warp total
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < kGThreads / 32; ++i) t += s_warp[i];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
+// Single-block exclusive scan of the tile counts; writes the grand total to out_count.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const int32_t* __restrict__ counts,
+                                                         int32_t* __restrict__ offsets, int num_tiles,
+                                                         int32_t* __restrict__ out_count) {
+  __shared__ int s_warp[32];
+  const int per = (num_tiles + 1023) / 1024;
+  const int begin = threadIdx.x * per;
+  int end = begin + per;
+  if (end > num_tiles) end = num_tiles;
+  int sum = 0;
+  for (int i = begin; i < end; ++i) sum += counts[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    s_warp[lane] = wi - w;  // exclusive warp offsets
+  }
+  __syncthreads();
+  int run = s_warp[warp] + incl - sum;
+  for (int i = begin; i < end; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+  if (threadIdx.x == 1023) *out_count = run;
+}
+
+struct G1Pe {
+  double scale;          // 0 = no positional encoding
+  const double* div;     // [D/6] divisors 10000^(6 i / D), host-computed in f64
+  double w_orig, h_orig, res0, res1, res2, noise0, noise1, noise2, mean_x, mean_y, mean_z;
+};
+
+template <bool FEAT_BF16>
+__global__ void __launch_bounds__(kGThreads)
+g1_scatter_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int D,
+                  const int32_t* __restrict__ tile_offsets, float* __restrict__ out_tok,
+                  int32_t* __restrict__ out_src, int cap, G1Pe pe) {
+  __shared__ int s_cnt[kIters * 8];
+  __shared__ int s_off[kIters * 8 + 1];
+  __shared__ int s_sel[kTile];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile_base = static_cast<int64_t>(blockIdx.x) * kTile;
+  uint32_t ballots[kIters];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    const int64_t n = tile_base + it * kGThreads + threadIdx.x;
+    const bool p = (n < g.total) && g1_pred(g, n);
+    ballots[it] = __ballot_sync(0xffffffffu, p);
+    mine |= (p ? 1u : 0u) << it;
+    if (lane == 0) s_cnt[it * 8 + warp] = __popc(ballots[it]);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the 64 (iteration, warp) counts, two per lane
+    const int v0 = s_cnt[lane * 2], v1 = s_cnt[lane * 2 + 1];
+    const int sum = v0 + v1;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    s_off[lane * 2] = incl - sum;
+    s_off[lane * 2 + 1] = incl - sum + v0;
+    if (lane == 31) s_off[kIters * 8] = incl;
+  }
+  __syncthreads();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int it = 0; it < kIters; ++it)
+    if ((mine >> it) & 1u) {
+      const int pos = s_off[it * 8 + warp] + __popc(ballots[it] & lt_mask);
+      s_sel[pos] = it * kGThreads + threadIdx.x;
+    }
+  __syncthreads();
+  const int tile_n = s_off[kIters * 8];
+  const int64_t tile_off = tile_offsets[blockIdx.x];
+  const int third = D / 3, two_third = (2 * D) / 3, npair2 = 2 * (D / 6);
+  for (int j = warp; j < tile_n; j += 8) {
+    const int64_t row_out = tile_off + j;
+    if (row_out >= cap) break;
+    const int64_t n = tile_base + s_sel[j];
+    const int k = static_cast<int>(n % g.S);
+    const int64_t q = n / g.S;
+    const int b = static_cast<int>(q % g.w);
+    const int a = static_cast<int>(q / g.w);
+    if (lane == 0) {
+      out_src[row_out * 3 + 0] = k;
+      out_src[row_out * 3 + 1] = a;
+      out_src[row_out * 3 + 2] = b;
+    }
+    double x = 0., y = 0., z = 0.;
+    if (pe.scale != 0.) {
+      // reference meshgrid(indexing='xy') quirk: xi = (n / S) % h, yi = n / (h*S), zi = n % S
+      const double xi = static_cast<double>(q % g.h), yi = static_cast<double>(n / (static_cast<int64_t>(g.h) * g.S));
+      x = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(xi / static_cast<double>(g.w), pe.w_orig), pe.res0), pe.mean_x), pe.noise0);
+      y = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(yi / static_cast<double>(g.h), pe.h_orig), pe.res1), pe.mean_y), pe.noise1);
+      z = __dadd_rn(__dsub_rn(__dmul_rn(static_cast<double>(k), pe.res2), pe.mean_z), pe.noise2);
+    }
+    const int64_t src_row = (static_cast<int64_t>(k) * g.h + a) * g.w + b;
+    for (int c0 = lane * 8; c0 < D; c0 += 256) {
+      float f[8];
+      if (FEAT_BF16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(feat) + src_row * ld_feat + c0);
+        const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
+        f[0] = p0.x; f[1] = p0.y; f[2] = p1.x; f[3] = p1.y; f[4] = p2.x; f[5] = p2.y; f[6] = p3.x; f[7] = p3.y;
+      } else {
+        const float* fp = static_cast<const float*>(feat) + src_row * ld_feat + c0;
+        const float4 u0 = *reinterpret_cast<const float4*>(fp), u1 = *reinterpret_cast<const float4*>(fp + 4);
+        f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
+      }
+      if (pe.scale != 0.) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = c0 + i;
+          int jj;
+          double v;
+          if (col < third) { jj = col; v = x; }
+          else if (col < two_third) { jj = col - third; v = y; }
+          else { jj = col - two_third; v = z; }
+          if (jj < npair2) {
+            const double arg = v / pe.div[jj >> 1];
+            const double enc = (jj & 1) ? cos(arg) : sin(arg);
+            f[i] = static_cast<float>(__dadd_rn(static_cast<double>(f[i]), __dmul_rn(enc, pe.scale)));
+          }
+        }
+      }
+      float* op = out_tok + row_out * D + c0;
+      *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- G2
+__global__ void bbox_init_kernel(int32_t* bbox) {
+  if (threadIdx.x < 6) bbox[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(256) voxel_bbox_kernel(const uint8_t* __restrict__ mask, int H, int S,
+                                                         int64_t total, int32_t* __restrict__ bbox) {
+  int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-1, -1, -1};
+  // 16 mask bytes per thread per step
+  const int64_t nvec = total >> 4;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec + 1; v += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t wds[4] = {0, 0, 0, 0};
+    int cnt = 16;
+    if (v < nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(mask) + v);
+      wds[0] = u.x; wds[1] = u.y; wds[2] = u.z; wds[3] = u.w;
+    } else {  // tail
+      cnt = static_cast<int>(total - (nvec << 4));
+      for (int i = 0; i < cnt; ++i) wds[i >> 2] |= static_cast<uint32_t>(mask[(nvec << 4) + i]) << ((i & 3) * 8);
+    }
+    if ((wds[0] | wds[1] | wds[2] | wds[3]) == 0) continue;
+    for (int i = 0; i < cnt; ++i) {
+      if ((wds[i >> 2] >> ((i & 3) * 8)) & 0xffu) {
+        const int64_t n = (v << 4) + i;
+        const int zi = static_cast<int>(n % S);
+        const int64_t q = n / S;
+        const int xi = static_cast<int>(q % H), yi = static_cast<int>(q / H);
+        lo[0] = min(lo[0], xi); hi[0] = max(hi[0], xi);
+        lo[1] = min(lo[1], yi); hi[1] = max(hi[1], yi);
+        lo[2] = min(lo[2], zi); hi[2] = max(hi[2], zi);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0 && hi[a] >= 0) {
+      atomicMin(bbox + 2 * a, lo[a]);
+      atomicMax(bbox + 2 * a + 1, hi[a]);
+    }
+  }
+}
+
+// Voxels inside the box, ascending flat index n = (yi*H + xi)*S + zi: a box in (yi, xi, zi) is
+// lexicographically ordered exactly like n, so output row j maps to its voxel in closed form.
+__global__ void __launch_bounds__(256)
+voxel_gather_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, int H, int S,
+                    const int32_t* __restrict__ bbox, int32_t* __restrict__ out_flat, float* __restrict__ out_raw,
+                    uint8_t* __restrict__ out_mask, int32_t* __restrict__ out_count, int cap) {
+  const int x0 = bbox[0], x1 = bbox[1], y0 = bbox[2], y1 = bbox[3], z0 = bbox[4], z1 = bbox[5];
+  const int64_t ex = (x1 >= x0) ? (x1 - x0 + 1) : 0, ey = (y1 >= y0) ? (y1 - y0 + 1) : 0, ez = (z1 >= z0) ? (z1 - z0 + 1) : 0;
+  const int64_t count = ex * ey * ez;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = static_cast<int32_t>(count);
+  const int64_t lim = count < cap ? count : cap;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < lim; j += (int64_t)gridDim.x * blockDim.x) {
+    const int zi = z0 + static_cast<int>(j % ez);
+    const int64_t t = j / ez;
+    const int xi = x0 + static_cast<int>(t % ex);
+    const int yi = y0 + static_cast<int>(t / ex);
+    const int64_t n = (static_cast<int64_t>(yi) * H + xi) * S + zi;
+    out_flat[j] = static_cast<int32_t>(n);
+    out_raw[j] = __ldg(img + n);
+    out_mask[j] = __ldg(mask + n);
+  }
+}
+
+}  // namespace vdr
+
+extern "C" size_t vdr_mask_gather_workspace_bytes(int S, int h, int w) {
+  const int64_t total = (int64_t)S * h * w;
+  const int64_t tiles = (total + vdr::kTile - 1) / vdr::kTile;
+  return (size_t)(tiles > 0 ? tiles : 1) * 2 * sizeof(int32_t);
+}
+
+extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, const uint8_t* mask, int hm, int wm,
+                               const int32_t* row_map, const int32_t* col_map, int S, int h, int w, int D,
+                               float* out_tok, int32_t* out_src, int32_t* out_count, int cap, double pe_scale,
+                               const double* pe_div, const double* coef_host, void* workspace,
+                               size_t workspace_bytes, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(feat && mask && row_map && col_map && out_tok && out_src && out_count && workspace, VDR_EINVAL, "vdr_mask_gather: null pointer");
+  VDR_CHECK_ARG(S > 0 && h > 0 && w > 0 && hm > 0 && wm > 0 && D > 0 && cap >= 0, VDR_EINVAL, "vdr_mask_gather: bad shape");
+  VDR_CHECK_ARG(D % 8 == 0 && ld_feat % 8 == 0 && ld_feat >= D, VDR_EALIGN, "vdr_mask_gather: D (%d) and ld_feat must be multiples of 8", D);
+  VDR_CHECK_ARG(aligned16(feat) && aligned16(out_tok), VDR_EALIGN, "vdr_mask_gather: feat/out_tok must be 16-byte aligned");
+  VDR_CHECK_ARG(feat_dtype == VDR_DTYPE_BF16 || feat_dtype == VDR_DTYPE_F32, VDR_EINVAL, "vdr_mask_gather: bad feat_dtype");
+  VDR_CHECK_ARG((int64_t)S * h * w < 0x7fffffffLL, VDR_EINVAL, "vdr_mask_gather: too many candidates");
+  VDR_CHECK_ARG(workspace_bytes >= vdr_mask_gather_workspace_bytes(S, h, w), VDR_EWORKSPACE, "vdr_mask_gather: workspace too small (%zu < %zu)", workspace_bytes, vdr_mask_gather_workspace_bytes(S, h, w));
+  VDR_CHECK_ARG(pe_scale == 0.0 || (pe_div && coef_host), VDR_EINVAL, "vdr_mask_gather: positional encoding needs pe_div and coef_host");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  G1Geom g{mask, row_map, col_map, S, h, w, hm, wm, (int64_t)S * h * w};
+  const int tiles = (int)((g.total + kTile - 1) / kTile);
+  int32_t* counts = static_cast<int32_t*>(workspace);
+  int32_t* offsets = counts + tiles;
+  G1Pe pe{};
+  pe.scale = pe_scale;
+  pe.div = pe_div;
+  if (pe_scale != 0.0) {
+    pe.w_orig = coef_host[0]; pe.h_orig = coef_host[1];
+    pe.res0 = coef_host[2]; pe.res1 = coef_host[3]; pe.res2 = coef_host[4];
+    pe.noise0 = coef_host[5]; pe.noise1 = coef_host[6]; pe.noise2 = coef_host[7];
+    pe.mean_x = coef_host[8]; pe.mean_y = coef_host[9]; pe.mean_z = coef_host[10];
+  }
+  g1_count_kernel<<<tiles, kGThreads, 0, s>>>(g, counts);
+  VDR_CHECK_LAUNCH("g1_count_kernel");
+  tile_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, tiles, out_count);
+  VDR_CHECK_LAUNCH("tile_scan_kernel");
+  if (feat_dtype == VDR_DTYPE_BF16)
+    g1_scatter_kernel<true><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe);
+  else
+    g1_scatter_kernel<false><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe);
+  count_launch(3);
+  VDR_CHECK_LAUNCH("g1_scatter_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_voxel_bbox(const uint8_t* mask, int H, int W, int S, int32_t* bbox, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(mask && bbox, VDR_EINVAL, "vdr_voxel_bbox: null pointer");
+  VDR_CHECK_ARG(H > 0 && W > 0 && S > 0, VDR_EINVAL, "vdr_voxel_bbox: bad shape");
+  VDR_CHECK_ARG((int64_t)H * W * S < 0x7fffffffLL, VDR_EINVAL, "vdr_voxel_bbox: volume too large for int32 flat indices");
+  VDR_CHECK_ARG(aligned16(mask), VDR_EALIGN, "vdr_voxel_bbox: mask must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)H * W * S;
+  bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
+  int64_t blocks = ((total >> 4) + 1 + 255) / 256;
+  const int64_t capb = (int64_t)num_sms() * 8;
+  if (blocks > capb) blocks = capb;
+  voxel_bbox_kernel<<<(unsigned)blocks, 256, 0, s>>>(mask, H, S, total, bbox);
+  count_launch(2);
+  VDR_CHECK_LAUNCH("voxel_bbox_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_voxel_gather(const float* img, const uint8_t* mask, int H, int W, int S, const int32_t* bbox,
+                                int32_t* out_flat, float* out_raw, uint8_t* out_mask, int32_t* out_count, int cap,
+                                vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(img && mask && bbox && out_flat && out_raw && out_mask && out_count, VDR_EINVAL, "vdr_voxel_gather: null pointer");
+  VDR_CHECK_ARG(H > 0 && W > 0 && S > 0 && cap >= 0, VDR_EINVAL, "vdr_voxel_gather: bad shape");
+  VDR_CHECK_ARG((int64_t)H * W * S < 0x7fffffffLL, VDR_EINVAL, "vdr_voxel_gather: volume too large for int32 flat indices");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int64_t blocks = ((int64_t)cap + 255) / 256;
+  const int64_t capb = (int64_t)num_sms() * 8;
+  if (blocks > capb) blocks = capb;
+  if (blocks < 1) blocks = 1;
+  voxel_gather_kernel<<<(unsigned)blocks, 256, 0, s>>>(img, mask, H, S, bbox, out_flat, out_raw, out_mask, out_count, cap);
+  count_launch();
+  VDR_CHECK_LAUNCH("voxel_gather_kernel");
+  return VDR_OK;
+}

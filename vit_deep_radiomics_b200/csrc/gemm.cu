@@ -1,0 +1,285 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = epi(A[M,K] * W[N,K]^T + bias (+ R)).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM)
+//   warps 2..9  epilogue       (tcgen05.ld -> bias / GELU / residual -> vector stores)
+// Two TMEM accumulator buffers (2*BN columns) let the epilogue of tile i overlap the MMAs of
+// tile i+1.  Replaces the torch.nn.Linear call sites listed in include/vdr.h.
+#include "common.cuh"
+
+namespace vdr {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+
+struct GemmParams {
+  const float* bias;
+  const void* R;
+  void* C;
+  int64_t ldr, ldc;
+  int M, N, K;
+  int epilogue, r_dtype, c_dtype;
+  int out_group, out_group_stride, out_offset;
+  int res_mod, res_offset;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytesA = BM * BK * 2;
+  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
+          tma_load_2d(&tmW, &full_bar[stage], sa + Cfg::kStageBytesA, kb * BK, n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // +32 bytes per K step inside the 128-byte swizzle row  (encoded address units of 16 B)
+            umma_ss(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 2;
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;            // which half of the BN columns
+    constexpr int kColsPerWarp = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      int64_t out_row = m;
+      if (p.out_group > 0) out_row = static_cast<int64_t>(m / p.out_group) * p.out_group_stride + p.out_offset + m % p.out_group;
+      int64_t res_row = out_row;
+      if (p.res_mod > 0) res_row = p.res_offset + m % p.res_mod;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        const int col0 = half * kColsPerWarp + c;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN + col0) + (static_cast<uint32_t>(quarter * 32) << 16);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + col0;
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            if (n < p.N) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              if (p.bias != nullptr) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (p.epilogue == VDR_EPI_BIAS_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+              } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
+                if (p.r_dtype == VDR_DTYPE_BF16) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.R) + res_row * p.ldr + n);
+                  const float2 a0 = unpack_bf16x2(rv.x), a1 = unpack_bf16x2(rv.y), a2 = unpack_bf16x2(rv.z), a3 = unpack_bf16x2(rv.w);
+                  v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
+                  v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+                } else {
+                  const float* rp = static_cast<const float*>(p.R) + res_row * p.ldr + n;
+                  const float4 a0 = *reinterpret_cast<const float4*>(rp);
+                  const float4 a1 = *reinterpret_cast<const float4*>(rp + 4);
+                  v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                  v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                }
+              }
+              if (p.c_dtype == VDR_DTYPE_BF16) {
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n) = o;
+              } else {
+                float* cp = static_cast<float*>(p.C) + out_row * p.ldc + n;
+                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
+    configured = true;
+  }
+  gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, p);
+  count_launch();
+  VDR_CHECK_LAUNCH("gemm_tcgen05_kernel");
+  return VDR_OK;
+}
+
+}  // namespace vdr
+
+extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(a != nullptr, VDR_EINVAL, "vdr_gemm: null args");
+  VDR_CHECK_ARG(a->A && a->W && a->C, VDR_EINVAL, "vdr_gemm: null A/W/C");
+  VDR_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, VDR_EINVAL, "vdr_gemm: non-positive shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  VDR_CHECK_ARG(a->N % 8 == 0, VDR_EINVAL, "vdr_gemm: N (%d) must be a multiple of 8", a->N);
+  VDR_CHECK_ARG(a->lda >= a->K && a->ldw >= a->K && a->ldc >= a->N, VDR_EINVAL, "vdr_gemm: leading dimension smaller than row length");
+  VDR_CHECK_ARG(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldc % 8 == 0, VDR_EALIGN, "vdr_gemm: lda/ldw/ldc must be multiples of 8 elements");
+  VDR_CHECK_ARG(aligned16(a->A) && aligned16(a->W) && aligned16(a->C), VDR_EALIGN, "vdr_gemm: A/W/C must be 16-byte aligned");
+  VDR_CHECK_ARG(a->bias == nullptr || aligned16(a->bias), VDR_EALIGN, "vdr_gemm: bias must be 16-byte aligned");
+  VDR_CHECK_ARG(a->epilogue >= VDR_EPI_BIAS && a->epilogue <= VDR_EPI_BIAS_RESIDUAL, VDR_EINVAL, "vdr_gemm: unknown epilogue %d", a->epilogue);
+  VDR_CHECK_ARG(a->c_dtype == VDR_DTYPE_BF16 || a->c_dtype == VDR_DTYPE_F32, VDR_EINVAL, "vdr_gemm: bad c_dtype %d", a->c_dtype);
+  if (a->epilogue == VDR_EPI_BIAS_RESIDUAL) {
+    VDR_CHECK_ARG(a->R != nullptr, VDR_EINVAL, "vdr_gemm: residual epilogue needs R");
+    VDR_CHECK_ARG(a->r_dtype == VDR_DTYPE_BF16 || a->r_dtype == VDR_DTYPE_F32, VDR_EINVAL, "vdr_gemm: bad r_dtype %d", a->r_dtype);
+    VDR_CHECK_ARG(aligned16(a->R) && a->ldr % 8 == 0 && a->ldr >= a->N, VDR_EALIGN, "vdr_gemm: R must be 16-byte aligned with ldr %% 8 == 0");
+  }
+  VDR_CHECK_ARG(a->out_group >= 0 && a->res_mod >= 0, VDR_EINVAL, "vdr_gemm: negative row-remap parameters");
+
+  const int sms = num_sms();
+  const int m_tiles = (a->M + BM - 1) / BM;
+  auto tiles = [&](int bn) { return m_tiles * ((a->N + bn - 1) / bn); };
+  int bn = 256;
+  if (a->N % 256 != 0 && a->N % 128 == 0) bn = 128;
+  if (bn == 256 && tiles(256) < sms) bn = 128;
+  if (bn == 128 && tiles(128) < sms) bn = 64;
+
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM, BK);
+  if (rc != VDR_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmW, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, (uint32_t)bn, BK);
+  if (rc != VDR_OK) return rc;
+
+  GemmParams p;
+  p.bias = a->bias; p.R = a->R; p.C = a->C; p.ldr = a->ldr; p.ldc = a->ldc;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.epilogue = a->epilogue; p.r_dtype = a->r_dtype; p.c_dtype = a->c_dtype;
+  p.out_group = a->out_group; p.out_group_stride = a->out_group_stride; p.out_offset = a->out_offset;
+  p.res_mod = a->res_mod; p.res_offset = a->res_offset;
+
+  const int total = tiles(bn);
+  const int grid = total < sms ? total : sms;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch_gemm<256>(tmA, tmW, p, grid, s);
+  if (bn == 128) return launch_gemm<128>(tmA, tmW, p, grid, s);
+  return launch_gemm<64>(tmA, tmW, p, grid, s);
+}

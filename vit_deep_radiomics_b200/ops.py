@@ -1,0 +1,241 @@
+"""Tensor-level wrappers over the C ABI (include/vdr.h).  PyTorch is used only for device
+memory and the current CUDA stream; all arithmetic happens in libvdr.so.  No fallbacks."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _C
+
+_DT = {torch.bfloat16: _C.VDR_DTYPE_BF16, torch.float32: _C.VDR_DTYPE_F32}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (libvdr has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, epilogue: str = "bias",
+         residual: torch.Tensor | None = None, out: torch.Tensor | None = None, out_dtype=torch.bfloat16,
+         k: int | None = None, out_rows: int | None = None, out_group=(0, 0, 0), res_mod=(0, 0)) -> torch.Tensor:
+    """out = epi(a @ w.T + bias [+ residual]) on tcgen05.  a (M, K[ld]) bf16, w (N, K[ld]) bf16."""
+    _req(a, torch.bfloat16, "a"), _req(w, torch.bfloat16, "w")
+    if a.dim() != 2 or w.dim() != 2 or a.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("a and w must be 2-D with unit inner stride")
+    M, N = a.shape[0], w.shape[0]
+    K = k if k is not None else a.shape[1]
+    if w.shape[1] < K or a.shape[1] < K:
+        raise ValueError("K larger than the operand rows")
+    epi = {"bias": _C.EPI_BIAS, "gelu": _C.EPI_BIAS_GELU, "residual": _C.EPI_BIAS_RESIDUAL}[epilogue]
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else M, N), dtype=out_dtype, device=a.device)
+    if out.dim() != 2 or out.stride(1) != 1 or out.shape[1] != N:
+        raise ValueError("out must be (rows, N) with unit inner stride")
+    args = _C.GemmArgs()
+    args.A, args.lda = a.data_ptr(), a.stride(0)
+    args.W, args.ldw = w.data_ptr(), w.stride(0)
+    args.bias = _req(bias, torch.float32, "bias").data_ptr() if bias is not None else None
+    if epi == _C.EPI_BIAS_RESIDUAL:
+        if residual is None:
+            raise ValueError("residual epilogue needs `residual`")
+        args.R, args.ldr, args.r_dtype = residual.data_ptr(), residual.stride(0), _DT[residual.dtype]
+    else:
+        args.R, args.ldr, args.r_dtype = None, 0, 0
+    args.C, args.ldc, args.c_dtype = out.data_ptr(), out.stride(0), _DT[out.dtype]
+    args.M, args.N, args.K = M, N, K
+    args.epilogue = epi
+    args.out_group, args.out_group_stride, args.out_offset = out_group
+    args.res_mod, args.res_offset = res_mod
+    _C.check(_C.lib().vdr_gemm(C.byref(args), _stream()), "vdr_gemm")
+    return out
+
+
+def im2col_patches(src: torch.Tensor, strides, B: int, H: int, W: int, patch: int,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+    """A[(b,py,px),(c,iy,ix)] bf16 from an f32 image tensor addressed by element `strides`
+    (batch, channel, row, col); channel stride 0 replicates a gray image (gray2rgb)."""
+    _req(src, torch.float32, "src")
+    gh, gw = H // patch, W // patch
+    K = 3 * patch * patch
+    ldk = (K + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((B * gh * gw, ldk), dtype=torch.bfloat16, device=src.device)
+    sb, sc, sy, sx = (int(s) for s in strides)
+    _C.check(_C.lib().vdr_im2col_patches(src.data_ptr(), sb, sc, sy, sx, B, H, W, patch, out.data_ptr(), _stream()),
+             "vdr_im2col_patches")
+    return out
+
+
+def write_cls_rows(cls: torch.Tensor, pos0: torch.Tensor, x: torch.Tensor, B: int, N: int, d: int) -> None:
+    _req(cls, torch.float32, "cls"), _req(pos0, torch.float32, "pos0"), _req(x, torch.bfloat16, "x")
+    _C.check(_C.lib().vdr_write_cls_rows(cls.data_ptr(), pos0.data_ptr(), x.data_ptr(), B, N, d, _stream()),
+             "vdr_write_cls_rows")
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, out_dtype=torch.bfloat16,
+              out: torch.Tensor | None = None, save_stats: bool = False):
+    _req(x, torch.bfloat16, "x"), _req(gamma, torch.float32, "gamma"), _req(beta, torch.float32, "beta")
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty((rows, d), dtype=out_dtype, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().vdr_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                        out.data_ptr(), out.stride(0), _DT[out.dtype],
+                                        mean.data_ptr() if save_stats else None,
+                                        rstd.data_ptr() if save_stats else None,
+                                        rows, d, float(eps), _stream()), "vdr_layernorm_fwd")
+    return (out, mean, rstd) if save_stats else out
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
+    """Returns dx (bf16); ACCUMULATES into dgamma / dbeta (f32)."""
+    rows, d = x.shape
+    dx = torch.empty((rows, d), dtype=torch.bfloat16, device=x.device)
+    _C.check(_C.lib().vdr_layernorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
+                                        mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dx.stride(0),
+                                        dgamma.data_ptr(), dbeta.data_ptr(), rows, d, _stream()),
+             "vdr_layernorm_bwd")
+    return dx
+
+
+def cls_concat_layernorm(x: torch.Tensor, cls: torch.Tensor, gamma, beta, eps: float, save_stats: bool = False):
+    """Y[0] = LN(cls), Y[1+i] = LN(x[i]); x (n, d) f32 -> Y (n+1, d) bf16."""
+    _req(x, torch.float32, "x"), _req(cls, torch.float32, "cls")
+    n, d = x.shape
+    y = torch.empty((n + 1, d), dtype=torch.bfloat16, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(n + 1, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(n + 1, dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().vdr_cls_concat_layernorm_fwd(x.data_ptr() if n else None, cls.data_ptr(), gamma.data_ptr(),
+                                                   beta.data_ptr(), y.data_ptr(),
+                                                   mean.data_ptr() if save_stats else None,
+                                                   rstd.data_ptr() if save_stats else None,
+                                                   n, d, float(eps), _stream()), "vdr_cls_concat_layernorm_fwd")
+    return (y, mean, rstd) if save_stats else y
+
+
+def flash_attn(qkv: torch.Tensor, B: int, N: int, heads: int, scale: float | None = None,
+               out: torch.Tensor | None = None, return_lse: bool = False):
+    """qkv (B*N, 3*heads*64) bf16 -> out (B*N, heads*64) bf16."""
+    _req(qkv, torch.bfloat16, "qkv")
+    d = heads * 64
+    if qkv.shape != (B * N, 3 * d):
+        raise ValueError(f"qkv must be ({B * N}, {3 * d}), got {tuple(qkv.shape)}")
+    if scale is None:
+        scale = 1.0 / math.sqrt(64)
+    if out is None:
+        out = torch.empty((B * N, d), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if return_lse else None
+    _C.check(_C.lib().vdr_flash_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0),
+                                         lse.data_ptr() if return_lse else None, B, N, heads, float(scale),
+                                         _stream()), "vdr_flash_attn_fwd")
+    return (out, lse) if return_lse else out
+
+
+# ----------------------------------------------------------------------------- gathers
+def nearest_index_map(n_out: int, n_in: int) -> np.ndarray:
+    """Order-0 resize source indices (skimage.transform.resize(order=0) semantics used at
+    reference src/train_models.py:151): floor((o + 0.5) * (n_in / n_out) - 0.5 + 0.5), clipped."""
+    ratio = np.float64(n_in) / np.float64(n_out)
+    o = np.arange(n_out, dtype=np.float64)
+    idx = np.floor((o + 0.5) * ratio - 0.5 + 0.5).astype(np.int64)
+    return np.clip(idx, 0, n_in - 1).astype(np.int32)
+
+
+_PE_DIV_CACHE: dict = {}
+
+
+def _pe_div(D: int, device, scale=10000) -> torch.Tensor:
+    key = (D, str(device), scale)
+    if key not in _PE_DIV_CACHE:
+        div = np.array([scale ** (6 * i / D) for i in range(D // 6)], dtype=np.float64)  # train_models.py:34
+        if div.size == 0:
+            div = np.ones(1)
+        _PE_DIV_CACHE[key] = torch.from_numpy(div).to(device)
+    return _PE_DIV_CACHE[key]
+
+
+def grid_means(h: int, w: int, S: int, h_orig: int, w_orig: int, res) -> tuple:
+    """Means of the reference's physical grid coordinates over ALL h*w*S grid points
+    (src/train_models.py:166-176), reproducing numpy's summation so the result is bit-identical."""
+    n = np.arange(h * w * S, dtype=np.int64)
+    x = ((n // S) % h / w) * w_orig * res[0]
+    y = ((n // (h * S)) / h) * h_orig * res[1]
+    z = (n % S) * res[2]
+    return float(x.mean()), float(y.mean()), float(z.mean())
+
+
+def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = None, pe: dict | None = None):
+    """G1.  feat (S, h, w, D) bf16/f32 CUDA; mask_u8 (S, hm, wm) uint8 CUDA.
+    Returns (tokens (cap, D) f32, src (cap, 3) int32, count int32[1]) -- all on device; rows >= count
+    are unspecified.  `pe` = dict(res=(3,), noise=(3,), scale=0.25) adds the 3-D positional encoding."""
+    if feat.dim() != 4 or mask_u8.dim() != 3:
+        raise ValueError("feat must be (S,h,w,D) and mask (S,hm,wm)")
+    _req(mask_u8, torch.uint8, "mask")
+    if feat.dtype not in _DT:
+        raise ValueError("feat must be bf16 or f32")
+    if not feat.is_contiguous() or not mask_u8.is_contiguous():
+        raise ValueError("feat and mask must be contiguous")
+    S, h, w, D = feat.shape
+    _, hm, wm = mask_u8.shape
+    dev = feat.device
+    row_map = torch.from_numpy(nearest_index_map(h, hm)).to(dev)
+    col_map = torch.from_numpy(nearest_index_map(w, wm)).to(dev)
+    if cap is None:
+        cap = S * h * w
+    tokens = torch.empty((cap, D), dtype=torch.float32, device=dev)
+    src = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = _C.lib().vdr_mask_gather_workspace_bytes(S, h, w)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    pe_scale, pe_div_ptr, coef = 0.0, None, None
+    if pe is not None:
+        res, noise = [float(v) for v in pe["res"]], [float(v) for v in pe.get("noise", (0, 0, 0))]
+        mx, my, mz = grid_means(h, w, S, hm, wm, res)
+        coef = (C.c_double * 11)(float(wm), float(hm), res[0], res[1], res[2], noise[0], noise[1], noise[2], mx, my, mz)
+        pe_scale = float(pe.get("scale", 0.25))
+        pe_div_ptr = _pe_div(D, dev).data_ptr()
+    _C.check(_C.lib().vdr_mask_gather(feat.data_ptr(), _DT[feat.dtype], D, mask_u8.data_ptr(), hm, wm,
+                                      row_map.data_ptr(), col_map.data_ptr(), S, h, w, D,
+                                      tokens.data_ptr(), src.data_ptr(), count.data_ptr(), cap,
+                                      pe_scale, pe_div_ptr, coef, ws.data_ptr(), ws_bytes, _stream()),
+             "vdr_mask_gather")
+    return tokens, src, count
+
+
+def voxel_bbox(mask_u8: torch.Tensor) -> torch.Tensor:
+    """G2 pass 1: index-space bounding box (xi_min, xi_max, yi_min, yi_max, zi_min, zi_max) int32[6]."""
+    _req(mask_u8, torch.uint8, "mask")
+    H, W, S = mask_u8.shape
+    bbox = torch.empty(6, dtype=torch.int32, device=mask_u8.device)
+    _C.check(_C.lib().vdr_voxel_bbox(mask_u8.data_ptr(), H, W, S, bbox.data_ptr(), _stream()), "vdr_voxel_bbox")
+    return bbox
+
+
+def voxel_gather(img: torch.Tensor, mask_u8: torch.Tensor, bbox: torch.Tensor, cap: int):
+    """G2 pass 2: (flat int32, raw f32, mask u8, count int32[1]) of the voxels inside bbox."""
+    _req(img, torch.float32, "img"), _req(mask_u8, torch.uint8, "mask")
+    H, W, S = img.shape
+    dev = img.device
+    flat = torch.empty(cap, dtype=torch.int32, device=dev)
+    raw = torch.empty(cap, dtype=torch.float32, device=dev)
+    mk = torch.empty(cap, dtype=torch.uint8, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    _C.check(_C.lib().vdr_voxel_gather(img.data_ptr(), mask_u8.data_ptr(), H, W, S, bbox.data_ptr(),
+                                       flat.data_ptr(), raw.data_ptr(), mk.data_ptr(), count.data_ptr(), cap,
+                                       _stream()), "vdr_voxel_gather")
+    return flat, raw, mk, count
