@@ -129,10 +129,14 @@ int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_ou
  * (h,w,S) flatten order (:159-163), boolean row gather (:180) and, optionally, the 3-D
  * sinusoidal positional encoding added as PE/4 (:30-44,178-180; computed in f64).
  *
- *   feat      (S, h, w, D) descriptors, slice-major as the backbone writes them (bf16 or f32),
- *             row stride ld_feat elements between consecutive (s,a,b) tokens
- *   mask      (S, hm, wm) u8 pixel masks; row_map[h], col_map[w] (int32) give the source pixel
- *             row/col of each feature-grid row/col (the order-0 resize index maps)
+ *   feat      descriptors, slice-major as the backbone writes them (bf16 or f32): token (k,a,b) is
+ *             row  k*feat_slice_rows + feat_row0 + a*feat_row_pitch + b  of a matrix with ld_feat
+ *             elements per row -- a dense (S,h,w,D) tensor is (h*w, w, 0); the ROI (r0:,c0:) of the
+ *             backbone's token matrix (CLS first, grid gh x gw) is (gh*gw+1, gw, 1+r0*gw+c0),
+ *             which is extract_roi (visualization_utils.py:115-125) without a copy
+ *   mask      u8 pixel masks: value (k,r,c) at mask[k*mask_slice_stride + r*mask_row_stride + c];
+ *             row_map[h], col_map[w] (int32) give the source pixel row/col of each feature-grid
+ *             row/col (the order-0 resize index maps of :151)
  *   out_tok   (cap, D) f32 packed tokens in ascending n = a*(w*S) + b*S + k   (stable)
  *   out_src   (cap, 3) int32 (slice k, row a, col b) per token
  *   out_count int32[1] number selected (may exceed cap: rows beyond cap are not written)
@@ -144,8 +148,10 @@ int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_ou
  *   workspace >= vdr_mask_gather_workspace_bytes(S,h,w)
  */
 size_t vdr_mask_gather_workspace_bytes(int S, int h, int w);
-int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat,
-                    const uint8_t* mask, int hm, int wm, const int32_t* row_map, const int32_t* col_map,
+int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
+                    int64_t feat_row_pitch, int64_t feat_row0,
+                    const uint8_t* mask, int64_t mask_slice_stride, int64_t mask_row_stride,
+                    const int32_t* row_map, const int32_t* col_map,
                     int S, int h, int w, int D,
                     float* out_tok, int32_t* out_src, int32_t* out_count, int cap,
                     double pe_scale, const double* pe_div, const double* coef_host,

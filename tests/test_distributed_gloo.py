@@ -1,0 +1,68 @@
+"""The N>1 host logic on CPU: world_size-2 gloo processes (all_gather_table, allreduce_grads, sharding)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vit_deep_radiomics_b200.distributed import all_gather_table, allreduce_grads, shard_modulo, shard_range
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    keys = torch.stack([torch.arange(40) // 10, torch.randperm(40, generator=g) % 7, torch.arange(40) % 5], 1).int()
+    rows = torch.randn(40, 6, generator=g)
+    mine = shard_modulo(40, rank, world)
+    k, r = all_gather_table(keys[mine], rows[mine])
+    # canonical order == single-process sort of the full table
+    order = torch.arange(40)
+    for col in (2, 1, 0):
+        order = order[torch.sort(keys[order, col], stable=True).indices]
+    ok_table = torch.equal(k, keys[order]) and torch.equal(r, rows[order])
+    # contiguous slice sharding: rank-order concatenation already sorted
+    lo, hi = shard_range(40, rank, world)
+    k2, r2 = all_gather_table(keys[lo:hi], rows[lo:hi], sort=False)
+    ok_contig = torch.equal(k2, keys) and torch.equal(r2, rows)
+    # gradient all-reduce == accumulation over all samples on one process
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Linear(4, 2))
+    data = torch.randn(8, 6, generator=g)
+    for i in range(rank, 8, world):
+        (model(data[i]).sum() / 8).backward()
+    allreduce_grads(model)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Linear(4, 2))
+    ref.load_state_dict(model.state_dict())
+    for i in range(8):
+        (ref(data[i]).sum() / 8).backward()
+    ok_grad = all(torch.allclose(a.grad, b.grad, atol=1e-6) for a, b in zip(model.parameters(), ref.parameters()))
+    out[rank] = (ok_table, ok_contig, ok_grad)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        assert out[rank] == (True, True, True), (rank, out[rank])
+
+
+def test_shards_partition():
+    for n in (1, 7, 120, 1000):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert sorted(sum((shard_modulo(n, r, w) for r in range(w)), [])) == list(range(n))

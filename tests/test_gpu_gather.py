@@ -1,0 +1,96 @@
+"""-m gpu: the mask gathers through the C ABI -- bit-exact against the golden vectors frozen from the
+reference and against the NumPy oracle on seeded inputs, incl. empty / full / ragged cases."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+CASES = ["square", "ragged", "wide", "probe", "empty", "full", "single"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_g1_golden(cuda, golden_dir, name):
+    from oracle import gather_np as G
+    from vit_deep_radiomics_b200 import ops
+    g = np.load(os.path.join(golden_dir, "gather_g1.npz"))
+    feats, masks = g[f"{name}__features"], g[f"{name}__masks"]
+    res, noise = g[f"{name}__res"], g[f"{name}__noise"]
+    want = g[f"{name}__out_transformer"]                       # reference output (float64)
+    f_t, m_t = torch.from_numpy(feats).to(cuda), torch.from_numpy(masks.astype(np.uint8)).to(cuda)
+    tok, src, cnt = ops.mask_gather(f_t, m_t, pe=dict(res=res, noise=noise))
+    n = int(cnt.item())
+    assert n == want.shape[0]
+    o = G.token_gather(list(feats), list(masks), res, noise)
+    assert np.array_equal(src[:n].cpu().numpy(), o["src"])     # integer contract: bit-exact
+    raw, _, _ = ops.mask_gather(f_t, m_t)
+    assert np.array_equal(raw[:n].cpu().numpy(), o["raw"])     # gathered payload: bit-exact
+    # tokens + PE/4: reference casts its float64 result to float32 (train_models.py:120); the device
+    # computes the PE in fp64 with CUDA's sin/cos (<= 1 ulp f64) -> identical after the f32 cast up to 1 ulp f32
+    got = tok[:n].cpu().numpy()
+    assert np.allclose(got, want.astype(np.float32), rtol=0, atol=2.5e-7 * max(1.0, np.abs(want).max()) if n else 0)
+
+
+def test_g1_roi_and_token_matrix_layout(cuda):
+    """Gather straight out of a CLS-first token matrix with an ROI window == extract_roi + _get_features."""
+    from oracle import gather_np as G
+    from vit_deep_radiomics_b200 import ops
+    rng = np.random.default_rng(8)
+    S, gh, gw, D, HM, WM = 6, 8, 8, 64, 128, 128
+    tok = rng.standard_normal((S, gh * gw + 1, D)).astype(np.float32)
+    mask = rng.random((S, HM, WM)) < 0.2
+    fr, mr = (2, 7, 1, 6), (30, 110, 17, 99)
+    feats = [tok[s, 1:].reshape(gh, gw, D)[fr[0]:fr[1], fr[2]:fr[3]] for s in range(S)]
+    masks = [mask[s, mr[0]:mr[1], mr[2]:mr[3]] for s in range(S)]
+    res = (0.8, 0.8, 0.8)
+    o = G.token_gather(feats, masks, res)
+    t, src, cnt = ops.mask_gather(torch.from_numpy(tok.reshape(-1, D)).to(cuda), torch.from_numpy(mask.astype(np.uint8)).to(cuda),
+                                  grid=(S, gh, gw, gh * gw + 1, 1), feat_roi=fr, mask_roi=mr, pe=dict(res=res))
+    n = int(cnt.item())
+    assert n == o["flat"].size and np.array_equal(src[:n].cpu().numpy(), o["src"])
+    assert np.allclose(t[:n].cpu().numpy(), o["tokens"].astype(np.float32), rtol=0, atol=1e-6)
+
+
+def test_g1_cap_and_bf16(cuda):
+    from vit_deep_radiomics_b200 import ops
+    rng = np.random.default_rng(9)
+    feats = torch.from_numpy(rng.standard_normal((4, 10, 10, 32)).astype(np.float32)).to(cuda)
+    mask = torch.from_numpy((rng.random((4, 40, 40)) < 0.5).astype(np.uint8)).to(cuda)
+    full, src, cnt = ops.mask_gather(feats, mask)
+    n = int(cnt.item())
+    small, src2, cnt2 = ops.mask_gather(feats, mask, cap=7)     # count still reports the true total
+    assert int(cnt2.item()) == n and torch.equal(small[:7], full[:7]) and torch.equal(src2[:7], src[:7])
+    b16, _, _ = ops.mask_gather(feats.bfloat16(), mask)
+    assert torch.equal(b16[:n], full[:n].bfloat16().float())
+
+
+@pytest.mark.parametrize("name", ["sq", "rect", "edge", "empty"])
+def test_g2_golden(cuda, golden_dir, name):
+    from vit_deep_radiomics_b200 import create_pointcloud_dataframe as pcd
+    g = np.load(os.path.join(golden_dir, "pointcloud_g2.npz"))
+    img, mask, res = g[f"{name}__img"], g[f"{name}__mask"], g[f"{name}__res"]
+    df = pcd.to_pointcloud_df(img, mask, 1, res)
+    for col in ("x", "y", "z", "raw", "mask", "mask_box"):
+        assert np.array_equal(df[col].values, g[f"{name}__{col}"]), col
+    box = pcd.pointcloud_box(img, mask, res, centre=False)
+    keep = g[f"{name}__mask_box"]
+    for col in ("x", "y", "z", "raw", "mask"):
+        assert np.array_equal(box[col].values, g[f"{name}__{col}"][keep]), col
+
+
+def test_g2_full_size_properties(cuda):
+    """512x512x120 (BASELINE config C2): count = box volume, ascending flat order, payload == fancy index."""
+    from vit_deep_radiomics_b200 import ops, synth
+    img, mask, res, _ = synth.make_case("C2")
+    i_t, m_t = torch.from_numpy(img).to(cuda), torch.from_numpy(mask.view(np.uint8)).to(cuda)
+    bb = ops.voxel_bbox(m_t).cpu().numpy()
+    rows, cols, sl = np.nonzero(mask.any(2).any(1))[0], np.nonzero(mask.any(2).any(0))[0], np.nonzero(mask.any(0).any(0))[0]
+    assert bb.tolist() == [cols[0], cols[-1], rows[0], rows[-1], sl[0], sl[-1]]       # H == W: xi = col, yi = row
+    cap = int((bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1) * (bb[5] - bb[4] + 1))
+    flat, raw, mk, cnt = ops.voxel_gather(i_t, m_t, ops.voxel_bbox(m_t), cap)
+    assert int(cnt.item()) == cap
+    flat = flat.cpu().numpy().astype(np.int64)
+    assert np.all(np.diff(flat) > 0)
+    assert np.array_equal(raw.cpu().numpy(), img.reshape(-1)[flat]) and np.array_equal(mk.cpu().numpy().astype(bool), mask.reshape(-1)[flat])
+    assert int(mk.sum().item()) == int(mask.sum())                                     # every in-mask voxel is inside the box

@@ -1,0 +1,128 @@
+"""-m gpu: each CUDA kernel (through the C ABI) against a plain PyTorch fp32 reference of the same op.
+Tolerances are for bf16 operands / bf16 outputs with fp32 accumulation (bf16 eps = 2^-8 = 3.9e-3)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, rel_to_peak):
+    got, ref = got.double().cpu(), ref.double().cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= rel_to_peak * max(ref.abs().max().item(), 1e-6), f"max abs err {err} vs peak {ref.abs().max().item()}"
+
+
+@pytest.mark.parametrize("M,N,K,epi,cdt", [
+    (128, 256, 64, "bias", torch.float32), (300, 384, 200, "gelu", torch.bfloat16),
+    (1025, 768, 768, "residual", torch.bfloat16), (4100, 2304, 768, "bias", torch.bfloat16),
+    (1, 512, 256, "gelu", torch.bfloat16), (130, 8, 72, "bias", torch.float32),
+    (1576, 1152, 384, "bias", torch.bfloat16), (257, 1024, 592, "residual", torch.float32),
+    (2050, 768, 3072, "residual", torch.bfloat16)])
+def test_gemm(cuda, M, N, K, epi, cdt):
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=cuda) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=cuda) * 0.05).bfloat16()
+    b = torch.randn(N, device=cuda) * 0.1
+    r = torch.randn(M, N, device=cuda).to(cdt) if epi == "residual" else None
+    ref = a.float() @ w.float().t() + b
+    if epi == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    if epi == "residual":
+        ref = ref + r.float()
+    out = ops.gemm(a, w, b, epilogue=epi, residual=r, out_dtype=cdt)
+    _close(out, ref, 1e-5 if cdt == torch.float32 else 5e-3)
+
+
+def test_gemm_k_tail_and_row_remap(cuda):
+    """K = 588 (14x14 patches) inside ld 592, rows written behind a CLS row, pos-embed as residual."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(0)
+    B, Np, d, K, ld = 3, 256, 1024, 588, 592
+    a = torch.zeros(B * Np, ld, device=cuda, dtype=torch.bfloat16)
+    a[:, :K] = (torch.randn(B * Np, K, device=cuda) * 0.5).bfloat16()
+    a[:, K:] = 7.0                                              # garbage in the padding must be ignored
+    w = torch.zeros(d, ld, device=cuda, dtype=torch.bfloat16)
+    w[:, :K] = (torch.randn(d, K, device=cuda) * 0.05).bfloat16()
+    w[:, K:] = -3.0
+    bias, pos = torch.randn(d, device=cuda) * 0.1, torch.randn(Np + 1, d, device=cuda)
+    out = torch.zeros(B * (Np + 1), d, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, epilogue="residual", residual=pos, out=out, k=K, out_group=(Np, Np + 1, 1), res_mod=(Np, 1))
+    ref = (a[:, :K].float() @ w[:, :K].float().t() + bias).reshape(B, Np, d) + pos[1:]
+    o3 = out.reshape(B, Np + 1, d)
+    _close(o3[:, 1:], ref, 5e-3)
+    assert (o3[:, 0] == 0).all()
+
+
+def test_gemm_argument_errors(cuda):
+    from vit_deep_radiomics_b200 import ops
+    a = torch.zeros(16, 64, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.gemm(a, torch.zeros(12, 64, device=cuda, dtype=torch.bfloat16))          # N % 8 != 0
+    with pytest.raises(ValueError):
+        ops.gemm(a[:, 1:], torch.zeros(16, 63, device=cuda, dtype=torch.bfloat16))   # misaligned / ld % 8
+
+
+@pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (2, 197, 6), (1, 1025, 2), (3, 300, 4), (1, 7, 1), (2, 257, 16)])
+def test_flash_attention(cuda, B, N, heads):
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(B * 1000 + N)
+    d = heads * 64
+    qkv = torch.randn(B * N, 3 * d, device=cuda).bfloat16()
+    q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / math.sqrt(64)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, d)
+    out, lse = ops.flash_attn(qkv, B, N, heads, return_lse=True)
+    _close(out, ref, 8e-3)
+    _close(lse, torch.logsumexp(s, -1), 5e-4)
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 256), (1025, 768), (333, 384), (77, 1024), (50, 2048), (3, 8)])
+def test_layernorm_fwd_bwd(cuda, rows, d):
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(rows + d)
+    x = (torch.randn(rows, d, device=cuda) * 2 + 0.5).bfloat16()
+    g, b = torch.randn(d, device=cuda), torch.randn(d, device=cuda)
+    ref = torch.nn.functional.layer_norm(x.float(), (d,), g, b, 1e-6)
+    _close(ops.layernorm(x, g, b, 1e-6, out_dtype=torch.float32), ref, 1e-6)
+    y, mu, rs = ops.layernorm(x, g, b, 1e-6, save_stats=True)
+    _close(y, ref, 5e-3)
+    _close(mu, x.float().mean(1), 1e-5)
+    if d <= 1024:
+        dy = torch.randn(rows, d, device=cuda).bfloat16()
+        xr, gr, br = x.float().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-6).backward(dy.float())
+        dg, db = torch.zeros(d, device=cuda), torch.zeros(d, device=cuda)
+        dx = ops.layernorm_bwd(dy, x, g, mu, rs, dg, db)
+        _close(dx, xr.grad, 5e-3)
+        _close(dg, gr.grad, 1e-4)
+        _close(db, br.grad, 1e-4)
+
+
+def test_cls_concat_layernorm(cuda):
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(1)
+    for n, d in [(777, 256), (0, 256), (5, 768)]:
+        x, cls = torch.randn(n, d, device=cuda), torch.randn(d, device=cuda)
+        g, b = torch.randn(d, device=cuda), torch.randn(d, device=cuda)
+        ref = torch.nn.functional.layer_norm(torch.cat([cls[None], x]), (d,), g, b, 1e-5)
+        _close(ops.cls_concat_layernorm(x, cls, g, b, 1e-5), ref, 5e-3)
+
+
+def test_im2col_bit_exact(cuda):
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(5)
+    for (B, H, W, p, gray) in [(2, 64, 64, 16, True), (2, 56, 42, 14, False), (3, 224, 224, 16, True)]:
+        if gray:   # (H, W, S) volume layout as np.dstack gives; gray2rgb by channel stride 0
+            vol = torch.randn(H, W, B, device=cuda)
+            img = vol.permute(2, 0, 1)[:, None].expand(B, 3, H, W)
+            A = ops.im2col_patches(vol, (1, 0, W * B, B), B, H, W, p)
+        else:
+            img = torch.randn(B, 3, H, W, device=cuda)
+            A = ops.im2col_patches(img, img.stride(), B, H, W, p)
+        ref = torch.nn.functional.unfold(img.contiguous(), kernel_size=p, stride=p).transpose(1, 2).reshape(-1, 3 * p * p)
+        K = 3 * p * p
+        assert torch.equal(A[:, :K].float(), ref.bfloat16().float()) and (A[:, K:] == 0).all()

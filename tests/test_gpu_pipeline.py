@@ -1,0 +1,149 @@
+"""-m gpu: the assembled hot path against the oracle.
+Floating-point tolerances (bf16 activations / fp32 accumulation vs the fp32 oracle), as BASELINE.json's
+north_star asks: per-descriptor max-abs and relative error, token cosine >= 0.999; gather indices bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# |descriptor error| <= ABS_TOL (final-LayerNorm outputs are O(1)), rms relative error <= REL_TOL, cosine >= COS
+ABS_TOL, REL_TOL, COS = 0.12, 0.02, 0.999
+
+
+def _oracle_dense(model, imgs_nchw):
+    from oracle import vit_fp32
+    with torch.no_grad():
+        return vit_fp32.vit_forward(model.state_dict_f32, vit_fp32.VIT_CONFIGS[model.model_name], imgs_nchw).numpy()
+
+
+def _check_descriptors(got, want):
+    got, want = got.astype(np.float64), want.astype(np.float64)
+    err = np.abs(got - want).max()
+    rel = np.sqrt(((got - want) ** 2).sum() / (want ** 2).sum())
+    g2, w2 = got.reshape(-1, got.shape[-1]), want.reshape(-1, want.shape[-1])
+    cos = (g2 * w2).sum(1) / (np.linalg.norm(g2, axis=1) * np.linalg.norm(w2, axis=1))
+    assert err <= ABS_TOL and rel <= REL_TOL and cos.min() >= COS, (err, rel, cos.min())
+
+
+@pytest.mark.parametrize("name,hw,B", [("vit_t16", (64, 64), 3), ("vit_t16", (48, 80), 2), ("vit_s16", (224, 224), 8)])
+def test_vit_dense_descriptors_vs_oracle(cuda, name, hw, B):
+    """C1 (ViT-S/16, 224^2, batch 8) and tiny / non-square variants."""
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    torch.manual_seed(0)
+    model = tdd.load_model(name, img_hw=hw, device=cuda, seed=11)
+    x = torch.rand(B, 3, *hw)
+    got = model.dense_descriptors(x.to(cuda)).cpu().numpy()
+    want = _oracle_dense(model, x)
+    assert got.shape == want.shape == (B, hw[0] // 16, hw[1] // 16, model.cfg["dim"])
+    _check_descriptors(got, want)
+
+
+def test_vit_l14_patch14_k_tail(cuda):
+    """ViT-L/14 geometry (K = 588 not a multiple of 64, 24 layers) at a small image: 56x56 -> 4x4 patches."""
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    model = tdd.load_model("vit_l14", img_hw=(56, 56), device=cuda, seed=5)
+    x = torch.rand(2, 3, 56, 56)
+    _check_descriptors(model.dense_descriptors(x.to(cuda)).cpu().numpy(), _oracle_dense(model, x))
+
+
+def test_get_dense_descriptor_single_slice_api(cuda):
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    model = tdd.load_model("vit_t16", img_hw=(64, 64), device=cuda, seed=2)
+    img = np.random.default_rng(0).random((64, 64)).astype(np.float32)       # gray slice in 0..1
+    f = tdd.get_dense_descriptor(model, img)
+    assert f.shape == (4, 4, 128) and f.dtype == np.float32
+    want = _oracle_dense(model, torch.from_numpy(np.stack([img] * 3))[None])
+    _check_descriptors(f[None], want)
+
+
+@pytest.mark.parametrize("case", ["T0", "C1"])
+def test_extract_point_cloud_vs_oracle(cuda, case):
+    """Fused extraction + gather == oracle generate_features + _get_features on the oracle's fp32 descriptors:
+    identical token set / order / coordinates (bit-exact), descriptors within tolerance."""
+    from oracle import gather_np as G
+    from vit_deep_radiomics_b200 import synth, tfds_dense_descriptor as tdd
+    img, mask, res, name = synth.make_case(case)
+    H, W, S = img.shape
+    model = tdd.load_model(name, img_hw=(H, W), device=cuda, seed=7)
+    noise = (1.5, -2.0, 0.25)
+    out = tdd.extract_point_cloud(model, img, mask, res, noise=noise)
+
+    def oracle_descriptor(img2d):
+        return _oracle_dense(model, torch.from_numpy(np.stack([img2d] * 3))[None].float())[0]
+
+    feats, masks = G.generate_features(oracle_descriptor, img, mask)
+    ref = G.token_gather(feats, masks, res, noise)
+    assert out["count"] == ref["flat"].size > 0
+    assert np.array_equal(out["src"].numpy(), ref["src"])
+    _check_descriptors(out["tokens"].numpy()[None], ref["tokens"][None])
+    # generate_features API: same shapes / masks as the oracle's, descriptors within tolerance
+    fl, ml = tdd.generate_features(model, img, mask)
+    assert len(fl) == len(feats) == S
+    assert all(a.shape == b.shape for a, b in zip(fl, feats)) and all(np.array_equal(a, b) for a, b in zip(ml, masks))
+    _check_descriptors(np.stack(fl), np.stack(feats))
+    # gathering the device descriptors with the oracle gives the device tokens bit-for-bit (PE aside): the
+    # gather itself adds no error
+    ref2 = G.token_gather(fl, ml, res, noise)
+    assert np.allclose(out["tokens"].numpy(), ref2["tokens"].astype(np.float32), rtol=0, atol=1e-6)
+
+
+def test_c2_full_size_properties(cuda):
+    """BASELINE config C2 (ViT-B/16, 512x512x120): size-independent properties of the gather at full size."""
+    from vit_deep_radiomics_b200 import ops, synth, tfds_dense_descriptor as tdd
+    img, mask, res, name = synth.make_case("C2")
+    H, W, S = img.shape
+    model = tdd.load_model(name, img_hw=(H, W), device=cuda, seed=1234)
+    out = tdd.extract_point_cloud(model, img, mask, res, add_pe=False, to_host=False)
+    n = int(out["count"].item())
+    src = out["src"][:n].cpu().numpy().astype(np.int64)
+    fy0, fy1, fx0, fx1 = out["plan"]["feat_roi"]
+    my0, my1, mx0, mx1 = out["plan"]["mask_roi"]
+    h, w = fy1 - fy0, fx1 - fx0
+    # expected selection from the host mask with the oracle-validated index maps
+    rm, cm = ops.nearest_index_map(h, my1 - my0), ops.nearest_index_map(w, mx1 - mx0)
+    sel = mask[my0:my1, mx0:mx1][np.ix_(rm, cm)]                    # (h, w, S)
+    assert n == int(sel.sum()) and 3000 < n < 8000
+    flat = src[:, 1] * (w * S) + src[:, 2] * S + src[:, 0]
+    assert np.all(np.diff(flat) > 0)                                 # stable, ascending reference order
+    assert sel.reshape(-1)[flat].all()
+    # payload: gathered rows are exactly the rows of the final token matrix
+    tok = model._ws[S]["OUT"].view(S, model.n_tokens, -1)
+    rows = tok[torch.from_numpy(src[:, 0]).to(cuda), torch.from_numpy(1 + (src[:, 1] + fy0) * model.grid[1] + src[:, 2] + fx0).to(cuda)]
+    assert torch.equal(out["tokens"][:n], rows)
+    assert torch.isfinite(out["tokens"][:n]).all()
+
+
+def test_classifier_forward_vs_golden(cuda, golden_dir):
+    """Point-cloud classifier forward (kernels) against the reference's own outputs (golden) -- bf16 tolerance."""
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier
+    g = np.load(os.path.join(golden_dir, "classifier_small.npz"))
+    d, ff, heads, layers = g["cfg"].tolist()
+    model = TransformerNoduleClassifier(d, ff, heads, 2, layers)
+    model.load_state_dict({k[len("param__"):]: torch.tensor(g[k]) for k in g.files if k.startswith("param__")})
+    model = model.to(cuda).eval()
+    with torch.no_grad():
+        logits, cls = model(torch.tensor(g["x"]).to(cuda))
+    assert logits.shape == (1, 2) and cls.shape == (1, d)
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < 0.03
+    c, w = cls.cpu().numpy()[0].astype(np.float64), g["cls"][0].astype(np.float64)
+    assert (c * w).sum() / (np.linalg.norm(c) * np.linalg.norm(w)) > 0.999
+    assert np.abs(c - w).max() < 0.06
+
+
+def test_classifier_full_config_vs_oracle(cuda):
+    """Reference hyper-parameters (d 256, ff 1024, 4 heads, 2 layers) on a 2,000-token cloud vs the fp32 oracle."""
+    from oracle import classifier_fp32 as C
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier
+    sd = C.init_state_dict(256, 1024, 2, 2, seed=4)
+    model = TransformerNoduleClassifier(256, 1024, 4, 2, 2)
+    model.load_state_dict(sd)
+    model = model.to(cuda).eval()
+    x = torch.randn(1, 2000, 256, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        logits, cls = model(x.to(cuda))
+        want_l, want_c = C.classifier_forward(sd, x, 4, 2)
+    assert (logits.cpu() - want_l).abs().max() < 0.05
+    assert torch.nn.functional.cosine_similarity(cls.cpu(), want_c).item() > 0.999

@@ -1,0 +1,130 @@
+"""Host-side mirror of the reference interface: geometry, config, synthetic data, PE, loss (CPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import gather_np as G
+from vit_deep_radiomics_b200 import config_manager, ops, synth
+from vit_deep_radiomics_b200 import train_models as tm
+from vit_deep_radiomics_b200 import visualization_utils as vu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_geometry_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "geometry.npz"))
+    for i, m in enumerate(g["geo__masks"]):
+        assert list(vu.extract_coords(m, 1)) == g["geo__coords_m1"][i].tolist()
+        assert list(vu.extract_coords(m, 2)) == g["geo__coords_m2"][i].tolist()
+        img = np.zeros((m.shape[0] // 4, m.shape[1] // 4, 3))
+        got = list(vu.extract_roi(img, m).shape[:2]) + list(vu.extract_roi(m, m).shape[:2])
+        assert got == g["geo__roi_shapes"][i].tolist()
+    assert vu.crop_window(g["gen__mask"]) == G.crop_window(g["gen__mask"])
+    with pytest.raises(ValueError):
+        vu.extract_coords(np.zeros((4, 4), bool), 1)
+
+
+def test_survey_probe_values():
+    # rows 5..8, cols 10..15, margin 2 -> (12, 3, 17, 6)
+    m = np.zeros((20, 20), bool)
+    m[5:9, 10:16] = True
+    assert vu.extract_coords(m, 2) == (12, 3, 17, 6)
+    assert vu.crop_image(np.zeros((10, 12)), -3, 2, 40, 7).shape == (5, 12)
+
+
+def test_config_manager_reads_reference_schema():
+    cfg = config_manager.load_conf(project_dir=ROOT)
+    t = cfg["models"]["transformer"]
+    assert (t["learning_rate"], t["feature_dim"], t["batch_size"], t["virtual_batch_size"], t["num_epochs"], t["patience"]) == \
+        (0.0005, 256, 1, 32, 50, 15)
+    for mod in ("ct", "pet", "chest"):
+        assert t[mod] == {"num_layers": 2, "num_heads": 4, "mlp_ratio": 4}
+    assert config_manager.get_project_dir(os.path.join(ROOT, "tests")) == ROOT
+    ref = "/root/reference/conf/parameters_models.yaml"
+    if os.path.isfile(ref):
+        assert cfg["models"] == yaml.safe_load(open(ref))["models"]
+
+
+def test_kfold_schema_and_split(tmp_path):
+    ids, labels, sizes, cloud = synth.point_cloud_patients(50, d=64, n_range=(8, 16))
+    kf = synth.kfold_yaml_dict(ids, labels)
+    folds = kf["kfold_patients"]["ct"]["stanford"]
+    assert sorted(folds) == [0, 1, 2, 3, 4]                       # int fold keys like the reference file
+    alltest = sorted(sum((folds[k]["test"] for k in folds), []))
+    assert alltest == sorted(ids)
+    for k in folds:
+        assert not set(folds[k]["train"]) & set(folds[k]["test"])
+    (tmp_path / "conf").mkdir()
+    (tmp_path / "conf" / "parameters_kfold.yaml").write_text(yaml.safe_dump(kf))
+    (tmp_path / "conf" / "parameters_models.yaml").write_text(open(os.path.join(ROOT, "conf", "parameters_models.yaml")).read())
+    cfg = config_manager.load_conf(project_dir=tmp_path)
+    assert cfg["kfold_patients"]["ct"]["stanford"][0]["test"] == folds[0]["test"] and "models" in cfg
+    assert cloud(3).shape == (sizes[3], 64) and np.array_equal(cloud(3), cloud(3))
+
+
+def test_positional_encoding_and_maps(golden_dir):
+    g = np.load(os.path.join(golden_dir, "geometry.npz"))
+    x, y, z = g["pe__xyz"]
+    for D in (12, 256, 384):
+        assert np.array_equal(tm.positional_encoding_3d(x, y, z, D), g[f"pe__{D}"])
+    for n_in in range(1, 30):
+        for n_out in range(1, 30):
+            assert np.array_equal(ops.nearest_index_map(n_out, n_in), G.nearest_index_map(n_out, n_in))
+    # grid means reproduce the reference's x.mean() exactly (same array, same numpy reduction)
+    h, w, S, hm, wm, res = 7, 5, 3, 30, 22, (0.8, 0.7, 1.25)
+    n = np.arange(h * w * S)
+    xr = ((n // S) % h / w) * wm * res[0]
+    assert ops.grid_means(h, w, S, hm, wm, res)[0] == xr.mean()
+
+
+def test_focal_loss_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "classifier_small.npz"))
+    lg, tg = torch.tensor(g["focal__logits"]), torch.tensor(g["focal__targets"])
+    crit = tm.FocalLoss(alpha=torch.tensor([0.25, 0.75]), gamma=2)
+    assert abs(crit(lg, tg).item() - float(g["focal__loss_alpha"])) < 1e-6
+    assert abs(tm.FocalLoss(gamma=2)(lg, tg).item() - float(g["focal__loss_noalpha"])) < 1e-6
+    assert np.allclose([crit(lg[i], tg[i]).item() for i in range(6)], g["focal__loss_single"], atol=1e-6)
+
+
+def test_synth_cases_are_seeded():
+    a = synth.make_case("T0")
+    b = synth.make_case("T0")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[0].dtype == np.float32
+    assert a[0].min() >= 0 and a[0].max() <= 1 and a[1].any()
+    img, mask, res, name = synth.make_case("C1")
+    assert img.shape == (224, 224, 8) and name == "vit_s16"
+
+
+def test_cli_flags_match_reference():
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    a = tdd.build_arg_parser().parse_args(["-mn", "vit_b16", "-mp", "x.pth", "-d", "d", "-f", "f", "-h5", "h", "-df", "c", "-mod", "chest"])
+    assert (a.model_name, a.model_path, a.dataset_path, a.feature_folder, a.hdf5_path, a.df_path, a.modality) == \
+        ("vit_b16", "x.pth", "d", "f", "h", "c", "chest")
+    b = tm.build_arg_parser().parse_args(["-a", "transformer", "-d", "stanford", "-b", "vit", "-m", "ct", "-gpu", "1", "-l", "focal", "-e", "e"])
+    assert (b.arch, b.dataset, b.backbone, b.modality, b.gpu, b.loss, b.experiment) == ("transformer", "stanford", "vit", "ct", 1, "focal", "e")
+    with pytest.raises(NotImplementedError):
+        tdd.load_model("medsam")
+
+
+def test_build_model_and_state_dict_keys():
+    cfg = config_manager.load_conf(project_dir=ROOT)
+    model = tm.build_model(cfg, "transformer", "ct")
+    keys = set(model.state_dict().keys())
+    want = {"cls_token", "norm.weight", "norm.bias", "classifier.dense1.weight", "classifier.dense1.bias",
+            "classifier.dense2.weight", "classifier.dense2.bias"}
+    for i in range(2):
+        p = f"transformer_encoder.layers.{i}."
+        want |= {p + s for s in ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+                                 "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight",
+                                 "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")}
+    assert keys == want
+    assert sum(p.numel() for p in model.parameters()) == 1_712_898
+    if os.path.isdir("/root/reference/src"):
+        from oracle import ref_shim
+        ma = ref_shim.load_reference("models_archs")
+        ref = ma.TransformerNoduleClassifier(256, 1024, 4, 2, 2)
+        assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        model.load_state_dict(ref.state_dict())                          # .pth interchange

@@ -1,0 +1,42 @@
+"""oracle/vit_fp32.py against transformers.ViTModel with copied weights (CPU)."""
+import pytest
+import torch
+
+from oracle import vit_fp32
+
+
+def test_vit_oracle_matches_hf():
+    tr = pytest.importorskip("transformers")
+    cfg = dict(dim=128, depth=2, heads=2, patch=16)
+    H = W = 64
+    w = vit_fp32.init_weights(cfg, (H, W), seed=3)
+    hf_cfg = tr.ViTConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
+                          image_size=H, patch_size=16, hidden_act="gelu", layer_norm_eps=1e-6, qkv_bias=True,
+                          hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = tr.ViTModel(hf_cfg, add_pooling_layer=False).eval()
+    sd = m.state_dict()
+    d = 128
+    sd["embeddings.cls_token"] = w["cls_token"]
+    sd["embeddings.position_embeddings"] = w["pos_embed"]
+    sd["embeddings.patch_embeddings.projection.weight"] = w["patch_embed.weight"]
+    sd["embeddings.patch_embeddings.projection.bias"] = w["patch_embed.bias"]
+    for i in range(2):
+        b, hb = f"blocks.{i}.", f"encoder.layer.{i}."
+        qkv_w, qkv_b = w[b + "attn.qkv.weight"], w[b + "attn.qkv.bias"]
+        for j, nm in enumerate(("query", "key", "value")):
+            sd[hb + f"attention.attention.{nm}.weight"] = qkv_w[j * d:(j + 1) * d]
+            sd[hb + f"attention.attention.{nm}.bias"] = qkv_b[j * d:(j + 1) * d]
+        sd[hb + "attention.output.dense.weight"] = w[b + "attn.proj.weight"]
+        sd[hb + "attention.output.dense.bias"] = w[b + "attn.proj.bias"]
+        sd[hb + "layernorm_before.weight"], sd[hb + "layernorm_before.bias"] = w[b + "norm1.weight"], w[b + "norm1.bias"]
+        sd[hb + "layernorm_after.weight"], sd[hb + "layernorm_after.bias"] = w[b + "norm2.weight"], w[b + "norm2.bias"]
+        sd[hb + "intermediate.dense.weight"], sd[hb + "intermediate.dense.bias"] = w[b + "mlp.fc1.weight"], w[b + "mlp.fc1.bias"]
+        sd[hb + "output.dense.weight"], sd[hb + "output.dense.bias"] = w[b + "mlp.fc2.weight"], w[b + "mlp.fc2.bias"]
+    sd["layernorm.weight"], sd["layernorm.bias"] = w["norm.weight"], w["norm.bias"]
+    m.load_state_dict(sd)
+    x = torch.randn(2, 3, H, W)
+    with torch.no_grad():
+        want = m(pixel_values=x).last_hidden_state
+        dense, tok = vit_fp32.vit_forward(w, cfg, x, return_tokens=True)
+    assert torch.allclose(tok, want, atol=2e-5, rtol=1e-4)
+    assert dense.shape == (2, 4, 4, 128) and torch.equal(dense.reshape(2, 16, 128), tok[:, 1:])

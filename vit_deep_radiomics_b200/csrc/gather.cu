@@ -16,7 +16,9 @@ struct G1Geom {
   const uint8_t* mask;
   const int32_t* row_map;
   const int32_t* col_map;
-  int S, h, w, hm, wm;
+  int S, h, w;
+  int64_t mask_slice_stride, mask_row_stride;   // bytes between slices / rows of the pixel mask
+  int64_t feat_slice_rows, feat_row_pitch, feat_row0;  // token row = k*slice_rows + row0 + a*pitch + b
   int64_t total;
 };
 
@@ -26,7 +28,7 @@ __device__ __forceinline__ bool g1_pred(const G1Geom& g, int64_t n) {
   const int64_t q = n / g.S;
   const int b = static_cast<int>(q % g.w);
   const int a = static_cast<int>(q / g.w);
-  const int64_t off = (static_cast<int64_t>(k) * g.hm + __ldg(g.row_map + a)) * g.wm + __ldg(g.col_map + b);
+  const int64_t off = static_cast<int64_t>(k) * g.mask_slice_stride + __ldg(g.row_map + a) * g.mask_row_stride + __ldg(g.col_map + b);
   return __ldg(g.mask + off) != 0;
 }
 
@@ -162,7 +164,7 @@ g1_scatter_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int 
       y = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(yi / static_cast<double>(g.h), pe.h_orig), pe.res1), pe.mean_y), pe.noise1);
       z = __dadd_rn(__dsub_rn(__dmul_rn(static_cast<double>(k), pe.res2), pe.mean_z), pe.noise2);
     }
-    const int64_t src_row = (static_cast<int64_t>(k) * g.h + a) * g.w + b;
+    const int64_t src_row = static_cast<int64_t>(k) * g.feat_slice_rows + g.feat_row0 + a * g.feat_row_pitch + b;
     for (int c0 = lane * 8; c0 < D; c0 += 256) {
       float f[8];
       if (FEAT_BF16) {
@@ -275,14 +277,17 @@ extern "C" size_t vdr_mask_gather_workspace_bytes(int S, int h, int w) {
   return (size_t)(tiles > 0 ? tiles : 1) * 2 * sizeof(int32_t);
 }
 
-extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, const uint8_t* mask, int hm, int wm,
+extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
+                               int64_t feat_row_pitch, int64_t feat_row0, const uint8_t* mask,
+                               int64_t mask_slice_stride, int64_t mask_row_stride,
                                const int32_t* row_map, const int32_t* col_map, int S, int h, int w, int D,
                                float* out_tok, int32_t* out_src, int32_t* out_count, int cap, double pe_scale,
                                const double* pe_div, const double* coef_host, void* workspace,
                                size_t workspace_bytes, vdr_stream_t stream) {
   using namespace vdr;
   VDR_CHECK_ARG(feat && mask && row_map && col_map && out_tok && out_src && out_count && workspace, VDR_EINVAL, "vdr_mask_gather: null pointer");
-  VDR_CHECK_ARG(S > 0 && h > 0 && w > 0 && hm > 0 && wm > 0 && D > 0 && cap >= 0, VDR_EINVAL, "vdr_mask_gather: bad shape");
+  VDR_CHECK_ARG(S > 0 && h > 0 && w > 0 && D > 0 && cap >= 0, VDR_EINVAL, "vdr_mask_gather: bad shape");
+  VDR_CHECK_ARG(feat_slice_rows >= 0 && feat_row_pitch >= w && feat_row0 >= 0 && mask_slice_stride >= 0 && mask_row_stride >= 0, VDR_EINVAL, "vdr_mask_gather: bad strides");
   VDR_CHECK_ARG(D % 8 == 0 && ld_feat % 8 == 0 && ld_feat >= D, VDR_EALIGN, "vdr_mask_gather: D (%d) and ld_feat must be multiples of 8", D);
   VDR_CHECK_ARG(aligned16(feat) && aligned16(out_tok), VDR_EALIGN, "vdr_mask_gather: feat/out_tok must be 16-byte aligned");
   VDR_CHECK_ARG(feat_dtype == VDR_DTYPE_BF16 || feat_dtype == VDR_DTYPE_F32, VDR_EINVAL, "vdr_mask_gather: bad feat_dtype");
@@ -290,7 +295,7 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   VDR_CHECK_ARG(workspace_bytes >= vdr_mask_gather_workspace_bytes(S, h, w), VDR_EWORKSPACE, "vdr_mask_gather: workspace too small (%zu < %zu)", workspace_bytes, vdr_mask_gather_workspace_bytes(S, h, w));
   VDR_CHECK_ARG(pe_scale == 0.0 || (pe_div && coef_host), VDR_EINVAL, "vdr_mask_gather: positional encoding needs pe_div and coef_host");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  G1Geom g{mask, row_map, col_map, S, h, w, hm, wm, (int64_t)S * h * w};
+  G1Geom g{mask, row_map, col_map, S, h, w, mask_slice_stride, mask_row_stride, feat_slice_rows, feat_row_pitch, feat_row0, (int64_t)S * h * w};
   const int tiles = (int)((g.total + kTile - 1) / kTile);
   int32_t* counts = static_cast<int32_t*>(workspace);
   int32_t* offsets = counts + tiles;

@@ -1,0 +1,97 @@
+"""Point-cloud transformer classifier -- drop-in for the reference's src/models_archs.py.
+
+``TransformerNoduleClassifier(input_dim, dim_feedforward, num_heads, num_classes, num_layers)``
+has the reference's constructor, ``forward(x) -> (logits, cls)`` contract and state-dict keys
+(``cls_token``, ``norm.*``, ``transformer_encoder.layers.{i}.self_attn.in_proj_weight`` ...,
+``classifier.dense{1,2}.*``) so ``.pth`` files interchange with the
+reference (``save_checkpoint`` / ``load_checkpoint`` keep its file naming, :14-35).
+
+The arithmetic does not go through torch.nn: parameters are only *stored* in torch modules.
+Forward and backward run in libvdr.so (CLS-concat+LayerNorm kernel, tcgen05 GEMMs with fused
+bias/GELU/residual epilogues, fused attention, LayerNorm) -- see ``classifier_kernels.py``.
+Deviation: dropout (0.1 in the reference's train mode) is not applied (p = 0).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import classifier_kernels as ck
+
+
+def save(model, model_path):
+    torch.save(model.state_dict(), model_path)
+
+
+def load(model, model_path):
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    model.load_state_dict(torch.load(model_path, map_location=device))
+    return model.to(device)
+
+
+def save_checkpoint(model, save_dir, epoch):
+    """reference: models_archs.py:14-19 -- <save_dir>/model_epoch_<epoch:04d>.pth (state-dict only)."""
+    os.makedirs(save_dir, exist_ok=True)
+    save(model, os.path.join(save_dir, f"model_epoch_{str(epoch).zfill(4)}.pth"))
+
+
+def load_checkpoint(model, save_dir, epoch):
+    """reference: models_archs.py:22-25."""
+    return load(model, os.path.join(save_dir, f"model_epoch_{str(epoch).zfill(4)}.pth"))
+
+
+class MLPLayer(nn.Module):
+    """Parameter container for the reference's MLPLayer (:186-200): dense1 -> GELU -> dense2."""
+
+    def __init__(self, input_dim, hidden_features, out_features, dropout_rate=0.1):
+        super().__init__()
+        self.dense1 = nn.Linear(input_dim, hidden_features, bias=True)
+        self.dense2 = nn.Linear(hidden_features, out_features, bias=True)
+        self.dropout_rate = dropout_rate
+
+
+class TransformerNoduleClassifier(nn.Module):
+    """reference: models_archs.py:127-147."""
+
+    def __init__(self, input_dim, dim_feedforward, num_heads, num_classes, num_layers):
+        super().__init__()
+        if input_dim % num_heads or input_dim // num_heads != 64:
+            raise ValueError("the fused attention kernel needs head_dim == 64 "
+                             f"(input_dim {input_dim} / num_heads {num_heads})")
+        # torch modules are used as parameter containers only: identical names, shapes and init laws
+        # to the reference, never called.
+        layer = nn.TransformerEncoderLayer(d_model=input_dim, dim_feedforward=dim_feedforward, nhead=num_heads,
+                                           activation="gelu", batch_first=True, dropout=0.1)
+        self.norm = nn.LayerNorm(input_dim)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=num_layers, enable_nested_tensor=False)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, input_dim))
+        self.classifier = MLPLayer(input_dim, input_dim * 2, num_classes)
+        self.input_dim, self.dim_feedforward = input_dim, dim_feedforward
+        self.num_heads, self.num_layers, self.num_classes = num_heads, num_layers, num_classes
+
+    def param_list(self):
+        """Parameters in the fixed order the kernels expect (see classifier_kernels.PARAM_ORDER)."""
+        ps = [self.cls_token, self.norm.weight, self.norm.bias]
+        for lyr in self.transformer_encoder.layers:
+            ps += [lyr.self_attn.in_proj_weight, lyr.self_attn.in_proj_bias,
+                   lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias,
+                   lyr.norm1.weight, lyr.norm1.bias,
+                   lyr.linear1.weight, lyr.linear1.bias, lyr.linear2.weight, lyr.linear2.bias,
+                   lyr.norm2.weight, lyr.norm2.bias]
+        ps += [self.classifier.dense1.weight, self.classifier.dense1.bias,
+               self.classifier.dense2.weight, self.classifier.dense2.bias]
+        return ps
+
+    def forward(self, x):
+        """x (batch, seq_len, feature_dim) f32 CUDA -> (logits (batch, classes), cls (batch, feature_dim)).
+        The reference runs batch 1 (variable-length clouds, no padding); batches are looped."""
+        if x.dim() != 3 or x.shape[2] != self.input_dim:
+            raise ValueError(f"expected (batch, seq_len, {self.input_dim}), got {tuple(x.shape)}")
+        logits, cls = [], []
+        for b in range(x.shape[0]):
+            lg, c = ck.ClassifierFunction.apply(x[b], self.num_heads, self.num_layers, *self.param_list())
+            logits.append(lg)
+            cls.append(c)
+        return torch.stack(logits, 0), torch.stack(cls, 0)

@@ -12,6 +12,27 @@ from . import _C
 
 _DT = {torch.bfloat16: _C.VDR_DTYPE_BF16, torch.float32: _C.VDR_DTYPE_F32}
 
+#: when set to a list, gemm / flash_attn append (kind, algorithmic flops, start event, end event) per launch
+#: (CUDA events on the launching stream) -- used by bench.py for the roofline numbers.
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.kind, self.flops, self.e0, e1))
+        return False
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -56,7 +77,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
     args.epilogue = epi
     args.out_group, args.out_group_stride, args.out_offset = out_group
     args.res_mod, args.res_offset = res_mod
-    _C.check(_C.lib().vdr_gemm(C.byref(args), _stream()), "vdr_gemm")
+    with _Prof("gemm", 2.0 * M * N * K):
+        _C.check(_C.lib().vdr_gemm(C.byref(args), _stream()), "vdr_gemm")
     return out
 
 
@@ -140,9 +162,10 @@ def flash_attn(qkv: torch.Tensor, B: int, N: int, heads: int, scale: float | Non
     if out is None:
         out = torch.empty((B * N, d), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if return_lse else None
-    _C.check(_C.lib().vdr_flash_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0),
-                                         lse.data_ptr() if return_lse else None, B, N, heads, float(scale),
-                                         _stream()), "vdr_flash_attn_fwd")
+    with _Prof("attn", 4.0 * B * heads * N * N * 64):
+        _C.check(_C.lib().vdr_flash_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0),
+                                             lse.data_ptr() if return_lse else None, B, N, heads, float(scale),
+                                             _stream()), "vdr_flash_attn_fwd")
     return (out, lse) if return_lse else out
 
 
@@ -179,19 +202,45 @@ def grid_means(h: int, w: int, S: int, h_orig: int, w_orig: int, res) -> tuple:
     return float(x.mean()), float(y.mean()), float(z.mean())
 
 
-def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = None, pe: dict | None = None):
-    """G1.  feat (S, h, w, D) bf16/f32 CUDA; mask_u8 (S, hm, wm) uint8 CUDA.
-    Returns (tokens (cap, D) f32, src (cap, 3) int32, count int32[1]) -- all on device; rows >= count
-    are unspecified.  `pe` = dict(res=(3,), noise=(3,), scale=0.25) adds the 3-D positional encoding."""
-    if feat.dim() != 4 or mask_u8.dim() != 3:
-        raise ValueError("feat must be (S,h,w,D) and mask (S,hm,wm)")
+def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = None, pe: dict | None = None,
+                grid: tuple | None = None, feat_roi: tuple | None = None, mask_roi: tuple | None = None):
+    """G1 (reference src/train_models.py:143-182 on device).
+
+    feat     (S, h, w, D) dense descriptors, or the backbone's token matrix (S*slice_rows, D) together
+             with ``grid=(S, gh, gw, slice_rows, first_row)`` (CLS-first layout: slice_rows = gh*gw+1,
+             first_row = 1).  bf16 or f32, CUDA, unit inner stride.
+    mask_u8  (S, HM, WM) uint8 CUDA pixel masks (contiguous).
+    feat_roi (r0, r1, c0, c1) feature-grid window, mask_roi (y0, y1, x0, x1) pixel window: the
+             extract_roi crops of tfds_dense_descriptor.py:278-279, applied by pointer arithmetic.
+    pe       dict(res=(3,), noise=(3,), scale=0.25): add the 3-D positional encoding / 4 (:178-180).
+    Returns (tokens (cap, D) f32, src (cap, 3) int32 [slice,row,col in ROI coords], count int32[1]),
+    all on the device; rows >= count are unspecified.
+    """
     _req(mask_u8, torch.uint8, "mask")
-    if feat.dtype not in _DT:
-        raise ValueError("feat must be bf16 or f32")
-    if not feat.is_contiguous() or not mask_u8.is_contiguous():
-        raise ValueError("feat and mask must be contiguous")
-    S, h, w, D = feat.shape
-    _, hm, wm = mask_u8.shape
+    if feat.dtype not in _DT or not feat.is_cuda:
+        raise ValueError("feat must be a bf16 or f32 CUDA tensor")
+    if not mask_u8.is_contiguous() or mask_u8.dim() != 3:
+        raise ValueError("mask must be a contiguous (S, HM, WM) tensor")
+    if feat.dim() == 4:
+        if not feat.is_contiguous():
+            raise ValueError("dense feat must be contiguous")
+        S, gh, gw, D = feat.shape
+        slice_rows, first_row, ld = gh * gw, 0, D
+    elif feat.dim() == 2 and grid is not None:
+        S, gh, gw, slice_rows, first_row = (int(v) for v in grid)
+        D, ld = feat.shape[1], feat.stride(0)
+        if feat.stride(1) != 1 or feat.shape[0] < S * slice_rows:
+            raise ValueError("token matrix too small / not unit inner stride")
+    else:
+        raise ValueError("feat must be (S,h,w,D) or a token matrix with grid=(S,gh,gw,slice_rows,first_row)")
+    if mask_u8.shape[0] != S:
+        raise ValueError(f"mask has {mask_u8.shape[0]} slices, features {S}")
+    r0, r1, c0, c1 = feat_roi if feat_roi is not None else (0, gh, 0, gw)
+    HM, WM = mask_u8.shape[1], mask_u8.shape[2]
+    y0, y1, x0, x1 = mask_roi if mask_roi is not None else (0, HM, 0, WM)
+    h, w, hm, wm = r1 - r0, c1 - c0, y1 - y0, x1 - x0
+    if min(h, w, hm, wm) <= 0 or r1 > gh or c1 > gw or y1 > HM or x1 > WM or min(r0, c0, y0, x0) < 0:
+        raise ValueError("empty or out-of-range ROI")
     dev = feat.device
     row_map = torch.from_numpy(nearest_index_map(h, hm)).to(dev)
     col_map = torch.from_numpy(nearest_index_map(w, wm)).to(dev)
@@ -209,7 +258,8 @@ def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = 
         coef = (C.c_double * 11)(float(wm), float(hm), res[0], res[1], res[2], noise[0], noise[1], noise[2], mx, my, mz)
         pe_scale = float(pe.get("scale", 0.25))
         pe_div_ptr = _pe_div(D, dev).data_ptr()
-    _C.check(_C.lib().vdr_mask_gather(feat.data_ptr(), _DT[feat.dtype], D, mask_u8.data_ptr(), hm, wm,
+    _C.check(_C.lib().vdr_mask_gather(feat.data_ptr(), _DT[feat.dtype], ld, slice_rows, gw, first_row + r0 * gw + c0,
+                                      mask_u8.data_ptr() + y0 * WM + x0, HM * WM, WM,
                                       row_map.data_ptr(), col_map.data_ptr(), S, h, w, D,
                                       tokens.data_ptr(), src.data_ptr(), count.data_ptr(), cap,
                                       pe_scale, pe_div_ptr, coef, ws.data_ptr(), ws_bytes, _stream()),

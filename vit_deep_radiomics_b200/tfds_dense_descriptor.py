@@ -1,0 +1,242 @@
+"""ViT dense-descriptor extraction -- drop-in for the reference's src/tfds_dense_descriptor.py.
+
+Same entry points (``load_model``, ``prepare_image``, ``get_dense_descriptor``,
+``generate_features``, ``save_features``, ``apply_window_ct``, ``flip_image``, ``rotate_image``,
+``get_voxels``) and the same CLI flags; the backbone forward runs in libvdr.so (tcgen05 GEMMs,
+fused attention, warp-shuffle LayerNorm) on batches of slices instead of one slice per call
+with a host round trip (reference hot loop, :271-283).
+
+``extract_point_cloud`` is the fused device path for one patient: crop -> batched ViT forward ->
+ROI crop -> tumour-mask gather (+ positional encoding), i.e. L2 -> L4a of SURVEY.md without
+the HDF5 hand-off; it returns exactly what ``PETCTDataset3D._get_features`` would compute from
+the files ``generate_features`` + ``save_features`` write.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+from .visualization_utils import crop_image, crop_window, extract_roi, roi_window
+from .vit import VIT_CONFIGS, ViTBackbone
+
+# --------------------------------------------------------------------------------------------- model
+def load_model(model_name, model_path=None, img_hw=None, device="cuda:0", seed=1234):
+    """reference: tfds_dense_descriptor.py:51-67.  ``model_name`` extends the reference's
+    {'medsam', 'dinov2'} with the plain-ViT backbones of BASELINE.json: 'vit_s16', 'vit_b16',
+    'vit_l14'.  ``model_path`` (optional) is a torch state-dict with timm/DINOv2 key names;
+    without it the weights are seeded random (no checkpoints exist offline)."""
+    if model_name in ("medsam", "dinov2"):
+        raise NotImplementedError(
+            f"backbone {model_name!r} needs third-party code/checkpoints that are not vendored by the reference "
+            "(segment_anything / torch.hub); the SAM-specific encoder (windowed attention, rel-pos bias, neck) is "
+            "the next scope row (SURVEY.md section 8f N1).  Use 'vit_s16', 'vit_b16' or 'vit_l14'.")
+    if model_name not in VIT_CONFIGS:
+        raise ValueError(f"unknown model_name {model_name!r}")
+    if img_hw is None:
+        img_hw = (518, 518) if VIT_CONFIGS[model_name]["patch"] == 14 else (512, 512)
+    sd = None
+    if model_path is not None:
+        sd = torch.load(model_path, map_location="cpu")
+        sd = sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+    model = ViTBackbone(model_name, img_hw=img_hw, state_dict=sd, device=device, seed=seed)
+    model.model_name = model_name
+    return model
+
+
+def prepare_image(img, size=None, device="cuda:0"):
+    """reference: tfds_dense_descriptor.py:30-48 -- gray2rgb, (resize), HWC -> NCHW, float32, to GPU.
+    Returns a (1, 3, h, w) CUDA tensor.  The reference always resizes to 1024^2 / 896^2 with
+    skimage; here the backbone is built for the crop size, so only the identity resize is
+    accepted (GPU bilinear pre-processing is scope row N2)."""
+    img = np.asarray(img)
+    if img.ndim < 3:
+        img = np.stack([img] * 3, axis=-1)          # gray2rgb (:41)
+    if size is not None and tuple(size) != tuple(img.shape[0:2]):
+        raise NotImplementedError(f"resize {img.shape[0:2]} -> {tuple(size)} is not implemented on the device path")
+    t = torch.as_tensor(np.ascontiguousarray(img.transpose((2, 0, 1))[None]), dtype=torch.float32)
+    return t.to(device)
+
+
+def get_dense_descriptor(model, img):
+    """reference: tfds_dense_descriptor.py:110-139.  img (N, M[, CH]) in 0..1 ->
+    features (N//patch, M//patch, feature_dim) float32 numpy (patch tokens only, HWC)."""
+    x = prepare_image(img, size=model.img_hw, device=model.device)
+    feats = model.dense_descriptors(x)
+    return feats[0].cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------- volume level
+def _plan(model, mask_3d):
+    """Host-side index math of generate_features (:257-267, :278-279): crop window, feature ROI,
+    pixel-mask ROI.  Pure integer geometry on the union mask."""
+    H, W = mask_3d.shape[0:2]
+    bigger = np.any(mask_3d, axis=-1)                                    # == (np.sum(mask_3d, -1) > 0), :257
+    x0, y0, x1, y1 = crop_window(bigger)
+    y0c, y1c = [max(0, min(v, H)) for v in (y0, y1)]
+    x0c, x1c = [max(0, min(v, W)) for v in (x0, x1)]
+    bigger_c = bigger[y0c:y1c, x0c:x1c]
+    ch, cw = bigger_c.shape
+    if (ch, cw) != tuple(model.img_hw):
+        raise NotImplementedError(
+            f"crop window {ch}x{cw} differs from the backbone input {model.img_hw}: the resize of "
+            "prepare_image is not implemented on the device path (scope row N2); build the model with img_hw="
+            f"({ch}, {cw})")
+    gh, gw = model.grid
+    fx0, fy0, fx1, fy1 = roi_window((gh, gw), bigger_c, margin=1)      # extract_roi(features, bigger_mask)
+    mx0, my0, mx1, my1 = roi_window((ch, cw), bigger_c, margin=1)      # extract_roi(mask, bigger_mask)
+    return dict(crop=(y0c, y1c, x0c, x1c), feat_roi=(fy0, fy1, fx0, fx1), mask_roi=(my0, my1, mx0, mx1))
+
+
+def _forward_volume(model, img_dev, plan, max_batch=None):
+    """Batched backbone forward over all slices of a device-resident volume (H, W, S[, 3]) f32.
+    Slices are read in place through element strides (no host transpose, no NCHW copy)."""
+    y0, y1, x0, x1 = plan["crop"]
+    S = img_dev.shape[2]
+    view = img_dev[y0:y1, x0:x1]
+    if img_dev.dim() == 3:
+        strides = (view.stride(2), 0, view.stride(0), view.stride(1))
+    else:
+        strides = (view.stride(2), view.stride(3), view.stride(0), view.stride(1))
+    if max_batch is None or max_batch >= S:
+        return model.forward_tokens(view, strides, S)
+    outs = []
+    for s0 in range(0, S, max_batch):
+        b = min(max_batch, S - s0)
+        outs.append(model.forward_tokens(view[:, :, s0:s0 + b], strides, b).clone())
+    return torch.cat(outs, dim=0)
+
+
+def generate_features(model, img_3d, mask_3d, tqdm_text="", display=False, max_batch=None):
+    """reference: tfds_dense_descriptor.py:242-284.  Returns (features_list, mask_list): per slice the
+    ROI-cropped descriptor map (h_f, w_f, D) float32 and the ROI-cropped boolean pixel mask."""
+    img_3d, mask_3d = np.asarray(img_3d), np.asarray(mask_3d)
+    plan = _plan(model, mask_3d)
+    img_dev = torch.as_tensor(np.ascontiguousarray(img_3d, dtype=np.float32)).to(model.device)
+    tok = _forward_volume(model, img_dev, plan, max_batch)
+    S, d = img_3d.shape[2], model.cfg["dim"]
+    gh, gw = model.grid
+    fy0, fy1, fx0, fx1 = plan["feat_roi"]
+    feats = tok.view(S, model.n_tokens, d)[:, 1:, :].reshape(S, gh, gw, d)[:, fy0:fy1, fx0:fx1, :].cpu().numpy()
+    y0, y1, x0, x1 = plan["crop"]
+    my0, my1, mx0, mx1 = plan["mask_roi"]
+    mask_c = mask_3d[y0:y1, x0:x1]
+    features_list = [feats[s] for s in range(S)]
+    mask_list = [(mask_c[:, :, s] > 0)[my0:my1, mx0:mx1] for s in range(S)]
+    return features_list, mask_list
+
+
+def extract_point_cloud(model, img_3d, mask_3d, spatial_res, noise=(0.0, 0.0, 0.0), add_pe=True,
+                        pinned=None, to_host=True):
+    """Fused device path for one patient: what ``_get_features`` (train_models.py:143-182) returns for
+    the features/masks that ``generate_features`` produces, without leaving the GPU in between.
+
+    img_3d (H, W, S) float32 in 0..1, mask_3d (H, W, S) bool/uint8 (numpy, or pinned torch tensors).
+    Returns dict(tokens (n, D) f32, src (n, 3) int32 (slice, row, col) in ROI coords, count, plan).
+    """
+    mask_np = mask_3d.numpy() if isinstance(mask_3d, torch.Tensor) else np.asarray(mask_3d)
+    plan = _plan(model, mask_np)
+    dev = model.device
+    img_t = img_3d if isinstance(img_3d, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(img_3d, dtype=np.float32))
+    mask_t = mask_3d if isinstance(mask_3d, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(mask_np).view(np.uint8) if mask_np.dtype == bool else np.ascontiguousarray(mask_np, dtype=np.uint8))
+    img_dev = img_t.to(dev, non_blocking=True)
+    mask_dev = mask_t.to(dev, non_blocking=True)                       # (H, W, S) u8
+    tok = _forward_volume(model, img_dev, plan)
+    S = img_dev.shape[2]
+    y0, y1, x0, x1 = plan["crop"]
+    # pixel masks slice-major for the gather (S, ch, cw): a u8 transpose of the crop, done on the device
+    mask_s = mask_dev[y0:y1, x0:x1].permute(2, 0, 1).contiguous()
+    gh, gw = model.grid
+    pe = dict(res=spatial_res, noise=noise, scale=0.25) if add_pe else None
+    tokens, src, count = ops.mask_gather(tok, mask_s, grid=(S, gh, gw, model.n_tokens, 1), feat_roi=plan["feat_roi"],
+                                         mask_roi=plan["mask_roi"], pe=pe)
+    out = dict(plan=plan)
+    if to_host:
+        n = int(count.item())                                          # D2H sync: the step's result
+        out.update(tokens=tokens[:n].cpu(), src=src[:n].cpu(), count=n)
+    else:
+        out.update(tokens=tokens, src=src, count=count)
+    return out
+
+
+# --------------------------------------------------------------------------------------------- host helpers
+def windowing_ct(width, level):
+    """reference: tfds_dense_descriptor.py:204-239."""
+    return level - width / 2, level + width / 2
+
+
+def apply_window_ct(ct, width, level):
+    """reference: tfds_dense_descriptor.py:287-303 -- HU window to 0..1."""
+    lo, hi = windowing_ct(width, level)
+    return np.clip((ct - lo) / (hi - lo), 0, 1)
+
+
+def flip_image(image, mask, flip_type):
+    """reference: tfds_dense_descriptor.py:306-325 (None | 'horizontal' | 'vertical')."""
+    image, mask = image.copy(), mask.copy()
+    if flip_type == "horizontal":
+        return image[:, ::-1, ...], mask[:, ::-1, ...]
+    if flip_type == "vertical":
+        return image[::-1, ...], mask[::-1, ...]
+    return image, mask
+
+
+def rotate_image(image, mask, angle, axes=(0, 1)):
+    """reference: tfds_dense_descriptor.py:328-350 -- offline augmentation on the host (scipy cubic
+    spline, mode='nearest'); image clipped to 0..1, mask re-binarised."""
+    from scipy.ndimage import rotate
+    image, mask = image.copy(), mask.copy()
+    if angle == 0:
+        return image, mask
+    image = np.clip(rotate(image, angle, axes=axes, reshape=False, mode="nearest"), 0, 1)
+    mask = rotate(mask, angle, axes=axes, reshape=False, mode="nearest") > 0
+    return image, mask
+
+
+def _h5py():
+    try:
+        import h5py
+        return h5py
+    except ImportError as e:  # the reference's on-disk hand-off needs h5py; it is not in this image
+        raise ImportError("h5py is required for the HDF5 hand-off (save_features / get_voxels)") from e
+
+
+def save_features(filename, all_features, all_masks, patient_id):
+    """reference: tfds_dense_descriptor.py:142-165 -- <pid>/features/<i>, <pid>/masks/<i>, lzf, one chunk."""
+    h5py = _h5py()
+    with h5py.File(filename, "a") as h5f:
+        if patient_id in h5f:
+            print(f"features for {patient_id} already exists")
+            del h5f[patient_id]
+        grp = h5f.create_group(patient_id)
+        for i, (feature, mask) in enumerate(zip(all_features, all_masks)):
+            grp.create_dataset(f"features/{i}", compression="lzf", data=feature, chunks=feature.shape)
+            grp.create_dataset(f"masks/{i}", compression="lzf", data=mask, chunks=mask.shape)
+
+
+def get_voxels(hdf5_path, patient_id, modality):
+    """reference: tfds_dense_descriptor.py:353-362 -- (H, W, S) image + mask, isotropic 0.8 mm."""
+    h5py = _h5py()
+    spatial_res = np.array([0.8, 0.8, 0.8])
+    with h5py.File(hdf5_path, "r") as h5f:
+        idm = f"{patient_id}_{modality}"
+        slices = sorted(int(k) for k in h5f[f"{idm}/img_exam"].keys())
+        img = np.dstack([h5f[f"{idm}/img_exam/{k}"][()] for k in slices])
+        mask = np.dstack([h5f[f"{idm}/mask_exam/{k}"][()] for k in slices])
+    return img, mask, spatial_res
+
+
+def build_arg_parser():
+    """Same flags as the reference CLI (tfds_dense_descriptor.py:365-382)."""
+    p = argparse.ArgumentParser(description="ViT patch embeddings of the lung_radiomics datasets (B200-native)")
+    p.add_argument("-mn", "--model_name", type=str, default="vit_b16", help="vit_s16 | vit_b16 | vit_l14 (medsam, dinov2: not available)")
+    p.add_argument("-mp", "--model_path", type=str, default=None)
+    p.add_argument("-d", "--dataset_path", type=str, default=os.path.join("data", "lung_radiomics"))
+    p.add_argument("-f", "--feature_folder", type=str, default=os.path.join("data", "features"))
+    p.add_argument("-h5", "--hdf5_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets.hdf5"))
+    p.add_argument("-df", "--df_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets.csv"))
+    p.add_argument("-mod", "--modality", type=str, default="ct")
+    return p

@@ -1,0 +1,142 @@
+"""Gather + classifier training -- drop-in for the hot-path parts of the reference's src/train_models.py.
+
+Kept entry points: ``positional_encoding_3d`` (:30-44), ``PETCTDataset3D._get_features`` semantics
+(:143-182, here ``get_features`` on device), ``FocalLoss`` (:381-405), ``build_model`` (:455-486),
+``get_y_true_and_pred`` (:283-311), the gradient-accumulation train step (:652-688) and the CLI flags
+(:500-515).  Metrics JSON / plotting / early stopping policy (:726-810) are outside the hot path.
+"""
+from __future__ import annotations
+
+import argparse
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .models_archs import TransformerNoduleClassifier
+
+
+def positional_encoding_3d(x, y, z, D, scale=10000):
+    """reference: train_models.py:30-44 (host, float64).  The device gather computes the same encoding
+    in its epilogue (ops.mask_gather(pe=...)); this is the API-compatible host version."""
+    x, y, z = np.asarray(x, np.float64), np.asarray(y, np.float64), np.asarray(z, np.float64)
+    enc = np.zeros((x.shape[0], D))
+    i = np.arange(D // 6)
+    div = np.array([scale ** (6 * k / D) for k in range(D // 6)])
+    for base, v in ((0, x), (D // 3, y), (2 * D // 3, z)):
+        arg = v[:, None] / div[None, :]
+        enc[:, 2 * i + base] = np.sin(arg)
+        enc[:, 2 * i + 1 + base] = np.cos(arg)
+    return enc
+
+
+def get_features(features, masks, spatial_res, noise=(0.0, 0.0, 0.0), feature_dim=None, arch="transformer",
+                 device="cuda:0", add_pe=True):
+    """Device version of ``PETCTDataset3D._get_features`` (train_models.py:143-182) for data already in
+    memory: ``features`` = S arrays (h, w, D) (or one (S,h,w,D) tensor), ``masks`` = S pixel masks (hm, wm).
+    Returns the (n_sel, D) float32 token sequence (features[mask] + PE/4) on the device."""
+    if arch != "transformer":
+        raise NotImplementedError("arch='conv' (Conv3d classifier) is outside the hot path")
+    f = features if isinstance(features, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.stack(features, 0)))
+    m = masks if isinstance(masks, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.stack(masks, 0)).astype(np.uint8))
+    f, m = f.to(device), m.to(device)
+    if f.dtype not in (torch.float32, torch.bfloat16):
+        f = f.float()
+    pe = dict(res=spatial_res, noise=noise, scale=0.25) if add_pe else None
+    tokens, src, count = ops.mask_gather(f.contiguous(), m.contiguous(), pe=pe)
+    n = int(count.item())
+    return tokens[:n]
+
+
+class FocalLoss(nn.Module):
+    """reference: train_models.py:381-405 -- sum over samples of -alpha_c (1-p_c)^gamma log p_c at the
+    true class c = argmax(one-hot target).  (2-element tensors: host-launched elementwise math.)"""
+
+    def __init__(self, gamma=2, alpha=None):
+        super().__init__()
+        self.gamma = gamma
+        self.weight = alpha
+
+    def forward(self, inputs, targets):
+        if inputs.dim() == 1:
+            inputs, targets = inputs.unsqueeze(0), targets.unsqueeze(0)
+        cls_idx = torch.argmax(targets, dim=1)
+        logpt = F.log_softmax(inputs, dim=1)
+        logpt = (1 - torch.exp(logpt)) ** self.gamma * logpt
+        return F.nll_loss(logpt, cls_idx, self.weight, reduction="sum")
+
+
+def get_y_true_and_pred(y_true, y_pred, cpu=False):
+    """reference: train_models.py:283-311."""
+    y_true, y_pred = torch.squeeze(y_true), torch.squeeze(y_pred)
+    assert y_pred.size() == y_true.size()
+    if y_true.dim() == 1:
+        y_pred, y_true = y_pred.unsqueeze(0), y_true.unsqueeze(0)
+    y_score = F.softmax(y_pred, dim=1)
+    y_true = torch.argmax(y_true, dim=1)
+    if cpu:
+        y_true, y_score = y_true.detach().cpu().numpy(), y_score.detach().cpu().numpy()
+    return y_true, y_score
+
+
+def build_model(cfg, arch, modality, modality_a="pet", modality_b="ct", num_classes=2):
+    """reference: train_models.py:455-486.  Only the unimodal transformer is on the hot path."""
+    cfg_model = cfg["models"][arch]
+    feature_dim = cfg_model["feature_dim"]
+    if modality in ("petct", "petchest"):
+        raise NotImplementedError("bimodal PET+CT classifier is scope row N4 (next)")
+    if arch == "conv":
+        raise NotImplementedError("Conv3d classifier is out of scope (north star names the transformer)")
+    m = cfg_model[modality]
+    return TransformerNoduleClassifier(input_dim=feature_dim, dim_feedforward=int(feature_dim * m["mlp_ratio"]),
+                                       num_heads=m["num_heads"], num_classes=num_classes, num_layers=m["num_layers"])
+
+
+def make_optimizer(model, cfg, arch="transformer"):
+    """reference: train_models.py:600-601 -- AdamW(lr, wd 0.01) + cosine annealing to 1e-4 over 0.8*epochs."""
+    c = cfg["models"][arch]
+    opt = torch.optim.AdamW(model.parameters(), lr=c["learning_rate"], weight_decay=0.01)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=int(c["num_epochs"] * 0.8), eta_min=1e-4)
+    return opt, sched
+
+
+def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, grad_sync=None):
+    """One pass of the reference's accumulation loop (train_models.py:652-688).
+
+    samples: iterable of (tokens (n, d) f32 CUDA, one-hot label (C,) f32 CUDA).
+    Loss is divided by iters_to_accumulate = min(virtual_batch, len(samples)) (:655,674); the optimizer
+    steps every iters_to_accumulate samples and at the last sample (:685-687).  ``grad_sync`` (optional
+    callable) is invoked right before each optimizer step: the data-parallel gradient all-reduce.
+    Returns (mean loss, list of softmax scores)."""
+    samples = list(samples)
+    iters = min(virtual_batch_size, len(samples))
+    model.train()
+    optimizer.zero_grad()
+    total, scores = 0.0, []
+    for i, (tokens, label) in enumerate(samples):
+        logits, _ = model(tokens.unsqueeze(0))
+        loss = criterion(torch.squeeze(logits), label) / iters
+        loss.backward()
+        total += float(loss.item()) * iters
+        scores.append(torch.softmax(logits.detach(), dim=1)[0].cpu().numpy())
+        if (i + 1) % iters == 0 or (i + 1) == len(samples):
+            if grad_sync is not None:
+                grad_sync(model)
+            optimizer.step()
+            optimizer.zero_grad()
+    return total / max(len(samples), 1), scores
+
+
+def build_arg_parser():
+    """Same flags as the reference CLI (train_models.py:500-515)."""
+    p = argparse.ArgumentParser(description="Train the point-cloud transformer for lung nodule classification")
+    p.add_argument("-a", "--arch", type=str, default="transformer")
+    p.add_argument("-d", "--dataset", type=str, default="stanford")
+    p.add_argument("-b", "--backbone", type=str, default="vit_b16")
+    p.add_argument("-m", "--modality", type=str, default="ct")
+    p.add_argument("-gpu", "--gpu", type=int, default=0)
+    p.add_argument("-l", "--loss", type=str, default="focal")
+    p.add_argument("-e", "--experiment", type=str, default="exp")
+    return p

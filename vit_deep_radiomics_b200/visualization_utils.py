@@ -1,0 +1,66 @@
+"""Geometry helpers that decide WHAT gets stored/gathered (host integer math).
+
+Mirror of the reference's src/visualization_utils.py:93-125 (crop_image, extract_coords,
+extract_roi).  The display helpers of that file (:16-90) are out of scope (interactive plotting).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def crop_image(img, xmin, ymin, xmax, ymax):
+    """reference: visualization_utils.py:93-98 (window clamped to the image)."""
+    h, w = img.shape[0:2]
+    ymin, ymax = [max(0, min(int(v), h)) for v in (ymin, ymax)]
+    xmin, xmax = [max(0, min(int(v), w)) for v in (xmin, xmax)]
+    return img[ymin:ymax, xmin:xmax]
+
+
+def extract_coords(mask, margin):
+    """reference: visualization_utils.py:101-112.  NOTE the reference SHIFTS the bounding box by
+    `margin` (rows up, columns right) and keeps extent max-min; it does not expand it.  Kept as is."""
+    rows = np.flatnonzero(np.any(mask, axis=1))
+    cols = np.flatnonzero(np.any(mask, axis=0))
+    if rows.size == 0:
+        raise ValueError("extract_coords: empty mask")  # reference: np.min of an empty array raises too
+    ymin = int(rows[0]) - margin
+    xmin = int(cols[0]) + margin
+    ymax = int(rows[-1]) - margin
+    xmax = int(cols[-1]) + margin
+    h = max(ymax - ymin, margin)
+    w = max(xmax - xmin, margin)
+    return xmin, ymin, xmin + w, ymin + h
+
+
+def roi_window(img_hw, mask, margin=1):
+    """(xmin, ymin, xmax, ymax) that extract_roi crops from an array of spatial shape img_hw,
+    clamped like crop_image.  reference: visualization_utils.py:115-125."""
+    xmin, ymin, xmax, ymax = extract_coords(mask, margin)
+    if tuple(img_hw) != tuple(mask.shape[0:2]):
+        hs = img_hw[0] / mask.shape[0]
+        ws = img_hw[1] / mask.shape[1]
+        xmin, ymin, xmax, ymax = [int(v) for v in (xmin * ws, ymin * hs, xmax * ws, ymax * hs)]
+        h = max(ymax - ymin, margin)
+        w = max(xmax - xmin, margin)
+        xmax = xmin + w
+        ymax = ymin + h
+    H, W = img_hw
+    ymin, ymax = [max(0, min(v, H)) for v in (ymin, ymax)]
+    xmin, xmax = [max(0, min(v, W)) for v in (xmin, xmax)]
+    return xmin, ymin, xmax, ymax
+
+
+def extract_roi(img, mask, margin=1):
+    """reference: visualization_utils.py:115-125."""
+    xmin, ymin, xmax, ymax = roi_window(img.shape[0:2], mask, margin)
+    return img[ymin:ymax, xmin:xmax]
+
+
+def crop_window(mask_3d):
+    """Square crop window of generate_features (tfds_dense_descriptor.py:257-263), unclamped:
+    half-side 2*max(bbox w, bbox h) about the (shifted) bbox centre of the union mask."""
+    bigger = mask_3d if mask_3d.ndim == 2 else np.any(mask_3d, axis=-1)   # union over slices (:257)
+    xmin, ymin, xmax, ymax = extract_coords(bigger, margin=2)
+    crop_size = max(xmax - xmin, ymax - ymin) * 2
+    xmid, ymid = int(xmin + (xmax - xmin) / 2), int(ymin + (ymax - ymin) / 2)
+    return xmid - crop_size, ymid - crop_size, xmid + crop_size, ymid + crop_size

@@ -1,0 +1,164 @@
+"""Plain ViT backbone (ViT-S/16, ViT-B/16, ViT-L/14 of BASELINE.json) whose forward pass runs
+entirely in libvdr.so kernels.
+
+Replaces the backbone call of the reference, ``model.image_encoder(img_tensor)``
+(src/tfds_dense_descriptor.py:123), and produces what ``get_dense_descriptor`` returns
+(:124-133): per-slice dense descriptor maps (H/p, W/p, D), patch tokens only.
+
+Weights live in an ordinary state-dict (timm / DINOv2 key names, fp32) so checkpoints stay
+interchangeable; ``prepare()`` makes the bf16 operand copies the tcgen05 GEMMs read.  Activations
+are bf16 with fp32 accumulation; the final LayerNorm writes fp32 descriptors.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+VIT_CONFIGS = {
+    "vit_s16": dict(dim=384, depth=12, heads=6, patch=16),
+    "vit_b16": dict(dim=768, depth=12, heads=12, patch=16),
+    "vit_l14": dict(dim=1024, depth=24, heads=16, patch=14),
+    "vit_t16": dict(dim=128, depth=2, heads=2, patch=16),   # tiny, for tests
+}
+
+
+def init_vit_state_dict(cfg: dict, img_hw, seed: int = 1234) -> dict:
+    """Seeded random init (no checkpoints are available offline): trunc_normal(0.02) weights,
+    LayerNorm gamma ~ 1, small biases.  Same law as the oracle's init so parity tests can share it."""
+    g = torch.Generator().manual_seed(seed)
+    d, L, p = cfg["dim"], cfg["depth"], cfg["patch"]
+    n_tok = (img_hw[0] // p) * (img_hw[1] // p) + 1
+
+    def tn(*shape, std=0.02):
+        t = torch.empty(*shape, dtype=torch.float32)
+        torch.nn.init.trunc_normal_(t, std=std, a=-2 * std, b=2 * std, generator=g)
+        return t
+
+    w = {"patch_embed.weight": tn(d, 3, p, p), "patch_embed.bias": tn(d, std=0.01),
+         "cls_token": tn(1, 1, d), "pos_embed": tn(1, n_tok, d),
+         "norm.weight": 1.0 + tn(d, std=0.05), "norm.bias": tn(d, std=0.01)}
+    for i in range(L):
+        b = f"blocks.{i}."
+        w[b + "norm1.weight"] = 1.0 + tn(d, std=0.05)
+        w[b + "norm1.bias"] = tn(d, std=0.01)
+        w[b + "attn.qkv.weight"] = tn(3 * d, d)
+        w[b + "attn.qkv.bias"] = tn(3 * d, std=0.01)
+        w[b + "attn.proj.weight"] = tn(d, d)
+        w[b + "attn.proj.bias"] = tn(d, std=0.01)
+        w[b + "norm2.weight"] = 1.0 + tn(d, std=0.05)
+        w[b + "norm2.bias"] = tn(d, std=0.01)
+        w[b + "mlp.fc1.weight"] = tn(4 * d, d)
+        w[b + "mlp.fc1.bias"] = tn(4 * d, std=0.01)
+        w[b + "mlp.fc2.weight"] = tn(d, 4 * d)
+        w[b + "mlp.fc2.bias"] = tn(d, std=0.01)
+    return w
+
+
+class ViTBackbone:
+    """Holds device weights + workspaces and runs the forward pass through the C ABI."""
+
+    def __init__(self, name: str, img_hw=(512, 512), state_dict: dict | None = None, device="cuda:0",
+                 seed: int = 1234):
+        if name not in VIT_CONFIGS:
+            raise ValueError(f"unknown backbone {name!r}; choose from {sorted(VIT_CONFIGS)}")
+        self.model_name = name
+        self.cfg = dict(VIT_CONFIGS[name])
+        self.img_hw = (int(img_hw[0]), int(img_hw[1]))
+        p = self.cfg["patch"]
+        if self.img_hw[0] % p or self.img_hw[1] % p:
+            raise ValueError(f"image size {self.img_hw} is not a multiple of the patch size {p}")
+        self.grid = (self.img_hw[0] // p, self.img_hw[1] // p)
+        self.n_patches = self.grid[0] * self.grid[1]
+        self.n_tokens = self.n_patches + 1
+        self.device = torch.device(device)
+        self.state_dict_f32 = state_dict if state_dict is not None else init_vit_state_dict(self.cfg, self.img_hw, seed)
+        self._ws: dict = {}
+        self.prepare()
+
+    # -- weights -----------------------------------------------------------------------------
+    def prepare(self):
+        sd, dev, d, p = self.state_dict_f32, self.device, self.cfg["dim"], self.cfg["patch"]
+        if sd["pos_embed"].shape[1] != self.n_tokens:
+            raise ValueError(f"pos_embed has {sd['pos_embed'].shape[1]} tokens, image needs {self.n_tokens}")
+        K = 3 * p * p
+        ldk = (K + 7) // 8 * 8
+        w_pe = torch.zeros(d, ldk, dtype=torch.bfloat16, device=dev)
+        w_pe[:, :K] = sd["patch_embed.weight"].reshape(d, K).to(dev).bfloat16()
+        f32 = lambda k: sd[k].to(dev, torch.float32).contiguous()   # noqa: E731
+        bf = lambda k: sd[k].to(dev).bfloat16().contiguous()        # noqa: E731
+        self.w = dict(pe_w=w_pe, pe_b=f32("patch_embed.bias"), cls=f32("cls_token").reshape(d),
+                      pos=f32("pos_embed").reshape(self.n_tokens, d),
+                      norm_w=f32("norm.weight"), norm_b=f32("norm.bias"), blocks=[])
+        for i in range(self.cfg["depth"]):
+            b = f"blocks.{i}."
+            self.w["blocks"].append(dict(
+                n1w=f32(b + "norm1.weight"), n1b=f32(b + "norm1.bias"),
+                qkv_w=bf(b + "attn.qkv.weight"), qkv_b=f32(b + "attn.qkv.bias"),
+                proj_w=bf(b + "attn.proj.weight"), proj_b=f32(b + "attn.proj.bias"),
+                n2w=f32(b + "norm2.weight"), n2b=f32(b + "norm2.bias"),
+                fc1_w=bf(b + "mlp.fc1.weight"), fc1_b=f32(b + "mlp.fc1.bias"),
+                fc2_w=bf(b + "mlp.fc2.weight"), fc2_b=f32(b + "mlp.fc2.bias")))
+        self.K, self.ldk = K, ldk
+
+    def _workspace(self, B: int) -> dict:
+        ws = self._ws.get(B)
+        if ws is None:
+            d, N, dev = self.cfg["dim"], self.n_tokens, self.device
+            bf = torch.bfloat16
+            ws = dict(A=torch.empty(B * self.n_patches, self.ldk, dtype=bf, device=dev),
+                      X=torch.empty(B * N, d, dtype=bf, device=dev),
+                      Y=torch.empty(B * N, d, dtype=bf, device=dev),
+                      QKV=torch.empty(B * N, 3 * d, dtype=bf, device=dev),
+                      H=torch.empty(B * N, 4 * d, dtype=bf, device=dev),
+                      OUT=torch.empty(B * N, d, dtype=torch.float32, device=dev))
+            self._ws = {B: ws}   # keep one batch size resident
+        return ws
+
+    # -- forward -----------------------------------------------------------------------------
+    def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
+        """src: f32 CUDA storage holding B images of self.img_hw addressed by element `strides`
+        (batch, channel, row, col).  Returns the final-LayerNorm token matrix (B*N, d) f32
+        (row b*N is the CLS token, rows b*N+1.. the patch tokens in (py, px) order)."""
+        cfg, w, ws = self.cfg, self.w, self._workspace(B)
+        d, heads, N, Np = cfg["dim"], cfg["heads"], self.n_tokens, self.n_patches
+        H, W = self.img_hw
+        ops.im2col_patches(src, strides, B, H, W, cfg["patch"], out=ws["A"])
+        # patch embedding GEMM: bias + pos-embed fused, rows written behind each image's CLS row
+        ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=ws["X"], k=self.K,
+                 out_group=(Np, N, 1), res_mod=(Np, 1))
+        ops.write_cls_rows(w["cls"], w["pos"], ws["X"], B, N, d)
+        X, Y, QKV, Hb = ws["X"], ws["Y"], ws["QKV"], ws["H"]
+        scale = 1.0 / math.sqrt(64)
+        for blk in w["blocks"]:
+            ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
+            ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=QKV)
+            ops.flash_attn(QKV, B, N, heads, scale, out=Y)
+            ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X)
+            ops.layernorm(X, blk["n2w"], blk["n2b"], 1e-6, out=Y)
+            ops.gemm(Y, blk["fc1_w"], blk["fc1_b"], epilogue="gelu", out=Hb)
+            ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X)
+        ops.layernorm(X, w["norm_w"], w["norm_b"], 1e-6, out=ws["OUT"])
+        return ws["OUT"]
+
+    def dense_descriptors(self, images: torch.Tensor) -> torch.Tensor:
+        """images (B, 3, H, W) or (B, H, W) f32 CUDA -> (B, H/p, W/p, d) f32 (a copy)."""
+        if images.dim() == 3:
+            B = images.shape[0]
+            strides = (images.stride(0), 0, images.stride(1), images.stride(2))
+        else:
+            B = images.shape[0]
+            strides = images.stride()
+        if tuple(images.shape[-2:]) != self.img_hw:
+            raise ValueError(f"expected images of {self.img_hw}, got {tuple(images.shape[-2:])}")
+        tok = self.forward_tokens(images, strides, B)
+        d = self.cfg["dim"]
+        return tok.view(B, self.n_tokens, d)[:, 1:, :].reshape(B, self.grid[0], self.grid[1], d)
+
+    def flops_per_slice(self) -> float:
+        """F = 2*Np*3p^2*d + L*(24*N*d^2 + 4*N^2*d)."""
+        d, L, p = self.cfg["dim"], self.cfg["depth"], self.cfg["patch"]
+        N, Np = self.n_tokens, self.n_patches
+        return 2.0 * Np * 3 * p * p * d + L * (24.0 * N * d * d + 4.0 * N * N * d)
