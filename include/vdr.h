@@ -85,6 +85,15 @@ int vdr_gemm(const vdr_gemm_args* args, vdr_stream_t stream);
 int vdr_im2col_patches(const float* src, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                        int B, int H, int W, int patch, void* A_bf16, vdr_stream_t stream);
 
+/* Batched slice staging for a whole volume: (H, W, S) f32 (slice index fastest, the np.dstack layout of
+ * get_voxels, tfds_dense_descriptor.py:353-362) -> (S, ch, cw) bf16 slices of the crop window
+ * [y0, y0+ch) x [x0, x0+cw) (crop_image, :265), transposed through shared memory so reads and writes are
+ * both coalesced; then im2col of those gray slices with the 3 channels replicated (gray2rgb, :41). */
+int vdr_volume_to_slices(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw,
+                         void* slices_bf16, vdr_stream_t stream);
+int vdr_im2col_gray_bf16(const void* slices_bf16, int B, int H, int W, int patch, void* A_bf16,
+                         vdr_stream_t stream);
+
 /* CLS rows of the token matrix: X[b*N + 0, :] = cls[:] + pos[0, :]   (f32 params -> bf16 tokens) */
 int vdr_write_cls_rows(const float* cls, const float* pos0, void* X_bf16, int B, int N, int d,
                        vdr_stream_t stream);

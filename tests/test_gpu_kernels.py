@@ -126,3 +126,21 @@ def test_im2col_bit_exact(cuda):
         ref = torch.nn.functional.unfold(img.contiguous(), kernel_size=p, stride=p).transpose(1, 2).reshape(-1, 3 * p * p)
         K = 3 * p * p
         assert torch.equal(A[:, :K].float(), ref.bfloat16().float()) and (A[:, K:] == 0).all()
+
+
+def test_volume_staging_and_gray_im2col(cuda):
+    """(H, W, S) f32 volume -> crop -> (S, ch, cw) bf16 slices -> im2col with replicated channels
+    == unfold of gray2rgb(crop) (prepare_image + patch-embed data movement), bit-exact in bf16."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(6)
+    for (H, W, S, crop, p) in [(64, 64, 5, (0, 64, 0, 64), 16), (80, 72, 37, (8, 72, 4, 68), 16), (60, 70, 3, (2, 58, 0, 70), 14)]:
+        vol = torch.rand(H, W, S, device=cuda)
+        y0, y1, x0, x1 = crop
+        sl = ops.volume_to_slices(vol, crop)
+        want = vol[y0:y1, x0:x1].permute(2, 0, 1).contiguous()
+        assert torch.equal(sl.float(), want.bfloat16().float())
+        A = ops.im2col_gray_bf16(sl, p)
+        ref = torch.nn.functional.unfold(want[:, None].expand(-1, 3, -1, -1).contiguous(), kernel_size=p, stride=p)
+        ref = ref.transpose(1, 2).reshape(-1, 3 * p * p)
+        K = 3 * p * p
+        assert torch.equal(A[:, :K].float(), ref.bfloat16().float()) and (A[:, K:] == 0).all()

@@ -101,7 +101,7 @@ template <bool FEAT_BF16>
 __global__ void __launch_bounds__(kGThreads)
 g1_scatter_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int D,
                   const int32_t* __restrict__ tile_offsets, float* __restrict__ out_tok,
-                  int32_t* __restrict__ out_src, int cap, G1Pe pe) {
+                  int32_t* __restrict__ out_src, int cap, G1Pe pe, bool vec_ok) {
   __shared__ int s_cnt[kIters * 8];
   __shared__ int s_off[kIters * 8 + 1];
   __shared__ int s_sel[kTile];
@@ -165,36 +165,46 @@ g1_scatter_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int 
       z = __dadd_rn(__dsub_rn(__dmul_rn(static_cast<double>(k), pe.res2), pe.mean_z), pe.noise2);
     }
     const int64_t src_row = static_cast<int64_t>(k) * g.feat_slice_rows + g.feat_row0 + a * g.feat_row_pitch + b;
-    for (int c0 = lane * 8; c0 < D; c0 += 256) {
-      float f[8];
-      if (FEAT_BF16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(feat) + src_row * ld_feat + c0);
-        const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
-        f[0] = p0.x; f[1] = p0.y; f[2] = p1.x; f[3] = p1.y; f[4] = p2.x; f[5] = p2.y; f[6] = p3.x; f[7] = p3.y;
-      } else {
-        const float* fp = static_cast<const float*>(feat) + src_row * ld_feat + c0;
-        const float4 u0 = *reinterpret_cast<const float4*>(fp), u1 = *reinterpret_cast<const float4*>(fp + 4);
-        f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
+    auto pe_add = [&](float f, int col) -> float {
+      int jj;
+      double v;
+      if (col < third) { jj = col; v = x; }
+      else if (col < two_third) { jj = col - third; v = y; }
+      else { jj = col - two_third; v = z; }
+      if (jj < npair2) {
+        const double arg = v / pe.div[jj >> 1];
+        const double enc = (jj & 1) ? cos(arg) : sin(arg);
+        return static_cast<float>(__dadd_rn(static_cast<double>(f), __dmul_rn(enc, pe.scale)));
       }
-      if (pe.scale != 0.) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int col = c0 + i;
-          int jj;
-          double v;
-          if (col < third) { jj = col; v = x; }
-          else if (col < two_third) { jj = col - third; v = y; }
-          else { jj = col - two_third; v = z; }
-          if (jj < npair2) {
-            const double arg = v / pe.div[jj >> 1];
-            const double enc = (jj & 1) ? cos(arg) : sin(arg);
-            f[i] = static_cast<float>(__dadd_rn(static_cast<double>(f[i]), __dmul_rn(enc, pe.scale)));
-          }
+      return static_cast<float>(static_cast<double>(f));
+    };
+    if (vec_ok) {
+      for (int c0 = lane * 8; c0 < D; c0 += 256) {
+        float f[8];
+        if (FEAT_BF16) {
+          const uint4 v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(feat) + src_row * ld_feat + c0);
+          const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
+          f[0] = p0.x; f[1] = p0.y; f[2] = p1.x; f[3] = p1.y; f[4] = p2.x; f[5] = p2.y; f[6] = p3.x; f[7] = p3.y;
+        } else {
+          const float* fp = static_cast<const float*>(feat) + src_row * ld_feat + c0;
+          const float4 u0 = *reinterpret_cast<const float4*>(fp), u1 = *reinterpret_cast<const float4*>(fp + 4);
+          f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
         }
+        if (pe.scale != 0.) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = pe_add(f[i], c0 + i);
+        }
+        float* op = out_tok + row_out * D + c0;
+        *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
       }
-      float* op = out_tok + row_out * D + c0;
-      *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-      *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {  // any D / alignment: one element per lane
+      for (int c = lane; c < D; c += 32) {
+        float f = FEAT_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(feat)[src_row * ld_feat + c])
+                            : static_cast<const float*>(feat)[src_row * ld_feat + c];
+        if (pe.scale != 0.) f = pe_add(f, c);
+        out_tok[row_out * D + c] = f;
+      }
     }
   }
 }
@@ -288,8 +298,9 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   VDR_CHECK_ARG(feat && mask && row_map && col_map && out_tok && out_src && out_count && workspace, VDR_EINVAL, "vdr_mask_gather: null pointer");
   VDR_CHECK_ARG(S > 0 && h > 0 && w > 0 && D > 0 && cap >= 0, VDR_EINVAL, "vdr_mask_gather: bad shape");
   VDR_CHECK_ARG(feat_slice_rows >= 0 && feat_row_pitch >= w && feat_row0 >= 0 && mask_slice_stride >= 0 && mask_row_stride >= 0, VDR_EINVAL, "vdr_mask_gather: bad strides");
-  VDR_CHECK_ARG(D % 8 == 0 && ld_feat % 8 == 0 && ld_feat >= D, VDR_EALIGN, "vdr_mask_gather: D (%d) and ld_feat must be multiples of 8", D);
-  VDR_CHECK_ARG(aligned16(feat) && aligned16(out_tok), VDR_EALIGN, "vdr_mask_gather: feat/out_tok must be 16-byte aligned");
+  VDR_CHECK_ARG(ld_feat >= D, VDR_EINVAL, "vdr_mask_gather: ld_feat (%lld) smaller than D (%d)", (long long)ld_feat, D);
+  // 16-byte vector path when the rows allow it; otherwise an element-wise path (any D, e.g. the reference's D = 12 tests)
+  const bool vec_ok = D % 8 == 0 && ld_feat % 8 == 0 && aligned16(feat) && aligned16(out_tok);
   VDR_CHECK_ARG(feat_dtype == VDR_DTYPE_BF16 || feat_dtype == VDR_DTYPE_F32, VDR_EINVAL, "vdr_mask_gather: bad feat_dtype");
   VDR_CHECK_ARG((int64_t)S * h * w < 0x7fffffffLL, VDR_EINVAL, "vdr_mask_gather: too many candidates");
   VDR_CHECK_ARG(workspace_bytes >= vdr_mask_gather_workspace_bytes(S, h, w), VDR_EWORKSPACE, "vdr_mask_gather: workspace too small (%zu < %zu)", workspace_bytes, vdr_mask_gather_workspace_bytes(S, h, w));
@@ -313,9 +324,9 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   tile_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, tiles, out_count);
   VDR_CHECK_LAUNCH("tile_scan_kernel");
   if (feat_dtype == VDR_DTYPE_BF16)
-    g1_scatter_kernel<true><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe);
+    g1_scatter_kernel<true><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe, vec_ok);
   else
-    g1_scatter_kernel<false><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe);
+    g1_scatter_kernel<false><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe, vec_ok);
   count_launch(3);
   VDR_CHECK_LAUNCH("g1_scatter_kernel");
   return VDR_OK;

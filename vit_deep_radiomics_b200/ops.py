@@ -98,6 +98,35 @@ def im2col_patches(src: torch.Tensor, strides, B: int, H: int, W: int, patch: in
     return out
 
 
+def volume_to_slices(vol: torch.Tensor, crop, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(H, W, S) f32 volume -> (S, ch, cw) bf16 slices of the crop window (y0, y1, x0, x1)."""
+    _req(vol, torch.float32, "vol")
+    if vol.dim() != 3 or not vol.is_contiguous():
+        raise ValueError("vol must be a contiguous (H, W, S) tensor")
+    H, W, S = vol.shape
+    y0, y1, x0, x1 = (int(v) for v in crop)
+    if out is None:
+        out = torch.empty((S, y1 - y0, x1 - x0), dtype=torch.bfloat16, device=vol.device)
+    _C.check(_C.lib().vdr_volume_to_slices(vol.data_ptr(), H, W, S, y0, x0, y1 - y0, x1 - x0, out.data_ptr(), _stream()),
+             "vdr_volume_to_slices")
+    return out
+
+
+def im2col_gray_bf16(slices: torch.Tensor, patch: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(B, H, W) bf16 gray slices -> A[(b,py,px),(c,iy,ix)] bf16 with the 3 channels replicated."""
+    _req(slices, torch.bfloat16, "slices")
+    if slices.dim() != 3 or not slices.is_contiguous():
+        raise ValueError("slices must be a contiguous (B, H, W) tensor")
+    B, H, W = slices.shape
+    K = 3 * patch * patch
+    ldk = (K + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((B * (H // patch) * (W // patch), ldk), dtype=torch.bfloat16, device=slices.device)
+    _C.check(_C.lib().vdr_im2col_gray_bf16(slices.data_ptr(), B, H, W, patch, out.data_ptr(), _stream()),
+             "vdr_im2col_gray_bf16")
+    return out
+
+
 def write_cls_rows(cls: torch.Tensor, pos0: torch.Tensor, x: torch.Tensor, B: int, N: int, d: int) -> None:
     _req(cls, torch.float32, "cls"), _req(pos0, torch.float32, "pos0"), _req(x, torch.bfloat16, "x")
     _C.check(_C.lib().vdr_write_cls_rows(cls.data_ptr(), pos0.data_ptr(), x.data_ptr(), B, N, d, _stream()),

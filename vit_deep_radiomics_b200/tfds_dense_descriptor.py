@@ -101,6 +101,8 @@ def _forward_volume(model, img_dev, plan, max_batch=None):
         strides = (view.stride(2), 0, view.stride(0), view.stride(1))
     else:
         strides = (view.stride(2), view.stride(3), view.stride(0), view.stride(1))
+    if img_dev.dim() == 3 and img_dev.is_contiguous() and (max_batch is None or max_batch >= S):
+        return model.forward_volume(img_dev, plan["crop"])          # coalesced slice staging + bf16 im2col
     if max_batch is None or max_batch >= S:
         return model.forward_tokens(view, strides, S)
     outs = []

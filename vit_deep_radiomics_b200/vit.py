@@ -118,14 +118,29 @@ class ViTBackbone:
         return ws
 
     # -- forward -----------------------------------------------------------------------------
+    def forward_volume(self, vol: torch.Tensor, crop) -> torch.Tensor:
+        """vol: (H, W, S) f32 CUDA volume (np.dstack layout), crop = (y0, y1, x0, x1) of size self.img_hw.
+        All S slices go through the backbone as one batch; returns the (S*N, d) f32 token matrix."""
+        S = vol.shape[2]
+        ws = self._workspace(S)
+        if "SL" not in ws:
+            ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
+        ops.volume_to_slices(vol, crop, out=ws["SL"])
+        ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=ws["A"])
+        return self._encode(S)
+
     def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
         """src: f32 CUDA storage holding B images of self.img_hw addressed by element `strides`
         (batch, channel, row, col).  Returns the final-LayerNorm token matrix (B*N, d) f32
         (row b*N is the CLS token, rows b*N+1.. the patch tokens in (py, px) order)."""
+        H, W = self.img_hw
+        ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"], out=self._workspace(B)["A"])
+        return self._encode(B)
+
+    def _encode(self, B: int) -> torch.Tensor:
+        """Patch-embedding GEMM + transformer blocks + final LayerNorm over the im2col matrix in ws['A']."""
         cfg, w, ws = self.cfg, self.w, self._workspace(B)
         d, heads, N, Np = cfg["dim"], cfg["heads"], self.n_tokens, self.n_patches
-        H, W = self.img_hw
-        ops.im2col_patches(src, strides, B, H, W, cfg["patch"], out=ws["A"])
         # patch embedding GEMM: bias + pos-embed fused, rows written behind each image's CLS row
         ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=ws["X"], k=self.K,
                  out_group=(Np, N, 1), res_mod=(Np, 1))
