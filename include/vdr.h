@@ -57,7 +57,8 @@ uint64_t    vdr_launch_count(void);
  * Row remapping (used to write patch tokens behind the CLS token and to add pos-embed):
  *   out_row(m) = (out_group > 0) ? (m / out_group) * out_group_stride + out_offset + m % out_group : m
  *   res_row(m) = (res_mod   > 0) ? res_offset + m % res_mod : out_row(m)
- * Requirements: N % 8 == 0, lda/ldw/ldc/ldr % 8 == 0, 16-byte aligned pointers.  K is arbitrary
+ * Requirements: lda/ldw/ldc/ldr % 8 == 0, 16-byte aligned pointers.  N is arbitrary (a ragged last
+ *   column group is stored element-wise) and K is arbitrary
  *   (the K tail is zero-filled by TMA), e.g. K = 588 for 14x14 patches with lda = ldw = 592.
  */
 typedef struct {
@@ -180,6 +181,36 @@ int vdr_voxel_bbox(const uint8_t* mask, int H, int W, int S, int32_t* bbox, vdr_
 int vdr_voxel_gather(const float* img, const uint8_t* mask, int H, int W, int S, const int32_t* bbox,
                      int32_t* out_flat, float* out_raw, uint8_t* out_mask, int32_t* out_count, int cap,
                      vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training-only kernels of the point-cloud classifier (backward of models_archs.py:141-147 as driven by
+ * loss.backward() at train_models.py:683).  dgrad / wgrad reuse vdr_gemm on transposed operands.
+ */
+/* h = gelu_erf(z), dz = dh * gelu'(z); bf16, n elements (n % 8 == 0). */
+int vdr_gelu_fwd(const void* z, void* h, int64_t n, vdr_stream_t stream);
+int vdr_gelu_bwd(const void* dh, const void* z, void* dz, int64_t n, vdr_stream_t stream);
+/* out (cols, rows; pitch ld_out) = in (rows, cols; pitch ld_in)^T, bf16, through a shared-memory tile. */
+int vdr_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols,
+                       vdr_stream_t stream);
+/* out_accum[c] += sum_r in[r][c]  (bias gradients; bf16 in, f32 accumulate). */
+int vdr_colsum_bf16(const void* in, int64_t ld, int rows, int cols, float* out_accum, vdr_stream_t stream);
+/* Attention backward pieces (scores materialised per head; N <= ~16k tokens in this model):
+ *   delta[h][i] = sum_c dO[i][h*64+c] * O[i][h*64+c]
+ *   P = exp(S*scale - lse) (0 for key columns >= N),  dS = P * (dP - delta) * scale     (S, dP f32; P, dS bf16) */
+int vdr_attn_delta(const void* dO, const void* O, int64_t ld, int N, int heads, float* delta, vdr_stream_t stream);
+int vdr_attn_p_ds(const float* S, const float* dP, const float* lse, const float* delta, void* P, void* dS,
+                  int N, int64_t ldp, float scale, vdr_stream_t stream);
+/* Backward of vdr_cls_concat_layernorm_fwd: accumulates dgamma, dbeta and dcls (the point cloud X is data). */
+int vdr_cls_concat_layernorm_bwd(const void* dY, const float* X, const float* cls, const float* gamma,
+                                 const float* mean, const float* rstd, float* dgamma, float* dbeta, float* dcls,
+                                 int n, int d, vdr_stream_t stream);
+/* Classification head MLPLayer (models_archs.py:186-200): zc = W1 cls + b1, logits = W2 gelu(zc) + b2, and its
+ * backward (accumulates dW1, db1, dW2, db2; writes dcls = W1^T dzc + dcls_in).  Single CTA, f32 weights. */
+int vdr_cls_head_fwd(const void* cls_bf16, const float* W1, const float* b1, const float* W2, const float* b2,
+                     float* zc, float* logits, int d, int H1, int C, vdr_stream_t stream);
+int vdr_cls_head_bwd(const void* cls_bf16, const float* W1, const float* W2, const float* zc, const float* dlogits,
+                     const float* dcls_in, float* dW1, float* db1, float* dW2, float* db2, float* dcls,
+                     int d, int H1, int C, vdr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,8 @@ def test_g1_cap_and_bf16(cuda):
 def test_g2_golden(cuda, golden_dir, name):
     from vit_deep_radiomics_b200 import create_pointcloud_dataframe as pcd
     g = np.load(os.path.join(golden_dir, "pointcloud_g2.npz"))
-    img, mask, res = g[f"{name}__img"], g[f"{name}__mask"], g[f"{name}__res"]
+    img, res = g[f"{name}__img"], g[f"{name}__res"]
+    mask = g[f"{name}__mask"].reshape(img.shape)          # stored flattened (the DataFrame column)
     df = pcd.to_pointcloud_df(img, mask, 1, res)
     for col in ("x", "y", "z", "raw", "mask", "mask_box"):
         assert np.array_equal(df[col].values, g[f"{name}__{col}"]), col

@@ -22,6 +22,8 @@ EXPORTS = (
     "vdr_flash_attn_fwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather",
     "vdr_voxel_bbox", "vdr_voxel_gather",
+    "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
+    "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
 )
 
 
@@ -75,6 +77,15 @@ def lib() -> C.CDLL:
                                   vp, vp, vp, i32, f64, vp, C.POINTER(f64), vp, sz, vp]
     L.vdr_voxel_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_voxel_gather.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
+    L.vdr_gelu_fwd.argtypes = [vp, vp, i64, vp]
+    L.vdr_gelu_bwd.argtypes = [vp, vp, vp, i64, vp]
+    L.vdr_transpose_bf16.argtypes = [vp, i64, vp, i64, i32, i32, vp]
+    L.vdr_colsum_bf16.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.vdr_attn_delta.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+    L.vdr_attn_p_ds.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, f32, vp]
+    L.vdr_cls_concat_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    L.vdr_cls_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    L.vdr_cls_head_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("vdr_version", "vdr_last_error_string", "vdr_launch_count",

@@ -1,4 +1,4 @@
-"""Forward/backward of the point-cloud classifier through libvdr kernels (SURVEY.md rows M1, K9-K11).
+"""Forward/backward of the point-cloud classifier through libvdr kernels (SURVEY.md rows M1, K9-K12).
 
 One ``torch.autograd.Function`` covers the whole network so that the saved activations and the
 hand-written backward chain stay in one place.  Layer arithmetic (post-norm encoder layer of
@@ -13,43 +13,45 @@ src/models_archs.py:130-147):
                 h   = gelu(y1 W_1^T + b_1)                 tcgen05 GEMM (bias+GELU epilogue)
                 u   = h W_2^T + b_2 + y1                   tcgen05 GEMM (bias+residual epilogue)
                 y   = LN2(u)
-    cls = y[0];  logits = gelu(cls W_d1^T + b_d1) W_d2^T + b_d2
+    cls = y[0];  logits = W_d2 gelu(W_d1 cls + b_d1) + b_d2        fused head kernel (fp32)
+
+Backward: dgrad / wgrad are the same tcgen05 GEMM on transposed operands (transpose kernel), bias
+grads are column sums, LayerNorm / GELU have their own backward kernels, and the attention backward
+recomputes P from the saved log-sum-exp with the score matrices materialised per head
+(N <= ~16k tokens here: N^2 bf16 is at most a few hundred MB of the 180 GB HBM).
 """
 from __future__ import annotations
+
+import math
 
 import torch
 
 from . import ops
 
-#: weakly-keyed cache of bf16 operand copies: param id -> (version, tensor)
-_BF16_CACHE: dict = {}
+#: cache of bf16 operand copies: (param id, tag) -> (version, tensor); refreshed when the optimizer steps
+_CACHE: dict = {}
 
 
-def _bf16(p: torch.Tensor, pad_rows_to: int | None = None) -> torch.Tensor:
-    """bf16 copy of a weight, refreshed only when the parameter changed (optimizer step)."""
-    key = (id(p), pad_rows_to)
-    hit = _BF16_CACHE.get(key)
+def _cached(p: torch.Tensor, tag: str, make):
+    key = (id(p), tag)
+    hit = _CACHE.get(key)
     if hit is not None and hit[0] == p._version and hit[1].device == p.device:
         return hit[1]
-    w = p.detach()
-    if pad_rows_to is not None and w.shape[0] < pad_rows_to:
-        wp = torch.zeros((pad_rows_to,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
-        wp[: w.shape[0]] = w
-        w = wp
-    w = w.to(torch.bfloat16).contiguous()
-    _BF16_CACHE[key] = (p._version, w)
-    return w
+    val = make(p.detach())
+    _CACHE[key] = (p._version, val)
+    return val
 
 
-def _f32_padded(p: torch.Tensor, n: int) -> torch.Tensor:
-    key = (id(p), "f32pad", n)
-    hit = _BF16_CACHE.get(key)
-    if hit is not None and hit[0] == p._version and hit[1].device == p.device:
-        return hit[1]
-    out = torch.zeros(n, dtype=torch.float32, device=p.device)
-    out[: p.shape[0]] = p.detach()
-    _BF16_CACHE[key] = (p._version, out)
-    return out
+def _bf16(p):      # (out, in) bf16: forward operand
+    return _cached(p, "bf16", lambda w: w.to(torch.bfloat16).contiguous())
+
+
+def _bf16_t(p):    # (in, out) bf16: dgrad operand
+    return _cached(p, "bf16_t", lambda w: w.t().to(torch.bfloat16).contiguous())
+
+
+def _f32(p):
+    return p.detach().contiguous()
 
 
 def classifier_forward(x, num_heads, num_layers, params, save=False):
@@ -58,54 +60,125 @@ def classifier_forward(x, num_heads, num_layers, params, save=False):
     N = n + 1
     it = iter(params)
     cls_tok, norm_w, norm_b = next(it), next(it), next(it)
+    x = x.contiguous()
+    cls_vec = _f32(cls_tok).reshape(d)
     saved = {}
     if save:
-        y, mu0, rs0 = ops.cls_concat_layernorm(x.contiguous(), cls_tok.detach().reshape(d).contiguous(),
-                                               norm_w.detach(), norm_b.detach(), 1e-5, save_stats=True)
+        y, mu0, rs0 = ops.cls_concat_layernorm(x, cls_vec, _f32(norm_w), _f32(norm_b), 1e-5, save_stats=True)
         saved["ln0"] = (mu0, rs0)
     else:
-        y = ops.cls_concat_layernorm(x.contiguous(), cls_tok.detach().reshape(d).contiguous(), norm_w.detach(),
-                                     norm_b.detach(), 1e-5)
+        y = ops.cls_concat_layernorm(x, cls_vec, _f32(norm_w), _f32(norm_b), 1e-5)
     layers = []
     for _ in range(num_layers):
         (w_in, b_in, w_o, b_o, n1w, n1b, w1, b1, w2, b2, n2w, n2b) = (next(it) for _ in range(12))
-        qkv = ops.gemm(y, _bf16(w_in), b_in.detach())
+        qkv = ops.gemm(y, _bf16(w_in), _f32(b_in))
         if save:
             a, lse = ops.flash_attn(qkv, 1, N, num_heads, return_lse=True)
         else:
             a, lse = ops.flash_attn(qkv, 1, N, num_heads), None
-        t = ops.gemm(a, _bf16(w_o), b_o.detach(), epilogue="residual", residual=y)
+        t = ops.gemm(a, _bf16(w_o), _f32(b_o), epilogue="residual", residual=y)
         if save:
-            y1, mu1, rs1 = ops.layernorm(t, n1w.detach(), n1b.detach(), 1e-5, save_stats=True)
-            z = ops.gemm(y1, _bf16(w1), b1.detach())                       # pre-activation kept for GELU'
+            y1, mu1, rs1 = ops.layernorm(t, _f32(n1w), _f32(n1b), 1e-5, save_stats=True)
+            z = ops.gemm(y1, _bf16(w1), _f32(b1))                      # pre-activation kept for GELU'
             h = ops.gelu(z)
         else:
-            y1 = ops.layernorm(t, n1w.detach(), n1b.detach(), 1e-5)
-            h = ops.gemm(y1, _bf16(w1), b1.detach(), epilogue="gelu")
-        u = ops.gemm(h, _bf16(w2), b2.detach(), epilogue="residual", residual=y1)
+            y1 = ops.layernorm(t, _f32(n1w), _f32(n1b), 1e-5)
+            h = ops.gemm(y1, _bf16(w1), _f32(b1), epilogue="gelu")
+        u = ops.gemm(h, _bf16(w2), _f32(b2), epilogue="residual", residual=y1)
         if save:
-            y2, mu2, rs2 = ops.layernorm(u, n2w.detach(), n2b.detach(), 1e-5, save_stats=True)
+            y2, mu2, rs2 = ops.layernorm(u, _f32(n2w), _f32(n2b), 1e-5, save_stats=True)
             layers.append(dict(y_in=y, qkv=qkv, a=a, lse=lse, t=t, mu1=mu1, rs1=rs1, y1=y1, z=z, h=h, u=u,
                                mu2=mu2, rs2=rs2))
         else:
-            y2 = ops.layernorm(u, n2w.detach(), n2b.detach(), 1e-5)
+            y2 = ops.layernorm(u, _f32(n2w), _f32(n2b), 1e-5)
         y = y2
     wd1, bd1, wd2, bd2 = next(it), next(it), next(it), next(it)
-    cls_bf = y[0:1]                                                          # (1, d) bf16
-    C = wd2.shape[0]
-    Cp = (C + 7) // 8 * 8
+    logits, zc = ops.cls_head_fwd(y[0], _f32(wd1), _f32(bd1), _f32(wd2), _f32(bd2))
+    cls = y[0].float()
     if save:
-        zc = ops.gemm(cls_bf, _bf16(wd1), bd1.detach())
-        hc = ops.gelu(zc)
-        saved.update(zc=zc, hc=hc)
-    else:
-        hc = ops.gemm(cls_bf, _bf16(wd1), bd1.detach(), epilogue="gelu")
-    logits = ops.gemm(hc, _bf16(wd2, pad_rows_to=Cp), _f32_padded(bd2, Cp), out_dtype=torch.float32)[0, :C]
-    cls = cls_bf[0].float()
-    if save:
-        saved.update(layers=layers, y_last=y)
+        saved.update(layers=layers, y_last=y, zc=zc, x=x)
         return logits, cls, saved
     return logits, cls
+
+
+def attention_backward(qkv, a, da, lse, heads):
+    """dqkv (N, 3d) bf16 from da (N, d): per head, S and dP are materialised in f32, P and dS in bf16."""
+    N, d3 = qkv.shape
+    d = d3 // 3
+    Np = (N + 7) // 8 * 8
+    dev = qkv.device
+    scale = 1.0 / math.sqrt(64)
+    dqkv = torch.empty((N, d3), dtype=torch.bfloat16, device=dev)
+    delta = ops.attn_delta(da, a, heads)
+    S = torch.empty((N, Np), dtype=torch.float32, device=dev)
+    dP = torch.empty((N, Np), dtype=torch.float32, device=dev)
+    for h in range(heads):
+        q, k, v = (qkv[:, o + h * 64:o + (h + 1) * 64] for o in (0, d, 2 * d))
+        do = da[:, h * 64:(h + 1) * 64]
+        ops.gemm(q, k, out=S[:, :N])                                   # S = Q K^T
+        ops.gemm(do, v, out=dP[:, :N])                                 # dP = dO V^T
+        P, dS = ops.attn_p_ds(S, dP, lse[0, h], delta[h], N, scale)    # P = softmax, dS = P (dP - delta) / 8
+        do_t = ops.transpose(do)                                       # (64, N)
+        ops.gemm(ops.transpose(P[:, :N]), do_t, out=dqkv[:, 2 * d + h * 64:2 * d + (h + 1) * 64])   # dV = P^T dO
+        ops.gemm(ops.transpose(dS[:, :N]), ops.transpose(q), out=dqkv[:, d + h * 64:d + (h + 1) * 64])  # dK = dS^T Q
+        ops.gemm(dS[:, :N], ops.transpose(k), out=dqkv[:, h * 64:(h + 1) * 64])                      # dQ = dS K
+    return dqkv
+
+
+def classifier_backward(num_heads, num_layers, params, saved, d_logits, d_cls):
+    """Gradients for every parameter, in ``params`` order (f32)."""
+    dev = params[0].device
+    x = saved["x"]
+    n, d = x.shape
+    N = n + 1
+    g = [None] * len(params)
+
+    def zeros_like_param(i):
+        g[i] = torch.zeros(params[i].shape, dtype=torch.float32, device=dev)
+        return g[i]
+
+    # ---- head
+    iw1 = len(params) - 4
+    wd1, wd2 = params[iw1], params[iw1 + 2]
+    y_last = saved["y_last"]
+    dlog = d_logits.detach().float().contiguous() if d_logits is not None else torch.zeros(wd2.shape[0], device=dev)
+    dcls_in = d_cls.detach().float().contiguous() if d_cls is not None else None
+    dcls = ops.cls_head_bwd(y_last[0], _f32(wd1), _f32(wd2), saved["zc"], dlog, dcls_in,
+                            zeros_like_param(iw1), zeros_like_param(iw1 + 1), zeros_like_param(iw1 + 2),
+                            zeros_like_param(iw1 + 3))
+    dy = torch.zeros((N, d), dtype=torch.bfloat16, device=dev)          # only the CLS row carries gradient
+    dy[0] = dcls.to(torch.bfloat16)
+
+    # ---- encoder layers, last to first
+    for l in reversed(range(num_layers)):
+        base = 3 + 12 * l
+        (w_in, b_in, w_o, b_o, n1w, n1b, w1, b1, w2, b2, n2w, n2b) = params[base:base + 12]
+        s = saved["layers"][l]
+        du = ops.layernorm_bwd(dy, s["u"], _f32(n2w), s["mu2"], s["rs2"], zeros_like_param(base + 10), zeros_like_param(base + 11))
+        ops.colsum_accum(du, zeros_like_param(base + 9))
+        du_t = ops.transpose(du)
+        g[base + 8] = ops.gemm(du_t, ops.transpose(s["h"]), out_dtype=torch.float32)          # dW2 = du^T h
+        dh = ops.gemm(du, _bf16_t(w2))                                                         # dh = du W2
+        dz = ops.gelu_bwd(dh, s["z"])
+        ops.colsum_accum(dz, zeros_like_param(base + 7))
+        g[base + 6] = ops.gemm(ops.transpose(dz), ops.transpose(s["y1"]), out_dtype=torch.float32)   # dW1 = dz^T y1
+        dy1 = ops.gemm(dz, _bf16_t(w1), epilogue="residual", residual=du)                      # + residual branch
+        dt = ops.layernorm_bwd(dy1, s["t"], _f32(n1w), s["mu1"], s["rs1"], zeros_like_param(base + 4), zeros_like_param(base + 5))
+        ops.colsum_accum(dt, zeros_like_param(base + 3))
+        g[base + 2] = ops.gemm(ops.transpose(dt), ops.transpose(s["a"]), out_dtype=torch.float32)    # dWo = dt^T a
+        da = ops.gemm(dt, _bf16_t(w_o))
+        dqkv = attention_backward(s["qkv"], s["a"], da, s["lse"], num_heads)
+        ops.colsum_accum(dqkv, zeros_like_param(base + 1))
+        g[base] = ops.gemm(ops.transpose(dqkv), ops.transpose(s["y_in"]), out_dtype=torch.float32)   # dWin = dqkv^T y
+        dy = ops.gemm(dqkv, _bf16_t(w_in), epilogue="residual", residual=dt)
+
+    # ---- input LayerNorm + CLS token
+    mu0, rs0 = saved["ln0"]
+    g_cls = torch.zeros(d, dtype=torch.float32, device=dev)
+    ops.cls_concat_layernorm_bwd(dy, x, _f32(params[0]).reshape(d), _f32(params[1]), mu0, rs0,
+                                 zeros_like_param(1), zeros_like_param(2), g_cls)
+    g[0] = g_cls.reshape(params[0].shape)
+    return g
 
 
 class ClassifierFunction(torch.autograd.Function):
@@ -113,19 +186,14 @@ class ClassifierFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, num_heads, num_layers, *params):
-        need_grad = any(ctx.needs_input_grad[3:])
-        if not need_grad:
-            logits, cls = classifier_forward(x, num_heads, num_layers, params, save=False)
-            return logits, cls
         logits, cls, saved = classifier_forward(x, num_heads, num_layers, params, save=True)
         ctx.saved = saved
-        ctx.x = x
         ctx.params = params
         ctx.num_heads, ctx.num_layers = num_heads, num_layers
         return logits, cls
 
     @staticmethod
     def backward(ctx, d_logits, d_cls):
-        from .classifier_backward import classifier_backward
-        grads = classifier_backward(ctx.x, ctx.num_heads, ctx.num_layers, ctx.params, ctx.saved, d_logits, d_cls)
+        grads = classifier_backward(ctx.num_heads, ctx.num_layers, ctx.params, ctx.saved, d_logits, d_cls)
+        ctx.saved = None
         return (None, None, None) + tuple(grads)

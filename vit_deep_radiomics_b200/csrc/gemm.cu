@@ -159,7 +159,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int n = n0 + g * 8;
-            if (n < p.N) {
+            if (n + 8 <= p.N) {
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
@@ -195,6 +195,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float* cp = static_cast<float*>(p.C) + out_row * p.ldc + n;
                 *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
+            } else if (n < p.N) {   // ragged last column group (N % 8 != 0): element-wise
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (n + i < p.N) {
+                  float v = __uint_as_float(r[g * 8 + i]);
+                  if (p.bias != nullptr) v += __ldg(p.bias + n + i);
+                  if (p.epilogue == VDR_EPI_BIAS_GELU) v = gelu_erf(v);
+                  else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL)
+                    v += (p.r_dtype == VDR_DTYPE_BF16) ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.R)[res_row * p.ldr + n + i])
+                                                       : static_cast<const float*>(p.R)[res_row * p.ldr + n + i];
+                  if (p.c_dtype == VDR_DTYPE_BF16) static_cast<__nv_bfloat16*>(p.C)[out_row * p.ldc + n + i] = __float2bfloat16_rn(v);
+                  else static_cast<float*>(p.C)[out_row * p.ldc + n + i] = v;
+                }
               }
             }
           }
@@ -241,11 +255,11 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   VDR_CHECK_ARG(a != nullptr, VDR_EINVAL, "vdr_gemm: null args");
   VDR_CHECK_ARG(a->A && a->W && a->C, VDR_EINVAL, "vdr_gemm: null A/W/C");
   VDR_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, VDR_EINVAL, "vdr_gemm: non-positive shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  VDR_CHECK_ARG(a->N % 8 == 0, VDR_EINVAL, "vdr_gemm: N (%d) must be a multiple of 8", a->N);
   VDR_CHECK_ARG(a->lda >= a->K && a->ldw >= a->K && a->ldc >= a->N, VDR_EINVAL, "vdr_gemm: leading dimension smaller than row length");
   VDR_CHECK_ARG(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldc % 8 == 0, VDR_EALIGN, "vdr_gemm: lda/ldw/ldc must be multiples of 8 elements");
   VDR_CHECK_ARG(aligned16(a->A) && aligned16(a->W) && aligned16(a->C), VDR_EALIGN, "vdr_gemm: A/W/C must be 16-byte aligned");
   VDR_CHECK_ARG(a->bias == nullptr || aligned16(a->bias), VDR_EALIGN, "vdr_gemm: bias must be 16-byte aligned");
+  // N itself may be ragged (last column group handled element-wise); rows must still start 16-byte aligned.
   VDR_CHECK_ARG(a->epilogue >= VDR_EPI_BIAS && a->epilogue <= VDR_EPI_BIAS_RESIDUAL, VDR_EINVAL, "vdr_gemm: unknown epilogue %d", a->epilogue);
   VDR_CHECK_ARG(a->c_dtype == VDR_DTYPE_BF16 || a->c_dtype == VDR_DTYPE_F32, VDR_EINVAL, "vdr_gemm: bad c_dtype %d", a->c_dtype);
   if (a->epilogue == VDR_EPI_BIAS_RESIDUAL) {

@@ -89,9 +89,14 @@ class TransformerNoduleClassifier(nn.Module):
         The reference runs batch 1 (variable-length clouds, no padding); batches are looped."""
         if x.dim() != 3 or x.shape[2] != self.input_dim:
             raise ValueError(f"expected (batch, seq_len, {self.input_dim}), got {tuple(x.shape)}")
+        params = self.param_list()
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         logits, cls = [], []
         for b in range(x.shape[0]):
-            lg, c = ck.ClassifierFunction.apply(x[b], self.num_heads, self.num_layers, *self.param_list())
+            if train:
+                lg, c = ck.ClassifierFunction.apply(x[b], self.num_heads, self.num_layers, *params)
+            else:
+                lg, c = ck.classifier_forward(x[b], self.num_heads, self.num_layers, params)
             logits.append(lg)
             cls.append(c)
         return torch.stack(logits, 0), torch.stack(cls, 0)

@@ -318,3 +318,80 @@ def voxel_gather(img: torch.Tensor, mask_u8: torch.Tensor, bbox: torch.Tensor, c
                                        flat.data_ptr(), raw.data_ptr(), mk.data_ptr(), count.data_ptr(), cap,
                                        _stream()), "vdr_voxel_gather")
     return flat, raw, mk, count
+
+
+# ----------------------------------------------------------------------------- training-only kernels
+def gelu(z: torch.Tensor) -> torch.Tensor:
+    _req(z, torch.bfloat16, "z")
+    h = torch.empty_like(z)
+    _C.check(_C.lib().vdr_gelu_fwd(z.data_ptr(), h.data_ptr(), z.numel(), _stream()), "vdr_gelu_fwd")
+    return h
+
+
+def gelu_bwd(dh: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    dz = torch.empty_like(z)
+    _C.check(_C.lib().vdr_gelu_bwd(dh.data_ptr(), z.data_ptr(), dz.data_ptr(), z.numel(), _stream()), "vdr_gelu_bwd")
+    return dz
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """(rows, cols) bf16 (unit inner stride, any row pitch) -> (cols, rows) view of a buffer whose pitch is
+    rounded up to 8 elements, as the GEMM's TMA descriptors need."""
+    _req(x, torch.bfloat16, "x")
+    rows, cols = x.shape
+    ld = (rows + 7) // 8 * 8
+    buf = torch.empty((cols, ld), dtype=torch.bfloat16, device=x.device)
+    _C.check(_C.lib().vdr_transpose_bf16(x.data_ptr(), x.stride(0), buf.data_ptr(), ld, rows, cols, _stream()),
+             "vdr_transpose_bf16")
+    return buf[:, :rows]
+
+
+def colsum_accum(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[c] += sum_r x[r, c]   (x bf16, out f32)."""
+    _req(x, torch.bfloat16, "x"), _req(out, torch.float32, "out")
+    rows, cols = x.shape
+    _C.check(_C.lib().vdr_colsum_bf16(x.data_ptr(), x.stride(0), rows, cols, out.data_ptr(), _stream()), "vdr_colsum_bf16")
+
+
+def attn_delta(dO: torch.Tensor, O: torch.Tensor, heads: int) -> torch.Tensor:
+    N = O.shape[0]
+    delta = torch.empty((heads, N), dtype=torch.float32, device=O.device)
+    _C.check(_C.lib().vdr_attn_delta(dO.data_ptr(), O.data_ptr(), O.stride(0), N, heads, delta.data_ptr(), _stream()),
+             "vdr_attn_delta")
+    return delta
+
+
+def attn_p_ds(S: torch.Tensor, dP: torch.Tensor, lse: torch.Tensor, delta: torch.Tensor, N: int, scale: float):
+    ldp = S.shape[1]
+    P = torch.empty((N, ldp), dtype=torch.bfloat16, device=S.device)
+    dS = torch.empty((N, ldp), dtype=torch.bfloat16, device=S.device)
+    _C.check(_C.lib().vdr_attn_p_ds(S.data_ptr(), dP.data_ptr(), lse.data_ptr(), delta.data_ptr(), P.data_ptr(),
+                                    dS.data_ptr(), N, ldp, float(scale), _stream()), "vdr_attn_p_ds")
+    return P, dS
+
+
+def cls_concat_layernorm_bwd(dY, X, cls, gamma, mean, rstd, dgamma, dbeta, dcls):
+    n, d = X.shape
+    _C.check(_C.lib().vdr_cls_concat_layernorm_bwd(dY.data_ptr(), X.data_ptr() if n else None, cls.data_ptr(),
+                                                   gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dgamma.data_ptr(),
+                                                   dbeta.data_ptr(), dcls.data_ptr(), n, d, _stream()),
+             "vdr_cls_concat_layernorm_bwd")
+
+
+def cls_head_fwd(cls_bf16, W1, b1, W2, b2):
+    d, H1, Cn = cls_bf16.numel(), W1.shape[0], W2.shape[0]
+    zc = torch.empty(H1, dtype=torch.float32, device=W1.device)
+    logits = torch.empty(Cn, dtype=torch.float32, device=W1.device)
+    _C.check(_C.lib().vdr_cls_head_fwd(cls_bf16.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                       zc.data_ptr(), logits.data_ptr(), d, H1, Cn, _stream()), "vdr_cls_head_fwd")
+    return logits, zc
+
+
+def cls_head_bwd(cls_bf16, W1, W2, zc, dlogits, dcls_in, dW1, db1, dW2, db2):
+    d, H1, Cn = cls_bf16.numel(), W1.shape[0], W2.shape[0]
+    dcls = torch.empty(d, dtype=torch.float32, device=W1.device)
+    _C.check(_C.lib().vdr_cls_head_bwd(cls_bf16.data_ptr(), W1.data_ptr(), W2.data_ptr(), zc.data_ptr(), dlogits.data_ptr(),
+                                       dcls_in.data_ptr() if dcls_in is not None else None, dW1.data_ptr(), db1.data_ptr(),
+                                       dW2.data_ptr(), db2.data_ptr(), dcls.data_ptr(), d, H1, Cn, _stream()),
+             "vdr_cls_head_bwd")
+    return dcls
