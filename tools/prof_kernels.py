@@ -1,0 +1,31 @@
+"""Launch the two hot kernels once each on BASELINE config C2 shapes (for `ncu --set full`)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vit_deep_radiomics_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+M, d = 120 * 1025, 768
+torch.manual_seed(0)
+if which in ("gemm", "all"):
+    a = (torch.randn(M, d, device=dev) * 0.5).bfloat16()
+    for (N, K, epi) in [(2304, 768, "bias"), (768, 768, "residual"), (3072, 768, "gelu"), (768, 3072, "residual")]:
+        x = a if K == d else (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+        w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+        b = torch.randn(N, device=dev)
+        r = torch.randn(M, N, device=dev).bfloat16() if epi == "residual" else None
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.gemm(x, w, b, epilogue=epi, residual=r, out=out)
+        torch.cuda.synchronize()
+if which in ("attn", "all"):
+    qkv = torch.randn(M, 3 * d, device=dev).bfloat16()
+    out = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.flash_attn(qkv, 120, 1025, 12, out=out)
+    torch.cuda.synchronize()
+print("done")

@@ -23,6 +23,7 @@ recomputes P from the saved log-sum-exp with the score matrices materialised per
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 
@@ -35,10 +36,11 @@ _CACHE: dict = {}
 def _cached(p: torch.Tensor, tag: str, make):
     key = (id(p), tag)
     hit = _CACHE.get(key)
-    if hit is not None and hit[0] == p._version and hit[1].device == p.device:
-        return hit[1]
+    # the weak reference guards against id() reuse after a model has been freed
+    if hit is not None and hit[0]() is p and hit[1] == p._version and hit[2].device == p.device:
+        return hit[2]
     val = make(p.detach())
-    _CACHE[key] = (p._version, val)
+    _CACHE[key] = (weakref.ref(p), p._version, val)
     return val
 
 
