@@ -10,6 +10,19 @@
 
 namespace vdr {
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// trace record (CTA 0 only): slot = tile_iter * 8 + event
+//   0 mma: accumulator free   1 mma: first stage landed   2 mma: last MMA issued
+//   3 epi: accumulator ready  4 epi: tile stored          5 producer: first TMA of tile issued  6 producer: last TMA issued
+#define VDR_TRACE(ev, it)                                                                      \
+  do {                                                                                         \
+    if (p.trace != nullptr && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 8 + (ev)] = gtime(); \
+  } while (0)
+
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
@@ -25,6 +38,7 @@ struct GemmParams {
   int epilogue, r_dtype, c_dtype;
   int out_group, out_group_stride, out_offset;
   int res_mod, res_offset;
+  unsigned long long* trace;   // debug: per-tile timestamps of CTA 0 (nullptr = off)
 };
 
 template <int BN>
@@ -34,7 +48,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 * 4 /*bias staging*/ + kEpiWarps * 2048 /*store staging*/;
 };
 
 template <int BN>
@@ -51,6 +65,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_smem = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);  // [kEpiWarps][BN/2]
+  const uint32_t stage_base = base + kStages * Cfg::kStageBytes + 256 + BN * 16;          // [kEpiWarps][32 rows][64 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,7 +101,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -93,8 +110,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
           tma_load_2d(&tmW, &full_bar[stage], sa + Cfg::kStageBytesA, kb * BK, n_blk * BN);
+          if (kb == 0) VDR_TRACE(5, it);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        VDR_TRACE(6, it);
       }
     }
   } else if (warp == 1) {
@@ -105,13 +124,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
+        VDR_TRACE(0, it);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0) VDR_TRACE(1, it);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
@@ -125,6 +147,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete
+        VDR_TRACE(2, it);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -137,86 +160,127 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kColsPerWarp = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    float* sbias = bias_smem + ew * kColsPerWarp;
+    const bool res_bf16 = p.epilogue == VDR_EPI_BIAS_RESIDUAL && p.r_dtype == VDR_DTYPE_BF16;
+    // Per-warp staging tile (32 rows x 64 B, 16-byte chunks XOR-swizzled): accumulators arrive with
+    // thread == row, but global memory wants consecutive lanes on consecutive addresses.  Going through
+    // this tile turns 32 scattered 16-byte accesses per instruction into 8 rows x 64 contiguous bytes.
+    const uint32_t stg = stage_base + ew * 2048;
+    auto sw = [](int row, int chunk) -> uint32_t { return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); };
+    const int crow = lane >> 2, cchk = lane & 3;   // coalesced layout: rows crow + 8 i, 16-byte chunk cchk
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m_warp = m_blk * BM + quarter * 32;
+      const int m = m_warp + lane;
+      const bool row_ok = m < p.M;
+      auto map_rows = [&](int mm, int64_t& orow, int64_t& rrow_) {
+        orow = mm;
+        if (p.out_group > 0) orow = static_cast<int64_t>(mm / p.out_group) * p.out_group_stride + p.out_offset + mm % p.out_group;
+        rrow_ = orow;
+        if (p.res_mod > 0) rrow_ = p.res_offset + mm % p.res_mod;
+      };
+      int64_t out_row, res_row;
+      map_rows(m, out_row, res_row);
+      int64_t out_row_c[4], res_row_c[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) map_rows(m_warp + crow + 8 * i, out_row_c[i], res_row_c[i]);
+      const int nw0 = n_blk * BN + half * kColsPerWarp;      // first column of this warp
+      // Work that does not depend on the accumulator is done BEFORE waiting for the MMAs: stage this
+      // warp's bias slice in shared memory and prefetch the first residual chunk.
+      __syncwarp();
+      for (int i = lane; i < kColsPerWarp; i += 32)
+        sbias[i] = (p.bias != nullptr && nw0 + i < p.N) ? __ldg(p.bias + nw0 + i) : 0.f;
+      __syncwarp();
+      const __nv_bfloat16* Rb = static_cast<const __nv_bfloat16*>(p.R);
+      __nv_bfloat16* Cb = static_cast<__nv_bfloat16*>(p.C);
+      uint4 rcur[4], rnxt[4];
+      auto load_res = [&](uint4 (&dst)[4], int c) {   // coalesced layout; only full bf16 chunks
+        const int n = nw0 + c;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = (res_bf16 && n + 32 <= p.N && m_warp + crow + 8 * i < p.M)
+                       ? *reinterpret_cast<const uint4*>(Rb + res_row_c[i] * p.ldr + n + cchk * 8) : make_uint4(0, 0, 0, 0);
+      };
+      load_res(rcur, 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int m = m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-      int64_t out_row = m;
-      if (p.out_group > 0) out_row = static_cast<int64_t>(m / p.out_group) * p.out_group_stride + p.out_offset + m % p.out_group;
-      int64_t res_row = out_row;
-      if (p.res_mod > 0) res_row = p.res_offset + m % p.res_mod;
+      if (ew == 0 && lane == 0) VDR_TRACE(3, it);
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {
         const int col0 = half * kColsPerWarp + c;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN + col0) + (static_cast<uint32_t>(quarter * 32) << 16);
         tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
+        if (c + 32 < kColsPerWarp) load_res(rnxt, c + 32);   // overlap the next residual chunk with this one
         const int n0 = n_blk * BN + col0;
-        if (row_ok) {
+        const bool fast = p.c_dtype == VDR_DTYPE_BF16 && n0 + 32 <= p.N && (p.epilogue != VDR_EPI_BIAS_RESIDUAL || res_bf16);
+        uint4 rr[4];
+        if (fast && res_bf16) {   // residual: coalesced registers -> staging tile -> this thread's row
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(crow + 8 * i, cchk)), "r"(rcur[i].x), "r"(rcur[i].y), "r"(rcur[i].z), "r"(rcur[i].w) : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[g].x), "=r"(rr[g].y), "=r"(rr[g].z), "=r"(rr[g].w) : "r"(stg + sw(lane, g)) : "memory");
+          __syncwarp();
+        }
+        tmem_ld_wait();
+        if (fast) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + g * 8 + 4);
+            v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
+            if (p.epilogue == VDR_EPI_BIAS_GELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+            } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
+              const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
+              v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
+              v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
+                         "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(stg + sw(crow + 8 * i, cchk)) : "memory");
+            if (m_warp + crow + 8 * i < p.M) *reinterpret_cast<uint4*>(Cb + out_row_c[i] * p.ldc + n0 + cchk * 8) = o;
+          }
+          __syncwarp();
+        } else if (row_ok) {   // f32 output, f32 residual (pos-embed) or a ragged last column group: direct path
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int n = n0 + g * 8;
-            if (n + 8 <= p.N) {
-              float v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (p.epilogue == VDR_EPI_BIAS_GELU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-              } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
-                if (p.r_dtype == VDR_DTYPE_BF16) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.R) + res_row * p.ldr + n);
-                  const float2 a0 = unpack_bf16x2(rv.x), a1 = unpack_bf16x2(rv.y), a2 = unpack_bf16x2(rv.z), a3 = unpack_bf16x2(rv.w);
-                  v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
-                  v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
-                } else {
-                  const float* rp = static_cast<const float*>(p.R) + res_row * p.ldr + n;
-                  const float4 a0 = *reinterpret_cast<const float4*>(rp);
-                  const float4 a1 = *reinterpret_cast<const float4*>(rp + 4);
-                  v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                  v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-                }
-              }
-              if (p.c_dtype == VDR_DTYPE_BF16) {
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n) = o;
-              } else {
-                float* cp = static_cast<float*>(p.C) + out_row * p.ldc + n;
-                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              }
-            } else if (n < p.N) {   // ragged last column group (N % 8 != 0): element-wise
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (n + i < p.N) {
-                  float v = __uint_as_float(r[g * 8 + i]);
-                  if (p.bias != nullptr) v += __ldg(p.bias + n + i);
-                  if (p.epilogue == VDR_EPI_BIAS_GELU) v = gelu_erf(v);
-                  else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL)
-                    v += (p.r_dtype == VDR_DTYPE_BF16) ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.R)[res_row * p.ldr + n + i])
-                                                       : static_cast<const float*>(p.R)[res_row * p.ldr + n + i];
-                  if (p.c_dtype == VDR_DTYPE_BF16) static_cast<__nv_bfloat16*>(p.C)[out_row * p.ldc + n + i] = __float2bfloat16_rn(v);
-                  else static_cast<float*>(p.C)[out_row * p.ldc + n + i] = v;
-                }
+            for (int i = 0; i < 8; ++i) {
+              if (n + i < p.N) {
+                float v = __uint_as_float(r[g * 8 + i]) + sbias[c + g * 8 + i];
+                if (p.epilogue == VDR_EPI_BIAS_GELU) v = gelu_fast(v);
+                else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL)
+                  v += (p.r_dtype == VDR_DTYPE_BF16) ? __bfloat162float(Rb[res_row * p.ldr + n + i])
+                                                     : static_cast<const float*>(p.R)[res_row * p.ldr + n + i];
+                if (p.c_dtype == VDR_DTYPE_BF16) Cb[out_row * p.ldc + n + i] = __float2bfloat16_rn(v);
+                else static_cast<float*>(p.C)[out_row * p.ldc + n + i] = v;
               }
             }
           }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
       tc_fence_before();
       __syncwarp();
+      if (ew == 0 && lane == 0) VDR_TRACE(4, it);
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -249,6 +313,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const Gem
 }
 
 }  // namespace vdr
+
+static unsigned long long* g_trace = nullptr;
+// debug hook (not part of the drop-in surface): device buffer of 64*8 u64 receiving CTA 0's per-tile timestamps
+extern "C" void vdr_debug_set_gemm_trace(void* device_buf) { g_trace = static_cast<unsigned long long*>(device_buf); }
 
 extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   using namespace vdr;
@@ -289,6 +357,7 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   p.epilogue = a->epilogue; p.r_dtype = a->r_dtype; p.c_dtype = a->c_dtype;
   p.out_group = a->out_group; p.out_group_stride = a->out_group_stride; p.out_offset = a->out_offset;
   p.res_mod = a->res_mod; p.res_offset = a->res_offset;
+  p.trace = g_trace;
 
   const int total = tiles(bn);
   const int grid = total < sms ? total : sms;
