@@ -212,11 +212,19 @@ def run_ours(args):
     # per-kernel profile pass (CUDA events around every GEMM launch, same stream), separate from `value`
     ms_p, _, prof = timed(step_resident, max(1, min(args.steps, 3)), profile=True)
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for (kind, fl, a, b) in prof if kind == "gemm")
-    gemm_fl = sum(fl for (kind, fl, a, b) in prof if kind == "gemm")
-    attn_ms = sum(a.elapsed_time(b) for (kind, fl, a, b) in prof if kind == "attn")
-    attn_fl = sum(fl for (kind, fl, a, b) in prof if kind == "attn")
+    gemm_ms = sum(a.elapsed_time(b) for (kind, fl, a, b, _) in prof if kind == "gemm")
+    gemm_fl = sum(fl for (kind, fl, a, b, _) in prof if kind == "gemm")
+    attn_ms = sum(a.elapsed_time(b) for (kind, fl, a, b, _) in prof if kind == "attn")
+    attn_fl = sum(fl for (kind, fl, a, b, _) in prof if kind == "attn")
     n_gemm = sum(1 for p in prof if p[0] == "gemm")
+    by_label = {}
+    for (kind, fl, a, b, label) in prof:
+        t = by_label.setdefault(label, [0, 0.0, 0.0])
+        t[0] += 1
+        t[1] += a.elapsed_time(b)
+        t[2] += fl
+    per_kernel = {k: {"launches": v[0], "ms_per_launch": v[1] / v[0], "tflops": v[2] / (v[1] / 1e3) / 1e12}
+                  for k, v in sorted(by_label.items(), key=lambda kv: -kv[1][1])}
 
     for _ in range(2):
         step_e2e()
@@ -254,7 +262,8 @@ def run_ours(args):
                      "peak_source": peaks["source"], "launches_timed": n_gemm,
                      "share_of_step": gemm_ms / ms_p if ms_p else None,
                      "attention": {"achieved": attn_fl / (attn_ms / 1e3) / 1e12 if attn_ms else None,
-                                   "share_of_step": attn_ms / ms_p if ms_p else None}},
+                                   "share_of_step": attn_ms / ms_p if ms_p else None},
+                     "per_kernel": per_kernel},
         "cpu_baseline": cb,
         "clocks": clocks}))
 
@@ -262,7 +271,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=str, default="C2")

@@ -1,0 +1,23 @@
+"""Debug: per-kv-block timeline of one CTA of the attention kernel (ns)."""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vit_deep_radiomics_b200 import _C, ops
+dev = torch.device("cuda:0")
+L = _C.lib()
+L.vdr_debug_set_attn_trace.argtypes = [ctypes.c_void_p]
+B, N, h = 120, 1025, 12
+qkv = torch.randn(B * N, 3 * h * 64, device=dev).bfloat16()
+out = torch.empty(B * N, h * 64, device=dev, dtype=torch.bfloat16)
+for _ in range(3):
+    ops.flash_attn(qkv, B, N, h, out=out)
+buf = torch.zeros(16 * 8, dtype=torch.int64, device=dev)
+L.vdr_debug_set_attn_trace(buf.data_ptr())
+ops.flash_attn(qkv, B, N, h, out=out)
+torch.cuda.synchronize()
+L.vdr_debug_set_attn_trace(None)
+t = buf.cpu().view(16, 8).numpy()
+t0 = int(t[0, 0])
+print("cols: loop_top s_ready s_loaded softmax_done after_sync o_ready o_accumulated  (us)")
+for j in range(9):
+    print(j, " ".join(f"{(int(v) - t0) / 1e3:7.2f}" for v in t[j, :7]))

@@ -12,10 +12,10 @@
 
 namespace vdr {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;   // softmax warpgroup + issuer warpgroup
 constexpr int kBQ = 128, kBKV = 128, kHD = 64;
 constexpr int kTileBytes = 128 * kHD * 2;               // 16 KB: one 128 x 64 bf16 tile
-constexpr int kAttnSmem = 6 * kTileBytes /*Q, 3 ring slots, P lo/hi*/ + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int kAttnSmem = 7 * kTileBytes /*Q, 4 ring slots, P lo/hi*/ + 256 /*barriers*/;
 constexpr int kAttnTmemCols = 256;                       // S: [0,128)  O: [128,192)
 
 __device__ __forceinline__ float ex2(float x) {
@@ -42,35 +42,90 @@ struct AttnParams {
   int64_t ld_out;
   int B, N, heads, d;
   float scale_log2;
+  unsigned long long* trace;   // debug: per-iteration timestamps of CTA (0,0,0) thread 32
 };
 
+__device__ __forceinline__ unsigned long long attn_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATT_TRACE(ev)                                                                                              \
+  do {                                                                                                             \
+    if (p.trace != nullptr && tid == 32 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 8 + (ev)] = attn_gtime(); \
+  } while (0)
+
+// packed fp32x2 helpers (FFMA2 / FADD2 on sm_100): halve the issue slots of the softmax inner loop
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
+// Warp roles: warps 0-3 = softmax warpgroup (thread t owns query row t = TMEM lane t);
+//             warp 4    = issuer (TMA ring + tcgen05.mma), warps 5-7 idle (setmaxnreg works per warpgroup).
+// Pipeline per 128-key block j (no CTA-wide barrier in the loop):
+//   issuer : wait S_j consumed -> prefetch K_{j+2}, issue S_{j+1};  wait P_j ready -> issue O_j = P_j V_j
+//   softmax: wait S_j -> registers -> signal "consumed" -> max / exp2 / sum -> fold O_{j-1} (finished long ago)
+//            -> write P_j -> signal "ready"
+// so the tensor pipe computes S_{j+1} and O_{j-1} while the exponentials of block j are evaluated.
 __global__ void __launch_bounds__(kAttnThreads, 2)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  // layout: Q | ring0 | ring1 | ring2 | P_lo | P_hi | barriers
-  const uint32_t sQ = base, sRing = base + kTileBytes, sP = base + 4 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);
-  uint64_t* bar_q = bars;          // Q landed
-  uint64_t* bar_kv = bars + 1;     // [3] ring slot landed
-  uint64_t* bar_s = bars + 4;      // S = QK^T complete
-  uint64_t* bar_o = bars + 5;      // O_j = PV complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  // layout: Q | ring0..3 | P_lo | P_hi | barriers
+  const uint32_t sQ = base, sRing = base + kTileBytes, sP = base + 5 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
+  uint64_t* bar_q = bars;            // Q landed
+  uint64_t* bar_kv = bars + 1;       // [4] ring slot landed
+  uint64_t* bar_s = bars + 5;        // S_j = Q K_j^T complete            (tcgen05.commit)
+  uint64_t* bar_o = bars + 6;        // O_j = P_j V_j complete            (tcgen05.commit)
+  uint64_t* bar_sfree = bars + 7;    // S_j is in registers               (4 softmax warps arrive)
+  uint64_t* bar_pready = bars + 8;   // P_j is in smem, O_{j-1} consumed  (4 softmax warps arrive)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
   const int row_base = b * p.N;                       // first token row of this image in the qkv matrix
   const int colQ = head * kHD, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
   const int nkv = (p.N + kBKV - 1) / kBKV;
-  const int ntiles = 2 * nkv;                         // ring tiles: K0 V0 K1 V1 ...
+  const int ntiles = 2 * nkv;                         // ring tiles: K0 V0 K1 V1 ...  (K: slots 0/2, V: slots 1/3)
 
   if (tid == 0) {
+    if (base & 1023u) { printf("vdr: attention smem base not 1024-byte aligned\n"); __trap(); }
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(&bar_kv[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_kv[i], 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
+    mbar_init(bar_sfree, 4);
+    mbar_init(bar_pready, 4);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<kAttnTmemCols>(tmem_ptr);
@@ -79,150 +134,177 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
-  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
 
-  auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2, odd = V block t/2
-    const int slot = t % 3;
-    const int kv0 = (t >> 1) * kBKV;
-    mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
-    tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + kv0);
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, kTileBytes);
-    tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
-    for (int t = 0; t < 3 && t < ntiles; ++t) issue_tile(t);
-  }
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
-
-  float o_acc[kHD];
+  if (warp >= 4) {
+    // =============================================================== issuer warpgroup
+    reg_dec<24>();
+    if (warp == 4 && lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
+      auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2, odd = V block t/2
+        const int slot = t & 3;
+        mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
+        tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + (t >> 1) * kBKV);
+      };
+      auto issue_s = [&](int j) {      // S = Q K_j^T
+        const int t = 2 * j;
+        mbar_wait(&bar_kv[t & 3], (t >> 2) & 1);
+        tc_fence_after();
+        const uint64_t dq = umma_desc_kmajor_sw128(sQ);
+        const uint64_t dk = umma_desc_kmajor_sw128(sRing + (t & 3) * kTileBytes);
 #pragma unroll
-  for (int i = 0; i < kHD; ++i) o_acc[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-
-  for (int j = 0; j < nkv; ++j) {
-    const int kv0 = j * kBKV;
-    // ---- S = Q K_j^T
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      const int t = 2 * j;
-      mbar_wait(&bar_kv[t % 3], (t / 3) & 1);
-      tc_fence_after();
-      const uint64_t dq = umma_desc_kmajor_sw128(sQ);
-      const uint64_t dk = umma_desc_kmajor_sw128(sRing + (t % 3) * kTileBytes);
-#pragma unroll
-      for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_s, j & 1);
-    tc_fence_after();
-    if (tid == 0 && 2 * j + 3 < ntiles) issue_tile(2 * j + 3);   // K_j's slot is free again
-    __syncwarp();
-
-    // ---- online softmax over this thread's row (two passes over TMEM: max, then exp)
-    const bool tail = kv0 + kBKV > p.N;
-    float m_blk = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float s = __uint_as_float(r[i]);
-        if (tail && kv0 + c * 32 + i >= p.N) s = -INFINITY;
-        m_blk = fmaxf(m_blk, s);
-      }
-    }
-    const float m_new = fmaxf(m_run, m_blk * p.scale_log2);
-    const float alpha = ex2(m_run - m_new);
-    float l_blk = 0.f;
-    const uint32_t prow = sP + tid * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
-        float p0 = ex2(fmaf(s0, p.scale_log2, -m_new));
-        float p1 = ex2(fmaf(s1, p.scale_log2, -m_new));
-        if (tail) {
-          if (kv0 + c * 32 + i >= p.N) p0 = 0.f;
-          if (kv0 + c * 32 + i + 1 >= p.N) p1 = 0.f;
+        for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      };
+      mbar_arrive_expect_tx(bar_q, kTileBytes);
+      tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
+      for (int t = 0; t < 4 && t < ntiles; ++t) issue_tile(t);
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(bar_sfree, j & 1);                       // S_j consumed -> K_j's slot and the S columns are free
+        tc_fence_after();
+        if (2 * j + 4 < ntiles) issue_tile(2 * j + 4);     // K_{j+2}
+        if (j + 1 < nkv) issue_s(j + 1);
+        if (j >= 1 && 2 * j + 3 < ntiles) {                // V_{j+1} goes into V_{j-1}'s slot: O_{j-1} must be complete
+          mbar_wait(bar_o, (j - 1) & 1);
+          issue_tile(2 * j + 3);
         }
-        // the row sum uses the bf16-rounded probabilities that the P V product actually sees
-        const uint32_t w = pack_bf16x2(p0, p1);
-        const float2 pr = unpack_bf16x2(w);
-        l_blk += pr.x + pr.y;
-        pk[i >> 1] = w;
-      }
-      // P[row][kv] bf16, K-major, 128B swizzle: halves of 64 kv columns (16 KB each)
-      const uint32_t half_base = prow + (c >> 1) * kTileBytes;
+        mbar_wait(bar_pready, j & 1);                      // P_j written, O_{j-1} read
+        tc_fence_after();
+        const int t = 2 * j + 1;
+        mbar_wait(&bar_kv[t & 3], (t >> 2) & 1);
+        tc_fence_after();
+        const uint32_t sV = sRing + (t & 3) * kTileBytes;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q) ^ static_cast<uint32_t>(tid & 7);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(half_base + chunk * 16), "r"(pk[q * 4]),
-                     "r"(pk[q * 4 + 1]), "r"(pk[q * 4 + 2]), "r"(pk[q * 4 + 3])
-                     : "memory");
+        for (int k = 0; k < kBKV / 16; ++k) {
+          const uint64_t dp = umma_desc_kmajor_sw128(sP + (k >> 2) * kTileBytes) + 2 * (k & 3);
+          const uint64_t dv = umma_desc_mnmajor_sw128(sV + k * 2048);   // 16 kv rows x 128 B
+          umma_ss(tmem_O, dp, dv, idesc_o, k != 0);
+        }
+        umma_commit(bar_o);
       }
     }
-    l_run = l_run * alpha + l_blk;
-    m_run = m_new;
-    fence_proxy_async_smem();   // P stores -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
+  } else {
+    // =============================================================== softmax warpgroup
+    reg_inc<232>();
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    uint64_t o_acc[kHD / 2];
+#pragma unroll
+    for (int i = 0; i < kHD / 2; ++i) o_acc[i] = 0ull;   // two +0.0f
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+    const uint32_t prow = sP + tid * 128;
 
-    // ---- O_j = P V_j
-    if (tid == 0) {
-      const int t = 2 * j + 1;
-      mbar_wait(&bar_kv[t % 3], (t / 3) & 1);
+    auto fold_o = [&](float alpha) {   // o_acc = o_acc * alpha + O (from TMEM)
+      const uint64_t alpha2 = pack2(alpha, alpha);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          o_acc[c * 16 + (i >> 1)] = fma2(o_acc[c * 16 + (i >> 1)], alpha2, pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+      }
+    };
+
+    for (int j = 0; j < nkv; ++j) {
+      const int kv0 = j * kBKV;
+      ATT_TRACE(0);
+      mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      const uint32_t sV = sRing + (t % 3) * kTileBytes;
+      ATT_TRACE(1);
+      // the whole 128-wide score row of this thread -> registers, then hand the S columns back
+      uint32_t sr[4][32];
 #pragma unroll
-      for (int k = 0; k < kBKV / 16; ++k) {
-        const uint64_t dp = umma_desc_kmajor_sw128(sP + (k >> 2) * kTileBytes) + 2 * (k & 3);
-        const uint64_t dv = umma_desc_mnmajor_sw128(sV + k * 2048);   // 16 kv rows x 128 B
-        umma_ss(tmem_O, dp, dv, idesc_o, k != 0);
-      }
-      umma_commit(bar_o);
-    }
-    __syncwarp();
-    mbar_wait(bar_o, j & 1);
-    tc_fence_after();
-    if (tid == 0 && 2 * j + 4 < ntiles) issue_tile(2 * j + 4);   // V_j's slot is free again
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, sr[c]);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);
+      ATT_TRACE(2);
+      if (kv0 + kBKV > p.N) {   // last block: keys past the end of the sequence do not exist
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(r[i]));
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + c * 32 + i >= p.N) sr[c][i] = 0xff800000u;   // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = ex2(m_run - m_new);
+      const uint64_t negm2 = pack2(-m_new, -m_new);
+      uint64_t lsum2 = 0ull;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0, x1;
+          unpack2(fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2), x0, x1);
+          const float p0 = ex2(x0), p1 = ex2(x1);
+          lsum2 = add2(lsum2, pack2(p0, p1));
+          pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
+        }
+      }
+      float l0, l1;
+      unpack2(lsum2, l0, l1);
+      l_run = l_run * alpha + (l0 + l1);
+      m_run = m_new;
+      ATT_TRACE(3);
+      if (j > 0) {   // O_{j-1} finished while the exponentials above were computed; P_{j-1} is no longer read
+        mbar_wait(bar_o, (j - 1) & 1);
+        tc_fence_after();
+        fold_o(alpha_prev);
+      }
+      alpha_prev = alpha;
+      ATT_TRACE(4);
+      // P[row][kv] bf16, K-major, 128B swizzle: halves of 64 kv columns (16 KB each)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t half_base = prow + (c >> 1) * kTileBytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q) ^ static_cast<uint32_t>(tid & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(half_base + chunk * 16), "r"(pk[c * 16 + q * 4]),
+                       "r"(pk[c * 16 + q * 4 + 1]), "r"(pk[c * 16 + q * 4 + 2]), "r"(pk[c * 16 + q * 4 + 3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();   // P stores -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pready);
+      ATT_TRACE(5);
     }
-    tc_fence_before();   // ordered before the next iteration's barrier -> S / O may be overwritten
-  }
+    mbar_wait(bar_o, (nkv - 1) & 1);
+    tc_fence_after();
+    fold_o(alpha_prev);
 
-  // ---- normalise and store
-  const int q = q0 + tid;
-  if (q < p.N) {
-    const float inv = 1.f / l_run;
-    __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
+    // ---- normalise and store
+    const int q = q0 + tid;
+    if (q < p.N) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
 #pragma unroll
-    for (int i = 0; i < kHD; i += 8) {
-      uint4 o;
-      o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-      o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-      o.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-      o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-      *reinterpret_cast<uint4*>(op + i) = o;
+      for (int i = 0; i < kHD / 2; i += 4) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) unpack2(o_acc[i + k], v[2 * k], v[2 * k + 1]);
+        uint4 o;
+        o.x = cvt_bf16x2(v[0] * inv, v[1] * inv);
+        o.y = cvt_bf16x2(v[2] * inv, v[3] * inv);
+        o.z = cvt_bf16x2(v[4] * inv, v[5] * inv);
+        o.w = cvt_bf16x2(v[6] * inv, v[7] * inv);
+        *reinterpret_cast<uint4*>(op + i * 2) = o;
+      }
+      if (p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
     }
-    if (p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
   }
   tc_fence_before();
   __syncthreads();
@@ -233,6 +315,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
 }
 
 }  // namespace vdr
+
+static unsigned long long* g_attn_trace = nullptr;
+extern "C" void vdr_debug_set_attn_trace(void* device_buf) { g_attn_trace = static_cast<unsigned long long*>(device_buf); }
 
 extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B,
                                   int N, int heads, float scale, vdr_stream_t stream) {
@@ -258,6 +343,7 @@ extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, in
   p.ld_out = ld_out;
   p.B = B; p.N = N; p.heads = heads; p.d = d;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
   dim3 grid((N + kBQ - 1) / kBQ, heads, B);
   flash_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
   count_launch();

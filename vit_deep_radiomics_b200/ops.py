@@ -18,8 +18,8 @@ PROFILE = None
 
 
 class _Prof:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, label=""):
+        self.kind, self.flops, self.label = kind, flops, label
 
     def __enter__(self):
         if PROFILE is not None:
@@ -30,7 +30,7 @@ class _Prof:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.kind, self.flops, self.e0, e1))
+            PROFILE.append((self.kind, self.flops, self.e0, e1, self.label))
         return False
 
 
@@ -77,7 +77,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
     args.epilogue = epi
     args.out_group, args.out_group_stride, args.out_offset = out_group
     args.res_mod, args.res_offset = res_mod
-    with _Prof("gemm", 2.0 * M * N * K):
+    with _Prof("gemm", 2.0 * M * N * K, f"gemm M{M} N{N} K{K} {epilogue}"):
         _C.check(_C.lib().vdr_gemm(C.byref(args), _stream()), "vdr_gemm")
     return out
 
@@ -191,7 +191,7 @@ def flash_attn(qkv: torch.Tensor, B: int, N: int, heads: int, scale: float | Non
     if out is None:
         out = torch.empty((B * N, d), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if return_lse else None
-    with _Prof("attn", 4.0 * B * heads * N * N * 64):
+    with _Prof("attn", 4.0 * B * heads * N * N * 64, f"attn B{B} N{N} h{heads}"):
         _C.check(_C.lib().vdr_flash_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0),
                                              lse.data_ptr() if return_lse else None, B, N, heads, float(scale),
                                              _stream()), "vdr_flash_attn_fwd")
