@@ -200,19 +200,34 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 6 FMAs instead of
-// erff's two-branch polynomial -- the GEMM epilogue applies it to every element of the MLP hidden layer.
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 + approx-unit error ~1e-7): one MUFU.RCP, one MUFU.EX2
+// and a handful of FMAs, branch-free, no slow-path calls -- the GEMM epilogue applies it to every element of
+// the MLP hidden layer, where erff() (two-branch polynomial) made the epilogue the bottleneck.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float r = 1.0f - p * t * __expf(-ax * ax);
+  const float e = ex2_approx(ax * ax * -1.4426950408889634f);
+  const float r = fmaf(-p * t, e, 1.0f);
   return copysignf(r, x);
 }
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_fast(x * 0.70710678118654752f), hx);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

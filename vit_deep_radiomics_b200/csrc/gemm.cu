@@ -214,7 +214,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld_32x32b_x32(taddr, r);
         if (c + 32 < kColsPerWarp) load_res(rnxt, c + 32);   // overlap the next residual chunk with this one
         const int n0 = n_blk * BN + col0;
-        const bool fast = p.c_dtype == VDR_DTYPE_BF16 && n0 + 32 <= p.N && (p.epilogue != VDR_EPI_BIAS_RESIDUAL || res_bf16);
+        const bool fast = p.c_dtype == VDR_DTYPE_BF16 && n0 + 32 <= p.N;
         uint4 rr[4];
         if (fast && res_bf16) {   // residual: coalesced registers -> staging tile -> this thread's row
 #pragma unroll
@@ -241,9 +241,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
             } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
-              const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
-              v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
-              v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+              if (res_bf16) {
+                const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
+                v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
+                v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+              } else if (row_ok) {   // f32 residual (position embedding: small, cache-resident): row-layout loads
+                const float* rp = static_cast<const float*>(p.R) + res_row * p.ldr + n0 + g * 8;
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(rp));
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+              }
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
                          "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
