@@ -171,8 +171,15 @@ def run_ours(args):
     img_pin = torch.as_tensor(img).pin_memory()
     mask_pin = torch.as_tensor(np.ascontiguousarray(mask).view(np.uint8)).pin_memory()
 
-    def step_e2e():
-        return tdd.extract_point_cloud(model, img_pin, mask_pin, res)
+    extractor = tdd.PointCloudExtractor(model)
+
+    def run_e2e(k):
+        """k patients through the public streaming API: H2D of patient i+1 overlaps the backbone of patient i;
+        every patient's point cloud is read back to the host."""
+        last = None
+        for out in extractor.run([(img_pin, mask_pin, res)] * k):
+            last = out
+        return last
 
     def barrier():
         if world > 1:
@@ -226,9 +233,8 @@ def run_ours(args):
     per_kernel = {k: {"launches": v[0], "ms_per_launch": v[1] / v[0], "tflops": v[2] / (v[1] / 1e3) / 1e12}
                   for k, v in sorted(by_label.items(), key=lambda kv: -kv[1][1])}
 
-    for _ in range(2):
-        step_e2e()
-    ms_e, out_e, _ = timed(step_e2e, args.steps)
+    run_e2e(2)
+    ms_e, out_e, _ = timed(lambda: run_e2e(args.steps), 1)
     e2e_value = world * S * args.steps / (ms_e / 1e3)
     h2d = img_pin.numel() * 4 + mask_pin.numel()
     d2h = out_e["count"] * (model.cfg["dim"] * 4 + 12) + 4
@@ -255,7 +261,7 @@ def run_ours(args):
                    "weights": "seeded random init (no checkpoints offline)"},
         "model_tflops": flops_step * world * args.steps / (ms / 1e3) / 1e12,
         "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e / args.steps, "api": "tfds_dense_descriptor.extract_point_cloud (pinned host buffers)"},
+                "ms_per_step": ms_e / args.steps, "api": "tfds_dense_descriptor.PointCloudExtractor.run (pinned host buffers, uploads double-buffered on a copy stream)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16"],
                      "unit": "TFLOP/s", "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": traffic,

@@ -144,7 +144,8 @@ int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_ou
  *             elements per row -- a dense (S,h,w,D) tensor is (h*w, w, 0); the ROI (r0:,c0:) of the
  *             backbone's token matrix (CLS first, grid gh x gw) is (gh*gw+1, gw, 1+r0*gw+c0),
  *             which is extract_roi (visualization_utils.py:115-125) without a copy
- *   mask      u8 pixel masks: value (k,r,c) at mask[k*mask_slice_stride + r*mask_row_stride + c];
+ *   mask      u8 pixel masks: value (k,r,c) at mask[k*mask_slice_stride + r*mask_row_stride + c*mask_col_stride]
+ *             ((HM*WM, WM, 1) for slice-major masks, (1, W*S, S) for an (H,W,S) volume mask read in place);
  *             row_map[h], col_map[w] (int32) give the source pixel row/col of each feature-grid
  *             row/col (the order-0 resize index maps of :151)
  *   out_tok   (cap, D) f32 packed tokens in ascending n = a*(w*S) + b*S + k   (stable)
@@ -160,7 +161,7 @@ int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_ou
 size_t vdr_mask_gather_workspace_bytes(int S, int h, int w);
 int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
                     int64_t feat_row_pitch, int64_t feat_row0,
-                    const uint8_t* mask, int64_t mask_slice_stride, int64_t mask_row_stride,
+                    const uint8_t* mask, int64_t mask_slice_stride, int64_t mask_row_stride, int64_t mask_col_stride,
                     const int32_t* row_map, const int32_t* col_map,
                     int S, int h, int w, int D,
                     float* out_tok, int32_t* out_src, int32_t* out_count, int cap,
@@ -178,6 +179,9 @@ int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t f
  *   like n = (yi*H + xi)*S + zi, so pass 2 needs no scan: output row j maps to its voxel in closed form.
  */
 int vdr_voxel_bbox(const uint8_t* mask, int H, int W, int S, int32_t* bbox, vdr_stream_t stream);
+/* Same reduction in (col, row, slice) order: bbox = col_min, col_max, row_min, row_max, slice_min, slice_max of mask > 0
+ * = the bounding box of the union mask over slices that generate_features starts from (tfds_dense_descriptor.py:257-260). */
+int vdr_mask_bbox(const uint8_t* mask, int H, int W, int S, int32_t* bbox, vdr_stream_t stream);
 int vdr_voxel_gather(const float* img, const uint8_t* mask, int H, int W, int S, const int32_t* bbox,
                      int32_t* out_flat, float* out_raw, uint8_t* out_mask, int32_t* out_count, int cap,
                      vdr_stream_t stream);

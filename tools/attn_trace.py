@@ -11,13 +11,13 @@ qkv = torch.randn(B * N, 3 * h * 64, device=dev).bfloat16()
 out = torch.empty(B * N, h * 64, device=dev, dtype=torch.bfloat16)
 for _ in range(3):
     ops.flash_attn(qkv, B, N, h, out=out)
-buf = torch.zeros(16 * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(16 * 16, dtype=torch.int64, device=dev)
 L.vdr_debug_set_attn_trace(buf.data_ptr())
 ops.flash_attn(qkv, B, N, h, out=out)
 torch.cuda.synchronize()
 L.vdr_debug_set_attn_trace(None)
-t = buf.cpu().view(16, 8).numpy()
+t = buf.cpu().view(16, 16).numpy()
 t0 = int(t[0, 0])
-print("cols: loop_top s_ready s_loaded softmax_done after_sync o_ready o_accumulated  (us)")
+print("softmax: loop_top s_ready s_loaded math_done o_wait_done p_stored | issuer: top sfree_seen s_next_issued before_pready pready_seen pv_issued (us)")
 for j in range(9):
-    print(j, " ".join(f"{(int(v) - t0) / 1e3:7.2f}" for v in t[j, :7]))
+    print(j, " ".join(f"{(int(v) - t0) / 1e3:7.2f}" for v in t[j, :6]), "|", " ".join(f"{(int(v) - t0) / 1e3:7.2f}" for v in t[j, 8:14]))

@@ -21,7 +21,7 @@ EXPORTS = (
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd",
     "vdr_flash_attn_fwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather",
-    "vdr_voxel_bbox", "vdr_voxel_gather",
+    "vdr_voxel_bbox", "vdr_mask_bbox", "vdr_voxel_gather",
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
     "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
 )
@@ -73,9 +73,10 @@ def lib() -> C.CDLL:
     L.vdr_flash_attn_fwd.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, f32, vp]
     L.vdr_mask_gather_workspace_bytes.argtypes = [i32, i32, i32]
     L.vdr_mask_gather_workspace_bytes.restype = sz
-    L.vdr_mask_gather.argtypes = [vp, i32, i64, i64, i64, i64, vp, i64, i64, vp, vp, i32, i32, i32, i32,
+    L.vdr_mask_gather.argtypes = [vp, i32, i64, i64, i64, i64, vp, i64, i64, i64, vp, vp, i32, i32, i32, i32,
                                   vp, vp, vp, i32, f64, vp, C.POINTER(f64), vp, sz, vp]
     L.vdr_voxel_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.vdr_mask_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_voxel_gather.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
     L.vdr_gelu_fwd.argtypes = [vp, vp, i64, vp]
     L.vdr_gelu_bwd.argtypes = [vp, vp, vp, i64, vp]

@@ -8,6 +8,8 @@
 //   O = O*alpha + O_j in registers (no TMEM round trip for the rescale)
 // K/V tiles stream through a 3-slot TMA ring; two CTAs are resident per SM so the tensor pipe of one
 // overlaps the softmax of the other.  Q, K, V are read in place from the packed QKV GEMM output.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vdr {
@@ -16,7 +18,7 @@ constexpr int kAttnThreads = 256;   // softmax warpgroup + issuer warpgroup
 constexpr int kBQ = 128, kBKV = 128, kHD = 64;
 constexpr int kTileBytes = 128 * kHD * 2;               // 16 KB: one 128 x 64 bf16 tile
 constexpr int kAttnSmem = 7 * kTileBytes /*Q, 4 ring slots, P lo/hi*/ + 256 /*barriers*/;
-constexpr int kAttnTmemCols = 256;                       // S: [0,128)  O: [128,192)
+constexpr int kAttnTmemCols = 256;                       // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -52,7 +54,12 @@ __device__ __forceinline__ unsigned long long attn_gtime() {
 }
 #define ATT_TRACE(ev)                                                                                              \
   do {                                                                                                             \
-    if (p.trace != nullptr && tid == 32 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 8 + (ev)] = attn_gtime(); \
+    if (p.trace != nullptr && tid == 32 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 16 + (ev)] = attn_gtime(); \
+  } while (0)
+
+#define ISS_TRACE(ev)                                                                                              \
+  do {                                                                                                             \
+    if (p.trace != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 16 + 8 + (ev)] = attn_gtime(); \
   } while (0)
 
 // packed fp32x2 helpers (FFMA2 / FADD2 on sm_100): halve the issue slots of the softmax inner loop
@@ -85,6 +92,27 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
   return r;
 }
 
+// exp2 of two non-positive arguments on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial,
+// max relative error 7.7e-5 -- far below the bf16 rounding of P): relieves the MUFU, which is the ceiling of
+// head_dim-64 attention (128 x 128 exponentials per 4.2 MFLOP block).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t magic2 = pack2(12582912.f, 12582912.f);           // 1.5 * 2^23: t = x + magic rounds x to an integer
+  const uint64_t t2 = add2(x2, magic2);
+  const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), x2);              // f = x - round(x) in [-0.5, 0.5]
+  uint64_t q2 = fma2(f2, pack2(0.05508868396282196f, 0.05508868396282196f), pack2(0.24260404706001282f, 0.24260404706001282f));
+  q2 = fma2(q2, f2, pack2(0.6932762265205383f, 0.6932762265205383f));
+  q2 = fma2(q2, f2, pack2(0.9999289512634277f, 0.9999289512634277f));
+  float t0, t1, q0, q1;
+  unpack2(t2, t0, t1);
+  unpack2(q2, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));   // * 2^round(x) through the exponent field
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
@@ -100,7 +128,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   // layout: Q | ring0..3 | P_lo | P_hi | barriers
-  const uint32_t sQ = base, sRing = base + kTileBytes, sP = base + 5 * kTileBytes;
+  const uint32_t sQ = base, sRing = base + kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
   uint64_t* bar_q = bars;            // Q landed
   uint64_t* bar_kv = bars + 1;       // [4] ring slot landed
@@ -133,20 +161,23 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
 
   if (warp >= 4) {
     // =============================================================== issuer warpgroup
-    reg_dec<24>();
+    reg_dec<48>();
+    // Two issuing threads so that the two dependent MMA chains of a block (S_{j+1} = Q K^T: 4 steps, O += P V:
+    // 8 steps, each step waiting ~130 cycles on the accumulator of the previous one) are dispatched concurrently.
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
+    auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2 (slots 0/2), odd = V block t/2 (slots 1/3)
+      const int slot = t & 3;
+      mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
+      tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + (t >> 1) * kBKV);
+    };
     if (warp == 4 && lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
-      auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2, odd = V block t/2
-        const int slot = t & 3;
-        mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
-        tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + (t >> 1) * kBKV);
-      };
-      auto issue_s = [&](int j) {      // S = Q K_j^T
+      // ---- K tiles + S = Q K^T
+      auto issue_s = [&](int j) {
         const int t = 2 * j;
         mbar_wait(&bar_kv[t & 3], (t >> 2) & 1);
         tc_fence_after();
@@ -158,56 +189,55 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       };
       mbar_arrive_expect_tx(bar_q, kTileBytes);
       tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
-      for (int t = 0; t < 4 && t < ntiles; ++t) issue_tile(t);
+      issue_tile(0);
+      if (nkv > 1) issue_tile(2);
       mbar_wait(bar_q, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(bar_sfree, j & 1);                       // S_j consumed -> K_j's slot and the S columns are free
+        ISS_TRACE(0);
+        mbar_wait(bar_sfree, j & 1);                       // S_j is in registers -> K_j's slot and the S columns are free
         tc_fence_after();
-        if (2 * j + 4 < ntiles) issue_tile(2 * j + 4);     // K_{j+2}
+        ISS_TRACE(1);
         if (j + 1 < nkv) issue_s(j + 1);
-        if (j >= 1 && 2 * j + 3 < ntiles) {                // V_{j+1} goes into V_{j-1}'s slot: O_{j-1} must be complete
-          mbar_wait(bar_o, (j - 1) & 1);
-          issue_tile(2 * j + 3);
-        }
-        mbar_wait(bar_pready, j & 1);                      // P_j written, O_{j-1} read
+        if (j + 2 < nkv) issue_tile(2 * j + 4);            // K_{j+2} into K_j's slot
+        ISS_TRACE(2);
+      }
+    } else if (warp == 5 && lane == 0) {
+      // ---- V tiles + O += P V
+      issue_tile(1);
+      if (nkv > 1) issue_tile(3);
+      for (int j = 0; j < nkv; ++j) {
+        ISS_TRACE(3);
+        mbar_wait(bar_pready, j & 1);                      // P_j is in TMEM (and O rescaled if the maximum moved)
         tc_fence_after();
+        ISS_TRACE(4);
+        if (j >= 1 && j + 1 < nkv) {                       // V_{j+1} goes into V_{j-1}'s slot: O_{j-1} must be complete.
+          mbar_wait(bar_o, (j - 1) & 1);                   // (waited BEFORE O_j is committed: a parity wait must never
+          issue_tile(2 * j + 3);                           //  be two phases behind its barrier)
+        }
         const int t = 2 * j + 1;
         mbar_wait(&bar_kv[t & 3], (t >> 2) & 1);
         tc_fence_after();
         const uint32_t sV = sRing + (t & 3) * kTileBytes;
 #pragma unroll
         for (int k = 0; k < kBKV / 16; ++k) {
-          const uint64_t dp = umma_desc_kmajor_sw128(sP + (k >> 2) * kTileBytes) + 2 * (k & 3);
           const uint64_t dv = umma_desc_mnmajor_sw128(sV + k * 2048);   // 16 kv rows x 128 B
-          umma_ss(tmem_O, dp, dv, idesc_o, k != 0);
+          // A = P from TMEM (16 bf16 = 8 columns per K step); O accumulates in TMEM across all key blocks
+          umma_ts(tmem_O, tmem_P + k * 8, dv, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         }
         umma_commit(bar_o);
+        ISS_TRACE(5);
       }
     }
   } else {
     // =============================================================== softmax warpgroup
-    reg_inc<232>();
+    reg_inc<208>();
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    uint64_t o_acc[kHD / 2];
-#pragma unroll
-    for (int i = 0; i < kHD / 2; ++i) o_acc[i] = 0ull;   // two +0.0f
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    // Online softmax with LAZY rescaling: probabilities are taken relative to a reference maximum m_ref that is
+    // only moved when the running maximum exceeds it by more than 2^8; O then accumulates in TMEM across key
+    // blocks (the P V MMAs run with accumulate = 1) and is touched by this warpgroup only on those rare moves.
+    float m_ref = -INFINITY, l_run = 0.f;
     const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
-    const uint32_t prow = sP + tid * 128;
-
-    auto fold_o = [&](float alpha) {   // o_acc = o_acc * alpha + O (from TMEM)
-      const uint64_t alpha2 = pack2(alpha, alpha);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          o_acc[c * 16 + (i >> 1)] = fma2(o_acc[c * 16 + (i >> 1)], alpha2, pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
-      }
-    };
 
     for (int j = 0; j < nkv; ++j) {
       const int kv0 = j * kBKV;
@@ -224,59 +254,85 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sfree);
       ATT_TRACE(2);
-      if (kv0 + kBKV > p.N) {   // last block: keys past the end of the sequence do not exist
+      float alpha = 1.f;
+      bool moved = false;
+      uint64_t lsum2 = 0ull;
+      uint32_t pk[64];
+      // The body exists twice: the masked copy runs only for the last, partial key block (a real, warp-uniform
+      // branch -- written inline the compiler if-converts the mask into 384 predicated selects per block).
+      auto softmax_body = [&](auto tail_tag) {
+        constexpr bool kTail = decltype(tail_tag)::value;
+        if constexpr (kTail) {   // keys past the end of the sequence do not exist
+          const int valid = p.N - kv0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
+        }
+        float mx = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kv0 + c * 32 + i >= p.N) sr[c][i] = 0xff800000u;   // -inf
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = ex2(m_run - m_new);
-      const uint64_t negm2 = pack2(-m_new, -m_new);
-      uint64_t lsum2 = 0ull;
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float x0, x1;
-          unpack2(fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2), x0, x1);
-          const float p0 = ex2(x0), p1 = ex2(x1);
-          lsum2 = add2(lsum2, pack2(p0, p1));
-          pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
+          for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+        const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+        moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);   // warp-uniform: TMEM accesses are warp-wide
+        if (moved) {
+          alpha = ex2(m_ref - m_new);
+          m_ref = m_new;
         }
-      }
+        const uint64_t negm2 = pack2(-m_ref, -m_ref);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2);
+            float p0, p1;
+            if (((i >> 1) & 7) == 1 || ((i >> 1) & 7) == 4 || ((i >> 1) & 7) == 6) {   // 3 of every 8 pairs: FMA-pipe exp2
+              exp2_poly2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              p0 = ex2(x0);
+              p1 = ex2(x1);
+            }
+            lsum2 = add2(lsum2, pack2(p0, p1));
+            pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
+          }
+        }
+      };
+      if (kv0 + kBKV > p.N) softmax_body(std::true_type{});
+      else softmax_body(std::false_type{});
       float l0, l1;
       unpack2(lsum2, l0, l1);
       l_run = l_run * alpha + (l0 + l1);
-      m_run = m_new;
       ATT_TRACE(3);
-      if (j > 0) {   // O_{j-1} finished while the exponentials above were computed; P_{j-1} is no longer read
+      if (j > 0) {   // P_{j-1} must have been consumed (and O_{j-1} accumulated) before P / O are touched
         mbar_wait(bar_o, (j - 1) & 1);
         tc_fence_after();
-        fold_o(alpha_prev);
-      }
-      alpha_prev = alpha;
-      ATT_TRACE(4);
-      // P[row][kv] bf16, K-major, 128B swizzle: halves of 64 kv columns (16 KB each)
+        if (moved) {   // rare after the first blocks: rescale the TMEM accumulator in place
+          const uint64_t alpha2 = pack2(alpha, alpha);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t half_base = prow + (c >> 1) * kTileBytes;
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q) ^ static_cast<uint32_t>(tid & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(half_base + chunk * 16), "r"(pk[c * 16 + q * 4]),
-                       "r"(pk[c * 16 + q * 4 + 1]), "r"(pk[c * 16 + q * 4 + 2]), "r"(pk[c * 16 + q * 4 + 3])
-                       : "memory");
+            for (int i = 0; i < 32; i += 2) {
+              float a, bq;
+              unpack2(fma2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2, 0ull), a, bq);
+              r[i] = __float_as_uint(a);
+              r[i + 1] = __float_as_uint(bq);
+            }
+            tmem_st_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+          }
         }
       }
-      fence_proxy_async_smem();   // P stores -> visible to the tensor core (async proxy)
+      ATT_TRACE(4);
+      // P (bf16 pairs) -> TMEM columns [192, 256): the A operand of O += P V
+      tmem_st_32x32b_x32(tmem_P + lane_sel, pk);
+      tmem_st_32x32b_x32(tmem_P + lane_sel + 32, pk + 32);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pready);
@@ -284,27 +340,29 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     }
     mbar_wait(bar_o, (nkv - 1) & 1);
     tc_fence_after();
-    fold_o(alpha_prev);
 
     // ---- normalise and store
     const int q = q0 + tid;
-    if (q < p.N) {
-      const float inv = 1.f / l_run;
-      __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
 #pragma unroll
-      for (int i = 0; i < kHD / 2; i += 4) {
-        float v[8];
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+      tmem_ld_wait();
+      if (q < p.N) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) unpack2(o_acc[i + k], v[2 * k], v[2 * k + 1]);
-        uint4 o;
-        o.x = cvt_bf16x2(v[0] * inv, v[1] * inv);
-        o.y = cvt_bf16x2(v[2] * inv, v[3] * inv);
-        o.z = cvt_bf16x2(v[4] * inv, v[5] * inv);
-        o.w = cvt_bf16x2(v[6] * inv, v[7] * inv);
-        *reinterpret_cast<uint4*>(op + i * 2) = o;
+        for (int i = 0; i < 32; i += 8) {
+          uint4 o;
+          o.x = cvt_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+          o.y = cvt_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+          o.z = cvt_bf16x2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+          o.w = cvt_bf16x2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c * 32 + i) = o;
+        }
       }
-      if (p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_run + log2f(l_run)) * 0.69314718055994531f;
     }
+    if (q < p.N && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_run)) * 0.69314718055994531f;
   }
   tc_fence_before();
   __syncthreads();

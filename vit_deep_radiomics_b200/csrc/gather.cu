@@ -17,7 +17,7 @@ struct G1Geom {
   const int32_t* row_map;
   const int32_t* col_map;
   int S, h, w;
-  int64_t mask_slice_stride, mask_row_stride;   // bytes between slices / rows of the pixel mask
+  int64_t mask_slice_stride, mask_row_stride, mask_col_stride;   // bytes between slices / rows / columns of the pixel mask
   int64_t feat_slice_rows, feat_row_pitch, feat_row0;  // token row = k*slice_rows + row0 + a*pitch + b
   int64_t total;
 };
@@ -28,7 +28,7 @@ __device__ __forceinline__ bool g1_pred(const G1Geom& g, int64_t n) {
   const int64_t q = n / g.S;
   const int b = static_cast<int>(q % g.w);
   const int a = static_cast<int>(q / g.w);
-  const int64_t off = static_cast<int64_t>(k) * g.mask_slice_stride + __ldg(g.row_map + a) * g.mask_row_stride + __ldg(g.col_map + b);
+  const int64_t off = static_cast<int64_t>(k) * g.mask_slice_stride + __ldg(g.row_map + a) * g.mask_row_stride + __ldg(g.col_map + b) * g.mask_col_stride;
   return __ldg(g.mask + off) != 0;
 }
 
@@ -97,11 +97,8 @@ struct G1Pe {
   double w_orig, h_orig, res0, res1, res2, noise0, noise1, noise2, mean_x, mean_y, mean_z;
 };
 
-template <bool FEAT_BF16>
 __global__ void __launch_bounds__(kGThreads)
-g1_scatter_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int D,
-                  const int32_t* __restrict__ tile_offsets, float* __restrict__ out_tok,
-                  int32_t* __restrict__ out_src, int cap, G1Pe pe, bool vec_ok) {
+g1_scatter_kernel(G1Geom g, const int32_t* __restrict__ tile_offsets, int32_t* __restrict__ out_src, int cap) {
   __shared__ int s_cnt[kIters * 8];
   __shared__ int s_off[kIters * 8 + 1];
   __shared__ int s_sel[kTile];
@@ -142,24 +139,38 @@ g1_scatter_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int 
   __syncthreads();
   const int tile_n = s_off[kIters * 8];
   const int64_t tile_off = tile_offsets[blockIdx.x];
-  const int third = D / 3, two_third = (2 * D) / 3, npair2 = 2 * (D / 6);
-  for (int j = warp; j < tile_n; j += 8) {
+  // write the (slice, row, col) of every selected candidate of this tile, in order
+  for (int j = threadIdx.x; j < tile_n; j += kGThreads) {
     const int64_t row_out = tile_off + j;
     if (row_out >= cap) break;
     const int64_t n = tile_base + s_sel[j];
     const int k = static_cast<int>(n % g.S);
     const int64_t q = n / g.S;
-    const int b = static_cast<int>(q % g.w);
-    const int a = static_cast<int>(q / g.w);
-    if (lane == 0) {
-      out_src[row_out * 3 + 0] = k;
-      out_src[row_out * 3 + 1] = a;
-      out_src[row_out * 3 + 2] = b;
-    }
+    out_src[row_out * 3 + 0] = k;
+    out_src[row_out * 3 + 1] = static_cast<int>(q / g.w);
+    out_src[row_out * 3 + 2] = static_cast<int>(q % g.w);
+  }
+}
+
+// One warp per OUTPUT row (grid-stride over the device-side count): copies the descriptor row and adds the
+// positional encoding.  Decoupled from the compaction so that the fp64 sin/cos work is spread evenly over
+// the SMs however the mask is distributed over the candidate tiles.
+template <bool FEAT_BF16>
+__global__ void __launch_bounds__(kGThreads)
+g1_emit_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int D, const int32_t* __restrict__ out_src,
+               const int32_t* __restrict__ out_count, float* __restrict__ out_tok, int cap, G1Pe pe, bool vec_ok) {
+  const int lane = threadIdx.x & 31;
+  int64_t count = *out_count;
+  if (count > cap) count = cap;
+  const int third = D / 3, two_third = (2 * D) / 3, npair2 = 2 * (D / 6);
+  for (int64_t row_out = blockIdx.x * (int64_t)(kGThreads / 32) + (threadIdx.x >> 5); row_out < count;
+       row_out += (int64_t)gridDim.x * (kGThreads / 32)) {
+    const int k = out_src[row_out * 3 + 0], a = out_src[row_out * 3 + 1], b = out_src[row_out * 3 + 2];
+    const int64_t n = (static_cast<int64_t>(a) * g.w + b) * g.S + k;
     double x = 0., y = 0., z = 0.;
     if (pe.scale != 0.) {
       // reference meshgrid(indexing='xy') quirk: xi = (n / S) % h, yi = n / (h*S), zi = n % S
-      const double xi = static_cast<double>(q % g.h), yi = static_cast<double>(n / (static_cast<int64_t>(g.h) * g.S));
+      const double xi = static_cast<double>((n / g.S) % g.h), yi = static_cast<double>(n / (static_cast<int64_t>(g.h) * g.S));
       x = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(xi / static_cast<double>(g.w), pe.w_orig), pe.res0), pe.mean_x), pe.noise0);
       y = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(yi / static_cast<double>(g.h), pe.h_orig), pe.res1), pe.mean_y), pe.noise1);
       z = __dadd_rn(__dsub_rn(__dmul_rn(static_cast<double>(k), pe.res2), pe.mean_z), pe.noise2);
@@ -176,7 +187,7 @@ g1_scatter_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int 
         const double enc = (jj & 1) ? cos(arg) : sin(arg);
         return static_cast<float>(__dadd_rn(static_cast<double>(f), __dmul_rn(enc, pe.scale)));
       }
-      return static_cast<float>(static_cast<double>(f));
+      return f;
     };
     if (vec_ok) {
       for (int c0 = lane * 8; c0 < D; c0 += 256) {
@@ -214,7 +225,10 @@ __global__ void bbox_init_kernel(int32_t* bbox) {
   if (threadIdx.x < 6) bbox[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
 }
 
-__global__ void __launch_bounds__(256) voxel_bbox_kernel(const uint8_t* __restrict__ mask, int H, int S,
+// kRowCol = false: the reference's xy-meshgrid convention (xi = (n/S) % H, yi = n/(H*S));  true: (col, row) of voxel n,
+// i.e. the bounding box of the union mask over slices that generate_features starts from (tfds_dense_descriptor.py:257-260).
+template <bool kRowCol>
+__global__ void __launch_bounds__(256) voxel_bbox_kernel(const uint8_t* __restrict__ mask, int H, int W, int S,
                                                          int64_t total, int32_t* __restrict__ bbox) {
   int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-1, -1, -1};
   // 16 mask bytes per thread per step
@@ -235,7 +249,8 @@ __global__ void __launch_bounds__(256) voxel_bbox_kernel(const uint8_t* __restri
         const int64_t n = (v << 4) + i;
         const int zi = static_cast<int>(n % S);
         const int64_t q = n / S;
-        const int xi = static_cast<int>(q % H), yi = static_cast<int>(q / H);
+        const int xi = kRowCol ? static_cast<int>(q % W) : static_cast<int>(q % H);
+        const int yi = kRowCol ? static_cast<int>(q / W) : static_cast<int>(q / H);
         lo[0] = min(lo[0], xi); hi[0] = max(hi[0], xi);
         lo[1] = min(lo[1], yi); hi[1] = max(hi[1], yi);
         lo[2] = min(lo[2], zi); hi[2] = max(hi[2], zi);
@@ -289,7 +304,7 @@ extern "C" size_t vdr_mask_gather_workspace_bytes(int S, int h, int w) {
 
 extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
                                int64_t feat_row_pitch, int64_t feat_row0, const uint8_t* mask,
-                               int64_t mask_slice_stride, int64_t mask_row_stride,
+                               int64_t mask_slice_stride, int64_t mask_row_stride, int64_t mask_col_stride,
                                const int32_t* row_map, const int32_t* col_map, int S, int h, int w, int D,
                                float* out_tok, int32_t* out_src, int32_t* out_count, int cap, double pe_scale,
                                const double* pe_div, const double* coef_host, void* workspace,
@@ -297,7 +312,7 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   using namespace vdr;
   VDR_CHECK_ARG(feat && mask && row_map && col_map && out_tok && out_src && out_count && workspace, VDR_EINVAL, "vdr_mask_gather: null pointer");
   VDR_CHECK_ARG(S > 0 && h > 0 && w > 0 && D > 0 && cap >= 0, VDR_EINVAL, "vdr_mask_gather: bad shape");
-  VDR_CHECK_ARG(feat_slice_rows >= 0 && feat_row_pitch >= w && feat_row0 >= 0 && mask_slice_stride >= 0 && mask_row_stride >= 0, VDR_EINVAL, "vdr_mask_gather: bad strides");
+  VDR_CHECK_ARG(feat_slice_rows >= 0 && feat_row_pitch >= w && feat_row0 >= 0 && mask_slice_stride >= 0 && mask_row_stride >= 0 && mask_col_stride >= 1, VDR_EINVAL, "vdr_mask_gather: bad strides");
   VDR_CHECK_ARG(ld_feat >= D, VDR_EINVAL, "vdr_mask_gather: ld_feat (%lld) smaller than D (%d)", (long long)ld_feat, D);
   // 16-byte vector path when the rows allow it; otherwise an element-wise path (any D, e.g. the reference's D = 12 tests)
   const bool vec_ok = D % 8 == 0 && ld_feat % 8 == 0 && aligned16(feat) && aligned16(out_tok);
@@ -306,7 +321,7 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   VDR_CHECK_ARG(workspace_bytes >= vdr_mask_gather_workspace_bytes(S, h, w), VDR_EWORKSPACE, "vdr_mask_gather: workspace too small (%zu < %zu)", workspace_bytes, vdr_mask_gather_workspace_bytes(S, h, w));
   VDR_CHECK_ARG(pe_scale == 0.0 || (pe_div && coef_host), VDR_EINVAL, "vdr_mask_gather: positional encoding needs pe_div and coef_host");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  G1Geom g{mask, row_map, col_map, S, h, w, mask_slice_stride, mask_row_stride, feat_slice_rows, feat_row_pitch, feat_row0, (int64_t)S * h * w};
+  G1Geom g{mask, row_map, col_map, S, h, w, mask_slice_stride, mask_row_stride, mask_col_stride, feat_slice_rows, feat_row_pitch, feat_row0, (int64_t)S * h * w};
   const int tiles = (int)((g.total + kTile - 1) / kTile);
   int32_t* counts = static_cast<int32_t*>(workspace);
   int32_t* offsets = counts + tiles;
@@ -323,12 +338,17 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   VDR_CHECK_LAUNCH("g1_count_kernel");
   tile_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, tiles, out_count);
   VDR_CHECK_LAUNCH("tile_scan_kernel");
-  if (feat_dtype == VDR_DTYPE_BF16)
-    g1_scatter_kernel<true><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe, vec_ok);
-  else
-    g1_scatter_kernel<false><<<tiles, kGThreads, 0, s>>>(g, feat, ld_feat, D, offsets, out_tok, out_src, cap, pe, vec_ok);
-  count_launch(3);
+  g1_scatter_kernel<<<tiles, kGThreads, 0, s>>>(g, offsets, out_src, cap);
   VDR_CHECK_LAUNCH("g1_scatter_kernel");
+  int emit_blocks = (cap + (kGThreads / 32) - 1) / (kGThreads / 32);
+  if (emit_blocks > num_sms() * 8) emit_blocks = num_sms() * 8;
+  if (emit_blocks < 1) emit_blocks = 1;
+  if (feat_dtype == VDR_DTYPE_BF16)
+    g1_emit_kernel<true><<<emit_blocks, kGThreads, 0, s>>>(g, feat, ld_feat, D, out_src, out_count, out_tok, cap, pe, vec_ok);
+  else
+    g1_emit_kernel<false><<<emit_blocks, kGThreads, 0, s>>>(g, feat, ld_feat, D, out_src, out_count, out_tok, cap, pe, vec_ok);
+  count_launch(4);
+  VDR_CHECK_LAUNCH("g1_emit_kernel");
   return VDR_OK;
 }
 
@@ -344,7 +364,25 @@ extern "C" int vdr_voxel_bbox(const uint8_t* mask, int H, int W, int S, int32_t*
   int64_t blocks = ((total >> 4) + 1 + 255) / 256;
   const int64_t capb = (int64_t)num_sms() * 8;
   if (blocks > capb) blocks = capb;
-  voxel_bbox_kernel<<<(unsigned)blocks, 256, 0, s>>>(mask, H, S, total, bbox);
+  voxel_bbox_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(mask, H, W, S, total, bbox);
+  count_launch(2);
+  VDR_CHECK_LAUNCH("voxel_bbox_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_mask_bbox(const uint8_t* mask, int H, int W, int S, int32_t* bbox, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(mask && bbox, VDR_EINVAL, "vdr_mask_bbox: null pointer");
+  VDR_CHECK_ARG(H > 0 && W > 0 && S > 0, VDR_EINVAL, "vdr_mask_bbox: bad shape");
+  VDR_CHECK_ARG((int64_t)H * W * S < 0x7fffffffLL, VDR_EINVAL, "vdr_mask_bbox: volume too large for int32 flat indices");
+  VDR_CHECK_ARG(aligned16(mask), VDR_EALIGN, "vdr_mask_bbox: mask must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)H * W * S;
+  bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
+  int64_t blocks = ((total >> 4) + 1 + 255) / 256;
+  const int64_t capb = (int64_t)num_sms() * 8;
+  if (blocks > capb) blocks = capb;
+  voxel_bbox_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(mask, H, W, S, total, bbox);
   count_launch(2);
   VDR_CHECK_LAUNCH("voxel_bbox_kernel");
   return VDR_OK;

@@ -231,14 +231,26 @@ def grid_means(h: int, w: int, S: int, h_orig: int, w_orig: int, res) -> tuple:
     return float(x.mean()), float(y.mean()), float(z.mean())
 
 
+_MAP_CACHE: dict = {}
+
+
+def _index_map_dev(n_out: int, n_in: int, dev) -> torch.Tensor:
+    key = (n_out, n_in, str(dev))
+    if key not in _MAP_CACHE:
+        _MAP_CACHE[key] = torch.from_numpy(nearest_index_map(n_out, n_in)).to(dev)
+    return _MAP_CACHE[key]
+
+
 def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = None, pe: dict | None = None,
-                grid: tuple | None = None, feat_roi: tuple | None = None, mask_roi: tuple | None = None):
+                grid: tuple | None = None, feat_roi: tuple | None = None, mask_roi: tuple | None = None,
+                mask_layout: str = "shw"):
     """G1 (reference src/train_models.py:143-182 on device).
 
     feat     (S, h, w, D) dense descriptors, or the backbone's token matrix (S*slice_rows, D) together
              with ``grid=(S, gh, gw, slice_rows, first_row)`` (CLS-first layout: slice_rows = gh*gw+1,
              first_row = 1).  bf16 or f32, CUDA, unit inner stride.
-    mask_u8  (S, HM, WM) uint8 CUDA pixel masks (contiguous).
+    mask_u8  uint8 CUDA pixel masks, contiguous: (S, HM, WM) with mask_layout="shw", or the (HM, WM, S) volume
+             mask read in place with mask_layout="hws" (no transpose pass).
     feat_roi (r0, r1, c0, c1) feature-grid window, mask_roi (y0, y1, x0, x1) pixel window: the
              extract_roi crops of tfds_dense_descriptor.py:278-279, applied by pointer arithmetic.
     pe       dict(res=(3,), noise=(3,), scale=0.25): add the 3-D positional encoding / 4 (:178-180).
@@ -262,17 +274,24 @@ def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = 
             raise ValueError("token matrix too small / not unit inner stride")
     else:
         raise ValueError("feat must be (S,h,w,D) or a token matrix with grid=(S,gh,gw,slice_rows,first_row)")
-    if mask_u8.shape[0] != S:
-        raise ValueError(f"mask has {mask_u8.shape[0]} slices, features {S}")
+    if mask_layout == "shw":
+        SM, HM, WM = mask_u8.shape
+        ms, mr, mc = HM * WM, WM, 1
+    elif mask_layout == "hws":
+        HM, WM, SM = mask_u8.shape
+        ms, mr, mc = 1, WM * SM, SM
+    else:
+        raise ValueError("mask_layout must be 'shw' or 'hws'")
+    if SM != S:
+        raise ValueError(f"mask has {SM} slices, features {S}")
     r0, r1, c0, c1 = feat_roi if feat_roi is not None else (0, gh, 0, gw)
-    HM, WM = mask_u8.shape[1], mask_u8.shape[2]
     y0, y1, x0, x1 = mask_roi if mask_roi is not None else (0, HM, 0, WM)
     h, w, hm, wm = r1 - r0, c1 - c0, y1 - y0, x1 - x0
     if min(h, w, hm, wm) <= 0 or r1 > gh or c1 > gw or y1 > HM or x1 > WM or min(r0, c0, y0, x0) < 0:
         raise ValueError("empty or out-of-range ROI")
     dev = feat.device
-    row_map = torch.from_numpy(nearest_index_map(h, hm)).to(dev)
-    col_map = torch.from_numpy(nearest_index_map(w, wm)).to(dev)
+    row_map = _index_map_dev(h, hm, dev)
+    col_map = _index_map_dev(w, wm, dev)
     if cap is None:
         cap = S * h * w
     tokens = torch.empty((cap, D), dtype=torch.float32, device=dev)
@@ -288,7 +307,7 @@ def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = 
         pe_scale = float(pe.get("scale", 0.25))
         pe_div_ptr = _pe_div(D, dev).data_ptr()
     _C.check(_C.lib().vdr_mask_gather(feat.data_ptr(), _DT[feat.dtype], ld, slice_rows, gw, first_row + r0 * gw + c0,
-                                      mask_u8.data_ptr() + y0 * WM + x0, HM * WM, WM,
+                                      mask_u8.data_ptr() + y0 * mr + x0 * mc, ms, mr, mc,
                                       row_map.data_ptr(), col_map.data_ptr(), S, h, w, D,
                                       tokens.data_ptr(), src.data_ptr(), count.data_ptr(), cap,
                                       pe_scale, pe_div_ptr, coef, ws.data_ptr(), ws_bytes, _stream()),
@@ -303,6 +322,17 @@ def voxel_bbox(mask_u8: torch.Tensor) -> torch.Tensor:
     bbox = torch.empty(6, dtype=torch.int32, device=mask_u8.device)
     _C.check(_C.lib().vdr_voxel_bbox(mask_u8.data_ptr(), H, W, S, bbox.data_ptr(), _stream()), "vdr_voxel_bbox")
     return bbox
+
+
+def mask_bbox(mask_u8: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(col_min, col_max, row_min, row_max, slice_min, slice_max) int32[6] of an (H, W, S) uint8 mask: the bounding
+    box of the union mask over slices (reference tfds_dense_descriptor.py:257-260) without a host pass."""
+    _req(mask_u8, torch.uint8, "mask")
+    H, W, S = mask_u8.shape
+    if out is None:
+        out = torch.empty(6, dtype=torch.int32, device=mask_u8.device)
+    _C.check(_C.lib().vdr_mask_bbox(mask_u8.data_ptr(), H, W, S, out.data_ptr(), _stream()), "vdr_mask_bbox")
+    return out
 
 
 def voxel_gather(img: torch.Tensor, mask_u8: torch.Tensor, bbox: torch.Tensor, cap: int):

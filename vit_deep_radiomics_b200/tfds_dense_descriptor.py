@@ -20,7 +20,8 @@ import numpy as np
 import torch
 
 from . import ops
-from .visualization_utils import crop_image, crop_window, extract_roi, roi_window
+from .visualization_utils import (crop_image, crop_window, crop_window_from_bbox, extract_roi, mask_bbox, roi_window,
+                                  roi_window_from_bbox)
 from .vit import VIT_CONFIGS, ViTBackbone
 
 # --------------------------------------------------------------------------------------------- model
@@ -70,24 +71,47 @@ def get_dense_descriptor(model, img):
 
 
 # --------------------------------------------------------------------------------------------- volume level
+def _plan_from_bbox(model, H, W, bbox):
+    """Host-side index math of generate_features (:257-267, :278-279) from the union mask's bounding box
+    (row_min, row_max, col_min, col_max): crop window, feature ROI, pixel-mask ROI.  Pure integer geometry.
+    Returns None when the box is not inside its own crop window (then the cropped mask must be inspected)."""
+    rmin, rmax, cmin, cmax = bbox
+    x0, y0, x1, y1 = crop_window_from_bbox(bbox)
+    y0c, y1c = [max(0, min(v, H)) for v in (y0, y1)]
+    x0c, x1c = [max(0, min(v, W)) for v in (x0, x1)]
+    if not (y0c <= rmin and rmax < y1c and x0c <= cmin and cmax < x1c):
+        return None
+    ch, cw = y1c - y0c, x1c - x0c
+    if (ch, cw) != tuple(model.img_hw):
+        raise NotImplementedError(
+            f"crop window {ch}x{cw} differs from the backbone input {model.img_hw}: the resize of "
+            "prepare_image is not implemented on the device path (scope row N2); build the model with img_hw="
+            f"({ch}, {cw})")
+    bbox_c = (rmin - y0c, rmax - y0c, cmin - x0c, cmax - x0c)            # union mask after crop_image (:267)
+    gh, gw = model.grid
+    fx0, fy0, fx1, fy1 = roi_window_from_bbox((gh, gw), (ch, cw), bbox_c, margin=1)   # extract_roi(features, bigger_mask)
+    mx0, my0, mx1, my1 = roi_window_from_bbox((ch, cw), (ch, cw), bbox_c, margin=1)   # extract_roi(mask, bigger_mask)
+    return dict(crop=(y0c, y1c, x0c, x1c), feat_roi=(fy0, fy1, fx0, fx1), mask_roi=(my0, my1, mx0, mx1))
+
+
 def _plan(model, mask_3d):
-    """Host-side index math of generate_features (:257-267, :278-279): crop window, feature ROI,
-    pixel-mask ROI.  Pure integer geometry on the union mask."""
+    """Plan from a host mask (H, W, S)."""
     H, W = mask_3d.shape[0:2]
     bigger = np.any(mask_3d, axis=-1)                                    # == (np.sum(mask_3d, -1) > 0), :257
+    plan = _plan_from_bbox(model, H, W, mask_bbox(bigger))
+    if plan is not None:
+        return plan
+    # rare: the (shifted) crop window cuts the mask -> use the cropped union mask itself, as the reference does
     x0, y0, x1, y1 = crop_window(bigger)
     y0c, y1c = [max(0, min(v, H)) for v in (y0, y1)]
     x0c, x1c = [max(0, min(v, W)) for v in (x0, x1)]
     bigger_c = bigger[y0c:y1c, x0c:x1c]
     ch, cw = bigger_c.shape
     if (ch, cw) != tuple(model.img_hw):
-        raise NotImplementedError(
-            f"crop window {ch}x{cw} differs from the backbone input {model.img_hw}: the resize of "
-            "prepare_image is not implemented on the device path (scope row N2); build the model with img_hw="
-            f"({ch}, {cw})")
+        raise NotImplementedError(f"crop window {ch}x{cw} differs from the backbone input {model.img_hw} (scope row N2)")
     gh, gw = model.grid
-    fx0, fy0, fx1, fy1 = roi_window((gh, gw), bigger_c, margin=1)      # extract_roi(features, bigger_mask)
-    mx0, my0, mx1, my1 = roi_window((ch, cw), bigger_c, margin=1)      # extract_roi(mask, bigger_mask)
+    fx0, fy0, fx1, fy1 = roi_window((gh, gw), bigger_c, margin=1)
+    mx0, my0, mx1, my1 = roi_window((ch, cw), bigger_c, margin=1)
     return dict(crop=(y0c, y1c, x0c, x1c), feat_roi=(fy0, fy1, fx0, fx1), mask_roi=(my0, my1, mx0, mx1))
 
 
@@ -131,37 +155,110 @@ def generate_features(model, img_3d, mask_3d, tqdm_text="", display=False, max_b
     return features_list, mask_list
 
 
-def extract_point_cloud(model, img_3d, mask_3d, spatial_res, noise=(0.0, 0.0, 0.0), add_pe=True,
-                        pinned=None, to_host=True):
-    """Fused device path for one patient: what ``_get_features`` (train_models.py:143-182) returns for
-    the features/masks that ``generate_features`` produces, without leaving the GPU in between.
+def _as_pinned_pair(img_3d, mask_3d):
+    img_t = img_3d if isinstance(img_3d, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(img_3d, dtype=np.float32))
+    if isinstance(mask_3d, torch.Tensor):
+        mask_t = mask_3d
+    else:
+        m = np.ascontiguousarray(mask_3d)
+        mask_t = torch.as_tensor(m.view(np.uint8) if m.dtype == bool else (m > 0).view(np.uint8))
+    return img_t, mask_t
+
+
+class PointCloudExtractor:
+    """Fused device path for a stream of patients: crop -> batched ViT forward -> ROI -> tumour-mask gather
+    (+ positional encoding), i.e. what ``_get_features`` (train_models.py:143-182) returns for the features /
+    masks ``generate_features`` produces, without the HDF5 hand-off and without leaving the GPU in between.
+
+    Uploads are double-buffered on a copy stream: while patient i is in the backbone, patient i+1's volume and
+    mask cross PCIe, and the union-mask bounding box that the crop geometry needs (tfds_dense_descriptor.py:257-263)
+    is reduced on the device from the uploaded mask (24-byte read-back) instead of a host pass over 31 M voxels.
+    """
+
+    def __init__(self, model):
+        self.model = model
+        self.copy_stream = torch.cuda.Stream(device=model.device)
+        self.slots = [dict(), dict()]
+
+    def _upload(self, slot, img_t, mask_t):
+        dev = self.model.device
+        b = self.slots[slot]
+        if b.get("shape") != tuple(img_t.shape):
+            b.update(shape=tuple(img_t.shape), img=torch.empty(img_t.shape, dtype=torch.float32, device=dev),
+                     mask=torch.empty(mask_t.shape, dtype=torch.uint8, device=dev),
+                     bbox=torch.empty(6, dtype=torch.int32, device=dev),
+                     bbox_host=torch.empty(6, dtype=torch.int32).pin_memory(), ev=torch.cuda.Event(), ev_box=torch.cuda.Event())
+        with torch.cuda.stream(self.copy_stream):
+            if "free" in b:
+                self.copy_stream.wait_event(b["free"])          # the previous user of this slot has been consumed
+            b["mask"].copy_(mask_t, non_blocking=True)
+            ops.mask_bbox(b["mask"], out=b["bbox"])
+            b["bbox_host"].copy_(b["bbox"], non_blocking=True)
+            b["ev_box"].record(self.copy_stream)
+            b["img"].copy_(img_t, non_blocking=True)
+            b["ev"].record(self.copy_stream)
+
+    def _compute(self, slot, spatial_res, noise, add_pe):
+        model, b = self.model, self.slots[slot]
+        b["ev_box"].synchronize()                                # 24-byte bounding box is on the host
+        cmin, cmax, rmin, rmax, _, _ = (int(v) for v in b["bbox_host"])
+        if cmax < cmin:
+            raise ValueError("extract_coords: empty mask")
+        H, W, S = b["shape"]
+        plan = _plan_from_bbox(model, H, W, (rmin, rmax, cmin, cmax))
+        if plan is None:
+            plan = _plan(model, b["mask"].cpu().numpy())
+        main = torch.cuda.current_stream(model.device)
+        main.wait_event(b["ev"])
+        tok = _forward_volume(model, b["img"], plan)
+        gh, gw = model.grid
+        pe = dict(res=spatial_res, noise=noise, scale=0.25) if add_pe else None
+        tokens, src, count = ops.mask_gather(tok, b["mask"], grid=(S, gh, gw, model.n_tokens, 1), feat_roi=plan["feat_roi"],
+                                             mask_roi=_shift_roi(plan["mask_roi"], plan["crop"]), pe=pe, mask_layout="hws")
+        b["free"] = torch.cuda.Event()
+        b["free"].record(main)
+        return plan, tokens, src, count
+
+    def run(self, items, add_pe=True, to_host=True):
+        """items: iterable of (img_3d, mask_3d, spatial_res[, noise]); yields one result dict per patient."""
+        it = iter(items)
+        nxt = next(it, None)
+        slot = 0
+        if nxt is not None:
+            self._upload(slot, *_as_pinned_pair(nxt[0], nxt[1]))
+        while nxt is not None:
+            cur, cur_slot = nxt, slot
+            plan, tokens, src, count = self._compute(cur_slot, cur[2], cur[3] if len(cur) > 3 else (0.0, 0.0, 0.0), add_pe)
+            nxt = next(it, None)
+            slot ^= 1
+            if nxt is not None:                                   # overlaps with the backbone of `cur`
+                self._upload(slot, *_as_pinned_pair(nxt[0], nxt[1]))
+            out = dict(plan=plan)
+            if to_host:
+                n = int(count.item())                             # D2H sync: the step's result
+                out.update(tokens=tokens[:n].cpu(), src=src[:n].cpu(), count=n)
+            else:
+                out.update(tokens=tokens, src=src, count=count)
+            yield out
+
+
+def _shift_roi(mask_roi, crop):
+    """ROI of the cropped mask -> window of the full (H, W, S) mask."""
+    my0, my1, mx0, mx1 = mask_roi
+    y0, _, x0, _ = crop
+    return (my0 + y0, my1 + y0, mx0 + x0, mx1 + x0)
+
+
+def extract_point_cloud(model, img_3d, mask_3d, spatial_res, noise=(0.0, 0.0, 0.0), add_pe=True, to_host=True):
+    """One patient through the fused device path (see PointCloudExtractor).
 
     img_3d (H, W, S) float32 in 0..1, mask_3d (H, W, S) bool/uint8 (numpy, or pinned torch tensors).
     Returns dict(tokens (n, D) f32, src (n, 3) int32 (slice, row, col) in ROI coords, count, plan).
     """
-    mask_np = mask_3d.numpy() if isinstance(mask_3d, torch.Tensor) else np.asarray(mask_3d)
-    plan = _plan(model, mask_np)
-    dev = model.device
-    img_t = img_3d if isinstance(img_3d, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(img_3d, dtype=np.float32))
-    mask_t = mask_3d if isinstance(mask_3d, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(mask_np).view(np.uint8) if mask_np.dtype == bool else np.ascontiguousarray(mask_np, dtype=np.uint8))
-    img_dev = img_t.to(dev, non_blocking=True)
-    mask_dev = mask_t.to(dev, non_blocking=True)                       # (H, W, S) u8
-    tok = _forward_volume(model, img_dev, plan)
-    S = img_dev.shape[2]
-    y0, y1, x0, x1 = plan["crop"]
-    # pixel masks slice-major for the gather (S, ch, cw): a u8 transpose of the crop, done on the device
-    mask_s = mask_dev[y0:y1, x0:x1].permute(2, 0, 1).contiguous()
-    gh, gw = model.grid
-    pe = dict(res=spatial_res, noise=noise, scale=0.25) if add_pe else None
-    tokens, src, count = ops.mask_gather(tok, mask_s, grid=(S, gh, gw, model.n_tokens, 1), feat_roi=plan["feat_roi"],
-                                         mask_roi=plan["mask_roi"], pe=pe)
-    out = dict(plan=plan)
-    if to_host:
-        n = int(count.item())                                          # D2H sync: the step's result
-        out.update(tokens=tokens[:n].cpu(), src=src[:n].cpu(), count=n)
-    else:
-        out.update(tokens=tokens, src=src, count=count)
-    return out
+    ex = getattr(model, "_extractor", None)
+    if ex is None:
+        ex = model._extractor = PointCloudExtractor(model)
+    return next(ex.run([(img_3d, mask_3d, spatial_res, noise)], add_pe=add_pe, to_host=to_host))
 
 
 # --------------------------------------------------------------------------------------------- host helpers

@@ -16,29 +16,44 @@ def crop_image(img, xmin, ymin, xmax, ymax):
     return img[ymin:ymax, xmin:xmax]
 
 
-def extract_coords(mask, margin):
-    """reference: visualization_utils.py:101-112.  NOTE the reference SHIFTS the bounding box by
-    `margin` (rows up, columns right) and keeps extent max-min; it does not expand it.  Kept as is."""
+def mask_bbox(mask):
+    """(row_min, row_max, col_min, col_max) of the True pixels of a 2-D mask."""
     rows = np.flatnonzero(np.any(mask, axis=1))
     cols = np.flatnonzero(np.any(mask, axis=0))
     if rows.size == 0:
         raise ValueError("extract_coords: empty mask")  # reference: np.min of an empty array raises too
-    ymin = int(rows[0]) - margin
-    xmin = int(cols[0]) + margin
-    ymax = int(rows[-1]) - margin
-    xmax = int(cols[-1]) + margin
+    return int(rows[0]), int(rows[-1]), int(cols[0]), int(cols[-1])
+
+
+def coords_from_bbox(bbox, margin):
+    """extract_coords expressed on the mask's bounding box (row_min, row_max, col_min, col_max) -- all the
+    reference's formula uses (visualization_utils.py:101-112).  NOTE the reference SHIFTS the box by `margin`
+    (rows up, columns right) and keeps extent max-min; it does not expand it.  Kept as is."""
+    rmin, rmax, cmin, cmax = bbox
+    ymin, xmin = rmin - margin, cmin + margin
+    ymax, xmax = rmax - margin, cmax + margin
     h = max(ymax - ymin, margin)
     w = max(xmax - xmin, margin)
     return xmin, ymin, xmin + w, ymin + h
 
 
+def extract_coords(mask, margin):
+    """reference: visualization_utils.py:101-112."""
+    return coords_from_bbox(mask_bbox(mask), margin)
+
+
 def roi_window(img_hw, mask, margin=1):
     """(xmin, ymin, xmax, ymax) that extract_roi crops from an array of spatial shape img_hw,
     clamped like crop_image.  reference: visualization_utils.py:115-125."""
-    xmin, ymin, xmax, ymax = extract_coords(mask, margin)
-    if tuple(img_hw) != tuple(mask.shape[0:2]):
-        hs = img_hw[0] / mask.shape[0]
-        ws = img_hw[1] / mask.shape[1]
+    return roi_window_from_bbox(img_hw, mask.shape[0:2], mask_bbox(mask), margin)
+
+
+def roi_window_from_bbox(img_hw, mask_hw, bbox, margin=1):
+    """roi_window given only the mask's shape and bounding box (row_min, row_max, col_min, col_max)."""
+    xmin, ymin, xmax, ymax = coords_from_bbox(bbox, margin)
+    if tuple(img_hw) != tuple(mask_hw):
+        hs = img_hw[0] / mask_hw[0]
+        ws = img_hw[1] / mask_hw[1]
         xmin, ymin, xmax, ymax = [int(v) for v in (xmin * ws, ymin * hs, xmax * ws, ymax * hs)]
         h = max(ymax - ymin, margin)
         w = max(xmax - xmin, margin)
@@ -60,7 +75,12 @@ def crop_window(mask_3d):
     """Square crop window of generate_features (tfds_dense_descriptor.py:257-263), unclamped:
     half-side 2*max(bbox w, bbox h) about the (shifted) bbox centre of the union mask."""
     bigger = mask_3d if mask_3d.ndim == 2 else np.any(mask_3d, axis=-1)   # union over slices (:257)
-    xmin, ymin, xmax, ymax = extract_coords(bigger, margin=2)
+    return crop_window_from_bbox(mask_bbox(bigger))
+
+
+def crop_window_from_bbox(bbox):
+    """crop_window given the union mask's bounding box (row_min, row_max, col_min, col_max)."""
+    xmin, ymin, xmax, ymax = coords_from_bbox(bbox, margin=2)
     crop_size = max(xmax - xmin, ymax - ymin) * 2
     xmid, ymid = int(xmin + (xmax - xmin) / 2), int(ymin + (ymax - ymin) / 2)
     return xmid - crop_size, ymid - crop_size, xmid + crop_size, ymid + crop_size
