@@ -6,6 +6,8 @@
 //   warps 2..9  epilogue       (tcgen05.ld -> bias / GELU / residual -> vector stores)
 // Two TMEM accumulator buffers (2*BN columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  Replaces the torch.nn.Linear call sites listed in include/vdr.h.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vdr {
@@ -39,23 +41,29 @@ struct GemmParams {
   int out_group, out_group_stride, out_offset;
   int res_mod, res_offset;
   unsigned long long* trace;   // debug: per-tile timestamps of CTA 0 (nullptr = off)
+  int dbg;                     // debug: 1 = skip MMAs, 2 = skip TMA loads (timing experiments only; results are garbage)
 };
 
-template <int BN>
+// kCtas = 2: a CTA pair (cluster of two SMs, cta_group::2) computes a 256 x BN tile: each CTA stages its own 128 rows
+// of A and HALF of the BN rows of W per K block (32 KB instead of 48 KB at BN = 256), the leader CTA issues one
+// M = 256 tcgen05.mma that reads both halves, and each CTA's TMEM receives its 128 accumulator rows.  This halves
+// the B-operand shared-memory traffic, which bounds the single-CTA kernel (TMA writes + UMMA reads ~ 96 KB per
+// 512-cycle K block against 128 B/clk of shared-memory bandwidth).
+template <int BN, int kCtas>
 struct GemmCfg {
   static constexpr int kStageBytesA = BM * BK * 2;
-  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytesB = (BN / kCtas) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (kCtas == 2) ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 * 4 /*bias staging*/ + kEpiWarps * 2048 /*store staging*/;
 };
 
-template <int BN>
+template <int BN, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kCtas>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -70,10 +78,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM;
+  constexpr int kTileM = BM * kCtas;                        // rows of one (pair) tile
+  const int m_tiles = (p.M + kTileM - 1) / kTileM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
+  const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;   // both CTAs of a pair walk the same tiles
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -81,18 +92,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);                // pair: the leader's arrive.expect_tx covers the bytes of BOTH CTAs
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&tmem_empty[a], kEpiWarps * kCtas);   // pair: the epilogue warps of BOTH CTAs release the leader
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  if (warp == 2) {
+    if constexpr (kCtas == 2) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_ptr);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();   // barrier inits visible to the peer before any remote arrive / TMA credit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -102,14 +117,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
-          tma_load_2d(&tmW, &full_bar[stage], sa + Cfg::kStageBytesA, kb * BK, n_blk * BN);
+          if constexpr (kCtas == 2) {
+            // both CTAs load their own A rows and their half of W; all bytes are credited to the LEADER's barrier
+            const uint32_t lead_bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);
+            // (the peer's bytes may be credited before the leader's expect_tx of that phase: the transaction count
+            //  simply goes negative first; the phase cannot complete before the leader's own arrival)
+            if (p.dbg == 2) {
+              if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * 2);
+              tma_load_2d_2sm(&tmA, lead_bar, sa, kb * BK, m_blk * kTileM + static_cast<int>(cta_rank) * BM);
+              tma_load_2d_2sm(&tmW, lead_bar, sa + Cfg::kStageBytesA, kb * BK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
+            tma_load_2d(&tmW, &full_bar[stage], sa + Cfg::kStageBytesA, kb * BK, n_blk * BN);
+          }
           if (kb == 0) VDR_TRACE(5, it);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -118,14 +147,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && cta_rank == 0) {   // pair: only the leader CTA issues MMAs
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         VDR_TRACE(0, it);
@@ -139,14 +168,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
+            if (p.dbg == 1) break;
             // +32 bytes per K step inside the 128-byte swizzle row  (encoded address units of 16 B)
-            umma_ss(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kCtas == 2)
+              umma_ss_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_ss(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+          // smem slot free once these MMAs have read it (pair: in both CTAs)
+          if constexpr (kCtas == 2) umma_commit_2sm(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        // accumulator complete (pair: wakes the epilogue warps of both CTAs)
+        if constexpr (kCtas == 2) umma_commit_2sm(&tmem_full[acc], 3);
+        else umma_commit(&tmem_full[acc]);
         VDR_TRACE(2, it);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -169,9 +205,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto sw = [](int row, int chunk) -> uint32_t { return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); };
     const int crow = lane >> 2, cchk = lane & 3;   // coalesced layout: rows crow + 8 i, 16-byte chunk cchk
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int m_warp = m_blk * BM + quarter * 32;
+      const int m_warp = m_blk * kTileM + static_cast<int>(cta_rank) * BM + quarter * 32;
       const int m = m_warp + lane;
       const bool row_ok = m < p.M;
       auto map_rows = [&](int mm, int64_t& orow, int64_t& rrow_) {
@@ -289,33 +325,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (ew == 0 && lane == 0) VDR_TRACE(4, it);
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (kCtas == 2) mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty[acc]), 0));   // the leader's barrier
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();   // the peer may still be credited / read by in-flight pair operations
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (kCtas == 2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN>
+template <int BN, int kCtas>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int grid,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kCtas>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
   }
-  gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kCtas>, tmA, tmW, p);
   count_launch();
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tcgen05_kernel)");
   VDR_CHECK_LAUNCH("gemm_tcgen05_kernel");
   return VDR_OK;
 }
@@ -352,11 +406,15 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   if (a->N % 256 != 0 && a->N % 128 == 0) bn = 128;
   if (bn == 256 && tiles(256) < sms) bn = 128;
   if (bn == 128 && tiles(128) < sms) bn = 64;
+  // CTA pairs (256 x 256 tiles) when there is enough work to fill the 74 pairs
+  static const bool force_1cta = getenv("VDR_GEMM_1CTA") != nullptr;
+  const int pair_tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + 255) / 256);
+  const bool pair = !force_1cta && bn == 256 && pair_tiles >= sms / 2;
 
   CUtensorMap tmA, tmW;
   int rc = make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM, BK);
   if (rc != VDR_OK) return rc;
-  rc = make_tmap_2d_bf16(&tmW, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, (uint32_t)bn, BK);
+  rc = make_tmap_2d_bf16(&tmW, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, (uint32_t)(pair ? bn / 2 : bn), BK);
   if (rc != VDR_OK) return rc;
 
   GemmParams p;
@@ -366,11 +424,16 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   p.out_group = a->out_group; p.out_group_stride = a->out_group_stride; p.out_offset = a->out_offset;
   p.res_mod = a->res_mod; p.res_offset = a->res_offset;
   p.trace = g_trace;
+  p.dbg = getenv("VDR_GEMM_DBG") ? atoi(getenv("VDR_GEMM_DBG")) : 0;
 
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (pair) {
+    const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    return launch_gemm<256, 2>(tmA, tmW, p, 2 * pairs, s);
+  }
   const int total = tiles(bn);
   const int grid = total < sms ? total : sms;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256>(tmA, tmW, p, grid, s);
-  if (bn == 128) return launch_gemm<128>(tmA, tmW, p, grid, s);
-  return launch_gemm<64>(tmA, tmW, p, grid, s);
+  if (bn == 256) return launch_gemm<256, 1>(tmA, tmW, p, grid, s);
+  if (bn == 128) return launch_gemm<128, 1>(tmA, tmW, p, grid, s);
+  return launch_gemm<64, 1>(tmA, tmW, p, grid, s);
 }
