@@ -62,25 +62,6 @@ __device__ __forceinline__ unsigned long long attn_gtime() {
     if (p.trace != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 16 + 8 + (ev)] = attn_gtime(); \
   } while (0)
 
-// packed fp32x2 helpers (FFMA2 / FADD2 on sm_100): halve the issue slots of the softmax inner loop
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -143,7 +124,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   const int row_base = b * p.N;                       // first token row of this image in the qkv matrix
   const int colQ = head * kHD, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
   const int nkv = (p.N + kBKV - 1) / kBKV;
-  const int ntiles = 2 * nkv;                         // ring tiles: K0 V0 K1 V1 ...  (K: slots 0/2, V: slots 1/3)
+  const int valid_last = p.N - (nkv - 1) * kBKV;      // keys in the last block (1..128)
+  const int ntail = (valid_last + 15) & ~15;          // ... rounded to the MMA's 16-column granularity
 
   if (tid == 0) {
     if (base & 1023u) { printf("vdr: attention smem base not 1024-byte aligned\n"); __trap(); }
@@ -183,8 +165,10 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         tc_fence_after();
         const uint64_t dq = umma_desc_kmajor_sw128(sQ);
         const uint64_t dk = umma_desc_kmajor_sw128(sRing + (t & 3) * kTileBytes);
+        // the last key block only computes the (16-column granular) part of S that has keys behind it
+        const uint32_t idesc = (j == nkv - 1) ? umma_idesc_bf16(128, ntail) : idesc_s;
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
         umma_commit(bar_s);
       };
       mbar_arrive_expect_tx(bar_q, kTileBytes);
@@ -219,8 +203,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         mbar_wait(&bar_kv[t & 3], (t >> 2) & 1);
         tc_fence_after();
         const uint32_t sV = sRing + (t & 3) * kTileBytes;
-#pragma unroll
-        for (int k = 0; k < kBKV / 16; ++k) {
+        const int ksteps = (j == nkv - 1) ? ntail / 16 : kBKV / 16;
+#pragma unroll 1
+        for (int k = 0; k < ksteps; ++k) {
           const uint64_t dv = umma_desc_mnmajor_sw128(sV + k * 2048);   // 16 kv rows x 128 B
           // A = P from TMEM (16 bf16 = 8 columns per K step); O accumulates in TMEM across all key blocks
           umma_ts(tmem_O, tmem_P + k * 8, dv, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
@@ -245,6 +230,49 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       ATT_TRACE(1);
+      float alpha = 1.f;
+      bool moved = false;
+      uint64_t lsum2 = 0ull;
+      uint32_t pk[64];
+      if (j == nkv - 1 && ntail < kBKV) {
+        // ---- last, partial key block: only ntail (multiple of 16) columns exist in S; runtime loop over 16-column groups
+        float mx = -INFINITY;
+        for (int c = 0; c < ntail; c += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(tmem_S + lane_sel + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c + i < valid_last) ? __uint_as_float(r[i]) : -INFINITY);
+        }
+        const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+        moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);
+        if (moved) {
+          alpha = ex2(m_ref - m_new);
+          m_ref = m_new;
+        }
+        float lsum = 0.f;
+        if (j > 0) {   // P_{j-1} must have been consumed before its columns are overwritten
+          mbar_wait(bar_o, (j - 1) & 1);
+          tc_fence_after();
+        }
+        for (int c = 0; c < ntail; c += 16) {
+          uint32_t r[16], w[8];
+          tmem_ld_32x32b_x16(tmem_S + lane_sel + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = (c + i < valid_last) ? ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_ref)) : 0.f;
+            const float p1 = (c + i + 1 < valid_last) ? ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_ref)) : 0.f;
+            lsum += p0 + p1;
+            w[i >> 1] = cvt_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x8(tmem_P + lane_sel + (c >> 1), w);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfree);
+        lsum2 = pack2(lsum, 0.f);
+      } else {
       // the whole 128-wide score row of this thread -> registers, then hand the S columns back
       uint32_t sr[4][32];
 #pragma unroll
@@ -254,22 +282,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sfree);
       ATT_TRACE(2);
-      float alpha = 1.f;
-      bool moved = false;
-      uint64_t lsum2 = 0ull;
-      uint32_t pk[64];
-      // The body exists twice: the masked copy runs only for the last, partial key block (a real, warp-uniform
-      // branch -- written inline the compiler if-converts the mask into 384 predicated selects per block).
-      auto softmax_body = [&](auto tail_tag) {
-        constexpr bool kTail = decltype(tail_tag)::value;
-        if constexpr (kTail) {   // keys past the end of the sequence do not exist
-          const int valid = p.N - kv0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
-        }
+      {
         float mx = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -300,9 +313,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
             pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
           }
         }
-      };
-      if (kv0 + kBKV > p.N) softmax_body(std::true_type{});
-      else softmax_body(std::false_type{});
+      }
+      }
+      const bool narrow = (j == nkv - 1 && ntail < kBKV);
       float l0, l1;
       unpack2(lsum2, l0, l1);
       l_run = l_run * alpha + (l0 + l1);
@@ -329,9 +342,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         }
       }
       ATT_TRACE(4);
-      // P (bf16 pairs) -> TMEM columns [192, 256): the A operand of O += P V
-      tmem_st_32x32b_x32(tmem_P + lane_sel, pk);
-      tmem_st_32x32b_x32(tmem_P + lane_sel + 32, pk + 32);
+      // P (bf16 pairs) -> TMEM columns [192, 256): the A operand of O += P V  (the narrow tail path stored its own)
+      if (!narrow) {
+        tmem_st_32x32b_x32(tmem_P + lane_sel, pk);
+        tmem_st_32x32b_x32(tmem_P + lane_sel + 32, pk + 32);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -372,6 +387,77 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   }
 }
 
+// A handful of trailing query rows (N mod 128 <= 8, e.g. the 1025th token of a 32x32-patch image + CLS) would
+// otherwise occupy a whole 128-row tensor-core tile per (image, head): one warp per row instead.  Each lane
+// walks keys lane, lane+32, ... with its own online softmax (fp32), then the 32 partial states are merged.
+__global__ void __launch_bounds__(128)
+attn_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv, AttnParams p, int row0, int nrows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t total = static_cast<int64_t>(p.B) * p.heads * nrows;
+  if (wid >= total) return;
+  const int t = static_cast<int>(wid % nrows);
+  const int head = static_cast<int>((wid / nrows) % p.heads);
+  const int b = static_cast<int>(wid / (static_cast<int64_t>(nrows) * p.heads));
+  const int q = row0 + t;
+  const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * p.N * ld_qkv;
+  float qv[kHD];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(base + static_cast<int64_t>(q) * ld_qkv + head * kHD);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(qp + c);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      qv[c * 8 + 0] = a0.x * p.scale_log2; qv[c * 8 + 1] = a0.y * p.scale_log2; qv[c * 8 + 2] = a1.x * p.scale_log2; qv[c * 8 + 3] = a1.y * p.scale_log2;
+      qv[c * 8 + 4] = a2.x * p.scale_log2; qv[c * 8 + 5] = a2.y * p.scale_log2; qv[c * 8 + 6] = a3.x * p.scale_log2; qv[c * 8 + 7] = a3.y * p.scale_log2;
+    }
+  }
+  float m = -INFINITY, l = 0.f, o[kHD];
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) o[d] = 0.f;
+  for (int j = lane; j < p.N; j += 32) {
+    const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<int64_t>(j) * ld_qkv + p.d + head * kHD);
+    float sdot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(kp + c);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      sdot = fmaf(qv[c * 8 + 0], a0.x, sdot); sdot = fmaf(qv[c * 8 + 1], a0.y, sdot);
+      sdot = fmaf(qv[c * 8 + 2], a1.x, sdot); sdot = fmaf(qv[c * 8 + 3], a1.y, sdot);
+      sdot = fmaf(qv[c * 8 + 4], a2.x, sdot); sdot = fmaf(qv[c * 8 + 5], a2.y, sdot);
+      sdot = fmaf(qv[c * 8 + 6], a3.x, sdot); sdot = fmaf(qv[c * 8 + 7], a3.y, sdot);
+    }
+    const float m_new = fmaxf(m, sdot);
+    const float a = ex2(m - m_new), pj = ex2(sdot - m_new);
+    m = m_new;
+    l = l * a + pj;
+    const uint4* vp = reinterpret_cast<const uint4*>(base + static_cast<int64_t>(j) * ld_qkv + 2 * p.d + head * kHD);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(vp + c);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      o[c * 8 + 0] = fmaf(o[c * 8 + 0], a, pj * a0.x); o[c * 8 + 1] = fmaf(o[c * 8 + 1], a, pj * a0.y);
+      o[c * 8 + 2] = fmaf(o[c * 8 + 2], a, pj * a1.x); o[c * 8 + 3] = fmaf(o[c * 8 + 3], a, pj * a1.y);
+      o[c * 8 + 4] = fmaf(o[c * 8 + 4], a, pj * a2.x); o[c * 8 + 5] = fmaf(o[c * 8 + 5], a, pj * a2.y);
+      o[c * 8 + 6] = fmaf(o[c * 8 + 6], a, pj * a3.x); o[c * 8 + 7] = fmaf(o[c * 8 + 7], a, pj * a3.y);
+    }
+  }
+  // merge the 32 partial (m, l, o) states
+  float mw = m;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, s));
+  const float sc = (m == -INFINITY) ? 0.f : ex2(m - mw);
+  const float lw = warp_sum(l * sc);
+  const float inv = 1.f / lw;
+  __nv_bfloat16* op = p.out + (static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD;
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) {
+    const float v = warp_sum(o[d] * sc) * inv;
+    if (lane == (d & 31)) op[d] = __float2bfloat16_rn(v);
+  }
+  if (lane == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mw + log2f(lw)) * 0.69314718055994531f;
+}
+
 }  // namespace vdr
 
 static unsigned long long* g_attn_trace = nullptr;
@@ -402,9 +488,22 @@ extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, in
   p.B = B; p.N = N; p.heads = heads; p.d = d;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
-  dim3 grid((N + kBQ - 1) / kBQ, heads, B);
-  flash_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
-  count_launch();
-  VDR_CHECK_LAUNCH("flash_attn_fwd_kernel");
+  // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on a warp-per-row kernel
+  const int tail_rows = N % kBQ;
+  const bool vector_tail = tail_rows > 0 && tail_rows <= 8;
+  const int q_tiles = vector_tail ? N / kBQ : (N + kBQ - 1) / kBQ;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (q_tiles > 0) {
+    dim3 grid(q_tiles, heads, B);
+    flash_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
+    count_launch();
+    VDR_CHECK_LAUNCH("flash_attn_fwd_kernel");
+  }
+  if (vector_tail) {
+    const int64_t warps = (int64_t)B * heads * tail_rows;
+    attn_tail_rows_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, p, N - tail_rows, tail_rows);
+    count_launch();
+    VDR_CHECK_LAUNCH("attn_tail_rows_kernel");
+  }
   return VDR_OK;
 }

@@ -177,6 +177,21 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// 16-column variants for ragged tails
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (bf16, row = lane, two K elements per 32-bit column) comes from TMEM.
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -281,6 +296,31 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+// packed fp32x2 helpers (FFMA2 / FADD2 / FMUL2 on sm_100): two fp32 lanes per issue slot
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 + approx-unit error ~1e-7): one MUFU.RCP, one MUFU.EX2
 // and a handful of FMAs, branch-free, no slow-path calls -- the GEMM epilogue applies it to every element of
 // the MLP hidden layer, where erff() (two-branch polynomial) made the epilogue the bottleneck.
@@ -308,6 +348,31 @@ __device__ __forceinline__ float erf_fast(float x) {
 __device__ __forceinline__ float gelu_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, erf_fast(x * 0.70710678118654752f), hx);
+}
+
+// Exact-erf GELU of two values on the packed fp32x2 pipes.  erf by Abramowitz-Stegun 7.1.28,
+//   erf(z) = 1 - 1 / (1 + a1 z + ... + a6 z^6)^16  (z >= 0, |error| <= 3e-7; ~1e-6 as evaluated in fp32),
+// i.e. six FFMA2, four FMUL2 and ONE MUFU.RCP per element instead of erff()'s two-branch polynomial:
+// 9.5 issue slots per element instead of ~19, so the GELU epilogue hides behind the MMAs of the next tile.
+__device__ __forceinline__ uint64_t gelu_fast2(uint64_t x2) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  const uint64_t z2 = pack2(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+  uint64_t acc = fma2(z2, pack2(0.0000430638f, 0.0000430638f), pack2(0.0002765672f, 0.0002765672f));
+  acc = fma2(acc, z2, pack2(0.0001520143f, 0.0001520143f));
+  acc = fma2(acc, z2, pack2(0.0092705272f, 0.0092705272f));
+  acc = fma2(acc, z2, pack2(0.0422820123f, 0.0422820123f));
+  acc = fma2(acc, z2, pack2(0.0705230784f, 0.0705230784f));
+  acc = fma2(acc, z2, pack2(1.0f, 1.0f));
+  acc = mul2(acc, acc);
+  acc = mul2(acc, acc);
+  acc = mul2(acc, acc);
+  acc = mul2(acc, acc);
+  float p0, p1;
+  unpack2(acc, p0, p1);
+  const float e0 = copysignf(1.0f - rcp_approx(p0), x0), e1 = copysignf(1.0f - rcp_approx(p1), x1);   // erf(x / sqrt 2)
+  const uint64_t hx2 = mul2(x2, pack2(0.5f, 0.5f));
+  return fma2(hx2, pack2(e0, e1), hx2);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

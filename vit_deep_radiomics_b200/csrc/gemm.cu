@@ -242,12 +242,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (ew == 0 && lane == 0) VDR_TRACE(3, it);
+      // Software pipeline over the 32-column chunks of this warp: the tcgen05.ld of chunk c+1 is issued as soon as
+      // the registers of chunk c have been turned into packed outputs, so its latency hides behind the staging
+      // round trip and the global stores of chunk c.
+      uint32_t r[32];
+      const uint32_t taddr0 = tmem_base + static_cast<uint32_t>(acc * BN + half * kColsPerWarp) + (static_cast<uint32_t>(quarter * 32) << 16);
+      tmem_ld_32x32b_x32(taddr0, r);
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {
         const int col0 = half * kColsPerWarp + c;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN + col0) + (static_cast<uint32_t>(quarter * 32) << 16);
-        tmem_ld_32x32b_x32(taddr, r);
         if (c + 32 < kColsPerWarp) load_res(rnxt, c + 32);   // overlap the next residual chunk with this one
         const int n0 = n_blk * BN + col0;
         const bool fast = p.c_dtype == VDR_DTYPE_BF16 && n0 + 32 <= p.N;
@@ -264,6 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         tmem_ld_wait();
         if (fast) {
+          uint4 o[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float v[8];
@@ -275,7 +279,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
             if (p.epilogue == VDR_EPI_BIAS_GELU) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+              for (int i = 0; i < 8; i += 2) unpack2(gelu_fast2(pack2(v[i], v[i + 1])), v[i], v[i + 1]);
             } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
               if (res_bf16) {
                 const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
@@ -289,34 +293,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
               }
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
-                         "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
+            o[g] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           }
+          if (c + 32 < kColsPerWarp) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>(c + 32), r);   // next chunk in flight
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(o[g].x), "r"(o[g].y), "r"(o[g].z), "r"(o[g].w) : "memory");
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(stg + sw(crow + 8 * i, cchk)) : "memory");
-            if (m_warp + crow + 8 * i < p.M) *reinterpret_cast<uint4*>(Cb + out_row_c[i] * p.ldc + n0 + cchk * 8) = o;
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stg + sw(crow + 8 * i, cchk)) : "memory");
+            if (m_warp + crow + 8 * i < p.M) *reinterpret_cast<uint4*>(Cb + out_row_c[i] * p.ldc + n0 + cchk * 8) = q;
           }
           __syncwarp();
-        } else if (row_ok) {   // f32 output, f32 residual (pos-embed) or a ragged last column group: direct path
+        } else {
+          if (row_ok) {   // f32 output or a ragged last column group: direct element-wise path
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + g * 8;
+            for (int g = 0; g < 4; ++g) {
+              const int n = n0 + g * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (n + i < p.N) {
-                float v = __uint_as_float(r[g * 8 + i]) + sbias[c + g * 8 + i];
-                if (p.epilogue == VDR_EPI_BIAS_GELU) v = gelu_fast(v);
-                else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL)
-                  v += (p.r_dtype == VDR_DTYPE_BF16) ? __bfloat162float(Rb[res_row * p.ldr + n + i])
-                                                     : static_cast<const float*>(p.R)[res_row * p.ldr + n + i];
-                if (p.c_dtype == VDR_DTYPE_BF16) Cb[out_row * p.ldc + n + i] = __float2bfloat16_rn(v);
-                else static_cast<float*>(p.C)[out_row * p.ldc + n + i] = v;
+              for (int i = 0; i < 8; ++i) {
+                if (n + i < p.N) {
+                  float v = __uint_as_float(r[g * 8 + i]) + sbias[c + g * 8 + i];
+                  if (p.epilogue == VDR_EPI_BIAS_GELU) v = gelu_fast(v);
+                  else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL)
+                    v += (p.r_dtype == VDR_DTYPE_BF16) ? __bfloat162float(Rb[res_row * p.ldr + n + i])
+                                                       : static_cast<const float*>(p.R)[res_row * p.ldr + n + i];
+                  if (p.c_dtype == VDR_DTYPE_BF16) Cb[out_row * p.ldc + n + i] = __float2bfloat16_rn(v);
+                  else static_cast<float*>(p.C)[out_row * p.ldc + n + i] = v;
+                }
               }
             }
           }
+          if (c + 32 < kColsPerWarp) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>(c + 32), r);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
