@@ -39,6 +39,8 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) 
 }
 
 struct AttnParams {
+  const __nv_bfloat16* qkv;
+  int64_t ld_qkv;
   __nv_bfloat16* out;
   float* lse;
   int64_t ld_out;
@@ -123,9 +125,15 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
   const int row_base = b * p.N;                       // first token row of this image in the qkv matrix
   const int colQ = head * kHD, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
-  const int nkv = (p.N + kBKV - 1) / kBKV;
-  const int valid_last = p.N - (nkv - 1) * kBKV;      // keys in the last block (1..128)
-  const int ntail = (valid_last + 15) & ~15;          // ... rounded to the MMA's 16-column granularity
+  // Key blocks: full 128-key blocks on the tensor cores; a ragged last block either runs as a narrow MMA block
+  // (16-column granularity) or, when it holds only a few keys (<= 8, e.g. the 1025th token of a 32x32-patch image
+  // + CLS), is folded into the epilogue on the CUDA cores instead of costing every CTA one more pipeline round trip.
+  const int nkv_all = (p.N + kBKV - 1) / kBKV;
+  const int last_keys = p.N - (nkv_all - 1) * kBKV;              // keys in the last block (1..128)
+  const int tail_keys = (last_keys <= 8 && nkv_all > 1) ? last_keys : 0;
+  const int nkv = tail_keys ? nkv_all - 1 : nkv_all;             // blocks that go through the MMA pipeline
+  const int valid_last = tail_keys ? kBKV : last_keys;           // keys in the last MMA block
+  const int ntail = (valid_last + 15) & ~15;                     // ... rounded to the MMA's 16-column granularity
 
   if (tid == 0) {
     if (base & 1023u) { printf("vdr: attention smem base not 1024-byte aligned\n"); __trap(); }
@@ -356,25 +364,68 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     mbar_wait(bar_o, (nkv - 1) & 1);
     tc_fence_after();
 
-    // ---- normalise and store
+    // ---- epilogue: O (TMEM) -> registers, fold the few trailing keys (if any), normalise, store
     const int q = q0 + tid;
-    const float inv = 1.f / l_run;
-    __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
+    float o[kHD];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
       tmem_ld_wait();
-      if (q < p.N) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 o;
-          o.x = cvt_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-          o.y = cvt_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
-          o.z = cvt_bf16x2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
-          o.w = cvt_bf16x2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + c * 32 + i) = o;
+      for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(r[i]);
+    }
+    if (tail_keys) {
+      float qv[kHD];   // this thread's query row from the swizzled Q tile
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                     : "r"(sQ + tid * 128 + ((c ^ (tid & 7)) << 4)));
+        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+        qv[c * 8 + 0] = a0.x; qv[c * 8 + 1] = a0.y; qv[c * 8 + 2] = a1.x; qv[c * 8 + 3] = a1.y;
+        qv[c * 8 + 4] = a2.x; qv[c * 8 + 5] = a2.y; qv[c * 8 + 6] = a3.x; qv[c * 8 + 7] = a3.y;
+      }
+      for (int t = 0; t < tail_keys; ++t) {
+        const __nv_bfloat16* krow = p.qkv + static_cast<int64_t>(row_base + nkv * kBKV + t) * p.ld_qkv;
+        float sdot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(krow + colK) + c);
+          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+          sdot = fmaf(qv[c * 8 + 0], a0.x, sdot); sdot = fmaf(qv[c * 8 + 1], a0.y, sdot);
+          sdot = fmaf(qv[c * 8 + 2], a1.x, sdot); sdot = fmaf(qv[c * 8 + 3], a1.y, sdot);
+          sdot = fmaf(qv[c * 8 + 4], a2.x, sdot); sdot = fmaf(qv[c * 8 + 5], a2.y, sdot);
+          sdot = fmaf(qv[c * 8 + 6], a3.x, sdot); sdot = fmaf(qv[c * 8 + 7], a3.y, sdot);
         }
+        sdot *= p.scale_log2;
+        const float m_new = fmaxf(m_ref, sdot);
+        const float a = ex2(m_ref - m_new);
+        const float pj = __bfloat162float(__float2bfloat16_rn(ex2(sdot - m_new)));   // same bf16 rounding of P as the MMA path
+        m_ref = m_new;
+        l_run = l_run * a + pj;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(krow + colV) + c);
+          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+          o[c * 8 + 0] = fmaf(o[c * 8 + 0], a, pj * a0.x); o[c * 8 + 1] = fmaf(o[c * 8 + 1], a, pj * a0.y);
+          o[c * 8 + 2] = fmaf(o[c * 8 + 2], a, pj * a1.x); o[c * 8 + 3] = fmaf(o[c * 8 + 3], a, pj * a1.y);
+          o[c * 8 + 4] = fmaf(o[c * 8 + 4], a, pj * a2.x); o[c * 8 + 5] = fmaf(o[c * 8 + 5], a, pj * a2.y);
+          o[c * 8 + 6] = fmaf(o[c * 8 + 6], a, pj * a3.x); o[c * 8 + 7] = fmaf(o[c * 8 + 7], a, pj * a3.y);
+        }
+      }
+    }
+    const float inv = 1.f / l_run;
+    if (q < p.N) {
+      __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
+#pragma unroll
+      for (int i = 0; i < kHD; i += 8) {
+        uint4 w;
+        w.x = cvt_bf16x2(o[i] * inv, o[i + 1] * inv);
+        w.y = cvt_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
+        w.z = cvt_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
+        w.w = cvt_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+        *reinterpret_cast<uint4*>(op + i) = w;
       }
     }
     if (q < p.N && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_run)) * 0.69314718055994531f;
@@ -390,72 +441,68 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
 // A handful of trailing query rows (N mod 128 <= 8, e.g. the 1025th token of a 32x32-patch image + CLS) would
 // otherwise occupy a whole 128-row tensor-core tile per (image, head): one warp per row instead.  Each lane
 // walks keys lane, lane+32, ... with its own online softmax (fp32), then the 32 partial states are merged.
-__global__ void __launch_bounds__(128)
-attn_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv, AttnParams p, int row0, int nrows) {
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t total = static_cast<int64_t>(p.B) * p.heads * nrows;
-  if (wid >= total) return;
-  const int t = static_cast<int>(wid % nrows);
-  const int head = static_cast<int>((wid / nrows) % p.heads);
-  const int b = static_cast<int>(wid / (static_cast<int64_t>(nrows) * p.heads));
+constexpr int kTailWarps = 8;
+__global__ void __launch_bounds__(kTailWarps * 32)
+attn_tail_rows_kernel(AttnParams p, int row0, int nrows) {
+  // One CTA per (image, head, row).  8 lanes share a key (16 bytes of the 128-byte K / V row each), so a warp-wide
+  // load touches 4 rows x 128 contiguous bytes; the 32 lane-groups of the CTA each run an online softmax over the
+  // keys dealt to them and the partial states are merged at the end.
+  __shared__ float s_m[kTailWarps * 4], s_l[kTailWarps * 4], s_o[kTailWarps * 4][kHD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, grp = warp * 4 + (lane >> 3);          // 16-byte chunk of the row, key group 0..31
+  const int t = blockIdx.x % nrows;
+  const int head = (blockIdx.x / nrows) % p.heads;
+  const int b = blockIdx.x / (nrows * p.heads);
   const int q = row0 + t;
-  const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * p.N * ld_qkv;
-  float qv[kHD];
+  const __nv_bfloat16* base = p.qkv + static_cast<int64_t>(b) * p.N * p.ld_qkv + head * kHD + sub * 8;
+  float qv[8], o[8];
   {
-    const uint4* qp = reinterpret_cast<const uint4*>(base + static_cast<int64_t>(q) * ld_qkv + head * kHD);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = __ldg(qp + c);
-      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-      qv[c * 8 + 0] = a0.x * p.scale_log2; qv[c * 8 + 1] = a0.y * p.scale_log2; qv[c * 8 + 2] = a1.x * p.scale_log2; qv[c * 8 + 3] = a1.y * p.scale_log2;
-      qv[c * 8 + 4] = a2.x * p.scale_log2; qv[c * 8 + 5] = a2.y * p.scale_log2; qv[c * 8 + 6] = a3.x * p.scale_log2; qv[c * 8 + 7] = a3.y * p.scale_log2;
-    }
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(q) * p.ld_qkv));
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    qv[0] = a0.x * p.scale_log2; qv[1] = a0.y * p.scale_log2; qv[2] = a1.x * p.scale_log2; qv[3] = a1.y * p.scale_log2;
+    qv[4] = a2.x * p.scale_log2; qv[5] = a2.y * p.scale_log2; qv[6] = a3.x * p.scale_log2; qv[7] = a3.y * p.scale_log2;
   }
-  float m = -INFINITY, l = 0.f, o[kHD];
 #pragma unroll
-  for (int d = 0; d < kHD; ++d) o[d] = 0.f;
-  for (int j = lane; j < p.N; j += 32) {
-    const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<int64_t>(j) * ld_qkv + p.d + head * kHD);
-    float sdot = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = __ldg(kp + c);
-      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-      sdot = fmaf(qv[c * 8 + 0], a0.x, sdot); sdot = fmaf(qv[c * 8 + 1], a0.y, sdot);
-      sdot = fmaf(qv[c * 8 + 2], a1.x, sdot); sdot = fmaf(qv[c * 8 + 3], a1.y, sdot);
-      sdot = fmaf(qv[c * 8 + 4], a2.x, sdot); sdot = fmaf(qv[c * 8 + 5], a2.y, sdot);
-      sdot = fmaf(qv[c * 8 + 6], a3.x, sdot); sdot = fmaf(qv[c * 8 + 7], a3.y, sdot);
-    }
+  for (int d = 0; d < 8; ++d) o[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  const uint32_t gmask = 0xffu << (lane & 24);
+  for (int j = grp; j < p.N; j += kTailWarps * 4) {
+    const __nv_bfloat16* row = base + static_cast<int64_t>(j) * p.ld_qkv;
+    const uint4 ku = __ldg(reinterpret_cast<const uint4*>(row + p.d));
+    const uint4 vu = __ldg(reinterpret_cast<const uint4*>(row + 2 * p.d));
+    const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y), k2 = unpack_bf16x2(ku.z), k3 = unpack_bf16x2(ku.w);
+    float sdot = qv[0] * k0.x + qv[1] * k0.y + qv[2] * k1.x + qv[3] * k1.y + qv[4] * k2.x + qv[5] * k2.y + qv[6] * k3.x + qv[7] * k3.y;
+    sdot += __shfl_xor_sync(gmask, sdot, 1);   // reduce inside the 8-lane group (groups may leave the loop at
+    sdot += __shfl_xor_sync(gmask, sdot, 2);   //  different trip counts, so the mask names only this group)
+    sdot += __shfl_xor_sync(gmask, sdot, 4);
     const float m_new = fmaxf(m, sdot);
     const float a = ex2(m - m_new), pj = ex2(sdot - m_new);
     m = m_new;
     l = l * a + pj;
-    const uint4* vp = reinterpret_cast<const uint4*>(base + static_cast<int64_t>(j) * ld_qkv + 2 * p.d + head * kHD);
+    const float2 v0 = unpack_bf16x2(vu.x), v1 = unpack_bf16x2(vu.y), v2 = unpack_bf16x2(vu.z), v3 = unpack_bf16x2(vu.w);
+    o[0] = fmaf(o[0], a, pj * v0.x); o[1] = fmaf(o[1], a, pj * v0.y); o[2] = fmaf(o[2], a, pj * v1.x); o[3] = fmaf(o[3], a, pj * v1.y);
+    o[4] = fmaf(o[4], a, pj * v2.x); o[5] = fmaf(o[5], a, pj * v2.y); o[6] = fmaf(o[6], a, pj * v3.x); o[7] = fmaf(o[7], a, pj * v3.y);
+  }
+  if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = __ldg(vp + c);
-      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-      o[c * 8 + 0] = fmaf(o[c * 8 + 0], a, pj * a0.x); o[c * 8 + 1] = fmaf(o[c * 8 + 1], a, pj * a0.y);
-      o[c * 8 + 2] = fmaf(o[c * 8 + 2], a, pj * a1.x); o[c * 8 + 3] = fmaf(o[c * 8 + 3], a, pj * a1.y);
-      o[c * 8 + 4] = fmaf(o[c * 8 + 4], a, pj * a2.x); o[c * 8 + 5] = fmaf(o[c * 8 + 5], a, pj * a2.y);
-      o[c * 8 + 6] = fmaf(o[c * 8 + 6], a, pj * a3.x); o[c * 8 + 7] = fmaf(o[c * 8 + 7], a, pj * a3.y);
+  for (int d = 0; d < 8; ++d) s_o[grp][sub * 8 + d] = o[d];
+  __syncthreads();
+  if (warp == 0) {
+    float mt = -INFINITY;
+    for (int g = 0; g < kTailWarps * 4; ++g) mt = fmaxf(mt, s_m[g]);
+    float lt = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int g = 0; g < kTailWarps * 4; ++g) {
+      const float f = (s_m[g] == -INFINITY) ? 0.f : ex2(s_m[g] - mt);
+      lt += s_l[g] * f;
+      o0 += s_o[g][lane] * f;
+      o1 += s_o[g][lane + 32] * f;
     }
+    const float inv = 1.f / lt;
+    __nv_bfloat16* op = p.out + (static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD;
+    op[lane] = __float2bfloat16_rn(o0 * inv);
+    op[lane + 32] = __float2bfloat16_rn(o1 * inv);
+    if (lane == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mt + log2f(lt)) * 0.69314718055994531f;
   }
-  // merge the 32 partial (m, l, o) states
-  float mw = m;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, s));
-  const float sc = (m == -INFINITY) ? 0.f : ex2(m - mw);
-  const float lw = warp_sum(l * sc);
-  const float inv = 1.f / lw;
-  __nv_bfloat16* op = p.out + (static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD;
-#pragma unroll
-  for (int d = 0; d < kHD; ++d) {
-    const float v = warp_sum(o[d] * sc) * inv;
-    if (lane == (d & 31)) op[d] = __float2bfloat16_rn(v);
-  }
-  if (lane == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mw + log2f(lw)) * 0.69314718055994531f;
 }
 
 }  // namespace vdr
@@ -482,6 +529,8 @@ extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, in
     configured = true;
   }
   AttnParams p;
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.ld_qkv = ld_qkv;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   p.ld_out = ld_out;
@@ -500,8 +549,7 @@ extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, in
     VDR_CHECK_LAUNCH("flash_attn_fwd_kernel");
   }
   if (vector_tail) {
-    const int64_t warps = (int64_t)B * heads * tail_rows;
-    attn_tail_rows_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, p, N - tail_rows, tail_rows);
+    attn_tail_rows_kernel<<<(unsigned)(B * heads * tail_rows), kTailWarps * 32, 0, s>>>(p, N - tail_rows, tail_rows);
     count_launch();
     VDR_CHECK_LAUNCH("attn_tail_rows_kernel");
   }
