@@ -156,9 +156,11 @@ int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_ou
  *             pe_div (device, f64[D/6]) = 10000^(6i/D) as computed by the host (:34);
  *             coef_host (HOST, f64[11]) = {w_orig, h_orig, res0, res1, res2,
  *                                          noise0, noise1, noise2, mean_x, mean_y, mean_z}
- *   workspace >= vdr_mask_gather_workspace_bytes(S,h,w)
+ *             The encoding is evaluated once per distinct coordinate ((h + w + S) rows of 2*(D/6) f64 in the
+ *             workspace) and added row-wise: bit-identical to evaluating it per token.
+ *   workspace >= vdr_mask_gather_workspace_bytes(S,h,w,D), 16-byte aligned
  */
-size_t vdr_mask_gather_workspace_bytes(int S, int h, int w);
+size_t vdr_mask_gather_workspace_bytes(int S, int h, int w, int D);
 int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
                     int64_t feat_row_pitch, int64_t feat_row0,
                     const uint8_t* mask, int64_t mask_slice_stride, int64_t mask_row_stride, int64_t mask_col_stride,

@@ -35,7 +35,7 @@ def test_argument_errors_need_no_gpu():
     with pytest.raises(ValueError):
         _C.check(rc, "vdr_gemm")
     assert lib.vdr_layernorm_fwd(None, 0, None, None, None, 0, 0, None, None, 1, 8, 1e-6, None) == -1
-    assert lib.vdr_mask_gather_workspace_bytes(120, 32, 32) >= 2 * 4 * 60
+    assert lib.vdr_mask_gather_workspace_bytes(120, 32, 32, 768) >= 2 * 4 * 60 + (120 + 64) * 256 * 8
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -71,7 +71,7 @@ def lib() -> C.CDLL:
     L.vdr_layernorm_bwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp]
     L.vdr_cls_concat_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]
     L.vdr_flash_attn_fwd.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, f32, vp]
-    L.vdr_mask_gather_workspace_bytes.argtypes = [i32, i32, i32]
+    L.vdr_mask_gather_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.vdr_mask_gather_workspace_bytes.restype = sz
     L.vdr_mask_gather.argtypes = [vp, i32, i64, i64, i64, i64, vp, i64, i64, i64, vp, vp, i32, i32, i32, i32,
                                   vp, vp, vp, i32, f64, vp, C.POINTER(f64), vp, sz, vp]

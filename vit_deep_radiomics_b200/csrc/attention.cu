@@ -1,23 +1,30 @@
 // Fused flash-style self-attention forward on tcgen05 (head_dim 64), sm_100a.
 //
-// One CTA = 128 query rows of one (batch, head); 128 threads, thread t owns query row t = TMEM lane t
-// so row max / row sum need no shuffles.  Per 128-key block:
-//   S = Q K^T      tcgen05.mma 128x128x64 (both operands K-major, TMA SWIZZLE_128B tiles) -> TMEM
-//   softmax        tcgen05.ld S, online max/sum in registers, P (bf16) -> swizzled smem
-//   O_j = P V      tcgen05.mma 128x64x128 (A = P K-major, B = V MN-major straight from the TMA tile)
-//   O = O*alpha + O_j in registers (no TMEM round trip for the rescale)
-// K/V tiles stream through a 3-slot TMA ring; two CTAs are resident per SM so the tensor pipe of one
-// overlaps the softmax of the other.  Q, K, V are read in place from the packed QKV GEMM output.
+// One CTA = 128 query rows of one (batch, head), two CTAs per SM.  Per 128-key block j:
+//   S_j = Q K_j^T    tcgen05.mma 128x128x64 (both operands K-major, TMA SWIZZLE_128B tiles) -> TMEM
+//   softmax          tcgen05.ld S, online max / sum in registers, P_j (bf16) -> TMEM
+//   O  += P_j V_j    tcgen05.mma 128x64x128 (A = P from TMEM, B = V MN-major straight from the TMA tile)
+// Warp roles (12 warps):
+//   warps 0-7   softmax: warp w owns TMEM lanes 32*(w&3).. (one query row per lane) and the 64 score columns
+//               [64*(w>>2), +64) of the block -- TWO threads per query row, so that four softmax warps (two CTAs)
+//               are resident per scheduler: the exponentials are latency-bound per warp (MUFU / tcgen05.ld / barrier
+//               round trips), not issue-bound, and the extra warps fill those stalls.  The two half-row threads
+//               exchange their block maximum through shared memory (one 64-thread named barrier per block).
+//   warp 8      K tiles + S MMAs, warp 9: V tiles + PV MMAs (one lane each), warps 10-11 idle (setmaxnreg is per warpgroup)
+// Online softmax with LAZY rescaling: probabilities are taken relative to a reference maximum that only moves
+// when the running maximum exceeds it by 2^8, so O accumulates in TMEM across key blocks and is rescaled rarely.
+// Q, K, V are read in place from the packed QKV GEMM output through one 2-D tensor map.
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace vdr {
 
-constexpr int kAttnThreads = 256;   // softmax warpgroup + issuer warpgroup
+constexpr int kSoftmaxWarps = 8;
+constexpr int kAttnThreads = (kSoftmaxWarps + 4) * 32;   // 2 softmax warpgroups + issuer warpgroup
 constexpr int kBQ = 128, kBKV = 128, kHD = 64;
 constexpr int kTileBytes = 128 * kHD * 2;               // 16 KB: one 128 x 64 bf16 tile
-constexpr int kAttnSmem = 7 * kTileBytes /*Q, 4 ring slots, P lo/hi*/ + 256 /*barriers*/;
+constexpr int kAttnSmem = 5 * kTileBytes /*Q, 4 ring slots*/ + 256 /*barriers*/ + 3 * 2 * 128 * 4 /*max exchange x2, sum exchange*/;
 constexpr int kAttnTmemCols = 256;                       // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 
 __device__ __forceinline__ float ex2(float x) {
@@ -46,9 +53,10 @@ struct AttnParams {
   int64_t ld_out;
   int B, N, heads, d;
   float scale_log2;
-  unsigned long long* trace;   // debug: per-iteration timestamps of CTA (0,0,0) thread 32
+  unsigned long long* trace;   // debug (VDR_ATTN_TRACE builds only): per-iteration timestamps of CTA (0,0,0)
 };
 
+#ifdef VDR_ATTN_TRACE
 __device__ __forceinline__ unsigned long long attn_gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -58,11 +66,14 @@ __device__ __forceinline__ unsigned long long attn_gtime() {
   do {                                                                                                             \
     if (p.trace != nullptr && tid == 32 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 16 + (ev)] = attn_gtime(); \
   } while (0)
-
 #define ISS_TRACE(ev)                                                                                              \
   do {                                                                                                             \
     if (p.trace != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 16 + 8 + (ev)] = attn_gtime(); \
   } while (0)
+#else
+#define ATT_TRACE(ev) do { } while (0)
+#define ISS_TRACE(ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
@@ -99,27 +110,44 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
 template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
-// Warp roles: warps 0-3 = softmax warpgroup (thread t owns query row t = TMEM lane t);
-//             warp 4    = issuer (TMA ring + tcgen05.mma), warps 5-7 idle (setmaxnreg works per warpgroup).
+// 64-thread named barrier shared by the two warps that own the same 32 query rows (ids 1..4; 0 is __syncthreads)
+__device__ __forceinline__ void pair_bar_sync(int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
+// Issuer-side wait: back off between polls so the spinning lane does not take issue slots from the softmax warps
+// that share its scheduler (the MMAs it issues have a whole softmax block of slack).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) {
+      printf("vdr: attention issuer wait timeout block (%d,%d,%d) bar %p parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z, (void*)bar, parity);
+      __trap();
+    }
+  }
+}
+
 // Pipeline per 128-key block j (no CTA-wide barrier in the loop):
-//   issuer : wait S_j consumed -> prefetch K_{j+2}, issue S_{j+1};  wait P_j ready -> issue O_j = P_j V_j
-//   softmax: wait S_j -> registers -> signal "consumed" -> max / exp2 / sum -> fold O_{j-1} (finished long ago)
-//            -> write P_j -> signal "ready"
+//   issuers: wait S_j consumed -> prefetch K_{j+2}, issue S_{j+1};  wait P_j ready -> issue O += P_j V_j
+//   softmax: wait S_j -> registers -> signal "consumed" -> max (exchanged between the two half-row threads) ->
+//            exp2 / sum -> wait O_{j-1} -> (rare) rescale O -> write P_j -> signal "ready"
 // so the tensor pipe computes S_{j+1} and O_{j-1} while the exponentials of block j are evaluated.
 __global__ void __launch_bounds__(kAttnThreads, 2)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
-  // layout: Q | ring0..3 | P_lo | P_hi | barriers
+  // layout: Q | ring0..3 | barriers | max exchange [2 buffers][2 halves][128] | sum exchange [2 halves][128]
   const uint32_t sQ = base, sRing = base + kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
   uint64_t* bar_q = bars;            // Q landed
   uint64_t* bar_kv = bars + 1;       // [4] ring slot landed
   uint64_t* bar_s = bars + 5;        // S_j = Q K_j^T complete            (tcgen05.commit)
-  uint64_t* bar_o = bars + 6;        // O_j = P_j V_j complete            (tcgen05.commit)
-  uint64_t* bar_sfree = bars + 7;    // S_j is in registers               (4 softmax warps arrive)
-  uint64_t* bar_pready = bars + 8;   // P_j is in smem, O_{j-1} consumed  (4 softmax warps arrive)
+  uint64_t* bar_o = bars + 6;        // O += P_j V_j complete             (tcgen05.commit)
+  uint64_t* bar_sfree = bars + 7;    // S_j is in registers               (8 softmax warps arrive)
+  uint64_t* bar_pready = bars + 8;   // P_j is in TMEM, O rescaled        (8 softmax warps arrive)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  float* s_max = reinterpret_cast<float*>(smem + 5 * kTileBytes + 256);   // [2][2][128]
+  float* s_sum = s_max + 2 * 2 * 128;                                      // [2][128]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
@@ -142,8 +170,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     for (int i = 0; i < 4; ++i) mbar_init(&bar_kv[i], 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
-    mbar_init(bar_sfree, 4);
-    mbar_init(bar_pready, 4);
+    mbar_init(bar_sfree, kSoftmaxWarps);
+    mbar_init(bar_pready, kSoftmaxWarps);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<kAttnTmemCols>(tmem_ptr);
@@ -153,11 +181,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
 
-  if (warp >= 4) {
+  if (warp >= kSoftmaxWarps) {
     // =============================================================== issuer warpgroup
-    reg_dec<48>();
+    reg_dec<32>();
     // Two issuing threads so that the two dependent MMA chains of a block (S_{j+1} = Q K^T: 4 steps, O += P V:
-    // 8 steps, each step waiting ~130 cycles on the accumulator of the previous one) are dispatched concurrently.
+    // 8 steps) are dispatched concurrently.
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
     auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2 (slots 0/2), odd = V block t/2 (slots 1/3)
@@ -165,11 +193,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
       tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + (t >> 1) * kBKV);
     };
-    if (warp == 4 && lane == 0) {
+    if (warp == kSoftmaxWarps && lane == 0) {
       // ---- K tiles + S = Q K^T
       auto issue_s = [&](int j) {
         const int t = 2 * j;
-        mbar_wait(&bar_kv[t & 3], (t >> 2) & 1);
+        mbar_wait_relaxed(&bar_kv[t & 3], (t >> 2) & 1);
         tc_fence_after();
         const uint64_t dq = umma_desc_kmajor_sw128(sQ);
         const uint64_t dk = umma_desc_kmajor_sw128(sRing + (t & 3) * kTileBytes);
@@ -183,87 +211,99 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
       tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
       issue_tile(0);
       if (nkv > 1) issue_tile(2);
-      mbar_wait(bar_q, 0);
+      mbar_wait_relaxed(bar_q, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         ISS_TRACE(0);
-        mbar_wait(bar_sfree, j & 1);                       // S_j is in registers -> K_j's slot and the S columns are free
+        mbar_wait_relaxed(bar_sfree, j & 1);               // S_j is in registers -> K_j's slot and the S columns are free
         tc_fence_after();
         ISS_TRACE(1);
         if (j + 1 < nkv) issue_s(j + 1);
         if (j + 2 < nkv) issue_tile(2 * j + 4);            // K_{j+2} into K_j's slot
         ISS_TRACE(2);
       }
-    } else if (warp == 5 && lane == 0) {
+    } else if (warp == kSoftmaxWarps + 1 && lane == 0) {
       // ---- V tiles + O += P V
       issue_tile(1);
       if (nkv > 1) issue_tile(3);
       for (int j = 0; j < nkv; ++j) {
         ISS_TRACE(3);
-        mbar_wait(bar_pready, j & 1);                      // P_j is in TMEM (and O rescaled if the maximum moved)
+        mbar_wait_relaxed(bar_pready, j & 1);              // P_j is in TMEM (and O rescaled if the maximum moved)
         tc_fence_after();
         ISS_TRACE(4);
         if (j >= 1 && j + 1 < nkv) {                       // V_{j+1} goes into V_{j-1}'s slot: O_{j-1} must be complete.
-          mbar_wait(bar_o, (j - 1) & 1);                   // (waited BEFORE O_j is committed: a parity wait must never
+          mbar_wait_relaxed(bar_o, (j - 1) & 1);           // (waited BEFORE O_j is committed: a parity wait must never
           issue_tile(2 * j + 3);                           //  be two phases behind its barrier)
         }
         const int t = 2 * j + 1;
-        mbar_wait(&bar_kv[t & 3], (t >> 2) & 1);
+        mbar_wait_relaxed(&bar_kv[t & 3], (t >> 2) & 1);
         tc_fence_after();
-        const uint32_t sV = sRing + (t & 3) * kTileBytes;
-        const int ksteps = (j == nkv - 1) ? ntail / 16 : kBKV / 16;
+        const uint64_t dv0 = umma_desc_mnmajor_sw128(sRing + (t & 3) * kTileBytes);
+        // A = P from TMEM (16 bf16 = 8 columns per K step); O accumulates in TMEM across all key blocks.
+        // Each K step covers 16 kv rows x 128 B of the V tile = 2048 B = 128 descriptor address units.
+        if (j < nkv - 1 || ntail == kBKV) {
+#pragma unroll
+          for (int k = 0; k < kBKV / 16; ++k)
+            umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+        } else {
+          const int ksteps = ntail / 16;
 #pragma unroll 1
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t dv = umma_desc_mnmajor_sw128(sV + k * 2048);   // 16 kv rows x 128 B
-          // A = P from TMEM (16 bf16 = 8 columns per K step); O accumulates in TMEM across all key blocks
-          umma_ts(tmem_O, tmem_P + k * 8, dv, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          for (int k = 0; k < ksteps; ++k)
+            umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         }
         umma_commit(bar_o);
         ISS_TRACE(5);
       }
     }
   } else {
-    // =============================================================== softmax warpgroup
-    reg_inc<208>();
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    // Online softmax with LAZY rescaling: probabilities are taken relative to a reference maximum m_ref that is
-    // only moved when the running maximum exceeds it by more than 2^8; O then accumulates in TMEM across key
-    // blocks (the P V MMAs run with accumulate = 1) and is touched by this warpgroup only on those rare moves.
+    // =============================================================== softmax warpgroups
+    reg_inc<104>();
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;                              // query row of this thread inside the tile
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_S + lane_sel + half * 64;                // this thread's 64 score columns
+    const uint32_t tP = tmem_P + lane_sel + half * 32;                // ... as 32 packed bf16x2 columns of P
+    const uint32_t tO = tmem_O + lane_sel + half * 32;                // the 32 output columns this thread rescales / stores
     float m_ref = -INFINITY, l_run = 0.f;
     const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
 
     for (int j = 0; j < nkv; ++j) {
-      const int kv0 = j * kBKV;
       ATT_TRACE(0);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       ATT_TRACE(1);
       float alpha = 1.f;
       bool moved = false;
-      uint64_t lsum2 = 0ull;
-      uint32_t pk[64];
-      if (j == nkv - 1 && ntail < kBKV) {
-        // ---- last, partial key block: only ntail (multiple of 16) columns exist in S; runtime loop over 16-column groups
+      float lsum;
+      float* xmax = s_max + (j & 1) * 256;
+      const bool narrow = (j == nkv - 1 && ntail < kBKV);
+      if (narrow) {
+        // ---- last, partial key block: only ntail (multiple of 16) columns exist in S; runtime loop over the 16-column
+        //      groups of this thread's half
+        const int c_lo = half * 64, c_hi = min(ntail, c_lo + 64);
         float mx = -INFINITY;
-        for (int c = 0; c < ntail; c += 16) {
+        for (int c = c_lo; c < c_hi; c += 16) {
           uint32_t r[16];
           tmem_ld_32x32b_x16(tmem_S + lane_sel + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c + i < valid_last) ? __uint_as_float(r[i]) : -INFINITY);
         }
+        xmax[half * 128 + row] = mx;
+        pair_bar_sync(quarter);
+        mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]);
         const float m_new = fmaxf(m_ref, mx * p.scale_log2);
         moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);
         if (moved) {
           alpha = ex2(m_ref - m_new);
           m_ref = m_new;
         }
-        float lsum = 0.f;
+        lsum = 0.f;
         if (j > 0) {   // P_{j-1} must have been consumed before its columns are overwritten
           mbar_wait(bar_o, (j - 1) & 1);
           tc_fence_after();
         }
-        for (int c = 0; c < ntail; c += 16) {
+        for (int c = c_lo; c < c_hi; c += 16) {
           uint32_t r[16], w[8];
           tmem_ld_32x32b_x16(tmem_S + lane_sel + c, r);
           tmem_ld_wait();
@@ -279,32 +319,55 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfree);
-        lsum2 = pack2(lsum, 0.f);
+        l_run = l_run * alpha + lsum;
+        if (j > 0 && moved) {
+          const uint64_t alpha2 = pack2(alpha, alpha);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tO, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            unpack2(mul2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2), a0, a1);
+            r[i] = __float_as_uint(a0);
+            r[i + 1] = __float_as_uint(a1);
+          }
+          tmem_st_32x32b_x32(tO, r);
+        }
       } else {
-      // the whole 128-wide score row of this thread -> registers, then hand the S columns back
-      uint32_t sr[4][32];
+        // this thread's 64 score columns -> registers, then hand the S columns back
+        uint32_t sr[2][32];
+        tmem_ld_32x32b_x32(tS, sr[0]);
+        tmem_ld_32x32b_x32(tS + 32, sr[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfree);
+        ATT_TRACE(2);
+        // block maximum of this half row (four independent chains), exchanged with the other half-row thread
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, sr[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree);
-      ATT_TRACE(2);
-      {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = max3(mx0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+          mx1 = max3(mx1, __uint_as_float(sr[0][i + 2]), __uint_as_float(sr[0][i + 3]));
+          mx2 = max3(mx2, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+          mx3 = max3(mx3, __uint_as_float(sr[1][i + 2]), __uint_as_float(sr[1][i + 3]));
+        }
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        xmax[half * 128 + row] = mx;
+        pair_bar_sync(quarter);
+        mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]);
         const float m_new = fmaxf(m_ref, mx * p.scale_log2);
-        moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);   // warp-uniform: TMEM accesses are warp-wide
-        if (moved) {
+        moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);   // warp-uniform (TMEM accesses are warp-wide) and, since both
+        if (moved) {                                             //  half-row warps see the same row maxima, CTA-pair-uniform
           alpha = ex2(m_ref - m_new);
           m_ref = m_new;
         }
         const uint64_t negm2 = pack2(-m_ref, -m_ref);
+        uint64_t lsum2 = 0ull;
+        uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2);
@@ -321,39 +384,30 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
             pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
           }
         }
-      }
-      }
-      const bool narrow = (j == nkv - 1 && ntail < kBKV);
-      float l0, l1;
-      unpack2(lsum2, l0, l1);
-      l_run = l_run * alpha + (l0 + l1);
-      ATT_TRACE(3);
-      if (j > 0) {   // P_{j-1} must have been consumed (and O_{j-1} accumulated) before P / O are touched
-        mbar_wait(bar_o, (j - 1) & 1);
-        tc_fence_after();
-        if (moved) {   // rare after the first blocks: rescale the TMEM accumulator in place
-          const uint64_t alpha2 = pack2(alpha, alpha);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
+        float l0, l1;
+        unpack2(lsum2, l0, l1);
+        l_run = l_run * alpha + (l0 + l1);
+        ATT_TRACE(3);
+        if (j > 0) {   // P_{j-1} must have been consumed (and O_{j-1} accumulated) before P / O are touched
+          mbar_wait(bar_o, (j - 1) & 1);
+          tc_fence_after();
+          if (moved) {   // rare after the first blocks: rescale this thread's 32 columns of the TMEM accumulator in place
+            const uint64_t alpha2 = pack2(alpha, alpha);
             uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+            tmem_ld_32x32b_x32(tO, r);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              float a, bq;
-              unpack2(fma2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2, 0ull), a, bq);
-              r[i] = __float_as_uint(a);
-              r[i + 1] = __float_as_uint(bq);
+              float a0, a1;
+              unpack2(mul2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2), a0, a1);
+              r[i] = __float_as_uint(a0);
+              r[i + 1] = __float_as_uint(a1);
             }
-            tmem_st_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+            tmem_st_32x32b_x32(tO, r);
           }
         }
-      }
-      ATT_TRACE(4);
-      // P (bf16 pairs) -> TMEM columns [192, 256): the A operand of O += P V  (the narrow tail path stored its own)
-      if (!narrow) {
-        tmem_st_32x32b_x32(tmem_P + lane_sel, pk);
-        tmem_st_32x32b_x32(tmem_P + lane_sel + 32, pk + 32);
+        ATT_TRACE(4);
+        tmem_st_32x32b_x32(tP, pk);   // P (bf16 pairs): the A operand of O += P V
       }
       tmem_st_wait();
       tc_fence_before();
@@ -364,49 +418,45 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     mbar_wait(bar_o, (nkv - 1) & 1);
     tc_fence_after();
 
-    // ---- epilogue: O (TMEM) -> registers, fold the few trailing keys (if any), normalise, store
-    const int q = q0 + tid;
-    float o[kHD];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    // ---- epilogue: this thread's 32 columns of O (TMEM) -> registers, fold the few trailing keys (if any),
+    //      combine the two half-row sums, normalise, store
+    const int q = q0 + row;
+    float o[32];
+    {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_sel + c * 32, r);
+      tmem_ld_32x32b_x32(tO, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
     }
     if (tail_keys) {
-      float qv[kHD];   // this thread's query row from the swizzled Q tile
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 u;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                     : "r"(sQ + tid * 128 + ((c ^ (tid & 7)) << 4)));
-        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-        qv[c * 8 + 0] = a0.x; qv[c * 8 + 1] = a0.y; qv[c * 8 + 2] = a1.x; qv[c * 8 + 3] = a1.y;
-        qv[c * 8 + 4] = a2.x; qv[c * 8 + 5] = a2.y; qv[c * 8 + 6] = a3.x; qv[c * 8 + 7] = a3.y;
-      }
+      // both half-row threads evaluate the same full 64-wide dot products (same order -> identical m_ref / sums)
+      // and fold the key's V into their own 32 columns; the trailing key's probability is added to half 0's sum only
       for (int t = 0; t < tail_keys; ++t) {
         const __nv_bfloat16* krow = p.qkv + static_cast<int64_t>(row_base + nkv * kBKV + t) * p.ld_qkv;
         float sdot = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
+          uint4 qu;   // this thread's query row from the swizzled Q tile
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qu.x), "=r"(qu.y), "=r"(qu.z), "=r"(qu.w)
+                       : "r"(sQ + row * 128 + ((c ^ (row & 7)) << 4)));
           const uint4 u = __ldg(reinterpret_cast<const uint4*>(krow + colK) + c);
           const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-          sdot = fmaf(qv[c * 8 + 0], a0.x, sdot); sdot = fmaf(qv[c * 8 + 1], a0.y, sdot);
-          sdot = fmaf(qv[c * 8 + 2], a1.x, sdot); sdot = fmaf(qv[c * 8 + 3], a1.y, sdot);
-          sdot = fmaf(qv[c * 8 + 4], a2.x, sdot); sdot = fmaf(qv[c * 8 + 5], a2.y, sdot);
-          sdot = fmaf(qv[c * 8 + 6], a3.x, sdot); sdot = fmaf(qv[c * 8 + 7], a3.y, sdot);
+          const float2 q0v = unpack_bf16x2(qu.x), q1v = unpack_bf16x2(qu.y), q2v = unpack_bf16x2(qu.z), q3v = unpack_bf16x2(qu.w);
+          sdot = fmaf(q0v.x, a0.x, sdot); sdot = fmaf(q0v.y, a0.y, sdot);
+          sdot = fmaf(q1v.x, a1.x, sdot); sdot = fmaf(q1v.y, a1.y, sdot);
+          sdot = fmaf(q2v.x, a2.x, sdot); sdot = fmaf(q2v.y, a2.y, sdot);
+          sdot = fmaf(q3v.x, a3.x, sdot); sdot = fmaf(q3v.y, a3.y, sdot);
         }
         sdot *= p.scale_log2;
         const float m_new = fmaxf(m_ref, sdot);
         const float a = ex2(m_ref - m_new);
         const float pj = __bfloat162float(__float2bfloat16_rn(ex2(sdot - m_new)));   // same bf16 rounding of P as the MMA path
         m_ref = m_new;
-        l_run = l_run * a + pj;
+        l_run = l_run * a + (half == 0 ? pj : 0.f);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(krow + colV) + c);
+        for (int c = 0; c < 4; ++c) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(krow + colV + half * 32) + c);
           const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
           o[c * 8 + 0] = fmaf(o[c * 8 + 0], a, pj * a0.x); o[c * 8 + 1] = fmaf(o[c * 8 + 1], a, pj * a0.y);
           o[c * 8 + 2] = fmaf(o[c * 8 + 2], a, pj * a1.x); o[c * 8 + 3] = fmaf(o[c * 8 + 3], a, pj * a1.y);
@@ -415,11 +465,14 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         }
       }
     }
-    const float inv = 1.f / l_run;
+    s_sum[half * 128 + row] = l_run;
+    pair_bar_sync(quarter);
+    const float l_tot = l_run + s_sum[(half ^ 1) * 128 + row];
+    const float inv = 1.f / l_tot;
     if (q < p.N) {
-      __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
+      __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD + half * 32;
 #pragma unroll
-      for (int i = 0; i < kHD; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 w;
         w.x = cvt_bf16x2(o[i] * inv, o[i + 1] * inv);
         w.y = cvt_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
@@ -427,8 +480,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         w.w = cvt_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
         *reinterpret_cast<uint4*>(op + i) = w;
       }
+      if (half == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
     }
-    if (q < p.N && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_run)) * 0.69314718055994531f;
   }
   tc_fence_before();
   __syncthreads();
@@ -452,7 +505,7 @@ attn_tail_rows_kernel(AttnParams p, int row0, int nrows) {
   const int sub = lane & 7, grp = warp * 4 + (lane >> 3);          // 16-byte chunk of the row, key group 0..31
   const int t = blockIdx.x % nrows;
   const int head = (blockIdx.x / nrows) % p.heads;
-  const int b = blockIdx.x / (nrows * p.heads);
+  const int b = p.B - 1 - blockIdx.x / (nrows * p.heads);   // reverse order: the K / V the main kernel touched last are still in L2
   const int q = row0 + t;
   const __nv_bfloat16* base = p.qkv + static_cast<int64_t>(b) * p.N * p.ld_qkv + head * kHD + sub * 8;
   float qv[8], o[8];

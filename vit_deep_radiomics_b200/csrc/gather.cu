@@ -94,8 +94,27 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const int32_t* __restri
 struct G1Pe {
   double scale;          // 0 = no positional encoding
   const double* div;     // [D/6] divisors 10000^(6 i / D), host-computed in f64
+  double* table;         // [(h + w + S)][2*(D/6)] f64: scale * sin|cos(coord / div) per distinct coordinate (workspace)
   double w_orig, h_orig, res0, res1, res2, noise0, noise1, noise2, mean_x, mean_y, mean_z;
 };
+
+// The encoding of a token depends on its three grid indices separately (xi in [0,h), yi in [0,w), zi in [0,S) under
+// the reference's meshgrid quirk), so the h + w + S distinct coordinate rows are evaluated once in f64 (same operation
+// order as train_models.py:166-176 and :34-44) and the emit kernel only adds table entries: (h+w+S) * D/3 sin/cos
+// instead of n_sel * D.
+__global__ void __launch_bounds__(256) g1_pe_table_kernel(G1Pe pe, int S, int h, int w, int npair2) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(h + w + S) * npair2;
+  if (idx >= total) return;
+  const int e = static_cast<int>(idx / npair2), jj = static_cast<int>(idx % npair2);
+  double v;
+  if (e < h) v = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(static_cast<double>(e) / static_cast<double>(w), pe.w_orig), pe.res0), pe.mean_x), pe.noise0);
+  else if (e < h + w) v = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(static_cast<double>(e - h) / static_cast<double>(h), pe.h_orig), pe.res1), pe.mean_y), pe.noise1);
+  else v = __dadd_rn(__dsub_rn(__dmul_rn(static_cast<double>(e - h - w), pe.res2), pe.mean_z), pe.noise2);
+  const double arg = v / pe.div[jj >> 1];
+  const double enc = (jj & 1) ? cos(arg) : sin(arg);
+  pe.table[idx] = __dmul_rn(enc, pe.scale);
+}
 
 __global__ void __launch_bounds__(kGThreads)
 g1_scatter_kernel(G1Geom g, const int32_t* __restrict__ tile_offsets, int32_t* __restrict__ out_src, int cap) {
@@ -153,8 +172,7 @@ g1_scatter_kernel(G1Geom g, const int32_t* __restrict__ tile_offsets, int32_t* _
 }
 
 // One warp per OUTPUT row (grid-stride over the device-side count): copies the descriptor row and adds the
-// positional encoding.  Decoupled from the compaction so that the fp64 sin/cos work is spread evenly over
-// the SMs however the mask is distributed over the candidate tiles.
+// positional encoding from the per-coordinate f64 table (pure memory traffic: row in, row out, 3 L2-resident table rows).
 template <bool FEAT_BF16>
 __global__ void __launch_bounds__(kGThreads)
 g1_emit_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int D, const int32_t* __restrict__ out_src,
@@ -167,31 +185,32 @@ g1_emit_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int D, 
        row_out += (int64_t)gridDim.x * (kGThreads / 32)) {
     const int k = out_src[row_out * 3 + 0], a = out_src[row_out * 3 + 1], b = out_src[row_out * 3 + 2];
     const int64_t n = (static_cast<int64_t>(a) * g.w + b) * g.S + k;
-    double x = 0., y = 0., z = 0.;
-    if (pe.scale != 0.) {
-      // reference meshgrid(indexing='xy') quirk: xi = (n / S) % h, yi = n / (h*S), zi = n % S
-      const double xi = static_cast<double>((n / g.S) % g.h), yi = static_cast<double>(n / (static_cast<int64_t>(g.h) * g.S));
-      x = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(xi / static_cast<double>(g.w), pe.w_orig), pe.res0), pe.mean_x), pe.noise0);
-      y = __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(yi / static_cast<double>(g.h), pe.h_orig), pe.res1), pe.mean_y), pe.noise1);
-      z = __dadd_rn(__dsub_rn(__dmul_rn(static_cast<double>(k), pe.res2), pe.mean_z), pe.noise2);
-    }
+    // reference meshgrid(indexing='xy') quirk: xi = (n / S) % h, yi = n / (h*S), zi = n % S
+    const double* tx = pe.table + ((n / g.S) % g.h) * npair2;
+    const double* ty = pe.table + (g.h + n / (static_cast<int64_t>(g.h) * g.S)) * npair2;
+    const double* tz = pe.table + (g.h + g.w + k) * npair2;
     const int64_t src_row = static_cast<int64_t>(k) * g.feat_slice_rows + g.feat_row0 + a * g.feat_row_pitch + b;
     auto pe_add = [&](float f, int col) -> float {
       int jj;
-      double v;
-      if (col < third) { jj = col; v = x; }
-      else if (col < two_third) { jj = col - third; v = y; }
-      else { jj = col - two_third; v = z; }
-      if (jj < npair2) {
-        const double arg = v / pe.div[jj >> 1];
-        const double enc = (jj & 1) ? cos(arg) : sin(arg);
-        return static_cast<float>(__dadd_rn(static_cast<double>(f), __dmul_rn(enc, pe.scale)));
-      }
+      const double* t;
+      if (col < third) { jj = col; t = tx; }
+      else if (col < two_third) { jj = col - third; t = ty; }
+      else { jj = col - two_third; t = tz; }
+      if (jj < npair2) return static_cast<float>(__dadd_rn(static_cast<double>(f), __ldg(t + jj)));
       return f;
     };
     if (vec_ok) {
+      // D % 24 == 0 (every 8-column chunk lies inside one axis block and all of its columns are encoded): the chunk's
+      // eight table entries are four 16-byte loads issued together with the descriptor loads -- one memory round trip.
+      const bool pe_vec = pe.scale != 0. && D % 24 == 0;
       for (int c0 = lane * 8; c0 < D; c0 += 256) {
         float f[8];
+        double2 t4[4];
+        if (pe_vec) {
+          const double* t = (c0 < third) ? tx + c0 : (c0 < two_third) ? ty + (c0 - third) : tz + (c0 - two_third);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t4[i] = __ldg(reinterpret_cast<const double2*>(t) + i);
+        }
         if (FEAT_BF16) {
           const uint4 v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(feat) + src_row * ld_feat + c0);
           const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
@@ -201,13 +220,19 @@ g1_emit_kernel(G1Geom g, const void* __restrict__ feat, int64_t ld_feat, int D, 
           const float4 u0 = *reinterpret_cast<const float4*>(fp), u1 = *reinterpret_cast<const float4*>(fp + 4);
           f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
         }
-        if (pe.scale != 0.) {
+        if (pe_vec) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[2 * i] = static_cast<float>(__dadd_rn(static_cast<double>(f[2 * i]), t4[i].x));
+            f[2 * i + 1] = static_cast<float>(__dadd_rn(static_cast<double>(f[2 * i + 1]), t4[i].y));
+          }
+        } else if (pe.scale != 0.) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = pe_add(f[i], c0 + i);
         }
         float* op = out_tok + row_out * D + c0;
-        *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-        *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        __stcs(reinterpret_cast<float4*>(op), make_float4(f[0], f[1], f[2], f[3]));
+        __stcs(reinterpret_cast<float4*>(op + 4), make_float4(f[4], f[5], f[6], f[7]));
       }
     } else {  // any D / alignment: one element per lane
       for (int c = lane; c < D; c += 32) {
@@ -296,10 +321,14 @@ voxel_gather_kernel(const float* __restrict__ img, const uint8_t* __restrict__ m
 
 }  // namespace vdr
 
-extern "C" size_t vdr_mask_gather_workspace_bytes(int S, int h, int w) {
+static size_t g1_scan_bytes(int S, int h, int w) {   // tile counts + offsets, rounded up to 16 bytes
   const int64_t total = (int64_t)S * h * w;
   const int64_t tiles = (total + vdr::kTile - 1) / vdr::kTile;
-  return (size_t)(tiles > 0 ? tiles : 1) * 2 * sizeof(int32_t);
+  return (((size_t)(tiles > 0 ? tiles : 1) * 2 * sizeof(int32_t)) + 15) & ~(size_t)15;
+}
+
+extern "C" size_t vdr_mask_gather_workspace_bytes(int S, int h, int w, int D) {
+  return g1_scan_bytes(S, h, w) + (size_t)(h + w + S) * (size_t)(2 * (D / 6)) * sizeof(double);
 }
 
 extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
@@ -318,7 +347,8 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   const bool vec_ok = D % 8 == 0 && ld_feat % 8 == 0 && aligned16(feat) && aligned16(out_tok);
   VDR_CHECK_ARG(feat_dtype == VDR_DTYPE_BF16 || feat_dtype == VDR_DTYPE_F32, VDR_EINVAL, "vdr_mask_gather: bad feat_dtype");
   VDR_CHECK_ARG((int64_t)S * h * w < 0x7fffffffLL, VDR_EINVAL, "vdr_mask_gather: too many candidates");
-  VDR_CHECK_ARG(workspace_bytes >= vdr_mask_gather_workspace_bytes(S, h, w), VDR_EWORKSPACE, "vdr_mask_gather: workspace too small (%zu < %zu)", workspace_bytes, vdr_mask_gather_workspace_bytes(S, h, w));
+  VDR_CHECK_ARG(workspace_bytes >= vdr_mask_gather_workspace_bytes(S, h, w, D), VDR_EWORKSPACE, "vdr_mask_gather: workspace too small (%zu < %zu)", workspace_bytes, vdr_mask_gather_workspace_bytes(S, h, w, D));
+  VDR_CHECK_ARG(aligned16(workspace), VDR_EALIGN, "vdr_mask_gather: workspace must be 16-byte aligned");
   VDR_CHECK_ARG(pe_scale == 0.0 || (pe_div && coef_host), VDR_EINVAL, "vdr_mask_gather: positional encoding needs pe_div and coef_host");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   G1Geom g{mask, row_map, col_map, S, h, w, mask_slice_stride, mask_row_stride, mask_col_stride, feat_slice_rows, feat_row_pitch, feat_row0, (int64_t)S * h * w};
@@ -328,11 +358,19 @@ extern "C" int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat
   G1Pe pe{};
   pe.scale = pe_scale;
   pe.div = pe_div;
+  pe.table = reinterpret_cast<double*>(static_cast<uint8_t*>(workspace) + g1_scan_bytes(S, h, w));
+  const int npair2 = 2 * (D / 6);
   if (pe_scale != 0.0) {
     pe.w_orig = coef_host[0]; pe.h_orig = coef_host[1];
     pe.res0 = coef_host[2]; pe.res1 = coef_host[3]; pe.res2 = coef_host[4];
     pe.noise0 = coef_host[5]; pe.noise1 = coef_host[6]; pe.noise2 = coef_host[7];
     pe.mean_x = coef_host[8]; pe.mean_y = coef_host[9]; pe.mean_z = coef_host[10];
+  }
+  if (pe_scale != 0.0 && npair2 > 0) {
+    const int64_t entries = (int64_t)(h + w + S) * npair2;
+    g1_pe_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, s>>>(pe, S, h, w, npair2);
+    count_launch();
+    VDR_CHECK_LAUNCH("g1_pe_table_kernel");
   }
   g1_count_kernel<<<tiles, kGThreads, 0, s>>>(g, counts);
   VDR_CHECK_LAUNCH("g1_count_kernel");

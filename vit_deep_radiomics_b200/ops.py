@@ -297,7 +297,7 @@ def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = 
     tokens = torch.empty((cap, D), dtype=torch.float32, device=dev)
     src = torch.empty((cap, 3), dtype=torch.int32, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
-    ws_bytes = _C.lib().vdr_mask_gather_workspace_bytes(S, h, w)
+    ws_bytes = _C.lib().vdr_mask_gather_workspace_bytes(S, h, w, D)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     pe_scale, pe_div_ptr, coef = 0.0, None, None
     if pe is not None:
