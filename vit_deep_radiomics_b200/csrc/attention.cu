@@ -14,6 +14,7 @@
 // Online softmax with LAZY rescaling: probabilities are taken relative to a reference maximum that only moves
 // when the running maximum exceeds it by 2^8, so O accumulates in TMEM across key blocks and is rescaled rarely.
 // Q, K, V are read in place from the packed QKV GEMM output through one 2-D tensor map.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -24,7 +25,7 @@ constexpr int kSoftmaxWarps = 8;
 constexpr int kAttnThreads = (kSoftmaxWarps + 4) * 32;   // 2 softmax warpgroups + issuer warpgroup
 constexpr int kBQ = 128, kBKV = 128, kHD = 64;
 constexpr int kTileBytes = 128 * kHD * 2;               // 16 KB: one 128 x 64 bf16 tile
-constexpr int kAttnSmem = 5 * kTileBytes /*Q, 4 ring slots*/ + 256 /*barriers*/ + 3 * 2 * 128 * 4 /*max exchange x2, sum exchange*/;
+constexpr int kAttnSmem = 5 * kTileBytes /*Q, 4 ring slots*/ + 256 /*barriers*/ + 3 * 2 * 128 * 4 /*max exchange x2, sum exchange*/ + 8 * 2 * 128 /*trailing keys: K, V rows*/;
 constexpr int kAttnTmemCols = 256;                       // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 
 __device__ __forceinline__ float ex2(float x) {
@@ -53,6 +54,8 @@ struct AttnParams {
   int64_t ld_out;
   int B, N, heads, d;
   float scale_log2;
+  int dbg;                     // timing experiments only (VDR_ATTN_DBG): 1 = tail CTAs exit at once, 2 = skip the trailing-key fold
+  int q_tiles, tail_rows;      // full 128-row query tiles (tensor cores) / trailing rows handled by the extra CUDA-core CTA
   unsigned long long* trace;   // debug (VDR_ATTN_TRACE builds only): per-iteration timestamps of CTA (0,0,0)
 };
 
@@ -127,6 +130,95 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// A handful of trailing query rows (N mod 128 <= 8, e.g. the 1025th token of a 32x32-patch image + CLS) would otherwise
+// occupy a whole 128-row tensor-core tile per (image, head).  They are handled on the CUDA cores by one extra CTA per
+// (image, head) of the SAME grid (blockIdx.x == number of full query tiles), so that its K / V reads hit the L2 lines its
+// eight sibling tensor-core CTAs are streaming at the same time.  8 lanes share a key (16 bytes of the 128-byte K / V
+// row each): a warp-wide load touches 4 rows x 128 contiguous bytes; the 48 lane-groups of the CTA each run an online
+// softmax over the keys dealt to them and the partial states are merged through shared memory.
+__device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, int head, int b, int row0, int nrows) {
+  constexpr int kGroups = kAttnThreads / 8;                        // 48 key groups
+  float* s_m = sm;                                                 // [kGroups]
+  float* s_l = sm + kGroups;                                       // [kGroups]
+  float* s_o = sm + 2 * kGroups;                                   // [kGroups][kHD]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, grp = warp * 4 + (lane >> 3);          // 16-byte chunk of the row, key group
+  const __nv_bfloat16* base = p.qkv + static_cast<int64_t>(b) * p.N * p.ld_qkv + head * kHD + sub * 8;
+  const uint32_t gmask = 0xffu << (lane & 24);
+  // Pull this head's K and V rows towards L2 first (fire-and-forget, one 128-byte line per lane 0 / lane 1 of each key
+  // group): the CTA usually starts before its tensor-core siblings have streamed them in, and six dependent DRAM round
+  // trips would otherwise make this small CTA live longer than a full tile.
+  if (sub < 2)
+    for (int j = grp; j < p.N; j += kGroups) {
+      const __nv_bfloat16* line = p.qkv + (static_cast<int64_t>(b) * p.N + j) * p.ld_qkv + (1 + sub) * p.d + head * kHD;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
+  for (int t = 0; t < nrows; ++t) {
+    const int q = row0 + t;
+    float qv[8], o[8];
+    {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(q) * p.ld_qkv));
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      qv[0] = a0.x * p.scale_log2; qv[1] = a0.y * p.scale_log2; qv[2] = a1.x * p.scale_log2; qv[3] = a1.y * p.scale_log2;
+      qv[4] = a2.x * p.scale_log2; qv[5] = a2.y * p.scale_log2; qv[6] = a3.x * p.scale_log2; qv[7] = a3.y * p.scale_log2;
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    // four keys per step with all eight loads issued first: the loop is bound by L2 latency, not by arithmetic
+    for (int j0 = grp; j0 < p.N; j0 += 4 * kGroups) {
+      uint4 ku[4], vu[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * kGroups;
+        if (j < p.N) {
+          const __nv_bfloat16* row = base + static_cast<int64_t>(j) * p.ld_qkv;
+          ku[u] = __ldg(reinterpret_cast<const uint4*>(row + p.d));
+          vu[u] = __ldg(reinterpret_cast<const uint4*>(row + 2 * p.d));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u * kGroups < p.N) {   // uniform inside an 8-lane group
+          const float2 k0 = unpack_bf16x2(ku[u].x), k1 = unpack_bf16x2(ku[u].y), k2 = unpack_bf16x2(ku[u].z), k3 = unpack_bf16x2(ku[u].w);
+          float sdot = qv[0] * k0.x + qv[1] * k0.y + qv[2] * k1.x + qv[3] * k1.y + qv[4] * k2.x + qv[5] * k2.y + qv[6] * k3.x + qv[7] * k3.y;
+          sdot += __shfl_xor_sync(gmask, sdot, 1);   // reduce inside the 8-lane group (groups may leave the loop at
+          sdot += __shfl_xor_sync(gmask, sdot, 2);   //  different trip counts, so the mask names only this group)
+          sdot += __shfl_xor_sync(gmask, sdot, 4);
+          const float m_new = fmaxf(m, sdot);
+          const float a = ex2(m - m_new), pj = ex2(sdot - m_new);
+          m = m_new;
+          l = l * a + pj;
+          const float2 v0 = unpack_bf16x2(vu[u].x), v1 = unpack_bf16x2(vu[u].y), v2 = unpack_bf16x2(vu[u].z), v3 = unpack_bf16x2(vu[u].w);
+          o[0] = fmaf(o[0], a, pj * v0.x); o[1] = fmaf(o[1], a, pj * v0.y); o[2] = fmaf(o[2], a, pj * v1.x); o[3] = fmaf(o[3], a, pj * v1.y);
+          o[4] = fmaf(o[4], a, pj * v2.x); o[5] = fmaf(o[5], a, pj * v2.y); o[6] = fmaf(o[6], a, pj * v3.x); o[7] = fmaf(o[7], a, pj * v3.y);
+        }
+      }
+    }
+    if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) s_o[grp * kHD + sub * 8 + d] = o[d];
+    __syncthreads();
+    if (warp == 0) {
+      float mt = -INFINITY;
+      for (int g = 0; g < kGroups; ++g) mt = fmaxf(mt, s_m[g]);
+      float lt = 0.f, o0 = 0.f, o1 = 0.f;
+      for (int g = 0; g < kGroups; ++g) {
+        const float f = (s_m[g] == -INFINITY) ? 0.f : ex2(s_m[g] - mt);
+        lt += s_l[g] * f;
+        o0 += s_o[g * kHD + lane] * f;
+        o1 += s_o[g * kHD + lane + 32] * f;
+      }
+      const float inv = 1.f / lt;
+      __nv_bfloat16* op = p.out + (static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD;
+      op[lane] = __float2bfloat16_rn(o0 * inv);
+      op[lane + 32] = __float2bfloat16_rn(o1 * inv);
+      if (lane == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mt + log2f(lt)) * 0.69314718055994531f;
+    }
+    __syncthreads();
+  }
+}
+
 // Pipeline per 128-key block j (no CTA-wide barrier in the loop):
 //   issuers: wait S_j consumed -> prefetch K_{j+2}, issue S_{j+1};  wait P_j ready -> issue O += P_j V_j
 //   softmax: wait S_j -> registers -> signal "consumed" -> max (exchanged between the two half-row threads) ->
@@ -145,12 +237,18 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   uint64_t* bar_o = bars + 6;        // O += P_j V_j complete             (tcgen05.commit)
   uint64_t* bar_sfree = bars + 7;    // S_j is in registers               (8 softmax warps arrive)
   uint64_t* bar_pready = bars + 8;   // P_j is in TMEM, O rescaled        (8 softmax warps arrive)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bar_tail = bars + 9;     // trailing keys' K / V rows are in shared memory (warp 10 arrives)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
   float* s_max = reinterpret_cast<float*>(smem + 5 * kTileBytes + 256);   // [2][2][128]
   float* s_sum = s_max + 2 * 2 * 128;                                      // [2][128]
+  uint4* s_tail = reinterpret_cast<uint4*>(s_sum + 2 * 128);               // [tail_keys][K row (8 x 16 B) | V row (8 x 16 B)]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
+  if (static_cast<int>(blockIdx.x) >= p.q_tiles) {   // the extra CTA of this (image, head): trailing query rows on the CUDA cores
+    if (p.dbg != 1) attn_tail_rows(p, reinterpret_cast<float*>(smem), head, b, p.N - p.tail_rows, p.tail_rows);
+    return;
+  }
   const int row_base = b * p.N;                       // first token row of this image in the qkv matrix
   const int colQ = head * kHD, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
   // Key blocks: full 128-key blocks on the tensor cores; a ragged last block either runs as a narrow MMA block
@@ -163,7 +261,14 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   const int valid_last = tail_keys ? kBKV : last_keys;           // keys in the last MMA block
   const int ntail = (valid_last + 15) & ~15;                     // ... rounded to the MMA's 16-column granularity
 
-  if (tid == 0) {
+  auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2 (slots 0/2), odd = V block t/2 (slots 1/3)
+    const int slot = t & 3;
+    mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
+    tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + (t >> 1) * kBKV);
+  };
+  if (tid == kSoftmaxWarps * 32) {
+    // one thread initialises the barriers and immediately starts the first loads (Q, K0, V0, K1, V1), so that their
+    // latency overlaps the TMEM allocation and the CTA-wide barrier below
     if (base & 1023u) { printf("vdr: attention smem base not 1024-byte aligned\n"); __trap(); }
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_q, 1);
@@ -172,7 +277,16 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     mbar_init(bar_o, 1);
     mbar_init(bar_sfree, kSoftmaxWarps);
     mbar_init(bar_pready, kSoftmaxWarps);
+    mbar_init(bar_tail, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(bar_q, kTileBytes);
+    tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
+    issue_tile(0);
+    issue_tile(1);
+    if (nkv > 1) {
+      issue_tile(2);
+      issue_tile(3);
+    }
   }
   if (warp == 0) tmem_alloc<kAttnTmemCols>(tmem_ptr);
   tc_fence_before();
@@ -188,11 +302,6 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     // 8 steps) are dispatched concurrently.
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
-    auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2 (slots 0/2), odd = V block t/2 (slots 1/3)
-      const int slot = t & 3;
-      mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
-      tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + (t >> 1) * kBKV);
-    };
     if (warp == kSoftmaxWarps && lane == 0) {
       // ---- K tiles + S = Q K^T
       auto issue_s = [&](int j) {
@@ -207,10 +316,6 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
         umma_commit(bar_s);
       };
-      mbar_arrive_expect_tx(bar_q, kTileBytes);
-      tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
-      issue_tile(0);
-      if (nkv > 1) issue_tile(2);
       mbar_wait_relaxed(bar_q, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
@@ -222,10 +327,17 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         if (j + 2 < nkv) issue_tile(2 * j + 4);            // K_{j+2} into K_j's slot
         ISS_TRACE(2);
       }
+    } else if (warp == kSoftmaxWarps + 2) {
+      // ---- the few trailing keys (folded in by the softmax epilogue): their K and V rows -> shared memory, early
+      for (int i = lane; i < tail_keys * 16; i += 32) {
+        const int t = i >> 4, c = i & 15;
+        const __nv_bfloat16* krow = p.qkv + static_cast<int64_t>(row_base + nkv * kBKV + t) * p.ld_qkv;
+        s_tail[i] = __ldg(reinterpret_cast<const uint4*>(krow + (c < 8 ? colK : colV)) + (c & 7));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tail);
     } else if (warp == kSoftmaxWarps + 1 && lane == 0) {
       // ---- V tiles + O += P V
-      issue_tile(1);
-      if (nkv > 1) issue_tile(3);
       for (int j = 0; j < nkv; ++j) {
         ISS_TRACE(3);
         mbar_wait_relaxed(bar_pready, j & 1);              // P_j is in TMEM (and O rescaled if the maximum moved)
@@ -429,26 +541,26 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
 #pragma unroll
       for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
     }
-    if (tail_keys) {
+    if (tail_keys && p.dbg != 2) {
+      mbar_wait(bar_tail, 0);
       // both half-row threads evaluate the same full 64-wide dot products (same order -> identical m_ref / sums)
       // and fold the key's V into their own 32 columns; the trailing key's probability is added to half 0's sum only
       for (int t = 0; t < tail_keys; ++t) {
-        const __nv_bfloat16* krow = p.qkv + static_cast<int64_t>(row_base + nkv * kBKV + t) * p.ld_qkv;
-        float sdot = 0.f;
+        float sd0 = 0.f, sd1 = 0.f, sd2 = 0.f, sd3 = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint4 qu;   // this thread's query row from the swizzled Q tile
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qu.x), "=r"(qu.y), "=r"(qu.z), "=r"(qu.w)
+          asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qu.x), "=r"(qu.y), "=r"(qu.z), "=r"(qu.w)
                        : "r"(sQ + row * 128 + ((c ^ (row & 7)) << 4)));
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(krow + colK) + c);
+          const uint4 u = s_tail[t * 16 + c];
           const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
           const float2 q0v = unpack_bf16x2(qu.x), q1v = unpack_bf16x2(qu.y), q2v = unpack_bf16x2(qu.z), q3v = unpack_bf16x2(qu.w);
-          sdot = fmaf(q0v.x, a0.x, sdot); sdot = fmaf(q0v.y, a0.y, sdot);
-          sdot = fmaf(q1v.x, a1.x, sdot); sdot = fmaf(q1v.y, a1.y, sdot);
-          sdot = fmaf(q2v.x, a2.x, sdot); sdot = fmaf(q2v.y, a2.y, sdot);
-          sdot = fmaf(q3v.x, a3.x, sdot); sdot = fmaf(q3v.y, a3.y, sdot);
+          sd0 = fmaf(q0v.x, a0.x, sd0); sd0 = fmaf(q0v.y, a0.y, sd0);
+          sd1 = fmaf(q1v.x, a1.x, sd1); sd1 = fmaf(q1v.y, a1.y, sd1);
+          sd2 = fmaf(q2v.x, a2.x, sd2); sd2 = fmaf(q2v.y, a2.y, sd2);
+          sd3 = fmaf(q3v.x, a3.x, sd3); sd3 = fmaf(q3v.y, a3.y, sd3);
         }
-        sdot *= p.scale_log2;
+        const float sdot = ((sd0 + sd1) + (sd2 + sd3)) * p.scale_log2;
         const float m_new = fmaxf(m_ref, sdot);
         const float a = ex2(m_ref - m_new);
         const float pj = __bfloat162float(__float2bfloat16_rn(ex2(sdot - m_new)));   // same bf16 rounding of P as the MMA path
@@ -456,7 +568,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         l_run = l_run * a + (half == 0 ? pj : 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(krow + colV + half * 32) + c);
+          const uint4 u = s_tail[t * 16 + 8 + half * 4 + c];
           const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
           o[c * 8 + 0] = fmaf(o[c * 8 + 0], a, pj * a0.x); o[c * 8 + 1] = fmaf(o[c * 8 + 1], a, pj * a0.y);
           o[c * 8 + 2] = fmaf(o[c * 8 + 2], a, pj * a1.x); o[c * 8 + 3] = fmaf(o[c * 8 + 3], a, pj * a1.y);
@@ -488,73 +600,6 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<kAttnTmemCols>(tmem_base);
-  }
-}
-
-// A handful of trailing query rows (N mod 128 <= 8, e.g. the 1025th token of a 32x32-patch image + CLS) would
-// otherwise occupy a whole 128-row tensor-core tile per (image, head): one warp per row instead.  Each lane
-// walks keys lane, lane+32, ... with its own online softmax (fp32), then the 32 partial states are merged.
-constexpr int kTailWarps = 8;
-__global__ void __launch_bounds__(kTailWarps * 32)
-attn_tail_rows_kernel(AttnParams p, int row0, int nrows) {
-  // One CTA per (image, head, row).  8 lanes share a key (16 bytes of the 128-byte K / V row each), so a warp-wide
-  // load touches 4 rows x 128 contiguous bytes; the 32 lane-groups of the CTA each run an online softmax over the
-  // keys dealt to them and the partial states are merged at the end.
-  __shared__ float s_m[kTailWarps * 4], s_l[kTailWarps * 4], s_o[kTailWarps * 4][kHD];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & 7, grp = warp * 4 + (lane >> 3);          // 16-byte chunk of the row, key group 0..31
-  const int t = blockIdx.x % nrows;
-  const int head = (blockIdx.x / nrows) % p.heads;
-  const int b = p.B - 1 - blockIdx.x / (nrows * p.heads);   // reverse order: the K / V the main kernel touched last are still in L2
-  const int q = row0 + t;
-  const __nv_bfloat16* base = p.qkv + static_cast<int64_t>(b) * p.N * p.ld_qkv + head * kHD + sub * 8;
-  float qv[8], o[8];
-  {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(q) * p.ld_qkv));
-    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-    qv[0] = a0.x * p.scale_log2; qv[1] = a0.y * p.scale_log2; qv[2] = a1.x * p.scale_log2; qv[3] = a1.y * p.scale_log2;
-    qv[4] = a2.x * p.scale_log2; qv[5] = a2.y * p.scale_log2; qv[6] = a3.x * p.scale_log2; qv[7] = a3.y * p.scale_log2;
-  }
-#pragma unroll
-  for (int d = 0; d < 8; ++d) o[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  const uint32_t gmask = 0xffu << (lane & 24);
-  for (int j = grp; j < p.N; j += kTailWarps * 4) {
-    const __nv_bfloat16* row = base + static_cast<int64_t>(j) * p.ld_qkv;
-    const uint4 ku = __ldg(reinterpret_cast<const uint4*>(row + p.d));
-    const uint4 vu = __ldg(reinterpret_cast<const uint4*>(row + 2 * p.d));
-    const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y), k2 = unpack_bf16x2(ku.z), k3 = unpack_bf16x2(ku.w);
-    float sdot = qv[0] * k0.x + qv[1] * k0.y + qv[2] * k1.x + qv[3] * k1.y + qv[4] * k2.x + qv[5] * k2.y + qv[6] * k3.x + qv[7] * k3.y;
-    sdot += __shfl_xor_sync(gmask, sdot, 1);   // reduce inside the 8-lane group (groups may leave the loop at
-    sdot += __shfl_xor_sync(gmask, sdot, 2);   //  different trip counts, so the mask names only this group)
-    sdot += __shfl_xor_sync(gmask, sdot, 4);
-    const float m_new = fmaxf(m, sdot);
-    const float a = ex2(m - m_new), pj = ex2(sdot - m_new);
-    m = m_new;
-    l = l * a + pj;
-    const float2 v0 = unpack_bf16x2(vu.x), v1 = unpack_bf16x2(vu.y), v2 = unpack_bf16x2(vu.z), v3 = unpack_bf16x2(vu.w);
-    o[0] = fmaf(o[0], a, pj * v0.x); o[1] = fmaf(o[1], a, pj * v0.y); o[2] = fmaf(o[2], a, pj * v1.x); o[3] = fmaf(o[3], a, pj * v1.y);
-    o[4] = fmaf(o[4], a, pj * v2.x); o[5] = fmaf(o[5], a, pj * v2.y); o[6] = fmaf(o[6], a, pj * v3.x); o[7] = fmaf(o[7], a, pj * v3.y);
-  }
-  if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
-#pragma unroll
-  for (int d = 0; d < 8; ++d) s_o[grp][sub * 8 + d] = o[d];
-  __syncthreads();
-  if (warp == 0) {
-    float mt = -INFINITY;
-    for (int g = 0; g < kTailWarps * 4; ++g) mt = fmaxf(mt, s_m[g]);
-    float lt = 0.f, o0 = 0.f, o1 = 0.f;
-    for (int g = 0; g < kTailWarps * 4; ++g) {
-      const float f = (s_m[g] == -INFINITY) ? 0.f : ex2(s_m[g] - mt);
-      lt += s_l[g] * f;
-      o0 += s_o[g][lane] * f;
-      o1 += s_o[g][lane + 32] * f;
-    }
-    const float inv = 1.f / lt;
-    __nv_bfloat16* op = p.out + (static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD;
-    op[lane] = __float2bfloat16_rn(o0 * inv);
-    op[lane + 32] = __float2bfloat16_rn(o1 * inv);
-    if (lane == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mt + log2f(lt)) * 0.69314718055994531f;
   }
 }
 
@@ -590,21 +635,16 @@ extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, in
   p.B = B; p.N = N; p.heads = heads; p.d = d;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
-  // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on a warp-per-row kernel
+  p.dbg = getenv("VDR_ATTN_DBG") ? atoi(getenv("VDR_ATTN_DBG")) : 0;
+  // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head)
   const int tail_rows = N % kBQ;
   const bool vector_tail = tail_rows > 0 && tail_rows <= 8;
-  const int q_tiles = vector_tail ? N / kBQ : (N + kBQ - 1) / kBQ;
+  p.q_tiles = vector_tail ? N / kBQ : (N + kBQ - 1) / kBQ;
+  p.tail_rows = vector_tail ? tail_rows : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (q_tiles > 0) {
-    dim3 grid(q_tiles, heads, B);
-    flash_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
-    count_launch();
-    VDR_CHECK_LAUNCH("flash_attn_fwd_kernel");
-  }
-  if (vector_tail) {
-    attn_tail_rows_kernel<<<(unsigned)(B * heads * tail_rows), kTailWarps * 32, 0, s>>>(p, N - tail_rows, tail_rows);
-    count_launch();
-    VDR_CHECK_LAUNCH("attn_tail_rows_kernel");
-  }
+  dim3 grid(p.q_tiles + (vector_tail ? 1 : 0), heads, B);
+  flash_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
+  count_launch();
+  VDR_CHECK_LAUNCH("flash_attn_fwd_kernel");
   return VDR_OK;
 }
