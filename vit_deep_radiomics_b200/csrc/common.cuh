@@ -17,9 +17,9 @@ void set_error(const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 int  num_sms();
-// Encode a 2-D bf16 row-major tensor map (dims: inner = cols, outer = rows), 128B swizzle.
+// Encode a 2-D bf16 row-major tensor map (dims: inner = cols, outer = rows), 128-byte (default) or 64-byte swizzle.
 int  make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
-                       uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+                       uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
 #define VDR_CHECK_ARG(cond, code, ...)                 \
   do {                                                 \
@@ -110,6 +110,23 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared -> global tile store (bulk async group); the box is clipped at the tensor's edges
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest kPending bulk groups of this thread have finished READING their shared-memory source
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void tma_load_2d_addr(const CUtensorMap* map, uint64_t* bar, uint32_t dst_smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -351,9 +368,10 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // Exact-erf GELU of two values on the packed fp32x2 pipes.  erf by Abramowitz-Stegun 7.1.28,
-//   erf(z) = 1 - 1 / (1 + a1 z + ... + a6 z^6)^16  (z >= 0, |error| <= 3e-7; ~1e-6 as evaluated in fp32),
-// i.e. six FFMA2, four FMUL2 and ONE MUFU.RCP per element instead of erff()'s two-branch polynomial:
-// 9.5 issue slots per element instead of ~19, so the GELU epilogue hides behind the MMAs of the next tile.
+//   erf(z) = 1 - r,  r = 1 / (1 + a1 z + ... + a6 z^6)^16  (z >= 0, |error| <= 3e-7; ~1e-6 as evaluated in fp32),
+// and  gelu(x) = x/2 (1 + erf(x / sqrt 2)) = relu(x) - |x|/2 * r  (both signs; no copysign, no 1 - r):
+// two FMUL, eight packed FFMA2/FMUL2 for the polynomial and its 16th power, two MUFU.RCP, two FMNMX and two more
+// packed ops per PAIR of elements, branch-free, no slow-path calls.
 __device__ __forceinline__ uint64_t gelu_fast2(uint64_t x2) {
   float x0, x1;
   unpack2(x2, x0, x1);
@@ -370,9 +388,54 @@ __device__ __forceinline__ uint64_t gelu_fast2(uint64_t x2) {
   acc = mul2(acc, acc);
   float p0, p1;
   unpack2(acc, p0, p1);
-  const float e0 = copysignf(1.0f - rcp_approx(p0), x0), e1 = copysignf(1.0f - rcp_approx(p1), x1);   // erf(x / sqrt 2)
-  const uint64_t hx2 = mul2(x2, pack2(0.5f, 0.5f));
-  return fma2(hx2, pack2(e0, e1), hx2);
+  const uint64_t r2 = pack2(rcp_approx(p0), rcp_approx(p1));                              // 1 - erf(|x| / sqrt 2)
+  const uint64_t relu2 = pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+  const uint64_t nhax2 = mul2(z2, pack2(-0.70710678118654752f, -0.70710678118654752f));   // -|x| / 2
+  return fma2(nhax2, r2, relu2);
+}
+
+// The same GELU over the 16 packed pairs of an epilogue chunk, written step by step so that the 16 dependency chains
+// are interleaved.  Packed f32x2 on purpose: on B200 a packed FFMA2 / FMUL2 occupies the FMA pipe for ~4 cycles per
+// scheduler against ~1.2 for a scalar FFMA (tools/microbench/pipe_rates.cu), so scalar code has more raw throughput --
+// but it also executes ~1.6x the instructions, and the extraction step runs at the 1 kW power cap, where fewer
+// instructions win (measured in the pipeline: 0.61 ms packed vs 0.65 ms scalar for the fc1 GEMM).
+__device__ __forceinline__ void gelu_fast2_x16(uint64_t (&x2)[16]) {
+  uint64_t z2[16], acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x0, x1;
+    unpack2(x2[i], x0, x1);
+    z2[i] = pack2(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = fma2(z2[i], pack2(0.0000430638f, 0.0000430638f), pack2(0.0002765672f, 0.0002765672f));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = fma2(acc[i], z2[i], pack2(0.0001520143f, 0.0001520143f));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = fma2(acc[i], z2[i], pack2(0.0092705272f, 0.0092705272f));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = fma2(acc[i], z2[i], pack2(0.0422820123f, 0.0422820123f));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = fma2(acc[i], z2[i], pack2(0.0705230784f, 0.0705230784f));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = fma2(acc[i], z2[i], pack2(1.0f, 1.0f));
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = mul2(acc[i], acc[i]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float p0, p1;
+    unpack2(acc[i], p0, p1);
+    acc[i] = pack2(rcp_approx(p0), rcp_approx(p1));                     // 1 - erf(|x| / sqrt 2)
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x0, x1;
+    unpack2(x2[i], x0, x1);
+    const uint64_t relu2 = pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+    x2[i] = fma2(mul2(z2[i], pack2(-0.70710678118654752f, -0.70710678118654752f)), acc[i], relu2);   // relu(x) - |x|/2 * r
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -3,10 +3,11 @@
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM)
-//   warps 2..9  epilogue       (tcgen05.ld -> bias / GELU / residual -> vector stores)
+//   warps 2..9  epilogue       (tcgen05.ld -> bias / GELU / residual -> per-warp TMA stores)
 // Two TMEM accumulator buffers (2*BN columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  Replaces the torch.nn.Linear call sites listed in include/vdr.h.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -17,12 +18,12 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// trace record (CTA 0 only): slot = tile_iter * 8 + event
+// trace record (CTA 0 only): slot = tile_iter * 16 + event  (events 8.. = epilogue warp 0, chunks 0 and 1)
 //   0 mma: accumulator free   1 mma: first stage landed   2 mma: last MMA issued
 //   3 epi: accumulator ready  4 epi: tile stored          5 producer: first TMA of tile issued  6 producer: last TMA issued
 #define VDR_TRACE(ev, it)                                                                      \
   do {                                                                                         \
-    if (p.trace != nullptr && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 8 + (ev)] = gtime(); \
+    if (p.trace != nullptr && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 16 + (ev)] = gtime(); \
   } while (0)
 
 constexpr int BM = 128;
@@ -30,6 +31,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kTmaWarp = 0, kMmaWarp = 1, kFirstEpiWarp = 2;
 
 struct GemmParams {
   const float* bias;
@@ -40,6 +42,8 @@ struct GemmParams {
   int epilogue, r_dtype, c_dtype;
   int out_group, out_group_stride, out_offset;
   int res_mod, res_offset;
+  int tma_out;                 // 1: bf16 output tiles leave through TMA stores (tmC); 2: ... and the bf16 residual arrives through TMA loads (tmR)
+  int64_t out_rows;            // rows of the output matrix (TMA clipping bound)
   unsigned long long* trace;   // debug: per-tile timestamps of CTA 0 (nullptr = off)
   int dbg;                     // debug: 1 = skip MMAs, 2 = skip TMA loads (timing experiments only; results are garbage)
 };
@@ -54,27 +58,35 @@ struct GemmCfg {
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = (BN / kCtas) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (kCtas == 2) ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int kStages = (kCtas == 2) ? 5 : ((BN == 256) ? 4 : (BN == 128 ? 5 : 7));   // what fits 227 KB next to the epilogue tiles
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 * 4 /*bias staging*/ + kEpiWarps * 2048 /*store staging*/;
+  // per epilogue warp: a 2 KB store tile (+ a 2 KB TMA-loaded residual tile; the single-CTA 128 x 256 configuration has no
+  // room for it next to four 48 KB stages and keeps the register-staged residual path)
+  static constexpr bool kResTma = !(BN == 256 && kCtas == 1);
+  static constexpr int kEpiBufBytes = kResTma ? 4096 : 2048;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiBufBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 * 4 /*bias staging*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
 template <int BN, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = GemmCfg<BN, kCtas>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  // layout (base is 1024-byte aligned): stages | epilogue tiles (swizzle patterns need 512-byte alignment) | barriers | bias
+  constexpr int kAuxOff = kStages * Cfg::kStageBytes + kEpiWarps * Cfg::kEpiBufBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kAuxOff);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_smem = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);  // [kEpiWarps][BN/2]
-  const uint32_t stage_base = base + kStages * Cfg::kStageBytes + 256 + BN * 16;          // [kEpiWarps][32 rows][64 B]
+  uint64_t* res_bar = tmem_empty + 2;                       // [kEpiWarps] residual chunk landed (one per epilogue warp)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  float* bias_smem = reinterpret_cast<float*>(smem + kAuxOff + 256);  // [kEpiWarps][BN/2]
+  const uint32_t stage_base = base + kStages * Cfg::kStageBytes;                          // [kEpiWarps][store tile 2 KB (| residual tile 2 KB)]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,11 +98,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;   // both CTAs of a pair walk the same tiles
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    if (p.tma_out >= 1) tma_prefetch_desc(&tmC);
+    if (p.tma_out >= 2) tma_prefetch_desc(&tmR);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);                // pair: the leader's arrive.expect_tx covers the bytes of BOTH CTAs
       mbar_init(&empty_bar[s], 1);
@@ -99,9 +113,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps * kCtas);   // pair: the epilogue warps of BOTH CTAs release the leader
     }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == kFirstEpiWarp) {
     if constexpr (kCtas == 2) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_ptr);
     else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
   }
@@ -111,7 +126,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -145,7 +160,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         VDR_TRACE(6, it);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {   // pair: only the leader CTA issues MMAs
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
@@ -190,7 +205,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 2;
+    const int ew = warp - kFirstEpiWarp;
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = ew >> 2;            // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
@@ -201,9 +216,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Per-warp staging tile (32 rows x 64 B, 16-byte chunks XOR-swizzled): accumulators arrive with
     // thread == row, but global memory wants consecutive lanes on consecutive addresses.  Going through
     // this tile turns 32 scattered 16-byte accesses per instruction into 8 rows x 64 contiguous bytes.
-    const uint32_t stg = stage_base + ew * 2048;
-    auto sw = [](int row, int chunk) -> uint32_t { return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); };
+    const uint32_t stg = stage_base + ew * Cfg::kEpiBufBytes, rbuf = stg + 2048;
+    auto sw = [](int row, int chunk) -> uint32_t { return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); };   // = TMA SWIZZLE_64B
     const int crow = lane >> 2, cchk = lane & 3;   // coalesced layout: rows crow + 8 i, 16-byte chunk cchk
+    const bool tma_store = p.tma_out >= 1, tma_res = Cfg::kResTma && res_bf16 && p.tma_out >= 2;
+    uint32_t res_phase = 0;
     int it = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -218,12 +235,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       int64_t out_row, res_row;
       map_rows(m, out_row, res_row);
+      int64_t out_row_w, res_row_w;                 // first row of this warp's 32-row slab (TMA paths: the slab is contiguous)
+      map_rows(m_warp, out_row_w, res_row_w);
       int64_t out_row_c[4], res_row_c[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) map_rows(m_warp + crow + 8 * i, out_row_c[i], res_row_c[i]);
       const int nw0 = n_blk * BN + half * kColsPerWarp;      // first column of this warp
+      const bool warp_ok = m_warp < p.M;                     // the slab has at least one real row
       // Work that does not depend on the accumulator is done BEFORE waiting for the MMAs: stage this
-      // warp's bias slice in shared memory and prefetch the first residual chunk.
+      // warp's bias slice in shared memory and start the first residual chunk.
       __syncwarp();
       for (int i = lane; i < kColsPerWarp; i += 32)
         sbias[i] = (p.bias != nullptr && nw0 + i < p.N) ? __ldg(p.bias + nw0 + i) : 0.f;
@@ -231,82 +251,146 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const __nv_bfloat16* Rb = static_cast<const __nv_bfloat16*>(p.R);
       __nv_bfloat16* Cb = static_cast<__nv_bfloat16*>(p.C);
       uint4 rcur[4], rnxt[4];
-      auto load_res = [&](uint4 (&dst)[4], int c) {   // coalesced layout; only full bf16 chunks
+      auto load_res = [&](uint4 (&dst)[4], int c) {   // coalesced layout; only full bf16 chunks (non-TMA residual path)
         const int n = nw0 + c;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          dst[i] = (res_bf16 && n + 32 <= p.N && m_warp + crow + 8 * i < p.M)
+          dst[i] = (res_bf16 && !tma_res && n + 32 <= p.N && m_warp + crow + 8 * i < p.M)
                        ? *reinterpret_cast<const uint4*>(Rb + res_row_c[i] * p.ldr + n + cchk * 8) : make_uint4(0, 0, 0, 0);
       };
-      load_res(rcur, 0);
+      auto tma_res_load = [&](int c) {                // 32 rows x 32 columns of R -> rbuf (rows / columns past the edge arrive as zeros)
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&res_bar[ew], 2048);
+          tma_load_2d_addr(&tmR, &res_bar[ew], rbuf, nw0 + c, static_cast<int>(res_row_w));
+        }
+      };
+      if (tma_res) tma_res_load(0);
+      else load_res(rcur, 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (ew == 0 && lane == 0) VDR_TRACE(3, it);
       // Software pipeline over the 32-column chunks of this warp: the tcgen05.ld of chunk c+1 is issued as soon as
-      // the registers of chunk c have been turned into packed outputs, so its latency hides behind the staging
-      // round trip and the global stores of chunk c.
+      // the registers of chunk c have been turned into packed outputs; the finished chunk leaves through one TMA
+      // store per warp (asynchronous: the only wait is for the staging tile to be reusable one chunk later).
+      // (Issuing the tcgen05.ld of chunk c+1 before the arithmetic of chunk c -- two register buffers -- was measured and
+      //  does not help: while the MMAs of the next tile run, TMEM reads are served slowly and in order across the eight
+      //  warps, so a deeper queue only lengthens each load.)
       uint32_t r[32];
       const uint32_t taddr0 = tmem_base + static_cast<uint32_t>(acc * BN + half * kColsPerWarp) + (static_cast<uint32_t>(quarter * 32) << 16);
       tmem_ld_32x32b_x32(taddr0, r);
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {
         const int col0 = half * kColsPerWarp + c;
-        if (c + 32 < kColsPerWarp) load_res(rnxt, c + 32);   // overlap the next residual chunk with this one
+        if (!tma_res && c + 32 < kColsPerWarp) load_res(rnxt, c + 32);   // overlap the next residual chunk with this one
         const int n0 = n_blk * BN + col0;
         const bool fast = p.c_dtype == VDR_DTYPE_BF16 && n0 + 32 <= p.N;
         uint4 rr[4];
-        if (fast && res_bf16) {   // residual: coalesced registers -> staging tile -> this thread's row
+        if (fast && res_bf16) {
+          if (tma_res) {   // residual tile landed by TMA: this thread's row, then start the next chunk into the same tile
+            mbar_wait(&res_bar[ew], res_phase);
+            res_phase ^= 1u;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(crow + 8 * i, cchk)), "r"(rcur[i].x), "r"(rcur[i].y), "r"(rcur[i].z), "r"(rcur[i].w) : "memory");
-          __syncwarp();
+            for (int g = 0; g < 4; ++g)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[g].x), "=r"(rr[g].y), "=r"(rr[g].z), "=r"(rr[g].w) : "r"(rbuf + sw(lane, g)) : "memory");
+            __syncwarp();
+            if (c + 32 < kColsPerWarp) tma_res_load(c + 32);
+          } else {         // residual: coalesced registers -> staging tile -> this thread's row
+            if (tma_store) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[g].x), "=r"(rr[g].y), "=r"(rr[g].z), "=r"(rr[g].w) : "r"(stg + sw(lane, g)) : "memory");
-          __syncwarp();
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(crow + 8 * i, cchk)), "r"(rcur[i].x), "r"(rcur[i].y), "r"(rcur[i].z), "r"(rcur[i].w) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[g].x), "=r"(rr[g].y), "=r"(rr[g].z), "=r"(rr[g].w) : "r"(stg + sw(lane, g)) : "memory");
+            __syncwarp();
+          }
+        } else if (tma_res) {   // chunk not on the fast path (cannot happen with tma_out == 2: kept for protocol symmetry)
+          mbar_wait(&res_bar[ew], res_phase);
+          res_phase ^= 1u;
+          if (c + 32 < kColsPerWarp) tma_res_load(c + 32);
         }
         tmem_ld_wait();
+        if (ew == 0 && lane == 0 && c <= 32) VDR_TRACE(8 + (c >> 5) * 4, it);
         if (fast) {
           uint4 o[4];
+          uint64_t v2[16];   // the chunk's 32 columns as 16 packed fp32 pairs
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float v[8];
             const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + g * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + g * 8 + 4);
-            v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
-            v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
-            v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
-            v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
-            if (p.epilogue == VDR_EPI_BIAS_GELU) {
+            // bias add on the packed fp32x2 pipe (one issue slot per two columns)
+            v2[g * 4 + 0] = add2(pack2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])), pack2(b0.x, b0.y));
+            v2[g * 4 + 1] = add2(pack2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])), pack2(b0.z, b0.w));
+            v2[g * 4 + 2] = add2(pack2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])), pack2(b1.x, b1.y));
+            v2[g * 4 + 3] = add2(pack2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])), pack2(b1.z, b1.w));
+          }
+          if (p.epilogue == VDR_EPI_BIAS_GELU) {
+            gelu_fast2_x16(v2);   // all 16 pairs step by step: 16 independent dependency chains in flight
+          } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
+            if (res_bf16) {
 #pragma unroll
-              for (int i = 0; i < 8; i += 2) unpack2(gelu_fast2(pack2(v[i], v[i + 1])), v[i], v[i + 1]);
-            } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
-              if (res_bf16) {
+              for (int g = 0; g < 4; ++g) {
                 const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
-                v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
-                v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
-              } else if (row_ok) {   // f32 residual (position embedding: small, cache-resident): row-layout loads
+                v2[g * 4 + 0] = add2(v2[g * 4 + 0], pack2(a0.x, a0.y));
+                v2[g * 4 + 1] = add2(v2[g * 4 + 1], pack2(a1.x, a1.y));
+                v2[g * 4 + 2] = add2(v2[g * 4 + 2], pack2(a2.x, a2.y));
+                v2[g * 4 + 3] = add2(v2[g * 4 + 3], pack2(a3.x, a3.y));
+              }
+            } else if (row_ok) {   // f32 residual (position embedding: small, cache-resident): row-layout loads
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
                 const float* rp = static_cast<const float*>(p.R) + res_row * p.ldr + n0 + g * 8;
                 const float4 a0 = __ldg(reinterpret_cast<const float4*>(rp));
                 const float4 a1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                v2[g * 4 + 0] = add2(v2[g * 4 + 0], pack2(a0.x, a0.y));
+                v2[g * 4 + 1] = add2(v2[g * 4 + 1], pack2(a0.z, a0.w));
+                v2[g * 4 + 2] = add2(v2[g * 4 + 2], pack2(a1.x, a1.y));
+                v2[g * 4 + 3] = add2(v2[g * 4 + 3], pack2(a1.z, a1.w));
               }
             }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
+            unpack2(v2[g * 4 + 0], v[0], v[1]);
+            unpack2(v2[g * 4 + 1], v[2], v[3]);
+            unpack2(v2[g * 4 + 2], v[4], v[5]);
+            unpack2(v2[g * 4 + 3], v[6], v[7]);
             o[g] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           }
           if (c + 32 < kColsPerWarp) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>(c + 32), r);   // next chunk in flight
+          if (ew == 0 && lane == 0 && c <= 32) VDR_TRACE(9 + (c >> 5) * 4, it);
+          if (tma_store) {
+            if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's store has read the staging tile
+            __syncwarp();
+            if (ew == 0 && lane == 0 && c <= 32) VDR_TRACE(10 + (c >> 5) * 4, it);
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(o[g].x), "r"(o[g].y), "r"(o[g].z), "r"(o[g].w) : "memory");
-          __syncwarp();
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(o[g].x), "r"(o[g].y), "r"(o[g].z), "r"(o[g].w) : "memory");
+            fence_proxy_async_smem();                  // generic-proxy writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0 && warp_ok) {
+              tma_store_2d(&tmC, stg, n0, static_cast<int>(out_row_w));   // rows >= out_rows and columns >= N are clipped
+              tma_store_commit();
+            }
+            if (ew == 0 && lane == 0 && c <= 32) VDR_TRACE(11 + (c >> 5) * 4, it);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 q;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stg + sw(crow + 8 * i, cchk)) : "memory");
-            if (m_warp + crow + 8 * i < p.M) *reinterpret_cast<uint4*>(Cb + out_row_c[i] * p.ldc + n0 + cchk * 8) = q;
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(o[g].x), "r"(o[g].y), "r"(o[g].z), "r"(o[g].w) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 q;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stg + sw(crow + 8 * i, cchk)) : "memory");
+              if (m_warp + crow + 8 * i < p.M) *reinterpret_cast<uint4*>(Cb + out_row_c[i] * p.ldc + n0 + cchk * 8) = q;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         } else {
           if (row_ok) {   // f32 output or a ragged last column group: direct element-wise path
 #pragma unroll
@@ -342,12 +426,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (tma_store && lane == 0) tma_store_wait_read<0>();   // the staging tile must outlive its last store
   }
 
   tc_fence_before();
   if constexpr (kCtas == 2) cluster_sync_all();   // the peer may still be credited / read by in-flight pair operations
   else __syncthreads();
-  if (warp == 2) {
+  if (warp == kFirstEpiWarp) {
     tc_fence_after();
     if constexpr (kCtas == 2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
     else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -355,7 +440,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BN, int kCtas>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int grid,
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR, const GemmParams& p, int grid,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kCtas>;
   static bool configured = false;
@@ -377,7 +462,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kCtas>, tmA, tmW, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kCtas>, tmA, tmW, tmC, tmR, p);
   count_launch();
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tcgen05_kernel)");
   VDR_CHECK_LAUNCH("gemm_tcgen05_kernel");
@@ -436,14 +521,35 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   p.trace = g_trace;
   p.dbg = getenv("VDR_GEMM_DBG") ? atoi(getenv("VDR_GEMM_DBG")) : 0;
 
+  // bf16 outputs leave through per-warp TMA stores of 32 x 32 tiles (SWIZZLE_64B staging) when every warp's 32-row slab
+  // maps to 32 consecutive output rows; a bf16 residual without row remapping then arrives the same way.
+  static const bool no_tma_out = getenv("VDR_GEMM_NO_TMA_OUT") != nullptr;
+  CUtensorMap tmC, tmR;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmR, 0, sizeof(tmR));
+  p.tma_out = 0;
+  p.out_rows = a->M;
+  if (a->out_group > 0) p.out_rows = (int64_t)((a->M + a->out_group - 1) / a->out_group - 1) * a->out_group_stride + a->out_offset + a->out_group;
+  const bool slab_ok = a->out_group == 0 || (a->out_group % 32 == 0 && a->M % 32 == 0);
+  if (!no_tma_out && a->c_dtype == VDR_DTYPE_BF16 && slab_ok && p.out_rows < 0x7fffffffLL) {
+    rc = make_tmap_2d_bf16(&tmC, a->C, (uint64_t)p.out_rows, (uint64_t)a->N, (uint64_t)a->ldc, 32, 32, 64);
+    if (rc != VDR_OK) return rc;
+    p.tma_out = 1;
+    if (a->epilogue == VDR_EPI_BIAS_RESIDUAL && a->r_dtype == VDR_DTYPE_BF16 && a->res_mod == 0 && (pair || bn != 256)) {
+      rc = make_tmap_2d_bf16(&tmR, a->R, (uint64_t)p.out_rows, (uint64_t)a->N, (uint64_t)a->ldr, 32, 32, 64);
+      if (rc != VDR_OK) return rc;
+      p.tma_out = 2;
+    }
+  }
+
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pair) {
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
-    return launch_gemm<256, 2>(tmA, tmW, p, 2 * pairs, s);
+    return launch_gemm<256, 2>(tmA, tmW, tmC, tmR, p, 2 * pairs, s);
   }
   const int total = tiles(bn);
   const int grid = total < sms ? total : sms;
-  if (bn == 256) return launch_gemm<256, 1>(tmA, tmW, p, grid, s);
-  if (bn == 128) return launch_gemm<128, 1>(tmA, tmW, p, grid, s);
-  return launch_gemm<64, 1>(tmA, tmW, p, grid, s);
+  if (bn == 256) return launch_gemm<256, 1>(tmA, tmW, tmC, tmR, p, grid, s);
+  if (bn == 128) return launch_gemm<128, 1>(tmA, tmW, tmC, tmR, p, grid, s);
+  return launch_gemm<64, 1>(tmA, tmW, tmC, tmR, p, grid, s);
 }

@@ -58,7 +58,7 @@ static encode_tiled_fn get_encode() {
 }
 
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                      uint32_t box_rows, uint32_t box_cols) {
+                      uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   encode_tiled_fn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -69,7 +69,7 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu ld=%llu box=%ux%u ptr=%p", (int)r,
