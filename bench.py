@@ -230,8 +230,43 @@ def run_ours(args):
         t[0] += 1
         t[1] += a.elapsed_time(b)
         t[2] += fl
-    per_kernel = {k: {"launches": v[0], "ms_per_launch": v[1] / v[0], "tflops": v[2] / (v[1] / 1e3) / 1e12}
-                  for k, v in sorted(by_label.items(), key=lambda kv: -kv[1][1])}
+    kinds = {label: kind for (kind, fl, a, b, label) in prof}
+    per_kernel = {}
+    for k, v in sorted(by_label.items(), key=lambda kv: -kv[1][1]):
+        e = {"launches": v[0], "ms_per_launch": v[1] / v[0]}
+        if kinds[k] == "ln":      # HBM-bound: algorithmic bytes / time
+            e["gbs"] = v[2] / (v[1] / 1e3) / 1e9
+        else:
+            e["tflops"] = v[2] / (v[1] / 1e3) / 1e12
+        per_kernel[k] = e
+
+    # The HBM-bound kernels of the path, timed alone (CUDA events, 10 launches each after 3 warm-ups):
+    #   mask gather of this volume (C2: 5 k tokens out of a 14 k-candidate ROI -> launch / host-latency bound, reported as is)
+    #   and of a dense mask over the whole token grid (every token selected: the bandwidth of the compaction + emit kernels);
+    #   algorithmic bytes per SURVEY 8d: S*h*w mask bytes + n_sel * (D*4 read + D*4 written + 12).
+    def time_gather(mask_dev, roi, reps=10):
+        tok = model._workspace(S)["OUT"]
+        froi, mroi = (plan["feat_roi"], plan["mask_roi"]) if roi else (None, None)
+        call = lambda: ops.mask_gather(tok, mask_dev, grid=(S, gh, gw, model.n_tokens, 1), feat_roi=froi,  # noqa: E731
+                                       mask_roi=mroi, pe=pe)
+        for _ in range(3):
+            out_g = call()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(reps):
+            out_g = call()
+        g1.record()
+        torch.cuda.synchronize()
+        n_sel = int(out_g[2].item())
+        r0, r1, c0, c1 = plan["feat_roi"] if roi else (0, gh, 0, gw)
+        cand = S * (r1 - r0) * (c1 - c0)
+        nbytes = cand + n_sel * (model.cfg["dim"] * 8 + 12)
+        ms_g = g0.elapsed_time(g1) / reps
+        return {"ms": ms_g, "selected": n_sel, "candidates": cand, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms_g / 1e3) / 1e9}
+
+    gather_c2 = time_gather(mask_s, roi=True)                        # the workload's own gather (ROI of the tumour, ~35 % selected)
+    gather_dense = time_gather(torch.ones_like(mask_s), roi=False)   # whole 32x32xS grid, every token selected
 
     run_e2e(2)
     ms_e, out_e, _ = timed(lambda: run_e2e(args.steps), 1)
@@ -269,7 +304,9 @@ def run_ours(args):
                      "share_of_step": gemm_ms / ms_p if ms_p else None,
                      "attention": {"achieved": attn_fl / (attn_ms / 1e3) / 1e12 if attn_ms else None,
                                    "share_of_step": attn_ms / ms_p if ms_p else None},
-                     "per_kernel": per_kernel},
+                     "per_kernel": per_kernel,
+                     "hbm_kernels": {"peak_gbs": peaks["hbm"], "mask_gather_c2": gather_c2, "mask_gather_dense": gather_dense,
+                                     "mask_gather_dense_frac": gather_dense["gbs"] / peaks["hbm"] if peaks["hbm"] else None}},
         "cpu_baseline": cb,
         "clocks": clocks}))
 

@@ -52,6 +52,26 @@ def test_g1_roi_and_token_matrix_layout(cuda):
     assert np.allclose(t[:n].cpu().numpy(), o["tokens"].astype(np.float32), rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("D,gh,gw", [(48, 6, 7), (768, 5, 9), (96, 8, 8)])
+def test_g1_pe_table_vector_path(cuda, D, gh, gw):
+    """D % 24 == 0 takes the vectorised emit path (four 16-byte loads from the per-coordinate f64 PE table per 8 columns);
+    non-square grids exercise the reference's xy-meshgrid quirk in the table row selection."""
+    from oracle import gather_np as G
+    from vit_deep_radiomics_b200 import ops
+    rng = np.random.default_rng(100 + D)
+    S, HM, WM = 7, 40, 56
+    feats = rng.standard_normal((S, gh, gw, D)).astype(np.float32)
+    masks = rng.random((S, HM, WM)) < 0.35
+    res, noise = (0.8, 0.7, 1.25), (1.5, -2.0, 0.25)
+    o = G.token_gather(list(feats), list(masks), res, noise)
+    t, src, cnt = ops.mask_gather(torch.from_numpy(feats).to(cuda), torch.from_numpy(masks.astype(np.uint8)).to(cuda),
+                                  pe=dict(res=res, noise=noise))
+    n = int(cnt.item())
+    assert n == o["flat"].size and np.array_equal(src[:n].cpu().numpy(), o["src"])
+    want = o["tokens"].astype(np.float32)
+    assert np.allclose(t[:n].cpu().numpy(), want, rtol=0, atol=2.5e-7 * max(1.0, np.abs(want).max()))
+
+
 def test_g1_cap_and_bf16(cuda):
     from vit_deep_radiomics_b200 import ops
     rng = np.random.default_rng(9)

@@ -19,7 +19,7 @@ for k in gemm attn ln gather; do
   pat=$k; skip=0; cnt=12
   case $k in
     gemm) pat='regex:gemm_tcgen05'; skip=8; cnt=4;;
-    attn) pat='regex:flash_attn|attn_tail'; skip=4; cnt=2;;
+    attn) pat='regex:flash_attn'; skip=2; cnt=1;;
     ln) pat='regex:layernorm'; skip=2; cnt=1;;
     gather) pat='regex:g1_'; skip=16; cnt=8;;
   esac

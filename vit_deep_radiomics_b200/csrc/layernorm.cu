@@ -65,28 +65,56 @@ __device__ __forceinline__ void ln_row(float (&x)[MAXC][8], int chunks, int lane
   rstd_out = rstd;
 }
 
+// Forward: gamma / beta are staged in shared memory once per block (re-reading them from L1 per row cost twice the
+// payload in load traffic), each warp keeps the NEXT row's raw 16-byte vectors in flight while it reduces the current
+// one (the kernel is HBM-bound: what matters is bytes in flight per SM), stores bypass L1.
 template <int MAXC, bool OUT_F32>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, void* __restrict__ y, int64_t ldy,
                      float* __restrict__ mean, float* __restrict__ rstd, int rows, int d, float eps) {
+  extern __shared__ __align__(16) float s_gb[];   // gamma[d] | beta[d]
+  for (int i = threadIdx.x; i < d; i += kLnWarps * 32) {
+    s_gb[i] = gamma[i];
+    s_gb[d + i] = beta[i];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int chunks = d >> 3;
-  for (int64_t row = blockIdx.x * (int64_t)kLnWarps + (threadIdx.x >> 5); row < rows;
-       row += (int64_t)gridDim.x * kLnWarps) {
-    float v[MAXC][8];
-    const __nv_bfloat16* xr = x + row * ldx;
+  const int64_t stride = (int64_t)gridDim.x * kLnWarps;
+  int64_t row = blockIdx.x * (int64_t)kLnWarps + (threadIdx.x >> 5);
+  uint4 nxt[MAXC];
+  auto fetch = [&](int64_t r) {
+    const __nv_bfloat16* xr = x + r * ldx;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
-      if (lane + c * 32 < chunks) load8_bf16(xr + (lane + c * 32) * 8, v[c]);
+      if (lane + c * 32 < chunks) nxt[c] = __ldcs(reinterpret_cast<const uint4*>(xr + (lane + c * 32) * 8));
+  };
+  if (row < rows) fetch(row);
+  for (; row < rows; row += stride) {
+    float v[MAXC][8];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const float2 p0 = unpack_bf16x2(nxt[c].x), p1 = unpack_bf16x2(nxt[c].y), p2 = unpack_bf16x2(nxt[c].z), p3 = unpack_bf16x2(nxt[c].w);
+      v[c][0] = p0.x; v[c][1] = p0.y; v[c][2] = p1.x; v[c][3] = p1.y; v[c][4] = p2.x; v[c][5] = p2.y; v[c][6] = p3.x; v[c][7] = p3.y;
+    }
+    if (row + stride < rows) fetch(row + stride);
     float mu, rs;
-    ln_row<MAXC>(v, chunks, lane, d, eps, gamma, beta, mu, rs);
+    ln_row<MAXC>(v, chunks, lane, d, eps, s_gb, s_gb + d, mu, rs);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
       if (lane + c * 32 < chunks) {
         const int col = (lane + c * 32) * 8;
-        if (OUT_F32) store8_f32(static_cast<float*>(y) + row * ldy + col, v[c]);
-        else store8_bf16(static_cast<__nv_bfloat16*>(y) + row * ldy + col, v[c]);
+        if (OUT_F32) {
+          float* yp = static_cast<float*>(y) + row * ldy + col;
+          __stcs(reinterpret_cast<float4*>(yp), make_float4(v[c][0], v[c][1], v[c][2], v[c][3]));
+          __stcs(reinterpret_cast<float4*>(yp + 4), make_float4(v[c][4], v[c][5], v[c][6], v[c][7]));
+        } else {
+          uint4 o;
+          o.x = pack_bf16x2(v[c][0], v[c][1]); o.y = pack_bf16x2(v[c][2], v[c][3]);
+          o.z = pack_bf16x2(v[c][4], v[c][5]); o.w = pack_bf16x2(v[c][6], v[c][7]);
+          __stcs(reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + row * ldy + col), o);
+        }
       }
     if (lane == 0) {
       if (mean) mean[row] = mu;
@@ -219,12 +247,16 @@ extern "C" int vdr_layernorm_fwd(const void* x, int64_t ldx, const float* gamma,
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = ln_grid(rows);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  const size_t smem = (size_t)2 * d * sizeof(float);
 #define VDR_LN_LAUNCH(MAXC)                                                                                   \
   if (y_dtype == VDR_DTYPE_F32)                                                                               \
-    layernorm_fwd_kernel<MAXC, true><<<grid, kLnWarps * 32, 0, s>>>(xb, ldx, gamma, beta, y, ldy, mean, rstd, rows, d, eps); \
+    layernorm_fwd_kernel<MAXC, true><<<grid, kLnWarps * 32, smem, s>>>(xb, ldx, gamma, beta, y, ldy, mean, rstd, rows, d, eps); \
   else                                                                                                        \
-    layernorm_fwd_kernel<MAXC, false><<<grid, kLnWarps * 32, 0, s>>>(xb, ldx, gamma, beta, y, ldy, mean, rstd, rows, d, eps);
+    layernorm_fwd_kernel<MAXC, false><<<grid, kLnWarps * 32, smem, s>>>(xb, ldx, gamma, beta, y, ldy, mean, rstd, rows, d, eps);
+  // chunks of 8 columns per lane: exact for the backbone widths (384 -> 2, 768 -> 3, 1024 -> 4), generic otherwise
   if (d <= 256) { VDR_LN_LAUNCH(1) }
+  else if (d <= 512) { VDR_LN_LAUNCH(2) }
+  else if (d <= 768) { VDR_LN_LAUNCH(3) }
   else if (d <= 1024) { VDR_LN_LAUNCH(4) }
   else { VDR_LN_LAUNCH(16) }
 #undef VDR_LN_LAUNCH

@@ -143,11 +143,13 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     if save_stats:
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-    _C.check(_C.lib().vdr_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
-                                        out.data_ptr(), out.stride(0), _DT[out.dtype],
-                                        mean.data_ptr() if save_stats else None,
-                                        rstd.data_ptr() if save_stats else None,
-                                        rows, d, float(eps), _stream()), "vdr_layernorm_fwd")
+    # algorithmic bytes: read the row once, write it once
+    with _Prof("ln", float(rows * d * (2 + out.element_size())), f"layernorm rows{rows} d{d} -> {str(out.dtype).split('.')[-1]}"):
+        _C.check(_C.lib().vdr_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                            out.data_ptr(), out.stride(0), _DT[out.dtype],
+                                            mean.data_ptr() if save_stats else None,
+                                            rstd.data_ptr() if save_stats else None,
+                                            rows, d, float(eps), _stream()), "vdr_layernorm_fwd")
     return (out, mean, rstd) if save_stats else out
 
 
@@ -221,9 +223,22 @@ def _pe_div(D: int, device, scale=10000) -> torch.Tensor:
     return _PE_DIV_CACHE[key]
 
 
+_GRID_MEANS_CACHE: dict = {}
+
+
 def grid_means(h: int, w: int, S: int, h_orig: int, w_orig: int, res) -> tuple:
     """Means of the reference's physical grid coordinates over ALL h*w*S grid points
-    (src/train_models.py:166-176), reproducing numpy's summation so the result is bit-identical."""
+    (src/train_models.py:166-176), reproducing numpy's summation so the result is bit-identical.
+    Depends on the geometry only: cached (it is a host pass over every grid point)."""
+    key = (h, w, S, h_orig, w_orig, tuple(float(r) for r in res))
+    if key not in _GRID_MEANS_CACHE:
+        if len(_GRID_MEANS_CACHE) > 256:
+            _GRID_MEANS_CACHE.clear()
+        _GRID_MEANS_CACHE[key] = _grid_means(h, w, S, h_orig, w_orig, res)
+    return _GRID_MEANS_CACHE[key]
+
+
+def _grid_means(h: int, w: int, S: int, h_orig: int, w_orig: int, res) -> tuple:
     n = np.arange(h * w * S, dtype=np.int64)
     x = ((n // S) % h / w) * w_orig * res[0]
     y = ((n // (h * S)) / h) * h_orig * res[1]
