@@ -53,26 +53,28 @@ struct GemmParams {
 // M = 256 tcgen05.mma that reads both halves, and each CTA's TMEM receives its 128 accumulator rows.  This halves
 // the B-operand shared-memory traffic, which bounds the single-CTA kernel (TMA writes + UMMA reads ~ 96 KB per
 // 512-cycle K block against 128 B/clk of shared-memory bandwidth).
-template <int BN, int kCtas>
+template <int BN, int kCtas, bool kRes>
 struct GemmCfg {
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = (BN / kCtas) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (kCtas == 2) ? 5 : ((BN == 256) ? 4 : (BN == 128 ? 5 : 7));   // what fits 227 KB next to the epilogue tiles
+  // kRes = the instantiation that can take a TMA-loaded bf16 residual (2 KB more per epilogue warp): the stage count is what
+  // fits 227 KB next to the epilogue tiles -- the bias / GELU instantiation of the CTA-pair kernel keeps a sixth stage.
+  static constexpr int kStages = (kCtas == 2) ? (kRes ? 5 : 6) : ((BN == 256) ? 4 : (BN == 128 ? (kRes ? 5 : 6) : (kRes ? 7 : 8)));
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   // per epilogue warp: a 2 KB store tile (+ a 2 KB TMA-loaded residual tile; the single-CTA 128 x 256 configuration has no
   // room for it next to four 48 KB stages and keeps the register-staged residual path)
-  static constexpr bool kResTma = !(BN == 256 && kCtas == 1);
+  static constexpr bool kResTma = kRes && !(BN == 256 && kCtas == 1);
   static constexpr int kEpiBufBytes = kResTma ? 4096 : 2048;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiBufBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 * 4 /*bias staging*/;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
-template <int BN, int kCtas>
+template <int BN, int kCtas, bool kRes>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-  using Cfg = GemmCfg<BN, kCtas>;
+  using Cfg = GemmCfg<BN, kCtas, kRes>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -439,13 +441,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int kCtas>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR, const GemmParams& p, int grid,
+template <int BN, int kCtas, bool kRes>
+static int launch_gemm_(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR, const GemmParams& p, int grid,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, kCtas>;
+  using Cfg = GemmCfg<BN, kCtas, kRes>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kCtas, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
@@ -462,11 +464,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kCtas>, tmA, tmW, tmC, tmR, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kCtas, kRes>, tmA, tmW, tmC, tmR, p);
   count_launch();
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tcgen05_kernel)");
   VDR_CHECK_LAUNCH("gemm_tcgen05_kernel");
   return VDR_OK;
+}
+
+template <int BN, int kCtas>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  if (p.tma_out >= 2) return launch_gemm_<BN, kCtas, true>(tmA, tmW, tmC, tmR, p, grid, stream);
+  return launch_gemm_<BN, kCtas, false>(tmA, tmW, tmC, tmR, p, grid, stream);
 }
 
 }  // namespace vdr
