@@ -95,6 +95,19 @@ int vdr_volume_to_slices(const float* vol, int H, int W, int S, int y0, int x0, 
 int vdr_im2col_gray_bf16(const void* slices_bf16, int B, int H, int W, int patch, void* A_bf16,
                          vdr_stream_t stream);
 
+/* Patch embedding as ONE TMA-fed im2col GEMM (K1: Conv2d(3, d, p, p) + position embedding of the backbone the reference
+ * calls at tfds_dense_descriptor.py:123): the A operand is never materialised -- a 5-D tensor map (ix, iy, px, py, image)
+ * over the bf16 pictures delivers each 128-patch x 64-k tile of the im2col matrix straight into the swizzled shared-memory
+ * layout tcgen05.mma reads.  images (B*C, H, W) bf16, C = 1 (gray picture reused for the 3 input channels, gray2rgb :41) or 3;
+ * Wpe (d, 3*p*p) bf16 K-major with k = (c, iy, ix) = the conv weight as stored in the checkpoint; pos (N, d) f32 with
+ * N = patches + 1 (row 0 belongs to the CLS token); writes X[b*N + 1 + patch, :] = patch . Wpe^T + bias + pos[1 + patch] (bf16).
+ * vdr_patch_embed_supported: 1 when the geometry tiles into TMA boxes (p == 16, 128 % (W/p) == 0, patches % 128 == 0:
+ * 16-pixel patches on 256 / 512 / 1024 / 2048-wide pictures); otherwise use vdr_im2col_* + vdr_gemm. */
+int vdr_patch_embed_supported(int H, int W, int patch);
+int vdr_patch_embed_gemm(const void* images_bf16, int B, int C, int H, int W, int patch, const void* Wpe_bf16,
+                         int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d,
+                         vdr_stream_t stream);
+
 /* CLS rows of the token matrix: X[b*N + 0, :] = cls[:] + pos[0, :]   (f32 params -> bf16 tokens) */
 int vdr_write_cls_rows(const float* cls, const float* pos0, void* X_bf16, int B, int N, int d,
                        vdr_stream_t stream);

@@ -144,3 +144,44 @@ def test_volume_staging_and_gray_im2col(cuda):
         ref = ref.transpose(1, 2).reshape(-1, 3 * p * p)
         K = 3 * p * p
         assert torch.equal(A[:, :K].float(), ref.bfloat16().float()) and (A[:, K:] == 0).all()
+
+
+@pytest.mark.parametrize("B,C,H,W,d", [(3, 1, 512, 512, 768), (40, 1, 512, 512, 768), (2, 3, 256, 256, 384), (1, 1, 128, 1024, 128)])
+def test_patch_embed_tma_im2col_matches_materialised_path(cuda, B, C, H, W, d):
+    """vdr_patch_embed_gemm (5-D TMA im2col view, no A matrix) == vdr_im2col_patches + vdr_gemm: same K order, same
+    accumulation order -> bit-identical bf16 tokens; CLS rows are left untouched."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(3)
+    p = 16
+    assert ops.patch_embed_supported(H, W, p)
+    imgs = torch.rand((B, H, W) if C == 1 else (B, 3, H, W), device=cuda).bfloat16()
+    gh, gw = H // p, W // p
+    Np, N, K = gh * gw, gh * gw + 1, 3 * p * p
+    w_pe = (torch.randn(d, K, device=cuda) * 0.05).bfloat16()
+    bias, pos = torch.randn(d, device=cuda), torch.randn(N, d, device=cuda)
+    x_ref = torch.full((B * N, d), 7.0, device=cuda, dtype=torch.bfloat16)
+    src = imgs.float()
+    strides = (src.stride(0), 0, src.stride(1), src.stride(2)) if C == 1 else src.stride()
+    A = torch.empty(B * Np, K, device=cuda, dtype=torch.bfloat16)
+    ops.im2col_patches(src, strides, B, H, W, p, out=A)
+    ops.gemm(A, w_pe, bias, epilogue="residual", residual=pos, out=x_ref, k=K, out_group=(Np, N, 1), res_mod=(Np, 1))
+    x = torch.full((B * N, d), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.patch_embed(imgs, w_pe, bias, pos, p, out=x)
+    assert torch.equal(x, x_ref)
+    assert torch.all(x.view(B, N, d)[:, 0] == 7.0)
+    # against plain fp32 arithmetic (tolerance of bf16 operands / outputs)
+    patches = src.reshape(B, -1, gh, p, gw, p) if C == 3 else src[:, None].expand(-1, 3, -1, -1).reshape(B, 3, gh, p, gw, p)
+    a32 = patches.permute(0, 2, 4, 1, 3, 5).reshape(B * Np, K)
+    want = a32 @ w_pe.float().t() + bias + pos[1:].repeat(B, 1)
+    got = x.view(B, N, d)[:, 1:].reshape(B * Np, d).float()
+    assert (got - want).abs().max() <= 0.02 * want.abs().max()
+
+
+def test_patch_embed_unsupported_geometry_is_rejected(cuda):
+    from vit_deep_radiomics_b200 import ops
+    assert not ops.patch_embed_supported(224, 224, 16)      # 14 patches per row do not tile a 128-row box
+    assert not ops.patch_embed_supported(518, 518, 14)
+    imgs = torch.zeros(1, 224, 224, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.patch_embed(imgs, torch.zeros(64, 768, device=cuda, dtype=torch.bfloat16), torch.zeros(64, device=cuda),
+                        torch.zeros(197, 64, device=cuda), 16, out=torch.zeros(197, 64, device=cuda, dtype=torch.bfloat16))

@@ -21,6 +21,10 @@ int  num_sms();
 int  make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
                        uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
+// Rank-N (<= 5) bf16 tensor map: dims / box innermost first, strides_bytes for dims 1..rank-1.
+int  make_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, int swizzle_bytes = 128);
+
 #define VDR_CHECK_ARG(cond, code, ...)                 \
   do {                                                 \
     if (!(cond)) {                                     \
@@ -127,6 +131,14 @@ __device__ __forceinline__ void tma_load_2d_addr(const CUtensorMap* map, uint64_
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// 5-D tile load (the im2col view of the patch embedding: ix, iy, px, py, image)
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 
@@ -251,6 +263,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols) : "memory");
@@ -291,6 +309,17 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// K-major operand with 32-byte rows (16 bf16 = one MMA K step per row), 32-byte swizzle, 8-row groups 256 B apart:
+// what a SWIZZLE_32B TMA box with a 16-element inner dimension writes (the im2col view of the patch embedding).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
   return d;
 }
 // Instruction descriptor, kind::f16: bf16 A/B, f32 D.

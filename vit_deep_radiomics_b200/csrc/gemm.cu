@@ -42,6 +42,10 @@ struct GemmParams {
   int epilogue, r_dtype, c_dtype;
   int out_group, out_group_stride, out_offset;
   int res_mod, res_offset;
+  // A operand as an im2col VIEW of (images, H, W) bf16 pictures (patch embedding, 16-pixel patches): tmA is then a 5-D tensor
+  // map (ix, px, py, iy, image), SWIZZLE_32B, and a K block of a 128-patch tile lands as four [128 patches][16 ix] sub-tiles with
+  // 32-byte rows, one per pixel row iy = one per MMA K step (a SWIZZLE_128B box with a 32-byte inner dimension faults on sm_100a)
+  int a_im2col, ic_patch, ic_gw, ic_np, ic_chan, ic_kb_per_chan;
   int tma_out;                 // 1: bf16 output tiles leave through TMA stores (tmC); 2: ... and the bf16 residual arrives through TMA loads (tmR)
   int64_t out_rows;            // rows of the output matrix (TMA clipping bound)
   unsigned long long* trace;   // debug: per-tile timestamps of CTA 0 (nullptr = off)
@@ -148,12 +152,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
             } else {
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * 2);
-              tma_load_2d_2sm(&tmA, lead_bar, sa, kb * BK, m_blk * kTileM + static_cast<int>(cta_rank) * BM);
+              if (p.a_im2col) {
+                const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * BM, img = m0 / p.ic_np, py0 = (m0 % p.ic_np) / p.ic_gw;
+                const int c = kb / p.ic_kb_per_chan, iy0 = (kb % p.ic_kb_per_chan) * (BK / p.ic_patch);
+                tma_load_5d_2sm(&tmA, lead_bar, sa, 0, 0, py0, iy0, img * p.ic_chan + (p.ic_chan > 1 ? c : 0));
+              } else {
+                tma_load_2d_2sm(&tmA, lead_bar, sa, kb * BK, m_blk * kTileM + static_cast<int>(cta_rank) * BM);
+              }
               tma_load_2d_2sm(&tmW, lead_bar, sa + Cfg::kStageBytesA, kb * BK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
+            if (p.a_im2col) {
+              const int m0 = m_blk * BM, img = m0 / p.ic_np, py0 = (m0 % p.ic_np) / p.ic_gw;
+              const int c = kb / p.ic_kb_per_chan, iy0 = (kb % p.ic_kb_per_chan) * (BK / p.ic_patch);
+              tma_load_5d(&tmA, &full_bar[stage], sa, 0, 0, py0, iy0, img * p.ic_chan + (p.ic_chan > 1 ? c : 0));
+            } else {
+              tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
+            }
             tma_load_2d(&tmW, &full_bar[stage], sa + Cfg::kStageBytesA, kb * BK, n_blk * BN);
           }
           if (kb == 0) VDR_TRACE(5, it);
@@ -181,16 +197,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           if (kb == 0) VDR_TRACE(1, it);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
-          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          // A: +32 bytes per K step inside the 128-byte swizzle row (encoded address units of 16 B); in im2col mode the K
+          // steps are the four [128][16] sub-tiles (32-byte rows, SWIZZLE_32B), 4 KB = 256 address units apart
+          const uint64_t da = p.a_im2col ? umma_desc_kmajor_sw32(sa) : umma_desc_kmajor_sw128(sa);
+          const uint64_t da_step = p.a_im2col ? 256u : 2u;
           const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             if (p.dbg == 1) break;
-            // +32 bytes per K step inside the 128-byte swizzle row  (encoded address units of 16 B)
             if constexpr (kCtas == 2)
-              umma_ss_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss_2sm(d_tmem, da + da_step * k, db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
             else
-              umma_ss(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss(d_tmem, da + da_step * k, db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // smem slot free once these MMAs have read it (pair: in both CTAs)
           if constexpr (kCtas == 2) umma_commit_2sm(&empty_bar[stage], 3);
@@ -484,14 +502,21 @@ static unsigned long long* g_trace = nullptr;
 // debug hook (not part of the drop-in surface): device buffer of 64*8 u64 receiving CTA 0's per-tile timestamps
 extern "C" void vdr_debug_set_gemm_trace(void* device_buf) { g_trace = static_cast<unsigned long long*>(device_buf); }
 
-extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
+namespace {
+struct Im2colSpec {   // A = im2col view of `images` pictures (H, W) bf16 with `chan` channel planes each (1 = gray, reused for all 3)
+  const void* src;
+  int images, chan, H, W, patch;
+};
+}  // namespace
+
+static int gemm_impl(const vdr_gemm_args* a, const Im2colSpec* ic, vdr_stream_t stream) {
   using namespace vdr;
   VDR_CHECK_ARG(a != nullptr, VDR_EINVAL, "vdr_gemm: null args");
-  VDR_CHECK_ARG(a->A && a->W && a->C, VDR_EINVAL, "vdr_gemm: null A/W/C");
+  VDR_CHECK_ARG((a->A || ic) && a->W && a->C, VDR_EINVAL, "vdr_gemm: null A/W/C");
   VDR_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, VDR_EINVAL, "vdr_gemm: non-positive shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  VDR_CHECK_ARG(a->lda >= a->K && a->ldw >= a->K && a->ldc >= a->N, VDR_EINVAL, "vdr_gemm: leading dimension smaller than row length");
-  VDR_CHECK_ARG(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldc % 8 == 0, VDR_EALIGN, "vdr_gemm: lda/ldw/ldc must be multiples of 8 elements");
-  VDR_CHECK_ARG(aligned16(a->A) && aligned16(a->W) && aligned16(a->C), VDR_EALIGN, "vdr_gemm: A/W/C must be 16-byte aligned");
+  VDR_CHECK_ARG((ic || a->lda >= a->K) && a->ldw >= a->K && a->ldc >= a->N, VDR_EINVAL, "vdr_gemm: leading dimension smaller than row length");
+  VDR_CHECK_ARG((ic || a->lda % 8 == 0) && a->ldw % 8 == 0 && a->ldc % 8 == 0, VDR_EALIGN, "vdr_gemm: lda/ldw/ldc must be multiples of 8 elements");
+  VDR_CHECK_ARG((ic || aligned16(a->A)) && aligned16(a->W) && aligned16(a->C), VDR_EALIGN, "vdr_gemm: A/W/C must be 16-byte aligned");
   VDR_CHECK_ARG(a->bias == nullptr || aligned16(a->bias), VDR_EALIGN, "vdr_gemm: bias must be 16-byte aligned");
   // N itself may be ragged (last column group handled element-wise); rows must still start 16-byte aligned.
   VDR_CHECK_ARG(a->epilogue >= VDR_EPI_BIAS && a->epilogue <= VDR_EPI_BIAS_RESIDUAL, VDR_EINVAL, "vdr_gemm: unknown epilogue %d", a->epilogue);
@@ -516,7 +541,17 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   const bool pair = !force_1cta && bn == 256 && pair_tiles >= sms / 2;
 
   CUtensorMap tmA, tmW;
-  int rc = make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM, BK);
+  int rc;
+  if (ic) {
+    const int gw = ic->W / ic->patch, gh = ic->H / ic->patch;
+    // (ix, px, py, iy, image): the box lands as [iy][py][px][ix] = one [128 patches][16 ix] sub-tile per pixel row
+    const uint64_t dims[5] = {(uint64_t)ic->patch, (uint64_t)gw, (uint64_t)gh, (uint64_t)ic->patch, (uint64_t)ic->images * ic->chan};
+    const uint64_t strides[4] = {(uint64_t)ic->patch * 2, (uint64_t)ic->patch * ic->W * 2, (uint64_t)ic->W * 2, (uint64_t)ic->H * ic->W * 2};
+    const uint32_t box[5] = {(uint32_t)ic->patch, (uint32_t)gw, (uint32_t)(BM / gw), (uint32_t)(BK / ic->patch), 1};
+    rc = make_tmap_nd_bf16(&tmA, ic->src, 5, dims, strides, box, 32);
+  } else {
+    rc = make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM, BK);
+  }
   if (rc != VDR_OK) return rc;
   rc = make_tmap_2d_bf16(&tmW, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, (uint32_t)(pair ? bn / 2 : bn), BK);
   if (rc != VDR_OK) return rc;
@@ -529,6 +564,15 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   p.res_mod = a->res_mod; p.res_offset = a->res_offset;
   p.trace = g_trace;
   p.dbg = getenv("VDR_GEMM_DBG") ? atoi(getenv("VDR_GEMM_DBG")) : 0;
+  p.a_im2col = ic ? 1 : 0;
+  p.ic_patch = p.ic_gw = p.ic_np = p.ic_chan = p.ic_kb_per_chan = 1;
+  if (ic) {
+    p.ic_patch = ic->patch;
+    p.ic_gw = ic->W / ic->patch;
+    p.ic_np = (ic->H / ic->patch) * p.ic_gw;
+    p.ic_chan = ic->chan;
+    p.ic_kb_per_chan = ic->patch * ic->patch / BK;
+  }
 
   // bf16 outputs leave through per-warp TMA stores of 32 x 32 tiles (SWIZZLE_64B staging) when every warp's 32-row slab
   // maps to 32 consecutive output rows; a bf16 residual without row remapping then arrives the same way.
@@ -561,4 +605,39 @@ extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) {
   if (bn == 256) return launch_gemm<256, 1>(tmA, tmW, tmC, tmR, p, grid, s);
   if (bn == 128) return launch_gemm<128, 1>(tmA, tmW, tmC, tmR, p, grid, s);
   return launch_gemm<64, 1>(tmA, tmW, tmC, tmR, p, grid, s);
+}
+
+extern "C" int vdr_gemm(const vdr_gemm_args* a, vdr_stream_t stream) { return gemm_impl(a, nullptr, stream); }
+
+extern "C" int vdr_patch_embed_supported(int H, int W, int patch) {
+  if (patch <= 0 || H <= 0 || W <= 0 || H % patch || W % patch) return 0;
+  const int gw = W / patch, np = (H / patch) * gw;
+  // one pixel row of a patch = one 16-wide MMA K step (32-byte TMA rows), 128-row tiles made of whole patch rows of one image
+  return (patch == 16 && W % 8 == 0 && gw <= 128 && 128 % gw == 0 && np % 128 == 0) ? 1 : 0;
+}
+
+extern "C" int vdr_patch_embed_gemm(const void* images_bf16, int B, int C, int H, int W, int patch, const void* Wpe_bf16,
+                                    int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d,
+                                    vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(images_bf16 && Wpe_bf16 && pos && X_bf16, VDR_EINVAL, "vdr_patch_embed_gemm: null pointer");
+  VDR_CHECK_ARG(B > 0 && (C == 1 || C == 3) && d > 0, VDR_EINVAL, "vdr_patch_embed_gemm: bad shape B=%d C=%d d=%d", B, C, d);
+  VDR_CHECK_ARG(vdr_patch_embed_supported(H, W, patch), VDR_EINVAL,
+                "vdr_patch_embed_gemm: %dx%d images with %d-pixel patches do not tile into TMA im2col boxes (use vdr_im2col_* + vdr_gemm)", H, W, patch);
+  VDR_CHECK_ARG(aligned16(images_bf16), VDR_EALIGN, "vdr_patch_embed_gemm: images must be 16-byte aligned");
+  const int np = (H / patch) * (W / patch);
+  VDR_CHECK_ARG((int64_t)B * np < 0x7fffffffLL, VDR_EINVAL, "vdr_patch_embed_gemm: too many patches");
+  vdr_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = nullptr; a.lda = 0;
+  a.W = Wpe_bf16; a.ldw = ldw;
+  a.bias = bias;
+  a.R = pos; a.ldr = d; a.r_dtype = VDR_DTYPE_F32;
+  a.C = X_bf16; a.ldc = ldx; a.c_dtype = VDR_DTYPE_BF16;
+  a.M = B * np; a.N = d; a.K = 3 * patch * patch;
+  a.epilogue = VDR_EPI_BIAS_RESIDUAL;
+  a.out_group = np; a.out_group_stride = np + 1; a.out_offset = 1;   // patch tokens behind each image's CLS row
+  a.res_mod = np; a.res_offset = 1;                                   // + pos_embed[1 + patch index]
+  const Im2colSpec ic{images_bf16, B, C, H, W, patch};
+  return gemm_impl(&a, &ic, stream);
 }

@@ -80,6 +80,28 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
   return VDR_OK;
 }
 
+int make_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes) {
+  encode_tiled_fn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return VDR_EDRIVER;
+  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (rank %d) failed (CUresult %d) ptr=%p", rank, (int)r, ptr);
+    return VDR_EINVAL;
+  }
+  return VDR_OK;
+}
+
 }  // namespace vdr
 
 extern "C" {

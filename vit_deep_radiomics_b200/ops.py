@@ -133,6 +133,33 @@ def write_cls_rows(cls: torch.Tensor, pos0: torch.Tensor, x: torch.Tensor, B: in
              "vdr_write_cls_rows")
 
 
+def patch_embed_supported(H: int, W: int, patch: int) -> bool:
+    """True when the geometry tiles into TMA im2col boxes (vdr_patch_embed_supported)."""
+    return bool(_C.lib().vdr_patch_embed_supported(int(H), int(W), int(patch)))
+
+
+def patch_embed(images: torch.Tensor, w_pe: torch.Tensor, bias: torch.Tensor, pos: torch.Tensor, patch: int,
+                out: torch.Tensor) -> torch.Tensor:
+    """Patch embedding + position embedding as one TMA-fed im2col GEMM (no materialised im2col matrix).
+    images (B, H, W) [gray, reused for the 3 input channels] or (B, 3, H, W), bf16 contiguous; w_pe (d, >= 3*p*p) bf16
+    (k = (c, iy, ix)); bias (d) f32; pos (N, d) f32 with N = patches + 1; out (B*N, d) bf16: rows b*N + 1.. are written."""
+    _req(images, torch.bfloat16, "images"), _req(w_pe, torch.bfloat16, "w_pe"), _req(pos, torch.float32, "pos")
+    _req(out, torch.bfloat16, "out"), _req(bias, torch.float32, "bias")
+    if not images.is_contiguous() or images.dim() not in (3, 4) or (images.dim() == 4 and images.shape[1] != 3):
+        raise ValueError("images must be contiguous (B, H, W) or (B, 3, H, W)")
+    B, C = images.shape[0], (1 if images.dim() == 3 else 3)
+    H, W = images.shape[-2:]
+    d = w_pe.shape[0]
+    N = (H // patch) * (W // patch) + 1
+    if pos.shape != (N, d) or not pos.is_contiguous() or out.shape != (B * N, d) or out.stride(1) != 1:
+        raise ValueError(f"pos must be ({N}, {d}) and out ({B * N}, {d})")
+    with _Prof("gemm", 2.0 * B * (N - 1) * d * 3 * patch * patch, f"patch-embed gemm (TMA im2col) M{B * (N - 1)} N{d} K{3 * patch * patch}"):
+        _C.check(_C.lib().vdr_patch_embed_gemm(images.data_ptr(), B, C, H, W, patch, w_pe.data_ptr(), w_pe.stride(0),
+                                               bias.data_ptr(), pos.data_ptr(), out.data_ptr(), out.stride(0), d, _stream()),
+                 "vdr_patch_embed_gemm")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, out_dtype=torch.bfloat16,
               out: torch.Tensor | None = None, save_stats: bool = False):
     _req(x, torch.bfloat16, "x"), _req(gamma, torch.float32, "gamma"), _req(beta, torch.float32, "beta")

@@ -126,6 +126,8 @@ class ViTBackbone:
         if "SL" not in ws:
             ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
         ops.volume_to_slices(vol, crop, out=ws["SL"])
+        if ops.patch_embed_supported(self.img_hw[0], self.img_hw[1], self.cfg["patch"]):
+            return self._encode(S, images=ws["SL"])          # patch embedding reads the slices through a TMA im2col view
         ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=ws["A"])
         return self._encode(S)
 
@@ -137,13 +139,17 @@ class ViTBackbone:
         ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"], out=self._workspace(B)["A"])
         return self._encode(B)
 
-    def _encode(self, B: int) -> torch.Tensor:
-        """Patch-embedding GEMM + transformer blocks + final LayerNorm over the im2col matrix in ws['A']."""
+    def _encode(self, B: int, images: torch.Tensor | None = None) -> torch.Tensor:
+        """Patch-embedding GEMM + transformer blocks + final LayerNorm.  The patch embedding reads either `images`
+        ((B, H, W) bf16 slices, through the TMA im2col view) or the materialised im2col matrix in ws['A']."""
         cfg, w, ws = self.cfg, self.w, self._workspace(B)
         d, heads, N, Np = cfg["dim"], cfg["heads"], self.n_tokens, self.n_patches
         # patch embedding GEMM: bias + pos-embed fused, rows written behind each image's CLS row
-        ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=ws["X"], k=self.K,
-                 out_group=(Np, N, 1), res_mod=(Np, 1))
+        if images is not None:
+            ops.patch_embed(images, w["pe_w"], w["pe_b"], w["pos"], cfg["patch"], out=ws["X"])
+        else:
+            ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=ws["X"], k=self.K,
+                     out_group=(Np, N, 1), res_mod=(Np, 1))
         ops.write_cls_rows(w["cls"], w["pos"], ws["X"], B, N, d)
         X, Y, QKV, Hb = ws["X"], ws["Y"], ws["QKV"], ws["H"]
         scale = 1.0 / math.sqrt(64)
