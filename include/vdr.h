@@ -113,6 +113,40 @@ int vdr_write_cls_rows(const float* cls, const float* pos0, void* X_bf16, int B,
                        vdr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The whole backbone forward as one call: patch embedding -> depth x (LN, QKV, attention, proj + residual, LN, fc1 + GELU,
+ * fc2 + residual) -> final LayerNorm, every kernel enqueued on `stream` (no host synchronisation, no allocation).
+ * Replaces: `model.image_encoder(img_tensor)` for a batch of slices (tfds_dense_descriptor.py:123; pre-norm ViT with the
+ * timm / DINOv2 parameter set: patch_embed, cls_token, pos_embed, blocks[i].{norm1, attn.qkv, attn.proj, norm2, mlp.fc1, mlp.fc2}, norm).
+ *   weights   device pointers; GEMM weights bf16 row-major (out_features, in_features), everything else f32.
+ *             `blocks` is a HOST array of `depth` entries.  pe_w is (dim, pe_ldw >= 3*patch^2) with k = (c, iy, ix).
+ *   images    (B*C, H, W) bf16, C = 1 (gray slices reused for the 3 input channels) or 3
+ *   tokens    (B*N, dim) f32 with row pitch ld_out, N = patches + 1; row b*N is image b's CLS token
+ *   workspace >= vdr_vit_forward_workspace_bytes(weights, B), 256-byte aligned
+ */
+typedef struct {
+  const float *n1w, *n1b;
+  const void* qkv_w;  const float* qkv_b;     /* (3*dim, dim) */
+  const void* proj_w; const float* proj_b;    /* (dim, dim) */
+  const float *n2w, *n2b;
+  const void* fc1_w;  const float* fc1_b;     /* (4*dim, dim) */
+  const void* fc2_w;  const float* fc2_b;     /* (dim, 4*dim) */
+} vdr_vit_block;
+
+typedef struct {
+  int dim, depth, heads, patch, H, W;
+  float eps;                                  /* LayerNorm epsilon (<= 0: 1e-6) */
+  const void* pe_w; int64_t pe_ldw; const float* pe_b;
+  const float* cls;                           /* (dim) */
+  const float* pos;                           /* (N, dim) */
+  const float *norm_w, *norm_b;
+  const vdr_vit_block* blocks;
+} vdr_vit_weights;
+
+size_t vdr_vit_forward_workspace_bytes(const vdr_vit_weights* weights, int B);
+int vdr_vit_forward(const vdr_vit_weights* weights, const void* images_bf16, int B, int C, float* tokens, int64_t ld_out,
+                    void* workspace, size_t workspace_bytes, vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * LayerNorm over the last dim, one warp per row, 16-byte vector loads, fp32 statistics.
  * Replaces: Block.norm1/norm2 + final norm of the backbone (K2) and nn.LayerNorm in the
  * classifier (models_archs.py:145 and the post-norms inside nn.TransformerEncoderLayer).

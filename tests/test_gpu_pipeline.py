@@ -210,3 +210,20 @@ def test_train_step_accumulation_semantics(cuda):
     assert abs(loss_gpu - tot / len(data)) < 0.02
     for k, v in model.state_dict().items():
         assert (v.cpu() - sd[k].detach()).abs().max() < 3e-3, k     # 3 AdamW steps of lr 5e-4: updates ~1.5e-3
+
+
+def test_native_vit_forward_equals_op_by_op_path(cuda):
+    """vdr_vit_forward (one C call) enqueues the same kernels in the same order as the Python op-by-op path: identical tokens."""
+    from vit_deep_radiomics_b200 import synth, tfds_dense_descriptor as tdd
+    rng = np.random.default_rng(21)
+    for name, hw, S in (("vit_t16", (256, 256), 5), ("vit_t16", (64, 64), 3)):     # TMA im2col view / materialised im2col
+        model = tdd.load_model(name, img_hw=hw, device=cuda, seed=5)
+        vol = torch.from_numpy(rng.random(hw + (S,), dtype=np.float32)).to(cuda)
+        crop = (0, hw[0], 0, hw[1])
+        model.use_native_forward = True
+        a = model.forward_volume(vol, crop).clone()
+        model.use_native_forward = False
+        b = model.forward_volume(vol, crop).clone()
+        model.use_native_forward = True
+        assert torch.equal(a, b)
+        assert torch.isfinite(a).all()

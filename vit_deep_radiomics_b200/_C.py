@@ -17,7 +17,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 #: every symbol include/vdr.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "vdr_version", "vdr_last_error_string", "vdr_launch_count",
-    "vdr_gemm", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
+    "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd",
     "vdr_flash_attn_fwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather",
@@ -25,6 +25,19 @@ EXPORTS = (
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
     "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
 )
+
+
+class VitBlock(C.Structure):
+    """== vdr_vit_block (include/vdr.h)"""
+    _fields_ = [(n, C.c_void_p) for n in ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b",
+                                          "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class VitWeights(C.Structure):
+    """== vdr_vit_weights (include/vdr.h)"""
+    _fields_ = [("dim", C.c_int), ("depth", C.c_int), ("heads", C.c_int), ("patch", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("eps", C.c_float), ("pe_w", C.c_void_p), ("pe_ldw", C.c_int64), ("pe_b", C.c_void_p), ("cls", C.c_void_p),
+                ("pos", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("blocks", C.POINTER(VitBlock))]
 
 
 class GemmArgs(C.Structure):
@@ -70,6 +83,9 @@ def lib() -> C.CDLL:
     L.vdr_layernorm_fwd.argtypes = [vp, i64, vp, vp, vp, i64, i32, vp, vp, i32, i32, f32, vp]
     L.vdr_layernorm_bwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp]
     L.vdr_cls_concat_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]
+    L.vdr_vit_forward_workspace_bytes.argtypes = [C.POINTER(VitWeights), i32]
+    L.vdr_vit_forward_workspace_bytes.restype = sz
+    L.vdr_vit_forward.argtypes = [C.POINTER(VitWeights), vp, i32, i32, vp, i64, vp, sz, vp]
     L.vdr_patch_embed_supported.argtypes = [i32, i32, i32]
     L.vdr_patch_embed_gemm.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp, i64, i32, vp]
     L.vdr_flash_attn_fwd.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, f32, vp]
@@ -92,7 +108,7 @@ def lib() -> C.CDLL:
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("vdr_version", "vdr_last_error_string", "vdr_launch_count",
-                        "vdr_mask_gather_workspace_bytes"):
+                        "vdr_mask_gather_workspace_bytes", "vdr_vit_forward_workspace_bytes"):
             fn.restype = i32
     _lib = L
     return L

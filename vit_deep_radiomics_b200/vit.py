@@ -15,7 +15,7 @@ import math
 
 import torch
 
-from . import ops
+from . import _C, ops
 
 VIT_CONFIGS = {
     "vit_s16": dict(dim=384, depth=12, heads=6, patch=16),
@@ -102,19 +102,37 @@ class ViTBackbone:
                 fc1_w=bf(b + "mlp.fc1.weight"), fc1_b=f32(b + "mlp.fc1.bias"),
                 fc2_w=bf(b + "mlp.fc2.weight"), fc2_b=f32(b + "mlp.fc2.bias")))
         self.K, self.ldk = K, ldk
+        # the same pointers as a vdr_vit_weights struct: the whole forward is then one C call (vdr_vit_forward)
+        import ctypes as C
+        blocks = (_C.VitBlock * self.cfg["depth"])()
+        for i, blk in enumerate(self.w["blocks"]):
+            for name in ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b"):
+                setattr(blocks[i], name, blk[name].data_ptr())
+        w = self.w
+        self._native_blocks = blocks          # keeps the array alive
+        self._native = _C.VitWeights(d, self.cfg["depth"], self.cfg["heads"], p, self.img_hw[0], self.img_hw[1], 1e-6,
+                                     w["pe_w"].data_ptr(), w["pe_w"].stride(0), w["pe_b"].data_ptr(), w["cls"].data_ptr(),
+                                     w["pos"].data_ptr(), w["norm_w"].data_ptr(), w["norm_b"].data_ptr(),
+                                     C.cast(blocks, C.POINTER(_C.VitBlock)))
 
     def _workspace(self, B: int) -> dict:
         ws = self._ws.get(B)
         if ws is None:
             d, N, dev = self.cfg["dim"], self.n_tokens, self.device
-            bf = torch.bfloat16
-            ws = dict(A=torch.empty(B * self.n_patches, self.ldk, dtype=bf, device=dev),
+            ws = dict(OUT=torch.empty(B * N, d, dtype=torch.float32, device=dev))
+            self._ws = {B: ws}   # keep one batch size resident
+        return ws
+
+    def _op_buffers(self, B: int) -> dict:
+        """Activation buffers of the op-by-op path (the native path, vdr_vit_forward, carves its own out of one workspace)."""
+        ws = self._workspace(B)
+        if "X" not in ws:
+            d, N, dev, bf = self.cfg["dim"], self.n_tokens, self.device, torch.bfloat16
+            ws.update(A=torch.empty(B * self.n_patches, self.ldk, dtype=bf, device=dev),
                       X=torch.empty(B * N, d, dtype=bf, device=dev),
                       Y=torch.empty(B * N, d, dtype=bf, device=dev),
                       QKV=torch.empty(B * N, 3 * d, dtype=bf, device=dev),
-                      H=torch.empty(B * N, 4 * d, dtype=bf, device=dev),
-                      OUT=torch.empty(B * N, d, dtype=torch.float32, device=dev))
-            self._ws = {B: ws}   # keep one batch size resident
+                      H=torch.empty(B * N, 4 * d, dtype=bf, device=dev))
         return ws
 
     # -- forward -----------------------------------------------------------------------------
@@ -126,9 +144,11 @@ class ViTBackbone:
         if "SL" not in ws:
             ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
         ops.volume_to_slices(vol, crop, out=ws["SL"])
+        if ops.PROFILE is None and self.use_native_forward:
+            return self._encode_native(S, ws["SL"])          # one C call enqueues the whole forward (same kernels, same order)
         if ops.patch_embed_supported(self.img_hw[0], self.img_hw[1], self.cfg["patch"]):
             return self._encode(S, images=ws["SL"])          # patch embedding reads the slices through a TMA im2col view
-        ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=ws["A"])
+        ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=self._op_buffers(S)["A"])
         return self._encode(S)
 
     def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
@@ -136,7 +156,7 @@ class ViTBackbone:
         (batch, channel, row, col).  Returns the final-LayerNorm token matrix (B*N, d) f32
         (row b*N is the CLS token, rows b*N+1.. the patch tokens in (py, px) order)."""
         H, W = self.img_hw
-        ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"], out=self._workspace(B)["A"])
+        ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"], out=self._op_buffers(B)["A"])
         return self._encode(B)
 
     def _encode(self, B: int, images: torch.Tensor | None = None) -> torch.Tensor:
@@ -144,6 +164,7 @@ class ViTBackbone:
         ((B, H, W) bf16 slices, through the TMA im2col view) or the materialised im2col matrix in ws['A']."""
         cfg, w, ws = self.cfg, self.w, self._workspace(B)
         d, heads, N, Np = cfg["dim"], cfg["heads"], self.n_tokens, self.n_patches
+        ws = self._op_buffers(B)
         # patch embedding GEMM: bias + pos-embed fused, rows written behind each image's CLS row
         if images is not None:
             ops.patch_embed(images, w["pe_w"], w["pe_b"], w["pos"], cfg["patch"], out=ws["X"])
@@ -163,6 +184,23 @@ class ViTBackbone:
             ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X)
         ops.layernorm(X, w["norm_w"], w["norm_b"], 1e-6, out=ws["OUT"])
         return ws["OUT"]
+
+    #: route forward_volume through vdr_vit_forward (per-kernel profiling, ops.PROFILE, always uses the op-by-op path)
+    use_native_forward = True
+
+    def _encode_native(self, B: int, images: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+        ws = self._workspace(B)
+        need = _C.lib().vdr_vit_forward_workspace_bytes(C.byref(self._native), B)
+        buf = ws.get("NATIVE")
+        if buf is None or buf.numel() < need:
+            # the per-op buffers are not needed on this path: reuse their storage for the native workspace when it fits
+            buf = ws["NATIVE"] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = ws["OUT"]
+        Cimg = 1 if images.dim() == 3 else 3
+        _C.check(_C.lib().vdr_vit_forward(C.byref(self._native), images.data_ptr(), B, Cimg, out.data_ptr(), out.stride(0),
+                                          buf.data_ptr(), buf.numel(), ops._stream()), "vdr_vit_forward")
+        return out
 
     def dense_descriptors(self, images: torch.Tensor) -> torch.Tensor:
         """images (B, 3, H, W) or (B, H, W) f32 CUDA -> (B, H/p, W/p, d) f32 (a copy)."""
