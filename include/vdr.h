@@ -94,6 +94,14 @@ int vdr_volume_to_slices(const float* vol, int H, int W, int S, int y0, int x0, 
                          void* slices_bf16, vdr_stream_t stream);
 int vdr_im2col_gray_bf16(const void* slices_bf16, int B, int H, int W, int patch, void* A_bf16,
                          vdr_stream_t stream);
+/* The same staging with prepare_image's resize (tfds_dense_descriptor.py:40-44, skimage.transform.resize of a float image)
+ * for crop windows whose size differs from the backbone input: optional Gaussian anti-aliasing (only when an axis shrinks:
+ * sigma = (in/out - 1)/2, truncate 4, boundary 'mirror') + order-1 resampling at (o + 0.5) * in/out - 0.5 with mirrored
+ * indices (scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True), which is what skimage >= 0.19 calls), f32 arithmetic,
+ * bf16 slices (S, OH, OW) out.  workspace: vdr_volume_to_slices_resized_workspace_bytes (0 when nothing shrinks). */
+size_t vdr_volume_to_slices_resized_workspace_bytes(int S, int ch, int cw, int OH, int OW);
+int vdr_volume_to_slices_resized(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH, int OW,
+                                 void* slices_bf16, void* workspace, size_t workspace_bytes, vdr_stream_t stream);
 
 /* Patch embedding as ONE TMA-fed im2col GEMM (K1: Conv2d(3, d, p, p) + position embedding of the backbone the reference
  * calls at tfds_dense_descriptor.py:123): the A operand is never materialised -- a 5-D tensor map (ix, iy, px, py, image)

@@ -227,3 +227,51 @@ def test_native_vit_forward_equals_op_by_op_path(cuda):
         model.use_native_forward = True
         assert torch.equal(a, b)
         assert torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("ch,cw,oh,ow", [(37, 53, 64, 64), (200, 180, 256, 256), (96, 80, 64, 48), (300, 260, 128, 224)])
+def test_resize_staging_matches_oracle(cuda, ch, cw, oh, ow):
+    """vdr_volume_to_slices_resized == prepare_image's skimage resize (oracle/resize_np.py, pinned to scipy.ndimage):
+    f32 arithmetic on the device, bf16 slices out -> within one bf16 rounding of the float64 oracle."""
+    from oracle import resize_np
+    from vit_deep_radiomics_b200 import ops
+    rng = np.random.default_rng(ch + ow)
+    H, W, S, y0, x0 = ch + 11, cw + 7, 5, 6, 3
+    vol = rng.random((H, W, S), dtype=np.float32)
+    got = ops.volume_to_slices(torch.from_numpy(vol).to(cuda), (y0, y0 + ch, x0, x0 + cw), out_hw=(oh, ow)).float().cpu().numpy()
+    assert got.shape == (S, oh, ow)
+    for s in range(S):
+        want = resize_np.resize(vol[y0:y0 + ch, x0:x0 + cw, s], (oh, ow))
+        assert np.abs(got[s] - want).max() <= 2 ** -8 * max(1.0, np.abs(want).max()) + 1e-4      # bf16 rounding + f32 arithmetic
+
+
+def test_generate_features_resizes_crop_to_backbone_input(cuda):
+    """A crop window of another size than the backbone input (the normal case on real data: the window is 4x the tumour
+    bounding box) is resized on the device; descriptors match the fp32 oracle ViT run on the oracle-resized slices, and the
+    ROI geometry matches the reference's extract_roi scaling."""
+    from oracle import gather_np, resize_np
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    from vit_deep_radiomics_b200.visualization_utils import crop_window
+    rng = np.random.default_rng(31)
+    H = W = 160
+    S = 4
+    img = rng.random((H, W, S), dtype=np.float32)
+    mask = np.zeros((H, W, S), dtype=bool)
+    mask[70:85, 60:80, 1:3] = True                      # bbox 15 x 20 -> window side 80, backbone input 64
+    model = tdd.load_model("vit_t16", img_hw=(64, 64), device=cuda, seed=3)
+    feats, masks = tdd.generate_features(model, img, mask)
+    x0, y0, x1, y1 = crop_window(mask.any(-1))
+    y0, y1, x0, x1 = max(0, y0), min(H, y1), max(0, x0), min(W, x1)
+    assert (y1 - y0, x1 - x0) != (64, 64)
+    crop = img[y0:y1, x0:x1]
+    resized = np.stack([resize_np.resize(crop[:, :, s], (64, 64)) for s in range(S)]).astype(np.float32)
+    dense = _oracle_dense(model, torch.from_numpy(resized)[:, None].expand(-1, 3, -1, -1).contiguous())
+    from vit_deep_radiomics_b200.visualization_utils import roi_window
+    bigger_c = mask.any(-1)[y0:y1, x0:x1]
+    fx0, fy0, fx1, fy1 = roi_window(model.grid, bigger_c, margin=1)
+    mx0, my0, mx1, my1 = roi_window(bigger_c.shape, bigger_c, margin=1)
+    assert len(feats) == S
+    for s in range(S):
+        assert feats[s].shape == dense[s, fy0:fy1, fx0:fx1].shape
+        _check_descriptors(feats[s], dense[s, fy0:fy1, fx0:fx1])
+        assert np.array_equal(masks[s], mask[y0:y1, x0:x1, s][my0:my1, mx0:mx1])

@@ -64,6 +64,86 @@ volume_to_slices_kernel(const float* __restrict__ src, int W_full, int S, int y0
   }
 }
 
+// ---- prepare_image's resize on the device (scope row N2) ---------------------------------------------------------
+// skimage.transform.resize(img, (OH, OW)) of a float image (tfds_dense_descriptor.py:42/44) = optional Gaussian
+// anti-aliasing (only when an axis shrinks: sigma = (in/out - 1)/2, truncate 4, mode 'mirror') followed by
+// scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True): output pixel o samples input coordinate
+// (o + 0.5) * in/out - 0.5 with linear weights, indices mirrored about the edge pixel centres (d c b | a b c d | c b a).
+__device__ __forceinline__ int mirror_idx(int i, int n) {
+  if (n == 1) return 0;
+  const int p = 2 * n - 2;
+  i %= p;
+  if (i < 0) i += p;
+  return i >= n ? p - i : i;
+}
+
+// One Gaussian pass along x (kAlongY = false) or y (true) over the crop window, layout (rows, cols, S) with the slice index
+// fastest: consecutive threads walk s, so every tap is a coalesced read.  Weights are built once per block.
+template <bool kAlongY>
+__global__ void __launch_bounds__(256)
+gauss_pass_kernel(const float* __restrict__ src, int64_t src_row_pitch, int64_t src_col_pitch, int rows, int cols, int S,
+                  float sigma, int radius, float* __restrict__ dst) {
+  extern __shared__ float wts[];   // [2 * radius + 1]
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int j = -radius; j <= radius; ++j) {
+      const float x = static_cast<float>(j) / sigma;
+      wts[j + radius] = expf(-0.5f * x * x);
+      sum += wts[j + radius];
+    }
+    for (int j = 0; j <= 2 * radius; ++j) wts[j] /= sum;
+  }
+  __syncthreads();
+  const int64_t total = static_cast<int64_t>(rows) * cols * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = static_cast<int>(i % S);
+    const int64_t t = i / S;
+    const int x = static_cast<int>(t % cols), y = static_cast<int>(t / cols);
+    float acc = 0.f;
+    for (int j = -radius; j <= radius; ++j) {
+      const int yy = kAlongY ? mirror_idx(y + j, rows) : y, xx = kAlongY ? x : mirror_idx(x + j, cols);
+      acc = fmaf(wts[j + radius], __ldg(src + yy * src_row_pitch + xx * src_col_pitch + s), acc);
+    }
+    dst[i] = acc;
+  }
+}
+
+// Bilinear resample of the (rows, cols, S) window to (S, OH, OW) bf16 slices, transposed through a 32x33 smem tile like
+// volume_to_slices_kernel (reads coalesced along s, writes along x).
+__global__ void __launch_bounds__(256)
+resize_to_slices_kernel(const float* __restrict__ src, int64_t src_row_pitch, int64_t src_col_pitch, int rows, int cols, int S,
+                        int OH, int OW, float sy, float sx, __nv_bfloat16* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int Y = blockIdx.y;
+  const int xb = blockIdx.x * 32, sb = blockIdx.z * 32;
+  const float fy = (Y + 0.5f) * sy - 0.5f;
+  const float fy0 = floorf(fy);
+  const float wy = fy - fy0;
+  const int y0 = mirror_idx(static_cast<int>(fy0), rows), y1 = mirror_idx(static_cast<int>(fy0) + 1, rows);
+#pragma unroll
+  for (int j = threadIdx.y; j < 32; j += 8) {          // j: X within tile, threadIdx.x: s within tile
+    const int X = xb + j, sidx = sb + threadIdx.x;
+    float v = 0.f;
+    if (X < OW && sidx < S) {
+      const float fx = (X + 0.5f) * sx - 0.5f;
+      const float fx0 = floorf(fx);
+      const float wx = fx - fx0;
+      const int x0 = mirror_idx(static_cast<int>(fx0), cols), x1 = mirror_idx(static_cast<int>(fx0) + 1, cols);
+      const float a00 = __ldg(src + y0 * src_row_pitch + x0 * src_col_pitch + sidx), a01 = __ldg(src + y0 * src_row_pitch + x1 * src_col_pitch + sidx);
+      const float a10 = __ldg(src + y1 * src_row_pitch + x0 * src_col_pitch + sidx), a11 = __ldg(src + y1 * src_row_pitch + x1 * src_col_pitch + sidx);
+      const float top = fmaf(wx, a01 - a00, a00), bot = fmaf(wx, a11 - a10, a10);
+      v = fmaf(wy, bot - top, top);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = threadIdx.y; j < 32; j += 8) {          // j: s within tile, threadIdx.x: X within tile
+    const int sidx = sb + j, X = xb + threadIdx.x;
+    if (sidx < S && X < OW) dst[(static_cast<int64_t>(sidx) * OH + Y) * OW + X] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
 // im2col from bf16 slices (B, H, W), gray replicated to 3 channels: 16-byte copies when patch % 8 == 0.
 __global__ void __launch_bounds__(256)
 im2col_gray_bf16_kernel(const __nv_bfloat16* __restrict__ src, int H, int W, int gh, int gw, int patch, int K,
@@ -150,6 +230,66 @@ extern "C" int vdr_volume_to_slices(const float* vol, int H, int W, int S, int y
       vol, W, S, y0, x0, ch, cw, static_cast<__nv_bfloat16*>(slices_bf16));
   count_launch();
   VDR_CHECK_LAUNCH("volume_to_slices_kernel");
+  return VDR_OK;
+}
+
+static void resize_sigmas(int ch, int cw, int OH, int OW, float* sig_y, float* sig_x) {
+  // skimage: anti-aliasing is on when ANY axis shrinks; per-axis sigma = max(0, (in/out - 1) / 2)
+  const bool aa = OH < ch || OW < cw;
+  const float fy = static_cast<float>(ch) / OH, fx = static_cast<float>(cw) / OW;
+  *sig_y = aa ? fmaxf(0.f, (fy - 1.f) * 0.5f) : 0.f;
+  *sig_x = aa ? fmaxf(0.f, (fx - 1.f) * 0.5f) : 0.f;
+}
+static int gauss_radius(float sigma) { return sigma > 1e-15f ? static_cast<int>(4.0f * sigma + 0.5f) : 0; }
+
+extern "C" size_t vdr_volume_to_slices_resized_workspace_bytes(int S, int ch, int cw, int OH, int OW) {
+  float sy, sx;
+  resize_sigmas(ch, cw, OH, OW, &sy, &sx);
+  const int passes = (gauss_radius(sy) > 0 ? 1 : 0) + (gauss_radius(sx) > 0 ? 1 : 0);
+  return static_cast<size_t>(passes) * ch * cw * S * sizeof(float);
+}
+
+extern "C" int vdr_volume_to_slices_resized(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH,
+                                            int OW, void* slices_bf16, void* workspace, size_t workspace_bytes,
+                                            vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(vol && slices_bf16, VDR_EINVAL, "vdr_volume_to_slices_resized: null pointer");
+  VDR_CHECK_ARG(H > 0 && W > 0 && S > 0 && ch > 0 && cw > 0 && y0 >= 0 && x0 >= 0 && y0 + ch <= H && x0 + cw <= W, VDR_EINVAL,
+                "vdr_volume_to_slices_resized: crop window (%d:%d, %d:%d) outside the %dx%d volume", y0, y0 + ch, x0, x0 + cw, H, W);
+  VDR_CHECK_ARG(OH > 0 && OW > 0 && OH <= 65535 && (S + 31) / 32 <= 65535, VDR_EINVAL, "vdr_volume_to_slices_resized: bad output size %dx%d", OH, OW);
+  const size_t need = vdr_volume_to_slices_resized_workspace_bytes(S, ch, cw, OH, OW);
+  VDR_CHECK_ARG(need == 0 || (workspace && workspace_bytes >= need), VDR_EWORKSPACE,
+                "vdr_volume_to_slices_resized: workspace too small (%zu < %zu)", workspace_bytes, need);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float sig_y, sig_x;
+  resize_sigmas(ch, cw, OH, OW, &sig_y, &sig_x);
+  const int ry = gauss_radius(sig_y), rx = gauss_radius(sig_x);
+  VDR_CHECK_ARG(ry <= 4096 && rx <= 4096, VDR_EINVAL, "vdr_volume_to_slices_resized: shrink factor too large");
+  // source window: rows y0.., cols x0.. of the (H, W, S) volume
+  const float* src = vol + (static_cast<int64_t>(y0) * W + x0) * S;
+  int64_t row_pitch = static_cast<int64_t>(W) * S, col_pitch = S;
+  float* tmp = static_cast<float*>(workspace);
+  const int64_t total = static_cast<int64_t>(ch) * cw * S;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  if (rx > 0) {
+    gauss_pass_kernel<false><<<(unsigned)blocks, 256, (2 * rx + 1) * sizeof(float), s>>>(src, row_pitch, col_pitch, ch, cw, S, sig_x, rx, tmp);
+    count_launch();
+    VDR_CHECK_LAUNCH("gauss_pass_kernel<x>");
+    src = tmp; row_pitch = static_cast<int64_t>(cw) * S; col_pitch = S;
+    tmp += total;
+  }
+  if (ry > 0) {
+    gauss_pass_kernel<true><<<(unsigned)blocks, 256, (2 * ry + 1) * sizeof(float), s>>>(src, row_pitch, col_pitch, ch, cw, S, sig_y, ry, tmp);
+    count_launch();
+    VDR_CHECK_LAUNCH("gauss_pass_kernel<y>");
+    src = tmp; row_pitch = static_cast<int64_t>(cw) * S; col_pitch = S;
+  }
+  dim3 grid((OW + 31) / 32, OH, (S + 31) / 32), block(32, 8);
+  resize_to_slices_kernel<<<grid, block, 0, s>>>(src, row_pitch, col_pitch, ch, cw, S, OH, OW, static_cast<float>(ch) / OH,
+                                                static_cast<float>(cw) / OW, static_cast<__nv_bfloat16*>(slices_bf16));
+  count_launch();
+  VDR_CHECK_LAUNCH("resize_to_slices_kernel");
   return VDR_OK;
 }
 

@@ -98,13 +98,24 @@ def im2col_patches(src: torch.Tensor, strides, B: int, H: int, W: int, patch: in
     return out
 
 
-def volume_to_slices(vol: torch.Tensor, crop, out: torch.Tensor | None = None) -> torch.Tensor:
-    """(H, W, S) f32 volume -> (S, ch, cw) bf16 slices of the crop window (y0, y1, x0, x1)."""
+def volume_to_slices(vol: torch.Tensor, crop, out: torch.Tensor | None = None, out_hw=None) -> torch.Tensor:
+    """(H, W, S) f32 volume -> (S, ch, cw) bf16 slices of the crop window (y0, y1, x0, x1); with ``out_hw`` different
+    from the window size the slices are resized as prepare_image does (tfds_dense_descriptor.py:40-44: skimage resize =
+    Gaussian anti-aliasing when shrinking + order-1 resampling, mirrored borders)."""
     _req(vol, torch.float32, "vol")
     if vol.dim() != 3 or not vol.is_contiguous():
         raise ValueError("vol must be a contiguous (H, W, S) tensor")
     H, W, S = vol.shape
     y0, y1, x0, x1 = (int(v) for v in crop)
+    if out_hw is not None and tuple(int(v) for v in out_hw) != (y1 - y0, x1 - x0):
+        OH, OW = (int(v) for v in out_hw)
+        if out is None:
+            out = torch.empty((S, OH, OW), dtype=torch.bfloat16, device=vol.device)
+        need = _C.lib().vdr_volume_to_slices_resized_workspace_bytes(S, y1 - y0, x1 - x0, OH, OW)
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=vol.device)
+        _C.check(_C.lib().vdr_volume_to_slices_resized(vol.data_ptr(), H, W, S, y0, x0, y1 - y0, x1 - x0, OH, OW, out.data_ptr(),
+                                                       ws.data_ptr(), need, _stream()), "vdr_volume_to_slices_resized")
+        return out
     if out is None:
         out = torch.empty((S, y1 - y0, x1 - x0), dtype=torch.bfloat16, device=vol.device)
     _C.check(_C.lib().vdr_volume_to_slices(vol.data_ptr(), H, W, S, y0, x0, y1 - y0, x1 - x0, out.data_ptr(), _stream()),

@@ -49,15 +49,20 @@ def load_model(model_name, model_path=None, img_hw=None, device="cuda:0", seed=1
 
 
 def prepare_image(img, size=None, device="cuda:0"):
-    """reference: tfds_dense_descriptor.py:30-48 -- gray2rgb, (resize), HWC -> NCHW, float32, to GPU.
-    Returns a (1, 3, h, w) CUDA tensor.  The reference always resizes to 1024^2 / 896^2 with
-    skimage; here the backbone is built for the crop size, so only the identity resize is
-    accepted (GPU bilinear pre-processing is scope row N2)."""
+    """reference: tfds_dense_descriptor.py:30-48 -- gray2rgb, resize, HWC -> NCHW, float32, to GPU.
+    Returns a (1, 3, h, w) CUDA tensor.  The reference resizes to 1024^2 / 896^2 with skimage.transform.resize; here
+    ``size`` is the backbone input and the resize (same algorithm: anti-aliasing Gaussian when shrinking + order-1
+    resampling with mirrored borders) runs on the device in f32, rounded to bf16 like every backbone input."""
     img = np.asarray(img)
+    if size is not None and tuple(size) != tuple(img.shape[0:2]):
+        planes = img[..., None] if img.ndim < 3 else img                      # (H, W, C): channels take the slice axis
+        vol = torch.as_tensor(np.ascontiguousarray(planes, dtype=np.float32)).to(device)
+        out = ops.volume_to_slices(vol, (0, img.shape[0], 0, img.shape[1]), out_hw=size).float()   # (C, h, w)
+        if out.shape[0] == 1:
+            out = out.expand(3, -1, -1)                                        # gray2rgb (:41)
+        return out[None].contiguous()
     if img.ndim < 3:
         img = np.stack([img] * 3, axis=-1)          # gray2rgb (:41)
-    if size is not None and tuple(size) != tuple(img.shape[0:2]):
-        raise NotImplementedError(f"resize {img.shape[0:2]} -> {tuple(size)} is not implemented on the device path")
     t = torch.as_tensor(np.ascontiguousarray(img.transpose((2, 0, 1))[None]), dtype=torch.float32)
     return t.to(device)
 
@@ -81,12 +86,7 @@ def _plan_from_bbox(model, H, W, bbox):
     x0c, x1c = [max(0, min(v, W)) for v in (x0, x1)]
     if not (y0c <= rmin and rmax < y1c and x0c <= cmin and cmax < x1c):
         return None
-    ch, cw = y1c - y0c, x1c - x0c
-    if (ch, cw) != tuple(model.img_hw):
-        raise NotImplementedError(
-            f"crop window {ch}x{cw} differs from the backbone input {model.img_hw}: the resize of "
-            "prepare_image is not implemented on the device path (scope row N2); build the model with img_hw="
-            f"({ch}, {cw})")
+    ch, cw = y1c - y0c, x1c - x0c          # a window of another size than the backbone input is resized on the device (:40-44)
     bbox_c = (rmin - y0c, rmax - y0c, cmin - x0c, cmax - x0c)            # union mask after crop_image (:267)
     gh, gw = model.grid
     fx0, fy0, fx1, fy1 = roi_window_from_bbox((gh, gw), (ch, cw), bbox_c, margin=1)   # extract_roi(features, bigger_mask)
@@ -107,8 +107,6 @@ def _plan(model, mask_3d):
     x0c, x1c = [max(0, min(v, W)) for v in (x0, x1)]
     bigger_c = bigger[y0c:y1c, x0c:x1c]
     ch, cw = bigger_c.shape
-    if (ch, cw) != tuple(model.img_hw):
-        raise NotImplementedError(f"crop window {ch}x{cw} differs from the backbone input {model.img_hw} (scope row N2)")
     gh, gw = model.grid
     fx0, fy0, fx1, fy1 = roi_window((gh, gw), bigger_c, margin=1)
     mx0, my0, mx1, my1 = roi_window((ch, cw), bigger_c, margin=1)
@@ -117,16 +115,24 @@ def _plan(model, mask_3d):
 
 def _forward_volume(model, img_dev, plan, max_batch=None):
     """Batched backbone forward over all slices of a device-resident volume (H, W, S[, 3]) f32.
-    Slices are read in place through element strides (no host transpose, no NCHW copy)."""
+    Gray volumes are staged slice-major (and resized to the backbone input when the crop window has another size) by one
+    kernel; RGB volumes are read in place through element strides (no host transpose, no NCHW copy)."""
     y0, y1, x0, x1 = plan["crop"]
     S = img_dev.shape[2]
-    view = img_dev[y0:y1, x0:x1]
     if img_dev.dim() == 3:
-        strides = (view.stride(2), 0, view.stride(0), view.stride(1))
-    else:
-        strides = (view.stride(2), view.stride(3), view.stride(0), view.stride(1))
-    if img_dev.dim() == 3 and img_dev.is_contiguous() and (max_batch is None or max_batch >= S):
-        return model.forward_volume(img_dev, plan["crop"])          # coalesced slice staging + bf16 im2col
+        if img_dev.is_contiguous() and (max_batch is None or max_batch >= S):
+            return model.forward_volume(img_dev, plan["crop"])      # coalesced slice staging (+ resize) -> TMA im2col GEMM
+        step = S if max_batch is None else max_batch
+        outs = []
+        for s0 in range(0, S, step):
+            chunk = img_dev[:, :, s0:s0 + min(step, S - s0)].contiguous()
+            outs.append(model.forward_volume(chunk, plan["crop"]).clone())
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+    if (y1 - y0, x1 - x0) != tuple(model.img_hw):
+        raise NotImplementedError("RGB volumes whose crop window differs from the backbone input: resize slice by slice with "
+                                  "prepare_image(img, size=model.img_hw)")
+    view = img_dev[y0:y1, x0:x1]
+    strides = (view.stride(2), view.stride(3), view.stride(0), view.stride(1))
     if max_batch is None or max_batch >= S:
         return model.forward_tokens(view, strides, S)
     outs = []

@@ -137,13 +137,14 @@ class ViTBackbone:
 
     # -- forward -----------------------------------------------------------------------------
     def forward_volume(self, vol: torch.Tensor, crop) -> torch.Tensor:
-        """vol: (H, W, S) f32 CUDA volume (np.dstack layout), crop = (y0, y1, x0, x1) of size self.img_hw.
-        All S slices go through the backbone as one batch; returns the (S*N, d) f32 token matrix."""
+        """vol: (H, W, S) f32 CUDA volume (np.dstack layout), crop = (y0, y1, x0, x1); a window whose size differs from
+        self.img_hw is resized to it as prepare_image does.  All S slices go through the backbone as one batch; returns the
+        (S*N, d) f32 token matrix."""
         S = vol.shape[2]
         ws = self._workspace(S)
         if "SL" not in ws:
             ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
-        ops.volume_to_slices(vol, crop, out=ws["SL"])
+        ops.volume_to_slices(vol, crop, out=ws["SL"], out_hw=self.img_hw)
         if ops.PROFILE is None and self.use_native_forward:
             return self._encode_native(S, ws["SL"])          # one C call enqueues the whole forward (same kernels, same order)
         if ops.patch_embed_supported(self.img_hw[0], self.img_hw[1], self.cfg["patch"]):
