@@ -255,7 +255,17 @@ int vdr_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out,
                        vdr_stream_t stream);
 /* out_accum[c] += sum_r in[r][c]  (bias gradients; bf16 in, f32 accumulate). */
 int vdr_colsum_bf16(const void* in, int64_t ld, int rows, int cols, float* out_accum, vdr_stream_t stream);
-/* Attention backward pieces (scores materialised per head; N <= ~16k tokens in this model):
+/* Fused flash-style attention backward on tcgen05 (head_dim 64): dqkv (B*N, 3d) bf16 = [dQ | dK | dV] from the packed qkv of
+ * the forward, its output O, the upstream gradient dO and the log-sum-exp the forward saved.  One CTA per (128-key block, head,
+ * image) keeps dK / dV in TMEM while it walks the query blocks; S, dP, P, dS never leave the SM; dQ is accumulated in an f32
+ * scratch with vector reductions and converted at the end.  Replaces: autograd of F.scaled_dot_product_attention inside
+ * nn.TransformerEncoderLayer (models_archs.py:146) on the training path (loss.backward(), train_models.py:683).
+ * workspace >= vdr_flash_attn_bwd_workspace_bytes(B, N, heads), 16-byte aligned. */
+size_t vdr_flash_attn_bwd_workspace_bytes(int B, int N, int heads);
+int vdr_flash_attn_bwd(const void* qkv, int64_t ld_qkv, const void* O, const void* dO, int64_t ld_o, const float* lse,
+                       void* dqkv, int64_t ld_dqkv, int B, int N, int heads, float scale, void* workspace,
+                       size_t workspace_bytes, vdr_stream_t stream);
+/* Attention backward pieces of the earlier, unfused path (scores materialised per head; N <= ~16k tokens in this model):
  *   delta[h][i] = sum_c dO[i][h*64+c] * O[i][h*64+c]
  *   P = exp(S*scale - lse) (0 for key columns >= N),  dS = P * (dP - delta) * scale     (S, dP f32; P, dS bf16) */
 int vdr_attn_delta(const void* dO, const void* O, int64_t ld, int N, int heads, float* delta, vdr_stream_t stream);

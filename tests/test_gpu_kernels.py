@@ -185,3 +185,28 @@ def test_patch_embed_unsupported_geometry_is_rejected(cuda):
     with pytest.raises(ValueError):
         ops.patch_embed(imgs, torch.zeros(64, 768, device=cuda, dtype=torch.bfloat16), torch.zeros(64, device=cuda),
                         torch.zeros(197, 64, device=cuda), 16, out=torch.zeros(197, 64, device=cuda, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (1, 300, 2), (2, 257, 4), (1, 1025, 2), (1, 2500, 4)])
+def test_flash_attention_backward_vs_fp32_autograd(cuda, B, N, heads):
+    """vdr_flash_attn_bwd against torch fp32 autograd of softmax(q k^T / 8) v on the same bf16 inputs: dq, dk, dv within bf16
+    operand tolerance (P and dS are rounded to bf16 for the tensor cores, as in the forward)."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(N + heads)
+    d = heads * 64
+    qkv = (torch.randn(B * N, 3 * d, device=cuda) * 0.8).bfloat16()
+    do = (torch.randn(B * N, d, device=cuda) * 0.5).bfloat16()
+    out, lse = ops.flash_attn(qkv, B, N, heads, return_lse=True)
+    dqkv = ops.flash_attn_bwd(qkv, out, do, lse, B, N, heads).float()
+    x = qkv.float().view(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)     # (3, B, h, N, 64)
+    q, k, v = x[0], x[1], x[2]
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    o = p @ v
+    o.backward(do.float().view(B, N, heads, 64).permute(0, 2, 1, 3))
+    want = x.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * d)
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        g, w = dqkv[:, sl], want[:, sl]
+        err = (g - w).abs().max().item()
+        assert err <= 0.02 * w.abs().max().item() + 2e-3, (name, err, w.abs().max().item())
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), w.flatten(), dim=0).item()
+        assert cos > 0.999, (name, cos)

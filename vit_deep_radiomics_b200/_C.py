@@ -19,7 +19,7 @@ EXPORTS = (
     "vdr_version", "vdr_last_error_string", "vdr_launch_count",
     "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd",
-    "vdr_flash_attn_fwd",
+    "vdr_flash_attn_fwd", "vdr_flash_attn_bwd_workspace_bytes", "vdr_flash_attn_bwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather",
     "vdr_voxel_bbox", "vdr_mask_bbox", "vdr_voxel_gather",
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
@@ -91,6 +91,9 @@ def lib() -> C.CDLL:
     L.vdr_volume_to_slices_resized.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
     L.vdr_patch_embed_supported.argtypes = [i32, i32, i32]
     L.vdr_patch_embed_gemm.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp, i64, i32, vp]
+    L.vdr_flash_attn_bwd_workspace_bytes.argtypes = [i32, i32, i32]
+    L.vdr_flash_attn_bwd_workspace_bytes.restype = sz
+    L.vdr_flash_attn_bwd.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, i32, f32, vp, sz, vp]
     L.vdr_flash_attn_fwd.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, f32, vp]
     L.vdr_mask_gather_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.vdr_mask_gather_workspace_bytes.restype = sz
@@ -112,7 +115,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         if name not in ("vdr_version", "vdr_last_error_string", "vdr_launch_count",
                         "vdr_mask_gather_workspace_bytes", "vdr_vit_forward_workspace_bytes",
-                        "vdr_volume_to_slices_resized_workspace_bytes"):
+                        "vdr_volume_to_slices_resized_workspace_bytes", "vdr_flash_attn_bwd_workspace_bytes"):
             fn.restype = i32
     _lib = L
     return L

@@ -103,7 +103,18 @@ def classifier_forward(x, num_heads, num_layers, params, save=False):
     return logits, cls
 
 
+#: use the fused tcgen05 backward (vdr_flash_attn_bwd); False = the earlier path with materialised scores (kept as a cross-check)
+FUSED_ATTENTION_BACKWARD = True
+
+
 def attention_backward(qkv, a, da, lse, heads):
+    """dqkv (N, 3d) bf16 from da (N, d)."""
+    if FUSED_ATTENTION_BACKWARD:
+        return ops.flash_attn_bwd(qkv, a, da.contiguous(), lse, 1, qkv.shape[0], heads)
+    return attention_backward_materialised(qkv, a, da, lse, heads)
+
+
+def attention_backward_materialised(qkv, a, da, lse, heads):
     """dqkv (N, 3d) bf16 from da (N, d): per head, S and dP are materialised in f32, P and dS in bf16."""
     N, d3 = qkv.shape
     d = d3 // 3

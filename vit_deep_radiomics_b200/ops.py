@@ -436,6 +436,25 @@ def colsum_accum(x: torch.Tensor, out: torch.Tensor) -> None:
     _C.check(_C.lib().vdr_colsum_bf16(x.data_ptr(), x.stride(0), rows, cols, out.data_ptr(), _stream()), "vdr_colsum_bf16")
 
 
+def flash_attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Tensor, B: int, N: int, heads: int,
+                   scale: float | None = None) -> torch.Tensor:
+    """dqkv (B*N, 3d) bf16 from the forward's packed qkv, output o, upstream gradient do (all bf16) and lse (B, heads, N) f32."""
+    _req(qkv, torch.bfloat16, "qkv"), _req(o, torch.bfloat16, "o"), _req(do, torch.bfloat16, "do"), _req(lse, torch.float32, "lse")
+    d = heads * 64
+    if qkv.shape != (B * N, 3 * d) or o.shape != (B * N, d) or do.shape != (B * N, d) or o.stride(0) != do.stride(0):
+        raise ValueError("flash_attn_bwd: qkv (B*N, 3d), o / do (B*N, d) with equal row pitch expected")
+    if scale is None:
+        scale = 1.0 / math.sqrt(64)
+    dqkv = torch.empty((B * N, 3 * d), dtype=torch.bfloat16, device=qkv.device)
+    need = _C.lib().vdr_flash_attn_bwd_workspace_bytes(B, N, heads)
+    ws = torch.empty(need, dtype=torch.uint8, device=qkv.device)
+    with _Prof("attn_bwd", 10.0 * B * heads * N * N * 64, f"attn-bwd B{B} N{N} h{heads}"):
+        _C.check(_C.lib().vdr_flash_attn_bwd(qkv.data_ptr(), qkv.stride(0), o.data_ptr(), do.data_ptr(), o.stride(0), lse.data_ptr(),
+                                             dqkv.data_ptr(), dqkv.stride(0), B, N, heads, float(scale), ws.data_ptr(), need, _stream()),
+                 "vdr_flash_attn_bwd")
+    return dqkv
+
+
 def attn_delta(dO: torch.Tensor, O: torch.Tensor, heads: int) -> torch.Tensor:
     N = O.shape[0]
     delta = torch.empty((heads, N), dtype=torch.float32, device=O.device)
