@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvdr.so")
+LIB_PATH = os.environ.get("VDR_LIB") or os.path.join(_HERE, "lib", "libvdr.so")   # VDR_LIB: kernel-variant experiments only
 
 VDR_DTYPE_BF16, VDR_DTYPE_F32 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2

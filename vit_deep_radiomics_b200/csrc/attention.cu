@@ -19,6 +19,10 @@
 
 #include "common.cuh"
 
+#ifndef VDR_ATTN_POLY_MASK
+#define VDR_ATTN_POLY_MASK 0x02u   // 1 pair of every 8: measured in the pipeline (power-capped) 0/8 0.874, 1/8 0.759, 2/8 0.799, 3/8 0.812, 4/8 0.887 ms
+#endif
+
 namespace vdr {
 
 constexpr int kSoftmaxWarps = 8;
@@ -26,6 +30,7 @@ constexpr int kAttnThreads = (kSoftmaxWarps + 4) * 32;   // 2 softmax warpgroups
 constexpr int kBQ = 128, kBKV = 128, kHD = 64;
 constexpr int kTileBytes = 128 * kHD * 2;               // 16 KB: one 128 x 64 bf16 tile
 constexpr int kAttnSmem = 5 * kTileBytes /*Q, 4 ring slots*/ + 256 /*barriers*/ + 3 * 2 * 128 * 4 /*max exchange x2, sum exchange*/ + 8 * 2 * 128 /*trailing keys: K, V rows*/;
+constexpr uint32_t kPolyMask = VDR_ATTN_POLY_MASK;        // which of every 8 column pairs take the polynomial exp2 (bit i = pair i)
 constexpr int kAttnTmemCols = 256;                       // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 
 __device__ __forceinline__ float ex2(float x) {
@@ -484,7 +489,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
           for (int i = 0; i < 32; i += 2) {
             const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2);
             float p0, p1;
-            if (((i >> 1) & 7) == 1 || ((i >> 1) & 7) == 4 || ((i >> 1) & 7) == 6) {   // 3 of every 8 pairs: FMA-pipe exp2
+            if ((kPolyMask >> ((i >> 1) & 7)) & 1u) {   // a fixed subset of every 8 pairs: FMA-pipe exp2
               exp2_poly2(x2, p0, p1);
             } else {
               float x0, x1;
