@@ -275,3 +275,37 @@ def test_generate_features_resizes_crop_to_backbone_input(cuda):
         assert feats[s].shape == dense[s, fy0:fy1, fx0:fx1].shape
         _check_descriptors(feats[s], dense[s, fy0:fy1, fx0:fx1])
         assert np.array_equal(masks[s], mask[y0:y1, x0:x1, s][my0:my1, mx0:mx1])
+
+
+def test_c5_extraction_feeds_classifier_training_step(cuda):
+    """BASELINE config C5 as a chain: device extraction -> point cloud (tokens stay on the GPU) -> classifier forward, focal
+    loss, backward.  The classifier's logits / CLS token / gradients on the extracted tokens match the fp32 oracle classifier
+    evaluated on the same tokens (tolerances of the classifier tests)."""
+    from oracle import classifier_fp32 as C
+    from vit_deep_radiomics_b200 import synth, tfds_dense_descriptor as tdd
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier
+    from vit_deep_radiomics_b200.train_models import FocalLoss
+    img, mask, res, name = synth.make_case("T0")
+    model = tdd.load_model(name, img_hw=img.shape[:2], device=cuda, seed=7)
+    out = tdd.extract_point_cloud(model, img, mask, res, to_host=False)
+    n = int(out["count"].item())
+    assert n > 0
+    tokens = out["tokens"][:n]
+    D = model.cfg["dim"]
+    torch.manual_seed(1)
+    clf = TransformerNoduleClassifier(D, 4 * D, D // 64, 2, 2).to(cuda)
+    y = torch.tensor([0.0, 1.0], device=cuda)
+    logits, cls = clf(tokens.unsqueeze(0))
+    loss = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=cuda), gamma=2)(torch.squeeze(logits), y)
+    loss.backward()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in clf.state_dict().items()}
+    lg, cl = C.classifier_forward(sd, tokens.detach().cpu()[None], D // 64, 2)
+    ref_loss = C.focal_loss(lg[0], y.cpu(), 2.0, torch.tensor([0.25, 0.75]))
+    ref_loss.backward()
+    assert torch.allclose(logits.detach().cpu().reshape(-1), lg.detach().reshape(-1), atol=0.05, rtol=0.05)
+    assert torch.nn.functional.cosine_similarity(cls.detach().cpu().reshape(1, -1), cl.detach().reshape(1, -1)).item() > 0.999
+    assert abs(float(loss) - float(ref_loss)) < 0.05 * max(1.0, abs(float(ref_loss)))
+    for k, p in clf.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    gw = dict(clf.named_parameters())["classifier.dense2.weight"].grad.cpu()
+    assert torch.nn.functional.cosine_similarity(gw.reshape(1, -1), sd["classifier.dense2.weight"].grad.reshape(1, -1)).item() > 0.99
