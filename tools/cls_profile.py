@@ -6,9 +6,11 @@ from vit_deep_radiomics_b200 import _C, synth
 from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier
 from vit_deep_radiomics_b200.train_models import FocalLoss
 dev = torch.device("cuda:0")
-ids, labels, sizes, cloud = synth.point_cloud_patients(16, d=256, n_range=(512, 4096), seed=1236)
+D = int(os.environ.get("CLS_D", "256"))
+NR = (int(os.environ.get("CLS_NMIN", "512")), int(os.environ.get("CLS_NMAX", "4096")))
+ids, labels, sizes, cloud = synth.point_cloud_patients(16, d=D, n_range=NR, seed=1236)
 torch.manual_seed(0)
-model = TransformerNoduleClassifier(256, 1024, 4, 2, 2).to(dev)
+model = TransformerNoduleClassifier(D, 4 * D, D // 64, 2, 2).to(dev)
 crit = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=dev), gamma=2)
 data = [(torch.from_numpy(cloud(i)).to(dev), torch.eye(2, device=dev)[int(labels[i])]) for i in range(16)]
 def run(sync):
@@ -37,4 +39,4 @@ with torch.no_grad():
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     run(False); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=16, max_name_column_width=60))

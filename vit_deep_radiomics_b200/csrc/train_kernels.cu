@@ -154,64 +154,68 @@ cls_concat_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dY, const floa
   }
 }
 
-// ---- classification head: zc = W1 cls + b1; hc = gelu(zc); logits = W2 hc + b2   (single CTA, fp32 weights)
+// ---- classification head (MLPLayer, models_archs.py:186-200): zc = W1 cls + b1; hc = gelu(zc); logits = W2 hc + b2, fp32 weights.
+// One warp per hidden unit, eight per CTA, H1 / 8 CTAs: W1 (d x H1 floats, 4.7 MB for d = 768) is streamed by the whole GPU
+// instead of by one CTA (0.7 ms -> a few microseconds).
+constexpr int kHeadWarps = 8;
+
+__global__ void __launch_bounds__(kHeadWarps * 32)
+cls_head_hidden_kernel(const __nv_bfloat16* __restrict__ cls, const float* __restrict__ W1, const float* __restrict__ b1,
+                       float* __restrict__ zc, int d, int H1) {
+  const int lane = threadIdx.x & 31, j = blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
+  if (j >= H1) return;
+  float acc = 0.f;
+  for (int c = lane; c < d; c += 32) acc = fmaf(__ldg(W1 + static_cast<int64_t>(j) * d + c), __bfloat162float(cls[c]), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) zc[j] = acc + b1[j];
+}
+
 __global__ void __launch_bounds__(256)
-cls_head_fwd_kernel(const __nv_bfloat16* __restrict__ cls, const float* __restrict__ W1, const float* __restrict__ b1,
-                    const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ zc,
-                    float* __restrict__ logits, int d, int H1, int C) {
-  extern __shared__ float sm[];      // [d] cls, [H1] hc
-  float* s_cls = sm;
-  float* s_h = sm + d;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) s_cls[c] = __bfloat162float(cls[c]);
-  __syncthreads();
+cls_head_out_kernel(const float* __restrict__ zc, const float* __restrict__ W2, const float* __restrict__ b2,
+                    float* __restrict__ logits, int H1, int C) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = warp; j < H1; j += nw) {
-    float acc = 0.f;
-    for (int c = lane; c < d; c += 32) acc += W1[static_cast<int64_t>(j) * d + c] * s_cls[c];
-    acc = warp_sum(acc) + b1[j];
-    if (lane == 0) { zc[j] = acc; s_h[j] = gelu_erf(acc); }
-  }
-  __syncthreads();
   for (int k = warp; k < C; k += nw) {
     float acc = 0.f;
-    for (int j = lane; j < H1; j += 32) acc += W2[static_cast<int64_t>(k) * H1 + j] * s_h[j];
-    acc = warp_sum(acc) + b2[k];
-    if (lane == 0) logits[k] = acc;
+    for (int j = lane; j < H1; j += 32) acc = fmaf(W2[static_cast<int64_t>(k) * H1 + j], gelu_erf(zc[j]), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) logits[k] = acc + b2[k];
   }
 }
 
-// Gradients are ACCUMULATED into dW1, db1, dW2, db2; dcls (d) is written: W1^T dzc + dcls_in.
+// Backward.  Gradients are ACCUMULATED into dW1, db1, dW2, db2; dcls (d) = W1^T dzc + dcls_in.
 __global__ void __launch_bounds__(256)
-cls_head_bwd_kernel(const __nv_bfloat16* __restrict__ cls, const float* __restrict__ W1, const float* __restrict__ W2,
-                    const float* __restrict__ zc, const float* __restrict__ dlogits, const float* __restrict__ dcls_in,
-                    float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2,
-                    float* __restrict__ dcls, int d, int H1, int C) {
-  extern __shared__ float sm[];      // [d] cls, [H1] dzc
-  float* s_cls = sm;
-  float* s_dz = sm + d;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) s_cls[c] = __bfloat162float(cls[c]);
-  for (int j = threadIdx.x; j < H1; j += blockDim.x) {
+cls_head_bwd_init_kernel(const float* __restrict__ dlogits, const float* __restrict__ dcls_in, float* __restrict__ db2,
+                         float* __restrict__ dcls, int d, int C) {
+  for (int c = threadIdx.x; c < d; c += blockDim.x) dcls[c] = dcls_in ? dcls_in[c] : 0.f;
+  if (static_cast<int>(threadIdx.x) < C) db2[threadIdx.x] += dlogits[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kHeadWarps * 32)
+cls_head_bwd_rows_kernel(const __nv_bfloat16* __restrict__ cls, const float* __restrict__ W1, const float* __restrict__ W2,
+                         const float* __restrict__ zc, const float* __restrict__ dlogits, float* __restrict__ dW1,
+                         float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ dcls, int d, int H1, int C) {
+  extern __shared__ float s_dcls[];   // [d] this CTA's partial W1^T dzc
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s_dcls[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, j = blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
+  if (j < H1) {
     const float z = zc[j], h = gelu_erf(z);
     float dh = 0.f;
     for (int k = 0; k < C; ++k) {
-      dh += W2[static_cast<int64_t>(k) * H1 + j] * dlogits[k];
-      dW2[static_cast<int64_t>(k) * H1 + j] += dlogits[k] * h;
+      const float dl = dlogits[k];
+      dh = fmaf(W2[static_cast<int64_t>(k) * H1 + j], dl, dh);
+      if (lane == 0) dW2[static_cast<int64_t>(k) * H1 + j] += dl * h;
     }
     const float dz = dh * gelu_grad(z);
-    s_dz[j] = dz;
-    db1[j] += dz;
+    if (lane == 0) db1[j] += dz;
+    for (int c = lane; c < d; c += 32) {
+      const int64_t e = static_cast<int64_t>(j) * d + c;
+      dW1[e] += dz * __bfloat162float(cls[c]);
+      atomicAdd(&s_dcls[c], __ldg(W1 + e) * dz);
+    }
   }
-  if (threadIdx.x < C) db2[threadIdx.x] += dlogits[threadIdx.x];
   __syncthreads();
-  for (int64_t e = threadIdx.x; e < static_cast<int64_t>(H1) * d; e += blockDim.x) {
-    const int j = static_cast<int>(e / d), c = static_cast<int>(e - static_cast<int64_t>(j) * d);
-    dW1[e] += s_dz[j] * s_cls[c];
-  }
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = dcls_in ? dcls_in[c] : 0.f;
-    for (int j = 0; j < H1; ++j) acc += W1[static_cast<int64_t>(j) * d + c] * s_dz[j];
-    dcls[c] = acc;
-  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dcls + c, s_dcls[c]);
 }
 
 static int ew_grid(int64_t n) {
@@ -302,10 +306,11 @@ extern "C" int vdr_cls_concat_layernorm_bwd(const void* dY, const float* X, cons
 extern "C" int vdr_cls_head_fwd(const void* cls_bf16, const float* W1, const float* b1, const float* W2, const float* b2,
                                 float* zc, float* logits, int d, int H1, int C, vdr_stream_t stream) {
   VDR_CHECK_ARG(cls_bf16 && W1 && b1 && W2 && b2 && zc && logits, VDR_EINVAL, "vdr_cls_head_fwd: null pointer");
-  VDR_CHECK_ARG(d > 0 && H1 > 0 && C > 0 && (size_t)(d + H1) * 4 <= 48 * 1024, VDR_EINVAL, "vdr_cls_head_fwd: bad shape");
-  cls_head_fwd_kernel<<<1, 256, (d + H1) * sizeof(float), S_(stream)>>>(static_cast<const __nv_bfloat16*>(cls_bf16), W1, b1, W2, b2, zc, logits, d, H1, C);
-  count_launch();
-  VDR_CHECK_LAUNCH("cls_head_fwd_kernel");
+  VDR_CHECK_ARG(d > 0 && H1 > 0 && C > 0, VDR_EINVAL, "vdr_cls_head_fwd: bad shape");
+  cls_head_hidden_kernel<<<(H1 + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, 0, S_(stream)>>>(static_cast<const __nv_bfloat16*>(cls_bf16), W1, b1, zc, d, H1);
+  cls_head_out_kernel<<<1, 256, 0, S_(stream)>>>(zc, W2, b2, logits, H1, C);
+  count_launch(2);
+  VDR_CHECK_LAUNCH("cls_head_fwd kernels");
   return VDR_OK;
 }
 
@@ -313,10 +318,11 @@ extern "C" int vdr_cls_head_bwd(const void* cls_bf16, const float* W1, const flo
                                 const float* dcls_in, float* dW1, float* db1, float* dW2, float* db2, float* dcls, int d,
                                 int H1, int C, vdr_stream_t stream) {
   VDR_CHECK_ARG(cls_bf16 && W1 && W2 && zc && dlogits && dW1 && db1 && dW2 && db2 && dcls, VDR_EINVAL, "vdr_cls_head_bwd: null pointer");
-  VDR_CHECK_ARG(d > 0 && H1 > 0 && C > 0 && C <= 256 && (size_t)(d + H1) * 4 <= 48 * 1024, VDR_EINVAL, "vdr_cls_head_bwd: bad shape");
-  cls_head_bwd_kernel<<<1, 256, (d + H1) * sizeof(float), S_(stream)>>>(static_cast<const __nv_bfloat16*>(cls_bf16), W1, W2, zc, dlogits, dcls_in,
-                                                                       dW1, db1, dW2, db2, dcls, d, H1, C);
-  count_launch();
-  VDR_CHECK_LAUNCH("cls_head_bwd_kernel");
+  VDR_CHECK_ARG(d > 0 && H1 > 0 && C > 0 && C <= 256 && (size_t)d * 4 <= 48 * 1024, VDR_EINVAL, "vdr_cls_head_bwd: bad shape");
+  cls_head_bwd_init_kernel<<<1, 256, 0, S_(stream)>>>(dlogits, dcls_in, db2, dcls, d, C);
+  cls_head_bwd_rows_kernel<<<(H1 + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, d * sizeof(float), S_(stream)>>>(
+      static_cast<const __nv_bfloat16*>(cls_bf16), W1, W2, zc, dlogits, dW1, db1, dW2, dcls, d, H1, C);
+  count_launch(2);
+  VDR_CHECK_LAUNCH("cls_head_bwd kernels");
   return VDR_OK;
 }
