@@ -283,6 +283,21 @@ int vdr_cls_head_bwd(const void* cls_bf16, const float* W1, const float* W2, con
                      const float* dcls_in, float* dW1, float* db1, float* dW2, float* db2, float* dcls,
                      int d, int H1, int C, vdr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Bimodal PET+CT classifier pieces (TransformerNoduleBimodalClassifier, models_archs.py:38-124).
+ * Linear layer on one f32 vector: y = W x + b (W (rows, cols) row-major); backward ACCUMULATES dW, db (optional) and dx. */
+int vdr_linear_vec_fwd(const float* W, const float* b, const float* x, float* y, int rows, int cols, vdr_stream_t stream);
+int vdr_linear_vec_bwd(const float* W, const float* x, const float* dy, float* dW, float* db, float* dx, int rows, int cols,
+                       vdr_stream_t stream);
+/* Cross attention of CrossAttentionLayer (:174-183) for the single query row the model keeps (`x_attn[:, 0, :]`, :102-103):
+ * q0 (d) f32 = projected CLS query; kv (n, 2d) bf16 = [K | V] projections of the other modality's tokens; head_dim 64.
+ * fwd: p (heads, n) f32 = softmax(q0_h K_h^T scale) (saved), o (d) f32 = p V.  bwd: dq0 (d) f32, dkv (n, 2d) bf16
+ * (scratch: heads * n floats). */
+int vdr_cross_cls_attn_fwd(const float* q0, const void* kv, int64_t ld_kv, int n, int heads, float scale, float* p, float* o,
+                           vdr_stream_t stream);
+int vdr_cross_cls_attn_bwd(const float* q0, const void* kv, int64_t ld_kv, const float* p, const float* d_o, int n, int heads,
+                           float scale, float* dq0, void* dkv, int64_t ld_dkv, float* scratch, vdr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

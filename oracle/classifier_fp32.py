@@ -96,3 +96,74 @@ def init_state_dict(input_dim=256, dim_feedforward=1024, num_classes=2, num_laye
     sd["classifier.dense2.weight"] = rn(num_classes, 2 * d, std=1 / math.sqrt(2 * d))
     sd["classifier.dense2.bias"] = rn(num_classes, std=0.02)
     return sd
+
+
+def _encoder(sd, prefix_cls, prefix_norm, prefix_enc, x, num_heads, num_layers):
+    """cat(cls, x) -> LayerNorm -> post-norm encoder layers (the body of classifier_forward with the bimodal key prefixes)."""
+    B, n, d = x.shape
+    hd = d // num_heads
+    t = torch.cat([sd[prefix_cls].expand(B, 1, d), x], dim=1)
+    t = F.layer_norm(t, (d,), sd[prefix_norm + ".weight"], sd[prefix_norm + ".bias"], eps=1e-5)
+    N = n + 1
+    for i in range(num_layers):
+        p = f"{prefix_enc}.layers.{i}."
+        qkv = F.linear(t, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"])
+        q, k, v = qkv.split(d, dim=-1)
+        q = q.reshape(B, N, num_heads, hd).transpose(1, 2)
+        k = k.reshape(B, N, num_heads, hd).transpose(1, 2)
+        v = v.reshape(B, N, num_heads, hd).transpose(1, 2)
+        a = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+        o = (a @ v).transpose(1, 2).reshape(B, N, d)
+        o = F.linear(o, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+        t = F.layer_norm(t + o, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps=1e-5)
+        y = F.gelu(F.linear(t, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))
+        y = F.linear(y, sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+        t = F.layer_norm(t + y, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps=1e-5)
+    return t
+
+
+def _mlp(sd, prefix, x):
+    return F.linear(F.gelu(F.linear(x, sd[prefix + ".dense1.weight"], sd[prefix + ".dense1.bias"])),
+                    sd[prefix + ".dense2.weight"], sd[prefix + ".dense2.bias"])
+
+
+def _cross(sd, prefix, q_in, kv_in, num_heads):
+    """nn.MultiheadAttention(batch_first) restated: packed in_proj, per-head softmax(q k^T / sqrt(hd)) v, out_proj."""
+    d = q_in.shape[-1]
+    hd = d // num_heads
+    w, b = sd[prefix + ".multihead_attn.in_proj_weight"], sd[prefix + ".multihead_attn.in_proj_bias"]
+    q = F.linear(q_in, w[:d], b[:d])
+    k = F.linear(kv_in, w[d:2 * d], b[d:2 * d])
+    v = F.linear(kv_in, w[2 * d:], b[2 * d:])
+    B, Nq, Nk = q.shape[0], q.shape[1], k.shape[1]
+    q = q.reshape(B, Nq, num_heads, hd).transpose(1, 2)
+    k = k.reshape(B, Nk, num_heads, hd).transpose(1, 2)
+    v = v.reshape(B, Nk, num_heads, hd).transpose(1, 2)
+    a = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    o = (a @ v).transpose(1, 2).reshape(B, Nq, d)
+    return F.linear(o, sd[prefix + ".multihead_attn.out_proj.weight"], sd[prefix + ".multihead_attn.out_proj.bias"])
+
+
+def bimodal_forward(sd: dict, x_ct, x_pet, heads_ct, heads_pet, layers_ct, layers_pet):
+    """reference: src/models_archs.py:76-124 (TransformerNoduleBimodalClassifier.forward), dropout inactive.
+    Returns (logits_petct, petct_cls_token, logits_ct, logits_pet)."""
+    use_ct, use_pet = x_ct is not None, x_pet is not None
+    assert use_ct or use_pet
+    if use_ct:
+        t_ct = _encoder(sd, "cls_token_ct", "norm_ct", "transformer_encoder_ct", x_ct, heads_ct, layers_ct)
+        ct_cls = t_ct[:, 0, :]
+    if use_pet:
+        t_pet = _encoder(sd, "cls_token_pet", "norm_pet", "transformer_encoder_pet", x_pet, heads_pet, layers_pet)
+        pet_cls = t_pet[:, 0, :]
+    if use_ct and use_pet:
+        ct_cls = _cross(sd, "cross_attention_ct", t_ct, t_pet, heads_ct)[:, 0, :]            # :100-103
+        pet_cls = _cross(sd, "cross_attention_pet", t_pet, t_ct, heads_ct)[:, 0, :]          # built with num_heads_ct (:71)
+        logits_ct = _mlp(sd, "classifier_ct", ct_cls)
+        logits_pet = _mlp(sd, "classifier_pet", pet_cls)
+        z = _mlp(sd, "projection_petct", torch.cat([ct_cls, pet_cls], dim=1))
+        return _mlp(sd, "classifier_petct", z), z, logits_ct, logits_pet
+    if use_ct:
+        lg = _mlp(sd, "classifier_ct", ct_cls)
+        return lg, ct_cls, lg, lg
+    lg = _mlp(sd, "classifier_pet", pet_cls)
+    return lg, pet_cls, lg, lg

@@ -181,9 +181,45 @@ def golden_classifier():
     print("classifier_small.npz")
 
 
+def golden_bimodal():
+    """TransformerNoduleBimodalClassifier (models_archs.py:38-124), eval mode: outputs and gradients for both modalities and
+    for each modality alone; loss = sum of the three logit heads' focal losses + 0.1 * sum(petct_cls) so every path has gradient."""
+    ma = ref_shim.load_reference("models_archs")
+    tm = ref_shim.load_reference("train_models")
+    torch.manual_seed(123)
+    d = 64
+    model = ma.TransformerNoduleBimodalClassifier(d, 2, 2, 1, 1, 1, 2, 2).eval()
+    with torch.no_grad():
+        for n_, p in model.named_parameters():
+            if "norm" in n_:
+                p.add_(0.05 * torch.randn_like(p))
+            elif n_.endswith("bias"):
+                p.add_(0.02 * torch.randn_like(p))
+    x_ct, x_pet = torch.randn(1, 29, d), torch.randn(1, 41, d)
+    y = torch.tensor([1.0, 0.0])
+    crit = tm.FocalLoss(alpha=torch.tensor([0.25, 0.75]), gamma=2)
+    cases = {"x_ct": x_ct.numpy(), "x_pet": x_pet.numpy(), "y": y.numpy(), "cfg": np.array([d, 2, 2, 1, 1, 1, 2, 2])}
+    for n_, p in model.named_parameters():
+        cases["param__" + n_] = p.detach().numpy()
+    for mode, (a, b) in {"both": (x_ct, x_pet), "ct": (x_ct, None), "pet": (None, x_pet)}.items():
+        model.zero_grad()
+        lg, z, lg_ct, lg_pet = model(a, b)
+        loss = crit(torch.squeeze(lg), y) + crit(torch.squeeze(lg_ct), y) + crit(torch.squeeze(lg_pet), y) + 0.1 * z.sum()
+        loss.backward()
+        cases[f"{mode}__logits"], cases[f"{mode}__z"] = lg.detach().numpy(), z.detach().numpy()
+        cases[f"{mode}__logits_ct"], cases[f"{mode}__logits_pet"] = lg_ct.detach().numpy(), lg_pet.detach().numpy()
+        cases[f"{mode}__loss"] = loss.detach().numpy()
+        for n_, p in model.named_parameters():
+            if p.grad is not None:
+                cases[f"{mode}__grad__" + n_] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "bimodal_small.npz"), **cases)
+    print("bimodal_small.npz")
+
+
 if __name__ == "__main__":
     assert ref_shim.reference_available(), "needs /root/reference"
     golden_gather()
     golden_pointcloud()
     golden_geometry()
     golden_classifier()
+    golden_bimodal()

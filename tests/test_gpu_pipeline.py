@@ -309,3 +309,46 @@ def test_c5_extraction_feeds_classifier_training_step(cuda):
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
     gw = dict(clf.named_parameters())["classifier.dense2.weight"].grad.cpu()
     assert torch.nn.functional.cosine_similarity(gw.reshape(1, -1), sd["classifier.dense2.weight"].grad.reshape(1, -1)).item() > 0.99
+
+
+@pytest.mark.parametrize("mode", ["both", "ct", "pet"])
+def test_bimodal_classifier_vs_golden(cuda, golden_dir, mode):
+    """TransformerNoduleBimodalClassifier (scope row N4) through the kernels against the reference's own outputs and gradients
+    (tests/golden/bimodal_small.npz, frozen from the unmodified module): both modalities (cross attention) and each one alone."""
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleBimodalClassifier
+    from vit_deep_radiomics_b200.train_models import FocalLoss
+    g = np.load(os.path.join(golden_dir, "bimodal_small.npz"))
+    model = TransformerNoduleBimodalClassifier(*[int(v) for v in g["cfg"]])
+    model.load_state_dict({k[len("param__"):]: torch.tensor(g[k]) for k in g.files if k.startswith("param__")})
+    model = model.to(cuda).train()
+    x_ct = torch.tensor(g["x_ct"]).to(cuda) if mode in ("both", "ct") else None
+    x_pet = torch.tensor(g["x_pet"]).to(cuda) if mode in ("both", "pet") else None
+    y = torch.tensor(g["y"]).to(cuda)
+    crit = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=cuda), gamma=2)
+    lg, z, lg_ct, lg_pet = model(x_ct, x_pet)
+    assert lg.shape == (1, 2) and z.shape == (1, int(g["cfg"][0]))
+    for got, key in ((lg, "logits"), (lg_ct, "logits_ct"), (lg_pet, "logits_pet")):
+        assert np.abs(got.detach().cpu().numpy() - g[f"{mode}__{key}"]).max() < 0.04, key
+    zc, zw = z.detach().cpu().numpy()[0].astype(np.float64), g[f"{mode}__z"].reshape(-1).astype(np.float64)
+    assert (zc * zw).sum() / (np.linalg.norm(zc) * np.linalg.norm(zw)) > 0.999
+    loss = crit(torch.squeeze(lg), y) + crit(torch.squeeze(lg_ct), y) + crit(torch.squeeze(lg_pet), y) + 0.1 * z.sum()
+    assert abs(loss.item() - float(g[f"{mode}__loss"])) < 0.05
+    loss.backward()
+    checked = 0
+    for name, p in model.named_parameters():
+        key = f"{mode}__grad__{name}"
+        if key not in g.files:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name      # parameter not on this mode's path
+            continue
+        want = torch.tensor(g[key]).double().flatten()
+        assert p.grad is not None, name
+        got = p.grad.detach().cpu().double().flatten()
+        assert torch.isfinite(got).all(), name
+        if want.norm() < 1e-7:
+            assert got.norm() < 1e-4, name
+            continue
+        cos = float((got @ want) / (got.norm() * want.norm()))
+        rel = float((got - want).norm() / want.norm())
+        assert cos > 0.99 and rel < 0.15, (name, cos, rel)
+        checked += 1
+    assert checked >= 15

@@ -100,3 +100,24 @@ def test_focal_loss_golden(golden_dir):
     assert abs(C.focal_loss(lg, tg, 2.0, None).item() - float(g["focal__loss_noalpha"])) < 1e-6
     single = [C.focal_loss(lg[i], tg[i], 2.0, a).item() for i in range(6)]
     assert np.allclose(single, g["focal__loss_single"], atol=1e-6)
+
+
+def test_bimodal_oracle_against_golden(golden_dir):
+    """The bimodal restatement reproduces the reference's frozen outputs AND gradients (tests/golden/bimodal_small.npz)."""
+    import torch
+    from oracle import classifier_fp32 as C
+    g = np.load(os.path.join(golden_dir, "bimodal_small.npz"))
+    d, _, _, h_ct, h_pet, l_ct, l_pet, _ = (int(v) for v in g["cfg"])
+    x_ct, x_pet, y = torch.from_numpy(g["x_ct"]), torch.from_numpy(g["x_pet"]), torch.from_numpy(g["y"])
+    alpha = torch.tensor([0.25, 0.75])
+    for mode, (a, b) in {"both": (x_ct, x_pet), "ct": (x_ct, None), "pet": (None, x_pet)}.items():
+        sd = {k[7:]: torch.from_numpy(g[k]).clone().requires_grad_(True) for k in g.files if k.startswith("param__")}
+        lg, z, lg_ct, lg_pet = C.bimodal_forward(sd, a, b, h_ct, h_pet, l_ct, l_pet)
+        loss = C.focal_loss(lg[0], y, 2.0, alpha) + C.focal_loss(lg_ct[0], y, 2.0, alpha) + C.focal_loss(lg_pet[0], y, 2.0, alpha) + 0.1 * z.sum()
+        loss.backward()
+        assert np.allclose(lg.detach().numpy(), g[f"{mode}__logits"], atol=1e-5)
+        assert np.allclose(z.detach().numpy().reshape(-1), g[f"{mode}__z"].reshape(-1), atol=1e-5)
+        assert abs(float(loss) - float(g[f"{mode}__loss"])) < 1e-5
+        for k in g.files:
+            if k.startswith(f"{mode}__grad__"):
+                assert np.allclose(sd[k[len(mode) + 8:]].grad.numpy(), g[k], atol=2e-5), k

@@ -63,3 +63,18 @@ def test_classifier_against_reference_module():
         want_l, want_c = model(x)
         got_l, got_c = C.classifier_forward(dict(model.state_dict()), x, 2, 2)
     assert torch.allclose(want_l, got_l, atol=1e-5) and torch.allclose(want_c, got_c, atol=1e-5)
+
+
+def test_bimodal_classifier_against_reference_module():
+    """oracle/classifier_fp32.bimodal_forward vs the UNMODIFIED TransformerNoduleBimodalClassifier (eval mode), all three input modes."""
+    ma = ref_shim.load_reference("models_archs")
+    torch.manual_seed(4)
+    model = ma.TransformerNoduleBimodalClassifier(128, 2, 3, 2, 2, 2, 1, 2).eval()
+    x_ct, x_pet = torch.randn(1, 30, 128), torch.randn(1, 45, 128)
+    sd = dict(model.state_dict())
+    with torch.no_grad():
+        for a, b in ((x_ct, x_pet), (x_ct, None), (None, x_pet)):
+            want = model(a, b)
+            got = C.bimodal_forward(sd, a, b, 2, 2, 2, 1)
+            for w, g in zip(want, got):
+                assert torch.allclose(w.reshape(g.shape), g, atol=1e-5)

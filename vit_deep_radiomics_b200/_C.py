@@ -24,6 +24,7 @@ EXPORTS = (
     "vdr_voxel_bbox", "vdr_mask_bbox", "vdr_voxel_gather",
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
     "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
+    "vdr_linear_vec_fwd", "vdr_linear_vec_bwd", "vdr_cross_cls_attn_fwd", "vdr_cross_cls_attn_bwd",
 )
 
 
@@ -111,6 +112,10 @@ def lib() -> C.CDLL:
     L.vdr_cls_concat_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.vdr_cls_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     L.vdr_cls_head_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    L.vdr_linear_vec_fwd.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.vdr_linear_vec_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    L.vdr_cross_cls_attn_fwd.argtypes = [vp, vp, i64, i32, i32, f32, vp, vp, vp]
+    L.vdr_cross_cls_attn_bwd.argtypes = [vp, vp, i64, vp, vp, i32, i32, f32, vp, vp, i64, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("vdr_version", "vdr_last_error_string", "vdr_launch_count",

@@ -56,11 +56,13 @@ def _f32(p):
     return p.detach().contiguous()
 
 
-def classifier_forward(x, num_heads, num_layers, params, save=False):
-    """x (n, d) f32 CUDA.  Returns (logits (C,) f32, cls (d,) f32[, saved activations])."""
+def encoder_forward(x, num_heads, num_layers, enc_params, save=False):
+    """CLS-concat + LayerNorm + `num_layers` post-norm encoder layers.  x (n, d) f32 CUDA; enc_params = [cls_token, norm.weight,
+    norm.bias] + 12 tensors per layer (PARAM_ORDER of models_archs.param_list).  Returns y (n + 1, d) bf16 (row 0 = CLS)
+    [, saved activations]."""
     n, d = x.shape
     N = n + 1
-    it = iter(params)
+    it = iter(enc_params)
     cls_tok, norm_w, norm_b = next(it), next(it), next(it)
     x = x.contiguous()
     cls_vec = _f32(cls_tok).reshape(d)
@@ -94,11 +96,21 @@ def classifier_forward(x, num_heads, num_layers, params, save=False):
         else:
             y2 = ops.layernorm(u, _f32(n2w), _f32(n2b), 1e-5)
         y = y2
-    wd1, bd1, wd2, bd2 = next(it), next(it), next(it), next(it)
+    if save:
+        saved.update(layers=layers, x=x)
+        return y, saved
+    return y
+
+
+def classifier_forward(x, num_heads, num_layers, params, save=False):
+    """x (n, d) f32 CUDA.  Returns (logits (C,) f32, cls (d,) f32[, saved activations])."""
+    enc = encoder_forward(x, num_heads, num_layers, params[:-4], save=save)
+    y, saved = enc if save else (enc, None)
+    wd1, bd1, wd2, bd2 = params[-4:]
     logits, zc = ops.cls_head_fwd(y[0], _f32(wd1), _f32(bd1), _f32(wd2), _f32(bd2))
     cls = y[0].float()
     if save:
-        saved.update(layers=layers, y_last=y, zc=zc, x=x)
+        saved.update(y_last=y, zc=zc)
         return logits, cls, saved
     return logits, cls
 
@@ -138,34 +150,21 @@ def attention_backward_materialised(qkv, a, da, lse, heads):
     return dqkv
 
 
-def classifier_backward(num_heads, num_layers, params, saved, d_logits, d_cls):
-    """Gradients for every parameter, in ``params`` order (f32)."""
-    dev = params[0].device
+def encoder_backward(num_heads, num_layers, enc_params, saved, dy):
+    """Gradients of encoder_forward's parameters (in enc_params order, f32) from dy (n + 1, d) bf16, the gradient of its
+    output rows (the unimodal classifier only feeds the CLS row; the bimodal model's cross attention feeds every row)."""
+    dev = enc_params[0].device
     x = saved["x"]
     n, d = x.shape
-    N = n + 1
-    g = [None] * len(params)
+    g = [None] * len(enc_params)
 
     def zeros_like_param(i):
-        g[i] = torch.zeros(params[i].shape, dtype=torch.float32, device=dev)
+        g[i] = torch.zeros(enc_params[i].shape, dtype=torch.float32, device=dev)
         return g[i]
 
-    # ---- head
-    iw1 = len(params) - 4
-    wd1, wd2 = params[iw1], params[iw1 + 2]
-    y_last = saved["y_last"]
-    dlog = d_logits.detach().float().contiguous() if d_logits is not None else torch.zeros(wd2.shape[0], device=dev)
-    dcls_in = d_cls.detach().float().contiguous() if d_cls is not None else None
-    dcls = ops.cls_head_bwd(y_last[0], _f32(wd1), _f32(wd2), saved["zc"], dlog, dcls_in,
-                            zeros_like_param(iw1), zeros_like_param(iw1 + 1), zeros_like_param(iw1 + 2),
-                            zeros_like_param(iw1 + 3))
-    dy = torch.zeros((N, d), dtype=torch.bfloat16, device=dev)          # only the CLS row carries gradient
-    dy[0] = dcls.to(torch.bfloat16)
-
-    # ---- encoder layers, last to first
     for l in reversed(range(num_layers)):
         base = 3 + 12 * l
-        (w_in, b_in, w_o, b_o, n1w, n1b, w1, b1, w2, b2, n2w, n2b) = params[base:base + 12]
+        (w_in, b_in, w_o, b_o, n1w, n1b, w1, b1, w2, b2, n2w, n2b) = enc_params[base:base + 12]
         s = saved["layers"][l]
         du = ops.layernorm_bwd(dy, s["u"], _f32(n2w), s["mu2"], s["rs2"], zeros_like_param(base + 10), zeros_like_param(base + 11))
         ops.colsum_accum(du, zeros_like_param(base + 9))
@@ -188,10 +187,32 @@ def classifier_backward(num_heads, num_layers, params, saved, d_logits, d_cls):
     # ---- input LayerNorm + CLS token
     mu0, rs0 = saved["ln0"]
     g_cls = torch.zeros(d, dtype=torch.float32, device=dev)
-    ops.cls_concat_layernorm_bwd(dy, x, _f32(params[0]).reshape(d), _f32(params[1]), mu0, rs0,
+    ops.cls_concat_layernorm_bwd(dy, x, _f32(enc_params[0]).reshape(d), _f32(enc_params[1]), mu0, rs0,
                                  zeros_like_param(1), zeros_like_param(2), g_cls)
-    g[0] = g_cls.reshape(params[0].shape)
+    g[0] = g_cls.reshape(enc_params[0].shape)
     return g
+
+
+def head_backward(y_cls_bf16, head_params, zc, d_logits, d_cls_in):
+    """MLPLayer head backward: returns (grads of [W1, b1, W2, b2], d(input vector) f32)."""
+    wd1, bd1, wd2, bd2 = head_params
+    dev = wd1.device
+    gs = [torch.zeros(p.shape, dtype=torch.float32, device=dev) for p in head_params]
+    dlog = d_logits.detach().float().contiguous() if d_logits is not None else torch.zeros(wd2.shape[0], device=dev)
+    dcls_in = d_cls_in.detach().float().contiguous() if d_cls_in is not None else None
+    dvec = ops.cls_head_bwd(y_cls_bf16, _f32(wd1), _f32(wd2), zc, dlog, dcls_in, gs[0], gs[1], gs[2], gs[3])
+    return gs, dvec
+
+
+def classifier_backward(num_heads, num_layers, params, saved, d_logits, d_cls):
+    """Gradients for every parameter, in ``params`` order (f32)."""
+    dev = params[0].device
+    n, d = saved["x"].shape
+    y_last = saved["y_last"]
+    g_head, dcls = head_backward(y_last[0], params[-4:], saved["zc"], d_logits, d_cls)
+    dy = torch.zeros((n + 1, d), dtype=torch.bfloat16, device=dev)          # only the CLS row carries gradient
+    dy[0] = dcls.to(torch.bfloat16)
+    return encoder_backward(num_heads, num_layers, params[:-4], saved, dy) + g_head
 
 
 class ClassifierFunction(torch.autograd.Function):

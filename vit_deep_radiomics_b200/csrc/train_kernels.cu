@@ -218,6 +218,152 @@ cls_head_bwd_rows_kernel(const __nv_bfloat16* __restrict__ cls, const float* __r
   for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dcls + c, s_dcls[c]);
 }
 
+// ---- bimodal classifier pieces (models_archs.py:76-124): plain Linear on one vector, and the cross attention of
+// CrossAttentionLayer (:174-183, nn.MultiheadAttention) evaluated for the ONE query row the model keeps (`x_attn[:, 0, :]`).
+__global__ void __launch_bounds__(kHeadWarps * 32)
+linear_vec_fwd_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x, float* __restrict__ y,
+                      int rows, int cols) {
+  const int lane = threadIdx.x & 31, j = blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
+  if (j >= rows) return;
+  float acc = 0.f;
+  for (int c = lane; c < cols; c += 32) acc = fmaf(__ldg(W + static_cast<int64_t>(j) * cols + c), x[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[j] = acc + (b ? b[j] : 0.f);
+}
+
+// dW += dy x^T, db += dy, dx += W^T dy   (dx is ACCUMULATED: zero it or seed it with another path's gradient first)
+__global__ void __launch_bounds__(kHeadWarps * 32)
+linear_vec_bwd_kernel(const float* __restrict__ W, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dW,
+                      float* __restrict__ db, float* __restrict__ dx, int rows, int cols) {
+  extern __shared__ float s_dx[];   // [cols]
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) s_dx[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, j = blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
+  if (j < rows) {
+    const float g = dy[j];
+    if (lane == 0 && db) db[j] += g;
+    for (int c = lane; c < cols; c += 32) {
+      const int64_t e = static_cast<int64_t>(j) * cols + c;
+      dW[e] += g * x[c];
+      atomicAdd(&s_dx[c], __ldg(W + e) * g);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) atomicAdd(dx + c, s_dx[c]);
+}
+
+__device__ __forceinline__ float block_reduce(float v, float* scratch, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int i = 0; i < nw; ++i) r = is_max ? fmaxf(r, scratch[i]) : r + scratch[i];
+  return r;
+}
+
+// One CTA per head: p = softmax(q0_h . K_h^T * scale) over the n keys, o_h = p V_h.  kv: (n, 2d) bf16 = [K | V] as the
+// in-projection GEMM writes it.  p (heads, n) f32 is kept for the backward.
+__global__ void __launch_bounds__(256)
+cross_cls_attn_fwd_kernel(const float* __restrict__ q0, const __nv_bfloat16* __restrict__ kv, int64_t ld, int n, int d, float scale,
+                          float* __restrict__ p_out, float* __restrict__ o) {
+  __shared__ float s_q[64], s_red[8], s_o[4][64];
+  const int h = blockIdx.x, tid = threadIdx.x;
+  if (tid < 64) s_q[tid] = q0[h * 64 + tid] * scale;
+  __syncthreads();
+  float* p = p_out + static_cast<int64_t>(h) * n;
+  float mx = -INFINITY;
+  for (int k = tid; k < n; k += blockDim.x) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kv + static_cast<int64_t>(k) * ld + h * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(kr + c);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      const float* q = s_q + c * 8;
+      acc += q[0] * a0.x + q[1] * a0.y + q[2] * a1.x + q[3] * a1.y + q[4] * a2.x + q[5] * a2.y + q[6] * a3.x + q[7] * a3.y;
+    }
+    p[k] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = block_reduce(mx, s_red, true);
+  float sum = 0.f;
+  for (int k = tid; k < n; k += blockDim.x) {
+    const float e = __expf(p[k] - mx);
+    p[k] = e;
+    sum += e;
+  }
+  sum = block_reduce(sum, s_red, false);
+  const float inv = 1.f / sum;
+  for (int k = tid; k < n; k += blockDim.x) p[k] *= inv;
+  __syncthreads();
+  // o_h[dd] = sum_k p_k V[k][dd]: 64 dims x 4 key partitions
+  const int dd = tid & 63, part = tid >> 6;
+  float acc = 0.f;
+  for (int k = part; k < n; k += 4) acc = fmaf(p[k], __bfloat162float(kv[static_cast<int64_t>(k) * ld + d + h * 64 + dd]), acc);
+  s_o[part][dd] = acc;
+  __syncthreads();
+  if (tid < 64) o[h * 64 + tid] = s_o[0][tid] + s_o[1][tid] + s_o[2][tid] + s_o[3][tid];
+}
+
+// Backward of the above: given do (d): dV_k = p_k do_h, dp_k = V_k . do_h, ds_k = p_k (dp_k - sum_j p_j dp_j) scale,
+// dq0_h = sum_k ds_k K_k, dK_k = ds_k q0_h.  dkv (n, 2d) bf16 is written, dq0 (d) f32 is written.
+__global__ void __launch_bounds__(256)
+cross_cls_attn_bwd_kernel(const float* __restrict__ q0, const __nv_bfloat16* __restrict__ kv, int64_t ld, const float* __restrict__ p_in,
+                          const float* __restrict__ d_o, int n, int d, float scale, float* __restrict__ dq0,
+                          __nv_bfloat16* __restrict__ dkv, int64_t ld_dkv, float* __restrict__ dp_scratch) {
+  __shared__ float s_q[64], s_do[64], s_red[8], s_dq[4][64];
+  const int h = blockIdx.x, tid = threadIdx.x;
+  if (tid < 64) { s_q[tid] = q0[h * 64 + tid]; s_do[tid] = d_o[h * 64 + tid]; }
+  __syncthreads();
+  const float* p = p_in + static_cast<int64_t>(h) * n;
+  float* dp = dp_scratch + static_cast<int64_t>(h) * n;
+  float c_acc = 0.f;
+  for (int k = tid; k < n; k += blockDim.x) {
+    const uint4* vr = reinterpret_cast<const uint4*>(kv + static_cast<int64_t>(k) * ld + d + h * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(vr + c);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      const float* g = s_do + c * 8;
+      acc += g[0] * a0.x + g[1] * a0.y + g[2] * a1.x + g[3] * a1.y + g[4] * a2.x + g[5] * a2.y + g[6] * a3.x + g[7] * a3.y;
+    }
+    dp[k] = acc;
+    c_acc = fmaf(p[k], acc, c_acc);
+  }
+  c_acc = block_reduce(c_acc, s_red, false);
+  // per key: ds, dK row, dV row (each thread writes the two 128-byte rows of its keys)
+  for (int k = tid; k < n; k += blockDim.x) {
+    const float pk = p[k], ds = pk * (dp[k] - c_acc) * scale;
+    dp[k] = ds;
+    __nv_bfloat16* dk = dkv + static_cast<int64_t>(k) * ld_dkv + h * 64;
+    __nv_bfloat16* dv = dkv + static_cast<int64_t>(k) * ld_dkv + d + h * 64;
+#pragma unroll
+    for (int c = 0; c < 64; c += 8) {
+      uint4 a, b;
+      a.x = pack_bf16x2(ds * s_q[c], ds * s_q[c + 1]); a.y = pack_bf16x2(ds * s_q[c + 2], ds * s_q[c + 3]);
+      a.z = pack_bf16x2(ds * s_q[c + 4], ds * s_q[c + 5]); a.w = pack_bf16x2(ds * s_q[c + 6], ds * s_q[c + 7]);
+      b.x = pack_bf16x2(pk * s_do[c], pk * s_do[c + 1]); b.y = pack_bf16x2(pk * s_do[c + 2], pk * s_do[c + 3]);
+      b.z = pack_bf16x2(pk * s_do[c + 4], pk * s_do[c + 5]); b.w = pack_bf16x2(pk * s_do[c + 6], pk * s_do[c + 7]);
+      *reinterpret_cast<uint4*>(dk + c) = a;
+      *reinterpret_cast<uint4*>(dv + c) = b;
+    }
+  }
+  __syncthreads();
+  const int dd = tid & 63, part = tid >> 6;
+  float acc = 0.f;
+  for (int k = part; k < n; k += 4) acc = fmaf(dp[k], __bfloat162float(kv[static_cast<int64_t>(k) * ld + h * 64 + dd]), acc);
+  s_dq[part][dd] = acc;
+  __syncthreads();
+  if (tid < 64) dq0[h * 64 + tid] = s_dq[0][tid] + s_dq[1][tid] + s_dq[2][tid] + s_dq[3][tid];
+}
+
 static int ew_grid(int64_t n) {
   int64_t b = (n + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -324,5 +470,44 @@ extern "C" int vdr_cls_head_bwd(const void* cls_bf16, const float* W1, const flo
       static_cast<const __nv_bfloat16*>(cls_bf16), W1, W2, zc, dlogits, dW1, db1, dW2, dcls, d, H1, C);
   count_launch(2);
   VDR_CHECK_LAUNCH("cls_head_bwd kernels");
+  return VDR_OK;
+}
+
+extern "C" int vdr_linear_vec_fwd(const float* W, const float* b, const float* x, float* y, int rows, int cols, vdr_stream_t stream) {
+  VDR_CHECK_ARG(W && x && y && rows > 0 && cols > 0, VDR_EINVAL, "vdr_linear_vec_fwd: bad arguments");
+  linear_vec_fwd_kernel<<<(rows + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, 0, S_(stream)>>>(W, b, x, y, rows, cols);
+  count_launch();
+  VDR_CHECK_LAUNCH("linear_vec_fwd_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_linear_vec_bwd(const float* W, const float* x, const float* dy, float* dW, float* db, float* dx, int rows, int cols,
+                                  vdr_stream_t stream) {
+  VDR_CHECK_ARG(W && x && dy && dW && dx && rows > 0 && cols > 0 && (size_t)cols * 4 <= 48 * 1024, VDR_EINVAL, "vdr_linear_vec_bwd: bad arguments");
+  linear_vec_bwd_kernel<<<(rows + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, cols * sizeof(float), S_(stream)>>>(W, x, dy, dW, db, dx, rows, cols);
+  count_launch();
+  VDR_CHECK_LAUNCH("linear_vec_bwd_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_cross_cls_attn_fwd(const float* q0, const void* kv, int64_t ld_kv, int n, int heads, float scale, float* p, float* o,
+                                      vdr_stream_t stream) {
+  VDR_CHECK_ARG(q0 && kv && p && o && n > 0 && heads > 0 && ld_kv >= 2 * heads * 64 && ld_kv % 8 == 0 && aligned16(kv), VDR_EINVAL,
+                "vdr_cross_cls_attn_fwd: bad arguments");
+  cross_cls_attn_fwd_kernel<<<heads, 256, 0, S_(stream)>>>(q0, static_cast<const __nv_bfloat16*>(kv), ld_kv, n, heads * 64, scale, p, o);
+  count_launch();
+  VDR_CHECK_LAUNCH("cross_cls_attn_fwd_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_cross_cls_attn_bwd(const float* q0, const void* kv, int64_t ld_kv, const float* p, const float* d_o, int n, int heads,
+                                      float scale, float* dq0, void* dkv, int64_t ld_dkv, float* scratch, vdr_stream_t stream) {
+  VDR_CHECK_ARG(q0 && kv && p && d_o && dq0 && dkv && scratch && n > 0 && heads > 0, VDR_EINVAL, "vdr_cross_cls_attn_bwd: bad arguments");
+  VDR_CHECK_ARG(ld_kv >= 2 * heads * 64 && ld_kv % 8 == 0 && ld_dkv >= 2 * heads * 64 && ld_dkv % 8 == 0 && aligned16(kv) && aligned16(dkv), VDR_EALIGN,
+                "vdr_cross_cls_attn_bwd: kv / dkv must be 16-byte aligned with leading dimensions that are multiples of 8");
+  cross_cls_attn_bwd_kernel<<<heads, 256, 0, S_(stream)>>>(q0, static_cast<const __nv_bfloat16*>(kv), ld_kv, p, d_o, n, heads * 64, scale, dq0,
+                                                           static_cast<__nv_bfloat16*>(dkv), ld_dkv, scratch);
+  count_launch();
+  VDR_CHECK_LAUNCH("cross_cls_attn_bwd_kernel");
   return VDR_OK;
 }

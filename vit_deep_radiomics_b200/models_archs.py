@@ -18,6 +18,7 @@ import os
 import torch
 import torch.nn as nn
 
+from . import bimodal_kernels as bk
 from . import classifier_kernels as ck
 
 
@@ -100,3 +101,86 @@ class TransformerNoduleClassifier(nn.Module):
             logits.append(lg)
             cls.append(c)
         return torch.stack(logits, 0), torch.stack(cls, 0)
+
+
+class CrossAttentionLayer(nn.Module):
+    """Parameter container for the reference's CrossAttentionLayer (:174-183)."""
+
+    def __init__(self, input_dim, num_heads):
+        super().__init__()
+        self.multihead_attn = nn.MultiheadAttention(embed_dim=input_dim, num_heads=num_heads, batch_first=True)
+
+
+def _encoder_params(cls_token, norm, encoder):
+    ps = [cls_token, norm.weight, norm.bias]
+    for lyr in encoder.layers:
+        ps += [lyr.self_attn.in_proj_weight, lyr.self_attn.in_proj_bias, lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias,
+               lyr.norm1.weight, lyr.norm1.bias, lyr.linear1.weight, lyr.linear1.bias, lyr.linear2.weight, lyr.linear2.bias,
+               lyr.norm2.weight, lyr.norm2.bias]
+    return ps
+
+
+def _mlp_params(m):
+    return [m.dense1.weight, m.dense1.bias, m.dense2.weight, m.dense2.bias]
+
+
+class TransformerNoduleBimodalClassifier(nn.Module):
+    """reference: models_archs.py:38-124 -- same constructor, ``forward(x_ct=None, x_pet=None) ->
+    (logits_petct, petct_cls_token, logits_ct, logits_pet)`` and state-dict keys; arithmetic in libvdr (bimodal_kernels.py)."""
+
+    def __init__(self, input_dim, mlp_ratio_ct, mlp_ratio_pet, num_heads_ct, num_heads_pet, num_layers_ct, num_layers_pet,
+                 num_classes):
+        super().__init__()
+        for h in (num_heads_ct, num_heads_pet):
+            if input_dim % h or input_dim // h != 64:
+                raise ValueError(f"the fused attention kernels need head_dim == 64 (input_dim {input_dim} / num_heads {h})")
+
+        def enc(ratio, heads, layers):
+            layer = nn.TransformerEncoderLayer(d_model=input_dim, dim_feedforward=int(ratio * input_dim), nhead=heads,
+                                               activation="gelu", batch_first=True, dropout=0.5)
+            return nn.TransformerEncoder(layer, num_layers=layers, enable_nested_tensor=False)
+
+        self.transformer_encoder_ct = enc(mlp_ratio_ct, num_heads_ct, num_layers_ct)
+        self.transformer_encoder_pet = enc(mlp_ratio_pet, num_heads_pet, num_layers_pet)
+        self.norm_ct = nn.LayerNorm(input_dim)
+        self.norm_pet = nn.LayerNorm(input_dim)
+        self.cls_token_ct = nn.Parameter(torch.randn(1, 1, input_dim))
+        self.cls_token_pet = nn.Parameter(torch.randn(1, 1, input_dim))
+        self.classifier_ct = MLPLayer(input_dim, input_dim * 2, num_classes, dropout_rate=0.1)
+        self.classifier_pet = MLPLayer(input_dim, input_dim * 2, num_classes, dropout_rate=0.1)
+        self.projection_petct = MLPLayer(input_dim * 2, input_dim, input_dim, dropout_rate=0.1)
+        self.cross_attention_ct = CrossAttentionLayer(input_dim, num_heads_ct)
+        self.cross_attention_pet = CrossAttentionLayer(input_dim, num_heads_ct)          # (sic) the reference uses num_heads_ct for both (:70-71)
+        self.classifier_petct = MLPLayer(input_dim, input_dim * 2, num_classes, dropout_rate=0.1)
+        self.input_dim = input_dim
+        self.cfg = dict(heads_ct=num_heads_ct, heads_pet=num_heads_pet, layers_ct=num_layers_ct, layers_pet=num_layers_pet)
+
+    def param_groups(self):
+        ca = lambda m: [m.multihead_attn.in_proj_weight, m.multihead_attn.in_proj_bias,          # noqa: E731
+                        m.multihead_attn.out_proj.weight, m.multihead_attn.out_proj.bias]
+        return dict(enc_ct=_encoder_params(self.cls_token_ct, self.norm_ct, self.transformer_encoder_ct),
+                    enc_pet=_encoder_params(self.cls_token_pet, self.norm_pet, self.transformer_encoder_pet),
+                    cross_ct=ca(self.cross_attention_ct), cross_pet=ca(self.cross_attention_pet),
+                    head_ct=_mlp_params(self.classifier_ct), head_pet=_mlp_params(self.classifier_pet),
+                    proj=_mlp_params(self.projection_petct), head_petct=_mlp_params(self.classifier_petct))
+
+    def forward(self, x_ct=None, x_pet=None):
+        """x_* (batch, seq_len, feature_dim) f32 CUDA or None (at least one).  Batches are looped (the reference runs batch 1)."""
+        if x_ct is None and x_pet is None:
+            raise AssertionError("At least one modality should be used")
+        groups = self.param_groups()
+        flat = [p for k in bk.GROUPS for p in groups[k]]
+        sizes = tuple(len(groups[k]) for k in bk.GROUPS)
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in flat)
+        B = (x_ct if x_ct is not None else x_pet).shape[0]
+        outs = [[], [], [], []]
+        for b in range(B):
+            xc = x_ct[b] if x_ct is not None else None
+            xp = x_pet[b] if x_pet is not None else None
+            if train:
+                r = bk.BimodalFunction.apply(xc, xp, self.cfg, sizes, *flat)
+            else:
+                r = bk.bimodal_forward(xc, xp, self.cfg, groups)
+            for o, v in zip(outs, r):
+                o.append(v)
+        return tuple(torch.stack(o, 0) for o in outs)

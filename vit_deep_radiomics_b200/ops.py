@@ -497,3 +497,44 @@ def cls_head_bwd(cls_bf16, W1, W2, zc, dlogits, dcls_in, dW1, db1, dW2, db2):
                                        dW2.data_ptr(), db2.data_ptr(), dcls.data_ptr(), d, H1, Cn, _stream()),
              "vdr_cls_head_bwd")
     return dcls
+
+
+# ----------------------------------------------------------------------------- bimodal classifier pieces
+def linear_vec_fwd(W: torch.Tensor, b, x: torch.Tensor) -> torch.Tensor:
+    """y = W x + b on one f32 vector (W (rows, cols) f32 contiguous)."""
+    _req(W, torch.float32, "W"), _req(x, torch.float32, "x")
+    rows, cols = W.shape
+    y = torch.empty(rows, dtype=torch.float32, device=W.device)
+    _C.check(_C.lib().vdr_linear_vec_fwd(W.data_ptr(), b.data_ptr() if b is not None else None, x.data_ptr(), y.data_ptr(), rows, cols,
+                                         _stream()), "vdr_linear_vec_fwd")
+    return y
+
+
+def linear_vec_bwd(W, x, dy, dW, db, dx):
+    """ACCUMULATES dW += dy x^T, db += dy (optional), dx += W^T dy."""
+    rows, cols = W.shape
+    _C.check(_C.lib().vdr_linear_vec_bwd(W.data_ptr(), x.data_ptr(), dy.data_ptr(), dW.data_ptr(), db.data_ptr() if db is not None else None,
+                                         dx.data_ptr(), rows, cols, _stream()), "vdr_linear_vec_bwd")
+
+
+def cross_cls_attn_fwd(q0: torch.Tensor, kv: torch.Tensor, heads: int, scale: float):
+    """q0 (d) f32, kv (n, 2d) bf16 -> (o (d) f32, p (heads, n) f32)."""
+    _req(q0, torch.float32, "q0"), _req(kv, torch.bfloat16, "kv")
+    n = kv.shape[0]
+    p = torch.empty((heads, n), dtype=torch.float32, device=kv.device)
+    o = torch.empty(heads * 64, dtype=torch.float32, device=kv.device)
+    _C.check(_C.lib().vdr_cross_cls_attn_fwd(q0.data_ptr(), kv.data_ptr(), kv.stride(0), n, heads, float(scale), p.data_ptr(), o.data_ptr(),
+                                             _stream()), "vdr_cross_cls_attn_fwd")
+    return o, p
+
+
+def cross_cls_attn_bwd(q0, kv, p, d_o, heads: int, scale: float):
+    """-> (dq0 (d) f32, dkv (n, 2d) bf16)."""
+    n = kv.shape[0]
+    dq0 = torch.empty(heads * 64, dtype=torch.float32, device=kv.device)
+    dkv = torch.empty((n, 2 * heads * 64), dtype=torch.bfloat16, device=kv.device)
+    scratch = torch.empty((heads, n), dtype=torch.float32, device=kv.device)
+    _C.check(_C.lib().vdr_cross_cls_attn_bwd(q0.data_ptr(), kv.data_ptr(), kv.stride(0), p.data_ptr(), d_o.data_ptr(), n, heads, float(scale),
+                                             dq0.data_ptr(), dkv.data_ptr(), dkv.stride(0), scratch.data_ptr(), _stream()),
+             "vdr_cross_cls_attn_bwd")
+    return dq0, dkv
