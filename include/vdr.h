@@ -71,6 +71,16 @@ typedef struct {
   int epilogue;
   int out_group, out_group_stride, out_offset;    /* 0,0,0 = identity */
   int res_mod, res_offset;                        /* 0,0 = same row as the output */
+  /* LayerNorm folded into the GEMMs either side of it (all NULL / 0 = off), the ViT blocks' `x -> LN -> Linear` pairs:
+   *   LN(x) W^T + b  =  rstd_m * (x W'^T - mean_m * colsum_n) + b'_n   with W' = gamma (.) W, colsum_n = sum_k W'[n,k],
+   *   b' = b + W beta (vdr_fold_layernorm).  The GEMM then reads the raw residual stream x and normalises in its epilogue.
+   * stats_out (producer, EPI_BIAS_RESIDUAL only, N % 64 == 0, no row remapping, bf16 C): per output row and per 64-column
+   *   slot, (sum, sum of squares) of the values written: float pairs laid out [N/64][M].  Deterministic (no atomics).
+   * ln_stats (consumer): such a table for the rows of A, `ln_slots` slots (summed in slot order); the row mean / rstd over
+   *   K elements with `ln_eps`; W must be the folded W', bias the folded b', ln_colsum (N) f32.  bf16 C, N % 32 == 0. */
+  const float* ln_stats;  int ln_slots;  float ln_eps;
+  const float* ln_colsum;
+  float* stats_out;
 } vdr_gemm_args;
 
 int vdr_gemm(const vdr_gemm_args* args, vdr_stream_t stream);
@@ -138,6 +148,10 @@ typedef struct {
   const float *n2w, *n2b;
   const void* fc1_w;  const float* fc1_b;     /* (4*dim, dim) */
   const void* fc2_w;  const float* fc2_b;     /* (dim, 4*dim) */
+  /* optional (all six or none): norm1 folded into qkv and norm2 into fc1 by vdr_fold_layernorm.  When present the forward runs
+   * no LayerNorm kernel inside the blocks: the residual GEMMs emit row statistics and the qkv / fc1 GEMMs normalise in their epilogue. */
+  const void* qkv_wf; const float* qkv_bf; const float* qkv_cs;
+  const void* fc1_wf; const float* fc1_bf; const float* fc1_cs;
 } vdr_vit_block;
 
 typedef struct {
@@ -164,6 +178,15 @@ int vdr_vit_forward(const vdr_vit_weights* weights, const void* images_bf16, int
 int vdr_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta,
                       void* y, int64_t ldy, int y_dtype, float* mean, float* rstd,
                       int rows, int d, float eps, vdr_stream_t stream);
+
+/* Row statistics in the layout vdr_gemm's `ln_stats` reads, one slot: stats[2*r] = sum_k x[r,k], stats[2*r+1] = sum_k x[r,k]^2. */
+int vdr_row_stats(const void* x_bf16, int64_t ldx, int rows, int d, float* stats, vdr_stream_t stream);
+
+/* Fold a LayerNorm (gamma, beta over K) into the Linear (W (N,K) bf16, bias (N) f32 or NULL) that consumes it:
+ * Wf = bf16(gamma (.) W), colsum[n] = sum_k float(Wf[n,k]) (of the ROUNDED weights, so the identity holds for what the
+ * tensor cores multiply), bias_f[n] = bias[n] + sum_k beta[k] W[n,k].  Weight preparation, run once per checkpoint. */
+int vdr_fold_layernorm(const void* W_bf16, int64_t ldw, const float* bias, const float* gamma, const float* beta, int N, int K,
+                       void* Wf_bf16, int64_t ldwf, float* bias_f, float* colsum, vdr_stream_t stream);
 
 /* dx, dgamma, dbeta of the LayerNorm above.  dgamma/dbeta are ACCUMULATED (+=) into f32 buffers. */
 int vdr_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx,

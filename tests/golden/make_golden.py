@@ -216,10 +216,30 @@ def golden_bimodal():
     print("bimodal_small.npz")
 
 
+def golden_crossmodal():
+    """CrossModalFocalLoss (train_models.py:332-378): batch and single-sample values plus logit gradients, for the default
+    constructor and for the training script's setting (:593-596)."""
+    tm = ref_shim.load_reference("train_models")
+    torch.manual_seed(77)
+    lx, lc, lp = (torch.randn(6, 2) * 2 for _ in range(3))
+    tg = torch.eye(2)[torch.tensor([1, 0, 1, 1, 0, 0])]
+    cases = {"lx": lx.numpy(), "lc": lc.numpy(), "lp": lp.numpy(), "targets": tg.numpy()}
+    for tag, kw in (("default", {}), ("train", dict(alpha=torch.tensor([0.25, 0.75]), gamma_unimodal=2.0, gamma_bimodal=1.0, beta=0.6))):
+        crit = tm.CrossModalFocalLoss(**kw)
+        a, b, c = (t.clone().requires_grad_(True) for t in (lx, lc, lp))
+        loss = crit(a, b, c, tg)
+        loss.backward()
+        cases[f"{tag}__loss"] = loss.detach().numpy()
+        for n_, t in (("gx", a), ("gc", b), ("gp", c)):
+            cases[f"{tag}__{n_}"] = t.grad.numpy()
+        cases[f"{tag}__single"] = np.array([crit(lx[i], lc[i], lp[i], tg[i]).item() for i in range(6)])
+    np.savez_compressed(os.path.join(OUT, "crossmodal_loss.npz"), **cases)
+    print("crossmodal_loss.npz")
+
+
 if __name__ == "__main__":
     assert ref_shim.reference_available(), "needs /root/reference"
-    golden_gather()
-    golden_pointcloud()
-    golden_geometry()
-    golden_classifier()
-    golden_bimodal()
+    only = sys.argv[1:]
+    for fn in (golden_gather, golden_pointcloud, golden_geometry, golden_classifier, golden_bimodal, golden_crossmodal):
+        if not only or fn.__name__ in only:
+            fn()

@@ -37,6 +37,103 @@ def test_gemm(cuda, M, N, K, epi, cdt):
     _close(out, ref, 1e-5 if cdt == torch.float32 else 5e-3)
 
 
+@pytest.mark.parametrize("M,d,N,epi", [(1025, 768, 2304, "bias"), (4100, 768, 3072, "gelu"), (333, 384, 1152, "bias"),
+                                       (40000, 768, 2304, "bias"), (70, 192, 576, "gelu"), (2050, 1024, 4096, "gelu")])
+def test_gemm_folded_layernorm_consumer(cuda, M, d, N, epi):
+    """`x -> LayerNorm -> Linear` as ONE GEMM on the raw x (vdr_gemm ln_stats / ln_colsum + vdr_fold_layernorm + vdr_row_stats)
+    against fp32 LayerNorm + matmul; x carries a per-row offset and scale so mean and rstd both matter."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(M + N)
+    x = ((torch.randn(M, d, device=cuda) * (0.5 + 2 * torch.rand(M, 1, device=cuda)) + torch.randn(M, 1, device=cuda))).bfloat16()
+    w = (torch.randn(N, d, device=cuda) * 0.05).bfloat16()
+    b = torch.randn(N, device=cuda) * 0.1
+    gamma, beta = 1 + 0.3 * torch.randn(d, device=cuda), 0.2 * torch.randn(d, device=cuda)
+    ref = torch.nn.functional.layer_norm(x.float(), (d,), gamma, beta, eps=1e-6) @ w.float().t() + b
+    if epi == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    wf, bf, cs = ops.fold_layernorm(w, b, gamma, beta)
+    assert torch.equal(wf, (w.float() * gamma).bfloat16())
+    assert torch.allclose(cs, wf.float().sum(1), atol=1e-4) and torch.allclose(bf, b + w.float() @ beta, atol=1e-4)
+    st = ops.row_stats(x)
+    assert st.shape == (1, M, 2)
+    assert torch.allclose(st[0, :, 0], x.float().sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[0, :, 1], (x.float() ** 2).sum(1), rtol=1e-5, atol=1e-3)
+    out = ops.gemm(x, wf, bf, epilogue=epi, ln_stats=st, ln_colsum=cs, ln_eps=1e-6)
+    _close(out, ref, 6e-3)
+    # the same statistics split over several slots (the layout a residual GEMM's stats_out produces) give the same result
+    st3 = torch.stack([st[0] * 0.25, st[0] * 0.5, st[0] * 0.25]).contiguous()
+    out3 = ops.gemm(x, wf, bf, epilogue=epi, ln_stats=st3, ln_colsum=cs, ln_eps=1e-6)
+    _close(out3, out.float(), 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(1025, 768, 768), (2050, 768, 3072), (40000, 768, 768), (300, 384, 1536), (90, 192, 192), (130, 1024, 256)])
+def test_gemm_residual_emits_row_statistics(cuda, M, N, K):
+    """stats_out of a residual GEMM: per row and 64-column slot, (sum, sum of squares) of the values written (in place on the
+    residual, as the ViT blocks run it); deterministic, and feeding it to a folded consumer equals LayerNorm of the output."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(M + K)
+    a = (torch.randn(M, K, device=cuda) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=cuda) * 0.05).bfloat16()
+    b = torch.randn(N, device=cuda) * 0.1
+    x0 = torch.randn(M, N, device=cuda).bfloat16()
+    outs = []
+    for _ in range(2):
+        x = x0.clone()
+        st = torch.full((N // 64, M, 2), float("nan"), device=cuda)
+        ops.gemm(a, w, b, epilogue="residual", residual=x, out=x, stats_out=st)
+        outs.append((x, st))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    x, st = outs[0]
+    _close(x, a.float() @ w.float().t() + b + x0.float(), 5e-3)
+    assert torch.equal(x, ops.gemm(a, w, b, epilogue="residual", residual=x0))          # statistics do not change the output
+    xs = x.float().reshape(M, N // 64, 64)
+    # statistics are taken before the bf16 rounding of the output: compare within that rounding
+    assert torch.allclose(st[:, :, 0].t(), xs.sum(2), atol=0.15, rtol=0)
+    assert torch.allclose(st[:, :, 1].t(), (xs ** 2).sum(2), rtol=1e-2, atol=0.05)
+    d = N
+    w2 = (torch.randn(256, d, device=cuda) * 0.05).bfloat16()
+    gamma, beta = 1 + 0.3 * torch.randn(d, device=cuda), 0.2 * torch.randn(d, device=cuda)
+    wf, bf, cs = ops.fold_layernorm(w2, None, gamma, beta)
+    out = ops.gemm(x, wf, bf, ln_stats=st, ln_colsum=cs, ln_eps=1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (d,), gamma, beta, eps=1e-6) @ w2.float().t()
+    _close(out, ref, 6e-3)
+
+
+def test_gemm_inplace_residual_tile_reuse_hazard(cuda):
+    """Regression: the TMA-loaded residual tile of an epilogue warp is overwritten by the next chunk's load; without a fence after
+    the (asynchronously completing) shared-memory reads, a read delayed behind the main loop's traffic saw the next chunk's bytes --
+    a 16-byte corruption in a few rows, a few times per hundred launches (pair tiles, K = 768).  40 launches must agree bit for bit."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(5)
+    M, N, K = 60000, 768, 768
+    a = (torch.randn(M, K, device=cuda) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=cuda) * 0.05).bfloat16()
+    b = torch.randn(N, device=cuda) * 0.1
+    x0 = torch.randn(M, N, device=cuda).bfloat16()
+    ref = None
+    for _ in range(40):
+        x = x0.clone()
+        ops.gemm(a, w, b, epilogue="residual", residual=x, out=x)
+        if ref is None:
+            ref = x
+            _close(x, a.float() @ w.float().t() + b + x0.float(), 5e-3)
+        else:
+            assert torch.equal(x, ref)
+
+
+def test_gemm_folded_layernorm_argument_errors(cuda):
+    from vit_deep_radiomics_b200 import ops
+    a = torch.zeros(64, 128, device=cuda, dtype=torch.bfloat16)
+    w = torch.zeros(96, 128, device=cuda, dtype=torch.bfloat16)
+    st = torch.zeros(1, 64, 2, device=cuda)
+    with pytest.raises(ValueError):          # stats_out needs the residual epilogue and N % 64 == 0
+        ops.gemm(a, w, None, stats_out=torch.zeros(2, 64, 2, device=cuda))
+    with pytest.raises(ValueError):          # f32 output with a folded LayerNorm
+        ops.gemm(a, w, None, ln_stats=st, ln_colsum=torch.zeros(96, device=cuda), out_dtype=torch.float32)
+    with pytest.raises(ValueError):
+        ops.gemm(a, w, None, ln_stats=torch.zeros(1, 63, 2, device=cuda), ln_colsum=torch.zeros(96, device=cuda))
+
+
 def test_gemm_k_tail_and_row_remap(cuda):
     """K = 588 (14x14 patches) inside ld 592, rows written behind a CLS row, pos-embed as residual."""
     from vit_deep_radiomics_b200 import ops

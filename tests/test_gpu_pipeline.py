@@ -212,6 +212,43 @@ def test_train_step_accumulation_semantics(cuda):
         assert (v.cpu() - sd[k].detach()).abs().max() < 3e-3, k     # 3 AdamW steps of lr 5e-4: updates ~1.5e-3
 
 
+def test_train_epoch_bimodal_crossmodal_loss_matches_cpu_training(cuda, golden_dir):
+    """The reference's bimodal loop (train_models.py:656-688 with loss_func 'crossmodal'): model(ct, pet) -> CrossModalFocalLoss on
+    outputs[0], [2], [3] / iters, optimizer steps as in the unimodal loop -- against the fp32 oracle trained the same way on CPU."""
+    from oracle import classifier_fp32 as C
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleBimodalClassifier
+    from vit_deep_radiomics_b200.train_models import CrossModalFocalLoss, make_criterion, train_epoch
+    g = np.load(os.path.join(golden_dir, "bimodal_small.npz"))
+    cfg = [int(v) for v in g["cfg"]]
+    d, heads_ct, heads_pet, layers_ct, layers_pet = cfg[0], cfg[3], cfg[4], cfg[5], cfg[6]
+    sd0 = {k[len("param__"):]: torch.tensor(g[k]) for k in g.files if k.startswith("param__")}
+    model = TransformerNoduleBimodalClassifier(*cfg)
+    model.load_state_dict(sd0)
+    model = model.to(cuda)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.01)
+    gen = torch.Generator().manual_seed(4)
+    data = [(torch.randn(nc, d, generator=gen), torch.randn(np_, d, generator=gen), torch.eye(2)[c])
+            for nc, np_, c in [(30, 12, 0), (21, 40, 1), (17, 9, 1), (26, 26, 0)]]
+    crit = make_criterion("crossmodal", cuda)
+    loss_gpu, scores = train_epoch(model, [tuple(t.to(cuda) for t in s_) for s_ in data], crit, opt, virtual_batch_size=3)
+    assert len(scores) == 4 and all(abs(float(sc.sum()) - 1) < 1e-5 for sc in scores)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    opt_c = torch.optim.AdamW(list(sd.values()), lr=5e-4, weight_decay=0.01)
+    crit_c = CrossModalFocalLoss(alpha=torch.tensor([0.25, 0.75]), gamma_unimodal=2.0, gamma_bimodal=1.0, beta=0.6)
+    iters, tot = 3, 0.0
+    for i, (xc, xp, y) in enumerate(data):
+        lg, _, lc, lp = C.bimodal_forward(sd, xc[None], xp[None], heads_ct, heads_pet, layers_ct, layers_pet)
+        l = crit_c(lg[0], lc[0], lp[0], y) / iters
+        l.backward()
+        tot += l.item() * iters
+        if (i + 1) % iters == 0 or i + 1 == len(data):
+            opt_c.step()
+            opt_c.zero_grad()
+    assert abs(loss_gpu - tot / len(data)) < 0.02
+    for k, v in model.state_dict().items():
+        assert (v.cpu() - sd[k].detach()).abs().max() < 3e-3, k     # 2 AdamW steps of lr 5e-4
+
+
 def test_native_vit_forward_equals_op_by_op_path(cuda):
     """vdr_vit_forward (one C call) enqueues the same kernels in the same order as the Python op-by-op path: identical tokens."""
     from vit_deep_radiomics_b200 import synth, tfds_dense_descriptor as tdd
@@ -227,6 +264,33 @@ def test_native_vit_forward_equals_op_by_op_path(cuda):
         model.use_native_forward = True
         assert torch.equal(a, b)
         assert torch.isfinite(a).all()
+
+
+def test_folded_layernorm_forward_matches_layernorm_kernel_path(cuda):
+    """LayerNorms folded into the qkv / fc1 GEMMs (default) against the path that runs the LayerNorm kernels: same tokens within
+    bf16 noise, both within the oracle tolerance (test_vit_dense_descriptors_vs_oracle covers the default path), and run-to-run
+    bit-identical (the statistics tables are written without atomics)."""
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    from vit_deep_radiomics_b200.vit import ViTBackbone
+    rng = np.random.default_rng(3)
+    for name, hw, S in (("vit_s16", (256, 256), 6), ("vit_t16", (64, 64), 3)):
+        folded = tdd.load_model(name, img_hw=hw, device=cuda, seed=8)
+        assert folded.fold_layernorm and "qkv_wf" in folded.w["blocks"][0]
+        try:
+            ViTBackbone.fold_layernorm = False
+            plain = tdd.load_model(name, img_hw=hw, device=cuda, seed=8)
+        finally:
+            ViTBackbone.fold_layernorm = True
+        assert "qkv_wf" not in plain.w["blocks"][0]
+        vol = torch.from_numpy(rng.random(hw + (S,), dtype=np.float32)).to(cuda)
+        crop = (0, hw[0], 0, hw[1])
+        a = folded.forward_volume(vol, crop).clone()
+        a2 = folded.forward_volume(vol, crop).clone()
+        b = plain.forward_volume(vol, crop).clone()
+        assert torch.equal(a, a2)
+        _check_descriptors(a.cpu().numpy(), b.cpu().numpy())
+        x = torch.from_numpy(rng.random((2, 3) + hw, dtype=np.float32))
+        _check_descriptors(plain.dense_descriptors(x.to(cuda)).cpu().numpy(), _oracle_dense(plain, x))
 
 
 @pytest.mark.parametrize("ch,cw,oh,ow", [(37, 53, 64, 64), (200, 180, 256, 256), (96, 80, 64, 48), (300, 260, 128, 224)])

@@ -89,6 +89,41 @@ def test_focal_loss_matches_golden(golden_dir):
     assert np.allclose([crit(lg[i], tg[i]).item() for i in range(6)], g["focal__loss_single"], atol=1e-6)
 
 
+def test_crossmodal_focal_loss_matches_golden(golden_dir):
+    """CrossModalFocalLoss (reference train_models.py:332-378): value, per-sample values and logit gradients."""
+    g = np.load(os.path.join(golden_dir, "crossmodal_loss.npz"))
+    tg = torch.tensor(g["targets"])
+    for tag, kw in (("default", {}), ("train", dict(alpha=torch.tensor([0.25, 0.75]), gamma_unimodal=2.0, gamma_bimodal=1.0, beta=0.6))):
+        crit = tm.CrossModalFocalLoss(**kw)
+        a, b, c = (torch.tensor(g[k]).requires_grad_(True) for k in ("lx", "lc", "lp"))
+        loss = crit(a, b, c, tg)
+        loss.backward()
+        assert abs(loss.item() - float(g[f"{tag}__loss"])) < 1e-6
+        for n_, t in (("gx", a), ("gc", b), ("gp", c)):
+            assert np.allclose(t.grad.numpy(), g[f"{tag}__{n_}"], atol=1e-6)
+        single = [crit(a[i], b[i], c[i], tg[i]).item() for i in range(6)]
+        assert np.allclose(single, g[f"{tag}__single"], atol=1e-6)
+    crit = tm.make_criterion("crossmodal", "cpu")
+    assert (crit.gamma_bimodal, crit.gamma_unimodal, crit.beta) == (1.0, 2.0, 0.6) and crit.alpha.tolist() == [0.25, 0.75]
+    assert isinstance(tm.make_criterion("focal", "cpu"), tm.FocalLoss)
+
+
+def test_build_model_bimodal_takes_ct_from_modality_b():
+    """reference train_models.py:455-472: CT encoder <- cfg[modality_b], PET encoder <- cfg[modality_a]."""
+    cfg = {"models": {"transformer": {"feature_dim": 128,
+                                      "pet": {"mlp_ratio": 2, "num_heads": 2, "num_layers": 1},
+                                      "ct": {"mlp_ratio": 4, "num_heads": 2, "num_layers": 3}}}}
+    m = tm.build_model(cfg, "transformer", "petct", "pet", "ct")
+    assert len(m.transformer_encoder_ct.layers) == 3 and len(m.transformer_encoder_pet.layers) == 1
+    assert m.transformer_encoder_ct.layers[0].linear1.out_features == 512
+    assert m.transformer_encoder_pet.layers[0].linear1.out_features == 256
+    if os.path.isdir("/root/reference/src"):
+        from oracle import ref_shim
+        ref = ref_shim.load_reference("train_models").build_model(cfg, "transformer", "petct", "pet", "ct")
+        assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(ref.state_dict())
+
+
 def test_synth_cases_are_seeded():
     a = synth.make_case("T0")
     b = synth.make_case("T0")

@@ -18,7 +18,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 EXPORTS = (
     "vdr_version", "vdr_last_error_string", "vdr_launch_count",
     "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
-    "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd",
+    "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd", "vdr_row_stats", "vdr_fold_layernorm",
     "vdr_flash_attn_fwd", "vdr_flash_attn_bwd_workspace_bytes", "vdr_flash_attn_bwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather",
     "vdr_voxel_bbox", "vdr_mask_bbox", "vdr_voxel_gather",
@@ -31,7 +31,8 @@ EXPORTS = (
 class VitBlock(C.Structure):
     """== vdr_vit_block (include/vdr.h)"""
     _fields_ = [(n, C.c_void_p) for n in ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b",
-                                          "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+                                          "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                                          "qkv_wf", "qkv_bf", "qkv_cs", "fc1_wf", "fc1_bf", "fc1_cs")]
 
 
 class VitWeights(C.Structure):
@@ -52,6 +53,8 @@ class GemmArgs(C.Structure):
         ("epilogue", C.c_int),
         ("out_group", C.c_int), ("out_group_stride", C.c_int), ("out_offset", C.c_int),
         ("res_mod", C.c_int), ("res_offset", C.c_int),
+        ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -84,6 +87,8 @@ def lib() -> C.CDLL:
     L.vdr_layernorm_fwd.argtypes = [vp, i64, vp, vp, vp, i64, i32, vp, vp, i32, i32, f32, vp]
     L.vdr_layernorm_bwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp]
     L.vdr_cls_concat_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]
+    L.vdr_row_stats.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.vdr_fold_layernorm.argtypes = [vp, i64, vp, vp, vp, i32, i32, vp, i64, vp, vp, vp]
     L.vdr_vit_forward_workspace_bytes.argtypes = [C.POINTER(VitWeights), i32]
     L.vdr_vit_forward_workspace_bytes.restype = sz
     L.vdr_vit_forward.argtypes = [C.POINTER(VitWeights), vp, i32, i32, vp, i64, vp, sz, vp]

@@ -30,8 +30,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;
-constexpr int kTmaWarp = 0, kMmaWarp = 1, kFirstEpiWarp = 2;
+constexpr int kThreads = 64 + kEpiWarps * 32 + 32;
+constexpr int kTmaWarp = 0, kMmaWarp = 1, kFirstEpiWarp = 2, kStatsWarp = kFirstEpiWarp + kEpiWarps;
 
 struct GemmParams {
   const float* bias;
@@ -42,6 +42,10 @@ struct GemmParams {
   int epilogue, r_dtype, c_dtype;
   int out_group, out_group_stride, out_offset;
   int res_mod, res_offset;
+  // LayerNorm folded into this GEMM (vdr.h): consumer side (ln_stats: [ln_slots][M] (sum, sumsq) of A's rows -> per-row rstd / mean,
+  // ln_colsum: column sums of the folded weight) and producer side (stats_out: [N/64][M] (sum, sumsq) of the rows written)
+  const float2* ln_stats; const float* ln_colsum; float2* stats_out;
+  int ln_slots; float ln_eps;
   // A operand as an im2col VIEW of (images, H, W) bf16 pictures (patch embedding, 16-pixel patches): tmA is then a 5-D tensor
   // map (ix, px, py, iy, image), SWIZZLE_32B, and a K block of a 128-patch tile lands as four [128 patches][16 ix] sub-tiles with
   // 32-byte rows, one per pixel row iy = one per MMA K step (a SWIZZLE_128B box with a 32-byte inner dimension faults on sm_100a)
@@ -70,7 +74,8 @@ struct GemmCfg {
   // room for it next to four 48 KB stages and keeps the register-staged residual path)
   static constexpr bool kResTma = kRes && !(BN == 256 && kCtas == 1);
   static constexpr int kEpiBufBytes = kResTma ? 4096 : 2048;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiBufBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 * 4 /*bias staging*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiBufBytes + 1024 /*align slack*/ + 512 /*barriers*/ + 2 * BN * 4 /*bias, two tiles*/ + 2 * BN * 4 /*folded-LayerNorm column sums*/ +
+                                    2 * BM * 8 /*folded-LayerNorm row coefficients*/;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
@@ -90,8 +95,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;                       // [kEpiWarps] residual chunk landed (one per epilogue warp)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
-  float* bias_smem = reinterpret_cast<float*>(smem + kAuxOff + 256);  // [kEpiWarps][BN/2]
+  uint64_t* ln_full = res_bar + kEpiWarps;                  // [2] row coefficients of a tile staged by the statistics warp
+  uint64_t* ln_empty = ln_full + 2;                         // [2] ... and read by all epilogue warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ln_empty + 2);
+  // per-tile epilogue constants, staged one tile ahead by the auxiliary warp (two buffers):
+  float* bias_smem = reinterpret_cast<float*>(smem + kAuxOff + 512);  // [2][BN] bias of the tile's columns
+  float* csum_smem = bias_smem + 2 * BN;                              // [2][BN] folded-LayerNorm column sums
+  float2* ln_ab = reinterpret_cast<float2*>(csum_smem + 2 * BN);      // [2][BM] folded-LayerNorm row coefficients (rstd, -mean * rstd)
   const uint32_t stage_base = base + kStages * Cfg::kStageBytes;                          // [kEpiWarps][store tile 2 KB (| residual tile 2 KB)]
 
   const int warp = threadIdx.x >> 5;
@@ -120,6 +130,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tmem_empty[a], kEpiWarps * kCtas);   // pair: the epilogue warps of BOTH CTAs release the leader
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ln_full[a], 1);
+      mbar_init(&ln_empty[a], kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == kFirstEpiWarp) {
@@ -223,6 +237,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+  } else if (warp == kStatsWarp) {
+    // ------------------------------------------------------------------ auxiliary warp: epilogue constants, one tile ahead
+    // Stages what the epilogue warps need besides the accumulator -- the bias of the tile's columns and, for a folded LayerNorm,
+    // the column sums and each row's (rstd, -mean * rstd) from the (sum, sumsq) slots -- in shared memory, so that no global-load
+    // latency sits between two tiles of the epilogue warps.
+    const float inv_k = 1.0f / static_cast<float>(p.K);
+    int it = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&ln_empty[buf], ((it >> 1) & 1) ^ 1u);
+      const int m0 = (tile / n_tiles) * kTileM + static_cast<int>(cta_rank) * BM, n0 = (tile % n_tiles) * BN;
+      for (int i = lane; i < BN; i += 32) bias_smem[buf * BN + i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      if (p.ln_stats != nullptr) {
+        for (int i = lane; i < BN; i += 32) csum_smem[buf * BN + i] = (n0 + i < p.N) ? __ldg(p.ln_colsum + n0 + i) : 0.f;
+        float su[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sl = 0; sl < p.ln_slots; ++sl) {
+          const float2* st = p.ln_stats + static_cast<int64_t>(sl) * p.M;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int m = m0 + lane + 32 * j;
+            const float2 t = m < p.M ? __ldg(st + m) : make_float2(0.f, 0.f);
+            su[j] += t.x;
+            sq[j] += t.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mean = su[j] * inv_k;
+          const float rstd = rsqrtf(fmaxf(sq[j] * inv_k - mean * mean, 0.f) + p.ln_eps);
+          ln_ab[buf * BM + lane + 32 * j] = make_float2(rstd, -mean * rstd);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ln_full[buf]);
+    }
   } else {
     // ------------------------------------------------------------------ epilogue
     const int ew = warp - kFirstEpiWarp;
@@ -231,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kColsPerWarp = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    float* sbias = bias_smem + ew * kColsPerWarp;
+    const bool ln_in = p.ln_stats != nullptr, st_out = p.stats_out != nullptr;
     const bool res_bf16 = p.epilogue == VDR_EPI_BIAS_RESIDUAL && p.r_dtype == VDR_DTYPE_BF16;
     // Per-warp staging tile (32 rows x 64 B, 16-byte chunks XOR-swizzled): accumulators arrive with
     // thread == row, but global memory wants consecutive lanes on consecutive addresses.  Going through
@@ -262,11 +311,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int i = 0; i < 4; ++i) map_rows(m_warp + crow + 8 * i, out_row_c[i], res_row_c[i]);
       const int nw0 = n_blk * BN + half * kColsPerWarp;      // first column of this warp
       const bool warp_ok = m_warp < p.M;                     // the slab has at least one real row
-      // Work that does not depend on the accumulator is done BEFORE waiting for the MMAs: stage this
-      // warp's bias slice in shared memory and start the first residual chunk.
-      __syncwarp();
-      for (int i = lane; i < kColsPerWarp; i += 32)
-        sbias[i] = (p.bias != nullptr && nw0 + i < p.N) ? __ldg(p.bias + nw0 + i) : 0.f;
+      // The tile's epilogue constants were staged by the auxiliary warp; start the first residual chunk before waiting for the MMAs.
+      const int cbuf = it & 1;
+      const float* sbias = bias_smem + cbuf * BN + half * kColsPerWarp;
+      const float* scsum = csum_smem + cbuf * BN + half * kColsPerWarp;
+      uint64_t st_sum2 = pack2(0.f, 0.f), st_sq2 = pack2(0.f, 0.f);
       __syncwarp();
       const __nv_bfloat16* Rb = static_cast<const __nv_bfloat16*>(p.R);
       __nv_bfloat16* Cb = static_cast<__nv_bfloat16*>(p.C);
@@ -286,6 +335,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       if (tma_res) tma_res_load(0);
       else load_res(rcur, 0);
+      mbar_wait(&ln_full[cbuf], (it >> 1) & 1);
+      // folded LayerNorm: out = rstd * acc - (mean * rstd) * colsum + bias'
+      uint64_t ln_a2 = 0, ln_b2 = 0;
+      if (ln_in) {
+        const float2 ab = ln_ab[cbuf * BM + quarter * 32 + lane];
+        ln_a2 = pack2(ab.x, ab.x);
+        ln_b2 = pack2(ab.y, ab.y);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (ew == 0 && lane == 0) VDR_TRACE(3, it);
@@ -312,6 +369,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[g].x), "=r"(rr[g].y), "=r"(rr[g].z), "=r"(rr[g].w) : "r"(rbuf + sw(lane, g)) : "memory");
+            // The next TMA load overwrites the tile just read.  The loads above are only ISSUED at this point (nothing consumes
+            // rr until after the accumulator wait); without the fence a load delayed behind the main loop's shared-memory traffic
+            // can observe the next chunk's bytes (seen as a rare 16-byte corruption of the residual, K = 768, pair tiles).
+            fence_proxy_async_smem();   // membar.cta: the reads are performed; generic -> async proxy ordering
             __syncwarp();
             if (c + 32 < kColsPerWarp) tma_res_load(c + 32);
           } else {         // residual: coalesced registers -> staging tile -> this thread's row
@@ -338,6 +399,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (fast) {
           uint4 o[4];
           uint64_t v2[16];   // the chunk's 32 columns as 16 packed fp32 pairs
+          if (ln_in) {   // folded LayerNorm: rstd * acc + (-mean * rstd * colsum + bias')
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + g * 8 + 4);
+              const float4 s0 = *reinterpret_cast<const float4*>(scsum + c + g * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(scsum + c + g * 8 + 4);
+              v2[g * 4 + 0] = fma2(ln_a2, pack2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])), fma2(ln_b2, pack2(s0.x, s0.y), pack2(b0.x, b0.y)));
+              v2[g * 4 + 1] = fma2(ln_a2, pack2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])), fma2(ln_b2, pack2(s0.z, s0.w), pack2(b0.z, b0.w)));
+              v2[g * 4 + 2] = fma2(ln_a2, pack2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])), fma2(ln_b2, pack2(s1.x, s1.y), pack2(b1.x, b1.y)));
+              v2[g * 4 + 3] = fma2(ln_a2, pack2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])), fma2(ln_b2, pack2(s1.z, s1.w), pack2(b1.z, b1.w)));
+            }
+          } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + g * 8);
@@ -347,6 +421,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v2[g * 4 + 1] = add2(pack2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])), pack2(b0.z, b0.w));
             v2[g * 4 + 2] = add2(pack2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])), pack2(b1.x, b1.y));
             v2[g * 4 + 3] = add2(pack2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])), pack2(b1.z, b1.w));
+          }
           }
           if (p.epilogue == VDR_EPI_BIAS_GELU) {
             gelu_fast2_x16(v2);   // all 16 pairs step by step: 16 independent dependency chains in flight
@@ -371,6 +446,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v2[g * 4 + 2] = add2(v2[g * 4 + 2], pack2(a1.x, a1.y));
                 v2[g * 4 + 3] = add2(v2[g * 4 + 3], pack2(a1.z, a1.w));
               }
+            }
+          }
+          if (st_out) {   // row statistics of what this GEMM writes (the next GEMM's folded LayerNorm): one slot per 64 columns
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              st_sum2 = add2(st_sum2, v2[i]);
+              st_sq2 = fma2(v2[i], v2[i], st_sq2);
+            }
+            if ((c & 32) != 0) {
+              float s0, s1, q0, q1;
+              unpack2(st_sum2, s0, s1);
+              unpack2(st_sq2, q0, q1);
+              if (row_ok) p.stats_out[static_cast<int64_t>((n0 - 32) >> 6) * p.M + m] = make_float2(s0 + s1, q0 + q1);
+              st_sum2 = pack2(0.f, 0.f);
+              st_sq2 = pack2(0.f, 0.f);
             }
           }
 #pragma unroll
@@ -442,6 +532,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) {
         if constexpr (kCtas == 2) mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty[acc]), 0));   // the leader's barrier
         else mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive(&ln_empty[cbuf]);   // bias / column sums / row coefficients of this tile are no longer read
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -527,6 +618,16 @@ static int gemm_impl(const vdr_gemm_args* a, const Im2colSpec* ic, vdr_stream_t 
     VDR_CHECK_ARG(aligned16(a->R) && a->ldr % 8 == 0 && a->ldr >= a->N, VDR_EALIGN, "vdr_gemm: R must be 16-byte aligned with ldr %% 8 == 0");
   }
   VDR_CHECK_ARG(a->out_group >= 0 && a->res_mod >= 0, VDR_EINVAL, "vdr_gemm: negative row-remap parameters");
+  if (a->ln_stats != nullptr) {
+    VDR_CHECK_ARG(a->ln_colsum != nullptr && a->ln_slots > 0 && a->ln_eps > 0.f, VDR_EINVAL, "vdr_gemm: ln_stats needs ln_colsum, ln_slots > 0 and ln_eps > 0");
+    VDR_CHECK_ARG(a->c_dtype == VDR_DTYPE_BF16 && a->N % 32 == 0 && !ic, VDR_EINVAL, "vdr_gemm: folded LayerNorm needs a bf16 C and N %% 32 == 0 (N = %d)", a->N);
+    VDR_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0 && aligned16(a->ln_colsum), VDR_EALIGN, "vdr_gemm: ln_stats must be 8-byte and ln_colsum 16-byte aligned");
+  }
+  if (a->stats_out != nullptr) {
+    VDR_CHECK_ARG(a->epilogue == VDR_EPI_BIAS_RESIDUAL && a->c_dtype == VDR_DTYPE_BF16 && a->N % 64 == 0 && a->out_group == 0, VDR_EINVAL,
+                  "vdr_gemm: stats_out needs the residual epilogue, a bf16 C, N %% 64 == 0 (N = %d) and no row remapping", a->N);
+    VDR_CHECK_ARG((reinterpret_cast<uintptr_t>(a->stats_out) & 7) == 0, VDR_EALIGN, "vdr_gemm: stats_out must be 8-byte aligned");
+  }
 
   const int sms = num_sms();
   const int m_tiles = (a->M + BM - 1) / BM;
@@ -534,7 +635,7 @@ static int gemm_impl(const vdr_gemm_args* a, const Im2colSpec* ic, vdr_stream_t 
   int bn = 256;
   if (a->N % 256 != 0 && a->N % 128 == 0) bn = 128;
   if (bn == 256 && tiles(256) < sms) bn = 128;
-  if (bn == 128 && tiles(128) < sms) bn = 64;
+  if (bn == 128 && tiles(128) < sms && a->stats_out == nullptr) bn = 64;   // a statistics slot is 64 columns = one warp's slice at BN = 128
   // CTA pairs (256 x 256 tiles) when there is enough work to fill the 74 pairs
   static const bool force_1cta = getenv("VDR_GEMM_1CTA") != nullptr;
   const int pair_tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + 255) / 256);
@@ -562,6 +663,8 @@ static int gemm_impl(const vdr_gemm_args* a, const Im2colSpec* ic, vdr_stream_t 
   p.epilogue = a->epilogue; p.r_dtype = a->r_dtype; p.c_dtype = a->c_dtype;
   p.out_group = a->out_group; p.out_group_stride = a->out_group_stride; p.out_offset = a->out_offset;
   p.res_mod = a->res_mod; p.res_offset = a->res_offset;
+  p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats); p.ln_colsum = a->ln_colsum; p.ln_slots = a->ln_slots; p.ln_eps = a->ln_eps;
+  p.stats_out = reinterpret_cast<float2*>(a->stats_out);
   p.trace = g_trace;
   p.dbg = getenv("VDR_GEMM_DBG") ? atoi(getenv("VDR_GEMM_DBG")) : 0;
   p.a_im2col = ic ? 1 : 0;

@@ -232,6 +232,53 @@ static int ln_grid(int64_t rows) {
   return (int)blocks;
 }
 
+// (sum, sum of squares) of each row: one warp per row, 16-byte loads, grid-stride over rows.  Read-only pass: rows*d*2 bytes.
+__global__ void __launch_bounds__(kLnWarps * 32)
+row_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int d, float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * kLnWarps;
+  for (int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5); row < rows; row += warps) {
+    const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * ldx;
+    float s = 0.f, q = 0.f;
+    for (int c = lane * 8; c < d; c += 256) {
+      float f[8];
+      load8_bf16(xr + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s += f[i];
+        q = fmaf(f[i], f[i], q);
+      }
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) stats[row] = make_float2(s, q);
+  }
+}
+
+// LayerNorm folded into the Linear that consumes it: one warp per output feature n.
+__global__ void __launch_bounds__(kLnWarps * 32)
+fold_layernorm_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ bias, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int N, int K, __nv_bfloat16* __restrict__ Wf, int64_t ldwf,
+                      float* __restrict__ bias_f, float* __restrict__ colsum) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __bfloat162float(W[n * ldw + k]);
+    const __nv_bfloat16 wf = __float2bfloat16_rn(w * gamma[k]);
+    Wf[n * ldwf + k] = wf;
+    cs += __bfloat162float(wf);
+    bb = fmaf(beta[k], w, bb);
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = (bias ? bias[n] : 0.f) + bb;
+  }
+}
+
 }  // namespace vdr
 
 extern "C" int vdr_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y,
@@ -311,5 +358,30 @@ extern "C" int vdr_layernorm_bwd(const void* dy, int64_t lddy, const void* x, in
   }
   count_launch();
   VDR_CHECK_LAUNCH("layernorm_bwd_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_row_stats(const void* x, int64_t ldx, int rows, int d, float* stats, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(x && stats, VDR_EINVAL, "vdr_row_stats: null pointer");
+  VDR_CHECK_ARG(rows > 0 && d > 0 && d % 8 == 0, VDR_EINVAL, "vdr_row_stats: bad shape rows=%d d=%d (d must be a multiple of 8)", rows, d);
+  VDR_CHECK_ARG(ldx % 8 == 0 && ldx >= d && aligned16(x) && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, VDR_EALIGN,
+                "vdr_row_stats: x must be 16-byte aligned with ldx %% 8 == 0, stats 8-byte aligned");
+  row_stats_kernel<<<ln_grid(rows), kLnWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, rows, d, reinterpret_cast<float2*>(stats));
+  count_launch();
+  VDR_CHECK_LAUNCH("row_stats_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_fold_layernorm(const void* W, int64_t ldw, const float* bias, const float* gamma, const float* beta, int N, int K,
+                                  void* Wf, int64_t ldwf, float* bias_f, float* colsum, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(W && gamma && beta && Wf && bias_f && colsum, VDR_EINVAL, "vdr_fold_layernorm: null pointer");
+  VDR_CHECK_ARG(N > 0 && K > 0 && ldw >= K && ldwf >= K, VDR_EINVAL, "vdr_fold_layernorm: bad shape N=%d K=%d", N, K);
+  fold_layernorm_kernel<<<(N + kLnWarps - 1) / kLnWarps, kLnWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(W), ldw, bias, gamma, beta, N, K, static_cast<__nv_bfloat16*>(Wf), ldwf, bias_f, colsum);
+  count_launch();
+  VDR_CHECK_LAUNCH("fold_layernorm_kernel");
   return VDR_OK;
 }

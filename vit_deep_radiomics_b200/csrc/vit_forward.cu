@@ -13,7 +13,8 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 struct VitPlan {
   int N, Np, d, K, ldk;
   bool tma_patch_embed;
-  size_t off_x, off_y, off_qkv, off_h, off_a, total;
+  bool folded;   // LayerNorms folded into the qkv / fc1 GEMMs (vdr_vit_block::*_wf present)
+  size_t off_x, off_y, off_qkv, off_h, off_a, off_st, total;
 };
 
 int make_plan(const vdr_vit_weights* w, int B, VitPlan* pl) {
@@ -37,6 +38,18 @@ int make_plan(const vdr_vit_weights* w, int B, VitPlan* pl) {
   pl->off_h = off;   off += align256(rows * pl->d * 4 * 2);
   pl->off_a = off;
   if (!pl->tma_patch_embed) off += align256(static_cast<size_t>(B) * pl->Np * pl->ldk * 2);
+  int nf = 0;
+  if (w->blocks != nullptr)
+    for (int l = 0; l < w->depth; ++l) {
+      const vdr_vit_block& b = w->blocks[l];
+      const int have = (b.qkv_wf != nullptr) + (b.qkv_bf != nullptr) + (b.qkv_cs != nullptr) + (b.fc1_wf != nullptr) + (b.fc1_bf != nullptr) + (b.fc1_cs != nullptr);
+      VDR_CHECK_ARG(have == 0 || have == 6, VDR_EINVAL, "vdr_vit_forward: block %d has %d of the 6 folded-LayerNorm pointers (all or none)", l, have);
+      nf += have == 6;
+    }
+  VDR_CHECK_ARG(nf == 0 || nf == w->depth, VDR_EINVAL, "vdr_vit_forward: %d of %d blocks carry folded LayerNorm weights (all or none)", nf, w->depth);
+  pl->folded = nf > 0;
+  pl->off_st = off;
+  if (pl->folded) off += align256(rows * (pl->d / 64) * 8);      // row statistics: d/64 slots of (sum, sumsq) per row
   pl->total = off;
   return VDR_OK;
 }
@@ -87,16 +100,37 @@ extern "C" int vdr_vit_forward(const vdr_vit_weights* w, const void* images_bf16
   if (rc != VDR_OK) return rc;
 
   // ---- transformer blocks (pre-norm): x += proj(attn(LN1 x)); x += fc2(gelu(fc1(LN2 x)))
-  auto gemm = [&](const void* a, int64_t lda, const void* wt, const float* bias, int n, int k, int epi, const void* res, void* c) {
+  float* ST = reinterpret_cast<float*>(ws + pl.off_st);
+  // ln_slots > 0: A is the raw residual stream, normalised in the epilogue from ST; stats = true: emit the statistics of C into ST
+  auto gemm = [&](const void* a, int64_t lda, const void* wt, const float* bias, int n, int k, int epi, const void* res, void* c,
+                  int ln_slots = 0, const float* colsum = nullptr, bool stats = false) {
     vdr_gemm_args g;
     memset(&g, 0, sizeof(g));
     g.A = a; g.lda = lda; g.W = wt; g.ldw = k; g.bias = bias;
     g.R = res; g.ldr = d; g.r_dtype = VDR_DTYPE_BF16;
     g.C = c; g.ldc = n; g.c_dtype = VDR_DTYPE_BF16;
     g.M = M; g.N = n; g.K = k; g.epilogue = epi;
+    if (ln_slots > 0) { g.ln_stats = ST; g.ln_slots = ln_slots; g.ln_eps = eps; g.ln_colsum = colsum; }
+    if (stats) g.stats_out = ST;
     return vdr_gemm(&g, stream);
   };
   const float scale = 1.0f / sqrtf(64.f);
+  if (pl.folded) {
+    // No LayerNorm kernel inside the blocks: the residual GEMMs (in place on X) leave per-row (sum, sumsq) in ST, the qkv / fc1
+    // GEMMs read X itself and apply rstd * (acc - mean * colsum) + bias' in their epilogue.  Layer 0 takes its statistics from a
+    // read-only pass over the patch-embedding output.
+    const int slots = d / 64;
+    if ((rc = vdr_row_stats(X, d, M, d, ST, stream)) != VDR_OK) return rc;
+    for (int l = 0; l < w->depth; ++l) {
+      const vdr_vit_block& b = w->blocks[l];
+      if ((rc = gemm(X, d, b.qkv_wf, b.qkv_bf, 3 * d, d, VDR_EPI_BIAS, nullptr, QKV, l == 0 ? 1 : slots, b.qkv_cs)) != VDR_OK) return rc;
+      if ((rc = vdr_flash_attn_fwd(QKV, 3 * d, Y, d, nullptr, B, N, w->heads, scale, stream)) != VDR_OK) return rc;
+      if ((rc = gemm(Y, d, b.proj_w, b.proj_b, d, d, VDR_EPI_BIAS_RESIDUAL, X, X, 0, nullptr, true)) != VDR_OK) return rc;
+      if ((rc = gemm(X, d, b.fc1_wf, b.fc1_bf, 4 * d, d, VDR_EPI_BIAS_GELU, nullptr, Hb, slots, b.fc1_cs)) != VDR_OK) return rc;
+      if ((rc = gemm(Hb, 4 * d, b.fc2_w, b.fc2_b, d, 4 * d, VDR_EPI_BIAS_RESIDUAL, X, X, 0, nullptr, l + 1 < w->depth)) != VDR_OK) return rc;
+    }
+    return vdr_layernorm_fwd(X, d, w->norm_w, w->norm_b, tokens_out, ld_out, VDR_DTYPE_F32, nullptr, nullptr, M, d, eps, stream);
+  }
   for (int l = 0; l < w->depth; ++l) {
     const vdr_vit_block& b = w->blocks[l];
     if ((rc = vdr_layernorm_fwd(X, d, b.n1w, b.n1b, Y, d, VDR_DTYPE_BF16, nullptr, nullptr, M, d, eps, stream)) != VDR_OK) return rc;

@@ -48,8 +48,14 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, epilogue: str = "bias",
          residual: torch.Tensor | None = None, out: torch.Tensor | None = None, out_dtype=torch.bfloat16,
-         k: int | None = None, out_rows: int | None = None, out_group=(0, 0, 0), res_mod=(0, 0)) -> torch.Tensor:
-    """out = epi(a @ w.T + bias [+ residual]) on tcgen05.  a (M, K[ld]) bf16, w (N, K[ld]) bf16."""
+         k: int | None = None, out_rows: int | None = None, out_group=(0, 0, 0), res_mod=(0, 0),
+         ln_stats: torch.Tensor | None = None, ln_colsum: torch.Tensor | None = None, ln_eps: float = 1e-6,
+         stats_out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = epi(a @ w.T + bias [+ residual]) on tcgen05.  a (M, K[ld]) bf16, w (N, K[ld]) bf16.
+
+    Folded LayerNorm (include/vdr.h, vdr_gemm_args): ``ln_stats`` (slots, M, 2) f32 row statistics of ``a`` + ``ln_colsum`` (N)
+    with ``w`` / ``bias`` from fold_layernorm -> out = epi(LN(a) @ W.T + b); ``stats_out`` (N/64, M, 2) f32 receives the row
+    statistics of what a residual GEMM writes."""
     _req(a, torch.bfloat16, "a"), _req(w, torch.bfloat16, "w")
     if a.dim() != 2 or w.dim() != 2 or a.stride(1) != 1 or w.stride(1) != 1:
         raise ValueError("a and w must be 2-D with unit inner stride")
@@ -77,9 +83,43 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
     args.epilogue = epi
     args.out_group, args.out_group_stride, args.out_offset = out_group
     args.res_mod, args.res_offset = res_mod
+    if ln_stats is not None:
+        _req(ln_stats, torch.float32, "ln_stats"), _req(ln_colsum, torch.float32, "ln_colsum")
+        if ln_stats.dim() != 3 or ln_stats.shape[1:] != (M, 2) or not ln_stats.is_contiguous() or ln_colsum.numel() != N:
+            raise ValueError("ln_stats must be a contiguous (slots, M, 2) table and ln_colsum (N)")
+        args.ln_stats, args.ln_slots, args.ln_eps, args.ln_colsum = ln_stats.data_ptr(), ln_stats.shape[0], ln_eps, ln_colsum.data_ptr()
+    if stats_out is not None:
+        _req(stats_out, torch.float32, "stats_out")
+        if not stats_out.is_contiguous() or stats_out.numel() < (N // 64) * M * 2:
+            raise ValueError("stats_out must be a contiguous f32 buffer of at least (N/64, M, 2)")
+        args.stats_out = stats_out.data_ptr()
     with _Prof("gemm", 2.0 * M * N * K, f"gemm M{M} N{N} K{K} {epilogue}"):
         _C.check(_C.lib().vdr_gemm(C.byref(args), _stream()), "vdr_gemm")
     return out
+
+
+def row_stats(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(1, rows, 2) f32 table of (sum, sum of squares) per row of the bf16 matrix x: the one-slot form gemm(ln_stats=) reads."""
+    _req(x, torch.bfloat16, "x")
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty((1, rows, 2), dtype=torch.float32, device=x.device)
+    with _Prof("ln", 2.0 * rows * d, f"row_stats {rows}x{d}"):
+        _C.check(_C.lib().vdr_row_stats(x.data_ptr(), x.stride(0), rows, d, out.data_ptr(), _stream()), "vdr_row_stats")
+    return out
+
+
+def fold_layernorm(w: torch.Tensor, bias: torch.Tensor | None, gamma: torch.Tensor, beta: torch.Tensor):
+    """(W', b', colsum) of LayerNorm(gamma, beta) folded into the Linear (w bf16 (N, K), bias f32) that consumes it."""
+    _req(w, torch.bfloat16, "w"), _req(gamma, torch.float32, "gamma"), _req(beta, torch.float32, "beta")
+    N, K = w.shape
+    wf = torch.empty_like(w)
+    bf = torch.empty(N, dtype=torch.float32, device=w.device)
+    cs = torch.empty(N, dtype=torch.float32, device=w.device)
+    _C.check(_C.lib().vdr_fold_layernorm(w.data_ptr(), w.stride(0), bias.data_ptr() if bias is not None else None, gamma.data_ptr(),
+                                         beta.data_ptr(), N, K, wf.data_ptr(), wf.stride(0), bf.data_ptr(), cs.data_ptr(), _stream()),
+             "vdr_fold_layernorm")
+    return wf, bf, cs
 
 
 def im2col_patches(src: torch.Tensor, strides, B: int, H: int, W: int, patch: int,

@@ -15,7 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .models_archs import TransformerNoduleClassifier
+from .models_archs import TransformerNoduleBimodalClassifier, TransformerNoduleClassifier
 
 
 def positional_encoding_3d(x, y, z, D, scale=10000):
@@ -68,6 +68,38 @@ class FocalLoss(nn.Module):
         return F.nll_loss(logpt, cls_idx, self.weight, reduction="sum")
 
 
+class CrossModalFocalLoss(nn.Module):
+    """reference: train_models.py:332-378 -- bimodal focal term on the fused logits plus two unimodal
+    focal terms whose modulating factor uses the harmonic mean of the two unimodal probabilities:
+    beta * L_petct + (1-beta) * (L_ct + L_pet), each a class-weighted MEAN nll (FocalLoss sums)."""
+
+    def __init__(self, gamma_bimodal=0, gamma_unimodal=2, alpha=None, beta=0.5):
+        super().__init__()
+        self.gamma_bimodal, self.gamma_unimodal = gamma_bimodal, gamma_unimodal
+        self.alpha, self.beta, self.eps = alpha, beta, 1e-8
+
+    def forward(self, inputs_petct, inputs_ct, inputs_pet, targets):
+        if inputs_petct.dim() == 1:
+            inputs_petct, inputs_ct, inputs_pet, targets = (t.unsqueeze(0) for t in (inputs_petct, inputs_ct, inputs_pet, targets))
+        cls_idx = torch.argmax(targets, dim=1)
+        lp_x, lp_c, lp_p = (F.log_softmax(t, dim=1) for t in (inputs_petct, inputs_ct, inputs_pet))
+        nll = lambda lp: F.nll_loss(lp, cls_idx, self.alpha, reduction="mean")          # noqa: E731
+        loss_x = nll((1 - torch.exp(lp_x)) ** self.gamma_bimodal * lp_x)
+        pt_c, pt_p = torch.exp(lp_c), torch.exp(lp_p)
+        pt_mean = (2 * pt_c * pt_p) / (pt_c + pt_p + self.eps)
+        loss_c = nll((1 - pt_mean * pt_c) ** self.gamma_unimodal * lp_c)
+        loss_p = nll((1 - pt_mean * pt_p) ** self.gamma_unimodal * lp_p)
+        return self.beta * loss_x + (1 - self.beta) * (loss_c + loss_p)
+
+
+def make_criterion(loss_func, device):
+    """reference: train_models.py:591-598 -- class weights (0.25, 0.75); 'crossmodal' = gamma 2 / 1, beta 0.6."""
+    alpha = torch.tensor([0.25, 0.75], device=device)
+    if loss_func == "crossmodal":
+        return CrossModalFocalLoss(alpha=alpha, gamma_unimodal=2.0, gamma_bimodal=1.0, beta=0.6)
+    return FocalLoss(alpha=alpha, gamma=2.0)
+
+
 def get_y_true_and_pred(y_true, y_pred, cpu=False):
     """reference: train_models.py:283-311."""
     y_true, y_pred = torch.squeeze(y_true), torch.squeeze(y_pred)
@@ -82,11 +114,14 @@ def get_y_true_and_pred(y_true, y_pred, cpu=False):
 
 
 def build_model(cfg, arch, modality, modality_a="pet", modality_b="ct", num_classes=2):
-    """reference: train_models.py:455-486.  Only the unimodal transformer is on the hot path."""
+    """reference: train_models.py:455-486.  'petct'/'petchest' build the bimodal classifier with the CT
+    encoder configured from ``modality_b`` and the PET encoder from ``modality_a`` (:459-472)."""
     cfg_model = cfg["models"][arch]
     feature_dim = cfg_model["feature_dim"]
     if modality in ("petct", "petchest"):
-        raise NotImplementedError("bimodal PET+CT classifier is scope row N4 (next)")
+        ct, pet = cfg_model[modality_b], cfg_model[modality_a]
+        return TransformerNoduleBimodalClassifier(feature_dim, ct["mlp_ratio"], pet["mlp_ratio"], ct["num_heads"], pet["num_heads"],
+                                                  ct["num_layers"], pet["num_layers"], num_classes=num_classes)
     if arch == "conv":
         raise NotImplementedError("Conv3d classifier is out of scope (north star names the transformer)")
     m = cfg_model[modality]
@@ -105,7 +140,9 @@ def make_optimizer(model, cfg, arch="transformer"):
 def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, grad_sync=None):
     """One pass of the reference's accumulation loop (train_models.py:652-688).
 
-    samples: iterable of (tokens (n, d) f32 CUDA, one-hot label (C,) f32 CUDA).
+    samples: iterable of (tokens (n, d) f32 CUDA, one-hot label (C,) f32 CUDA); for the bimodal model
+    (tokens_ct, tokens_pet, label), and ``criterion`` may be CrossModalFocalLoss (:668-672: it takes
+    outputs[0], outputs[2], outputs[3]).
     Loss is divided by iters_to_accumulate = min(virtual_batch, len(samples)) (:655,674); the optimizer
     steps every iters_to_accumulate samples and at the last sample (:685-687).  ``grad_sync`` (optional
     callable) is invoked right before each optimizer step: the data-parallel gradient all-reduce.
@@ -115,9 +152,14 @@ def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, gra
     model.train()
     optimizer.zero_grad()
     total, scores = 0.0, []
-    for i, (tokens, label) in enumerate(samples):
-        logits, _ = model(tokens.unsqueeze(0))
-        loss = criterion(torch.squeeze(logits), label) / iters
+    for i, sample in enumerate(samples):
+        label = sample[-1]
+        outputs = model(*(t.unsqueeze(0) for t in sample[:-1]))
+        logits = outputs[0]
+        if isinstance(criterion, CrossModalFocalLoss):
+            loss = criterion(torch.squeeze(logits), torch.squeeze(outputs[2]), torch.squeeze(outputs[3]), label) / iters
+        else:
+            loss = criterion(torch.squeeze(logits), label) / iters
         loss.backward()
         total += float(loss.item()) * iters
         scores.append(torch.softmax(logits.detach(), dim=1)[0].cpu().numpy())

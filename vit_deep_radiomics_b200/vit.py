@@ -12,6 +12,7 @@ are bf16 with fp32 accumulation; the final LayerNorm writes fp32 descriptors.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -101,13 +102,21 @@ class ViTBackbone:
                 n2w=f32(b + "norm2.weight"), n2b=f32(b + "norm2.bias"),
                 fc1_w=bf(b + "mlp.fc1.weight"), fc1_b=f32(b + "mlp.fc1.bias"),
                 fc2_w=bf(b + "mlp.fc2.weight"), fc2_b=f32(b + "mlp.fc2.bias")))
+        self._folded = bool(self.fold_layernorm)
+        if self._folded:
+            # norm1 -> qkv and norm2 -> fc1 folded (vdr_fold_layernorm): the blocks then run no LayerNorm kernel
+            for blk in self.w["blocks"]:
+                blk["qkv_wf"], blk["qkv_bf"], blk["qkv_cs"] = ops.fold_layernorm(blk["qkv_w"], blk["qkv_b"], blk["n1w"], blk["n1b"])
+                blk["fc1_wf"], blk["fc1_bf"], blk["fc1_cs"] = ops.fold_layernorm(blk["fc1_w"], blk["fc1_b"], blk["n2w"], blk["n2b"])
         self.K, self.ldk = K, ldk
         # the same pointers as a vdr_vit_weights struct: the whole forward is then one C call (vdr_vit_forward)
         import ctypes as C
         blocks = (_C.VitBlock * self.cfg["depth"])()
         for i, blk in enumerate(self.w["blocks"]):
-            for name in ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b"):
-                setattr(blocks[i], name, blk[name].data_ptr())
+            for name in ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                         "qkv_wf", "qkv_bf", "qkv_cs", "fc1_wf", "fc1_bf", "fc1_cs"):
+                if name in blk:
+                    setattr(blocks[i], name, blk[name].data_ptr())
         w = self.w
         self._native_blocks = blocks          # keeps the array alive
         self._native = _C.VitWeights(d, self.cfg["depth"], self.cfg["heads"], p, self.img_hw[0], self.img_hw[1], 1e-6,
@@ -175,6 +184,22 @@ class ViTBackbone:
         ops.write_cls_rows(w["cls"], w["pos"], ws["X"], B, N, d)
         X, Y, QKV, Hb = ws["X"], ws["Y"], ws["QKV"], ws["H"]
         scale = 1.0 / math.sqrt(64)
+        if self._folded:
+            # same kernels in the same order as vdr_vit_forward's folded path: the residual GEMMs leave the row statistics in ST,
+            # the qkv / fc1 GEMMs read the raw residual stream X and normalise in their epilogue
+            if "ST" not in ws:
+                ws["ST"] = torch.empty(d // 64, B * N, 2, dtype=torch.float32, device=self.device)
+            ST = ws["ST"]
+            ops.row_stats(X, out=ST[:1])
+            depth = len(w["blocks"])
+            for i, blk in enumerate(w["blocks"]):
+                ops.gemm(X, blk["qkv_wf"], blk["qkv_bf"], out=QKV, ln_stats=ST[:1] if i == 0 else ST, ln_colsum=blk["qkv_cs"])
+                ops.flash_attn(QKV, B, N, heads, scale, out=Y)
+                ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X, stats_out=ST)
+                ops.gemm(X, blk["fc1_wf"], blk["fc1_bf"], epilogue="gelu", out=Hb, ln_stats=ST, ln_colsum=blk["fc1_cs"])
+                ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X, stats_out=ST if i + 1 < depth else None)
+            ops.layernorm(X, w["norm_w"], w["norm_b"], 1e-6, out=ws["OUT"])
+            return ws["OUT"]
         for blk in w["blocks"]:
             ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
             ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=QKV)
@@ -185,6 +210,9 @@ class ViTBackbone:
             ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X)
         ops.layernorm(X, w["norm_w"], w["norm_b"], 1e-6, out=ws["OUT"])
         return ws["OUT"]
+
+    #: fold norm1 / norm2 into the qkv / fc1 GEMMs (set False before prepare() for the LayerNorm-kernel path)
+    fold_layernorm = os.environ.get("VDR_NO_LN_FOLD") is None     # the env switch exists for A/B timing only
 
     #: route forward_volume through vdr_vit_forward (per-kernel profiling, ops.PROFILE, always uses the op-by-op path)
     use_native_forward = True
