@@ -1,4 +1,5 @@
-"""Debug: per-tile timeline of CTA 0 of the GEMM kernel (producer / MMA / epilogue timestamps, ns)."""
+"""Debug: per-tile timeline of CTA 0 of the GEMM kernel (producer / MMA / epilogue timestamps, ns).
+Needs a trace build: `make -C vit_deep_radiomics_b200/csrc EXTRA=-DVDR_GEMM_TRACE` (the stamps are compiled out otherwise)."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

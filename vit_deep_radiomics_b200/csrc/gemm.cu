@@ -21,10 +21,15 @@ __device__ __forceinline__ unsigned long long gtime() {
 // trace record (CTA 0 only): slot = tile_iter * 16 + event  (events 8.. = epilogue warp 0, chunks 0 and 1)
 //   0 mma: accumulator free   1 mma: first stage landed   2 mma: last MMA issued
 //   3 epi: accumulator ready  4 epi: tile stored          5 producer: first TMA of tile issued  6 producer: last TMA issued
+// (compiled in only with -DVDR_GEMM_TRACE, tools/gemm_trace.py: the checks sit in the per-chunk epilogue body)
+#ifdef VDR_GEMM_TRACE
 #define VDR_TRACE(ev, it)                                                                      \
   do {                                                                                         \
     if (p.trace != nullptr && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 16 + (ev)] = gtime(); \
   } while (0)
+#else
+#define VDR_TRACE(ev, it) do { } while (0)
+#endif
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
@@ -79,7 +84,10 @@ struct GemmCfg {
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
-template <int BN, int kCtas, bool kRes>
+// kFold >= 0 fixes the epilogue at compile time -- bit 0: ln_stats consumer, bit 1: stats_out producer, bits 2..3: epilogue
+// selector -- so that the per-chunk epilogue body carries neither branches nor dead code for the other roles (3 % on the K = 768
+// shapes); -1 reads everything from the parameters.
+template <int BN, int kCtas, bool kRes, int kFold>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
@@ -249,7 +257,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&ln_empty[buf], ((it >> 1) & 1) ^ 1u);
       const int m0 = (tile / n_tiles) * kTileM + static_cast<int>(cta_rank) * BM, n0 = (tile % n_tiles) * BN;
       for (int i = lane; i < BN; i += 32) bias_smem[buf * BN + i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-      if (p.ln_stats != nullptr) {
+      if (kFold >= 0 ? (kFold & 1) != 0 : p.ln_stats != nullptr) {
         for (int i = lane; i < BN; i += 32) csum_smem[buf * BN + i] = (n0 + i < p.N) ? __ldg(p.ln_colsum + n0 + i) : 0.f;
         float su[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
         for (int sl = 0; sl < p.ln_slots; ++sl) {
@@ -280,15 +288,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kColsPerWarp = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool ln_in = p.ln_stats != nullptr, st_out = p.stats_out != nullptr;
-    const bool res_bf16 = p.epilogue == VDR_EPI_BIAS_RESIDUAL && p.r_dtype == VDR_DTYPE_BF16;
+    const int epi_sel = kFold >= 0 ? (kFold >> 2) : p.epilogue;
+    const bool ln_in = kFold >= 0 ? (kFold & 1) != 0 : p.ln_stats != nullptr;
+    const bool st_out = kFold >= 0 ? (kFold & 2) != 0 : p.stats_out != nullptr;
+    // (the specialised instantiations are only dispatched for bf16 outputs through TMA stores with N a multiple of BN, and --
+    //  kRes -- for a bf16 residual through TMA loads: see launch_gemm)
+    const bool res_bf16 = (kFold >= 0 && kRes) ? true : (epi_sel == VDR_EPI_BIAS_RESIDUAL && p.r_dtype == VDR_DTYPE_BF16);
     // Per-warp staging tile (32 rows x 64 B, 16-byte chunks XOR-swizzled): accumulators arrive with
     // thread == row, but global memory wants consecutive lanes on consecutive addresses.  Going through
     // this tile turns 32 scattered 16-byte accesses per instruction into 8 rows x 64 contiguous bytes.
     const uint32_t stg = stage_base + ew * Cfg::kEpiBufBytes, rbuf = stg + 2048;
     auto sw = [](int row, int chunk) -> uint32_t { return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); };   // = TMA SWIZZLE_64B
     const int crow = lane >> 2, cchk = lane & 3;   // coalesced layout: rows crow + 8 i, 16-byte chunk cchk
-    const bool tma_store = p.tma_out >= 1, tma_res = Cfg::kResTma && res_bf16 && p.tma_out >= 2;
+    const bool tma_store = kFold >= 0 ? true : p.tma_out >= 1;
+    const bool tma_res = (kFold >= 0 && kRes) ? Cfg::kResTma : (Cfg::kResTma && res_bf16 && p.tma_out >= 2);
     uint32_t res_phase = 0;
     int it = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
@@ -360,7 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int col0 = half * kColsPerWarp + c;
         if (!tma_res && c + 32 < kColsPerWarp) load_res(rnxt, c + 32);   // overlap the next residual chunk with this one
         const int n0 = n_blk * BN + col0;
-        const bool fast = p.c_dtype == VDR_DTYPE_BF16 && n0 + 32 <= p.N;
+        const bool fast = kFold >= 0 ? true : (p.c_dtype == VDR_DTYPE_BF16 && n0 + 32 <= p.N);
         uint4 rr[4];
         if (fast && res_bf16) {
           if (tma_res) {   // residual tile landed by TMA: this thread's row, then start the next chunk into the same tile
@@ -423,12 +436,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v2[g * 4 + 3] = add2(pack2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])), pack2(b1.z, b1.w));
           }
           }
-          if (p.epilogue == VDR_EPI_BIAS_GELU) {
+          if (epi_sel == VDR_EPI_BIAS_GELU) {
             // all 16 pairs step by step: 16 independent dependency chains in flight.  (A cheaper x * sigmoid(quintic) form -- half the
             // FMA-pipe work, 2.6e-5 from erf -- was measured and changes nothing: at K = 768 the tile time is set by the L2 -> SM
             // operand feed, ~64 B/clk per SM demanded against ~45 delivered, not by this arithmetic.)
             gelu_fast2_x16(v2);
-          } else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL) {
+          } else if (epi_sel == VDR_EPI_BIAS_RESIDUAL) {
             if (res_bf16) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -513,8 +526,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 8; ++i) {
                 if (n + i < p.N) {
                   float v = __uint_as_float(r[g * 8 + i]) + sbias[c + g * 8 + i];
-                  if (p.epilogue == VDR_EPI_BIAS_GELU) v = gelu_fast(v);
-                  else if (p.epilogue == VDR_EPI_BIAS_RESIDUAL)
+                  if (epi_sel == VDR_EPI_BIAS_GELU) v = gelu_fast(v);
+                  else if (epi_sel == VDR_EPI_BIAS_RESIDUAL)
                     v += (p.r_dtype == VDR_DTYPE_BF16) ? __bfloat162float(Rb[res_row * p.ldr + n + i])
                                                        : static_cast<const float*>(p.R)[res_row * p.ldr + n + i];
                   if (p.c_dtype == VDR_DTYPE_BF16) Cb[out_row * p.ldc + n + i] = __float2bfloat16_rn(v);
@@ -553,13 +566,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int kCtas, bool kRes>
+template <int BN, int kCtas, bool kRes, int kFold>
 static int launch_gemm_(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR, const GemmParams& p, int grid,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kCtas, kRes>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kCtas, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kCtas, kRes, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
@@ -576,7 +589,7 @@ static int launch_gemm_(const CUtensorMap& tmA, const CUtensorMap& tmW, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kCtas, kRes>, tmA, tmW, tmC, tmR, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kCtas, kRes, kFold>, tmA, tmW, tmC, tmR, p);
   count_launch();
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tcgen05_kernel)");
   VDR_CHECK_LAUNCH("gemm_tcgen05_kernel");
@@ -586,8 +599,23 @@ static int launch_gemm_(const CUtensorMap& tmA, const CUtensorMap& tmW, const CU
 template <int BN, int kCtas>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR, const GemmParams& p, int grid,
                        cudaStream_t stream) {
-  if (p.tma_out >= 2) return launch_gemm_<BN, kCtas, true>(tmA, tmW, tmC, tmR, p, grid, stream);
-  return launch_gemm_<BN, kCtas, false>(tmA, tmW, tmC, tmR, p, grid, stream);
+  if constexpr (BN == 256 && kCtas == 2) {   // the hot configuration: one instantiation per epilogue / folded-LayerNorm role
+    const int fold = (p.ln_stats != nullptr ? 1 : 0) | (p.stats_out != nullptr ? 2 : 0);
+    const bool spec = p.tma_out >= 1 && p.c_dtype == VDR_DTYPE_BF16 && p.N % BN == 0 && p.trace == nullptr;
+    if (p.tma_out >= 2) {   // bf16 residual through TMA
+      if (spec && fold == 0) return launch_gemm_<BN, kCtas, true, (VDR_EPI_BIAS_RESIDUAL << 2) | 0>(tmA, tmW, tmC, tmR, p, grid, stream);
+      if (spec && fold == 2) return launch_gemm_<BN, kCtas, true, (VDR_EPI_BIAS_RESIDUAL << 2) | 2>(tmA, tmW, tmC, tmR, p, grid, stream);
+      return launch_gemm_<BN, kCtas, true, -1>(tmA, tmW, tmC, tmR, p, grid, stream);
+    }
+    if (spec && p.epilogue == VDR_EPI_BIAS && fold == 0) return launch_gemm_<BN, kCtas, false, (VDR_EPI_BIAS << 2) | 0>(tmA, tmW, tmC, tmR, p, grid, stream);
+    if (spec && p.epilogue == VDR_EPI_BIAS && fold == 1) return launch_gemm_<BN, kCtas, false, (VDR_EPI_BIAS << 2) | 1>(tmA, tmW, tmC, tmR, p, grid, stream);
+    if (spec && p.epilogue == VDR_EPI_BIAS_GELU && fold == 0) return launch_gemm_<BN, kCtas, false, (VDR_EPI_BIAS_GELU << 2) | 0>(tmA, tmW, tmC, tmR, p, grid, stream);
+    if (spec && p.epilogue == VDR_EPI_BIAS_GELU && fold == 1) return launch_gemm_<BN, kCtas, false, (VDR_EPI_BIAS_GELU << 2) | 1>(tmA, tmW, tmC, tmR, p, grid, stream);
+    return launch_gemm_<BN, kCtas, false, -1>(tmA, tmW, tmC, tmR, p, grid, stream);
+  } else {
+    if (p.tma_out >= 2) return launch_gemm_<BN, kCtas, true, -1>(tmA, tmW, tmC, tmR, p, grid, stream);
+    return launch_gemm_<BN, kCtas, false, -1>(tmA, tmW, tmC, tmR, p, grid, stream);
+  }
 }
 
 }  // namespace vdr
