@@ -134,6 +134,23 @@ def test_gemm_folded_layernorm_argument_errors(cuda):
         ops.gemm(a, w, None, ln_stats=torch.zeros(1, 63, 2, device=cuda), ln_colsum=torch.zeros(96, device=cuda))
 
 
+def test_gemm_gelu_epilogue_accuracy_over_the_whole_range(cuda):
+    """The bf16 epilogue's GELU (x * sigmoid of an odd quintic) against the erf form: identity weights so
+    that every output is gelu(a[m, n]); inputs sweep [-12, 12] plus saturated values.  Bound: 3e-5 absolute + one bf16 rounding."""
+    from vit_deep_radiomics_b200 import ops
+    M, N = 4096, 64
+    a = torch.linspace(-12, 12, M * N, device=cuda).reshape(M, N)
+    a[0, :8] = torch.tensor([-100.0, -30.0, -16.0, 16.0, 30.0, 100.0, 0.0, -0.0], device=cuda)
+    a = a.bfloat16()
+    w = torch.eye(N, device=cuda).bfloat16()
+    out = ops.gemm(a, w, None, epilogue="gelu").double()
+    ref = torch.nn.functional.gelu(a.double())
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs()
+    assert (err <= 3e-5 + ref.abs() * 2.0 ** -8).all(), float(err.max())
+    assert float(out[0, 0]) == 0.0 and float(out[0, 5]) == 100.0 and float(out[0, 4]) == 30.0
+
+
 def test_gemm_k_tail_and_row_remap(cuda):
     """K = 588 (14x14 patches) inside ld 592, rows written behind a CLS row, pos-embed as residual."""
     from vit_deep_radiomics_b200 import ops

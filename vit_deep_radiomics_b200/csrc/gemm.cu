@@ -437,10 +437,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           }
           if (epi_sel == VDR_EPI_BIAS_GELU) {
-            // all 16 pairs step by step: 16 independent dependency chains in flight.  (A cheaper x * sigmoid(quintic) form -- half the
-            // FMA-pipe work, 2.6e-5 from erf -- was measured and changes nothing: at K = 768 the tile time is set by the L2 -> SM
-            // operand feed, ~64 B/clk per SM demanded against ~45 delivered, not by this arithmetic.)
+            // all 16 pairs step by step: 16 independent dependency chains in flight
+#ifdef VDR_GELU_AS
             gelu_fast2_x16(v2);
+#else
+            gelu_sig2_x16(v2);
+#endif
           } else if (epi_sel == VDR_EPI_BIAS_RESIDUAL) {
             if (res_bf16) {
 #pragma unroll
