@@ -29,7 +29,7 @@ constexpr int kSoftmaxWarps = 8;
 constexpr int kAttnThreads = (kSoftmaxWarps + 4) * 32;   // 2 softmax warpgroups + issuer warpgroup
 constexpr int kBQ = 128, kBKV = 128, kHD = 64;
 constexpr int kTileBytes = 128 * kHD * 2;               // 16 KB: one 128 x 64 bf16 tile
-constexpr int kAttnSmem = 5 * kTileBytes /*Q, 4 ring slots*/ + 256 /*barriers*/ + 3 * 2 * 128 * 4 /*max exchange x2, sum exchange*/ + 8 * 2 * 128 /*trailing keys: K, V rows*/;
+constexpr int kAttnSmem = 5 * kTileBytes /*Q, 4 ring slots*/ + 256 /*barriers*/ + 3 * 2 * 128 * 4 /*max exchange x2, sum exchange*/ + 8 * 2 * 128 /*trailing keys: K, V rows*/ + 8 * 128 * 4 /*trailing keys: q . k per query row*/;
 constexpr uint32_t kPolyMask = VDR_ATTN_POLY_MASK;        // which of every 8 column pairs take the polynomial exp2 (bit i = pair i)
 constexpr int kAttnTmemCols = 256;                       // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 
@@ -256,6 +256,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   float* s_max = reinterpret_cast<float*>(smem + 5 * kTileBytes + 256);   // [2][2][128]
   float* s_sum = s_max + 2 * 2 * 128;                                      // [2][128]
   uint4* s_tail = reinterpret_cast<uint4*>(s_sum + 2 * 128);               // [tail_keys][K row (8 x 16 B) | V row (8 x 16 B)]
+  float* s_dot = reinterpret_cast<float*>(s_tail + 8 * 16);                // [tail_keys][128] q . k of every query row (unscaled)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
@@ -350,6 +351,33 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         s_tail[i] = __ldg(reinterpret_cast<const uint4*>(krow + (c < 8 ? colK : colV)) + (c & 7));
       }
       __syncwarp();
+      // ... and their scores: this warp is otherwise idle, so it evaluates q . k for the 128 query rows while the key blocks
+      // stream through the tensor pipe (the softmax threads used to do it in their epilogue, twice per row: 200 of the 750
+      // instructions a softmax warp spends per CTA outside the block loop)
+      if (tail_keys > 0) {
+        mbar_wait_relaxed(bar_q, 0);
+        for (int t = 0; t < tail_keys; ++t) {
+          for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            float acc = 0.f;
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {
+              uint4 qu;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qu.x), "=r"(qu.y), "=r"(qu.z), "=r"(qu.w)
+                           : "r"(sQ + r * 128 + ((c ^ (r & 7)) << 4)));
+              const uint4 u = s_tail[t * 16 + c];
+              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              const float2 q0v = unpack_bf16x2(qu.x), q1v = unpack_bf16x2(qu.y), q2v = unpack_bf16x2(qu.z), q3v = unpack_bf16x2(qu.w);
+              acc = fmaf(q0v.x, a0.x, acc); acc = fmaf(q0v.y, a0.y, acc);
+              acc = fmaf(q1v.x, a1.x, acc); acc = fmaf(q1v.y, a1.y, acc);
+              acc = fmaf(q2v.x, a2.x, acc); acc = fmaf(q2v.y, a2.y, acc);
+              acc = fmaf(q3v.x, a3.x, acc); acc = fmaf(q3v.y, a3.y, acc);
+            }
+            s_dot[t * 128 + r] = acc;
+          }
+        }
+        __syncwarp();
+      }
       if (lane == 0) mbar_arrive(bar_tail);
     } else if (warp == kSoftmaxWarps + 1 && lane == 0) {
       // ---- V tiles + O += P V
@@ -558,24 +586,10 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     }
     if (tail_keys && p.dbg != 2) {
       mbar_wait(bar_tail, 0);
-      // both half-row threads evaluate the same full 64-wide dot products (same order -> identical m_ref / sums)
-      // and fold the key's V into their own 32 columns; the trailing key's probability is added to half 0's sum only
+      // both half-row threads read the same score (-> identical m_ref / sums) and fold the key's V into their own 32 columns;
+      // the trailing key's probability is added to half 0's sum only
       for (int t = 0; t < tail_keys; ++t) {
-        float sd0 = 0.f, sd1 = 0.f, sd2 = 0.f, sd3 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 qu;   // this thread's query row from the swizzled Q tile
-          asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qu.x), "=r"(qu.y), "=r"(qu.z), "=r"(qu.w)
-                       : "r"(sQ + row * 128 + ((c ^ (row & 7)) << 4)));
-          const uint4 u = s_tail[t * 16 + c];
-          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-          const float2 q0v = unpack_bf16x2(qu.x), q1v = unpack_bf16x2(qu.y), q2v = unpack_bf16x2(qu.z), q3v = unpack_bf16x2(qu.w);
-          sd0 = fmaf(q0v.x, a0.x, sd0); sd0 = fmaf(q0v.y, a0.y, sd0);
-          sd1 = fmaf(q1v.x, a1.x, sd1); sd1 = fmaf(q1v.y, a1.y, sd1);
-          sd2 = fmaf(q2v.x, a2.x, sd2); sd2 = fmaf(q2v.y, a2.y, sd2);
-          sd3 = fmaf(q3v.x, a3.x, sd3); sd3 = fmaf(q3v.y, a3.y, sd3);
-        }
-        const float sdot = ((sd0 + sd1) + (sd2 + sd3)) * p.scale_log2;
+        const float sdot = s_dot[t * 128 + row] * p.scale_log2;   // q . k from the prefetch warp
         const float m_new = fmaxf(m_ref, sdot);
         const float a = ex2(m_ref - m_new);
         const float pj = __bfloat162float(__float2bfloat16_rn(ex2(sdot - m_new)));   // same bf16 rounding of P as the MMA path
