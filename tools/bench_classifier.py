@@ -58,6 +58,10 @@ def main():
                 allreduce_grads(model)
                 opt.step()
                 opt.zero_grad()
+        if world > 1:   # the loss trajectory is over ALL samples of the epoch, not rank 0's share
+            t = torch.tensor([tot, float(len(data))], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t)
+            return float(t[0] / t[1])
         return tot / len(data)
 
     losses = [epoch()]                                                     # warm-up epoch (also first loss)
