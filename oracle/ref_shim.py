@@ -203,6 +203,30 @@ def load_reference(name: str):
     return m
 
 
+class legacy_series_getitem:
+    """Context manager for running reference code written for pandas < 2: ``series[0]`` on a Series with a non-integer index
+    falls back to position 0 (the behaviour the reference's prepare_df relies on, train_models.py:424).  Test-only."""
+
+    def __enter__(self):
+        import pandas as pd
+        self._pd, self._orig = pd, pd.Series.__getitem__
+        orig = self._orig
+
+        def getitem(ser, key):
+            try:
+                return orig(ser, key)
+            except KeyError:
+                if isinstance(key, (int, np.integer)) and not pd.api.types.is_integer_dtype(ser.index):
+                    return ser.iloc[key]
+                raise
+        pd.Series.__getitem__ = getitem
+        return self
+
+    def __exit__(self, *exc):
+        self._pd.Series.__getitem__ = self._orig
+        return False
+
+
 def put_feature_file(path: str, patient_id: str, features: list, masks: list):
     """Fill an in-memory 'HDF5' file with the layout save_features() writes
     (tfds_dense_descriptor.py:156-165): <pid>/features/<i>, <pid>/masks/<i>."""
@@ -210,3 +234,24 @@ def put_feature_file(path: str, patient_id: str, features: list, masks: list):
     for i, (f, m) in enumerate(zip(features, masks)):
         store[f"{patient_id}/features/{i}"] = np.asarray(f)
         store[f"{patient_id}/masks/{i}"] = np.asarray(m)
+
+
+def make_dataset_table(seed=0, D=12):
+    """A three-patient CT + PET table in the layout the reference's parquet has (one row per stored slice and per
+    flip / angle copy), with the slice features and masks in the in-memory 'HDF5' files of ref_shim."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    rows = []
+    H5_FILES.clear()
+    for pid, nct, npet, lab in (("P1", 20, 6, 0), ("P2", 15, 4, 1), ("P3", 9, 3, 0), ("P4", 30, 9, 1)):
+        for mod, n, path, res in (("ct", nct, "ct.h5", (1.0, 1.0, 2.0)), ("pet", npet, "pet.h5", (4.0, 4.0, 3.0))):
+            feats, masks, fid = [], [], 0
+            for flip, angle in (("None", 0), ("H", 90), ("V", 45)):
+                for s_ in range(n):
+                    rows.append(dict(patient_id=pid, modality=mod, slice=s_, feature_id=fid, flip=flip, angle=angle, label=lab,
+                                     dataset="d", spatial_res=res))
+                    fid += 1
+                    feats.append(rng.standard_normal((4, 5, D)).astype(np.float32))
+                    masks.append(rng.random((16, 20)) < 0.4)
+            put_feature_file(path, pid, feats, masks)
+    return pd.DataFrame(rows)

@@ -416,3 +416,26 @@ def test_bimodal_classifier_vs_golden(cuda, golden_dir, mode):
         assert cos > 0.99 and rel < 0.15, (name, cos, rel)
         checked += 1
     assert checked >= 15
+
+
+@pytest.mark.parametrize("augment", [False, True])
+def test_dataset_items_on_device_match_oracle_gather(cuda, augment):
+    """PETCTDataset3D (scope row N3) with the device gather: every item's CT / PET token sequences are bit-identical to the
+    same dataset run with the CPU oracle gather (which tests/test_oracle_vs_reference.py pins to the reference's items)."""
+    from oracle import gather_np as G
+    from oracle import ref_shim
+    from vit_deep_radiomics_b200 import train_models as tm
+    D = 12
+    df = tm.prepare_df(ref_shim.make_dataset_table(seed=5, D=D))
+    enc = tm.get_label_encoder(df)
+    kw = dict(use_augmentation=augment, feature_dim=D, arch="transformer", store=ref_shim.H5_FILES)
+    dev_ds = tm.PETCTDataset3D(df, enc, "ct.h5", "pet.h5", device=cuda, **kw)
+    cpu_ds = tm.PETCTDataset3D(df, enc, "ct.h5", "pet.h5", gather=lambda f, m, r, n, d: G.token_gather(f, m, r, n, d)["tokens"], **kw)
+    assert len(dev_ds) == len(cpu_ds) > 0
+    for i in range(len(dev_ds)):
+        np.random.seed(7 + i)
+        a = dev_ds[i]
+        np.random.seed(7 + i)
+        b = cpu_ds[i]
+        assert a[0].is_cuda and a[1].is_cuda and a[3] == b[3] and torch.equal(a[2], b[2])
+        assert torch.equal(a[0].cpu(), b[0]) and torch.equal(a[1].cpu(), b[1])

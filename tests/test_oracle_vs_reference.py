@@ -78,3 +78,64 @@ def test_bimodal_classifier_against_reference_module():
             got = C.bimodal_forward(sd, a, b, 2, 2, 2, 1)
             for w, g in zip(want, got):
                 assert torch.allclose(w.reshape(g.shape), g, atol=1e-5)
+
+
+_dataset_table = ref_shim.make_dataset_table
+
+
+def test_prepare_df_and_label_encoder_match_reference():
+    """train_models.py:416-448 run unmodified (under the pandas < 2 indexing shim it was written for) against the port."""
+    import warnings
+
+    import pandas as pd
+    from vit_deep_radiomics_b200 import train_models as ours
+    tm = ref_shim.load_reference("train_models")
+    df = _dataset_table()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with ref_shim.legacy_series_getitem():
+            want = tm.prepare_df(df.copy())
+    got = ours.prepare_df(df.copy())
+    pd.testing.assert_frame_equal(want, got, check_dtype=False)
+    assert "divisor" not in df.columns                                  # the port does not modify its argument
+    assert got[got.modality == "ct"].groupby("patient_id_new")["slice"].nunique().max() == 14      # 13 + 1: inclusive bounds
+    assert got[(got.patient_id == "P3") & (got.modality == "ct")]["patient_id_new"].unique().tolist() == ["P3:0"]   # 9 slices, window 8
+    a, b = tm.get_label_encoder(got), ours.get_label_encoder(got)
+    x = np.array([[0], [1], [1]])
+    assert np.array_equal(a.transform(x).toarray(), b.transform(x).toarray())
+    assert [ours.find_divisor(n, m) for n, m in ((40, "ct"), (5, "chest"), (9, "pet"), (1, "pet"))] == \
+           [int(tm.find_divisor(n, m)) for n, m in ((40, "ct"), (5, "chest"), (9, "pet"), (1, "pet"))]
+
+
+@pytest.mark.parametrize("augment", [False, True])
+def test_dataset_sampling_matches_reference(augment):
+    """PETCTDataset3D (train_models.py:47-141): the same seeded draws from NumPy's global generator select the same window,
+    flip / angle, slice crop, noise and scale, so every item carries bit-identical token sequences (gather = the oracle here;
+    the device gather is checked against the same oracle in tests/test_gpu_gather.py), labels and patient ids."""
+    import warnings
+
+    from vit_deep_radiomics_b200 import train_models as ours
+    tm = ref_shim.load_reference("train_models")
+    D = 12
+    df = ours.prepare_df(_dataset_table(seed=3, D=D))
+    enc = ours.get_label_encoder(df)
+
+    def oracle_gather(feats, masks, res, noise, d):
+        return G.token_gather(feats, masks, res, noise, d)["tokens"]
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = tm.PETCTDataset3D(df.copy(), enc, "ct.h5", "pet.h5", use_augmentation=augment, feature_dim=D, arch="transformer")
+        mine = ours.PETCTDataset3D(df.copy(), enc, "ct.h5", "pet.h5", use_augmentation=augment, feature_dim=D, arch="transformer",
+                                   store=ref_shim.H5_FILES, gather=oracle_gather)
+        assert len(ref) == len(mine) > 0
+        for epoch in range(2):
+            for i in range(len(ref)):
+                np.random.seed(100 * epoch + i)
+                a, next_a = ref[i], np.random.random()
+                np.random.seed(100 * epoch + i)
+                b, next_b = mine[i], np.random.random()
+                assert next_a == next_b                               # the same number of draws from the global generator
+                assert a[3] == b[3] and torch.equal(a[2], b[2])
+                assert a[0].shape == b[0].shape and a[1].shape == b[1].shape
+                assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

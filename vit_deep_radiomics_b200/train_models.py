@@ -3,13 +3,16 @@
 Kept entry points: ``positional_encoding_3d`` (:30-44), ``PETCTDataset3D._get_features`` semantics
 (:143-182, here ``get_features`` on device), ``FocalLoss`` (:381-405), ``build_model`` (:455-486),
 ``get_y_true_and_pred`` (:283-311), the gradient-accumulation train step (:652-688) and the CLI flags
-(:500-515).  Metrics JSON / plotting / early stopping policy (:726-810) are outside the hot path.
+(:500-515); the callers on the data side of the path: ``prepare_df`` sliding windows (:416-448),
+``get_label_encoder`` (:492-499) and ``PETCTDataset3D`` with its augmentation sampling (:48-141).
+Metrics JSON / plotting / early stopping policy (:726-810) are outside the hot path.
 """
 from __future__ import annotations
 
 import argparse
 
 import numpy as np
+import pandas as pd
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -48,6 +51,138 @@ def get_features(features, masks, spatial_res, noise=(0.0, 0.0, 0.0), feature_di
     tokens, src, count = ops.mask_gather(f.contiguous(), m.contiguous(), pe=pe)
     n = int(count.item())
     return tokens[:n]
+
+
+def find_divisor(slice_count, modality):
+    """reference: train_models.py:408-413 -- slices per sample window: 13 for CT-like series, 2 for PET, at most the series."""
+    return int(np.clip(13 if modality in ("ct", "chest") else 2, 1, slice_count))
+
+
+def prepare_df(df, modality_a="pet", modality_b="ct"):
+    """reference: train_models.py:416-448.  Adds ``divisor`` (window size of the row's patient / modality) and
+    ``patient_id_new``; every CT-like series is expanded into overlapping windows -- window ``i`` holds the rows with
+    ``i <= slice <= i + divisor`` (divisor + 1 slice positions: the reference's bounds are inclusive) for
+    ``i in range(n_unique_slices - divisor)`` and is named ``<patient>:<i>``; series with no complete window disappear.
+    PET rows keep ``<patient>:<ceil(slice / divisor)>``.  CT windows first (patients in order of appearance), then PET.
+    (The reference body indexes a row Series by position, which pandas >= 2 rejects; same table, label-based here.)"""
+    df = df.copy()
+    last_slice = df.groupby(["patient_id", "modality"])["slice"].max()
+    divisor = {key: find_divisor(n, key[1]) for key, n in last_slice.items()}
+    df["divisor"] = [divisor[key] for key in zip(df["patient_id"], df["modality"])]
+    df["patient_id_new"] = [f"{pid}:{int(np.ceil(sl / dv))}" for pid, sl, dv in zip(df["patient_id"], df["slice"], df["divisor"])]
+    df_pet, df_ct = df[df["modality"] == modality_a], df[df["modality"] == modality_b]
+    windows = []
+    for patient_id in df_ct["patient_id"].unique():
+        rows = df_ct[df_ct["patient_id"] == patient_id]
+        window = int(rows["divisor"].max())
+        for i in range(len(rows["slice"].unique()) - window):
+            part = rows[(rows["slice"] >= i) & (rows["slice"] <= i + window)].copy()
+            part["patient_id_new"] = f"{patient_id}:{i}"
+            windows.append(part)
+    out = pd.concat(windows + [df_pet], axis=0) if windows else df_pet
+    return out.reset_index(drop=True)
+
+
+def get_label_encoder(df):
+    """reference: train_models.py:492-499 -- one-hot encoder over the sorted label values (label map = identity on them)."""
+    from sklearn.preprocessing import OneHotEncoder
+    names = sorted(df["label"].unique())
+    enc = OneHotEncoder(handle_unknown="ignore")
+    enc.fit(np.array(names).reshape(-1, 1))
+    return enc
+
+
+class PETCTDataset3D(torch.utils.data.Dataset):
+    """reference: train_models.py:47-141 -- one item = (CT tokens, PET tokens, one-hot label, patient id) of a sample window.
+
+    Same constructor, table handling and -- call for call -- the same draws from NumPy's global generator (position noise,
+    scale noise, flip / angle, window id, random slice crop), so a seeded run visits the same samples as the reference.
+    The token sequences come from the device gather (``get_features``: bit-identical to ``_get_features``, :143-182) and
+    stay on the GPU.  ``store`` selects where slice features and masks are read from: ``None`` = the HDF5 files the
+    reference writes (needs h5py), or a mapping ``{path: {"<pid>/features/<id>": array, "<pid>/masks/<id>": array}}``;
+    ``gather`` replaces the token gather (tests inject the CPU oracle)."""
+
+    def __init__(self, dataframe, label_encoder, hdf5_ct_path, hdf5_pet_path, modality_a="pet", modality_b="ct",
+                 use_augmentation=False, feature_dim=256, arch="conv", device="cuda:0", store=None, gather=None):
+        if arch != "transformer":
+            raise NotImplementedError("arch='conv' (Conv3d classifier) is outside the hot path")
+        self.modality_a, self.modality_b = modality_a, modality_b
+        self.slice_per_modality = dataframe.groupby(["patient_id", "modality"])["slice"].max()
+        ct = dataframe[dataframe["modality"] == modality_b].reset_index(drop=True)
+        pet = dataframe[dataframe["modality"] == modality_a].reset_index(drop=True)
+        if use_augmentation:
+            # one row per patient carrying its HIGHEST window index, repeated so that an epoch has about as many items as windows
+            n_windows = ct["patient_id_new"].nunique()
+            t = ct.copy()
+            t["patient_id_new_int"] = t["patient_id_new"].str.split(":").str[-1].astype(int)
+            t = t.sort_values(by="patient_id_new_int", ascending=False)
+            t = t.groupby(["patient_id"])[["modality", "dataset", "label", "patient_id_new", "patient_id_new_int"]].first().reset_index()
+            repeat = np.clip(np.ceil(n_windows / t.shape[0]), 2, 8)
+            self.dataframe = pd.DataFrame(np.repeat(t.values, repeat, axis=0), columns=t.columns)
+        else:
+            self.dataframe = ct.groupby(["patient_id_new"])[["modality", "dataset", "label", "patient_id"]].first().reset_index()
+        self.use_augmentation = use_augmentation
+        self.flip_angles = dataframe.groupby(["flip", "angle"], as_index=False).size()[["flip", "angle"]]
+        self.df_ct = ct.set_index(["patient_id_new", "angle", "flip"]).sort_index()
+        self.df_pet = pet.set_index(["patient_id", "angle", "flip"]).sort_index()
+        self.hdf5_ct_path, self.hdf5_pet_path = hdf5_ct_path, hdf5_pet_path
+        self.label_encoder, self.feature_dim, self.arch = label_encoder, feature_dim, arch
+        self.device, self.store, self.gather = device, store, gather
+
+    def __len__(self):
+        return len(self.dataframe)
+
+    def __getitem__(self, idx):
+        noise_val = 10
+        sample = self.dataframe.iloc[idx]
+        window_id, patient_id, label = sample.patient_id_new, sample.patient_id, sample.label
+        noise = np.random.random(3) * noise_val - noise_val / 2          # drawn in both modes, like the reference
+        scale_noise = np.random.uniform(0.85, 1.15)
+        if self.use_augmentation:
+            [[flip, angle]] = self.flip_angles.sample(n=1).values
+            top = sample.patient_id_new_int
+            window_id = f"{patient_id}:{np.random.randint(0, top) if top > 0 else top}"
+        else:
+            flip, angle, noise, scale_noise = "None", 0, noise * 0, 1.0
+        ct_rows = self.df_ct.loc[(window_id, angle, flip)]
+        ct_slices = ct_rows["slice"].values
+        first, last = ct_slices.argmin(), ct_slices.argmax()              # [first, last): the last slice is left out (:115)
+        if self.use_augmentation and len(ct_slices) > 7:                   # random slice crop of 7 .. n-1 slices
+            window = int(np.random.randint(7, len(ct_slices), 1)[0])
+            first = int(np.random.randint(0, len(ct_slices) - window, 1)[0])
+            last = first + window
+        res = np.abs(ct_rows["spatial_res"].values[0]) * scale_noise
+        features_ct = self._get_features(self.hdf5_ct_path, patient_id, ct_rows["feature_id"].values[first:last], angle, flip, noise, res)
+        # the same relative extent of the PET series
+        rel = ct_slices[first:last] / self.slice_per_modality.loc[(patient_id, self.modality_b)]
+        pet_last = self.slice_per_modality[patient_id, self.modality_a]
+        lo, hi = max(0, int(rel.min() * pet_last)), min(pet_last, int(rel.max() * pet_last))
+        pet_rows = self.df_pet.loc[(patient_id, angle, flip)]
+        res = np.abs(pet_rows["spatial_res"].values[0]) * scale_noise
+        ids = pet_rows[np.logical_and(pet_rows["slice"] >= lo, pet_rows["slice"] <= hi)]["feature_id"].values
+        features_pet = self._get_features(self.hdf5_pet_path, patient_id, ids, angle, flip, noise, res)
+        onehot = self.label_encoder.transform(np.array(label).reshape(-1, 1)).toarray()
+        return features_ct, features_pet, torch.as_tensor(onehot, dtype=torch.float32), patient_id
+
+    def _read(self, path, patient_id, feature_ids):
+        if self.store is not None:
+            f = self.store[str(path)]
+            return ([np.asarray(f[f"{patient_id}/features/{i}"]) for i in feature_ids],
+                    [np.asarray(f[f"{patient_id}/masks/{i}"]) for i in feature_ids])
+        from .tfds_dense_descriptor import _h5py
+        with _h5py().File(path, "r") as f:
+            return ([f[f"{patient_id}/features/{i}"][()] for i in feature_ids],
+                    [f[f"{patient_id}/masks/{i}"][()] for i in feature_ids])
+
+    def _get_features(self, hdf5_path, patient_id, feature_ids, angle, flip, noise, spatial_res):
+        """reference: :143-182 -- (n_sel, feature_dim) f32 tokens = features[mask] + PE/4 (``angle`` / ``flip`` select the
+        rows upstream; the stored arrays are already transformed)."""
+        feats, masks = self._read(hdf5_path, patient_id, feature_ids)
+        if not feats:
+            raise ValueError("need at least one array to stack")      # the reference's failure for an empty window
+        if self.gather is not None:
+            return torch.as_tensor(self.gather(feats, masks, spatial_res, noise, self.feature_dim), dtype=torch.float32)
+        return get_features(feats, masks, spatial_res, noise=noise, feature_dim=self.feature_dim, device=self.device)
 
 
 class FocalLoss(nn.Module):
