@@ -1,5 +1,7 @@
 """Oracle restatements against the LIVE reference (imported unmodified through oracle/ref_shim.py).
 Only runs where /root/reference exists (the build container); the golden tests cover the GPU box."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -139,3 +141,63 @@ def test_dataset_sampling_matches_reference(augment):
                 assert a[3] == b[3] and torch.equal(a[2], b[2])
                 assert a[0].shape == b[0].shape and a[1].shape == b[1].shape
                 assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def _feature_rows(rng, pid, dataset, label, n):
+    return [dict(patient_id=pid, dataset=dataset, label=label, modality=m, slice=s_, feature_id=s_, flip=f, angle=a,
+                 spatial_res=(1.0, 1.0, 2.0))
+            for m in ("ct", "pet") for (f, a) in (("None", 0), ("H", 90), (None, 0)) for s_ in range(n)]
+
+
+def test_split_patients_matches_reference_script(tmp_path, monkeypatch):
+    """src/split_patients.py executed unmodified (runpy) on a temporary project directory against the function port."""
+    import runpy
+    import sys
+    import types
+
+    import pandas as pd
+    import yaml
+    from vit_deep_radiomics_b200 import split_patients as sp
+    rng = np.random.default_rng(0)
+    rows = []
+    for ds, npat in (("stanford", 23), ("santa_maria", 17)):
+        for i in range(npat):
+            rows += _feature_rows(rng, f"{ds[:2]}{i:03d}", ds, int(rng.random() < 0.4), 2)
+    df = pd.DataFrame(rows)
+    (tmp_path / "data" / "features").mkdir(parents=True)
+    (tmp_path / "conf").mkdir()
+    df.to_parquet(tmp_path / "data" / "features" / "petct.parquet")
+    fake = types.ModuleType("config_manager")
+    fake.get_project_dir = lambda *a, **k: str(tmp_path)
+    monkeypatch.setitem(sys.modules, "config_manager", fake)
+    runpy.run_path(os.path.join(ref_shim.REFERENCE_SRC, "split_patients.py"), run_name="split_patients_ref")
+    want = yaml.safe_load((tmp_path / "conf" / "parameters_kfold.yaml").read_text())
+    os.remove(tmp_path / "conf" / "parameters_kfold.yaml")
+    assert sp.main(str(tmp_path)).endswith("parameters_kfold.yaml")
+    got = yaml.safe_load((tmp_path / "conf" / "parameters_kfold.yaml").read_text())
+    assert got == want and set(got["kfold_patients"]) == {"ct", "pet"}
+    folds = got["kfold_patients"]["ct"]["stanford"]
+    assert sorted(folds) == [0, 1, 2, 3, 4] and all(not set(f["train"]) & set(f["test"]) for f in folds.values())
+
+
+def test_merge_dataframe_features_matches_reference_script(tmp_path, monkeypatch):
+    """src/merge_dataframe_features.py executed unmodified (runpy, cwd = a temporary src/ directory) against the port."""
+    import runpy
+
+    import pandas as pd
+    from vit_deep_radiomics_b200 import merge_dataframe_features as mf
+    rng = np.random.default_rng(1)
+    feat = tmp_path / "data" / "features"
+    for ds, pids in (("stanford_dataset", ("a", "b", "c")), ("santa_maria_dataset", ("x", "y"))):
+        (feat / ds).mkdir(parents=True)
+        for pid in pids:
+            pd.DataFrame(_feature_rows(rng, pid, ds, 1, 3)).to_parquet(feat / ds / f"{pid}.parquet")
+    (tmp_path / "src").mkdir()
+    monkeypatch.chdir(tmp_path / "src")
+    runpy.run_path(os.path.join(ref_shim.REFERENCE_SRC, "merge_dataframe_features.py"), run_name="__main__")
+    want = pd.read_parquet(feat / "petct.parquet")
+    os.remove(feat / "petct.parquet")
+    got = mf.merge_features(os.path.join("..", "data", "features"))
+    pd.testing.assert_frame_equal(want, got)
+    assert (got["augmentation"] == ~((got["flip"] == "None") & (got["angle"] == 0))).all() and (got["flip"] == "None").any()
+    assert pd.read_parquet(mf.main(os.path.join("..", "data", "features"))).equals(want)
