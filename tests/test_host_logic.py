@@ -163,3 +163,29 @@ def test_build_model_and_state_dict_keys():
         ref = ma.TransformerNoduleClassifier(256, 1024, 4, 2, 2)
         assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in model.state_dict().items()}
         model.load_state_dict(ref.state_dict())                          # .pth interchange
+
+
+def test_epoch_policy_and_split_report():
+    """Epoch-end bookkeeping of the reference loop (train_models.py:727-810): patient-weighted report, target metric
+    test_auc^2 * sqrt(test_f1), checkpoint when >= the fold mean, stop when the first best epoch is `patience` epochs back."""
+    hist = [dict(epoch=0, test_auc=0.60, test_f1=0.50), dict(epoch=1, test_auc=0.70, test_f1=0.64),
+            dict(epoch=2, test_auc=0.62, test_f1=0.50), dict(epoch=3, test_auc=0.70, test_f1=0.64)]
+    save, stop, target = tm.epoch_policy(hist[:2], patience=2)
+    assert save and not stop and abs(target - 0.49 * 0.8) < 1e-12
+    save, stop, _ = tm.epoch_policy(hist[:3], patience=2)
+    assert not save and not stop                      # below the mean; best epoch 1 is one epoch back
+    save, stop, _ = tm.epoch_policy(hist, patience=2)
+    assert save and stop                              # ties count as improvement, but the FIRST best epoch (1) is 2 back
+    assert tm.get_sampler_weights(np.array(["a", "b", "a", "c", "a"])) == [1 / 3, 1, 1 / 3, 1, 1 / 3]
+    if os.path.isdir("/root/reference/src"):
+        from oracle import ref_shim
+        ref = ref_shim.load_reference("train_models")
+        assert ref.get_sampler_weights(np.array(["a", "b", "a", "c", "a"])) == tm.get_sampler_weights(np.array(["a", "b", "a", "c", "a"]))
+    y_true = [np.array([0]), np.array([1]), np.array([1]), np.array([0]), np.array([1])]
+    y_score = [np.array([[0.8, 0.2]]), np.array([[0.3, 0.7]]), np.array([[0.6, 0.4]]), np.array([[0.4, 0.6]]), np.array([[0.1, 0.9]])]
+    pids = [np.array(["p1"]), np.array(["p2"]), np.array(["p2"]), np.array(["p3"]), np.array(["p4"])]
+    rep = tm.split_report(y_true, y_score, pids, loss=0.25, kfold=1, epoch=4, split="test")
+    assert rep["split"] == "test" and rep["kfold"] == 1 and rep["epoch"] == 4 and rep["loss"] == 0.25
+    # weights 1, .5, .5, 1, 1: positives 2 (weighted), of which 1.5 predicted positive; negatives 2, of which 1 predicted negative
+    assert abs(rep["1"]["recall"] - 0.75) < 1e-12 and abs(rep["0"]["recall"] - 0.5) < 1e-12 and abs(rep["accuracy"] - 0.625) < 1e-12
+    assert 0.0 <= rep["ROC AUC"] <= 1.0

@@ -5,7 +5,8 @@ Kept entry points: ``positional_encoding_3d`` (:30-44), ``PETCTDataset3D._get_fe
 ``get_y_true_and_pred`` (:283-311), the gradient-accumulation train step (:652-688) and the CLI flags
 (:500-515); the callers on the data side of the path: ``prepare_df`` sliding windows (:416-448),
 ``get_label_encoder`` (:492-499) and ``PETCTDataset3D`` with its augmentation sampling (:48-141).
-Metrics JSON / plotting / early stopping policy (:726-810) are outside the hot path.
+The epoch-end bookkeeping is kept as functions (``split_report``, ``epoch_policy``: report JSON, checkpoint and
+early-stopping rule of :727-810); plotting is outside the path.
 """
 from __future__ import annotations
 
@@ -246,6 +247,43 @@ def get_y_true_and_pred(y_true, y_pred, cpu=False):
     if cpu:
         y_true, y_score = y_true.detach().cpu().numpy(), y_score.detach().cpu().numpy()
     return y_true, y_score
+
+
+def get_sampler_weights(train_labels):
+    """reference: train_models.py:313-328 -- 1 / (count of the element's value) for every element."""
+    values, counts = np.unique(train_labels, return_counts=True)
+    per_value = dict(zip(values, counts))
+    return [1 / per_value[v] for v in train_labels]
+
+
+def split_report(y_true, y_score, patient_ids, loss, kfold, epoch, split):
+    """The per-split report the epoch loop writes to ``<split>_metrics_<epoch>.json`` (reference: train_models.py:727-768):
+    sklearn's classification_report at threshold 0.5 on the positive-class score plus 'ROC AUC', 'kfold', 'loss', 'epoch',
+    'split', every sample weighted by 1 / (items of its patient) so that patients, not windows, count equally."""
+    from sklearn.metrics import classification_report, roc_auc_score
+    y_true = np.concatenate([np.atleast_1d(v) for v in y_true], axis=0)
+    score = np.concatenate([np.atleast_2d(v) for v in y_score], axis=0)[:, 1]
+    weights = get_sampler_weights(np.concatenate([np.atleast_1d(np.array(v)) for v in patient_ids], axis=0))
+    report = classification_report(y_true, (score >= 0.5) * 1, output_dict=True, zero_division=0, sample_weight=weights)
+    report.update({"ROC AUC": roc_auc_score(y_true, score, sample_weight=weights), "kfold": kfold, "loss": loss, "epoch": epoch,
+                   "split": split})
+    return report
+
+
+def epoch_policy(history, patience):
+    """Checkpoint / early-stopping decision at the end of an epoch (reference: train_models.py:786-810).  ``history`` = the
+    fold's per-epoch records so far (dicts or DataFrame rows with 'epoch', 'test_auc', 'test_f1'), the current epoch last.
+    target = test_auc^2 * sqrt(test_f1); a checkpoint is written when the current target is at least the fold's mean;
+    training stops when the FIRST epoch that reached the fold's maximum lies ``patience`` or more epochs back.
+    Returns (save_checkpoint, stop, target_metric of the current epoch)."""
+    df = pd.DataFrame(list(history)) if not isinstance(history, pd.DataFrame) else history.copy()
+    df["target_metric"] = df["test_auc"] * df["test_auc"] * np.sqrt(df["test_f1"])
+    df["is_improvement"] = df["target_metric"] >= df["target_metric"].max()
+    df = df.sort_values(by="epoch", ascending=True).reset_index(drop=True)
+    epoch = df["epoch"].iloc[-1]
+    since = epoch - df.iloc[df["is_improvement"].argmax()]["epoch"]
+    save = bool(df["target_metric"].iloc[-1] >= df["target_metric"].mean())
+    return save, bool(since >= patience), float(df["target_metric"].iloc[-1])
 
 
 def build_model(cfg, arch, modality, modality_a="pet", modality_b="ct", num_classes=2):
