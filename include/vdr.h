@@ -321,6 +321,31 @@ int vdr_cross_cls_attn_fwd(const float* q0, const void* kv, int64_t ld_kv, int n
 int vdr_cross_cls_attn_bwd(const float* q0, const void* kv, int64_t ld_kv, const float* p, const float* d_o, int n, int heads,
                            float scale, float* dq0, void* dkv, int64_t ld_dkv, float* scratch, vdr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MedSAM / SAM ViT-B image encoder pieces: what `model.image_encoder(img_tensor)` of
+ * sam_model_registry['vit_b'] (tfds_dense_descriptor.py:104,123; third-party segment_anything, un-vendored) needs beyond the
+ * plain-ViT kernels above.  All matrices are token-major bf16 (rows = tokens), head_dim 64.
+ *
+ * vdr_window_rows: window_partition / window_unpartition of the encoder blocks.  to_windows != 0: src (B*H*W, d) ->
+ *   dst (B*nwh*nww*ws*ws, d), nwh = ceil(H/ws), rows outside H x W written as zeros (the padding is applied after norm1);
+ *   to_windows == 0: the inverse, pad rows dropped.
+ * vdr_relpos_tables: decomposed relative-position terms of add_decomposed_rel_pos for every query of BW images/windows of
+ *   Sh x Sw tokens: rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = q . rel_pos_h[qh - j + Sh - 1] (j < Sh) or
+ *   q . rel_pos_w[qw - (j - Sh) + Sw - 1]; q = the UNSCALED query vector read from qkv; rel_pos_h (2*Sh-1, 64) f32,
+ *   rel_pos_w (2*Sw-1, 64) f32 (shared by the heads; tables of another length are interpolated by the caller).
+ * vdr_attn_relpos_fwd: out = softmax(q k^T * scale + rel_h[q, kh] + rel_w[q, kw]) v per (image/window, head); qkv
+ *   (BW*N, >= 3*heads*64) as the qkv GEMM writes it, N = Sh*Sw; out (BW*N, heads*64) bf16.
+ * vdr_im2col3x3_tokens: A[(b,y,x), (ky*3+kx)*C + c] = X[(b, y+ky-1, x+kx-1), c], zero padded: the A operand of the neck's
+ *   3x3 convolution as a GEMM against the weight permuted to (out, ky, kx, in). */
+int vdr_window_rows(const void* src_bf16, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int B, int H, int W, int ws, int d,
+                    int to_windows, vdr_stream_t stream);
+int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const float* rel_pos_h, const float* rel_pos_w, float* rel, int BW,
+                      int Sh, int Sw, int heads, vdr_stream_t stream);
+int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const float* rel, void* out_bf16, int64_t ld_out, int BW, int Sh,
+                        int Sw, int heads, float scale, vdr_stream_t stream);
+int vdr_im2col3x3_tokens(const void* X_bf16, int64_t ldx, void* A_bf16, int64_t lda, int B, int H, int W, int C,
+                         vdr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,204 @@
+"""-m gpu: the MedSAM / SAM image-encoder path and the reference's 'dinov2' patch-embedding mode
+against the oracle (oracle/sam_fp32.py, pinned to transformers' SamVisionEncoder) and the committed golden vector.
+
+Tolerances: integer / byte work (window partition, 3x3 im2col) bit-exact; bf16 activations with fp32 accumulation against
+the fp32 oracle: |error| <= ABS_TOL on the LayerNorm-ed descriptors (O(1) values), rms relative error <= REL_TOL,
+per-descriptor cosine >= 0.999 (BASELINE.json north_star)."""
+import importlib.util
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL, REL_TOL, COS = 0.15, 0.02, 0.999
+
+
+def _check_descriptors(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    err = np.abs(got - want).max()
+    rel = np.sqrt(((got - want) ** 2).sum() / (want ** 2).sum())
+    g2, w2 = got.reshape(-1, got.shape[-1]), want.reshape(-1, want.shape[-1])
+    cos = (g2 * w2).sum(1) / (np.linalg.norm(g2, axis=1) * np.linalg.norm(w2, axis=1))
+    assert err <= ABS_TOL and rel <= REL_TOL and cos.min() >= COS, (err, rel, cos.min())
+
+
+@pytest.mark.parametrize("B,H,W,ws,d", [(2, 16, 16, 14, 128), (1, 14, 14, 14, 64), (3, 9, 20, 7, 72), (1, 64, 64, 14, 768)])
+def test_window_rows_bit_exact(cuda, B, H, W, ws, d):
+    from oracle import sam_fp32
+    from vit_deep_radiomics_b200 import ops
+    x = torch.randn(B, H, W, d, generator=torch.Generator().manual_seed(1)).bfloat16()
+    want, pad_hw = sam_fp32.window_partition(x.float(), ws)
+    got = ops.window_rows(x.reshape(-1, d).to(cuda), B, H, W, ws, True)
+    assert torch.equal(got.cpu().float().reshape(want.shape), want)
+    back = ops.window_rows(got, B, H, W, ws, False)
+    assert torch.equal(back.cpu().reshape(B, H, W, d), x)
+    with pytest.raises(ValueError):
+        ops.window_rows(x.reshape(-1, d)[1:].to(cuda), B, H, W, ws, True)
+
+
+def _attn_reference(qkv, BW, Sh, Sw, heads, rel_h, rel_w):
+    """fp32 attention with the decomposed bias on the bf16-rounded operands (segment_anything Attention.forward)."""
+    N = Sh * Sw
+    q, k, v = qkv.float().reshape(BW, N, 3, heads, 64).permute(2, 0, 3, 1, 4).reshape(3, BW * heads, N, 64).unbind(0)
+    ih = torch.arange(Sh)[:, None] - torch.arange(Sh)[None, :] + Sh - 1
+    iw = torch.arange(Sw)[:, None] - torch.arange(Sw)[None, :] + Sw - 1
+    rq = q.reshape(BW * heads, Sh, Sw, 64)
+    bh = torch.einsum("bhwc,hkc->bhwk", rq, rel_h[ih])
+    bw = torch.einsum("bhwc,wkc->bhwk", rq, rel_w[iw])
+    a = (q * 0.125) @ k.transpose(-2, -1)
+    a = (a.view(BW * heads, Sh, Sw, Sh, Sw) + bh[..., :, None] + bw[..., None, :]).view(BW * heads, N, N).softmax(-1)
+    out = (a @ v).view(BW, heads, N, 64).permute(0, 2, 1, 3).reshape(BW * N, heads * 64)
+    return out, torch.cat([bh, bw], dim=-1).reshape(BW * heads * N, Sh + Sw)
+
+
+@pytest.mark.parametrize("BW,Sh,Sw,heads", [(3, 14, 14, 2), (2, 16, 16, 2), (1, 8, 12, 3), (1, 5, 3, 1), (1, 64, 64, 2), (50, 14, 14, 12)])
+def test_attn_relpos_vs_fp32(cuda, BW, Sh, Sw, heads):
+    """Windowed (14x14 = 196 tokens, a ragged last key tile), global (64x64 = 4096) and non-square extents."""
+    from vit_deep_radiomics_b200 import _C, ops
+    g = torch.Generator().manual_seed(BW * 1000 + Sh * 10 + Sw)
+    N, d = Sh * Sw, heads * 64
+    qkv = (torch.randn(BW * N, 3 * d, generator=g) * 1.2).bfloat16()
+    rel_h = torch.randn(2 * Sh - 1, 64, generator=g) * 0.1
+    rel_w = torch.randn(2 * Sw - 1, 64, generator=g) * 0.1
+    want, rel_want = _attn_reference(qkv, BW, Sh, Sw, heads, rel_h, rel_w)
+    rel = torch.full((BW * heads * N * (Sh + Sw),), float("nan"), device=cuda)
+    n0 = _C.launch_count()
+    got = ops.attn_relpos(qkv.to(cuda), BW, Sh, Sw, heads, rel_h.to(cuda), rel_w.to(cuda), rel=rel)
+    assert _C.launch_count() - n0 == 2
+    rel_got = rel.cpu().reshape(BW * heads * N, Sh + Sw)
+    assert torch.allclose(rel_got, rel_want, atol=2e-4, rtol=1e-4), float((rel_got - rel_want).abs().max())
+    got = got.cpu().float()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max()
+    cos = F.cosine_similarity(got.reshape(-1, 64), want.reshape(-1, 64), dim=1).min()
+    assert err < 2e-2 and cos > 0.9995, (float(err), float(cos))
+
+
+def test_attn_relpos_zero_bias_matches_flash_attention(cuda):
+    """With zero rel-pos tables the kernel computes plain softmax attention: same result as the tcgen05 flash kernel."""
+    from vit_deep_radiomics_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    BW, S, heads = 2, 16, 2
+    qkv = torch.randn(BW * S * S, 3 * heads * 64, generator=g).bfloat16().to(cuda)
+    z = torch.zeros(2 * S - 1, 64, device=cuda)
+    a = ops.attn_relpos(qkv, BW, S, S, heads, z, z).float()
+    b = ops.flash_attn(qkv, BW, S * S, heads).float()
+    assert (a - b).abs().max() < 1.6e-2
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (1, 5, 7, 8), (1, 64, 64, 256)])
+def test_im2col3x3_bit_exact(cuda, B, H, W, C):
+    from vit_deep_radiomics_b200 import ops
+    x = torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(3)).bfloat16()
+    got = ops.im2col3x3_tokens(x.reshape(-1, C).to(cuda), B, H, W).cpu()
+    # F.unfold orders (c, ky, kx); the kernel writes (ky, kx, c)
+    u = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1).reshape(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)
+    assert torch.equal(got.float(), u)
+
+
+def test_neck_conv3x3_as_gemm(cuda):
+    from vit_deep_radiomics_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, H, W, C = 2, 16, 16, 64
+    x = torch.randn(B, H, W, C, generator=g).bfloat16()
+    wt = (torch.randn(C, C, 3, 3, generator=g) * 0.05).bfloat16()
+    A = ops.im2col3x3_tokens(x.reshape(-1, C).to(cuda), B, H, W)
+    got = ops.gemm(A, wt.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous().to(cuda), None, out_dtype=torch.float32).cpu()
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, C)
+    assert torch.allclose(got, want, atol=2e-3, rtol=2e-3), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize("hw,B", [((256, 256), 2), ((224, 224), 1), ((192, 320), 1)])
+def test_sam_encoder_vs_oracle(cuda, hw, B):
+    """sam_tiny (4 blocks, windowed + global attention, neck): padded windows (16 -> 28), exact windows (14), non-square."""
+    from oracle import sam_fp32
+    from vit_deep_radiomics_b200 import _C, tfds_dense_descriptor as tdd
+    model = tdd.load_model("sam_tiny", img_hw=hw, device=cuda, seed=13)
+    x = torch.rand(B, 3, *hw, generator=torch.Generator().manual_seed(2))
+    n0 = _C.launch_count()
+    got = model.dense_descriptors(x.to(cuda)).cpu().numpy()
+    assert _C.launch_count() > n0
+    with torch.no_grad():
+        want = sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, x).numpy()
+    assert got.shape == want.shape == (B, hw[0] // 16, hw[1] // 16, 64)
+    _check_descriptors(got, want)
+
+
+def test_sam_encoder_against_committed_golden(cuda, golden_dir):
+    """tests/golden/sam_tiny_hf.npz = transformers' SamVisionEncoder on the same seeded weights / input."""
+    from vit_deep_radiomics_b200 import sam_encoder
+    spec = importlib.util.spec_from_file_location("make_golden_sam", os.path.join(golden_dir, "make_golden_sam.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = np.load(os.path.join(golden_dir, "sam_tiny_hf.npz"))
+    cfg = sam_encoder.SAM_CONFIGS["sam_tiny"]
+    sd = sam_encoder.init_sam_state_dict(cfg, (mk.IMG, mk.IMG), seed=mk.SEED_W)
+    full = {"image_encoder." + k: v for k, v in sd.items()}                      # as a full SAM checkpoint stores it
+    model = sam_encoder.SamImageEncoder("sam_tiny", img_hw=(mk.IMG, mk.IMG), state_dict=full, device=cuda)
+    got = model.dense_descriptors(mk.golden_input().to(cuda))[0].cpu().numpy()
+    _check_descriptors(got, g["descriptors"])
+
+
+def test_medsam_full_size_slice(cuda):
+    """The reference's actual configuration: ViT-B, 1024 x 1024 gray slice -> (64, 64, 256) (tfds_dense_descriptor.py:42,123-126).
+    One slice against the fp32 oracle on the host."""
+    from oracle import sam_fp32
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    model = tdd.load_model("medsam", device=cuda, seed=17)
+    assert model.img_hw == (1024, 1024) and model.grid == (64, 64) and model.feature_dim == 256
+    gray = torch.rand(1, 1024, 1024, generator=torch.Generator().manual_seed(5))
+    got = model.dense_descriptors(gray.to(cuda)).cpu().numpy()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        want = sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, gray[:, None].expand(-1, 3, -1, -1)).numpy()
+    assert got.shape == want.shape == (1, 64, 64, 256)
+    _check_descriptors(got, want)
+
+
+def test_medsam_point_cloud_through_the_gather(cuda):
+    """extract_point_cloud with the SAM encoder (no CLS row: token offset 0): indices bit-exact, tokens in tolerance."""
+    from oracle import gather_np, sam_fp32
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    rng = np.random.default_rng(8)
+    H = W = 128
+    S = 3
+    img = rng.random((H, W, S), dtype=np.float32)
+    yy, xx = np.mgrid[:H, :W]
+    mask = np.stack([((yy - 64) ** 2 + (xx - 60) ** 2) < (14 + 2 * s) ** 2 for s in range(S)], axis=-1)
+    res = np.array([0.8, 0.8, 0.8])
+    model = tdd.load_model("sam_tiny", img_hw=(256, 256), device=cuda, seed=19)
+    out = tdd.extract_point_cloud(model, img, mask, res)
+    y0, y1, x0, x1 = out["plan"]["crop"]
+    # oracle: the crop window resized by the product's own device resize (its parity is tests/test_gpu_pipeline.py's subject),
+    # then the fp32 encoder and the reference-order gather
+    from vit_deep_radiomics_b200 import ops
+    sl = ops.volume_to_slices(torch.from_numpy(img).to(cuda), out["plan"]["crop"], out_hw=model.img_hw).float().cpu()
+    with torch.no_grad():
+        dense = sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, sl[:, None].expand(-1, 3, -1, -1)).numpy()
+    fy0, fy1, fx0, fx1 = out["plan"]["feat_roi"]
+    my0, my1, mx0, mx1 = out["plan"]["mask_roi"]
+    mask_c = mask[y0:y1, x0:x1]
+    ref = gather_np.token_gather([dense[s, fy0:fy1, fx0:fx1] for s in range(S)], [mask_c[my0:my1, mx0:mx1, s] for s in range(S)], res)
+    assert out["count"] == ref["flat"].size and out["count"] > 0
+    assert np.array_equal(out["src"].numpy(), ref["src"])
+    got, want = out["tokens"].numpy().astype(np.float64), ref["tokens"]
+    cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
+    assert np.abs(got - want).max() < ABS_TOL and cos.min() > COS
+
+
+@pytest.mark.parametrize("hw,B", [((56, 84), 2), ((896, 896), 1)])
+def test_dinov2_patch_embed_mode(cuda, hw, B):
+    """The reference's 'dinov2' branch only calls model.patch_embed (:128-133)."""
+    from oracle import sam_fp32
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    model = tdd.load_model("dinov2", img_hw=hw, device=cuda, seed=23)
+    x = torch.rand(B, 3, *hw, generator=torch.Generator().manual_seed(6))
+    got = model.dense_descriptors(x.to(cuda)).cpu()
+    want = sam_fp32.dinov2_patch_embed(model.state_dict_f32, x)
+    assert got.shape == want.shape == (B, hw[0] // 14, hw[1] // 14, 384)
+    assert torch.allclose(got, want, atol=6e-3, rtol=1e-2), float((got - want).abs().max())

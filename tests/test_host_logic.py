@@ -140,8 +140,23 @@ def test_cli_flags_match_reference():
         ("vit_b16", "x.pth", "d", "f", "h", "c", "chest")
     b = tm.build_arg_parser().parse_args(["-a", "transformer", "-d", "stanford", "-b", "vit", "-m", "ct", "-gpu", "1", "-l", "focal", "-e", "e"])
     assert (b.arch, b.dataset, b.backbone, b.modality, b.gpu, b.loss, b.experiment) == ("transformer", "stanford", "vit", "ct", 1, "focal", "e")
-    with pytest.raises(NotImplementedError):
-        tdd.load_model("medsam")
+    assert tdd.build_arg_parser().parse_args(["-mn", "medsam"]).model_name == "medsam"     # the reference's default backbone
+
+
+def test_sam_encoder_host_side():
+    """Key names / geometry of the MedSAM encoder drop-in (no device work: the constructor itself needs CUDA)."""
+    from vit_deep_radiomics_b200 import sam_encoder
+    from oracle import sam_fp32
+    cfg = sam_encoder.SAM_CONFIGS["medsam"]
+    assert cfg == sam_fp32.SAM_CONFIGS["medsam"] and (cfg["dim"], cfg["depth"], cfg["heads"], cfg["out_chans"]) == (768, 12, 12, 256)
+    tiny = sam_encoder.SAM_CONFIGS["sam_tiny"]
+    a, b = sam_encoder.init_sam_state_dict(tiny, (256, 256), seed=3), sam_fp32.init_sam_state_dict(tiny, (256, 256), seed=3)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert a["blocks.0.attn.rel_pos_h"].shape == (27, 64) and a["blocks.1.attn.rel_pos_h"].shape == (31, 64)
+    full = {"image_encoder." + k: v for k, v in a.items()} | {"mask_decoder.x": torch.zeros(1)}
+    assert sam_encoder._strip_prefix(full, "image_encoder.").keys() == a.keys()
+    r = sam_encoder._fit_rel_pos(a["blocks.0.attn.rel_pos_h"], 16)                      # 27 -> 31 rows, linear
+    assert r.shape == (31, 64) and torch.allclose(r, sam_fp32.rel_pos_rows(16, a["blocks.0.attn.rel_pos_h"])[(torch.arange(31) - 15).clamp(min=0), (15 - torch.arange(31)).clamp(min=0)])
 
 
 def test_build_model_and_state_dict_keys():

@@ -1,0 +1,331 @@
+// the pieces of the MedSAM / SAM ViT-B image encoder (the backbone the reference loads by
+// default, src/tfds_dense_descriptor.py:104,123; code in the un-vendored segment_anything package) that the plain-ViT path
+// does not have: 14x14 window partition with zero padding, decomposed relative-position bias, attention with that bias,
+// and the 3x3 convolution of the neck as an im2col over token-major maps.  First correct path: the attention runs on
+// mma.sync (bf16 m16n8k16, fp32 accumulation) with the bias added in registers; the GEMMs either side are the tcgen05 kernel.
+#include "common.cuh"
+
+namespace vdr {
+
+// ------------------------------------------------------------------------------------------------ window (un)partition
+// to_windows: dst row (b, wy, wx, ty, tx) <- src row (b, wy*ws+ty, wx*ws+tx), zeros outside H x W (the padding is applied to
+//   the NORMALISED tokens, so pad tokens are exact zeros and take part in the window's softmax with q = k = v = bias);
+// else:       dst row (b, y, x) <- src row (b, y/ws, x/ws, y%ws, x%ws)   (pad rows are dropped).
+// One warp per destination row, 16-byte vectors.
+__global__ void __launch_bounds__(256)
+window_rows_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
+                   int H, int W, int ws, int nwh, int nww, int d, int64_t dst_rows, int to_windows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int wt = ws * ws;
+  for (int64_t r = warp0; r < dst_rows; r += nwarps) {
+    int64_t srow = -1;
+    if (to_windows) {
+      const int64_t win = r / wt;
+      const int t = static_cast<int>(r - win * wt);
+      const int64_t b = win / (nwh * nww);
+      const int wi = static_cast<int>(win - b * (nwh * nww));
+      const int y = (wi / nww) * ws + t / ws, x = (wi % nww) * ws + t % ws;
+      if (y < H && x < W) srow = (b * H + y) * W + x;
+    } else {
+      const int64_t b = r / ((int64_t)H * W);
+      const int rem = static_cast<int>(r - b * H * W);
+      const int y = rem / W, x = rem - y * W;
+      srow = ((b * nwh + y / ws) * nww + x / ws) * wt + (y % ws) * ws + x % ws;
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + r * ld_dst);
+    if (srow >= 0) {
+      const uint4* s = reinterpret_cast<const uint4*>(src + srow * ld_src);
+      for (int v = lane; v < (d >> 3); v += 32) o[v] = __ldg(s + v);
+    } else {
+      for (int v = lane; v < (d >> 3); v += 32) o[v] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ rel-pos tables
+// rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = q_vec . Rh[qh - j + Sh - 1]        (j <  Sh)
+//                                         = q_vec . Rw[qw - (j-Sh) + Sw - 1]   (j >= Sh)
+// with q_vec the UNSCALED query of token q = qh*Sw + qw, head h (segment_anything add_decomposed_rel_pos).  One warp per
+// (bw, q, h): the query sits in shared memory, lane j owns outputs j, j+32, ...
+__global__ void __launch_bounds__(128)
+relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ Rh, const float* __restrict__ Rw,
+                    float* __restrict__ rel, int64_t total /* BW*N*heads */, int N, int Sh, int Sw, int heads) {
+  __shared__ __align__(16) float qs[4][64];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t wid = blockIdx.x * 4LL + wib;
+  if (wid >= total) return;                        // whole warps leave together; no block-level barrier below
+  const int h = static_cast<int>(wid % heads);
+  const int64_t tok = wid / heads;                 // bw*N + q
+  const int q = static_cast<int>(tok % N);
+  const int qh = q / Sw, qw = q - qh * Sw;
+  const float2 qv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(qkv + tok * ld + h * 64) + lane));
+  qs[wib][2 * lane] = qv.x;
+  qs[wib][2 * lane + 1] = qv.y;
+  __syncwarp();
+  const int R = Sh + Sw;
+  const int64_t bw = tok / N;
+  float* o = rel + ((bw * heads + h) * N + q) * R;
+  for (int j = lane; j < R; j += 32) {
+    const float* row = (j < Sh) ? Rh + (int64_t)(qh - j + Sh - 1) * 64 : Rw + (int64_t)(qw - (j - Sh) + Sw - 1) * 64;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(row + c));
+      const float4 qq = *reinterpret_cast<const float4*>(&qs[wib][c]);
+      acc = fmaf(qq.x, rv.x, acc); acc = fmaf(qq.y, rv.y, acc); acc = fmaf(qq.z, rv.z, acc); acc = fmaf(qq.w, rv.w, acc);
+    }
+    o[j] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention + bias
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kRpBQ = 64, kRpBK = 64, kRpPitch = 72;   // 72 bf16 = 36 words per row: fragment loads hit 32 distinct banks
+
+// softmax(q k^T * scale + rel_h[q, kh] + rel_w[q, kw]) v   for one (64-query block, head, image-or-window).
+// 4 warps x 16 query rows; key tiles of 64; online softmax in the log2 domain; P rounded to bf16 for the second MMA.
+__global__ void __launch_bounds__(128)
+attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ rel,
+                   __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int heads, int Sh, int Sw, float scale_log2e) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [64 keys][72]
+  __nv_bfloat16* Vt = Ks + kRpBK * kRpPitch;                            // [64 d][72]  (transposed: keys contiguous)
+  float* relS = reinterpret_cast<float*>(Vt + 64 * kRpPitch);          // [64 query rows][R + 1], pre-multiplied by log2(e)
+  const int qb = blockIdx.x, h = blockIdx.y, bw = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int d = heads * 64;
+  const int q0 = qb * kRpBQ;
+  const int R = Sh + Sw, RP = R + 1;
+  const __nv_bfloat16* base = qkv + (int64_t)bw * N * ld + h * 64;     // q at +0, k at +d, v at +2d
+  const float* relg = rel + ((int64_t)(bw * heads + h) * N + q0) * R;
+  for (int i = tid; i < kRpBQ * R; i += 128) {
+    const int r = i / R, j = i - r * R;
+    relS[r * RP + j] = (q0 + r < N) ? __ldg(relg + (int64_t)r * R + j) * 1.4426950408889634f : 0.f;
+  }
+  // Q fragments (A operand, 16 rows x 64): rows r0 = g, r1 = g + 8 of this warp's 16
+  const int rl0 = warp * 16 + g, rl1 = rl0 + 8;
+  const int r0 = q0 + rl0, r1 = q0 + rl1;
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + ks * 16 + 2 * t);
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + ks * 16 + 2 * t);
+    qa[ks][0] = r0 < N ? __ldg(p0) : 0u;
+    qa[ks][1] = r1 < N ? __ldg(p1) : 0u;
+    qa[ks][2] = r0 < N ? __ldg(p0 + 4) : 0u;
+    qa[ks][3] = r1 < N ? __ldg(p1 + 4) : 0u;
+  }
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float* rel0 = relS + rl0 * RP;
+  const float* rel1 = relS + rl1 * RP;
+
+  for (int k0 = 0; k0 < N; k0 += kRpBK) {
+    __syncthreads();                                 // previous tile fully consumed (also orders the relS staging)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      {   // K: 8 lanes cover one 128-byte row (coalesced)
+        const int idx = tid + i * 128, row = idx >> 3, seg = idx & 7, key = k0 + row;
+        uint4 kv = make_uint4(0u, 0u, 0u, 0u);
+        if (key < N) kv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)key * ld + d + seg * 8));
+        *reinterpret_cast<uint4*>(Ks + row * kRpPitch + seg * 8) = kv;
+      }
+      {   // V, stored transposed: consecutive lanes take consecutive keys so the 2-byte scatter spreads over the banks
+        const int idx = tid + i * 128, row = idx & 63, seg = idx >> 6, key = k0 + row;
+        uint4 vv = make_uint4(0u, 0u, 0u, 0u);
+        if (key < N) vv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)key * ld + 2 * d + seg * 8));
+        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Vt[(seg * 8 + j) * kRpPitch + row] = e[j];
+      }
+    }
+    __syncthreads();
+
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t* kp = reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * kRpPitch + ks * 16 + 2 * t);
+        mma_bf16_16816(s[nt], qa[ks], kp[0], kp[4]);
+      }
+    }
+    // scale + bias + key mask; row maxima
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = k0 + nt * 8 + 2 * t + e;
+        if (key < N) {
+          const int kh = key / Sw, kw = key - kh * Sw;
+          s[nt][e] = fmaf(s[nt][e], scale_log2e, rel0[kh] + rel0[Sh + kw]);
+          s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2e, rel1[kh] + rel1[Sh + kw]);
+        } else {
+          s[nt][e] = -INFINITY;
+          s[nt][2 + e] = -INFINITY;
+        }
+        mx0 = fmaxf(mx0, s[nt][e]);
+        mx1 = fmaxf(mx1, s[nt][2 + e]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);      // finite: key k0 < N is valid in every tile
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);      // exp2(-inf) = 0 on the first tile
+    m0 = mn0; m1 = mn1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
+      s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+      ps0 += s[nt][0] + s[nt][1];
+      ps1 += s[nt][2] + s[nt][3];
+      o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
+    }
+    l0 = l0 * c0 + ps0;                               // per-thread partial sums; reduced over the quad at the end
+    l1 = l1 * c1 + ps1;
+    // O += P V : P (16 x 64 keys) from the S accumulators, V^T rows give the B fragments
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vt + (nt * 8 + g) * kRpPitch + kk * 16 + 2 * t);
+        mma_bf16_16816(o[nt], pa, vp[0], vp[4]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __nv_bfloat16* ob = out + (int64_t)bw * N * ld_out + h * 64;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (r0 < N) *reinterpret_cast<uint32_t*>(ob + (int64_t)r0 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < N) *reinterpret_cast<uint32_t*>(ob + (int64_t)r1 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 im2col (neck)
+// A[(b,y,x), (ky*3+kx)*C + c] = X[(b, y+ky-1, x+kx-1), c], zero outside the map (Conv2d padding 1).  One 16-byte vector per thread.
+__global__ void __launch_bounds__(256)
+im2col3x3_tokens_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ A, int64_t lda,
+                        int H, int W, int C, int64_t total_vec) {
+  const int vpt = C >> 3;                  // vectors per tap
+  const int vpr = 9 * vpt;                 // vectors per output row
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = v / vpr;
+    const int rem = static_cast<int>(v - m * vpr);
+    const int tap = rem / vpt, cv = rem - tap * vpt;
+    const int x = static_cast<int>(m % W);
+    const int64_t tq = m / W;
+    const int y = static_cast<int>(tq % H);
+    const int64_t b = tq / H;
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(reinterpret_cast<const uint4*>(X + ((b * H + yy) * W + xx) * ldx) + cv);
+    *reinterpret_cast<uint4*>(A + m * lda + (int64_t)tap * C + cv * 8) = val;
+  }
+}
+
+}  // namespace vdr
+
+// ================================================================================================ C ABI
+extern "C" int vdr_window_rows(const void* src_bf16, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int B, int H, int W, int ws,
+                               int d, int to_windows, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(src_bf16 && dst_bf16, VDR_EINVAL, "vdr_window_rows: null pointer");
+  VDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && ws > 0 && d > 0 && d % 8 == 0, VDR_EINVAL,
+                "vdr_window_rows: bad shape B=%d H=%d W=%d ws=%d d=%d (d must be a multiple of 8)", B, H, W, ws, d);
+  VDR_CHECK_ARG(aligned16(src_bf16) && aligned16(dst_bf16) && ld_src % 8 == 0 && ld_dst % 8 == 0 && ld_src >= d && ld_dst >= d,
+                VDR_EALIGN, "vdr_window_rows: pointers must be 16-byte aligned, leading dimensions multiples of 8 and >= d");
+  const int nwh = (H + ws - 1) / ws, nww = (W + ws - 1) / ws;
+  const int64_t dst_rows = to_windows ? (int64_t)B * nwh * nww * ws * ws : (int64_t)B * H * W;
+  int64_t blocks = (dst_rows + 7) / 8;
+  const int64_t max_blocks = (int64_t)num_sms() * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  window_rows_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src_bf16), ld_src, static_cast<__nv_bfloat16*>(dst_bf16), ld_dst, H, W, ws, nwh, nww, d,
+      dst_rows, to_windows ? 1 : 0);
+  count_launch();
+  VDR_CHECK_LAUNCH("window_rows_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const float* rel_pos_h, const float* rel_pos_w, float* rel,
+                                 int BW, int Sh, int Sw, int heads, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(qkv_bf16 && rel_pos_h && rel_pos_w && rel, VDR_EINVAL, "vdr_relpos_tables: null pointer");
+  VDR_CHECK_ARG(BW > 0 && Sh > 0 && Sw > 0 && heads > 0, VDR_EINVAL, "vdr_relpos_tables: bad shape BW=%d Sh=%d Sw=%d heads=%d", BW, Sh, Sw, heads);
+  VDR_CHECK_ARG(ld_qkv >= 3LL * heads * 64 && ld_qkv % 8 == 0 && aligned16(qkv_bf16) && aligned16(rel_pos_h) && aligned16(rel_pos_w),
+                VDR_EALIGN, "vdr_relpos_tables: qkv must be (rows, >= 3*heads*64) with ld %% 8 == 0; tables 16-byte aligned");
+  const int N = Sh * Sw;
+  const int64_t total = (int64_t)BW * N * heads;
+  VDR_CHECK_ARG((total + 3) / 4 < 0x7fffffffLL, VDR_EINVAL, "vdr_relpos_tables: too many rows");
+  relpos_table_kernel<<<(unsigned)((total + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, rel_pos_h, rel_pos_w, rel, total, N, Sh, Sw, heads);
+  count_launch();
+  VDR_CHECK_LAUNCH("relpos_table_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const float* rel, void* out_bf16, int64_t ld_out, int BW,
+                                   int Sh, int Sw, int heads, float scale, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(qkv_bf16 && rel && out_bf16, VDR_EINVAL, "vdr_attn_relpos_fwd: null pointer");
+  VDR_CHECK_ARG(BW > 0 && BW <= 65535 && Sh > 0 && Sw > 0 && heads > 0 && heads <= 65535, VDR_EINVAL,
+                "vdr_attn_relpos_fwd: bad shape BW=%d Sh=%d Sw=%d heads=%d", BW, Sh, Sw, heads);
+  VDR_CHECK_ARG(ld_qkv >= 3LL * heads * 64 && ld_qkv % 8 == 0 && ld_out >= heads * 64LL && ld_out % 8 == 0 && aligned16(qkv_bf16) &&
+                    aligned16(out_bf16),
+                VDR_EALIGN, "vdr_attn_relpos_fwd: qkv (rows, >= 3*heads*64) / out (rows, >= heads*64), ld %% 8 == 0, 16-byte aligned");
+  const int N = Sh * Sw;
+  const size_t smem = 2 * (size_t)kRpBK * kRpPitch * sizeof(__nv_bfloat16) + (size_t)kRpBQ * (Sh + Sw + 1) * sizeof(float);
+  VDR_CHECK_ARG(smem <= 200 * 1024, VDR_EINVAL, "vdr_attn_relpos_fwd: Sh + Sw = %d too large for the shared-memory bias tile", Sh + Sw);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_kernel)");
+    configured = smem;
+  }
+  dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
+  attn_relpos_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, rel, static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, Sh, Sw,
+      scale * 1.4426950408889634f);
+  count_launch();
+  VDR_CHECK_LAUNCH("attn_relpos_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_im2col3x3_tokens(const void* X_bf16, int64_t ldx, void* A_bf16, int64_t lda, int B, int H, int W, int C,
+                                    vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(X_bf16 && A_bf16, VDR_EINVAL, "vdr_im2col3x3_tokens: null pointer");
+  VDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, VDR_EINVAL, "vdr_im2col3x3_tokens: bad shape B=%d H=%d W=%d C=%d (C %% 8 == 0)", B, H, W, C);
+  VDR_CHECK_ARG(aligned16(X_bf16) && aligned16(A_bf16) && ldx % 8 == 0 && lda % 8 == 0 && ldx >= C && lda >= 9LL * C, VDR_EALIGN,
+                "vdr_im2col3x3_tokens: pointers must be 16-byte aligned, ldx >= C, lda >= 9*C, both multiples of 8");
+  const int64_t total_vec = (int64_t)B * H * W * 9 * (C >> 3);
+  int64_t blocks = (total_vec + 255) / 256;
+  const int64_t max_blocks = (int64_t)num_sms() * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  im2col3x3_tokens_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(X_bf16), ldx, static_cast<__nv_bfloat16*>(A_bf16), lda, H, W, C, total_vec);
+  count_launch();
+  VDR_CHECK_LAUNCH("im2col3x3_tokens_kernel");
+  return VDR_OK;
+}

@@ -578,3 +578,65 @@ def cross_cls_attn_bwd(q0, kv, p, d_o, heads: int, scale: float):
                                              dq0.data_ptr(), dkv.data_ptr(), dkv.stride(0), scratch.data_ptr(), _stream()),
              "vdr_cross_cls_attn_bwd")
     return dq0, dkv
+
+
+# ----------------------------------------------------------------------------- MedSAM / SAM encoder pieces
+def window_rows(src: torch.Tensor, B: int, H: int, W: int, ws: int, to_windows: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    """window_partition (to_windows) / window_unpartition of token-major bf16 rows: (B*H*W, d) <-> (B*nwh*nww*ws*ws, d),
+    zero rows for the padding (segment_anything image_encoder.py window_partition / window_unpartition)."""
+    _req(src, torch.bfloat16, "src")
+    d = src.shape[1]
+    nwh, nww = -(-H // ws), -(-W // ws)
+    rows_in = B * H * W if to_windows else B * nwh * nww * ws * ws
+    rows_out = B * nwh * nww * ws * ws if to_windows else B * H * W
+    if src.dim() != 2 or src.shape[0] != rows_in or src.stride(1) != 1:
+        raise ValueError(f"src must be ({rows_in}, d) with unit inner stride, got {tuple(src.shape)}")
+    if out is None:
+        out = torch.empty((rows_out, d), dtype=torch.bfloat16, device=src.device)
+    if out.shape != (rows_out, d) or out.stride(1) != 1:
+        raise ValueError(f"out must be ({rows_out}, {d})")
+    with _Prof("ln", float(2 * rows_out * d * 2), f"window_rows {'partition' if to_windows else 'unpartition'} {rows_out}x{d}"):
+        _C.check(_C.lib().vdr_window_rows(src.data_ptr(), src.stride(0), out.data_ptr(), out.stride(0), B, H, W, ws, d,
+                                          1 if to_windows else 0, _stream()), "vdr_window_rows")
+    return out
+
+
+def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor,
+                scale: float | None = None, out: torch.Tensor | None = None, rel: torch.Tensor | None = None) -> torch.Tensor:
+    """Attention with SAM's decomposed relative-position bias over BW images/windows of Sh x Sw tokens.
+    qkv (BW*Sh*Sw, 3*heads*64) bf16; rel_pos_h (2*Sh-1, 64), rel_pos_w (2*Sw-1, 64) f32 -> out (BW*Sh*Sw, heads*64) bf16.
+    Two launches: the per-query bias tables (vdr_relpos_tables), then the fused attention (vdr_attn_relpos_fwd)."""
+    _req(qkv, torch.bfloat16, "qkv"), _req(rel_pos_h, torch.float32, "rel_pos_h"), _req(rel_pos_w, torch.float32, "rel_pos_w")
+    N, d = Sh * Sw, heads * 64
+    if qkv.shape != (BW * N, 3 * d) or qkv.stride(1) != 1:
+        raise ValueError(f"qkv must be ({BW * N}, {3 * d}), got {tuple(qkv.shape)}")
+    if rel_pos_h.shape != (2 * Sh - 1, 64) or rel_pos_w.shape != (2 * Sw - 1, 64) or not rel_pos_h.is_contiguous() or not rel_pos_w.is_contiguous():
+        raise ValueError("rel_pos_h / rel_pos_w must be contiguous (2*S-1, 64) tables (interpolate them first when the extent differs)")
+    if scale is None:
+        scale = 1.0 / math.sqrt(64)
+    if out is None:
+        out = torch.empty((BW * N, d), dtype=torch.bfloat16, device=qkv.device)
+    if rel is None:
+        rel = torch.empty(BW * heads * N * (Sh + Sw), dtype=torch.float32, device=qkv.device)
+    if rel.numel() < BW * heads * N * (Sh + Sw):
+        raise ValueError("rel scratch too small")
+    with _Prof("attn", 2.0 * BW * heads * N * (Sh + Sw) * 64, f"relpos tables BW{BW} {Sh}x{Sw} h{heads}"):
+        _C.check(_C.lib().vdr_relpos_tables(qkv.data_ptr(), qkv.stride(0), rel_pos_h.data_ptr(), rel_pos_w.data_ptr(), rel.data_ptr(),
+                                            BW, Sh, Sw, heads, _stream()), "vdr_relpos_tables")
+    with _Prof("attn", 4.0 * BW * heads * N * N * 64, f"attn+relpos BW{BW} N{N} h{heads}"):
+        _C.check(_C.lib().vdr_attn_relpos_fwd(qkv.data_ptr(), qkv.stride(0), rel.data_ptr(), out.data_ptr(), out.stride(0), BW, Sh, Sw,
+                                              heads, float(scale), _stream()), "vdr_attn_relpos_fwd")
+    return out
+
+
+def im2col3x3_tokens(x: torch.Tensor, B: int, H: int, W: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(B*H*W, C) bf16 token-major map -> (B*H*W, 9*C) bf16, k = (ky, kx, c), zero padding 1."""
+    _req(x, torch.bfloat16, "x")
+    Cc = x.shape[1]
+    if x.dim() != 2 or x.shape[0] != B * H * W or x.stride(1) != 1:
+        raise ValueError(f"x must be ({B * H * W}, C)")
+    if out is None:
+        out = torch.empty((B * H * W, 9 * Cc), dtype=torch.bfloat16, device=x.device)
+    _C.check(_C.lib().vdr_im2col3x3_tokens(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), B, H, W, Cc, _stream()),
+             "vdr_im2col3x3_tokens")
+    return out

@@ -1,0 +1,297 @@
+"""The two backbones the reference's ``load_model`` actually knows (src/tfds_dense_descriptor.py:51-67), on libvdr kernels:
+
+* ``SamImageEncoder`` -- ``model.image_encoder`` of ``sam_model_registry['vit_b']`` (MedSAM, :104,123): patch embedding +
+  absolute position embedding, 12 pre-norm blocks with 14x14 windowed attention (global at blocks 2, 5, 8, 11) and the
+  decomposed relative-position bias, neck (1x1 conv, LayerNorm2d, 3x3 conv, LayerNorm2d) -> (H/16, W/16, 256) descriptors,
+  which is what gives the classifiers their ``feature_dim: 256`` (conf/parameters_models.yaml:4).
+* ``DinoV2PatchEmbed`` -- ``model.patch_embed`` of the torch.hub DINOv2 ViT-S/14 (:87,128): the reference's 'dinov2' mode
+  only runs the 14x14 strided convolution.
+
+State-dict keys are segment_anything's / DINOv2's, with or without the ``image_encoder.`` prefix of a full SAM checkpoint,
+so ``medsam_vit_b.pth`` loads unchanged.  The GEMMs are the tcgen05 kernel (vdr_gemm); the attention with bias is the
+first correct path of this row (vdr_relpos_tables + vdr_attn_relpos_fwd on mma.sync), not yet on tcgen05.
+There is no CPU path: every op is a libvdr call on CUDA tensors.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+SAM_CONFIGS = {
+    "medsam": dict(dim=768, depth=12, heads=12, global_attn=(2, 5, 8, 11), window=14, out_chans=256, patch=16),
+    "sam_tiny": dict(dim=128, depth=4, heads=2, global_attn=(1, 3), window=14, out_chans=64, patch=16),   # tests
+}
+
+
+def init_sam_state_dict(cfg: dict, img_hw, seed: int = 1234) -> dict:
+    """Seeded random weights with segment_anything key names (no checkpoints are available offline)."""
+    g = torch.Generator().manual_seed(seed)
+    d, p, oc, ws = cfg["dim"], cfg["patch"], cfg["out_chans"], cfg["window"]
+    gh, gw = img_hw[0] // p, img_hw[1] // p
+    hd = d // cfg["heads"]
+
+    def tn(*shape, std=0.02):
+        t = torch.empty(*shape, dtype=torch.float32)
+        torch.nn.init.trunc_normal_(t, std=std, a=-2 * std, b=2 * std, generator=g)
+        return t
+
+    w = {"pos_embed": tn(1, gh, gw, d), "patch_embed.proj.weight": tn(d, 3, p, p), "patch_embed.proj.bias": tn(d, std=0.01)}
+    for i in range(cfg["depth"]):
+        b = f"blocks.{i}."
+        sh, sw = (gh, gw) if i in cfg["global_attn"] else (ws, ws)
+        w[b + "norm1.weight"] = 1.0 + tn(d, std=0.05)
+        w[b + "norm1.bias"] = tn(d, std=0.01)
+        w[b + "attn.qkv.weight"] = tn(3 * d, d, std=0.04)
+        w[b + "attn.qkv.bias"] = tn(3 * d, std=0.01)
+        w[b + "attn.proj.weight"] = tn(d, d)
+        w[b + "attn.proj.bias"] = tn(d, std=0.01)
+        w[b + "attn.rel_pos_h"] = tn(2 * sh - 1, hd, std=0.1)
+        w[b + "attn.rel_pos_w"] = tn(2 * sw - 1, hd, std=0.1)
+        w[b + "norm2.weight"] = 1.0 + tn(d, std=0.05)
+        w[b + "norm2.bias"] = tn(d, std=0.01)
+        w[b + "mlp.lin1.weight"] = tn(4 * d, d)
+        w[b + "mlp.lin1.bias"] = tn(4 * d, std=0.01)
+        w[b + "mlp.lin2.weight"] = tn(d, 4 * d)
+        w[b + "mlp.lin2.bias"] = tn(d, std=0.01)
+    w["neck.0.weight"] = tn(oc, d, 1, 1, std=0.05)
+    w["neck.1.weight"] = 1.0 + tn(oc, std=0.05)
+    w["neck.1.bias"] = tn(oc, std=0.01)
+    w["neck.2.weight"] = tn(oc, oc, 3, 3, std=0.05)
+    w["neck.3.weight"] = 1.0 + tn(oc, std=0.05)
+    w["neck.3.bias"] = tn(oc, std=0.01)
+    return w
+
+
+def _strip_prefix(sd: dict, prefix: str) -> dict:
+    if any(k.startswith(prefix) for k in sd):
+        return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    return sd
+
+
+def _fit_rel_pos(rel_pos: torch.Tensor, size: int) -> torch.Tensor:
+    """segment_anything get_rel_pos: a table whose length is not 2*size-1 is linearly interpolated to it."""
+    L = 2 * size - 1
+    if rel_pos.shape[0] == L:
+        return rel_pos
+    r = F.interpolate(rel_pos.reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1), size=L, mode="linear")
+    return r.reshape(-1, L).permute(1, 0)
+
+
+class SamImageEncoder:
+    """MedSAM / SAM ViT-B image encoder; same call surface as ``vit.ViTBackbone`` for the extraction code."""
+
+    has_cls = False
+
+    def __init__(self, name: str = "medsam", img_hw=(1024, 1024), state_dict: dict | None = None, device="cuda:0", seed: int = 1234):
+        if name not in SAM_CONFIGS:
+            raise ValueError(f"unknown SAM encoder {name!r}; choose from {sorted(SAM_CONFIGS)}")
+        self.model_name = name
+        self.cfg = dict(SAM_CONFIGS[name])
+        self.img_hw = (int(img_hw[0]), int(img_hw[1]))
+        p = self.cfg["patch"]
+        if self.img_hw[0] % p or self.img_hw[1] % p:
+            raise ValueError(f"image size {self.img_hw} is not a multiple of the patch size {p}")
+        if self.cfg["dim"] != 64 * self.cfg["heads"]:
+            raise ValueError("libvdr attention kernels need head_dim 64")
+        self.grid = (self.img_hw[0] // p, self.img_hw[1] // p)
+        self.n_patches = self.n_tokens = self.grid[0] * self.grid[1]
+        self.token_offset = 0                                   # no CLS row in front of an image's tokens
+        self.feature_dim = self.cfg["out_chans"]
+        self.device = torch.device(device)
+        if state_dict is not None:
+            state_dict = _strip_prefix(state_dict, "image_encoder.")
+        self.state_dict_f32 = state_dict if state_dict is not None else init_sam_state_dict(self.cfg, self.img_hw, seed)
+        self._ws: dict = {}
+        self.prepare()
+
+    def prepare(self):
+        sd, dev, cfg = self.state_dict_f32, self.device, self.cfg
+        d, p, oc, ws = cfg["dim"], cfg["patch"], cfg["out_chans"], cfg["window"]
+        gh, gw = self.grid
+        if tuple(sd["pos_embed"].shape) != (1, gh, gw, d):
+            raise ValueError(f"pos_embed is {tuple(sd['pos_embed'].shape)}, the image needs (1, {gh}, {gw}, {d})")
+        f32 = lambda k: sd[k].to(dev, torch.float32).contiguous()   # noqa: E731
+        bf = lambda k: sd[k].to(dev).bfloat16().contiguous()        # noqa: E731
+        self.K = 3 * p * p
+        self.w = dict(pe_w=sd["patch_embed.proj.weight"].reshape(d, self.K).to(dev).bfloat16().contiguous(),
+                      pe_b=f32("patch_embed.proj.bias"), pos=f32("pos_embed").reshape(gh * gw, d), blocks=[],
+                      neck0=sd["neck.0.weight"].reshape(oc, d).to(dev).bfloat16().contiguous(),
+                      neck1_w=f32("neck.1.weight"), neck1_b=f32("neck.1.bias"),
+                      # 3x3 conv weight (out, in, ky, kx) -> (out, ky, kx, in): the K order vdr_im2col3x3_tokens writes
+                      neck2=sd["neck.2.weight"].permute(0, 2, 3, 1).reshape(oc, 9 * oc).to(dev).bfloat16().contiguous(),
+                      neck3_w=f32("neck.3.weight"), neck3_b=f32("neck.3.bias"))
+        for i in range(cfg["depth"]):
+            b = f"blocks.{i}."
+            sh, sw = (gh, gw) if i in cfg["global_attn"] else (ws, ws)
+            self.w["blocks"].append(dict(
+                n1w=f32(b + "norm1.weight"), n1b=f32(b + "norm1.bias"),
+                qkv_w=bf(b + "attn.qkv.weight"), qkv_b=f32(b + "attn.qkv.bias"),
+                proj_w=bf(b + "attn.proj.weight"), proj_b=f32(b + "attn.proj.bias"),
+                rel_h=_fit_rel_pos(sd[b + "attn.rel_pos_h"].float(), sh).to(dev).contiguous(),
+                rel_w=_fit_rel_pos(sd[b + "attn.rel_pos_w"].float(), sw).to(dev).contiguous(),
+                n2w=f32(b + "norm2.weight"), n2b=f32(b + "norm2.bias"),
+                fc1_w=bf(b + "mlp.lin1.weight"), fc1_b=f32(b + "mlp.lin1.bias"),
+                fc2_w=bf(b + "mlp.lin2.weight"), fc2_b=f32(b + "mlp.lin2.bias"),
+                window=0 if i in cfg["global_attn"] else ws))
+
+    def _buffers(self, B: int) -> dict:
+        ws = self._ws.get(B)
+        if ws is None:
+            cfg, dev, bf = self.cfg, self.device, torch.bfloat16
+            d, oc, win = cfg["dim"], cfg["out_chans"], cfg["window"]
+            gh, gw = self.grid
+            N = gh * gw
+            nwin = (-(-gh // win)) * (-(-gw // win))
+            NW = nwin * win * win                                    # rows per image in the windowed layout (>= N)
+            heads = cfg["heads"]
+            rel_elems = max(B * heads * N * (gh + gw), B * nwin * heads * win * win * 2 * win)
+            ws = dict(A=torch.empty(B * N, self.K, dtype=bf, device=dev),
+                      X=torch.empty(B * N, d, dtype=bf, device=dev), Y=torch.empty(B * N, d, dtype=bf, device=dev),
+                      YW=torch.empty(B * NW, d, dtype=bf, device=dev), OW=torch.empty(B * NW, d, dtype=bf, device=dev),
+                      QKV=torch.empty(B * max(N, NW), 3 * d, dtype=bf, device=dev),
+                      H=torch.empty(B * N, 4 * d, dtype=bf, device=dev),
+                      REL=torch.empty(rel_elems, dtype=torch.float32, device=dev),
+                      N0=torch.empty(B * N, oc, dtype=bf, device=dev), N1=torch.empty(B * N, oc, dtype=bf, device=dev),
+                      NA=torch.empty(B * N, 9 * oc, dtype=bf, device=dev),
+                      OUT=torch.empty(B * N, oc, dtype=torch.float32, device=dev))
+            self._ws = {B: ws}
+        return ws
+
+    # -- forward -----------------------------------------------------------------------------
+    def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
+        """src: f32 CUDA storage of B images addressed by element strides (batch, channel, row, col); channel stride 0 =
+        gray2rgb.  Returns the neck output as a token matrix (B*gh*gw, out_chans) f32, tokens in (row, col) order."""
+        H, W = self.img_hw
+        ws = self._buffers(B)
+        ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"], out=ws["A"])
+        return self._encode(B)
+
+    def forward_volume(self, vol: torch.Tensor, crop) -> torch.Tensor:
+        """(H, W, S) f32 CUDA volume + crop window -> (S*gh*gw, out_chans) f32; the window is resized to the encoder input
+        as prepare_image does (tfds_dense_descriptor.py:40-44)."""
+        S = vol.shape[2]
+        ws = self._buffers(S)
+        if "SL" not in ws:
+            ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
+        ops.volume_to_slices(vol, crop, out=ws["SL"], out_hw=self.img_hw)
+        ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=ws["A"])
+        return self._encode(S)
+
+    def _encode(self, B: int) -> torch.Tensor:
+        cfg, w, ws = self.cfg, self.w, self._buffers(B)
+        d, heads, win = cfg["dim"], cfg["heads"], cfg["window"]
+        gh, gw = self.grid
+        N = gh * gw
+        nwh, nww = -(-gh // win), -(-gw // win)
+        NW = nwh * nww * win * win
+        X, Y, Hb = ws["X"], ws["Y"], ws["H"]
+        scale = 1.0 / math.sqrt(64)
+        # patch embedding (Conv2d 16x16 stride 16) + absolute position embedding in the GEMM epilogue
+        ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=X, res_mod=(N, 0))
+        for blk in w["blocks"]:
+            ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
+            if blk["window"]:
+                ops.window_rows(Y, B, gh, gw, win, True, out=ws["YW"])
+                qkv = ws["QKV"][:B * NW]
+                ops.gemm(ws["YW"], blk["qkv_w"], blk["qkv_b"], out=qkv)
+                ops.attn_relpos(qkv, B * nwh * nww, win, win, heads, blk["rel_h"], blk["rel_w"], scale, out=ws["OW"], rel=ws["REL"])
+                ops.window_rows(ws["OW"], B, gh, gw, win, False, out=Y)
+            else:
+                qkv = ws["QKV"][:B * N]
+                ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=qkv)
+                ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_h"], blk["rel_w"], scale, out=Y, rel=ws["REL"])
+            ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X)
+            ops.layernorm(X, blk["n2w"], blk["n2b"], 1e-6, out=Y)
+            ops.gemm(Y, blk["fc1_w"], blk["fc1_b"], epilogue="gelu", out=Hb)
+            ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X)
+        # neck: 1x1 conv (a GEMM), LayerNorm2d = LayerNorm over the channels of each token, 3x3 conv as im2col + GEMM, LayerNorm2d
+        ops.gemm(X, w["neck0"], None, out=ws["N0"])
+        ops.layernorm(ws["N0"], w["neck1_w"], w["neck1_b"], 1e-6, out=ws["N1"])
+        ops.im2col3x3_tokens(ws["N1"], B, gh, gw, out=ws["NA"])
+        ops.gemm(ws["NA"], w["neck2"], None, out=ws["N0"])
+        ops.layernorm(ws["N0"], w["neck3_w"], w["neck3_b"], 1e-6, out=ws["OUT"])
+        return ws["OUT"]
+
+    def dense_descriptors(self, images: torch.Tensor) -> torch.Tensor:
+        """images (B, 3, H, W) or (B, H, W) f32 CUDA -> (B, H/16, W/16, out_chans) f32: get_dense_descriptor's result
+        for 'medsam' (:123-126), batched."""
+        B = images.shape[0]
+        strides = (images.stride(0), 0, images.stride(1), images.stride(2)) if images.dim() == 3 else images.stride()
+        if tuple(images.shape[-2:]) != self.img_hw:
+            raise ValueError(f"expected images of {self.img_hw}, got {tuple(images.shape[-2:])}")
+        tok = self.forward_tokens(images, strides, B)
+        return tok.view(B, self.grid[0], self.grid[1], self.feature_dim)
+
+    def flops_per_slice(self) -> float:
+        """Algorithmic flops of one image: patch embedding, per block 24*N*d^2 (+ the window padding rows of the qkv GEMM
+        are NOT counted) and 4*n^2*d per attention extent, rel-pos terms, neck."""
+        cfg = self.cfg
+        d, oc, win = cfg["dim"], cfg["out_chans"], cfg["window"]
+        gh, gw = self.grid
+        N = gh * gw
+        f = 2.0 * N * self.K * d
+        for i in range(cfg["depth"]):
+            f += 24.0 * N * d * d
+            if i in cfg["global_attn"]:
+                f += 4.0 * N * N * d + 2.0 * N * d * (gh + gw)
+            else:
+                nwin = (-(-gh // win)) * (-(-gw // win))
+                f += nwin * (4.0 * (win * win) ** 2 * d + 2.0 * win * win * d * 2 * win)
+        return f + 2.0 * N * d * oc + 2.0 * N * 9 * oc * oc
+
+
+class DinoV2PatchEmbed:
+    """The reference's 'dinov2' mode (:128-133): only ``model.patch_embed`` -- Conv2d(3, 384, 14, stride 14) + bias."""
+
+    has_cls = False
+
+    def __init__(self, img_hw=(896, 896), state_dict: dict | None = None, device="cuda:0", seed: int = 1234, dim: int = 384, patch: int = 14):
+        self.model_name = "dinov2"
+        self.img_hw = (int(img_hw[0]), int(img_hw[1]))
+        if self.img_hw[0] % patch or self.img_hw[1] % patch:
+            raise ValueError(f"image size {self.img_hw} is not a multiple of the patch size {patch}")     # DINOv2 PatchEmbed asserts this
+        self.device = torch.device(device)
+        if state_dict is None:
+            g = torch.Generator().manual_seed(seed)
+            wt = torch.empty(dim, 3, patch, patch)
+            torch.nn.init.trunc_normal_(wt, std=0.02, a=-0.04, b=0.04, generator=g)
+            bs = torch.empty(dim)
+            torch.nn.init.trunc_normal_(bs, std=0.01, a=-0.02, b=0.02, generator=g)
+            state_dict = {"patch_embed.proj.weight": wt, "patch_embed.proj.bias": bs}
+        self.state_dict_f32 = state_dict
+        wt = state_dict["patch_embed.proj.weight"]
+        dim, patch = wt.shape[0], wt.shape[-1]
+        self.cfg = dict(dim=dim, patch=patch, depth=0, heads=0)
+        self.grid = (self.img_hw[0] // patch, self.img_hw[1] // patch)
+        self.n_patches = self.n_tokens = self.grid[0] * self.grid[1]
+        self.token_offset = 0
+        self.feature_dim = dim
+        self.K = 3 * patch * patch
+        ldk = (self.K + 7) // 8 * 8
+        w = torch.zeros(dim, ldk, dtype=torch.bfloat16, device=self.device)
+        w[:, :self.K] = wt.reshape(dim, self.K).to(self.device).bfloat16()
+        self.w = dict(pe_w=w, pe_b=state_dict["patch_embed.proj.bias"].to(self.device, torch.float32).contiguous())
+
+    def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
+        H, W = self.img_hw
+        A = ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"])
+        return ops.gemm(A, self.w["pe_w"], self.w["pe_b"], out_dtype=torch.float32, k=self.K)
+
+    def forward_volume(self, vol: torch.Tensor, crop) -> torch.Tensor:
+        sl = ops.volume_to_slices(vol, crop, out_hw=self.img_hw)
+        A = ops.im2col_gray_bf16(sl, self.cfg["patch"])
+        return ops.gemm(A, self.w["pe_w"], self.w["pe_b"], out_dtype=torch.float32, k=self.K)
+
+    def dense_descriptors(self, images: torch.Tensor) -> torch.Tensor:
+        B = images.shape[0]
+        strides = (images.stride(0), 0, images.stride(1), images.stride(2)) if images.dim() == 3 else images.stride()
+        if tuple(images.shape[-2:]) != self.img_hw:
+            raise ValueError(f"expected images of {self.img_hw}, got {tuple(images.shape[-2:])}")
+        return self.forward_tokens(images, strides, B).view(B, self.grid[0], self.grid[1], self.feature_dim)
+
+    def flops_per_slice(self) -> float:
+        return 2.0 * self.n_patches * self.K * self.feature_dim

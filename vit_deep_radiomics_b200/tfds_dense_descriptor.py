@@ -22,27 +22,33 @@ import torch
 from . import ops
 from .visualization_utils import (crop_image, crop_window, crop_window_from_bbox, extract_roi, mask_bbox, roi_window,
                                   roi_window_from_bbox)
+from .sam_encoder import SAM_CONFIGS, DinoV2PatchEmbed, SamImageEncoder
 from .vit import VIT_CONFIGS, ViTBackbone
 
 # --------------------------------------------------------------------------------------------- model
 def load_model(model_name, model_path=None, img_hw=None, device="cuda:0", seed=1234):
-    """reference: tfds_dense_descriptor.py:51-67.  ``model_name`` extends the reference's
-    {'medsam', 'dinov2'} with the plain-ViT backbones of BASELINE.json: 'vit_s16', 'vit_b16',
-    'vit_l14'.  ``model_path`` (optional) is a torch state-dict with timm/DINOv2 key names;
-    without it the weights are seeded random (no checkpoints exist offline)."""
-    if model_name in ("medsam", "dinov2"):
-        raise NotImplementedError(
-            f"backbone {model_name!r} needs third-party code/checkpoints that are not vendored by the reference "
-            "(segment_anything / torch.hub); the SAM-specific encoder (windowed attention, rel-pos bias, neck) is "
-            "the next scope row (SURVEY.md section 8f N1).  Use 'vit_s16', 'vit_b16' or 'vit_l14'.")
-    if model_name not in VIT_CONFIGS:
-        raise ValueError(f"unknown model_name {model_name!r}")
-    if img_hw is None:
-        img_hw = (518, 518) if VIT_CONFIGS[model_name]["patch"] == 14 else (512, 512)
+    """reference: tfds_dense_descriptor.py:51-67.  ``model_name``: the reference's 'medsam' (SAM ViT-B image encoder,
+    sam_encoder.SamImageEncoder) and 'dinov2' (patch embedding only, as the reference uses it), plus the plain-ViT
+    backbones of BASELINE.json: 'vit_s16', 'vit_b16', 'vit_l14'.  ``model_path`` (optional) is a torch state-dict
+    (segment_anything / DINOv2 / timm key names); without it the weights are seeded random (no checkpoints exist offline)."""
     sd = None
     if model_path is not None:
         sd = torch.load(model_path, map_location="cpu")
         sd = sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+    if model_name in SAM_CONFIGS:
+        # load_medsam (:91-107): sam_model_registry['vit_b'](model_path); only model.image_encoder is ever called (:123).
+        # prepare_image feeds it 1024 x 1024 (:42); other sizes need a pos_embed of that grid.
+        model = SamImageEncoder(model_name, img_hw=img_hw or (1024, 1024), state_dict=sd, device=device, seed=seed)
+        model.model_name = model_name
+        return model
+    if model_name == "dinov2":
+        # load_dinov2 (:70-88) + model.patch_embed (:128): ViT-S/14 patch embedding only; RGB inputs are resized to 896^2 (:44)
+        model = DinoV2PatchEmbed(img_hw=img_hw or (896, 896), state_dict=sd, device=device, seed=seed)
+        return model
+    if model_name not in VIT_CONFIGS:
+        raise ValueError(f"unknown model_name {model_name!r}")
+    if img_hw is None:
+        img_hw = (518, 518) if VIT_CONFIGS[model_name]["patch"] == 14 else (512, 512)
     model = ViTBackbone(model_name, img_hw=img_hw, state_dict=sd, device=device, seed=seed)
     model.model_name = model_name
     return model
@@ -149,10 +155,10 @@ def generate_features(model, img_3d, mask_3d, tqdm_text="", display=False, max_b
     plan = _plan(model, mask_3d)
     img_dev = torch.as_tensor(np.ascontiguousarray(img_3d, dtype=np.float32)).to(model.device)
     tok = _forward_volume(model, img_dev, plan, max_batch)
-    S, d = img_3d.shape[2], model.cfg["dim"]
+    S, d, off = img_3d.shape[2], model.feature_dim, model.token_offset
     gh, gw = model.grid
     fy0, fy1, fx0, fx1 = plan["feat_roi"]
-    feats = tok.view(S, model.n_tokens, d)[:, 1:, :].reshape(S, gh, gw, d)[:, fy0:fy1, fx0:fx1, :].cpu().numpy()
+    feats = tok.view(S, model.n_tokens, d)[:, off:, :].reshape(S, gh, gw, d)[:, fy0:fy1, fx0:fx1, :].cpu().numpy()
     y0, y1, x0, x1 = plan["crop"]
     my0, my1, mx0, mx1 = plan["mask_roi"]
     mask_c = mask_3d[y0:y1, x0:x1]
@@ -219,7 +225,7 @@ class PointCloudExtractor:
         tok = _forward_volume(model, b["img"], plan)
         gh, gw = model.grid
         pe = dict(res=spatial_res, noise=noise, scale=0.25) if add_pe else None
-        tokens, src, count = ops.mask_gather(tok, b["mask"], grid=(S, gh, gw, model.n_tokens, 1), feat_roi=plan["feat_roi"],
+        tokens, src, count = ops.mask_gather(tok, b["mask"], grid=(S, gh, gw, model.n_tokens, model.token_offset), feat_roi=plan["feat_roi"],
                                              mask_roi=_shift_roi(plan["mask_roi"], plan["crop"]), pe=pe, mask_layout="hws")
         b["free"] = torch.cuda.Event()
         b["free"].record(main)
@@ -337,7 +343,7 @@ def get_voxels(hdf5_path, patient_id, modality):
 def build_arg_parser():
     """Same flags as the reference CLI (tfds_dense_descriptor.py:365-382)."""
     p = argparse.ArgumentParser(description="ViT patch embeddings of the lung_radiomics datasets (B200-native)")
-    p.add_argument("-mn", "--model_name", type=str, default="vit_b16", help="vit_s16 | vit_b16 | vit_l14 (medsam, dinov2: not available)")
+    p.add_argument("-mn", "--model_name", type=str, default="vit_b16", help="medsam | dinov2 | vit_s16 | vit_b16 | vit_l14")
     p.add_argument("-mp", "--model_path", type=str, default=None)
     p.add_argument("-d", "--dataset_path", type=str, default=os.path.join("data", "lung_radiomics"))
     p.add_argument("-f", "--feature_folder", type=str, default=os.path.join("data", "features"))

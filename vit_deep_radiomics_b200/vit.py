@@ -74,6 +74,8 @@ class ViTBackbone:
         self.grid = (self.img_hw[0] // p, self.img_hw[1] // p)
         self.n_patches = self.grid[0] * self.grid[1]
         self.n_tokens = self.n_patches + 1
+        self.token_offset = 1                 # the CLS row in front of every image's patch tokens
+        self.feature_dim = self.cfg["dim"]
         self.device = torch.device(device)
         self.state_dict_f32 = state_dict if state_dict is not None else init_vit_state_dict(self.cfg, self.img_hw, seed)
         self._ws: dict = {}
