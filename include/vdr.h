@@ -333,16 +333,19 @@ int vdr_cross_cls_attn_bwd(const float* q0, const void* kv, int64_t ld_kv, const
  *   Sh x Sw tokens: rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = q . rel_pos_h[qh - j + Sh - 1] (j < Sh) or
  *   q . rel_pos_w[qw - (j - Sh) + Sw - 1]; q = the UNSCALED query vector read from qkv; rel_pos_h (2*Sh-1, 64) f32,
  *   rel_pos_w (2*Sw-1, 64) f32 (shared by the heads; tables of another length are interpolated by the caller).
+ *   (A stand-alone fp32 evaluation of the bias terms: the attention below builds them on chip and does not read this table.)
  * vdr_attn_relpos_fwd: out = softmax(q k^T * scale + rel_h[q, kh] + rel_w[q, kw]) v per (image/window, head); qkv
- *   (BW*N, >= 3*heads*64) as the qkv GEMM writes it, N = Sh*Sw; out (BW*N, heads*64) bf16.
+ *   (BW*N, >= 3*heads*64) as the qkv GEMM writes it, N = Sh*Sw < 65536; out (BW*N, heads*64) bf16.  rcat_hi / rcat_lo
+ *   (2*Sh-1 + 2*Sw-1, 64) bf16: the concatenated tables [rel_pos_h ; rel_pos_w] split as hi = bf16(R), lo = bf16(R - hi);
+ *   the kernel multiplies the block's queries with both parts on the tensor cores (fp32-class accuracy) in its prologue.
  * vdr_im2col3x3_tokens: A[(b,y,x), (ky*3+kx)*C + c] = X[(b, y+ky-1, x+kx-1), c], zero padded: the A operand of the neck's
  *   3x3 convolution as a GEMM against the weight permuted to (out, ky, kx, in). */
 int vdr_window_rows(const void* src_bf16, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int B, int H, int W, int ws, int d,
                     int to_windows, vdr_stream_t stream);
 int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const float* rel_pos_h, const float* rel_pos_w, float* rel, int BW,
                       int Sh, int Sw, int heads, vdr_stream_t stream);
-int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const float* rel, void* out_bf16, int64_t ld_out, int BW, int Sh,
-                        int Sw, int heads, float scale, vdr_stream_t stream);
+int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, void* out_bf16,
+                        int64_t ld_out, int BW, int Sh, int Sw, int heads, float scale, vdr_stream_t stream);
 int vdr_im2col3x3_tokens(const void* X_bf16, int64_t ldx, void* A_bf16, int64_t lda, int B, int H, int W, int C,
                          vdr_stream_t stream);
 

@@ -56,7 +56,7 @@ def _attn_reference(qkv, BW, Sh, Sw, heads, rel_h, rel_w):
     return out, torch.cat([bh, bw], dim=-1).reshape(BW * heads * N, Sh + Sw)
 
 
-@pytest.mark.parametrize("BW,Sh,Sw,heads", [(3, 14, 14, 2), (2, 16, 16, 2), (1, 8, 12, 3), (1, 5, 3, 1), (1, 64, 64, 2), (50, 14, 14, 12)])
+@pytest.mark.parametrize("BW,Sh,Sw,heads", [(3, 14, 14, 2), (2, 16, 16, 2), (1, 8, 12, 3), (1, 5, 3, 1), (2, 7, 1, 1), (1, 64, 64, 2), (50, 14, 14, 12), (1, 40, 72, 1)])
 def test_attn_relpos_vs_fp32(cuda, BW, Sh, Sw, heads):
     """Windowed (14x14 = 196 tokens, a ragged last key tile), global (64x64 = 4096) and non-square extents."""
     from vit_deep_radiomics_b200 import _C, ops
@@ -66,12 +66,13 @@ def test_attn_relpos_vs_fp32(cuda, BW, Sh, Sw, heads):
     rel_h = torch.randn(2 * Sh - 1, 64, generator=g) * 0.1
     rel_w = torch.randn(2 * Sw - 1, 64, generator=g) * 0.1
     want, rel_want = _attn_reference(qkv, BW, Sh, Sw, heads, rel_h, rel_w)
-    rel = torch.full((BW * heads * N * (Sh + Sw),), float("nan"), device=cuda)
-    n0 = _C.launch_count()
-    got = ops.attn_relpos(qkv.to(cuda), BW, Sh, Sw, heads, rel_h.to(cuda), rel_w.to(cuda), rel=rel)
-    assert _C.launch_count() - n0 == 2
-    rel_got = rel.cpu().reshape(BW * heads * N, Sh + Sw)
+    rel_got = ops.relpos_tables(qkv.to(cuda), BW, Sh, Sw, heads, rel_h.to(cuda), rel_w.to(cuda)).cpu()
     assert torch.allclose(rel_got, rel_want, atol=2e-4, rtol=1e-4), float((rel_got - rel_want).abs().max())
+    hi, lo = ops.relpos_split(rel_h.to(cuda), rel_w.to(cuda))
+    assert (hi.float() + lo.float() - torch.cat([rel_h, rel_w]).to(cuda)).abs().max() < 2e-5
+    n0 = _C.launch_count()
+    got = ops.attn_relpos(qkv.to(cuda), BW, Sh, Sw, heads, hi, lo)
+    assert _C.launch_count() - n0 == 1            # bias terms are built inside the attention kernel
     got = got.cpu().float()
     assert torch.isfinite(got).all()
     err = (got - want).abs().max()
@@ -85,7 +86,7 @@ def test_attn_relpos_zero_bias_matches_flash_attention(cuda):
     g = torch.Generator().manual_seed(9)
     BW, S, heads = 2, 16, 2
     qkv = torch.randn(BW * S * S, 3 * heads * 64, generator=g).bfloat16().to(cuda)
-    z = torch.zeros(2 * S - 1, 64, device=cuda)
+    z = torch.zeros(2 * (2 * S - 1), 64, device=cuda, dtype=torch.bfloat16)
     a = ops.attn_relpos(qkv, BW, S, S, heads, z, z).float()
     b = ops.flash_attn(qkv, BW, S * S, heads).float()
     assert (a - b).abs().max() < 1.6e-2

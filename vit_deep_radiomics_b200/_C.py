@@ -124,7 +124,7 @@ def lib() -> C.CDLL:
     L.vdr_cross_cls_attn_bwd.argtypes = [vp, vp, i64, vp, vp, i32, i32, f32, vp, vp, i64, vp, vp]
     L.vdr_window_rows.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     L.vdr_relpos_tables.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, vp]
-    L.vdr_attn_relpos_fwd.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, i32, f32, vp]
+    L.vdr_attn_relpos_fwd.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp]
     L.vdr_im2col3x3_tokens.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

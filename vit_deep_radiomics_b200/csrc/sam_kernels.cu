@@ -1,8 +1,8 @@
 // the pieces of the MedSAM / SAM ViT-B image encoder (the backbone the reference loads by
 // default, src/tfds_dense_descriptor.py:104,123; code in the un-vendored segment_anything package) that the plain-ViT path
 // does not have: 14x14 window partition with zero padding, decomposed relative-position bias, attention with that bias,
-// and the 3x3 convolution of the neck as an im2col over token-major maps.  First correct path: the attention runs on
-// mma.sync (bf16 m16n8k16, fp32 accumulation) with the bias added in registers; the GEMMs either side are the tcgen05 kernel.
+// and the 3x3 convolution of the neck as an im2col over token-major maps.  The attention runs on mma.sync (bf16 m16n8k16,
+// fp32 accumulation; cp.async + ldmatrix feed) with the bias built and added on chip; the GEMMs either side are the tcgen05 kernel.
 #include "common.cuh"
 
 namespace vdr {
@@ -87,29 +87,60 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int kRpBQ = 64, kRpBK = 64, kRpPitch = 72;   // 72 bf16 = 36 words per row: fragment loads hit 32 distinct banks
+// cp.async / ldmatrix wrappers (sm_80+ forms; the data path of this kernel is plain LDGSTS + LDSM + HMMA)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 
-// softmax(q k^T * scale + rel_h[q, kh] + rel_w[q, kw]) v   for one (64-query block, head, image-or-window).
-// 4 warps x 16 query rows; key tiles of 64; online softmax in the log2 domain; P rounded to bf16 for the second MMA.
-__global__ void __launch_bounds__(128)
-attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ rel,
-                   __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int heads, int Sh, int Sw, float scale_log2e) {
+constexpr int kRpBQ = 128, kRpBK = 64, kRpPitch = 72;   // 72 bf16 = 144-byte rows: ldmatrix's 8 row segments hit 32 distinct banks
+constexpr int kRpTile = kRpBK * kRpPitch;               // elements of one K / V tile in shared memory
+
+// acc[nt] (16 query rows x 8 tile rows) += Q (A fragments, 16 x 64) * T^T for the 64 rows of a K-major bf16 tile in smem
+__device__ __forceinline__ void qk_tile_mma(float (&acc)[8][4], const uint32_t (&qa)[4][4], uint32_t tile_smem, int lane) {
+  const uint32_t lane_off = ((lane & 7) * kRpPitch + (lane >> 3) * 8) * 2;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int ksp = 0; ksp < 2; ++ksp) {
+      uint32_t b[4];     // b0/b1 of k-step 2*ksp, b0/b1 of k-step 2*ksp + 1
+      ldmatrix_x4(b, tile_smem + lane_off + (nt * 8 * kRpPitch + ksp * 32) * 2);
+      mma_bf16_16816(acc[nt], qa[2 * ksp], b[0], b[1]);
+      mma_bf16_16816(acc[nt], qa[2 * ksp + 1], b[2], b[3]);
+    }
+  }
+}
+
+// softmax(q k^T * scale + rel_h[q, kh] + rel_w[q, kw]) v   for one (128-query block, head, image-or-window).
+//   8 warps x 16 query rows; 64-key tiles, cp.async double buffering; K fragments by ldmatrix, V fragments by ldmatrix.trans;
+//   online softmax in the log2 domain; P rounded to bf16 for the second MMA.
+//   The decomposed relative-position terms are built in the prologue by the same MMA path: the block's queries times the
+//   concatenated tables [rel_pos_h ; rel_pos_w] (rows j), each table split into bf16 hi + lo parts (fp32-class accuracy),
+//   and the entries a query needs -- kh = qh + Sh-1 - j, kw = qw + Sw-1 - j' -- are kept in shared memory.
+__global__ void __launch_bounds__(256, 2)
+attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv_bfloat16* __restrict__ rcat_hi,
+                   const __nv_bfloat16* __restrict__ rcat_lo, __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int heads,
+                   int Sh, int Sw, uint32_t magic_sw, float scale_log2e) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [64 keys][72]
-  __nv_bfloat16* Vt = Ks + kRpBK * kRpPitch;                            // [64 d][72]  (transposed: keys contiguous)
-  float* relS = reinterpret_cast<float*>(Vt + 64 * kRpPitch);          // [64 query rows][R + 1], pre-multiplied by log2(e)
+  __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [2][64 keys][72]
+  __nv_bfloat16* Vb = Kb + 2 * kRpTile;                                 // [2][64 keys][72]
+  float* relS = reinterpret_cast<float*>(Vb + 2 * kRpTile);            // [128 query rows][Sh + Sw + 1], times log2(e)
   const int qb = blockIdx.x, h = blockIdx.y, bw = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int d = heads * 64;
   const int q0 = qb * kRpBQ;
-  const int R = Sh + Sw, RP = R + 1;
+  const int RP = Sh + Sw + 1;
   const __nv_bfloat16* base = qkv + (int64_t)bw * N * ld + h * 64;     // q at +0, k at +d, v at +2d
-  const float* relg = rel + ((int64_t)(bw * heads + h) * N + q0) * R;
-  for (int i = tid; i < kRpBQ * R; i += 128) {
-    const int r = i / R, j = i - r * R;
-    relS[r * RP + j] = (q0 + r < N) ? __ldg(relg + (int64_t)r * R + j) * 1.4426950408889634f : 0.f;
-  }
-  // Q fragments (A operand, 16 rows x 64): rows r0 = g, r1 = g + 8 of this warp's 16
+  const uint32_t kb_s = smem_u32(Kb), vb_s = smem_u32(Vb);
+  // Q fragments (A operand, 16 rows x 64): rows g and g + 8 of this warp's 16
   const int rl0 = warp * 16 + g, rl1 = rl0 + 8;
   const int r0 = q0 + rl0, r1 = q0 + rl1;
   uint32_t qa[4][4];
@@ -122,45 +153,87 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const floa
     qa[ks][2] = r0 < N ? __ldg(p0 + 4) : 0u;
     qa[ks][3] = r1 < N ? __ldg(p1 + 4) : 0u;
   }
+  float* rel0 = relS + rl0 * RP;
+  float* rel1 = relS + rl1 * RP;
+
+  // ---- prologue: the block's bias entries.  Table chunks of 64 rows go through the K buffers (hi -> Kb[0], lo -> Kb[1]).
+  {
+    const int RH = 2 * Sh - 1, RT = RH + 2 * Sw - 1;
+    const int qh0 = r0 / Sw, qh1 = r1 / Sw;
+    const int offh0 = qh0 + Sh - 1, offw0 = r0 - qh0 * Sw + Sw - 1;
+    const int offh1 = qh1 + Sh - 1, offw1 = r1 - qh1 * Sw + Sw - 1;
+    for (int c0 = 0; c0 < RT; c0 += 64) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = tid + i * 256, row = idx >> 3, seg = idx & 7, j = c0 + row;
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        if (j < RT) {
+          hi = __ldg(reinterpret_cast<const uint4*>(rcat_hi + (int64_t)j * 64 + seg * 8));
+          lo = __ldg(reinterpret_cast<const uint4*>(rcat_lo + (int64_t)j * 64 + seg * 8));
+        }
+        *reinterpret_cast<uint4*>(Kb + row * kRpPitch + seg * 8) = hi;
+        *reinterpret_cast<uint4*>(Kb + kRpTile + row * kRpPitch + seg * 8) = lo;
+      }
+      __syncthreads();
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+      qk_tile_mma(acc, qa, kb_s + kRpTile * 2, lane);      // low parts first, then the high parts on top
+      qk_tile_mma(acc, qa, kb_s, lane);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = c0 + nt * 8 + 2 * t + e;
+          if (j < RH) {
+            const int kh0 = offh0 - j, kh1 = offh1 - j;
+            if (r0 < N && kh0 >= 0 && kh0 < Sh) rel0[kh0] = acc[nt][e] * 1.4426950408889634f;
+            if (r1 < N && kh1 >= 0 && kh1 < Sh) rel1[kh1] = acc[nt][2 + e] * 1.4426950408889634f;
+          } else if (j < RT) {
+            const int kw0 = offw0 - (j - RH), kw1 = offw1 - (j - RH);
+            if (r0 < N && kw0 >= 0 && kw0 < Sw) rel0[Sh + kw0] = acc[nt][e] * 1.4426950408889634f;
+            if (r1 < N && kw1 >= 0 && kw1 < Sw) rel1[Sh + kw1] = acc[nt][2 + e] * 1.4426950408889634f;
+          }
+        }
+      }
+    }
+    __syncthreads();      // table chunks consumed: the K buffers may now receive key tiles; relS visible
+  }
+
+  auto issue_tile = [&](int kt) {
+    const int k0 = kt * kRpBK, buf = kt & 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256, row = idx >> 3, seg = idx & 7, key = k0 + row;
+      const int bytes = key < N ? 16 : 0;                                  // out-of-range keys are zero-filled
+      const __nv_bfloat16* src = base + (int64_t)(key < N ? key : N - 1) * ld + seg * 8;
+      const uint32_t off = (buf * kRpTile + row * kRpPitch + seg * 8) * 2;
+      cp_async16(kb_s + off, src + d, bytes);
+      cp_async16(vb_s + off, src + 2 * d, bytes);
+    }
+    cp_async_commit();
+  };
+
   float o[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const float* rel0 = relS + rl0 * RP;
-  const float* rel1 = relS + rl1 * RP;
-
-  for (int k0 = 0; k0 < N; k0 += kRpBK) {
-    __syncthreads();                                 // previous tile fully consumed (also orders the relS staging)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      {   // K: 8 lanes cover one 128-byte row (coalesced)
-        const int idx = tid + i * 128, row = idx >> 3, seg = idx & 7, key = k0 + row;
-        uint4 kv = make_uint4(0u, 0u, 0u, 0u);
-        if (key < N) kv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)key * ld + d + seg * 8));
-        *reinterpret_cast<uint4*>(Ks + row * kRpPitch + seg * 8) = kv;
-      }
-      {   // V, stored transposed: consecutive lanes take consecutive keys so the 2-byte scatter spreads over the banks
-        const int idx = tid + i * 128, row = idx & 63, seg = idx >> 6, key = k0 + row;
-        uint4 vv = make_uint4(0u, 0u, 0u, 0u);
-        if (key < N) vv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)key * ld + 2 * d + seg * 8));
-        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) Vt[(seg * 8 + j) * kRpPitch + row] = e[j];
-      }
+  const int n_tiles = (N + kRpBK - 1) / kRpBK;
+  issue_tile(0);
+  for (int kt = 0; kt < n_tiles; ++kt) {
+    const int k0 = kt * kRpBK, buf = kt & 1;
+    if (kt + 1 < n_tiles) {
+      issue_tile(kt + 1);          // into the buffer the previous iteration finished reading (barrier at its end)
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const uint32_t* kp = reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * kRpPitch + ks * 16 + 2 * t);
-        mma_bf16_16816(s[nt], qa[ks], kp[0], kp[4]);
-      }
-    }
+    qk_tile_mma(s, qa, kb_s + buf * kRpTile * 2, lane);
     // scale + bias + key mask; row maxima
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -169,7 +242,8 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const floa
       for (int e = 0; e < 2; ++e) {
         const int key = k0 + nt * 8 + 2 * t + e;
         if (key < N) {
-          const int kh = key / Sw, kw = key - kh * Sw;
+          const int kh = Sw == 1 ? key : (int)__umulhi((uint32_t)key, magic_sw);
+          const int kw = key - kh * Sw;
           s[nt][e] = fmaf(s[nt][e], scale_log2e, rel0[kh] + rel0[Sh + kw]);
           s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2e, rel1[kh] + rel1[Sh + kw]);
         } else {
@@ -183,20 +257,21 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const floa
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);      // finite: key k0 < N is valid in every tile
-    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);      // exp2(-inf) = 0 on the first tile
+    const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);   // ex2(-inf) = 0 on the first tile
     m0 = mn0; m1 = mn1;
     float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
-      s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+      s[nt][0] = ex2_approx(s[nt][0] - mn0); s[nt][1] = ex2_approx(s[nt][1] - mn0);
+      s[nt][2] = ex2_approx(s[nt][2] - mn1); s[nt][3] = ex2_approx(s[nt][3] - mn1);
       ps0 += s[nt][0] + s[nt][1];
       ps1 += s[nt][2] + s[nt][3];
       o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
     }
     l0 = l0 * c0 + ps0;                               // per-thread partial sums; reduced over the quad at the end
     l1 = l1 * c1 + ps1;
-    // O += P V : P (16 x 64 keys) from the S accumulators, V^T rows give the B fragments
+    // O += P V : P (16 x 64 keys) from the S accumulators; V (keys x d, row-major tile) through ldmatrix.trans
+    const uint32_t v_lane = vb_s + (buf * kRpTile + ((lane & 7) + ((lane >> 3) & 1) * 8) * kRpPitch + (lane >> 4) * 8) * 2;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t pa[4];
@@ -205,11 +280,14 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const floa
       pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vt + (nt * 8 + g) * kRpPitch + kk * 16 + 2 * t);
-        mma_bf16_16816(o[nt], pa, vp[0], vp[4]);
+      for (int ntp = 0; ntp < 4; ++ntp) {
+        uint32_t b[4];   // b0/b1 of d-tile 2*ntp, b0/b1 of d-tile 2*ntp + 1
+        ldmatrix_x4_trans(b, v_lane + (kk * 16 * kRpPitch + ntp * 16) * 2);
+        mma_bf16_16816(o[2 * ntp], pa, b[0], b[1]);
+        mma_bf16_16816(o[2 * ntp + 1], pa, b[2], b[3]);
       }
     }
+    __syncthreads();      // everyone is done with this tile's buffers before the next iteration refills them
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -285,17 +363,17 @@ extern "C" int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const flo
   return VDR_OK;
 }
 
-extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const float* rel, void* out_bf16, int64_t ld_out, int BW,
-                                   int Sh, int Sw, int heads, float scale, vdr_stream_t stream) {
+extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16,
+                                   void* out_bf16, int64_t ld_out, int BW, int Sh, int Sw, int heads, float scale, vdr_stream_t stream) {
   using namespace vdr;
-  VDR_CHECK_ARG(qkv_bf16 && rel && out_bf16, VDR_EINVAL, "vdr_attn_relpos_fwd: null pointer");
-  VDR_CHECK_ARG(BW > 0 && BW <= 65535 && Sh > 0 && Sw > 0 && heads > 0 && heads <= 65535, VDR_EINVAL,
-                "vdr_attn_relpos_fwd: bad shape BW=%d Sh=%d Sw=%d heads=%d", BW, Sh, Sw, heads);
+  VDR_CHECK_ARG(qkv_bf16 && rcat_hi_bf16 && rcat_lo_bf16 && out_bf16, VDR_EINVAL, "vdr_attn_relpos_fwd: null pointer");
+  VDR_CHECK_ARG(BW > 0 && BW <= 65535 && Sh > 0 && Sw > 0 && heads > 0 && heads <= 65535 && (int64_t)Sh * Sw < 65536, VDR_EINVAL,
+                "vdr_attn_relpos_fwd: bad shape BW=%d Sh=%d Sw=%d heads=%d (Sh*Sw < 65536)", BW, Sh, Sw, heads);
   VDR_CHECK_ARG(ld_qkv >= 3LL * heads * 64 && ld_qkv % 8 == 0 && ld_out >= heads * 64LL && ld_out % 8 == 0 && aligned16(qkv_bf16) &&
-                    aligned16(out_bf16),
+                    aligned16(out_bf16) && aligned16(rcat_hi_bf16) && aligned16(rcat_lo_bf16),
                 VDR_EALIGN, "vdr_attn_relpos_fwd: qkv (rows, >= 3*heads*64) / out (rows, >= heads*64), ld %% 8 == 0, 16-byte aligned");
   const int N = Sh * Sw;
-  const size_t smem = 2 * (size_t)kRpBK * kRpPitch * sizeof(__nv_bfloat16) + (size_t)kRpBQ * (Sh + Sw + 1) * sizeof(float);
+  const size_t smem = 4 * (size_t)kRpTile * sizeof(__nv_bfloat16) + (size_t)kRpBQ * (Sh + Sw + 1) * sizeof(float);
   VDR_CHECK_ARG(smem <= 200 * 1024, VDR_EINVAL, "vdr_attn_relpos_fwd: Sh + Sw = %d too large for the shared-memory bias tile", Sh + Sw);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -303,9 +381,11 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const f
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_kernel)");
     configured = smem;
   }
+  const uint32_t magic = Sw > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)Sw - 1) / (uint64_t)Sw) : 0u;   // key / Sw = umulhi(key, magic), key < 2^16
   dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
-  attn_relpos_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, rel, static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, Sh, Sw,
+  attn_relpos_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
+      static_cast<const __nv_bfloat16*>(rcat_lo_bf16), static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, Sh, Sw, magic,
       scale * 1.4426950408889634f);
   count_launch();
   VDR_CHECK_LAUNCH("attn_relpos_kernel");

@@ -601,31 +601,48 @@ def window_rows(src: torch.Tensor, B: int, H: int, W: int, ws: int, to_windows: 
     return out
 
 
-def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor,
-                scale: float | None = None, out: torch.Tensor | None = None, rel: torch.Tensor | None = None) -> torch.Tensor:
-    """Attention with SAM's decomposed relative-position bias over BW images/windows of Sh x Sw tokens.
-    qkv (BW*Sh*Sw, 3*heads*64) bf16; rel_pos_h (2*Sh-1, 64), rel_pos_w (2*Sw-1, 64) f32 -> out (BW*Sh*Sw, heads*64) bf16.
-    Two launches: the per-query bias tables (vdr_relpos_tables), then the fused attention (vdr_attn_relpos_fwd)."""
+def relpos_split(rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor):
+    """[rel_pos_h ; rel_pos_w] (f32, 64 columns) -> (hi, lo) bf16 with hi + lo == the table to ~2^-17 relative: the operand
+    form vdr_attn_relpos_fwd multiplies the queries with.  Weight preparation (once per checkpoint), on the tables' device."""
+    r = torch.cat([rel_pos_h, rel_pos_w], dim=0).to(torch.float32)
+    hi = r.bfloat16()
+    lo = (r - hi.float()).bfloat16()
+    return hi.contiguous(), lo.contiguous()
+
+
+def relpos_tables(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor) -> torch.Tensor:
+    """(BW*heads*Sh*Sw, Sh+Sw) f32: rel_h[q, kh] | rel_w[q, kw] of add_decomposed_rel_pos, evaluated in fp32 (vdr_relpos_tables)."""
     _req(qkv, torch.bfloat16, "qkv"), _req(rel_pos_h, torch.float32, "rel_pos_h"), _req(rel_pos_w, torch.float32, "rel_pos_w")
     N, d = Sh * Sw, heads * 64
     if qkv.shape != (BW * N, 3 * d) or qkv.stride(1) != 1:
         raise ValueError(f"qkv must be ({BW * N}, {3 * d}), got {tuple(qkv.shape)}")
     if rel_pos_h.shape != (2 * Sh - 1, 64) or rel_pos_w.shape != (2 * Sw - 1, 64) or not rel_pos_h.is_contiguous() or not rel_pos_w.is_contiguous():
-        raise ValueError("rel_pos_h / rel_pos_w must be contiguous (2*S-1, 64) tables (interpolate them first when the extent differs)")
+        raise ValueError("rel_pos_h / rel_pos_w must be contiguous (2*S-1, 64) tables")
+    rel = torch.empty((BW * heads * N, Sh + Sw), dtype=torch.float32, device=qkv.device)
+    _C.check(_C.lib().vdr_relpos_tables(qkv.data_ptr(), qkv.stride(0), rel_pos_h.data_ptr(), rel_pos_w.data_ptr(), rel.data_ptr(),
+                                        BW, Sh, Sw, heads, _stream()), "vdr_relpos_tables")
+    return rel
+
+
+def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rcat_hi: torch.Tensor, rcat_lo: torch.Tensor,
+                scale: float | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Attention with SAM's decomposed relative-position bias over BW images/windows of Sh x Sw tokens, one launch.
+    qkv (BW*Sh*Sw, 3*heads*64) bf16; (rcat_hi, rcat_lo) = relpos_split(rel_pos_h (2*Sh-1, 64), rel_pos_w (2*Sw-1, 64))
+    -> out (BW*Sh*Sw, heads*64) bf16."""
+    _req(qkv, torch.bfloat16, "qkv"), _req(rcat_hi, torch.bfloat16, "rcat_hi"), _req(rcat_lo, torch.bfloat16, "rcat_lo")
+    N, d = Sh * Sw, heads * 64
+    if qkv.shape != (BW * N, 3 * d) or qkv.stride(1) != 1:
+        raise ValueError(f"qkv must be ({BW * N}, {3 * d}), got {tuple(qkv.shape)}")
+    RT = 2 * Sh - 1 + 2 * Sw - 1
+    if rcat_hi.shape != (RT, 64) or rcat_lo.shape != (RT, 64) or not rcat_hi.is_contiguous() or not rcat_lo.is_contiguous():
+        raise ValueError(f"rcat_hi / rcat_lo must be contiguous ({RT}, 64) tables (relpos_split; interpolate first when the extent differs)")
     if scale is None:
         scale = 1.0 / math.sqrt(64)
     if out is None:
         out = torch.empty((BW * N, d), dtype=torch.bfloat16, device=qkv.device)
-    if rel is None:
-        rel = torch.empty(BW * heads * N * (Sh + Sw), dtype=torch.float32, device=qkv.device)
-    if rel.numel() < BW * heads * N * (Sh + Sw):
-        raise ValueError("rel scratch too small")
-    with _Prof("attn", 2.0 * BW * heads * N * (Sh + Sw) * 64, f"relpos tables BW{BW} {Sh}x{Sw} h{heads}"):
-        _C.check(_C.lib().vdr_relpos_tables(qkv.data_ptr(), qkv.stride(0), rel_pos_h.data_ptr(), rel_pos_w.data_ptr(), rel.data_ptr(),
-                                            BW, Sh, Sw, heads, _stream()), "vdr_relpos_tables")
-    with _Prof("attn", 4.0 * BW * heads * N * N * 64, f"attn+relpos BW{BW} N{N} h{heads}"):
-        _C.check(_C.lib().vdr_attn_relpos_fwd(qkv.data_ptr(), qkv.stride(0), rel.data_ptr(), out.data_ptr(), out.stride(0), BW, Sh, Sw,
-                                              heads, float(scale), _stream()), "vdr_attn_relpos_fwd")
+    with _Prof("attn", 4.0 * BW * heads * N * N * 64 + 2.0 * BW * heads * N * (Sh + Sw) * 64, f"attn+relpos BW{BW} N{N} h{heads}"):
+        _C.check(_C.lib().vdr_attn_relpos_fwd(qkv.data_ptr(), qkv.stride(0), rcat_hi.data_ptr(), rcat_lo.data_ptr(), out.data_ptr(),
+                                              out.stride(0), BW, Sh, Sw, heads, float(scale), _stream()), "vdr_attn_relpos_fwd")
     return out
 
 

@@ -9,7 +9,7 @@
 
 State-dict keys are segment_anything's / DINOv2's, with or without the ``image_encoder.`` prefix of a full SAM checkpoint,
 so ``medsam_vit_b.pth`` loads unchanged.  The GEMMs are the tcgen05 kernel (vdr_gemm); the attention with bias is the
-first correct path of this row (vdr_relpos_tables + vdr_attn_relpos_fwd on mma.sync), not yet on tcgen05.
+mma.sync kernel of this row (vdr_attn_relpos_fwd: bias terms built on chip, cp.async + ldmatrix feed), not yet on tcgen05.
 There is no CPU path: every op is a libvdr call on CUDA tensors.
 """
 from __future__ import annotations
@@ -127,12 +127,13 @@ class SamImageEncoder:
         for i in range(cfg["depth"]):
             b = f"blocks.{i}."
             sh, sw = (gh, gw) if i in cfg["global_attn"] else (ws, ws)
+            rel_hi, rel_lo = ops.relpos_split(_fit_rel_pos(sd[b + "attn.rel_pos_h"].float(), sh).to(dev),
+                                              _fit_rel_pos(sd[b + "attn.rel_pos_w"].float(), sw).to(dev))
             self.w["blocks"].append(dict(
                 n1w=f32(b + "norm1.weight"), n1b=f32(b + "norm1.bias"),
                 qkv_w=bf(b + "attn.qkv.weight"), qkv_b=f32(b + "attn.qkv.bias"),
                 proj_w=bf(b + "attn.proj.weight"), proj_b=f32(b + "attn.proj.bias"),
-                rel_h=_fit_rel_pos(sd[b + "attn.rel_pos_h"].float(), sh).to(dev).contiguous(),
-                rel_w=_fit_rel_pos(sd[b + "attn.rel_pos_w"].float(), sw).to(dev).contiguous(),
+                rel_hi=rel_hi, rel_lo=rel_lo,
                 n2w=f32(b + "norm2.weight"), n2b=f32(b + "norm2.bias"),
                 fc1_w=bf(b + "mlp.lin1.weight"), fc1_b=f32(b + "mlp.lin1.bias"),
                 fc2_w=bf(b + "mlp.lin2.weight"), fc2_b=f32(b + "mlp.lin2.bias"),
@@ -147,14 +148,11 @@ class SamImageEncoder:
             N = gh * gw
             nwin = (-(-gh // win)) * (-(-gw // win))
             NW = nwin * win * win                                    # rows per image in the windowed layout (>= N)
-            heads = cfg["heads"]
-            rel_elems = max(B * heads * N * (gh + gw), B * nwin * heads * win * win * 2 * win)
             ws = dict(A=torch.empty(B * N, self.K, dtype=bf, device=dev),
                       X=torch.empty(B * N, d, dtype=bf, device=dev), Y=torch.empty(B * N, d, dtype=bf, device=dev),
                       YW=torch.empty(B * NW, d, dtype=bf, device=dev), OW=torch.empty(B * NW, d, dtype=bf, device=dev),
                       QKV=torch.empty(B * max(N, NW), 3 * d, dtype=bf, device=dev),
                       H=torch.empty(B * N, 4 * d, dtype=bf, device=dev),
-                      REL=torch.empty(rel_elems, dtype=torch.float32, device=dev),
                       N0=torch.empty(B * N, oc, dtype=bf, device=dev), N1=torch.empty(B * N, oc, dtype=bf, device=dev),
                       NA=torch.empty(B * N, 9 * oc, dtype=bf, device=dev),
                       OUT=torch.empty(B * N, oc, dtype=torch.float32, device=dev))
@@ -198,12 +196,12 @@ class SamImageEncoder:
                 ops.window_rows(Y, B, gh, gw, win, True, out=ws["YW"])
                 qkv = ws["QKV"][:B * NW]
                 ops.gemm(ws["YW"], blk["qkv_w"], blk["qkv_b"], out=qkv)
-                ops.attn_relpos(qkv, B * nwh * nww, win, win, heads, blk["rel_h"], blk["rel_w"], scale, out=ws["OW"], rel=ws["REL"])
+                ops.attn_relpos(qkv, B * nwh * nww, win, win, heads, blk["rel_hi"], blk["rel_lo"], scale, out=ws["OW"])
                 ops.window_rows(ws["OW"], B, gh, gw, win, False, out=Y)
             else:
                 qkv = ws["QKV"][:B * N]
                 ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=qkv)
-                ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_h"], blk["rel_w"], scale, out=Y, rel=ws["REL"])
+                ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_hi"], blk["rel_lo"], scale, out=Y)
             ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X)
             ops.layernorm(X, blk["n2w"], blk["n2b"], 1e-6, out=Y)
             ops.gemm(Y, blk["fc1_w"], blk["fc1_b"], epilogue="gelu", out=Hb)
