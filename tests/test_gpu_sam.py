@@ -56,7 +56,7 @@ def _attn_reference(qkv, BW, Sh, Sw, heads, rel_h, rel_w):
     return out, torch.cat([bh, bw], dim=-1).reshape(BW * heads * N, Sh + Sw)
 
 
-@pytest.mark.parametrize("BW,Sh,Sw,heads", [(3, 14, 14, 2), (2, 16, 16, 2), (1, 8, 12, 3), (1, 5, 3, 1), (2, 7, 1, 1), (1, 64, 64, 2), (50, 14, 14, 12), (1, 40, 72, 1)])
+@pytest.mark.parametrize("BW,Sh,Sw,heads", [(3, 14, 14, 2), (2, 16, 16, 2), (1, 8, 12, 3), (1, 5, 3, 1), (2, 7, 1, 1), (1, 64, 64, 2), (2, 3, 64, 1), (50, 14, 14, 12), (1, 40, 72, 1)])
 def test_attn_relpos_vs_fp32(cuda, BW, Sh, Sw, heads):
     """Windowed (14x14 = 196 tokens, a ragged last key tile), global (64x64 = 4096) and non-square extents."""
     from vit_deep_radiomics_b200 import _C, ops

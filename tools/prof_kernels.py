@@ -62,3 +62,12 @@ if which in ("gather", "all"):
             ops.mask_gather(tok, mm, grid=(S, gh, gw, gh * gw + 1, 1), pe=pe)
         torch.cuda.synchronize()
 print("done")
+if which in ("sam",):
+    # MedSAM attention with rel-pos bias: 4 images of 64 x 64 tokens (global) and 100 windows of 14 x 14, 12 heads
+    for (BW, S) in [(4, 64), (100, 14)]:
+        qkv = torch.randn(BW * S * S, 3 * d, device=dev).bfloat16()
+        hi, lo = ops.relpos_split(torch.randn(2 * S - 1, 64, device=dev) * 0.1, torch.randn(2 * S - 1, 64, device=dev) * 0.1)
+        out = torch.empty(BW * S * S, d, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):   # launches 0-2 global, 3-5 windowed: ncu takes -s 2 -c 2 (one of each... the last global, the first windowed)
+            ops.attn_relpos(qkv, BW, S, S, 12, hi, lo, out=out)
+        torch.cuda.synchronize()

@@ -104,17 +104,19 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 constexpr int kRpBQ = 128, kRpBK = 64, kRpPitch = 72;   // 72 bf16 = 144-byte rows: ldmatrix's 8 row segments hit 32 distinct banks
 constexpr int kRpTile = kRpBK * kRpPitch;               // elements of one K / V tile in shared memory
 
-// acc[nt] (16 query rows x 8 tile rows) += Q (A fragments, 16 x 64) * T^T for the 64 rows of a K-major bf16 tile in smem
+// acc[nt] (16 query rows x 8 tile rows) += Q (A fragments, 16 x 64) * T^T for the 64 rows of a K-major bf16 tile in smem.
+// One ldmatrix.x4 feeds two n-tiles of one k-step, so consecutive MMAs never accumulate into the same registers
+// (a dependent HMMA chain stalls for the full pipe latency).
 __device__ __forceinline__ void qk_tile_mma(float (&acc)[8][4], const uint32_t (&qa)[4][4], uint32_t tile_smem, int lane) {
-  const uint32_t lane_off = ((lane & 7) * kRpPitch + (lane >> 3) * 8) * 2;
+  const uint32_t lane_off = (((lane & 7) + (lane >> 4) * 8) * kRpPitch + ((lane >> 3) & 1) * 8) * 2;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
+  for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-    for (int ksp = 0; ksp < 2; ++ksp) {
-      uint32_t b[4];     // b0/b1 of k-step 2*ksp, b0/b1 of k-step 2*ksp + 1
-      ldmatrix_x4(b, tile_smem + lane_off + (nt * 8 * kRpPitch + ksp * 32) * 2);
-      mma_bf16_16816(acc[nt], qa[2 * ksp], b[0], b[1]);
-      mma_bf16_16816(acc[nt], qa[2 * ksp + 1], b[2], b[3]);
+    for (int ntp = 0; ntp < 4; ++ntp) {
+      uint32_t b[4];     // b0/b1 of n-tile 2*ntp, b0/b1 of n-tile 2*ntp + 1, k-step ks
+      ldmatrix_x4(b, tile_smem + lane_off + (ntp * 16 * kRpPitch + ks * 16) * 2);
+      mma_bf16_16816(acc[2 * ntp], qa[ks], b[0], b[1]);
+      mma_bf16_16816(acc[2 * ntp + 1], qa[ks], b[2], b[3]);
     }
   }
 }
@@ -125,19 +127,21 @@ __device__ __forceinline__ void qk_tile_mma(float (&acc)[8][4], const uint32_t (
 //   The decomposed relative-position terms are built in the prologue by the same MMA path: the block's queries times the
 //   concatenated tables [rel_pos_h ; rel_pos_w] (rows j), each table split into bf16 hi + lo parts (fp32-class accuracy),
 //   and the entries a query needs -- kh = qh + Sh-1 - j, kw = qw + Sw-1 - j' -- are kept in shared memory.
+//   kRowTiles: Sw == 64 and N % 64 == 0 (the 64 x 64 token grid of a 1024^2 image): a key tile is exactly one grid row, so
+//   kh = tile index, kw = column -- no index arithmetic, no key mask, the rel_w terms come as aligned float2 loads.
+template <bool kRowTiles>
 __global__ void __launch_bounds__(256, 2)
 attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv_bfloat16* __restrict__ rcat_hi,
                    const __nv_bfloat16* __restrict__ rcat_lo, __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int heads,
-                   int Sh, int Sw, uint32_t magic_sw, float scale_log2e) {
+                   int Sh, int Sw, int RP, uint32_t magic_sw, float scale_log2e) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [2][64 keys][72]
   __nv_bfloat16* Vb = Kb + 2 * kRpTile;                                 // [2][64 keys][72]
-  float* relS = reinterpret_cast<float*>(Vb + 2 * kRpTile);            // [128 query rows][Sh + Sw + 1], times log2(e)
+  float* relS = reinterpret_cast<float*>(Vb + 2 * kRpTile);            // [128 query rows][RP >= Sh + Sw], times log2(e); RP % 32 == 8
   const int qb = blockIdx.x, h = blockIdx.y, bw = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int d = heads * 64;
   const int q0 = qb * kRpBQ;
-  const int RP = Sh + Sw + 1;
   const __nv_bfloat16* base = qkv + (int64_t)bw * N * ld + h * 64;     // q at +0, k at +d, v at +2d
   const uint32_t kb_s = smem_u32(Kb), vb_s = smem_u32(Vb);
   // Q fragments (A operand, 16 rows x 64): rows g and g + 8 of this warp's 16
@@ -155,6 +159,7 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
   }
   float* rel0 = relS + rl0 * RP;
   float* rel1 = relS + rl1 * RP;
+  const int WO = (Sh + 1) & ~1;                // rel_w terms start at an even column: float2 loads in the row-tile variant
 
   // ---- prologue: the block's bias entries.  Table chunks of 64 rows go through the K buffers (hi -> Kb[0], lo -> Kb[1]).
   {
@@ -192,8 +197,8 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
             if (r1 < N && kh1 >= 0 && kh1 < Sh) rel1[kh1] = acc[nt][2 + e] * 1.4426950408889634f;
           } else if (j < RT) {
             const int kw0 = offw0 - (j - RH), kw1 = offw1 - (j - RH);
-            if (r0 < N && kw0 >= 0 && kw0 < Sw) rel0[Sh + kw0] = acc[nt][e] * 1.4426950408889634f;
-            if (r1 < N && kw1 >= 0 && kw1 < Sw) rel1[Sh + kw1] = acc[nt][2 + e] * 1.4426950408889634f;
+            if (r0 < N && kw0 >= 0 && kw0 < Sw) rel0[WO + kw0] = acc[nt][e] * 1.4426950408889634f;
+            if (r1 < N && kw1 >= 0 && kw1 < Sw) rel1[WO + kw1] = acc[nt][2 + e] * 1.4426950408889634f;
           }
         }
       }
@@ -234,24 +239,40 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
     qk_tile_mma(s, qa, kb_s + buf * kRpTile * 2, lane);
-    // scale + bias + key mask; row maxima
+    // scale + bias (+ key mask on a ragged last tile); row maxima
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (kRowTiles) {
+      const float bh0 = rel0[kt], bh1 = rel1[kt];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 w0 = *reinterpret_cast<const float2*>(rel0 + WO + nt * 8 + 2 * t);
+        const float2 w1 = *reinterpret_cast<const float2*>(rel1 + WO + nt * 8 + 2 * t);
+        s[nt][0] = fmaf(s[nt][0], scale_log2e, bh0 + w0.x);
+        s[nt][1] = fmaf(s[nt][1], scale_log2e, bh0 + w0.y);
+        s[nt][2] = fmaf(s[nt][2], scale_log2e, bh1 + w1.x);
+        s[nt][3] = fmaf(s[nt][3], scale_log2e, bh1 + w1.y);
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+    } else {
+      const bool ragged = k0 + kRpBK > N;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int key = k0 + nt * 8 + 2 * t + e;
-        if (key < N) {
-          const int kh = Sw == 1 ? key : (int)__umulhi((uint32_t)key, magic_sw);
-          const int kw = key - kh * Sw;
-          s[nt][e] = fmaf(s[nt][e], scale_log2e, rel0[kh] + rel0[Sh + kw]);
-          s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2e, rel1[kh] + rel1[Sh + kw]);
-        } else {
-          s[nt][e] = -INFINITY;
-          s[nt][2 + e] = -INFINITY;
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = k0 + nt * 8 + 2 * t + e;
+          if (!ragged || key < N) {
+            const int kh = Sw == 1 ? key : (int)__umulhi((uint32_t)key, magic_sw);
+            const int kw = key - kh * Sw;
+            s[nt][e] = fmaf(s[nt][e], scale_log2e, rel0[kh] + rel0[WO + kw]);
+            s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2e, rel1[kh] + rel1[WO + kw]);
+          } else {
+            s[nt][e] = -INFINITY;
+            s[nt][2 + e] = -INFINITY;
+          }
+          mx0 = fmaxf(mx0, s[nt][e]);
+          mx1 = fmaxf(mx1, s[nt][2 + e]);
         }
-        mx0 = fmaxf(mx0, s[nt][e]);
-        mx1 = fmaxf(mx1, s[nt][2 + e]);
       }
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
@@ -266,7 +287,10 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
       s[nt][2] = ex2_approx(s[nt][2] - mn1); s[nt][3] = ex2_approx(s[nt][3] - mn1);
       ps0 += s[nt][0] + s[nt][1];
       ps1 += s[nt][2] + s[nt][3];
-      o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
+    }
+    if (__any_sync(0xffffffffu, c0 != 1.f || c1 != 1.f)) {      // the running maxima settle after the first tiles
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
     }
     l0 = l0 * c0 + ps0;                               // per-thread partial sums; reduced over the quad at the end
     l1 = l1 * c1 + ps1;
@@ -373,19 +397,23 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const v
                     aligned16(out_bf16) && aligned16(rcat_hi_bf16) && aligned16(rcat_lo_bf16),
                 VDR_EALIGN, "vdr_attn_relpos_fwd: qkv (rows, >= 3*heads*64) / out (rows, >= heads*64), ld %% 8 == 0, 16-byte aligned");
   const int N = Sh * Sw;
-  const size_t smem = 4 * (size_t)kRpTile * sizeof(__nv_bfloat16) + (size_t)kRpBQ * (Sh + Sw + 1) * sizeof(float);
+  const int rp0 = ((Sh + 1) & ~1) + Sw;                          // rel_h terms, pad to an even column, rel_w terms
+  const int RP = rp0 + (8 - rp0 % 32 + 32) % 32;                 // row pitch of the bias tile: RP % 32 == 8 spreads a warp's rows over the banks
+  const size_t smem = 4 * (size_t)kRpTile * sizeof(__nv_bfloat16) + (size_t)kRpBQ * RP * sizeof(float);
   VDR_CHECK_ARG(smem <= 200 * 1024, VDR_EINVAL, "vdr_attn_relpos_fwd: Sh + Sw = %d too large for the shared-memory bias tile", Sh + Sw);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool row_tiles = Sw == 64 && N % 64 == 0;
+  auto kernel = row_tiles ? attn_relpos_kernel<true> : attn_relpos_kernel<false>;
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[row_tiles]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_kernel)");
-    configured = smem;
+    configured[row_tiles] = smem;
   }
   const uint32_t magic = Sw > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)Sw - 1) / (uint64_t)Sw) : 0u;   // key / Sw = umulhi(key, magic), key < 2^16
   dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
-  attn_relpos_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
-      static_cast<const __nv_bfloat16*>(rcat_lo_bf16), static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, Sh, Sw, magic,
+      static_cast<const __nv_bfloat16*>(rcat_lo_bf16), static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, Sh, Sw, RP, magic,
       scale * 1.4426950408889634f);
   count_launch();
   VDR_CHECK_LAUNCH("attn_relpos_kernel");
