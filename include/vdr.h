@@ -329,21 +329,26 @@ int vdr_cross_cls_attn_bwd(const float* q0, const void* kv, int64_t ld_kv, const
  * vdr_window_rows: window_partition / window_unpartition of the encoder blocks.  to_windows != 0: src (B*H*W, d) ->
  *   dst (B*nwh*nww*ws*ws, d), nwh = ceil(H/ws), rows outside H x W written as zeros (the padding is applied after norm1);
  *   to_windows == 0: the inverse, pad rows dropped.
- * vdr_relpos_tables: decomposed relative-position terms of add_decomposed_rel_pos for every query of BW images/windows of
- *   Sh x Sw tokens: rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = q . rel_pos_h[qh - j + Sh - 1] (j < Sh) or
- *   q . rel_pos_w[qw - (j - Sh) + Sw - 1]; q = the UNSCALED query vector read from qkv; rel_pos_h (2*Sh-1, 64) f32,
- *   rel_pos_w (2*Sw-1, 64) f32 (shared by the heads; tables of another length are interpolated by the caller).
- *   (A stand-alone fp32 evaluation of the bias terms: the attention below builds them on chip and does not read this table.)
+ * Relative-position tables: rel_pos_h (2*Sh-1, 64) and rel_pos_w (2*Sw-1, 64) f32 (shared by the heads; tables of another
+ *   length are interpolated by the caller) are passed concatenated [rel_pos_h ; rel_pos_w] and split as rcat_hi = bf16(R),
+ *   rcat_lo = bf16(R - hi): the kernels multiply queries with both parts on the tensor cores (fp32-class accuracy).
+ * vdr_relpos_tables: the decomposed terms of add_decomposed_rel_pos for every query of BW images/windows of Sh x Sw tokens:
+ *   rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = out_scale * q . rel_pos_h[qh - j + Sh - 1] (j < Sh) or
+ *   out_scale * q . rel_pos_w[qw - (j - Sh) + Sw - 1]; q = the UNSCALED query vector read from qkv.
+ * vdr_flash_attn_relpos_fwd: the tcgen05 flash kernel (vdr_flash_attn_fwd) with that bias added to the scores, for token grids
+ *   of Sh x 64 with Sh % 4 == 0 (the 64 x 64 grid of SAM's global-attention blocks): rel_log2 = vdr_relpos_tables(..., Sw = 64,
+ *   out_scale = log2(e)).  out = softmax(q k^T * scale + rel_h[q, kh] + rel_w[q, kw]) v.
  * vdr_attn_relpos_fwd: out = softmax(q k^T * scale + rel_h[q, kh] + rel_w[q, kw]) v per (image/window, head); qkv
- *   (BW*N, >= 3*heads*64) as the qkv GEMM writes it, N = Sh*Sw < 65536; out (BW*N, heads*64) bf16.  rcat_hi / rcat_lo
- *   (2*Sh-1 + 2*Sw-1, 64) bf16: the concatenated tables [rel_pos_h ; rel_pos_w] split as hi = bf16(R), lo = bf16(R - hi);
- *   the kernel multiplies the block's queries with both parts on the tensor cores (fp32-class accuracy) in its prologue.
+ *   (BW*N, >= 3*heads*64) as the qkv GEMM writes it, N = Sh*Sw < 65536; out (BW*N, heads*64) bf16.  Any extent (the 14 x 14
+ *   windows); mma.sync kernel that builds its bias terms on chip from rcat_hi / rcat_lo in its prologue (no table in HBM).
  * vdr_im2col3x3_tokens: A[(b,y,x), (ky*3+kx)*C + c] = X[(b, y+ky-1, x+kx-1), c], zero padded: the A operand of the neck's
  *   3x3 convolution as a GEMM against the weight permuted to (out, ky, kx, in). */
 int vdr_window_rows(const void* src_bf16, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int B, int H, int W, int ws, int d,
                     int to_windows, vdr_stream_t stream);
-int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const float* rel_pos_h, const float* rel_pos_w, float* rel, int BW,
-                      int Sh, int Sw, int heads, vdr_stream_t stream);
+int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, float* rel, int BW,
+                      int Sh, int Sw, int heads, float out_scale, vdr_stream_t stream);
+int vdr_flash_attn_relpos_fwd(const void* qkv, int64_t ld_qkv, const float* rel_log2, void* out, int64_t ld_out, int B, int Sh,
+                              int heads, float scale, vdr_stream_t stream);
 int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, void* out_bf16,
                         int64_t ld_out, int BW, int Sh, int Sw, int heads, float scale, vdr_stream_t stream);
 int vdr_im2col3x3_tokens(const void* X_bf16, int64_t ldx, void* A_bf16, int64_t lda, int B, int H, int W, int C,

@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 #ifndef VDR_ATTN_POLY_MASK
@@ -62,7 +64,13 @@ struct AttnParams {
   int dbg;                     // timing experiments only (VDR_ATTN_DBG): 1 = tail CTAs exit at once, 2 = skip the trailing-key fold
   int q_tiles, tail_rows;      // full 128-row query tiles (tensor cores) / trailing rows handled by the extra CUDA-core CTA
   unsigned long long* trace;   // debug (VDR_ATTN_TRACE builds only): per-iteration timestamps of CTA (0,0,0)
+  // kBias instantiation only (SAM / MedSAM global attention over an Sh x 64 token grid, N % 128 == 0): additive bias
+  // rel[(b*heads + head)*N + q][kh] + rel[...][Sh + kw] for key (kh, kw), already multiplied by log2(e)  (vdr_relpos_tables)
+  const float* rel;
+  int rel_pitch;               // Sh + 64
 };
+constexpr int kBiasPitch = 136;                          // bytes per query row of the rel_w terms in shared memory: 64 halfs + 8 pad
+constexpr int kAttnSmemBias = kAttnSmem + 128 * kBiasPitch;
 
 #ifdef VDR_ATTN_TRACE
 __device__ __forceinline__ unsigned long long attn_gtime() {
@@ -238,6 +246,12 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
 //   softmax: wait S_j -> registers -> signal "consumed" -> max (exchanged between the two half-row threads) ->
 //            exp2 / sum -> wait O_{j-1} -> (rare) rescale O -> write P_j -> signal "ready"
 // so the tensor pipe computes S_{j+1} and O_{j-1} while the exponentials of block j are evaluated.
+// kBias: the additive decomposed relative-position bias of SAM's global-attention blocks.  A 128-key block is two rows of
+// the Sh x 64 token grid, so each softmax thread (one query row, 64 score columns) sees exactly one grid row per block:
+// its bias is one scalar rel_h[q, kh] per block (prefetched from global memory a block ahead) plus the 64 rel_w[q, kw]
+// of its query row, which are the same for every block and sit in shared memory as fp16 (16 KB per CTA; |rel_w| of a
+// few units -> 1e-3 absolute in the exponent, below the bf16 rounding of P).
+template <bool kBias>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -421,9 +435,27 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     const uint32_t tO = tmem_O + lane_sel + half * 32;                // the 32 output columns this thread rescales / stores
     float m_ref = -INFINITY, l_run = 0.f;
     const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+    const unsigned char* bw_row = smem + kAttnSmem + row * kBiasPitch;     // kBias: this query row's 64 rel_w terms (fp16)
+    const float* rel_row = nullptr;
+    float bh_next = 0.f;
+    if (kBias) {
+      rel_row = p.rel + (static_cast<int64_t>(b * p.heads + head) * p.N + q0 + row) * p.rel_pitch;
+      const float4* src = reinterpret_cast<const float4*>(rel_row + (p.rel_pitch - 64) + half * 32);   // this thread converts 32 of the 64
+      uint2* dst = reinterpret_cast<uint2*>(smem + kAttnSmem + row * kBiasPitch + half * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = __ldg(src + i);
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        dst[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+      bh_next = __ldg(rel_row + half);                                     // grid row of block 0, this half
+      pair_bar_sync(quarter);                                              // the other half-row warp wrote the other 32
+    }
 
     for (int j = 0; j < nkv; ++j) {
       ATT_TRACE(0);
+      const float bh_cur = bh_next;
+      if (kBias && j + 1 < nkv) bh_next = __ldg(rel_row + 2 * (j + 1) + half);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       ATT_TRACE(1);
@@ -499,6 +531,23 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfree);
         ATT_TRACE(2);
+        if (kBias) {   // scores -> log2 domain with the bias added: v = S * scale + (rel_h + rel_w)
+          const uint64_t bh2 = pack2(bh_cur, bh_cur);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const uint2 hb = *reinterpret_cast<const uint2*>(bw_row + (c * 32 + i) * 2);
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hb.x));
+              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&hb.y));
+              float v0, v1, v2, v3;
+              unpack2(fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, add2(pack2(f0.x, f0.y), bh2)), v0, v1);
+              unpack2(fma2(pack2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), scale2, add2(pack2(f1.x, f1.y), bh2)), v2, v3);
+              sr[c][i] = __float_as_uint(v0); sr[c][i + 1] = __float_as_uint(v1);
+              sr[c][i + 2] = __float_as_uint(v2); sr[c][i + 3] = __float_as_uint(v3);
+            }
+          }
+        }
         // block maximum of this half row (four independent chains), exchanged with the other half-row thread
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -512,7 +561,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         xmax[half * 128 + row] = mx;
         pair_bar_sync(quarter);
         mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]);
-        const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+        const float m_new = fmaxf(m_ref, kBias ? mx : mx * p.scale_log2);
         moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);   // warp-uniform (TMEM accesses are warp-wide) and, since both
         if (moved) {                                             //  half-row warps see the same row maxima, CTA-pair-uniform
           alpha = ex2(m_ref - m_new);
@@ -525,7 +574,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2);
+            const uint64_t s2 = pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+            const uint64_t x2 = kBias ? add2(s2, negm2) : fma2(s2, scale2, negm2);
             float p0, p1;
             if ((kPolyMask >> ((i >> 1) & 7)) & 1u) {   // a fixed subset of every 8 pairs: FMA-pipe exp2
               exp2_poly2(x2, p0, p1);
@@ -637,21 +687,22 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
 static unsigned long long* g_attn_trace = nullptr;
 extern "C" void vdr_debug_set_attn_trace(void* device_buf) { g_attn_trace = static_cast<unsigned long long*>(device_buf); }
 
-extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B,
-                                  int N, int heads, float scale, vdr_stream_t stream) {
+static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, const float* rel, int rel_pitch, void* out, int64_t ld_out,
+                             float* lse, int B, int N, int heads, float scale, vdr_stream_t stream) {
   using namespace vdr;
-  VDR_CHECK_ARG(qkv && out, VDR_EINVAL, "vdr_flash_attn_fwd: null pointer");
-  VDR_CHECK_ARG(B > 0 && N > 0 && heads > 0, VDR_EINVAL, "vdr_flash_attn_fwd: bad shape B=%d N=%d heads=%d", B, N, heads);
+  VDR_CHECK_ARG(qkv && out, VDR_EINVAL, "%s: null pointer", who);
+  VDR_CHECK_ARG(B > 0 && N > 0 && heads > 0, VDR_EINVAL, "%s: bad shape B=%d N=%d heads=%d", who, B, N, heads);
   const int d = heads * kHD;
-  VDR_CHECK_ARG(ld_qkv >= 3 * d && ld_qkv % 8 == 0 && ld_out >= d && ld_out % 8 == 0, VDR_EALIGN, "vdr_flash_attn_fwd: ld_qkv (%lld) / ld_out (%lld) too small or not multiples of 8", (long long)ld_qkv, (long long)ld_out);
-  VDR_CHECK_ARG(aligned16(qkv) && aligned16(out), VDR_EALIGN, "vdr_flash_attn_fwd: pointers must be 16-byte aligned");
-  VDR_CHECK_ARG(B <= 65535 && heads <= 65535, VDR_EINVAL, "vdr_flash_attn_fwd: B and heads must be <= 65535");
+  VDR_CHECK_ARG(ld_qkv >= 3 * d && ld_qkv % 8 == 0 && ld_out >= d && ld_out % 8 == 0, VDR_EALIGN, "%s: ld_qkv (%lld) / ld_out (%lld) too small or not multiples of 8", who, (long long)ld_qkv, (long long)ld_out);
+  VDR_CHECK_ARG(aligned16(qkv) && aligned16(out), VDR_EALIGN, "%s: pointers must be 16-byte aligned", who);
+  VDR_CHECK_ARG(B <= 65535 && heads <= 65535, VDR_EINVAL, "%s: B and heads must be <= 65535", who);
   CUtensorMap tm;
   int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * d, (uint64_t)ld_qkv, 128, kHD);
   if (rc != VDR_OK) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_fwd)");
     configured = true;
   }
@@ -665,6 +716,8 @@ extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, in
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
   p.dbg = getenv("VDR_ATTN_DBG") ? atoi(getenv("VDR_ATTN_DBG")) : 0;
+  p.rel = rel;
+  p.rel_pitch = rel_pitch;
   // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head)
   const int tail_rows = N % kBQ;
   const bool vector_tail = tail_rows > 0 && tail_rows <= 8;
@@ -672,8 +725,24 @@ extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, in
   p.tail_rows = vector_tail ? tail_rows : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.q_tiles + (vector_tail ? 1 : 0), heads, B);
-  flash_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
+  if (rel != nullptr)
+    flash_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, p);
+  else
+    flash_attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
   count_launch();
   VDR_CHECK_LAUNCH("flash_attn_fwd_kernel");
   return VDR_OK;
+}
+
+extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B,
+                                  int N, int heads, float scale, vdr_stream_t stream) {
+  return launch_flash_attn("vdr_flash_attn_fwd", qkv, ld_qkv, nullptr, 0, out, ld_out, lse, B, N, heads, scale, stream);
+}
+
+extern "C" int vdr_flash_attn_relpos_fwd(const void* qkv, int64_t ld_qkv, const float* rel_log2, void* out, int64_t ld_out, int B, int Sh,
+                                         int heads, float scale, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(rel_log2 != nullptr && aligned16(rel_log2), VDR_EINVAL, "vdr_flash_attn_relpos_fwd: rel table must be a 16-byte aligned device pointer");
+  VDR_CHECK_ARG(Sh > 0 && Sh % 4 == 0 && Sh <= 1020, VDR_EINVAL, "vdr_flash_attn_relpos_fwd: the token grid must be Sh x 64 with Sh a multiple of 4 (Sh = %d)", Sh);
+  return launch_flash_attn("vdr_flash_attn_relpos_fwd", qkv, ld_qkv, rel_log2, Sh + 64, out, ld_out, nullptr, B, Sh * 64, heads, scale, stream);
 }

@@ -44,42 +44,6 @@ window_rows_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld_src, __nv_b
   }
 }
 
-// ------------------------------------------------------------------------------------------------ rel-pos tables
-// rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = q_vec . Rh[qh - j + Sh - 1]        (j <  Sh)
-//                                         = q_vec . Rw[qw - (j-Sh) + Sw - 1]   (j >= Sh)
-// with q_vec the UNSCALED query of token q = qh*Sw + qw, head h (segment_anything add_decomposed_rel_pos).  One warp per
-// (bw, q, h): the query sits in shared memory, lane j owns outputs j, j+32, ...
-__global__ void __launch_bounds__(128)
-relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ Rh, const float* __restrict__ Rw,
-                    float* __restrict__ rel, int64_t total /* BW*N*heads */, int N, int Sh, int Sw, int heads) {
-  __shared__ __align__(16) float qs[4][64];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t wid = blockIdx.x * 4LL + wib;
-  if (wid >= total) return;                        // whole warps leave together; no block-level barrier below
-  const int h = static_cast<int>(wid % heads);
-  const int64_t tok = wid / heads;                 // bw*N + q
-  const int q = static_cast<int>(tok % N);
-  const int qh = q / Sw, qw = q - qh * Sw;
-  const float2 qv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(qkv + tok * ld + h * 64) + lane));
-  qs[wib][2 * lane] = qv.x;
-  qs[wib][2 * lane + 1] = qv.y;
-  __syncwarp();
-  const int R = Sh + Sw;
-  const int64_t bw = tok / N;
-  float* o = rel + ((bw * heads + h) * N + q) * R;
-  for (int j = lane; j < R; j += 32) {
-    const float* row = (j < Sh) ? Rh + (int64_t)(qh - j + Sh - 1) * 64 : Rw + (int64_t)(qw - (j - Sh) + Sw - 1) * 64;
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 64; c += 4) {
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(row + c));
-      const float4 qq = *reinterpret_cast<const float4*>(&qs[wib][c]);
-      acc = fmaf(qq.x, rv.x, acc); acc = fmaf(qq.y, rv.y, acc); acc = fmaf(qq.z, rv.z, acc); acc = fmaf(qq.w, rv.w, acc);
-    }
-    o[j] = acc;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ attention + bias
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -324,6 +288,76 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
   }
 }
 
+// ------------------------------------------------------------------------------------------------ rel-pos tables
+// rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = out_scale * q_vec . Rh[qh - j + Sh - 1]        (j <  Sh)
+//                                         = out_scale * q_vec . Rw[qw - (j-Sh) + Sw - 1]   (j >= Sh)
+// with q_vec the UNSCALED query of token q = qh*Sw + qw, head h (segment_anything add_decomposed_rel_pos).  Same MMA path as
+// the prologue of attn_relpos_kernel (queries x [rel_pos_h ; rel_pos_w], bf16 hi + lo parts), written to global memory: the
+// tcgen05 attention (vdr_flash_attn_relpos_fwd) reads its bias terms from this table.
+__global__ void __launch_bounds__(256, 2)
+relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv_bfloat16* __restrict__ rcat_hi,
+                    const __nv_bfloat16* __restrict__ rcat_lo, float* __restrict__ rel, int N, int heads, int Sh, int Sw, float out_scale) {
+  __shared__ __align__(16) __nv_bfloat16 Kb[2 * kRpTile];
+  const int qb = blockIdx.x, h = blockIdx.y, bw = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = qb * kRpBQ;
+  const __nv_bfloat16* base = qkv + (int64_t)bw * N * ld + h * 64;
+  const uint32_t kb_s = smem_u32(Kb);
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + ks * 16 + 2 * t);
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + ks * 16 + 2 * t);
+    qa[ks][0] = r0 < N ? __ldg(p0) : 0u;
+    qa[ks][1] = r1 < N ? __ldg(p1) : 0u;
+    qa[ks][2] = r0 < N ? __ldg(p0 + 4) : 0u;
+    qa[ks][3] = r1 < N ? __ldg(p1 + 4) : 0u;
+  }
+  const int R = Sh + Sw, RH = 2 * Sh - 1, RT = RH + 2 * Sw - 1;
+  float* o0 = rel + ((int64_t)(bw * heads + h) * N + r0) * R;
+  float* o1 = rel + ((int64_t)(bw * heads + h) * N + r1) * R;
+  const int qh0 = r0 / Sw, qh1 = r1 / Sw;
+  const int offh0 = qh0 + Sh - 1, offw0 = r0 - qh0 * Sw + Sw - 1;
+  const int offh1 = qh1 + Sh - 1, offw1 = r1 - qh1 * Sw + Sw - 1;
+  for (int c0 = 0; c0 < RT; c0 += 64) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256, row = idx >> 3, seg = idx & 7, j = c0 + row;
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+      if (j < RT) {
+        hi = __ldg(reinterpret_cast<const uint4*>(rcat_hi + (int64_t)j * 64 + seg * 8));
+        lo = __ldg(reinterpret_cast<const uint4*>(rcat_lo + (int64_t)j * 64 + seg * 8));
+      }
+      *reinterpret_cast<uint4*>(Kb + row * kRpPitch + seg * 8) = hi;
+      *reinterpret_cast<uint4*>(Kb + kRpTile + row * kRpPitch + seg * 8) = lo;
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    qk_tile_mma(acc, qa, kb_s + kRpTile * 2, lane);
+    qk_tile_mma(acc, qa, kb_s, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = c0 + nt * 8 + 2 * t + e;
+        if (j < RH) {
+          const int kh0 = offh0 - j, kh1 = offh1 - j;
+          if (r0 < N && kh0 >= 0 && kh0 < Sh) o0[kh0] = acc[nt][e] * out_scale;
+          if (r1 < N && kh1 >= 0 && kh1 < Sh) o1[kh1] = acc[nt][2 + e] * out_scale;
+        } else if (j < RT) {
+          const int kw0 = offw0 - (j - RH), kw1 = offw1 - (j - RH);
+          if (r0 < N && kw0 >= 0 && kw0 < Sw) o0[Sh + kw0] = acc[nt][e] * out_scale;
+          if (r1 < N && kw1 >= 0 && kw1 < Sw) o1[Sh + kw1] = acc[nt][2 + e] * out_scale;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ 3x3 im2col (neck)
 // A[(b,y,x), (ky*3+kx)*C + c] = X[(b, y+ky-1, x+kx-1), c], zero outside the map (Conv2d padding 1).  One 16-byte vector per thread.
 __global__ void __launch_bounds__(256)
@@ -370,18 +404,19 @@ extern "C" int vdr_window_rows(const void* src_bf16, int64_t ld_src, void* dst_b
   return VDR_OK;
 }
 
-extern "C" int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const float* rel_pos_h, const float* rel_pos_w, float* rel,
-                                 int BW, int Sh, int Sw, int heads, vdr_stream_t stream) {
+extern "C" int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, float* rel,
+                                 int BW, int Sh, int Sw, int heads, float out_scale, vdr_stream_t stream) {
   using namespace vdr;
-  VDR_CHECK_ARG(qkv_bf16 && rel_pos_h && rel_pos_w && rel, VDR_EINVAL, "vdr_relpos_tables: null pointer");
-  VDR_CHECK_ARG(BW > 0 && Sh > 0 && Sw > 0 && heads > 0, VDR_EINVAL, "vdr_relpos_tables: bad shape BW=%d Sh=%d Sw=%d heads=%d", BW, Sh, Sw, heads);
-  VDR_CHECK_ARG(ld_qkv >= 3LL * heads * 64 && ld_qkv % 8 == 0 && aligned16(qkv_bf16) && aligned16(rel_pos_h) && aligned16(rel_pos_w),
+  VDR_CHECK_ARG(qkv_bf16 && rcat_hi_bf16 && rcat_lo_bf16 && rel, VDR_EINVAL, "vdr_relpos_tables: null pointer");
+  VDR_CHECK_ARG(BW > 0 && BW <= 65535 && Sh > 0 && Sw > 0 && heads > 0 && heads <= 65535 && (int64_t)Sh * Sw < 65536, VDR_EINVAL,
+                "vdr_relpos_tables: bad shape BW=%d Sh=%d Sw=%d heads=%d", BW, Sh, Sw, heads);
+  VDR_CHECK_ARG(ld_qkv >= 3LL * heads * 64 && ld_qkv % 8 == 0 && aligned16(qkv_bf16) && aligned16(rcat_hi_bf16) && aligned16(rcat_lo_bf16),
                 VDR_EALIGN, "vdr_relpos_tables: qkv must be (rows, >= 3*heads*64) with ld %% 8 == 0; tables 16-byte aligned");
   const int N = Sh * Sw;
-  const int64_t total = (int64_t)BW * N * heads;
-  VDR_CHECK_ARG((total + 3) / 4 < 0x7fffffffLL, VDR_EINVAL, "vdr_relpos_tables: too many rows");
-  relpos_table_kernel<<<(unsigned)((total + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, rel_pos_h, rel_pos_w, rel, total, N, Sh, Sw, heads);
+  dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
+  relpos_table_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
+      static_cast<const __nv_bfloat16*>(rcat_lo_bf16), rel, N, heads, Sh, Sw, out_scale);
   count_launch();
   VDR_CHECK_LAUNCH("relpos_table_kernel");
   return VDR_OK;

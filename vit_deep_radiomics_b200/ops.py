@@ -610,25 +610,10 @@ def relpos_split(rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor):
     return hi.contiguous(), lo.contiguous()
 
 
-def relpos_tables(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor) -> torch.Tensor:
-    """(BW*heads*Sh*Sw, Sh+Sw) f32: rel_h[q, kh] | rel_w[q, kw] of add_decomposed_rel_pos, evaluated in fp32 (vdr_relpos_tables)."""
-    _req(qkv, torch.bfloat16, "qkv"), _req(rel_pos_h, torch.float32, "rel_pos_h"), _req(rel_pos_w, torch.float32, "rel_pos_w")
-    N, d = Sh * Sw, heads * 64
-    if qkv.shape != (BW * N, 3 * d) or qkv.stride(1) != 1:
-        raise ValueError(f"qkv must be ({BW * N}, {3 * d}), got {tuple(qkv.shape)}")
-    if rel_pos_h.shape != (2 * Sh - 1, 64) or rel_pos_w.shape != (2 * Sw - 1, 64) or not rel_pos_h.is_contiguous() or not rel_pos_w.is_contiguous():
-        raise ValueError("rel_pos_h / rel_pos_w must be contiguous (2*S-1, 64) tables")
-    rel = torch.empty((BW * heads * N, Sh + Sw), dtype=torch.float32, device=qkv.device)
-    _C.check(_C.lib().vdr_relpos_tables(qkv.data_ptr(), qkv.stride(0), rel_pos_h.data_ptr(), rel_pos_w.data_ptr(), rel.data_ptr(),
-                                        BW, Sh, Sw, heads, _stream()), "vdr_relpos_tables")
-    return rel
+LOG2E = 1.4426950408889634
 
 
-def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rcat_hi: torch.Tensor, rcat_lo: torch.Tensor,
-                scale: float | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Attention with SAM's decomposed relative-position bias over BW images/windows of Sh x Sw tokens, one launch.
-    qkv (BW*Sh*Sw, 3*heads*64) bf16; (rcat_hi, rcat_lo) = relpos_split(rel_pos_h (2*Sh-1, 64), rel_pos_w (2*Sw-1, 64))
-    -> out (BW*Sh*Sw, heads*64) bf16."""
+def _check_relpos_args(qkv, BW, Sh, Sw, heads, rcat_hi, rcat_lo):
     _req(qkv, torch.bfloat16, "qkv"), _req(rcat_hi, torch.bfloat16, "rcat_hi"), _req(rcat_lo, torch.bfloat16, "rcat_lo")
     N, d = Sh * Sw, heads * 64
     if qkv.shape != (BW * N, 3 * d) or qkv.stride(1) != 1:
@@ -636,10 +621,49 @@ def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rcat_h
     RT = 2 * Sh - 1 + 2 * Sw - 1
     if rcat_hi.shape != (RT, 64) or rcat_lo.shape != (RT, 64) or not rcat_hi.is_contiguous() or not rcat_lo.is_contiguous():
         raise ValueError(f"rcat_hi / rcat_lo must be contiguous ({RT}, 64) tables (relpos_split; interpolate first when the extent differs)")
+    return N, d
+
+
+def relpos_tables(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rcat_hi: torch.Tensor, rcat_lo: torch.Tensor,
+                  out_scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(BW*heads*Sh*Sw, Sh+Sw) f32: out_scale * [rel_h[q, kh] | rel_w[q, kw]] of add_decomposed_rel_pos (vdr_relpos_tables)."""
+    N, d = _check_relpos_args(qkv, BW, Sh, Sw, heads, rcat_hi, rcat_lo)
+    rows = BW * heads * N
+    if out is None:
+        out = torch.empty((rows, Sh + Sw), dtype=torch.float32, device=qkv.device)
+    rel = _req(out, torch.float32, "out")
+    if rel.numel() < rows * (Sh + Sw) or not rel.is_contiguous():
+        raise ValueError("rel scratch too small")
+    with _Prof("attn", 4.0 * rows * (2 * Sh - 1 + 2 * Sw - 1) * 64, f"relpos tables BW{BW} {Sh}x{Sw} h{heads}"):
+        _C.check(_C.lib().vdr_relpos_tables(qkv.data_ptr(), qkv.stride(0), rcat_hi.data_ptr(), rcat_lo.data_ptr(), rel.data_ptr(),
+                                            BW, Sh, Sw, heads, float(out_scale), _stream()), "vdr_relpos_tables")
+    return rel
+
+
+def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rcat_hi: torch.Tensor, rcat_lo: torch.Tensor,
+                scale: float | None = None, out: torch.Tensor | None = None, rel: torch.Tensor | None = None,
+                kernel: str = "auto") -> torch.Tensor:
+    """Attention with SAM's decomposed relative-position bias over BW images/windows of Sh x Sw tokens.
+    qkv (BW*Sh*Sw, 3*heads*64) bf16; (rcat_hi, rcat_lo) = relpos_split(rel_pos_h (2*Sh-1, 64), rel_pos_w (2*Sw-1, 64))
+    -> out (BW*Sh*Sw, heads*64) bf16.
+    kernel: "tcgen05" = bias table (vdr_relpos_tables, log2 domain; `rel` = optional f32 scratch of BW*heads*N*(Sh+Sw)) +
+    the tcgen05 flash kernel with bias (token grids of Sh x 64, Sh % 4 == 0: the global-attention blocks); "mma" = the one-launch
+    mma.sync kernel that builds the bias on chip (any extent: the 14 x 14 windows); "auto" picks tcgen05 where it applies."""
+    N, d = _check_relpos_args(qkv, BW, Sh, Sw, heads, rcat_hi, rcat_lo)
     if scale is None:
         scale = 1.0 / math.sqrt(64)
     if out is None:
         out = torch.empty((BW * N, d), dtype=torch.bfloat16, device=qkv.device)
+    if kernel == "auto":
+        kernel = "tcgen05" if (Sw == 64 and Sh % 4 == 0) else "mma"
+    if kernel == "tcgen05":
+        table = relpos_tables(qkv, BW, Sh, Sw, heads, rcat_hi, rcat_lo, out_scale=LOG2E, out=rel)
+        with _Prof("attn", 4.0 * BW * heads * N * N * 64, f"attn+relpos tcgen05 BW{BW} N{N} h{heads}"):
+            _C.check(_C.lib().vdr_flash_attn_relpos_fwd(qkv.data_ptr(), qkv.stride(0), table.data_ptr(), out.data_ptr(), out.stride(0),
+                                                        BW, Sh, heads, float(scale), _stream()), "vdr_flash_attn_relpos_fwd")
+        return out
+    if kernel != "mma":
+        raise ValueError(f"unknown kernel {kernel!r}")
     with _Prof("attn", 4.0 * BW * heads * N * N * 64 + 2.0 * BW * heads * N * (Sh + Sw) * 64, f"attn+relpos BW{BW} N{N} h{heads}"):
         _C.check(_C.lib().vdr_attn_relpos_fwd(qkv.data_ptr(), qkv.stride(0), rcat_hi.data_ptr(), rcat_lo.data_ptr(), out.data_ptr(),
                                               out.stride(0), BW, Sh, Sw, heads, float(scale), _stream()), "vdr_attn_relpos_fwd")

@@ -156,8 +156,13 @@ class SamImageEncoder:
                       N0=torch.empty(B * N, oc, dtype=bf, device=dev), N1=torch.empty(B * N, oc, dtype=bf, device=dev),
                       NA=torch.empty(B * N, 9 * oc, dtype=bf, device=dev),
                       OUT=torch.empty(B * N, oc, dtype=torch.float32, device=dev))
+            if gw == 64 and gh % 4 == 0 and self.global_attn_kernel != "mma":       # bias table of the tcgen05 global attention
+                ws["REL"] = torch.empty(B * cfg["heads"] * N * (gh + gw), dtype=torch.float32, device=dev)
             self._ws = {B: ws}
         return ws
+
+    #: "auto" (tcgen05 flash kernel with bias where the token grid is Sh x 64, else mma.sync) | "mma" (A/B timing, parity tests)
+    global_attn_kernel = "auto"
 
     # -- forward -----------------------------------------------------------------------------
     def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
@@ -201,7 +206,7 @@ class SamImageEncoder:
             else:
                 qkv = ws["QKV"][:B * N]
                 ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=qkv)
-                ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_hi"], blk["rel_lo"], scale, out=Y)
+                ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_hi"], blk["rel_lo"], scale, out=Y, rel=ws.get("REL"), kernel=self.global_attn_kernel)
             ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X)
             ops.layernorm(X, blk["n2w"], blk["n2b"], 1e-6, out=Y)
             ops.gemm(Y, blk["fc1_w"], blk["fc1_b"], epilogue="gelu", out=Hb)
