@@ -281,6 +281,7 @@ def run_ours(args):
 
     if rank != 0:
         return
+    medsam = medsam_side_measurement(dev) if args.medsam else None
     peaks = measured_peaks()
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
     traffic = None
@@ -313,7 +314,30 @@ def run_ours(args):
                      "hbm_kernels": {"peak_gbs": peaks["hbm"], "mask_gather_c2": gather_c2, "mask_gather_dense": gather_dense,
                                      "mask_gather_dense_frac": gather_dense["gbs"] / peaks["hbm"] if peaks["hbm"] else None}},
         "cpu_baseline": cb,
-        "clocks": clocks}))
+        "clocks": clocks,
+        "n1_medsam": medsam}))
+
+
+def medsam_side_measurement(dev, B=8, steps=3):
+    """Not part of `value`: the reference's own default backbone (load_model('medsam'): SAM ViT-B image encoder, 1024 x 1024
+    inputs, (64, 64, 256) descriptors) through the same libvdr kernels, B resident gray slices per pass."""
+    from vit_deep_radiomics_b200 import _C, tfds_dense_descriptor as tdd
+    model = tdd.load_model("medsam", device=dev, seed=1)
+    x = torch.rand(B, 1024, 1024, device=dev)
+    strides = (x.stride(0), 0, x.stride(1), x.stride(2))
+    for _ in range(3):
+        model.forward_tokens(x, strides, B)
+    torch.cuda.synchronize()
+    n0 = _C.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.forward_tokens(x, strides, B)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "MedSAM (SAM ViT-B) encoder slices/s, 1024x1024 gray slices resident, 1 GPU", "value": B / ms * 1e3, "batch": B,
+            "ms_per_batch": ms, "model_tflops": model.flops_per_slice() * B / ms / 1e9, "gpu_launches_per_batch": (_C.launch_count() - n0) // steps}
 
 
 def main():
@@ -324,6 +348,7 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=str, default="C2")
     ap.add_argument("--sample-slices", type=int, default=8, dest="sample_slices")
+    ap.add_argument("--no-medsam", action="store_false", dest="medsam", help="skip the MedSAM side measurement (key n1_medsam)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

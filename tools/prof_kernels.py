@@ -63,11 +63,15 @@ if which in ("gather", "all"):
         torch.cuda.synchronize()
 print("done")
 if which in ("sam",):
-    # MedSAM attention with rel-pos bias: 4 images of 64 x 64 tokens (global) and 100 windows of 14 x 14, 12 heads
+    # MedSAM attention with rel-pos bias, 12 heads: 4 images of 64 x 64 tokens (bias table kernel + tcgen05 flash kernel with
+    # bias) and 100 windows of 14 x 14 (mma.sync kernel).  One warm round (3 launches), then the round ncu captures:
+    #   ncu -k regex:'relpos|flash_attn' -s 3 -c 3
+    cases = []
     for (BW, S) in [(4, 64), (100, 14)]:
         qkv = torch.randn(BW * S * S, 3 * d, device=dev).bfloat16()
         hi, lo = ops.relpos_split(torch.randn(2 * S - 1, 64, device=dev) * 0.1, torch.randn(2 * S - 1, 64, device=dev) * 0.1)
-        out = torch.empty(BW * S * S, d, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):   # launches 0-2 global, 3-5 windowed: ncu takes -s 2 -c 2 (one of each... the last global, the first windowed)
+        cases.append((qkv, BW, S, hi, lo, torch.empty(BW * S * S, d, device=dev, dtype=torch.bfloat16)))
+    for _ in range(2):
+        for (qkv, BW, S, hi, lo, out) in cases:
             ops.attn_relpos(qkv, BW, S, S, 12, hi, lo, out=out)
         torch.cuda.synchronize()

@@ -71,12 +71,14 @@ constexpr int kRpTile = kRpBK * kRpPitch;               // elements of one K / V
 // acc[nt] (16 query rows x 8 tile rows) += Q (A fragments, 16 x 64) * T^T for the 64 rows of a K-major bf16 tile in smem.
 // One ldmatrix.x4 feeds two n-tiles of one k-step, so consecutive MMAs never accumulate into the same registers
 // (a dependent HMMA chain stalls for the full pipe latency).
-__device__ __forceinline__ void qk_tile_mma(float (&acc)[8][4], const uint32_t (&qa)[4][4], uint32_t tile_smem, int lane) {
+// `rows` (warp-uniform) = tile rows that hold data: 16-row groups beyond it are skipped (their accumulators stay 0).
+__device__ __forceinline__ void qk_tile_mma(float (&acc)[8][4], const uint32_t (&qa)[4][4], uint32_t tile_smem, int lane, int rows = kRpBK) {
   const uint32_t lane_off = (((lane & 7) + (lane >> 4) * 8) * kRpPitch + ((lane >> 3) & 1) * 8) * 2;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
     for (int ntp = 0; ntp < 4; ++ntp) {
+      if (ntp * 16 >= rows) continue;
       uint32_t b[4];     // b0/b1 of n-tile 2*ntp, b0/b1 of n-tile 2*ntp + 1, k-step ks
       ldmatrix_x4(b, tile_smem + lane_off + (ntp * 16 * kRpPitch + ks * 16) * 2);
       mma_bf16_16816(acc[2 * ntp], qa[ks], b[0], b[1]);
@@ -121,6 +123,7 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
     qa[ks][2] = r0 < N ? __ldg(p0 + 4) : 0u;
     qa[ks][3] = r1 < N ? __ldg(p1 + 4) : 0u;
   }
+  const bool warp_active = q0 + warp * 16 < N;      // a warp whose 16 query rows lie beyond N only helps with the loads and barriers
   float* rel0 = relS + rl0 * RP;
   float* rel1 = relS + rl1 * RP;
   const int WO = (Sh + 1) & ~1;                // rel_w terms start at an even column: float2 loads in the row-tile variant
@@ -145,11 +148,12 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
         *reinterpret_cast<uint4*>(Kb + kRpTile + row * kRpPitch + seg * 8) = lo;
       }
       __syncthreads();
+      if (!warp_active) continue;
       float acc[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-      qk_tile_mma(acc, qa, kb_s + kRpTile * 2, lane);      // low parts first, then the high parts on top
-      qk_tile_mma(acc, qa, kb_s, lane);
+      qk_tile_mma(acc, qa, kb_s + kRpTile * 2, lane, RT - c0);      // low parts first, then the high parts on top
+      qk_tile_mma(acc, qa, kb_s, lane, RT - c0);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -199,10 +203,12 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
       cp_async_wait<0>();
     }
     __syncthreads();
+    if (warp_active) {
+    const int rem = kRowTiles ? kRpBK : N - k0;      // keys in this tile (>= 64 except on a ragged last tile)
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
-    qk_tile_mma(s, qa, kb_s + buf * kRpTile * 2, lane);
+    qk_tile_mma(s, qa, kb_s + buf * kRpTile * 2, lane, rem);
     // scale + bias (+ key mask on a ragged last tile); row maxima
     float mx0 = -INFINITY, mx1 = -INFINITY;
     if (kRowTiles) {
@@ -262,6 +268,7 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
     const uint32_t v_lane = vb_s + (buf * kRpTile + ((lane & 7) + ((lane >> 3) & 1) * 8) * kRpPitch + (lane >> 4) * 8) * 2;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      if (kk * 16 >= rem) continue;                  // P is zero beyond the last key
       uint32_t pa[4];
       pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
       pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
@@ -274,6 +281,7 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
         mma_bf16_16816(o[2 * ntp], pa, b[0], b[1]);
         mma_bf16_16816(o[2 * ntp + 1], pa, b[2], b[3]);
       }
+    }
     }
     __syncthreads();      // everyone is done with this tile's buffers before the next iteration refills them
   }
