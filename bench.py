@@ -289,7 +289,7 @@ def run_ours(args):
     if os.path.isfile(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    cb, _ = cpu_baseline(args.config, args.sample_slices)
+    cb, _ = cpu_baseline(args.config, args.cpu_sample_slices)     # ~10 s of host work on rank 0
     c = synth.CONFIGS[args.config]
     flops_step = model.flops_per_slice() * S
     print(json.dumps({
@@ -348,6 +348,8 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=str, default="C2")
     ap.add_argument("--sample-slices", type=int, default=8, dest="sample_slices")
+    ap.add_argument("--cpu-sample-slices", type=int, default=32, dest="cpu_sample_slices",
+                    help="slices of the workload the cpu_baseline leg of our arm runs on the host cores (~0.3 s per slice)")
     ap.add_argument("--no-medsam", action="store_false", dest="medsam", help="skip the MedSAM side measurement (key n1_medsam)")
     args = ap.parse_args()
     if args.impl == "reference":

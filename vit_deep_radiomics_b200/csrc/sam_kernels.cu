@@ -296,6 +296,181 @@ attn_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv
   }
 }
 
+// ------------------------------------------------------------------------------------------------ resident-key variant
+// Small extents (N <= 208 tokens, 2*Sh-1 + 2*Sw-1 <= 64 table rows: SAM's 14 x 14 windows): two CTAs per (window, head), 7 warps
+// x 16 query rows each (rows 0..111 and 112..207), ALL keys / values and both table parts resident in shared memory after one
+// cp.async wave -- a single CTA barrier instead of two per key tile, no query rows beyond the 16-row granule, keys processed as
+// a 112- and a 96-wide tile (7 + 6 MMA k-steps) instead of four 64-wide ones.  Two CTAs fit an SM (registers and 96 KB of
+// shared memory each), so one CTA's load wave overlaps the other's arithmetic.
+constexpr int kWinRows = 208, kWinQ = 112, kWinWarps = 7, kWinThreads = kWinWarps * 32;
+
+template <int NT>   // 8-key n-tiles in this key tile (even)
+__device__ __forceinline__ void win_key_tile(float (&o)[8][4], float& m0, float& m1, float& l0, float& l1, const uint32_t (&qa)[4][4],
+                                             uint32_t k_s, uint32_t v_s, int k0, int N, const float* rel0, const float* rel1, int WO, int Sw,
+                                             uint32_t magic_sw, float scale_log2e, int lane) {
+  const int t = lane & 3;
+  float s[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+  const uint32_t k_lane = k_s + ((k0 + (lane & 7) + (lane >> 4) * 8) * kRpPitch + ((lane >> 3) & 1) * 8) * 2;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int ntp = 0; ntp < NT / 2; ++ntp) {
+      uint32_t b[4];
+      ldmatrix_x4(b, k_lane + (ntp * 16 * kRpPitch + ks * 16) * 2);
+      mma_bf16_16816(s[2 * ntp], qa[ks], b[0], b[1]);
+      mma_bf16_16816(s[2 * ntp + 1], qa[ks], b[2], b[3]);
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = k0 + nt * 8 + 2 * t + e;
+      if (key < N) {
+        const int kh = Sw == 1 ? key : (int)__umulhi((uint32_t)key, magic_sw);
+        const int kw = key - kh * Sw;
+        s[nt][e] = fmaf(s[nt][e], scale_log2e, rel0[kh] + rel0[WO + kw]);
+        s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2e, rel1[kh] + rel1[WO + kw]);
+      } else {
+        s[nt][e] = -INFINITY;
+        s[nt][2 + e] = -INFINITY;
+      }
+      mx0 = fmaxf(mx0, s[nt][e]);
+      mx1 = fmaxf(mx1, s[nt][2 + e]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);      // finite: key k0 < N is valid in every tile the caller passes
+  const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);
+  m0 = mn0; m1 = mn1;
+  float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = ex2_approx(s[nt][0] - mn0); s[nt][1] = ex2_approx(s[nt][1] - mn0);
+    s[nt][2] = ex2_approx(s[nt][2] - mn1); s[nt][3] = ex2_approx(s[nt][3] - mn1);
+    ps0 += s[nt][0] + s[nt][1];
+    ps1 += s[nt][2] + s[nt][3];
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+  l0 = l0 * c0 + ps0;
+  l1 = l1 * c1 + ps1;
+  const uint32_t v_lane = v_s + ((k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kRpPitch + (lane >> 4) * 8) * 2;
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int ntp = 0; ntp < 4; ++ntp) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, v_lane + (kk * 16 * kRpPitch + ntp * 16) * 2);
+      mma_bf16_16816(o[2 * ntp], pa, b[0], b[1]);
+      mma_bf16_16816(o[2 * ntp + 1], pa, b[2], b[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWinThreads, 2)
+attn_relpos_win_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv_bfloat16* __restrict__ rcat_hi,
+                       const __nv_bfloat16* __restrict__ rcat_lo, __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int heads,
+                       int Sh, int Sw, int RP, uint32_t magic_sw, float scale_log2e) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [208 keys][72]
+  __nv_bfloat16* Vs = Ks + kWinRows * kRpPitch;                         // [208 keys][72]
+  __nv_bfloat16* Rs = Vs + kWinRows * kRpPitch;                         // [2][64 table rows][72]: hi, lo
+  float* relS = reinterpret_cast<float*>(Rs + 2 * kRpTile);            // [112 query rows][RP], times log2(e)
+  const int h = blockIdx.x, bw = blockIdx.y, q0 = blockIdx.z * kWinQ;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int d = heads * 64;
+  const __nv_bfloat16* base = qkv + (int64_t)bw * N * ld + h * 64;
+  const uint32_t ks_s = smem_u32(Ks), vs_s = smem_u32(Vs), rs_s = smem_u32(Rs);
+  const int RH = 2 * Sh - 1, RT = RH + 2 * Sw - 1;
+  // one cp.async wave: K, V (rows beyond N zero-filled) and the two table parts (rows beyond RT zero-filled)
+  for (int idx = tid; idx < kWinRows * 8; idx += kWinThreads) {
+    const int row = idx >> 3, seg = idx & 7;
+    const int bytes = row < N ? 16 : 0;
+    const __nv_bfloat16* src = base + (int64_t)(row < N ? row : N - 1) * ld + seg * 8;
+    const uint32_t off = (row * kRpPitch + seg * 8) * 2;
+    cp_async16(ks_s + off, src + d, bytes);
+    cp_async16(vs_s + off, src + 2 * d, bytes);
+  }
+  for (int idx = tid; idx < 64 * 8; idx += kWinThreads) {
+    const int row = idx >> 3, seg = idx & 7;
+    const int bytes = row < RT ? 16 : 0;
+    const int64_t soff = (int64_t)(row < RT ? row : RT - 1) * 64 + seg * 8;
+    const uint32_t off = (row * kRpPitch + seg * 8) * 2;
+    cp_async16(rs_s + off, rcat_hi + soff, bytes);
+    cp_async16(rs_s + kRpTile * 2 + off, rcat_lo + soff, bytes);
+  }
+  cp_async_commit();
+  const int rl0 = q0 + warp * 16 + g, rl1 = rl0 + 8;     // this thread's query rows (tokens of the window)
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (int64_t)rl0 * ld + ks * 16 + 2 * t);
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (int64_t)rl1 * ld + ks * 16 + 2 * t);
+    qa[ks][0] = rl0 < N ? __ldg(p0) : 0u;
+    qa[ks][1] = rl1 < N ? __ldg(p1) : 0u;
+    qa[ks][2] = rl0 < N ? __ldg(p0 + 4) : 0u;
+    qa[ks][3] = rl1 < N ? __ldg(p1 + 4) : 0u;
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                       // the only CTA barrier
+  if (q0 + warp * 16 >= N) return;
+  float* rel0 = relS + (warp * 16 + g) * RP;
+  float* rel1 = rel0 + 8 * RP;
+  const int WO = (Sh + 1) & ~1;
+  {
+    const int qh0 = rl0 / Sw, qh1 = rl1 / Sw;
+    const int offh0 = qh0 + Sh - 1, offw0 = rl0 - qh0 * Sw + Sw - 1;
+    const int offh1 = qh1 + Sh - 1, offw1 = rl1 - qh1 * Sw + Sw - 1;
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    qk_tile_mma(acc, qa, rs_s + kRpTile * 2, lane, RT);
+    qk_tile_mma(acc, qa, rs_s, lane, RT);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + 2 * t + e;
+        if (j < RH) {
+          const int kh0 = offh0 - j, kh1 = offh1 - j;
+          if (rl0 < N && kh0 >= 0 && kh0 < Sh) rel0[kh0] = acc[nt][e] * 1.4426950408889634f;
+          if (rl1 < N && kh1 >= 0 && kh1 < Sh) rel1[kh1] = acc[nt][2 + e] * 1.4426950408889634f;
+        } else if (j < RT) {
+          const int kw0 = offw0 - (j - RH), kw1 = offw1 - (j - RH);
+          if (rl0 < N && kw0 >= 0 && kw0 < Sw) rel0[WO + kw0] = acc[nt][e] * 1.4426950408889634f;
+          if (rl1 < N && kw1 >= 0 && kw1 < Sw) rel1[WO + kw1] = acc[nt][2 + e] * 1.4426950408889634f;
+        }
+      }
+    }
+    __syncwarp();                                        // a warp reads only the bias rows it wrote itself
+  }
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  win_key_tile<14>(o, m0, m1, l0, l1, qa, ks_s, vs_s, 0, N, rel0, rel1, WO, Sw, magic_sw, scale_log2e, lane);
+  if (N > 112) win_key_tile<12>(o, m0, m1, l0, l1, qa, ks_s, vs_s, 112, N, rel0, rel1, WO, Sw, magic_sw, scale_log2e, lane);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __nv_bfloat16* ob = out + (int64_t)bw * N * ld_out + h * 64;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (rl0 < N) *reinterpret_cast<uint32_t*>(ob + (int64_t)rl0 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0] * i0, o[nt][1] * i0);
+    if (rl1 < N) *reinterpret_cast<uint32_t*>(ob + (int64_t)rl1 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ rel-pos tables
 // rel[((bw*heads + h)*N + q)*(Sh+Sw) + j] = out_scale * q_vec . Rh[qh - j + Sh - 1]        (j <  Sh)
 //                                         = out_scale * q_vec . Rw[qw - (j-Sh) + Sw - 1]   (j >= Sh)
@@ -444,6 +619,24 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const v
   const int RP = rp0 + (8 - rp0 % 32 + 32) % 32;                 // row pitch of the bias tile: RP % 32 == 8 spreads a warp's rows over the banks
   const size_t smem = 4 * (size_t)kRpTile * sizeof(__nv_bfloat16) + (size_t)kRpBQ * RP * sizeof(float);
   VDR_CHECK_ARG(smem <= 200 * 1024, VDR_EINVAL, "vdr_attn_relpos_fwd: Sh + Sw = %d too large for the shared-memory bias tile", Sh + Sw);
+  const uint32_t magic = Sw > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)Sw - 1) / (uint64_t)Sw) : 0u;   // key / Sw = umulhi(key, magic), key < 2^16
+  if (N <= kWinRows && 2 * Sh - 1 + 2 * Sw - 1 <= 64) {
+    // small extents (the 14 x 14 windows): two CTAs per (window, head) with everything resident
+    const size_t smem_w = (2 * (size_t)kWinRows * kRpPitch + 2 * (size_t)kRpTile) * sizeof(__nv_bfloat16) + (size_t)kWinQ * RP * sizeof(float);
+    static bool configured_w = false;
+    if (!configured_w) {
+      cudaError_t e = cudaFuncSetAttribute(attn_relpos_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_win_kernel)");
+      configured_w = true;
+    }
+    attn_relpos_win_kernel<<<dim3(heads, BW, N > kWinQ ? 2 : 1), kWinThreads, smem_w, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
+        static_cast<const __nv_bfloat16*>(rcat_lo_bf16), static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, Sh, Sw, RP, magic,
+        scale * 1.4426950408889634f);
+    count_launch();
+    VDR_CHECK_LAUNCH("attn_relpos_win_kernel");
+    return VDR_OK;
+  }
   const bool row_tiles = Sw == 64 && N % 64 == 0;
   auto kernel = row_tiles ? attn_relpos_kernel<true> : attn_relpos_kernel<false>;
   static size_t configured[2] = {0, 0};
@@ -452,7 +645,6 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const v
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_kernel)");
     configured[row_tiles] = smem;
   }
-  const uint32_t magic = Sw > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)Sw - 1) / (uint64_t)Sw) : 0u;   // key / Sw = umulhi(key, magic), key < 2^16
   dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
   kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
