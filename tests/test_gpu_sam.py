@@ -154,6 +154,24 @@ def test_sam_encoder_vs_oracle(cuda, hw, B):
     _check_descriptors(got, want)
 
 
+def test_sam_encoder_layernorm_kernel_path_and_mma_global_attention(cuda):
+    """The A/B switches: LayerNorm kernels instead of the folded GEMM epilogues, mma.sync instead of tcgen05 for a 64-wide grid."""
+    from oracle import sam_fp32
+    from vit_deep_radiomics_b200 import sam_encoder
+    hw = (128, 1024)                                           # 8 x 64 tokens: the global blocks qualify for the tcgen05 kernel
+    x = torch.rand(1, 3, *hw, generator=torch.Generator().manual_seed(12))
+    outs = []
+    for fold, kern in [(True, "auto"), (False, "mma")]:
+        model = sam_encoder.SamImageEncoder("sam_tiny", img_hw=hw, device=cuda, seed=29)
+        model.fold_layernorm, model.global_attn_kernel = fold, kern
+        model.prepare()
+        outs.append(model.dense_descriptors(x.to(cuda)).cpu().numpy())
+    with torch.no_grad():
+        want = sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, x).numpy()
+    for got in outs:
+        _check_descriptors(got, want)
+
+
 def test_sam_encoder_against_committed_golden(cuda, golden_dir):
     """tests/golden/sam_tiny_hf.npz = transformers' SamVisionEncoder on the same seeded weights / input."""
     from vit_deep_radiomics_b200 import sam_encoder

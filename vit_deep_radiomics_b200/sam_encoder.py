@@ -138,6 +138,14 @@ class SamImageEncoder:
                 fc1_w=bf(b + "mlp.lin1.weight"), fc1_b=f32(b + "mlp.lin1.bias"),
                 fc2_w=bf(b + "mlp.lin2.weight"), fc2_b=f32(b + "mlp.lin2.bias"),
                 window=0 if i in cfg["global_attn"] else ws))
+        if self.fold_layernorm:
+            # norm2 -> lin1 everywhere and norm1 -> qkv in the global blocks are folded into the GEMMs (vdr_fold_layernorm): the
+            # producing residual GEMM leaves the row statistics, the consumer normalises in its epilogue.
+            # The windowed blocks keep the norm1 kernel: their padding is defined on the normalised tokens.
+            for blk in self.w["blocks"]:
+                blk["fc1_wf"], blk["fc1_bf"], blk["fc1_cs"] = ops.fold_layernorm(blk["fc1_w"], blk["fc1_b"], blk["n2w"], blk["n2b"])
+                if not blk["window"]:
+                    blk["qkv_wf"], blk["qkv_bf"], blk["qkv_cs"] = ops.fold_layernorm(blk["qkv_w"], blk["qkv_b"], blk["n1w"], blk["n1b"])
 
     def _buffers(self, B: int) -> dict:
         ws = self._ws.get(B)
@@ -160,6 +168,9 @@ class SamImageEncoder:
                 ws["REL"] = torch.empty(B * cfg["heads"] * N * (gh + gw), dtype=torch.float32, device=dev)
             self._ws = {B: ws}
         return ws
+
+    #: fold norm2 (all blocks) / norm1 (global blocks) into the GEMMs that consume them (set False before prepare() for A/B)
+    fold_layernorm = True
 
     #: "auto" (tcgen05 flash kernel with bias where the token grid is Sh x 64, else mma.sync) | "mma" (A/B timing, parity tests)
     global_attn_kernel = "auto"
@@ -195,9 +206,17 @@ class SamImageEncoder:
         scale = 1.0 / math.sqrt(64)
         # patch embedding (Conv2d 16x16 stride 16) + absolute position embedding in the GEMM epilogue
         ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=X, res_mod=(N, 0))
-        for blk in w["blocks"]:
-            ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
+        fold = "fc1_wf" in w["blocks"][0]
+        if fold and "ST" not in ws:
+            ws["ST"] = torch.empty(d // 64, B * N, 2, dtype=torch.float32, device=self.device)
+        ST = ws.get("ST")
+        stats = None                      # row statistics of X as the last residual GEMM left them (None: not available)
+        if fold and not w["blocks"][0]["window"]:
+            stats = ops.row_stats(X, out=ST[:1])
+        nblk = len(w["blocks"])
+        for i, blk in enumerate(w["blocks"]):
             if blk["window"]:
+                ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
                 ops.window_rows(Y, B, gh, gw, win, True, out=ws["YW"])
                 qkv = ws["QKV"][:B * NW]
                 ops.gemm(ws["YW"], blk["qkv_w"], blk["qkv_b"], out=qkv)
@@ -205,12 +224,23 @@ class SamImageEncoder:
                 ops.window_rows(ws["OW"], B, gh, gw, win, False, out=Y)
             else:
                 qkv = ws["QKV"][:B * N]
-                ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=qkv)
+                if fold:
+                    ops.gemm(X, blk["qkv_wf"], blk["qkv_bf"], out=qkv, ln_stats=stats, ln_colsum=blk["qkv_cs"])
+                else:
+                    ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
+                    ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=qkv)
                 ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_hi"], blk["rel_lo"], scale, out=Y, rel=ws.get("REL"), kernel=self.global_attn_kernel)
-            ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X)
-            ops.layernorm(X, blk["n2w"], blk["n2b"], 1e-6, out=Y)
-            ops.gemm(Y, blk["fc1_w"], blk["fc1_b"], epilogue="gelu", out=Hb)
-            ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X)
+            if fold:
+                next_global = i + 1 < nblk and not w["blocks"][i + 1]["window"]
+                ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X, stats_out=ST)
+                ops.gemm(X, blk["fc1_wf"], blk["fc1_bf"], epilogue="gelu", out=Hb, ln_stats=ST, ln_colsum=blk["fc1_cs"])
+                ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X, stats_out=ST if next_global else None)
+                stats = ST if next_global else None
+            else:
+                ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X)
+                ops.layernorm(X, blk["n2w"], blk["n2b"], 1e-6, out=Y)
+                ops.gemm(Y, blk["fc1_w"], blk["fc1_b"], epilogue="gelu", out=Hb)
+                ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X)
         # neck: 1x1 conv (a GEMM), LayerNorm2d = LayerNorm over the channels of each token, 3x3 conv as im2col + GEMM, LayerNorm2d
         ops.gemm(X, w["neck0"], None, out=ws["N0"])
         ops.layernorm(ws["N0"], w["neck1_w"], w["neck1_b"], 1e-6, out=ws["N1"])
