@@ -234,6 +234,45 @@ def test_medsam_point_cloud_through_the_gather(cuda):
     assert np.abs(got - want).max() < ABS_TOL and cos.min() > COS
 
 
+def test_medsam_descriptors_feed_the_shipped_classifier_config(cuda):
+    """The reference's default pipeline end to end: SAM-encoder descriptors (256 channels, conf/parameters_models.yaml
+    feature_dim: 256) -> tumour-mask gather -> TransformerNoduleClassifier built by build_model from the shipped YAML ->
+    focal loss -> backward.  Logits / CLS / loss on the extracted tokens against the fp32 oracle classifier on the same tokens."""
+    import os
+    from oracle import classifier_fp32 as C
+    from vit_deep_radiomics_b200 import config_manager, tfds_dense_descriptor as tdd, train_models as tm
+    rng = np.random.default_rng(4)
+    H = W = 128
+    S = 4
+    img = rng.random((H, W, S), dtype=np.float32)
+    yy, xx = np.mgrid[:H, :W]
+    mask = np.stack([((yy - 60) ** 2 + (xx - 66) ** 2) < (12 + 2 * s) ** 2 for s in range(S)], axis=-1)
+    model = tdd.load_model("sam_small", img_hw=(256, 256), device=cuda, seed=31)
+    assert model.feature_dim == 256
+    out = tdd.extract_point_cloud(model, img, mask, np.array([0.8, 0.8, 0.8]), to_host=False)
+    n = int(out["count"].item())
+    assert n > 0
+    tokens = out["tokens"][:n]
+    cfg = config_manager.load_conf(project_dir=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    torch.manual_seed(2)
+    clf = tm.build_model(cfg, "transformer", "ct").to(cuda)
+    mcfg = cfg["models"]["transformer"]
+    assert mcfg["feature_dim"] == 256
+    heads, layers = mcfg["ct"]["num_heads"], mcfg["ct"]["num_layers"]
+    y = torch.tensor([0.0, 1.0], device=cuda)
+    logits, cls = clf(tokens.unsqueeze(0))
+    loss = tm.FocalLoss(alpha=torch.tensor([0.25, 0.75], device=cuda), gamma=2)(torch.squeeze(logits), y)
+    loss.backward()
+    sd = {k: v.detach().cpu().clone() for k, v in clf.state_dict().items()}
+    lg, cl = C.classifier_forward(sd, tokens.detach().cpu()[None], heads, layers)
+    ref_loss = C.focal_loss(lg[0], y.cpu(), 2.0, torch.tensor([0.25, 0.75]))
+    assert torch.allclose(logits.detach().cpu().reshape(-1), lg.reshape(-1), atol=0.05, rtol=0.05)
+    assert F.cosine_similarity(cls.detach().cpu().reshape(1, -1), cl.reshape(1, -1)).item() > 0.999
+    assert abs(float(loss) - float(ref_loss)) < 0.05 * max(1.0, abs(float(ref_loss)))
+    for k, p in clf.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
 @pytest.mark.parametrize("hw,B", [((56, 84), 2), ((896, 896), 1)])
 def test_dinov2_patch_embed_mode(cuda, hw, B):
     """The reference's 'dinov2' branch only calls model.patch_embed (:128-133)."""

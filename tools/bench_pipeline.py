@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--patients", type=int, default=8, help="patients per rank in the timed region")
     ap.add_argument("--config", type=str, default="C2")
     ap.add_argument("--cpu-slices", type=int, default=8, dest="cpu_slices")
+    ap.add_argument("--model", type=str, default=None, help="backbone override, e.g. medsam: the reference's default pipeline "
+                    "(SAM ViT-B encoder on the crop window resized to 1024^2 -> 256-wide descriptors -> the shipped classifier config)")
     args = ap.parse_args()
     rank, world = init_distributed("nccl")
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -37,10 +39,12 @@ def main():
     dev = torch.device(f"cuda:{local}")
     img, mask, res, name = synth.make_case(args.config, seed=1238 + rank)
     H, W, S = img.shape
-    backbone = tdd.load_model(name, img_hw=(H, W), device=dev, seed=1234)
-    D = backbone.cfg["dim"]
+    if args.model:
+        name = args.model
+    backbone = tdd.load_model(name, img_hw=None if args.model else (H, W), device=dev, seed=1234)
+    D = backbone.feature_dim
     torch.manual_seed(0)
-    clf = TransformerNoduleClassifier(D, 4 * D, D // 64, 2, 2).to(dev)
+    clf = TransformerNoduleClassifier(D, 4 * D, D // 64, 2, 2).to(dev)      # D = 256 (medsam): exactly conf/parameters_models.yaml
     if world > 1:
         for p in clf.parameters():
             torch.distributed.broadcast(p.data, 0)
@@ -83,6 +87,15 @@ def main():
         ms = float(t.item())
         torch.distributed.barrier()
     if rank != 0:
+        return
+    if args.model:       # no host-CPU leg for the override (the fp32 SAM oracle needs minutes per 1024^2 slice batch)
+        print(json.dumps({
+            "metric": f"patients/sec end-to-end: {name} extraction + mask gather + classifier fwd/bwd", "value": world * args.patients / (ms / 1e3),
+            "unit": "patients/s", "slices_per_s": world * args.patients * S / (ms / 1e3), "n_gpus": world, "patients_per_rank": args.patients,
+            "ms_per_patient": ms / args.patients, "tokens_per_patient": n_tok, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{name} ({backbone.img_hw[0]}x{backbone.img_hw[1]} encoder input, {backbone.grid[0]}x{backbone.grid[1]}x{D} descriptors) over a "
+                                   f"{H}x{W}x{S} volume -> point cloud -> 2-layer transformer classifier (d {D}, {D // 64} heads) training step per "
+                                   "patient; H2D of every volume inside the timed region"}, "loss": loss}))
         return
     # CPU baseline: the oracle port (fp32 ViT + NumPy gather + fp32 classifier fwd/bwd) on a bounded sample of slices
     from oracle import classifier_fp32 as C, gather_np, vit_fp32

@@ -24,6 +24,7 @@ from . import ops
 SAM_CONFIGS = {
     "medsam": dict(dim=768, depth=12, heads=12, global_attn=(2, 5, 8, 11), window=14, out_chans=256, patch=16),
     "sam_tiny": dict(dim=128, depth=4, heads=2, global_attn=(1, 3), window=14, out_chans=64, patch=16),   # tests
+    "sam_small": dict(dim=128, depth=2, heads=2, global_attn=(1,), window=14, out_chans=256, patch=16),   # tests: MedSAM's 256-wide neck
 }
 
 
