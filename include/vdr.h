@@ -351,6 +351,13 @@ int vdr_flash_attn_relpos_fwd(const void* qkv, int64_t ld_qkv, const float* rel_
                               int heads, float scale, vdr_stream_t stream);
 int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, void* out_bf16,
                         int64_t ld_out, int BW, int Sh, int Sw, int heads, float scale, vdr_stream_t stream);
+/* Windowed attention straight on the un-partitioned token rows of B images of gh x gw tokens (window_partition, the attention
+ * and window_unpartition of a windowed block in one launch): window (wy, wx) reads its ws x ws tokens in place, pad tokens
+ * (positions beyond the image: their normalised input is zero, so q = k = v = the qkv bias) are synthesised from qkv_bias
+ * ((3*heads*64) f32, the UNFOLDED bias of the qkv Linear), outputs of pad queries are dropped.  ws*ws <= 208. */
+int vdr_attn_relpos_windows_fwd(const void* qkv_bf16, int64_t ld_qkv, const float* qkv_bias, const void* rcat_hi_bf16,
+                                const void* rcat_lo_bf16, void* out_bf16, int64_t ld_out, int B, int gh, int gw, int ws, int heads,
+                                float scale, vdr_stream_t stream);
 int vdr_im2col3x3_tokens(const void* X_bf16, int64_t ldx, void* A_bf16, int64_t lda, int B, int H, int W, int C,
                          vdr_stream_t stream);
 

@@ -104,6 +104,26 @@ def test_flash_attn_relpos_tcgen05_vs_fp32(cuda, BW, Sh, heads):
         ops.attn_relpos(qkv.to(cuda)[:128], 1, 2, Sw, heads, hi2, lo2, kernel="tcgen05")
 
 
+@pytest.mark.parametrize("B,gh,gw,ws,heads", [(2, 16, 16, 14, 2), (1, 64, 64, 14, 12), (3, 9, 20, 7, 1), (1, 14, 14, 14, 2)])
+def test_attn_relpos_windows_in_place_equals_partitioned_path(cuda, B, gh, gw, ws, heads):
+    """Windows read in place (pad tokens = the qkv bias) against window_partition -> attention -> window_unpartition: bit for bit."""
+    from vit_deep_radiomics_b200 import ops
+    g = torch.Generator().manual_seed(B + gh + gw)
+    d = heads * 64
+    bias = (torch.randn(3 * d, generator=g) * 0.3).to(cuda)
+    qkv = (torch.randn(B * gh * gw, 3 * d, generator=g) * 1.1).bfloat16().to(cuda)
+    hi, lo = ops.relpos_split((torch.randn(2 * ws - 1, 64, generator=g) * 0.1).to(cuda), (torch.randn(2 * ws - 1, 64, generator=g) * 0.1).to(cuda))
+    got = ops.attn_relpos_windows(qkv, bias, B, gh, gw, ws, heads, hi, lo)
+    # partitioned path: pad rows of the windowed qkv matrix hold the bias (what the qkv GEMM writes for a zero input row)
+    qw = ops.window_rows(qkv, B, gh, gw, ws, True)
+    ones = ops.window_rows(torch.ones(B * gh * gw, 8, dtype=torch.bfloat16, device=cuda), B, gh, gw, ws, True)[:, 0]
+    qw[ones == 0] = bias.bfloat16()
+    nwin = (-(-gh // ws)) * (-(-gw // ws))
+    ow = ops.attn_relpos(qw, B * nwin, ws, ws, heads, hi, lo, kernel="mma")
+    want = ops.window_rows(ow, B, gh, gw, ws, False)
+    assert torch.equal(got, want)
+
+
 def test_attn_relpos_zero_bias_matches_flash_attention(cuda):
     """With zero rel-pos tables the kernel computes plain softmax attention: same result as the tcgen05 flash kernel."""
     from vit_deep_radiomics_b200 import ops
@@ -161,9 +181,9 @@ def test_sam_encoder_layernorm_kernel_path_and_mma_global_attention(cuda):
     hw = (128, 1024)                                           # 8 x 64 tokens: the global blocks qualify for the tcgen05 kernel
     x = torch.rand(1, 3, *hw, generator=torch.Generator().manual_seed(12))
     outs = []
-    for fold, kern in [(True, "auto"), (False, "mma")]:
+    for fold, kern, in_place in [(True, "auto", True), (False, "mma", True), (False, "auto", False)]:
         model = sam_encoder.SamImageEncoder("sam_tiny", img_hw=hw, device=cuda, seed=29)
-        model.fold_layernorm, model.global_attn_kernel = fold, kern
+        model.fold_layernorm, model.global_attn_kernel, model.windows_in_place = fold, kern, in_place
         model.prepare()
         outs.append(model.dense_descriptors(x.to(cuda)).cpu().numpy())
     with torch.no_grad():

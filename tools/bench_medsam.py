@@ -35,7 +35,7 @@ def main():
     torch.cuda.synchronize()
     agg = {}
     for kind, work, a, b, label in ops.PROFILE:
-        key = label.split(" ")[0] + (" global" if "N4096" in label or "64x64" in label else "")
+        key = label.split(" ")[0] + (" windows" if "windows" in label else " global" if "N4096" in label or "64x64" in label else "")
         t, w = agg.get(key, (0.0, 0.0))
         agg[key] = (t + a.elapsed_time(b), w + work)
     ops.PROFILE = None

@@ -25,7 +25,7 @@ EXPORTS = (
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
     "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
     "vdr_linear_vec_fwd", "vdr_linear_vec_bwd", "vdr_cross_cls_attn_fwd", "vdr_cross_cls_attn_bwd",
-    "vdr_window_rows", "vdr_relpos_tables", "vdr_attn_relpos_fwd", "vdr_flash_attn_relpos_fwd", "vdr_im2col3x3_tokens",
+    "vdr_window_rows", "vdr_relpos_tables", "vdr_attn_relpos_fwd", "vdr_flash_attn_relpos_fwd", "vdr_attn_relpos_windows_fwd", "vdr_im2col3x3_tokens",
 )
 
 
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
     L.vdr_relpos_tables.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, f32, vp]
     L.vdr_flash_attn_relpos_fwd.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, f32, vp]
     L.vdr_attn_relpos_fwd.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp]
+    L.vdr_attn_relpos_windows_fwd.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp]
     L.vdr_im2col3x3_tokens.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

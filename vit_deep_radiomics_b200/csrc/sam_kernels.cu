@@ -377,10 +377,20 @@ __device__ __forceinline__ void win_key_tile(float (&o)[8][4], float& m0, float&
   }
 }
 
+// kMapped: qkv / out hold the UN-partitioned token rows of B images of gh x gw tokens; window bw = (image, wy, wx) reads its
+// Sh x Sw tokens in place (window_partition without the copy) and pad tokens -- positions beyond the image, whose normalised
+// input is zero, so that q = k = v = the qkv bias -- are synthesised from `qkv_bias`; outputs of pad queries are dropped
+// (window_unpartition without the copy).
+struct WinMap {
+  int gh, gw, nwh, nww;
+  const float* qkv_bias;      // (3 * heads * 64) f32: the UNFOLDED bias of the qkv Linear
+};
+
+template <bool kMapped>
 __global__ void __launch_bounds__(kWinThreads, 2)
 attn_relpos_win_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv_bfloat16* __restrict__ rcat_hi,
                        const __nv_bfloat16* __restrict__ rcat_lo, __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int heads,
-                       int Sh, int Sw, int RP, uint32_t magic_sw, float scale_log2e) {
+                       int Sh, int Sw, int RP, uint32_t magic_sw, float scale_log2e, WinMap wm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [208 keys][72]
   __nv_bfloat16* Vs = Ks + kWinRows * kRpPitch;                         // [208 keys][72]
@@ -389,15 +399,41 @@ attn_relpos_win_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const 
   const int h = blockIdx.x, bw = blockIdx.y, q0 = blockIdx.z * kWinQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int d = heads * 64;
-  const __nv_bfloat16* base = qkv + (int64_t)bw * N * ld + h * 64;
+  const __nv_bfloat16* base = qkv + (kMapped ? 0 : (int64_t)bw * N * ld) + h * 64;
   const uint32_t ks_s = smem_u32(Ks), vs_s = smem_u32(Vs), rs_s = smem_u32(Rs);
+  // token r of this window -> its row in qkv / out (kMapped: -1 for a pad token)
+  int64_t img_row0 = 0;
+  int y0 = 0, x0 = 0;
+  if (kMapped) {
+    const int per_img = wm.nwh * wm.nww, bi = bw / per_img, wi = bw - bi * per_img;
+    img_row0 = (int64_t)bi * wm.gh * wm.gw;
+    y0 = (wi / wm.nww) * Sh;
+    x0 = (wi % wm.nww) * Sw;
+  }
+  auto token_row = [&](int r) -> int64_t {
+    if (!kMapped) return r;
+    const int ty = Sw == 1 ? r : (int)__umulhi((uint32_t)r, magic_sw), tx = r - ty * Sw;
+    const int y = y0 + ty, x = x0 + tx;
+    return (y < wm.gh && x < wm.gw) ? img_row0 + (int64_t)y * wm.gw + x : -1;
+  };
   const int RH = 2 * Sh - 1, RT = RH + 2 * Sw - 1;
   // one cp.async wave: K, V (rows beyond N zero-filled) and the two table parts (rows beyond RT zero-filled)
   for (int idx = tid; idx < kWinRows * 8; idx += kWinThreads) {
     const int row = idx >> 3, seg = idx & 7;
-    const int bytes = row < N ? 16 : 0;
-    const __nv_bfloat16* src = base + (int64_t)(row < N ? row : N - 1) * ld + seg * 8;
     const uint32_t off = (row * kRpPitch + seg * 8) * 2;
+    const int64_t trow = row < N ? token_row(row) : 0;
+    if (kMapped && trow < 0) {      // pad token: k = bias_k, v = bias_v (rounded to bf16 as the qkv GEMM would have stored them)
+      const float* bk = wm.qkv_bias + d + h * 64 + seg * 8;
+      const float4 k0 = __ldg(reinterpret_cast<const float4*>(bk)), k1 = __ldg(reinterpret_cast<const float4*>(bk) + 1);
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(bk + d)), v1 = __ldg(reinterpret_cast<const float4*>(bk + d) + 1);
+      *reinterpret_cast<uint4*>(Ks + row * kRpPitch + seg * 8) =
+          make_uint4(pack_bf16x2(k0.x, k0.y), pack_bf16x2(k0.z, k0.w), pack_bf16x2(k1.x, k1.y), pack_bf16x2(k1.z, k1.w));
+      *reinterpret_cast<uint4*>(Vs + row * kRpPitch + seg * 8) =
+          make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+      continue;
+    }
+    const int bytes = row < N ? 16 : 0;
+    const __nv_bfloat16* src = base + (kMapped ? trow : (int64_t)(row < N ? row : N - 1)) * ld + seg * 8;
     cp_async16(ks_s + off, src + d, bytes);
     cp_async16(vs_s + off, src + 2 * d, bytes);
   }
@@ -411,15 +447,16 @@ attn_relpos_win_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const 
   }
   cp_async_commit();
   const int rl0 = q0 + warp * 16 + g, rl1 = rl0 + 8;     // this thread's query rows (tokens of the window)
+  const int64_t tr0 = rl0 < N ? token_row(rl0) : -1, tr1 = rl1 < N ? token_row(rl1) : -1;   // -1: no such query (beyond N or pad)
   uint32_t qa[4][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
-    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (int64_t)rl0 * ld + ks * 16 + 2 * t);
-    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (int64_t)rl1 * ld + ks * 16 + 2 * t);
-    qa[ks][0] = rl0 < N ? __ldg(p0) : 0u;
-    qa[ks][1] = rl1 < N ? __ldg(p1) : 0u;
-    qa[ks][2] = rl0 < N ? __ldg(p0 + 4) : 0u;
-    qa[ks][3] = rl1 < N ? __ldg(p1 + 4) : 0u;
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (tr0 < 0 ? 0 : tr0) * ld + ks * 16 + 2 * t);
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (tr1 < 0 ? 0 : tr1) * ld + ks * 16 + 2 * t);
+    qa[ks][0] = tr0 >= 0 ? __ldg(p0) : 0u;
+    qa[ks][1] = tr1 >= 0 ? __ldg(p1) : 0u;
+    qa[ks][2] = tr0 >= 0 ? __ldg(p0 + 4) : 0u;
+    qa[ks][3] = tr1 >= 0 ? __ldg(p1 + 4) : 0u;
   }
   cp_async_wait<0>();
   __syncthreads();                                       // the only CTA barrier
@@ -463,11 +500,11 @@ attn_relpos_win_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const 
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
-  __nv_bfloat16* ob = out + (int64_t)bw * N * ld_out + h * 64;
+  __nv_bfloat16* ob = out + (kMapped ? 0 : (int64_t)bw * N * ld_out) + h * 64;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    if (rl0 < N) *reinterpret_cast<uint32_t*>(ob + (int64_t)rl0 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0] * i0, o[nt][1] * i0);
-    if (rl1 < N) *reinterpret_cast<uint32_t*>(ob + (int64_t)rl1 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2] * i1, o[nt][3] * i1);
+    if (tr0 >= 0) *reinterpret_cast<uint32_t*>(ob + tr0 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0] * i0, o[nt][1] * i0);
+    if (tr1 >= 0) *reinterpret_cast<uint32_t*>(ob + tr1 * ld_out + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2] * i1, o[nt][3] * i1);
   }
 }
 
@@ -625,14 +662,14 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const v
     const size_t smem_w = (2 * (size_t)kWinRows * kRpPitch + 2 * (size_t)kRpTile) * sizeof(__nv_bfloat16) + (size_t)kWinQ * RP * sizeof(float);
     static bool configured_w = false;
     if (!configured_w) {
-      cudaError_t e = cudaFuncSetAttribute(attn_relpos_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(attn_relpos_win_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_win_kernel)");
       configured_w = true;
     }
-    attn_relpos_win_kernel<<<dim3(heads, BW, N > kWinQ ? 2 : 1), kWinThreads, smem_w, reinterpret_cast<cudaStream_t>(stream)>>>(
+    attn_relpos_win_kernel<false><<<dim3(heads, BW, N > kWinQ ? 2 : 1), kWinThreads, smem_w, reinterpret_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
         static_cast<const __nv_bfloat16*>(rcat_lo_bf16), static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, Sh, Sw, RP, magic,
-        scale * 1.4426950408889634f);
+        scale * 1.4426950408889634f, WinMap{});
     count_launch();
     VDR_CHECK_LAUNCH("attn_relpos_win_kernel");
     return VDR_OK;
@@ -652,6 +689,43 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const v
       scale * 1.4426950408889634f);
   count_launch();
   VDR_CHECK_LAUNCH("attn_relpos_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_attn_relpos_windows_fwd(const void* qkv_bf16, int64_t ld_qkv, const float* qkv_bias, const void* rcat_hi_bf16,
+                                           const void* rcat_lo_bf16, void* out_bf16, int64_t ld_out, int B, int gh, int gw, int ws, int heads,
+                                           float scale, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(qkv_bf16 && qkv_bias && rcat_hi_bf16 && rcat_lo_bf16 && out_bf16, VDR_EINVAL, "vdr_attn_relpos_windows_fwd: null pointer");
+  VDR_CHECK_ARG(B > 0 && gh > 0 && gw > 0 && ws > 0 && heads > 0 && heads <= 65535, VDR_EINVAL,
+                "vdr_attn_relpos_windows_fwd: bad shape B=%d grid %dx%d ws=%d heads=%d", B, gh, gw, ws, heads);
+  const int N = ws * ws;
+  VDR_CHECK_ARG(N <= kWinRows && 4 * ws - 2 <= 64, VDR_EINVAL,
+                "vdr_attn_relpos_windows_fwd: windows of %dx%d tokens do not fit the resident-key kernel (<= %d tokens); use vdr_window_rows + vdr_attn_relpos_fwd",
+                ws, ws, kWinRows);
+  VDR_CHECK_ARG(ld_qkv >= 3LL * heads * 64 && ld_qkv % 8 == 0 && ld_out >= heads * 64LL && ld_out % 8 == 0 && aligned16(qkv_bf16) &&
+                    aligned16(out_bf16) && aligned16(rcat_hi_bf16) && aligned16(rcat_lo_bf16) && aligned16(qkv_bias),
+                VDR_EALIGN, "vdr_attn_relpos_windows_fwd: qkv (rows, >= 3*heads*64) / out (rows, >= heads*64), ld %% 8 == 0, 16-byte aligned");
+  const int nwh = (gh + ws - 1) / ws, nww = (gw + ws - 1) / ws;
+  const int64_t BW = (int64_t)B * nwh * nww;
+  VDR_CHECK_ARG(BW <= 65535, VDR_EINVAL, "vdr_attn_relpos_windows_fwd: %lld windows exceed the grid limit (65535): split the batch", (long long)BW);
+  const int rp0 = ((ws + 1) & ~1) + ws;
+  const int RP = rp0 + (8 - rp0 % 32 + 32) % 32;
+  const size_t smem_w = (2 * (size_t)kWinRows * kRpPitch + 2 * (size_t)kRpTile) * sizeof(__nv_bfloat16) + (size_t)kWinQ * RP * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_relpos_win_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_win_kernel<mapped>)");
+    configured = true;
+  }
+  const uint32_t magic = ws > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)ws - 1) / (uint64_t)ws) : 0u;
+  WinMap wm{gh, gw, nwh, nww, qkv_bias};
+  attn_relpos_win_kernel<true><<<dim3(heads, (unsigned)BW, N > kWinQ ? 2 : 1), kWinThreads, smem_w, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
+      static_cast<const __nv_bfloat16*>(rcat_lo_bf16), static_cast<__nv_bfloat16*>(out_bf16), ld_out, N, heads, ws, ws, RP, magic,
+      scale * 1.4426950408889634f, wm);
+  count_launch();
+  VDR_CHECK_LAUNCH("attn_relpos_win_kernel<mapped>");
   return VDR_OK;
 }
 

@@ -670,6 +670,30 @@ def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rcat_h
     return out
 
 
+def attn_relpos_windows(qkv: torch.Tensor, qkv_bias: torch.Tensor, B: int, gh: int, gw: int, ws: int, heads: int,
+                        rcat_hi: torch.Tensor, rcat_lo: torch.Tensor, scale: float | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """A windowed SAM block's window_partition -> attention (+ rel-pos bias) -> window_unpartition in one launch, on the
+    un-partitioned rows: qkv (B*gh*gw, 3*heads*64) bf16 as the qkv GEMM writes it, qkv_bias (3*heads*64) f32 = the unfolded
+    Linear bias (what a zero pad token projects to), tables for ws x ws windows -> out (B*gh*gw, heads*64) bf16."""
+    _req(qkv, torch.bfloat16, "qkv"), _req(qkv_bias, torch.float32, "qkv_bias"), _req(rcat_hi, torch.bfloat16, "rcat_hi"), _req(rcat_lo, torch.bfloat16, "rcat_lo")
+    d = heads * 64
+    if qkv.shape != (B * gh * gw, 3 * d) or qkv.stride(1) != 1 or qkv_bias.numel() != 3 * d or not qkv_bias.is_contiguous():
+        raise ValueError(f"qkv must be ({B * gh * gw}, {3 * d}) and qkv_bias ({3 * d})")
+    RT = 4 * ws - 2
+    if rcat_hi.shape != (RT, 64) or rcat_lo.shape != (RT, 64) or not rcat_hi.is_contiguous() or not rcat_lo.is_contiguous():
+        raise ValueError(f"rcat_hi / rcat_lo must be contiguous ({RT}, 64) tables (relpos_split)")
+    if scale is None:
+        scale = 1.0 / math.sqrt(64)
+    if out is None:
+        out = torch.empty((B * gh * gw, d), dtype=torch.bfloat16, device=qkv.device)
+    nwin = (-(-gh // ws)) * (-(-gw // ws))
+    with _Prof("attn", B * nwin * heads * (4.0 * (ws * ws) ** 2 * 64 + 2.0 * ws * ws * 2 * ws * 64), f"attn+relpos windows B{B} {gh}x{gw} ws{ws} h{heads}"):
+        _C.check(_C.lib().vdr_attn_relpos_windows_fwd(qkv.data_ptr(), qkv.stride(0), qkv_bias.data_ptr(), rcat_hi.data_ptr(), rcat_lo.data_ptr(),
+                                                      out.data_ptr(), out.stride(0), B, gh, gw, ws, heads, float(scale), _stream()),
+                 "vdr_attn_relpos_windows_fwd")
+    return out
+
+
 def im2col3x3_tokens(x: torch.Tensor, B: int, H: int, W: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """(B*H*W, C) bf16 token-major map -> (B*H*W, 9*C) bf16, k = (ky, kx, c), zero padding 1."""
     _req(x, torch.bfloat16, "x")

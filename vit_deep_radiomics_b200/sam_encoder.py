@@ -140,13 +140,12 @@ class SamImageEncoder:
                 fc2_w=bf(b + "mlp.lin2.weight"), fc2_b=f32(b + "mlp.lin2.bias"),
                 window=0 if i in cfg["global_attn"] else ws))
         if self.fold_layernorm:
-            # norm2 -> lin1 everywhere and norm1 -> qkv in the global blocks are folded into the GEMMs (vdr_fold_layernorm): the
-            # producing residual GEMM leaves the row statistics, the consumer normalises in its epilogue.
-            # The windowed blocks keep the norm1 kernel: their padding is defined on the normalised tokens.
+            # norm1 -> qkv and norm2 -> lin1 are folded into the GEMMs (vdr_fold_layernorm): the producing residual GEMM leaves the
+            # row statistics, the consumer normalises in its epilogue.  The windowed blocks can do that
+            # because their windows are read in place (vdr_attn_relpos_windows_fwd): a pad token is "the qkv bias", not a row.
             for blk in self.w["blocks"]:
                 blk["fc1_wf"], blk["fc1_bf"], blk["fc1_cs"] = ops.fold_layernorm(blk["fc1_w"], blk["fc1_b"], blk["n2w"], blk["n2b"])
-                if not blk["window"]:
-                    blk["qkv_wf"], blk["qkv_bf"], blk["qkv_cs"] = ops.fold_layernorm(blk["qkv_w"], blk["qkv_b"], blk["n1w"], blk["n1b"])
+                blk["qkv_wf"], blk["qkv_bf"], blk["qkv_cs"] = ops.fold_layernorm(blk["qkv_w"], blk["qkv_b"], blk["n1w"], blk["n1b"])
 
     def _buffers(self, B: int) -> dict:
         ws = self._ws.get(B)
@@ -172,6 +171,9 @@ class SamImageEncoder:
 
     #: fold norm2 (all blocks) / norm1 (global blocks) into the GEMMs that consume them (set False before prepare() for A/B)
     fold_layernorm = True
+
+    #: windowed blocks read their windows in place (vdr_attn_relpos_windows_fwd); False = window_partition / unpartition copies
+    windows_in_place = True
 
     #: "auto" (tcgen05 flash kernel with bias where the token grid is Sh x 64, else mma.sync) | "mma" (A/B timing, parity tests)
     global_attn_kernel = "auto"
@@ -211,12 +213,12 @@ class SamImageEncoder:
         if fold and "ST" not in ws:
             ws["ST"] = torch.empty(d // 64, B * N, 2, dtype=torch.float32, device=self.device)
         ST = ws.get("ST")
-        stats = None                      # row statistics of X as the last residual GEMM left them (None: not available)
-        if fold and not w["blocks"][0]["window"]:
-            stats = ops.row_stats(X, out=ST[:1])
-        nblk = len(w["blocks"])
+        in_place = self.windows_in_place and win * win <= 208          # windows read in place (no partition / unpartition copies)
+        if fold:
+            ops.row_stats(X, out=ST[:1])
         for i, blk in enumerate(w["blocks"]):
-            if blk["window"]:
+            qkv = ws["QKV"][:B * N]
+            if blk["window"] and not in_place:
                 ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
                 ops.window_rows(Y, B, gh, gw, win, True, out=ws["YW"])
                 qkv = ws["QKV"][:B * NW]
@@ -224,19 +226,19 @@ class SamImageEncoder:
                 ops.attn_relpos(qkv, B * nwh * nww, win, win, heads, blk["rel_hi"], blk["rel_lo"], scale, out=ws["OW"])
                 ops.window_rows(ws["OW"], B, gh, gw, win, False, out=Y)
             else:
-                qkv = ws["QKV"][:B * N]
                 if fold:
-                    ops.gemm(X, blk["qkv_wf"], blk["qkv_bf"], out=qkv, ln_stats=stats, ln_colsum=blk["qkv_cs"])
+                    ops.gemm(X, blk["qkv_wf"], blk["qkv_bf"], out=qkv, ln_stats=ST[:1] if i == 0 else ST, ln_colsum=blk["qkv_cs"])
                 else:
                     ops.layernorm(X, blk["n1w"], blk["n1b"], 1e-6, out=Y)
                     ops.gemm(Y, blk["qkv_w"], blk["qkv_b"], out=qkv)
-                ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_hi"], blk["rel_lo"], scale, out=Y, rel=ws.get("REL"), kernel=self.global_attn_kernel)
+                if blk["window"]:
+                    ops.attn_relpos_windows(qkv, blk["qkv_b"], B, gh, gw, win, heads, blk["rel_hi"], blk["rel_lo"], scale, out=Y)
+                else:
+                    ops.attn_relpos(qkv, B, gh, gw, heads, blk["rel_hi"], blk["rel_lo"], scale, out=Y, rel=ws.get("REL"), kernel=self.global_attn_kernel)
             if fold:
-                next_global = i + 1 < nblk and not w["blocks"][i + 1]["window"]
                 ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X, stats_out=ST)
                 ops.gemm(X, blk["fc1_wf"], blk["fc1_bf"], epilogue="gelu", out=Hb, ln_stats=ST, ln_colsum=blk["fc1_cs"])
-                ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X, stats_out=ST if next_global else None)
-                stats = ST if next_global else None
+                ops.gemm(Hb, blk["fc2_w"], blk["fc2_b"], epilogue="residual", residual=X, out=X, stats_out=ST)
             else:
                 ops.gemm(Y, blk["proj_w"], blk["proj_b"], epilogue="residual", residual=X, out=X)
                 ops.layernorm(X, blk["n2w"], blk["n2b"], 1e-6, out=Y)
