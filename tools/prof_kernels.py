@@ -63,15 +63,16 @@ if which in ("gather", "all"):
         torch.cuda.synchronize()
 print("done")
 if which in ("sam",):
-    # MedSAM attention with rel-pos bias, 12 heads: 4 images of 64 x 64 tokens (bias table kernel + tcgen05 flash kernel with
-    # bias) and 100 windows of 14 x 14 (mma.sync kernel).  One warm round (3 launches), then the round ncu captures:
-    #   ncu -k regex:'relpos|flash_attn' -s 3 -c 3
-    cases = []
-    for (BW, S) in [(4, 64), (100, 14)]:
-        qkv = torch.randn(BW * S * S, 3 * d, device=dev).bfloat16()
-        hi, lo = ops.relpos_split(torch.randn(2 * S - 1, 64, device=dev) * 0.1, torch.randn(2 * S - 1, 64, device=dev) * 0.1)
-        cases.append((qkv, BW, S, hi, lo, torch.empty(BW * S * S, d, device=dev, dtype=torch.bfloat16)))
+    # MedSAM attention with rel-pos bias, 4 images of 64 x 64 tokens, 12 heads: the global block (bias table kernel + tcgen05 flash
+    # kernel with bias) and a windowed block read in place (100 windows of 14 x 14, mma.sync resident-key kernel).
+    # One warm round (3 launches), then the round ncu captures:  ncu -k regex:'relpos|flash_attn' -s 3 -c 3
+    B, S = 4, 64
+    qkv = torch.randn(B * S * S, 3 * d, device=dev).bfloat16()
+    bias = torch.randn(3 * d, device=dev) * 0.1
+    out = torch.empty(B * S * S, d, device=dev, dtype=torch.bfloat16)
+    hi_g, lo_g = ops.relpos_split(torch.randn(2 * S - 1, 64, device=dev) * 0.1, torch.randn(2 * S - 1, 64, device=dev) * 0.1)
+    hi_w, lo_w = ops.relpos_split(torch.randn(27, 64, device=dev) * 0.1, torch.randn(27, 64, device=dev) * 0.1)
     for _ in range(2):
-        for (qkv, BW, S, hi, lo, out) in cases:
-            ops.attn_relpos(qkv, BW, S, S, 12, hi, lo, out=out)
+        ops.attn_relpos(qkv, B, S, S, 12, hi_g, lo_g, out=out)
+        ops.attn_relpos_windows(qkv, bias, B, S, S, 14, 12, hi_w, lo_w, out=out)
         torch.cuda.synchronize()

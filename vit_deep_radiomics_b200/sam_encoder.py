@@ -156,14 +156,16 @@ class SamImageEncoder:
             N = gh * gw
             nwin = (-(-gh // win)) * (-(-gw // win))
             NW = nwin * win * win                                    # rows per image in the windowed layout (>= N)
+            in_place = self.windows_in_place and win * win <= 208
             ws = dict(A=torch.empty(B * N, self.K, dtype=bf, device=dev),
                       X=torch.empty(B * N, d, dtype=bf, device=dev), Y=torch.empty(B * N, d, dtype=bf, device=dev),
-                      YW=torch.empty(B * NW, d, dtype=bf, device=dev), OW=torch.empty(B * NW, d, dtype=bf, device=dev),
-                      QKV=torch.empty(B * max(N, NW), 3 * d, dtype=bf, device=dev),
+                      QKV=torch.empty(B * (N if in_place else max(N, NW)), 3 * d, dtype=bf, device=dev),
                       H=torch.empty(B * N, 4 * d, dtype=bf, device=dev),
                       N0=torch.empty(B * N, oc, dtype=bf, device=dev), N1=torch.empty(B * N, oc, dtype=bf, device=dev),
                       NA=torch.empty(B * N, 9 * oc, dtype=bf, device=dev),
                       OUT=torch.empty(B * N, oc, dtype=torch.float32, device=dev))
+            if not in_place:                                         # window_partition / unpartition copies of the explicit path
+                ws.update(YW=torch.empty(B * NW, d, dtype=bf, device=dev), OW=torch.empty(B * NW, d, dtype=bf, device=dev))
             if gw == 64 and gh % 4 == 0 and self.global_attn_kernel != "mma":       # bias table of the tcgen05 global attention
                 ws["REL"] = torch.empty(B * cfg["heads"] * N * (gh + gw), dtype=torch.float32, device=dev)
             self._ws = {B: ws}
