@@ -204,3 +204,36 @@ def test_epoch_policy_and_split_report():
     # weights 1, .5, .5, 1, 1: positives 2 (weighted), of which 1.5 predicted positive; negatives 2, of which 1 predicted negative
     assert abs(rep["1"]["recall"] - 0.75) < 1e-12 and abs(rep["0"]["recall"] - 0.5) < 1e-12 and abs(rep["accuracy"] - 0.625) < 1e-12
     assert 0.0 <= rep["ROC AUC"] <= 1.0
+
+
+def test_extract_patient_features_augmentation_table():
+    """The per-patient extraction loop (tfds_dense_descriptor.py:452-488) with a stub backbone: 3 flips x 4 angles, the
+    metadata table the trainer reads, including the reference's all-True `augmentation` column (:486)."""
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    rng = np.random.default_rng(2)
+    S = 3
+    img = rng.random((16, 16, S)).astype(np.float32)
+    mask = np.zeros((16, 16, S), bool)
+    mask[5:9, 6:11] = True
+    seen = []
+
+    def stub(model, img_3d, mask_3d, tqdm_text, display):
+        seen.append((img_3d.copy(), mask_3d.copy(), tqdm_text))
+        return ([np.full((2, 2, 4), float(len(seen)), np.float32)] * img_3d.shape[2], [np.ones((2, 2), bool)] * img_3d.shape[2])
+
+    res = np.array([0.8, 0.8, 0.8])
+    df, feats, masks = tdd.extract_patient_features(None, img, mask, "p01", 1, "stanford_dataset", "ct", res, generate=stub)
+    assert len(seen) == 12 and len(feats) == len(masks) == 12 * S == len(df)
+    assert list(df.columns) == ["feature_id", "slice", "angle", "flip", "patient_id", "label", "dataset", "modality", "augmentation", "spatial_res"]
+    assert df["feature_id"].tolist() == list(range(12 * S)) and df["slice"].tolist() == list(range(S)) * 12
+    assert df["angle"].tolist() == [a for _ in range(3) for a in (0, 45, 90, 135) for _ in range(S)]
+    flips = df["flip"].tolist()            # pandas stores the None of the first four volumes as a missing value
+    assert all(f is None or f != f for f in flips[:4 * S]) and flips[4 * S:] == [f for f in ("horizontal", "vertical") for _ in range(4 * S)]
+    assert df["augmentation"].all() and (df["dataset"] == "stanford").all() and (df["patient_id"] == "p01").all()
+    assert all(np.array_equal(r, res) for r in df["spatial_res"]) and seen[0][2] == "ct p01"
+    assert np.array_equal(seen[0][0], img) and np.array_equal(seen[4][0], img[:, ::-1]) and np.array_equal(seen[8][0], img[::-1])
+    assert feats[0][0, 0, 0] == 1.0 and feats[-1][0, 0, 0] == 12.0        # concatenated in (flip, angle, slice) order
+    # the reference's expression for the augmentation column, evaluated literally
+    import pandas as pd
+    lit = np.logical_not(np.logical_and(df["flip"] is None, df["angle"] == 0))
+    assert np.array_equal(np.asarray(lit), df["augmentation"].values)

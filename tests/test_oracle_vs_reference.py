@@ -201,3 +201,29 @@ def test_merge_dataframe_features_matches_reference_script(tmp_path, monkeypatch
     pd.testing.assert_frame_equal(want, got)
     assert (got["augmentation"] == ~((got["flip"] == "None") & (got["angle"] == 0))).all() and (got["flip"] == "None").any()
     assert pd.read_parquet(mf.main(os.path.join("..", "data", "features"))).equals(want)
+
+
+def test_hu_to_rgb_and_flip_rotate_match_reference():
+    """visualization_utils.hu_to_rgb_vectorized (:128-186) bit for bit on every input dtype the HDF5 volumes may have (the
+    ramp ratio follows the input's dtype), interval edges included; flip_image / rotate_image (:306-350) on a small volume."""
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd, visualization_utils as V
+    vu = ref_shim.load_reference("visualization_utils")
+    ref = ref_shim.load_reference("tfds_dense_descriptor")
+    rng = np.random.default_rng(3)
+    edges = np.array([-1500, -1000, -999.5, -600, -599, -400, -399, -100, -99, -60, -59, 40, 41, 80, 81, 399, 400, 401, 1500, 0])
+    for dt in (np.float32, np.float64, np.int16, np.int32):
+        a = np.concatenate([rng.uniform(-1200, 800, 4000), edges]).astype(dt).reshape(-1, 4)
+        want, got = vu.hu_to_rgb_vectorized(a), V.hu_to_rgb_vectorized(a)
+        assert got.dtype == want.dtype == np.uint8 and got.shape == a.shape + (3,) and np.array_equal(got, want), dt
+    img = rng.random((12, 10, 3)).astype(np.float32)
+    mask = rng.random((12, 10, 3)) < 0.2
+    for flip in (None, "horizontal", "vertical"):
+        a, b = ref.flip_image(img, mask, flip), tdd.flip_image(img, mask, flip)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        for angle in tdd.AUG_ANGLES:
+            c, d = ref.rotate_image(a[0], a[1], angle), tdd.rotate_image(b[0], b[1], angle)
+            assert np.array_equal(c[0], d[0]) and np.array_equal(c[1], d[1]), (flip, angle)
+    hu = rng.uniform(-1100, 600, (6, 5, 2)).astype(np.float32)
+    assert np.array_equal(tdd.normalize_volume(hu, "ct", "medsam"), ref.apply_window_ct(hu, width=800, level=40))
+    assert np.array_equal(tdd.normalize_volume(hu, "ct", "dinov2"), vu.hu_to_rgb_vectorized(hu) / 255.0)
+    assert np.array_equal(tdd.normalize_volume(np.abs(hu), "pet", "medsam"), np.abs(hu) / np.abs(hu).max())

@@ -307,6 +307,60 @@ def rotate_image(image, mask, angle, axes=(0, 1)):
     return image, mask
 
 
+#: offline augmentation grid of the reference (tfds_dense_descriptor.py:463-465): 3 flips x 4 rotation angles
+AUG_FLIPS = (None, "horizontal", "vertical")
+AUG_ANGLES = tuple(range(0, 180, 45))
+
+
+def normalize_volume(img_raw, modality, model_name):
+    """Pixel normalisation of the extraction loop (:441-447): CT -> the lung window mapped to 0..1 for 'medsam', the tissue
+    colour map / 255 (an RGB volume) for the other backbones; PET -> divided by its maximum."""
+    from .visualization_utils import hu_to_rgb_vectorized
+    if modality == "ct":
+        if model_name == "medsam":
+            return apply_window_ct(img_raw, width=800, level=40)
+        return hu_to_rgb_vectorized(img_raw) / 255.0
+    return img_raw / img_raw.max()
+
+
+def extract_patient_features(model, img_raw, mask_raw, patient_id, label, dataset_name, modality, spatial_res, tqdm_text=None,
+                             generate=None):
+    """One patient of the reference's extraction loop (tfds_dense_descriptor.py:452-488): every (flip, angle) of the offline
+    augmentation grid goes through ``generate_features`` (all slices of a volume as one backbone batch here), the per-slice
+    feature maps / masks are concatenated and described by the metadata table the trainer reads.
+
+    Returns (df, all_features, all_masks); the caller writes ``df.to_parquet(df_path)`` and
+    ``save_features(features_file, all_features, all_masks, patient_id)`` as the reference does (:489-490).
+    Columns: feature_id (running index), slice, angle, flip, patient_id, label, dataset, modality, augmentation, spatial_res.
+    ``augmentation`` is True on EVERY row, also for (flip None, angle 0): the reference evaluates ``df['flip'] is None`` on the
+    Series object (:486), which is always False -- reproduced, because the trainer filters on this column."""
+    import pandas as pd
+    gen = generate or generate_features
+    rows = {"slice": [], "angle": [], "flip": []}
+    all_features, all_masks = [], []
+    for flip_type in AUG_FLIPS:
+        image_flip, mask_flip = flip_image(img_raw, mask_raw, flip_type)
+        for angle in AUG_ANGLES:
+            image, mask = rotate_image(image_flip, mask_flip, angle)
+            features, features_mask = gen(model=model, img_3d=image, mask_3d=mask,
+                                          tqdm_text=tqdm_text or f"{modality} {patient_id}", display=False)
+            all_masks += features_mask
+            all_features += features
+            rows["angle"] += [angle] * len(features)
+            rows["flip"] += [flip_type] * len(features)
+            rows["slice"] += list(range(0, len(features)))
+    df = pd.DataFrame(rows)
+    df.reset_index(drop=False, inplace=True)
+    df = df.rename(columns={"index": "feature_id"})
+    df["patient_id"] = patient_id
+    df["label"] = label
+    df["dataset"] = dataset_name.replace("_dataset", "")
+    df["modality"] = modality
+    df["augmentation"] = np.ones(df.shape[0], dtype=bool)          # see the docstring: the reference's expression is all-True
+    df["spatial_res"] = [spatial_res] * df.shape[0]
+    return df, all_features, all_masks
+
+
 def _h5py():
     try:
         import h5py

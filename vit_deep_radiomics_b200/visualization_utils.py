@@ -84,3 +84,40 @@ def crop_window_from_bbox(bbox):
     crop_size = max(xmax - xmin, ymax - ymin) * 2
     xmid, ymid = int(xmin + (xmax - xmin) / 2), int(ymin + (ymax - ymin) / 2)
     return xmid - crop_size, ymid - crop_size, xmid + crop_size, ymid + crop_size
+
+
+# ---------------------------------------------------------------------------------------------- HU -> RGB (non-MedSAM CT input)
+_AIR, _LUNG, _FAT = (0, 0, 0), (194, 105, 82), (194, 166, 115)
+_SOFT_LO, _SOFT_HI, _BONE = (102, 0, 0), (153, 0, 0), (255, 255, 255)
+#: (low, low_closed, high, high_closed, colour_at_ramp_start, colour_at_ramp_end or None, ramp_start, ramp_end) -- the nine HU
+#: intervals of the reference (visualization_utils.py:146-184).  The soft-tissue plateau [40, 80] is ramped over (80, 400) in the
+#: reference (:172-175), i.e. slightly EXTRAPOLATED below its first colour; kept as is.
+_HU_SEGMENTS = (
+    (-np.inf, False, -1000, True, _AIR, None, 0, 1),
+    (-1000, False, -600, False, _AIR, _LUNG, -1000, -600),
+    (-600, True, -400, True, _LUNG, None, 0, 1),
+    (-400, False, -100, False, _LUNG, _FAT, -400, -100),
+    (-100, True, -60, True, _FAT, None, 0, 1),
+    (-60, False, 40, False, _FAT, _SOFT_LO, -60, 40),
+    (40, True, 80, True, _SOFT_LO, _SOFT_HI, 80, 400),
+    (80, False, 400, False, _SOFT_HI, _BONE, 80, 400),
+    (400, True, np.inf, False, _BONE, None, 0, 1),
+)
+
+
+def hu_to_rgb_vectorized(hu_matrix):
+    """reference: visualization_utils.py:128-186 -- tissue colour map of a CT in Hounsfield units, (…) -> (…, 3) uint8; the
+    extraction divides it by 255 for the non-MedSAM backbones (tfds_dense_descriptor.py:445).  Same arithmetic as the reference
+    (ramp ratio in the input's dtype, colours mixed in float64, truncation into an integer image), table-driven."""
+    hu = np.asarray(hu_matrix)
+    rgb = np.zeros(hu.shape + (3,), dtype=int)
+    for lo, lo_closed, hi, hi_closed, c_a, c_b, r0, r1 in _HU_SEGMENTS:
+        above = (hu >= lo) if lo_closed else (hu > lo)
+        below = (hu <= hi) if hi_closed else (hu < hi)
+        sel = above & below
+        if c_b is None:
+            rgb[sel] = np.array(c_a)
+        else:
+            ratios = (hu[sel] - r0) / (r1 - r0)
+            rgb[sel] = np.array(c_a) * (1 - ratios[..., None]) + np.array(c_b) * ratios[..., None]
+    return rgb.astype(np.uint8)
