@@ -52,3 +52,26 @@ def test_ops_refuse_cpu_tensors():
         ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
     with pytest.raises(ValueError):
         ops.layernorm(torch.zeros(4, 8, dtype=torch.bfloat16), torch.ones(8), torch.zeros(8), 1e-6)
+
+
+def test_sam_entry_points_validate_arguments_without_a_gpu():
+    """The MedSAM entry points reject bad arguments before any CUDA call (no silent fallback between the attention kernels)."""
+    import torch
+    from vit_deep_radiomics_b200 import ops
+    lib = _C.lib()
+    assert lib.vdr_window_rows(None, 0, None, 0, 1, 4, 4, 2, 8, 1, None) == -1 and b"null" in lib.vdr_last_error_string()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.addressof(buf)
+    p += (-p) % 16
+    assert lib.vdr_window_rows(p, 12, p, 12, 1, 4, 4, 2, 12, 1, None) == -1                      # d not a multiple of 8
+    assert lib.vdr_attn_relpos_windows_fwd(p, 192, p, p, p, p, 64, 1, 64, 64, 20, 1, 0.125, None) == -1   # 20 x 20 windows: 400 tokens
+    assert b"resident-key" in lib.vdr_last_error_string()
+    assert lib.vdr_flash_attn_relpos_fwd(p, 192, p, p, 64, 1, 6, 1, 0.125, None) == -1           # Sh = 6: not a multiple of 4
+    assert b"multiple of 4" in lib.vdr_last_error_string()
+    assert lib.vdr_relpos_tables(p, 192, p, p, p, 1, 300, 300, 1, 1.0, None) == -1               # 90,000 tokens: beyond the index range
+    assert lib.vdr_im2col3x3_tokens(p, 12, p, 108, 1, 2, 2, 12, None) == -1
+    with pytest.raises(ValueError):
+        ops.window_rows(torch.zeros(16, 8, dtype=torch.bfloat16), 1, 4, 4, 2, True)
+    with pytest.raises(ValueError):
+        ops.attn_relpos(torch.zeros(16, 192, dtype=torch.bfloat16), 1, 4, 4, 1, torch.zeros(14, 64, dtype=torch.bfloat16),
+                        torch.zeros(14, 64, dtype=torch.bfloat16))
