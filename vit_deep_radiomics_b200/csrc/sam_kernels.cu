@@ -72,13 +72,15 @@ constexpr int kRpTile = kRpBK * kRpPitch;               // elements of one K / V
 // One ldmatrix.x4 feeds two n-tiles of one k-step, so consecutive MMAs never accumulate into the same registers
 // (a dependent HMMA chain stalls for the full pipe latency).
 // `rows` (warp-uniform) = tile rows that hold data: 16-row groups beyond it are skipped (their accumulators stay 0).
-__device__ __forceinline__ void qk_tile_mma(float (&acc)[8][4], const uint32_t (&qa)[4][4], uint32_t tile_smem, int lane, int rows = kRpBK) {
+// `need` (warp-uniform bit mask, bit p = the 16-row group p is wanted): further groups to skip.
+__device__ __forceinline__ void qk_tile_mma(float (&acc)[8][4], const uint32_t (&qa)[4][4], uint32_t tile_smem, int lane, int rows = kRpBK,
+                                            uint32_t need = 0xfu) {
   const uint32_t lane_off = (((lane & 7) + (lane >> 4) * 8) * kRpPitch + ((lane >> 3) & 1) * 8) * 2;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
     for (int ntp = 0; ntp < 4; ++ntp) {
-      if (ntp * 16 >= rows) continue;
+      if (ntp * 16 >= rows || !((need >> ntp) & 1u)) continue;
       uint32_t b[4];     // b0/b1 of n-tile 2*ntp, b0/b1 of n-tile 2*ntp + 1, k-step ks
       ldmatrix_x4(b, tile_smem + lane_off + (ntp * 16 * kRpPitch + ks * 16) * 2);
       mma_bf16_16816(acc[2 * ntp], qa[ks], b[0], b[1]);
@@ -540,6 +542,11 @@ relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __n
   const int qh0 = r0 / Sw, qh1 = r1 / Sw;
   const int offh0 = qh0 + Sh - 1, offw0 = r0 - qh0 * Sw + Sw - 1;
   const int offh1 = qh1 + Sh - 1, offw1 = r1 - qh1 * Sw + Sw - 1;
+  // table rows this warp's 16 queries can select: rel_h rows [qh_min, qh_max + Sh - 1], rel_w rows RH + [qw_min, qw_max + Sw - 1]
+  // (a query (qh, qw) reads rows qh + Sh-1 - kh and RH + qw + Sw-1 - kw, kh < Sh, kw < Sw); 16-row groups outside both are skipped
+  const int rw0 = q0 + warp * 16, rw1 = (rw0 + 15 < N ? rw0 + 15 : N - 1);
+  const int h_lo = rw0 / Sw, h_hi = rw1 / Sw + Sh - 1;
+  const int w_lo = RH + (h_lo == rw1 / Sw ? rw0 - h_lo * Sw : 0), w_hi = RH + (h_lo == rw1 / Sw ? rw1 - h_lo * Sw : Sw - 1) + Sw - 1;
   for (int c0 = 0; c0 < RT; c0 += 64) {
     __syncthreads();
 #pragma unroll
@@ -557,10 +564,17 @@ relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __n
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-    qk_tile_mma(acc, qa, kb_s + kRpTile * 2, lane);
-    qk_tile_mma(acc, qa, kb_s, lane);
+    uint32_t need = 0u;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int g_lo = c0 + 16 * p, g_hi = g_lo + 15;
+      if (rw0 < N && ((g_hi >= h_lo && g_lo <= h_hi) || (g_hi >= w_lo && g_lo <= w_hi))) need |= 1u << p;
+    }
+    qk_tile_mma(acc, qa, kb_s + kRpTile * 2, lane, RT - c0, need);
+    qk_tile_mma(acc, qa, kb_s, lane, RT - c0, need);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      if (!((need >> (nt >> 1)) & 1u)) continue;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = c0 + nt * 8 + 2 * t + e;
