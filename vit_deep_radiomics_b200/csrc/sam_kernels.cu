@@ -516,10 +516,11 @@ attn_relpos_win_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const 
 // with q_vec the UNSCALED query of token q = qh*Sw + qw, head h (segment_anything add_decomposed_rel_pos).  Same MMA path as
 // the prologue of attn_relpos_kernel (queries x [rel_pos_h ; rel_pos_w], bf16 hi + lo parts), written to global memory: the
 // tcgen05 attention (vdr_flash_attn_relpos_fwd) reads its bias terms from this table.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __nv_bfloat16* __restrict__ rcat_hi,
                     const __nv_bfloat16* __restrict__ rcat_lo, float* __restrict__ rel, int N, int heads, int Sh, int Sw, float out_scale) {
-  __shared__ __align__(16) __nv_bfloat16 Kb[2 * kRpTile];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(smem_raw);       // [4 sub-chunks of 64 table rows][hi, lo][64][72]
   const int qb = blockIdx.x, h = blockIdx.y, bw = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qb * kRpBQ;
@@ -547,20 +548,24 @@ relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __n
   const int rw0 = q0 + warp * 16, rw1 = (rw0 + 15 < N ? rw0 + 15 : N - 1);
   const int h_lo = rw0 / Sw, h_hi = rw1 / Sw + Sh - 1;
   const int w_lo = RH + (h_lo == rw1 / Sw ? rw0 - h_lo * Sw : 0), w_hi = RH + (h_lo == rw1 / Sw ? rw1 - h_lo * Sw : Sw - 1) + Sw - 1;
-  for (int c0 = 0; c0 < RT; c0 += 64) {
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + i * 256, row = idx >> 3, seg = idx & 7, j = c0 + row;
-      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-      if (j < RT) {
-        hi = __ldg(reinterpret_cast<const uint4*>(rcat_hi + (int64_t)j * 64 + seg * 8));
-        lo = __ldg(reinterpret_cast<const uint4*>(rcat_lo + (int64_t)j * 64 + seg * 8));
-      }
-      *reinterpret_cast<uint4*>(Kb + row * kRpPitch + seg * 8) = hi;
-      *reinterpret_cast<uint4*>(Kb + kRpTile + row * kRpPitch + seg * 8) = lo;
+  // up to 256 table rows (four 64-row sub-chunks, both parts) land in shared memory in one cp.async wave behind one barrier:
+  // the load -> barrier -> MMA -> store chain used to run once per 64 rows and left the kernel latency-bound
+  for (int s0 = 0; s0 < RT; s0 += 256) {
+    if (s0 > 0) __syncthreads();
+    for (int idx = tid; idx < 256 * 8; idx += 256) {
+      const int row = idx >> 3, seg = idx & 7, j = s0 + row;
+      if (j - (j & 63) >= RT) break;                                   // whole sub-chunk beyond the tables (uniform per 64 rows)
+      const int bytes = j < RT ? 16 : 0;
+      const int64_t soff = (int64_t)(j < RT ? j : RT - 1) * 64 + seg * 8;
+      const uint32_t off = ((row >> 6) * 2 * kRpTile + (row & 63) * kRpPitch + seg * 8) * 2;
+      cp_async16(kb_s + off, rcat_hi + soff, bytes);
+      cp_async16(kb_s + kRpTile * 2 + off, rcat_lo + soff, bytes);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
+  for (int c0 = s0; c0 < RT && c0 < s0 + 256; c0 += 64) {
+    const uint32_t sub_s = kb_s + ((c0 - s0) >> 6) * 2 * kRpTile * 2;
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
@@ -570,8 +575,9 @@ relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __n
       const int g_lo = c0 + 16 * p, g_hi = g_lo + 15;
       if (rw0 < N && ((g_hi >= h_lo && g_lo <= h_hi) || (g_hi >= w_lo && g_lo <= w_hi))) need |= 1u << p;
     }
-    qk_tile_mma(acc, qa, kb_s + kRpTile * 2, lane, RT - c0, need);
-    qk_tile_mma(acc, qa, kb_s, lane, RT - c0, need);
+    if (need == 0u) continue;
+    qk_tile_mma(acc, qa, sub_s + kRpTile * 2, lane, RT - c0, need);
+    qk_tile_mma(acc, qa, sub_s, lane, RT - c0, need);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (!((need >> (nt >> 1)) & 1u)) continue;
@@ -589,6 +595,7 @@ relpos_table_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const __n
         }
       }
     }
+  }
   }
 }
 
@@ -648,7 +655,14 @@ extern "C" int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const voi
                 VDR_EALIGN, "vdr_relpos_tables: qkv must be (rows, >= 3*heads*64) with ld %% 8 == 0; tables 16-byte aligned");
   const int N = Sh * Sw;
   dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
-  relpos_table_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  constexpr int kTableSmem = 4 * 2 * kRpTile * (int)sizeof(__nv_bfloat16);      // 73,728 B
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(relpos_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableSmem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(relpos_table_kernel)");
+    configured = true;
+  }
+  relpos_table_kernel<<<grid, 256, kTableSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
       static_cast<const __nv_bfloat16*>(rcat_lo_bf16), rel, N, heads, Sh, Sw, out_scale);
   count_launch();
