@@ -439,3 +439,34 @@ def test_dataset_items_on_device_match_oracle_gather(cuda, augment):
         b = cpu_ds[i]
         assert a[0].is_cuda and a[1].is_cuda and a[3] == b[3] and torch.equal(a[2], b[2])
         assert torch.equal(a[0].cpu(), b[0]) and torch.equal(a[1].cpu(), b[1])
+
+
+def test_run_fold_trains_the_shipped_classifier_config(cuda, tmp_path):
+    """One fold of the training script (train_models.py:562-810) end to end on the device: dataset items gathered on the GPU,
+    the classifier of conf/parameters_models.yaml (feature_dim 256) trained for three epochs with the reference's accumulation
+    rule, evaluation pass, metric files, checkpoints.  The training loss of the fixed seed goes down."""
+    import json
+    from oracle import ref_shim
+    from vit_deep_radiomics_b200 import config_manager, train_models as tm
+    D = 256
+    df = tm.prepare_df(ref_shim.make_dataset_table(seed=11, D=D))
+    enc = tm.get_label_encoder(df)
+    cfg = config_manager.load_conf(project_dir=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert cfg["models"]["transformer"]["feature_dim"] == D
+    cfg["models"]["transformer"].update(patience=10, virtual_batch_size=4)
+    torch.manual_seed(3)
+    np.random.seed(3)
+    hist = tm.run_fold(cfg, "transformer", "ct", df[df.patient_id.isin(["P1", "P2"])].reset_index(drop=True),
+                       df[df.patient_id.isin(["P3", "P4"])].reset_index(drop=True), enc, "ct.h5", "pet.h5", str(tmp_path), kfold=2,
+                       device=str(cuda), store=ref_shim.H5_FILES, num_epochs=3)
+    assert [h["epoch"] for h in hist] == [0, 1, 2]
+    assert all(np.isfinite(h["train_loss"]) and np.isfinite(h["test_loss"]) for h in hist)
+    assert hist[-1]["train_loss"] < hist[0]["train_loss"]
+    for e in range(3):
+        for split in ("train", "test"):
+            rep = json.load(open(tmp_path / f"{split}_metrics_{e}.json"))
+            assert rep["split"] == split and rep["epoch"] == e and rep["kfold"] == 2 and 0.0 <= rep["ROC AUC"] <= 1.0
+    saved = sorted(p.name for p in tmp_path.glob("model_epoch_*.pth"))
+    assert saved and saved[0] == "model_epoch_0000.pth"          # epoch 0: target == the fold's mean
+    sd = torch.load(tmp_path / saved[-1], map_location="cpu")
+    assert "cls_token" in sd and sd["cls_token"].shape[-1] == D

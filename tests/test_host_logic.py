@@ -237,3 +237,50 @@ def test_extract_patient_features_augmentation_table():
     import pandas as pd
     lit = np.logical_not(np.logical_and(df["flip"] is None, df["angle"] == 0))
     assert np.array_equal(np.asarray(lit), df["augmentation"].values)
+
+
+def test_run_fold_epoch_loop_files_and_policy(tmp_path, monkeypatch):
+    """The fold loop of the training script (train_models.py:562-810) with a stub classifier on the CPU (the real one needs
+    CUDA; tests/test_gpu_pipeline.py runs it): accumulation / evaluation passes, the per-epoch metric files, checkpoints by the
+    target-metric rule, early stopping by patience."""
+    import json
+    from oracle import gather_np as G
+    from oracle import ref_shim
+    D = 12
+    df = tm.prepare_df(ref_shim.make_dataset_table(seed=9, D=D))
+    enc = tm.get_label_encoder(df)
+    cfg = config_manager.load_conf(project_dir=ROOT)
+    cfg["models"]["transformer"].update(feature_dim=D, patience=1, virtual_batch_size=3)
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(D, 2)
+
+        def forward(self, x):
+            cls = x.mean(1)
+            return self.lin(cls), cls
+
+    steps = []
+    monkeypatch.setattr(tm, "build_model", lambda *a, **k: Stub())
+    monkeypatch.setattr(torch.optim.AdamW, "step", lambda self, *a, **k: steps.append(1))
+    torch.manual_seed(0)
+    np.random.seed(0)
+    hist = tm.run_fold(cfg, "transformer", "ct", df[df.patient_id.isin(["P1", "P2"])].reset_index(drop=True),
+                       df[df.patient_id.isin(["P3", "P4"])].reset_index(drop=True), enc, "ct.h5", "pet.h5", str(tmp_path), kfold=0,
+                       device="cpu", store=ref_shim.H5_FILES, num_epochs=4,
+                       gather=lambda f, m, r, n, d: G.token_gather(f, m, r, n, d)["tokens"])
+    # the optimizer never moves (step patched out): every epoch has the same test metrics -> the first epoch stays the first
+    # maximum, so patience 1 stops the fold after its second epoch
+    assert [h["epoch"] for h in hist] == [0, 1]
+    for e in (0, 1):
+        for split in ("train", "test"):
+            rep = json.load(open(tmp_path / f"{split}_metrics_{e}.json"))
+            assert rep["split"] == split and rep["epoch"] == e and rep["kfold"] == 0 and 0.0 <= rep["ROC AUC"] <= 1.0
+            assert np.isfinite(rep["loss"]) and "macro avg" in rep
+    assert (tmp_path / "model_epoch_0000.pth").exists() and (tmp_path / "model_epoch_0001.pth").exists()   # target == the fold's mean
+    assert hist[0]["test_loss"] == hist[1]["test_loss"] and np.isfinite(hist[0]["train_loss"])
+    # optimizer steps: every min(virtual_batch, items) items and at the last item of each training pass
+    n_items = len(tm.PETCTDataset3D(df[df.patient_id.isin(["P1", "P2"])].reset_index(drop=True), enc, "ct.h5", "pet.h5",
+                                    use_augmentation=True, feature_dim=D, arch="transformer", store=ref_shim.H5_FILES, gather=lambda *a: None))
+    assert len(steps) == 2 * -(-n_items // 3)

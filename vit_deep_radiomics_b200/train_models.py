@@ -11,6 +11,7 @@ early-stopping rule of :727-810); plotting is outside the path.
 from __future__ import annotations
 
 import argparse
+import os
 
 import numpy as np
 import pandas as pd
@@ -344,6 +345,125 @@ def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, gra
     return total / max(len(samples), 1), scores
 
 
+def _forward_item(model, item, modality, device):
+    """One dataset item through the model as the reference's loops do (train_models.py:656-667): which token sequences go in
+    depends on the modality flag.  Returns (outputs, one-hot label on the device, patient id)."""
+    ct, pet, onehot, patient_id = item
+    label = torch.squeeze(torch.as_tensor(onehot)).to(device)
+    if modality in ("petct", "petchest"):
+        outputs = model(ct.to(device).unsqueeze(0), pet.to(device).unsqueeze(0))
+    elif modality == "pet":
+        outputs = model(pet.to(device).unsqueeze(0))
+    else:                                     # 'ct' / 'chest'
+        outputs = model(ct.to(device).unsqueeze(0))
+    return outputs, label, patient_id
+
+
+def _item_loss(criterion, outputs, label):
+    if isinstance(criterion, CrossModalFocalLoss):
+        return criterion(torch.squeeze(outputs[0]), torch.squeeze(outputs[2]), torch.squeeze(outputs[3]), label)
+    return criterion(torch.squeeze(outputs[0]), label)
+
+
+def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None, virtual_batch_size=32, grad_sync=None):
+    """One pass over ``dataset`` in ``order`` (batch size 1, as the reference's loaders, :639-640).  With ``optimizer`` it is
+    the training loop (:648-688: loss / iters_to_accumulate, step every iters_to_accumulate items and at the last one),
+    without it the evaluation loop (:689-718, no gradients).  Returns (mean loss, y_true list, y_score list, patient ids)."""
+    train = optimizer is not None
+    iters = min(virtual_batch_size, len(order)) if train else 1
+    model.train(train)
+    if train:
+        optimizer.zero_grad()
+    total, y_true, y_score, pids = 0.0, [], [], []
+    with torch.enable_grad() if train else torch.no_grad():
+        for i, idx in enumerate(order):
+            outputs, label, pid = _forward_item(model, dataset[int(idx)], modality, device)
+            loss = _item_loss(criterion, outputs, label) / iters
+            yt, ys = get_y_true_and_pred(y_true=label, y_pred=outputs[0], cpu=True)
+            y_true.append(yt)
+            y_score.append(ys)
+            pids.append(np.array([pid]))
+            total += float(loss.item()) * iters
+            if train:
+                loss.backward()
+                if (i + 1) % iters == 0 or i + 1 == len(order):
+                    if grad_sync is not None:
+                        grad_sync(model)
+                    optimizer.step()
+                    optimizer.zero_grad()
+    return total / max(len(order), 1), y_true, y_score, pids
+
+
+def run_fold(cfg, arch, modality, df_train, df_test, label_encoder, hdf5_ct_path, hdf5_pet_path, save_dir, kfold,
+             loss_func="focal", device="cuda:0", modality_a="pet", modality_b="ct", store=None, num_epochs=None, grad_sync=None,
+             gather=None):
+    """One fold of the reference's training script (train_models.py:562-810): model / criterion / AdamW + cosine schedule from
+    the YAML, train and test datasets (augmentation on / off), per epoch a shuffled training pass, an evaluation pass, the
+    scheduler step, the patient-weighted reports written to ``<split>_metrics_<epoch>.json``, a checkpoint when the target
+    metric is at least the fold's mean and early stopping after ``patience`` epochs without a new maximum.
+    The loss plot (plotly, :797-798) is not produced.  Returns the fold's history (one dict per epoch)."""
+    import json
+    from .models_archs import save_checkpoint
+    os.makedirs(save_dir, exist_ok=True)
+    cfg_model = cfg["models"][arch]
+    model = build_model(cfg, arch, modality, modality_a, modality_b, num_classes=2).to(device)
+    criterion = make_criterion(loss_func, device)
+    optimizer, scheduler = make_optimizer(model, cfg, arch)
+    kw = dict(label_encoder=label_encoder, hdf5_ct_path=hdf5_ct_path, hdf5_pet_path=hdf5_pet_path, modality_a=modality_a,
+              modality_b=modality_b, feature_dim=cfg_model["feature_dim"], arch=arch, device=device, store=store, gather=gather)
+    train_ds = PETCTDataset3D(df_train, use_augmentation=True, **kw)
+    test_ds = PETCTDataset3D(df_test, use_augmentation=False, **kw)
+    history = []
+    for epoch in range(num_epochs if num_epochs is not None else cfg_model["num_epochs"]):
+        order = torch.randperm(len(train_ds)).tolist()                                   # DataLoader(shuffle=True), :639
+        tr_loss, yt, ys, pid = run_epoch(model, train_ds, order, criterion, modality, device, optimizer,
+                                         cfg_model["virtual_batch_size"], grad_sync)
+        te_loss, yt2, ys2, pid2 = run_epoch(model, test_ds, range(len(test_ds)), criterion, modality, device)
+        scheduler.step()
+        train_report = split_report(yt, ys, pid, tr_loss, kfold, epoch, "train")
+        test_report = split_report(yt2, ys2, pid2, te_loss, kfold, epoch, "test")
+        for name, rep in (("train", train_report), ("test", test_report)):
+            with open(os.path.join(save_dir, f"{name}_metrics_{epoch}.json"), "w") as fh:
+                json.dump(rep, fh)
+        history.append(dict(kfold=kfold, epoch=epoch, train_loss=tr_loss, test_loss=te_loss, train_auc=train_report["ROC AUC"],
+                            test_auc=test_report["ROC AUC"], train_f1=train_report["macro avg"]["f1-score"],
+                            test_f1=test_report["macro avg"]["f1-score"]))
+        save, stop, _ = epoch_policy(history, cfg_model["patience"])
+        if save:
+            save_checkpoint(model, save_dir, epoch)
+        if stop:
+            print(f"Early stopping triggered after {epoch + 1} epochs")
+            break
+    return history
+
+
+def main(argv=None):
+    """The reference's training entry point (train_models.py:500-810) on the libvdr classifier: same flags, same relative
+    paths (../data/features/features_masks_<modality>.hdf5, ../data/features/petct.parquet, ../models/<experiment>/...)."""
+    args = build_arg_parser().parse_args(argv)
+    from .config_manager import load_conf
+    modality_a, modality_b = "pet", ("chest" if "chest" in args.modality else "ct")
+    hdf5_pet = os.path.join("..", "data", "features", f"features_masks_{modality_a}.hdf5")
+    hdf5_ct = os.path.join("..", "data", "features", f"features_masks_{modality_b}.hdf5")
+    models_dir = os.path.join("..", "models", args.experiment, f"{args.backbone}_{args.arch}_{args.dataset}")
+    cfg = load_conf()
+    df = pd.read_parquet(os.path.join("..", "data", "features", "petct.parquet"))
+    df["flip"] = df["flip"].astype(str)
+    df.reset_index(drop=True, inplace=True)
+    df = prepare_df(df, modality_a, modality_b)
+    encoder = get_label_encoder(df)
+    folds = cfg["kfold_patients"][modality_b][args.dataset]
+    histories = {}
+    for kfold in folds:
+        split = folds[kfold]
+        df_train = df[df["patient_id"].isin(split["train"])].reset_index(drop=True)
+        df_test = df[df["patient_id"].isin(split["test"])].reset_index(drop=True)
+        save_dir = os.path.join(models_dir, args.modality, f"kfold_{kfold}")
+        histories[kfold] = run_fold(cfg, args.arch, args.modality, df_train, df_test, encoder, hdf5_ct, hdf5_pet, save_dir, kfold,
+                                    loss_func=args.loss, device=f"cuda:{args.gpu}", modality_a=modality_a, modality_b=modality_b)
+    return histories
+
+
 def build_arg_parser():
     """Same flags as the reference CLI (train_models.py:500-515)."""
     p = argparse.ArgumentParser(description="Train the point-cloud transformer for lung nodule classification")
@@ -355,3 +475,7 @@ def build_arg_parser():
     p.add_argument("-l", "--loss", type=str, default="focal")
     p.add_argument("-e", "--experiment", type=str, default="exp")
     return p
+
+
+if __name__ == "__main__":
+    main()
