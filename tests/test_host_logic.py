@@ -284,3 +284,44 @@ def test_run_fold_epoch_loop_files_and_policy(tmp_path, monkeypatch):
     n_items = len(tm.PETCTDataset3D(df[df.patient_id.isin(["P1", "P2"])].reset_index(drop=True), enc, "ct.h5", "pet.h5",
                                     use_augmentation=True, feature_dim=D, arch="transformer", store=ref_shim.H5_FILES, gather=lambda *a: None))
     assert len(steps) == 2 * -(-n_items // 3)
+
+
+def test_extraction_main_walks_the_metadata_table(tmp_path, monkeypatch):
+    """The extraction script's HDF5 branch (tfds_dense_descriptor.py:364-490) with the backbone, the HDF5 reader and writer
+    stubbed: which (patient, modality) pairs are processed, labels from the `egfr` column, output names, resume by parquet."""
+    import pandas as pd
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    meta = pd.DataFrame({"patient_id": ["a1", "a2", "b1", "b2"], "egfr": ["Mutant", "Wildtype", "Mutant", "Wildtype"],
+                         "dataset": ["stanford", "stanford", "santa_maria", "santa_maria"], "has_petct": [True, False, True, True]})
+    csv = tmp_path / "meta.csv"
+    meta.to_csv(csv, index=False)
+    calls, saved = [], []
+    rng = np.random.default_rng(0)
+
+    def voxels(ds_path, patient_id, modality):
+        m = np.zeros((12, 12, 2), bool)
+        m[4:8, 3:9] = True
+        return rng.random((12, 12, 2)).astype(np.float32), m, np.array([0.8, 0.8, 0.8])
+
+    def gen(model, img_3d, mask_3d, tqdm_text, display=False):
+        calls.append(tqdm_text)
+        return [np.zeros((2, 2, 4), np.float32)] * 2, [np.ones((2, 2), bool)] * 2
+
+    monkeypatch.setattr(tdd, "load_model", lambda name, path=None: ("model", name, path))
+    monkeypatch.setattr(tdd, "get_voxels", voxels)
+    monkeypatch.setattr(tdd, "generate_features", gen)
+    monkeypatch.setattr(tdd, "save_features", lambda f, feats, masks, pid: saved.append((os.path.basename(f), pid, len(feats))))
+    out = tmp_path / "features"
+    argv = ["-mn", "medsam", "-mp", "w.pth", "-f", str(out), "-h5", "vol.h5", "-df", str(csv), "-mod", "ct"]
+    tdd.main(argv)
+    files = sorted(str(p.relative_to(out)) for p in out.rglob("*.parquet"))
+    assert files == ["santa_maria_dataset/b1_ct.parquet", "santa_maria_dataset/b1_pet.parquet", "santa_maria_dataset/b2_ct.parquet",
+                     "santa_maria_dataset/b2_pet.parquet", "stanford_dataset/a1_ct.parquet", "stanford_dataset/a1_pet.parquet"]
+    assert len(calls) == 6 * 12 and len(saved) == 6 and all(n == 24 for _, _, n in saved)
+    assert {f for f, _, _ in saved} == {"features_masks_ct.hdf5", "features_masks_pet.hdf5"}
+    df = pd.read_parquet(out / "stanford_dataset" / "a1_ct.parquet")
+    assert (df["label"] == 1).all() and (df["dataset"] == "stanford").all() and (df["modality"] == "ct").all() and len(df) == 24
+    assert (pd.read_parquet(out / "santa_maria_dataset" / "b2_pet.parquet")["label"] == 0).all()
+    n = len(calls)
+    tdd.main(argv)                                   # every parquet exists: nothing is recomputed (:424)
+    assert len(calls) == n

@@ -405,3 +405,42 @@ def build_arg_parser():
     p.add_argument("-df", "--df_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets.csv"))
     p.add_argument("-mod", "--modality", type=str, default="ct")
     return p
+
+
+def process_patient(model, ds_path, patient_id, modality, label, dataset_name, df_path, features_file, voxels=None):
+    """One (patient, modality) of the reference's HDF5 branch (:449-490): read the isotropic volume, run the augmentation grid
+    through the backbone, write the metadata parquet and append the feature maps / masks to the modality's HDF5 file.
+    ``voxels`` = (img, mask, spatial_res) replaces the HDF5 read (``get_voxels`` needs h5py)."""
+    img_raw, mask_raw, spatial_res = voxels if voxels is not None else get_voxels(ds_path, patient_id, modality)
+    df, all_features, all_masks = extract_patient_features(model, img_raw, mask_raw, patient_id, label, dataset_name, modality, spatial_res)
+    df.to_parquet(df_path)
+    save_features(features_file, all_features, all_masks, patient_id)
+    return df
+
+
+def main(argv=None):
+    """The reference's extraction entry point for the HDF5 dataset (:364-490, ``use_tfds`` False; the tensorflow_datasets branch
+    is not provided): same flags, same outputs -- ``<feature_folder>/<dataset>/<patient>_<modality>.parquet`` and
+    ``<feature_folder>/features_masks_<modality>.hdf5``; patients whose parquet exists are skipped (:424)."""
+    import pandas as pd
+    args = build_arg_parser().parse_args(argv)
+    model = load_model(args.model_name, args.model_path)
+    modalities = ["pet", args.modality]
+    meta = pd.read_csv(args.df_path)
+    meta["label"] = (meta["egfr"] == "Mutant").astype(int)                               # :398
+    patient2label = dict(zip(meta["patient_id"], meta["label"]))
+    meta = meta[meta[f'has_{"".join(modalities)}']].reset_index(drop=True)                  # :400
+    for dataset_name in ("santa_maria_dataset", "stanford_dataset"):
+        features_dir = os.path.join(args.feature_folder, dataset_name)
+        os.makedirs(features_dir, exist_ok=True)
+        short = dataset_name.replace("_dataset", "")
+        for patient_id in list(meta[meta["dataset"] == short]["patient_id"].unique()):
+            for modality in modalities:
+                df_path = os.path.join(features_dir, f"{patient_id}_{modality}.parquet")
+                features_file = os.path.join(args.feature_folder, f"features_masks_{modality}.hdf5")
+                if not os.path.exists(df_path):
+                    process_patient(model, args.hdf5_path, patient_id, modality, patient2label[patient_id], dataset_name, df_path, features_file)
+
+
+if __name__ == "__main__":
+    main()
