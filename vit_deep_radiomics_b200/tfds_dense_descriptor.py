@@ -397,12 +397,13 @@ def get_voxels(hdf5_path, patient_id, modality):
 def build_arg_parser():
     """Same flags as the reference CLI (tfds_dense_descriptor.py:365-382)."""
     p = argparse.ArgumentParser(description="ViT patch embeddings of the lung_radiomics datasets (B200-native)")
-    p.add_argument("-mn", "--model_name", type=str, default="vit_b16", help="medsam | dinov2 | vit_s16 | vit_b16 | vit_l14")
-    p.add_argument("-mp", "--model_path", type=str, default=None)
+    p.add_argument("-mn", "--model_name", type=str, default="medsam", help="medsam (the reference's default) | dinov2 | vit_s16 | vit_b16 | vit_l14")
+    p.add_argument("-mp", "--model_path", type=str, default=None,
+                   help="state-dict .pth (the reference defaults to models/backbones/medsam/medsam_vit_b.pth); omitted = seeded random weights")
     p.add_argument("-d", "--dataset_path", type=str, default=os.path.join("data", "lung_radiomics"))
     p.add_argument("-f", "--feature_folder", type=str, default=os.path.join("data", "features"))
-    p.add_argument("-h5", "--hdf5_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets.hdf5"))
-    p.add_argument("-df", "--df_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets.csv"))
+    p.add_argument("-h5", "--hdf5_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets_isotropic.hdf5"))
+    p.add_argument("-df", "--df_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets_isotropic.csv"))
     p.add_argument("-mod", "--modality", type=str, default="ct")
     return p
 
