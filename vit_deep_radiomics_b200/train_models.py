@@ -469,11 +469,11 @@ def build_arg_parser():
     p = argparse.ArgumentParser(description="Train the point-cloud transformer for lung nodule classification")
     p.add_argument("-a", "--arch", type=str, default="transformer")
     p.add_argument("-d", "--dataset", type=str, default="stanford")
-    p.add_argument("-b", "--backbone", type=str, default="vit_b16")
-    p.add_argument("-m", "--modality", type=str, default="ct")
+    p.add_argument("-b", "--backbone", type=str, default="medsam")
+    p.add_argument("-m", "--modality", type=str, default="petchest")
     p.add_argument("-gpu", "--gpu", type=int, default=0)
     p.add_argument("-l", "--loss", type=str, default="focal")
-    p.add_argument("-e", "--experiment", type=str, default="exp")
+    p.add_argument("-e", "--experiment", type=str, default="petct")
     return p
 
 
