@@ -255,14 +255,14 @@ class SamImageEncoder:
         return ws["OUT"]
 
     def dense_descriptors(self, images: torch.Tensor) -> torch.Tensor:
-        """images (B, 3, H, W) or (B, H, W) f32 CUDA -> (B, H/16, W/16, out_chans) f32: get_dense_descriptor's result
+        """images (B, 3, H, W) or (B, H, W) f32 CUDA -> (B, H/16, W/16, out_chans) f32 (a copy): get_dense_descriptor's result
         for 'medsam' (:123-126), batched."""
         B = images.shape[0]
         strides = (images.stride(0), 0, images.stride(1), images.stride(2)) if images.dim() == 3 else images.stride()
         if tuple(images.shape[-2:]) != self.img_hw:
             raise ValueError(f"expected images of {self.img_hw}, got {tuple(images.shape[-2:])}")
         tok = self.forward_tokens(images, strides, B)
-        return tok.view(B, self.grid[0], self.grid[1], self.feature_dim)
+        return tok.view(B, self.grid[0], self.grid[1], self.feature_dim).clone()     # a copy: the workspace is reused by the next call
 
     def flops_per_slice(self) -> float:
         """Algorithmic flops of one image: patch embedding, per block 24*N*d^2 (+ the window padding rows of the qkv GEMM
