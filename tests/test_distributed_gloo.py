@@ -66,3 +66,54 @@ def test_shards_partition():
             spans = [shard_range(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert sorted(sum((shard_modulo(n, r, w) for r in range(w)), [])) == list(range(n))
+
+
+def _dp_worker(rank, world, port, out):
+    """Data-parallel run_epoch (world size 2, gloo, CPU stub classifier + oracle gather) == the single-process epoch."""
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import gather_np as G
+    from oracle import ref_shim
+    from vit_deep_radiomics_b200 import train_models as tm
+    D = 12
+    df = tm.prepare_df(ref_shim.make_dataset_table(seed=4, D=D))
+    enc = tm.get_label_encoder(df)
+    ds = tm.PETCTDataset3D(df, enc, "ct.h5", "pet.h5", use_augmentation=False, feature_dim=D, arch="transformer", store=ref_shim.H5_FILES,
+                           gather=lambda f, m, r, n, d: G.token_gather(f, m, r, n, d)["tokens"])
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(D, 2)
+
+        def forward(self, x):
+            cls = x.mean(1)
+            return self.lin(cls), cls
+
+    def epoch(r, w, sync):
+        torch.manual_seed(5)
+        model = Stub()
+        opt = torch.optim.SGD(model.parameters(), lr=0.1)
+        crit = tm.FocalLoss(alpha=torch.tensor([0.25, 0.75]), gamma=2.0)
+        order = torch.randperm(len(ds), generator=torch.Generator().manual_seed(1)).tolist()
+        res = tm.run_epoch(model, ds, order, crit, "ct", "cpu", opt, virtual_batch_size=4, grad_sync=sync, rank=r, world=w)
+        ev = tm.run_epoch(model, ds, range(len(ds)), crit, "ct", "cpu", rank=r, world=w)
+        return model, res, ev
+
+    m_dp, res_dp, ev_dp = epoch(rank, world, allreduce_grads)
+    m_1, res_1, ev_1 = epoch(0, 1, None)
+    ok_w = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(m_dp.state_dict().values(), m_1.state_dict().values()))
+    ok_loss = abs(res_dp[0] - res_1[0]) < 1e-6 and abs(ev_dp[0] - ev_1[0]) < 1e-6
+    ok_n = len(res_dp[1]) == len(res_1[1]) == len(ds) and sorted(np.concatenate(ev_dp[3]).tolist()) == sorted(np.concatenate(ev_1[3]).tolist())
+    out[rank] = (ok_w, ok_loss, ok_n, len(ds))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_epoch_equals_single_process():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        assert out[rank][:3] == (True, True, True) and out[rank][3] > 4, (rank, out[rank])

@@ -365,48 +365,73 @@ def _item_loss(criterion, outputs, label):
     return criterion(torch.squeeze(outputs[0]), label)
 
 
-def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None, virtual_batch_size=32, grad_sync=None):
+def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None, virtual_batch_size=32, grad_sync=None,
+              rank=0, world=1):
     """One pass over ``dataset`` in ``order`` (batch size 1, as the reference's loaders, :639-640).  With ``optimizer`` it is
     the training loop (:648-688: loss / iters_to_accumulate, step every iters_to_accumulate items and at the last one),
-    without it the evaluation loop (:689-718, no gradients).  Returns (mean loss, y_true list, y_score list, patient ids)."""
+    without it the evaluation loop (:689-718, no gradients).
+
+    Data parallel (``world`` > 1): an accumulation window is the same ``iters_to_accumulate`` consecutive
+    items of ``order`` on every rank; rank r takes the window's items r, r + world, ...; the loss keeps its GLOBAL 1 / iters
+    scale (:674), so ``grad_sync`` (``distributed.allreduce_grads``: one sum over the ranks) right before each optimizer step
+    yields the single-process gradients.  ``order`` must be the same list on every rank.  Labels / scores / ids / the loss
+    are gathered, so every rank returns the whole epoch's records.
+    Returns (mean loss, y_true list, y_score list, patient ids)."""
+    import torch.distributed as dist
     train = optimizer is not None
-    iters = min(virtual_batch_size, len(order)) if train else 1
+    order = list(order)
+    iters = min(virtual_batch_size, len(order)) if train else max(len(order), 1)
     model.train(train)
     if train:
         optimizer.zero_grad()
     total, y_true, y_score, pids = 0.0, [], [], []
     with torch.enable_grad() if train else torch.no_grad():
-        for i, idx in enumerate(order):
-            outputs, label, pid = _forward_item(model, dataset[int(idx)], modality, device)
-            loss = _item_loss(criterion, outputs, label) / iters
-            yt, ys = get_y_true_and_pred(y_true=label, y_pred=outputs[0], cpu=True)
-            y_true.append(yt)
-            y_score.append(ys)
-            pids.append(np.array([pid]))
-            total += float(loss.item()) * iters
+        for w0 in range(0, len(order), iters):
+            for idx in order[w0:w0 + iters][rank::world]:
+                outputs, label, pid = _forward_item(model, dataset[int(idx)], modality, device)
+                loss = _item_loss(criterion, outputs, label) / (iters if train else 1)
+                yt, ys = get_y_true_and_pred(y_true=label, y_pred=outputs[0], cpu=True)
+                y_true.append(yt)
+                y_score.append(ys)
+                pids.append(np.array([pid]))
+                total += float(loss.item()) * (iters if train else 1)           # :681, :716
+                if train:
+                    loss.backward()
             if train:
-                loss.backward()
-                if (i + 1) % iters == 0 or i + 1 == len(order):
-                    if grad_sync is not None:
-                        grad_sync(model)
-                    optimizer.step()
-                    optimizer.zero_grad()
+                if grad_sync is not None:
+                    grad_sync(model)
+                optimizer.step()
+                optimizer.zero_grad()
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (total, y_true, y_score, pids))
+        total = sum(p[0] for p in parts)
+        y_true, y_score, pids = ([x for p in parts for x in p[k]] for k in (1, 2, 3))
     return total / max(len(order), 1), y_true, y_score, pids
 
 
 def run_fold(cfg, arch, modality, df_train, df_test, label_encoder, hdf5_ct_path, hdf5_pet_path, save_dir, kfold,
              loss_func="focal", device="cuda:0", modality_a="pet", modality_b="ct", store=None, num_epochs=None, grad_sync=None,
-             gather=None):
+             gather=None, rank=0, world=1):
     """One fold of the reference's training script (train_models.py:562-810): model / criterion / AdamW + cosine schedule from
     the YAML, train and test datasets (augmentation on / off), per epoch a shuffled training pass, an evaluation pass, the
     scheduler step, the patient-weighted reports written to ``<split>_metrics_<epoch>.json``, a checkpoint when the target
     metric is at least the fold's mean and early stopping after ``patience`` epochs without a new maximum.
-    The loss plot (plotly, :797-798) is not produced.  Returns the fold's history (one dict per epoch)."""
+    The loss plot (plotly, :797-798) is not produced.  Returns the fold's history (one dict per epoch).
+    ``world`` > 1 (one process per GPU, process group initialised): the fold is data parallel over the virtual batch
+    (``run_epoch``); rank 0's initial weights and epoch orders are broadcast, rank 0 alone writes files."""
     import json
+    import torch.distributed as dist
+    from .distributed import allreduce_grads
     from .models_archs import save_checkpoint
-    os.makedirs(save_dir, exist_ok=True)
+    if rank == 0:
+        os.makedirs(save_dir, exist_ok=True)
     cfg_model = cfg["models"][arch]
     model = build_model(cfg, arch, modality, modality_a, modality_b, num_classes=2).to(device)
+    if world > 1:
+        for p_ in model.parameters():
+            dist.broadcast(p_.data, 0)
+        grad_sync = grad_sync or allreduce_grads
     criterion = make_criterion(loss_func, device)
     optimizer, scheduler = make_optimizer(model, cfg, arch)
     kw = dict(label_encoder=label_encoder, hdf5_ct_path=hdf5_ct_path, hdf5_pet_path=hdf5_pet_path, modality_a=modality_a,
@@ -415,33 +440,41 @@ def run_fold(cfg, arch, modality, df_train, df_test, label_encoder, hdf5_ct_path
     test_ds = PETCTDataset3D(df_test, use_augmentation=False, **kw)
     history = []
     for epoch in range(num_epochs if num_epochs is not None else cfg_model["num_epochs"]):
-        order = torch.randperm(len(train_ds)).tolist()                                   # DataLoader(shuffle=True), :639
-        tr_loss, yt, ys, pid = run_epoch(model, train_ds, order, criterion, modality, device, optimizer,
-                                         cfg_model["virtual_batch_size"], grad_sync)
-        te_loss, yt2, ys2, pid2 = run_epoch(model, test_ds, range(len(test_ds)), criterion, modality, device)
+        order = [torch.randperm(len(train_ds)).tolist()]                                 # DataLoader(shuffle=True), :639
+        if world > 1:
+            dist.broadcast_object_list(order, 0)
+        tr_loss, yt, ys, pid = run_epoch(model, train_ds, order[0], criterion, modality, device, optimizer,
+                                         cfg_model["virtual_batch_size"], grad_sync, rank, world)
+        te_loss, yt2, ys2, pid2 = run_epoch(model, test_ds, range(len(test_ds)), criterion, modality, device, rank=rank, world=world)
         scheduler.step()
         train_report = split_report(yt, ys, pid, tr_loss, kfold, epoch, "train")
         test_report = split_report(yt2, ys2, pid2, te_loss, kfold, epoch, "test")
         for name, rep in (("train", train_report), ("test", test_report)):
-            with open(os.path.join(save_dir, f"{name}_metrics_{epoch}.json"), "w") as fh:
-                json.dump(rep, fh)
+            if rank == 0:
+                with open(os.path.join(save_dir, f"{name}_metrics_{epoch}.json"), "w") as fh:
+                    json.dump(rep, fh)
         history.append(dict(kfold=kfold, epoch=epoch, train_loss=tr_loss, test_loss=te_loss, train_auc=train_report["ROC AUC"],
                             test_auc=test_report["ROC AUC"], train_f1=train_report["macro avg"]["f1-score"],
                             test_f1=test_report["macro avg"]["f1-score"]))
         save, stop, _ = epoch_policy(history, cfg_model["patience"])
-        if save:
+        if save and rank == 0:
             save_checkpoint(model, save_dir, epoch)
         if stop:
-            print(f"Early stopping triggered after {epoch + 1} epochs")
+            if rank == 0:
+                print(f"Early stopping triggered after {epoch + 1} epochs")
             break
     return history
 
 
 def main(argv=None):
     """The reference's training entry point (train_models.py:500-810) on the libvdr classifier: same flags, same relative
-    paths (../data/features/features_masks_<modality>.hdf5, ../data/features/petct.parquet, ../models/<experiment>/...)."""
+    paths (../data/features/features_masks_<modality>.hdf5, ../data/features/petct.parquet, ../models/<experiment>/...).
+    Launched with torchrun (one process per GPU) every fold trains data parallel: NCCL all-reduce of the gradients per optimizer step."""
     args = build_arg_parser().parse_args(argv)
     from .config_manager import load_conf
+    from .distributed import init_distributed
+    rank, world = init_distributed()                       # under torchrun: data parallel over the virtual batch (SURVEY 8e)
+    device = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}" if world > 1 else f"cuda:{args.gpu}"
     modality_a, modality_b = "pet", ("chest" if "chest" in args.modality else "ct")
     hdf5_pet = os.path.join("..", "data", "features", f"features_masks_{modality_a}.hdf5")
     hdf5_ct = os.path.join("..", "data", "features", f"features_masks_{modality_b}.hdf5")
@@ -460,7 +493,7 @@ def main(argv=None):
         df_test = df[df["patient_id"].isin(split["test"])].reset_index(drop=True)
         save_dir = os.path.join(models_dir, args.modality, f"kfold_{kfold}")
         histories[kfold] = run_fold(cfg, args.arch, args.modality, df_train, df_test, encoder, hdf5_ct, hdf5_pet, save_dir, kfold,
-                                    loss_func=args.loss, device=f"cuda:{args.gpu}", modality_a=modality_a, modality_b=modality_b)
+                                    loss_func=args.loss, device=device, modality_a=modality_a, modality_b=modality_b, rank=rank, world=world)
     return histories
 
 
