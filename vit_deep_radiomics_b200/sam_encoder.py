@@ -8,9 +8,10 @@
   only runs the 14x14 strided convolution.
 
 State-dict keys are segment_anything's / DINOv2's, with or without the ``image_encoder.`` prefix of a full SAM checkpoint,
-so ``medsam_vit_b.pth`` loads unchanged.  The GEMMs are the tcgen05 kernel (vdr_gemm); the attention with bias is the
-mma.sync kernel of this row (vdr_attn_relpos_fwd: bias terms built on chip, cp.async + ldmatrix feed), not yet on tcgen05.
-There is no CPU path: every op is a libvdr call on CUDA tensors.
+so ``medsam_vit_b.pth`` loads unchanged.  The GEMMs are the tcgen05 kernel (vdr_gemm, LayerNorms folded into their epilogues);
+the global blocks' attention is the tcgen05 flash kernel instantiated with the bias (vdr_relpos_tables +
+vdr_flash_attn_relpos_fwd), the windowed blocks read their 14x14 windows in place (vdr_attn_relpos_windows_fwd, mma.sync:
+partition, attention and unpartition in one launch).  There is no CPU path: every op is a libvdr call on CUDA tensors.
 """
 from __future__ import annotations
 
