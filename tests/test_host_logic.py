@@ -153,6 +153,8 @@ def test_sam_encoder_host_side():
     a, b = sam_encoder.init_sam_state_dict(tiny, (256, 256), seed=3), sam_fp32.init_sam_state_dict(tiny, (256, 256), seed=3)
     assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
     assert a["blocks.0.attn.rel_pos_h"].shape == (27, 64) and a["blocks.1.attn.rel_pos_h"].shape == (31, 64)
+    assert sam_encoder.SAM_CONFIGS == sam_fp32.SAM_CONFIGS
+    assert abs(sam_encoder.sam_flops_per_slice(cfg, (64, 64)) / 1e9 - 941.727) < 0.01
     full = {"image_encoder." + k: v for k, v in a.items()} | {"mask_decoder.x": torch.zeros(1)}
     assert sam_encoder._strip_prefix(full, "image_encoder.").keys() == a.keys()
     r = sam_encoder._fit_rel_pos(a["blocks.0.attn.rel_pos_h"], 16)                      # 27 -> 31 rows, linear

@@ -68,6 +68,25 @@ def init_sam_state_dict(cfg: dict, img_hw, seed: int = 1234) -> dict:
     return w
 
 
+def sam_flops_per_slice(cfg: dict, grid) -> float:
+    """Algorithmic flops of one image through the SAM encoder (mul-add = 2; softmax / LayerNorm / GELU excluded, SURVEY.md
+    section 8d convention): patch embedding, per block 24*N*d^2 for qkv / proj / MLP (the padding rows of partitioned windows are
+    NOT counted), 4*n^2*d per attention extent plus the decomposed rel-pos terms 2*n*d*(Sh+Sw), neck 1x1 and 3x3 convolutions.
+    medsam at 64 x 64 tokens: 941.7 GFLOP (block GEMMs + patch embedding 700.6, global attention 209.4, windows 25.3, neck 6.4)."""
+    d, oc, win, p = cfg["dim"], cfg["out_chans"], cfg["window"], cfg["patch"]
+    gh, gw = grid
+    N = gh * gw
+    f = 2.0 * N * (3 * p * p) * d
+    for i in range(cfg["depth"]):
+        f += 24.0 * N * d * d
+        if i in cfg["global_attn"]:
+            f += 4.0 * N * N * d + 2.0 * N * d * (gh + gw)
+        else:
+            nwin = (-(-gh // win)) * (-(-gw // win))
+            f += nwin * (4.0 * (win * win) ** 2 * d + 2.0 * win * win * d * 2 * win)
+    return f + 2.0 * N * d * oc + 2.0 * N * 9 * oc * oc
+
+
 def _strip_prefix(sd: dict, prefix: str) -> dict:
     if any(k.startswith(prefix) for k in sd):
         return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
@@ -266,21 +285,8 @@ class SamImageEncoder:
         return tok.view(B, self.grid[0], self.grid[1], self.feature_dim).clone()     # a copy: the workspace is reused by the next call
 
     def flops_per_slice(self) -> float:
-        """Algorithmic flops of one image: patch embedding, per block 24*N*d^2 (+ the window padding rows of the qkv GEMM
-        are NOT counted) and 4*n^2*d per attention extent, rel-pos terms, neck."""
-        cfg = self.cfg
-        d, oc, win = cfg["dim"], cfg["out_chans"], cfg["window"]
-        gh, gw = self.grid
-        N = gh * gw
-        f = 2.0 * N * self.K * d
-        for i in range(cfg["depth"]):
-            f += 24.0 * N * d * d
-            if i in cfg["global_attn"]:
-                f += 4.0 * N * N * d + 2.0 * N * d * (gh + gw)
-            else:
-                nwin = (-(-gh // win)) * (-(-gw // win))
-                f += nwin * (4.0 * (win * win) ** 2 * d + 2.0 * win * win * d * 2 * win)
-        return f + 2.0 * N * d * oc + 2.0 * N * 9 * oc * oc
+        """Algorithmic flops of one image (``sam_flops_per_slice``)."""
+        return sam_flops_per_slice(self.cfg, self.grid)
 
 
 class DinoV2PatchEmbed:
