@@ -117,3 +117,50 @@ def test_data_parallel_epoch_equals_single_process():
     mp.spawn(_dp_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     for rank in range(world):
         assert out[rank][:3] == (True, True, True) and out[rank][3] > 4, (rank, out[rank])
+
+
+def _fold_worker(rank, world, port, out, save_dir):
+    """run_fold at world size 2 (gloo, CPU stub classifier): rank 0's weights / epoch orders are broadcast, every rank sees the
+    gathered records (identical histories), rank 0 alone writes the metric files and checkpoints."""
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import gather_np as G
+    from oracle import ref_shim
+    from vit_deep_radiomics_b200 import config_manager, train_models as tm
+    D = 12
+    df = tm.prepare_df(ref_shim.make_dataset_table(seed=6, D=D))
+    enc = tm.get_label_encoder(df)
+    cfg = config_manager.load_conf(project_dir=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    cfg["models"]["transformer"].update(feature_dim=D, patience=5, virtual_batch_size=4)
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(D, 2)
+
+        def forward(self, x):
+            cls = x.mean(1)
+            return self.lin(cls), cls
+
+    tm.build_model = lambda *a, **k: Stub()           # each rank initialises differently (seed below): the broadcast must align them
+    torch.manual_seed(100 + rank)
+    np.random.seed(200 + rank)
+    my_dir = os.path.join(save_dir, f"rank{rank}")
+    hist = tm.run_fold(cfg, "transformer", "ct", df[df.patient_id.isin(["P1", "P2"])].reset_index(drop=True),
+                       df[df.patient_id.isin(["P3", "P4"])].reset_index(drop=True), enc, "ct.h5", "pet.h5", my_dir, kfold=1,
+                       device="cpu", store=ref_shim.H5_FILES, num_epochs=2, rank=rank, world=world,
+                       gather=lambda f, m, r, n, d: G.token_gather(f, m, r, n, d)["tokens"])
+    out[rank] = ([(h["epoch"], round(h["train_loss"], 9), round(h["test_loss"], 9), round(h["test_auc"], 9)) for h in hist],
+                 sorted(os.listdir(my_dir)) if os.path.isdir(my_dir) else None)
+    dist.destroy_process_group()
+
+
+def test_run_fold_world_size_2(tmp_path):
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fold_worker, args=(world, _free_port(), out, str(tmp_path)), nprocs=world, join=True)
+    assert out[0][0] == out[1][0] and len(out[0][0]) == 2              # same gathered records -> same history on both ranks
+    assert out[1][1] is None                                           # rank 1 writes nothing
+    assert {"train_metrics_0.json", "test_metrics_0.json", "train_metrics_1.json", "test_metrics_1.json", "model_epoch_0000.pth"} <= set(out[0][1])
