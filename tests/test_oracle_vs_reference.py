@@ -227,3 +227,21 @@ def test_hu_to_rgb_and_flip_rotate_match_reference():
     assert np.array_equal(tdd.normalize_volume(hu, "ct", "medsam"), ref.apply_window_ct(hu, width=800, level=40))
     assert np.array_equal(tdd.normalize_volume(hu, "ct", "dinov2"), vu.hu_to_rgb_vectorized(hu) / 255.0)
     assert np.array_equal(tdd.normalize_volume(np.abs(hu), "pet", "medsam"), np.abs(hu) / np.abs(hu).max())
+
+
+def test_report_text_and_param_count_match_reference(capsys):
+    """print_classification_report (:185-218) yields the same text for the same report dict; get_number_of_params (:450-453)."""
+    from vit_deep_radiomics_b200 import train_models as tm
+    ref = ref_shim.load_reference("train_models")
+    rng = np.random.default_rng(1)
+    y_true = [np.array([int(v)]) for v in rng.integers(0, 2, 40)]
+    y_score = [np.array([[1 - p, p]]) for p in rng.random(40)]
+    pids = [np.array([f"p{int(v)}"]) for v in rng.integers(0, 7, 40)]
+    rep = tm.split_report(y_true, y_score, pids, 0.1234567, 3, 7, "test")
+    want = ref.print_classification_report(dict(rep))
+    got = tm.print_classification_report(dict(rep), echo=False)
+    capsys.readouterr()
+    assert got == want
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    lin[0].bias.requires_grad_(False)
+    assert tm.get_number_of_params(lin) == int(ref.get_number_of_params(lin)) == 15 + 6 + 2

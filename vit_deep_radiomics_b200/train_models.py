@@ -257,6 +257,36 @@ def get_sampler_weights(train_labels):
     return [1 / per_value[v] for v in train_labels]
 
 
+def get_number_of_params(model):
+    """reference: train_models.py:450-453 -- number of trainable parameters."""
+    return int(sum(p.numel() for p in model.parameters() if p.requires_grad))
+
+
+#: the scalar entries a split report carries next to sklearn's per-class rows (reference: train_models.py:196-197)
+REPORT_GLOBALS = ("accuracy", "ROC AUC", "kfold", "loss", "epoch", "split")
+
+
+def print_classification_report(report, global_metrics=None, echo=True):
+    """reference: train_models.py:185-218 -- the text form of a split report: one line with the scalar metrics, then sklearn's
+    per-class table, both rendered by pandas (the string the reference keeps in its metrics table, :782-783).
+    Same text as the reference for the same dict; ``echo=False`` skips the print."""
+    names = list(global_metrics) if global_metrics is not None else list(REPORT_GLOBALS)
+    table = pd.DataFrame(report).round(3)
+    n_cols = len(table.index)                         # precision / recall / f1-score / support
+    table = table.T.astype(str)
+    support = table.loc["macro avg"].iloc[-1]
+    for name in names:                                # a scalar fills its whole column: keep one copy under 'f1-score'
+        value = table.loc[name].iloc[-2]
+        table.loc[name] = [" "] * (n_cols - 2) + [value, support]
+    per_class = table.loc[[r for r in table.index if r not in names]]
+    scalars = table.loc[names].T[-2:-1]
+    scalars.index = ["   "]
+    text = f"\n{scalars}\n\n{per_class}\n\n"
+    if echo:
+        print(text)
+    return text
+
+
 def split_report(y_true, y_score, patient_ids, loss, kfold, epoch, split):
     """The per-split report the epoch loop writes to ``<split>_metrics_<epoch>.json`` (reference: train_models.py:727-768):
     sklearn's classification_report at threshold 0.5 on the positive-class score plus 'ROC AUC', 'kfold', 'loss', 'epoch',
@@ -455,7 +485,9 @@ def run_fold(cfg, arch, modality, df_train, df_test, label_encoder, hdf5_ct_path
                     json.dump(rep, fh)
         history.append(dict(kfold=kfold, epoch=epoch, train_loss=tr_loss, test_loss=te_loss, train_auc=train_report["ROC AUC"],
                             test_auc=test_report["ROC AUC"], train_f1=train_report["macro avg"]["f1-score"],
-                            test_f1=test_report["macro avg"]["f1-score"]))
+                            test_f1=test_report["macro avg"]["f1-score"],
+                            train_report=print_classification_report(train_report, echo=rank == 0).replace("\n", "<br>").replace(" ", "  "),
+                            test_report=print_classification_report(test_report, echo=rank == 0).replace("\n", "<br>").replace(" ", "  ")))
         save, stop, _ = epoch_policy(history, cfg_model["patience"])
         if save and rank == 0:
             save_checkpoint(model, save_dir, epoch)
