@@ -245,3 +245,41 @@ def test_report_text_and_param_count_match_reference(capsys):
     lin = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
     lin[0].bias.requires_grad_(False)
     assert tm.get_number_of_params(lin) == int(ref.get_number_of_params(lin)) == 15 + 6 + 2
+
+
+def test_patient_pointcloud_matches_reference_loop_body(monkeypatch):
+    """create_pointcloud_dataframe.py:67-82 (inline in the reference's __main__): restated here step by step on the unmodified
+    to_pointcloud_df / apply_window_ct, against patient_pointcloud with the device box gather replaced by the oracle's."""
+    from vit_deep_radiomics_b200 import create_pointcloud_dataframe as cp
+    pc = ref_shim.load_reference("create_pointcloud_dataframe")
+    ref = ref_shim.load_reference("tfds_dense_descriptor")
+    rng = np.random.default_rng(12)
+
+    def oracle_box(img, mask, spatial_res, device):
+        o = G.voxel_pointcloud(np.asarray(img, np.float32), mask, spatial_res)
+        keep = o["mask_box"]
+        flat = np.flatnonzero(keep)
+        return None, dict(flat=flat, raw=o["raw"][keep], mask=o["mask"][keep], x=o["x"][keep], y=o["y"][keep], z=o["z"][keep])
+
+    monkeypatch.setattr(cp, "_gather_box", oracle_box)
+    for modality in ("ct", "pet"):
+        img = (rng.uniform(-1000, 600, (9, 7, 5)) if modality == "ct" else rng.uniform(0, 9, (9, 7, 5))).astype(np.float32)
+        mask = np.zeros((9, 7, 5), bool)
+        mask[2:6, 1:5, 1:4] = rng.random((4, 4, 3)) < 0.6
+        mask[3, 2, 2] = True
+        res = np.array([0.8, 0.8, 1.5])
+        # the reference's loop body
+        df = pc.to_pointcloud_df(img, mask, 1, res)
+        df["modality"] = modality
+        norm = ref.apply_window_ct(img, width=800, level=40) if modality == "ct" else img / img.max()
+        df["norm"] = norm.flatten()
+        df["dataset"] = "stanford_dataset".replace("_dataset", "")
+        df["patient_id"] = "p7"
+        df = df[df["mask_box"]].copy()
+        df["label"] = 1
+        df.reset_index(drop=True, inplace=True)
+        df[["x", "y", "z"]] = df[["x", "y", "z"]] - df[["x", "y", "z"]].mean(axis=0)
+        got = cp.patient_pointcloud(img, mask, 1, res, modality, "stanford_dataset", "p7", device="cpu")
+        assert list(got.columns) == list(df.columns) and len(got) == len(df) > 0
+        for col in df.columns:
+            assert np.array_equal(got[col].values, df[col].values), (modality, col)

@@ -58,6 +58,28 @@ def pointcloud_box(img, mask, spatial_res, device="cuda:0", centre=True) -> pd.D
     return df
 
 
+def patient_pointcloud(img_raw, mask_raw, label, spatial_res, modality, dataset_name, patient_id, device="cuda:0") -> pd.DataFrame:
+    """One (patient, modality) of the reference script's loop body (create_pointcloud_dataframe.py:67-82): the voxels inside the
+    mask's bounding box with their raw and normalised values (CT: lung window 800 / 40 mapped to 0..1, PET: divided by the
+    maximum), the metadata columns, coordinates centred on the kept rows.  Only the box is materialised (device G2 kernels);
+    the reference builds the table of ALL voxels first and filters it.
+    Columns, in the reference's order: x, y, z, raw, mask, mask_box, modality, norm, dataset, patient_id, label."""
+    from .tfds_dense_descriptor import apply_window_ct
+    img_raw = np.asarray(img_raw)
+    _, o = _gather_box(img_raw, mask_raw, spatial_res, device)
+    norm = apply_window_ct(img_raw, width=800, level=40) if modality == "ct" else img_raw / img_raw.max()
+    df = pd.DataFrame({"x": o["x"], "y": o["y"], "z": o["z"], "raw": o["raw"], "mask": o["mask"]})
+    df["mask_box"] = True
+    df["modality"] = modality
+    df["norm"] = norm.flatten()[o["flat"]]
+    df["dataset"] = dataset_name.replace("_dataset", "")
+    df["patient_id"] = patient_id
+    df["label"] = label
+    if len(df):
+        df[["x", "y", "z"]] = df[["x", "y", "z"]] - df[["x", "y", "z"]].mean(axis=0)
+    return df
+
+
 def to_pointcloud_df(img, mask, label, spatial_res, device="cuda:0") -> pd.DataFrame:
     """reference: create_pointcloud_dataframe.py:15-31 (same columns, same row order, all voxels).
     The mask_box column comes from the device bounding-box kernel; x/y/z are index * spatial_res."""
