@@ -75,3 +75,20 @@ def test_sam_entry_points_validate_arguments_without_a_gpu():
     with pytest.raises(ValueError):
         ops.attn_relpos(torch.zeros(16, 192, dtype=torch.bfloat16), 1, 4, 4, 1, torch.zeros(14, 64, dtype=torch.bfloat16),
                         torch.zeros(14, 64, dtype=torch.bfloat16))
+
+
+def test_every_entry_point_has_declared_argument_types():
+    """A ctypes function without argtypes would pass 64-bit device pointers as C ints: every exported function that takes
+    arguments declares them, and their count matches the header's parameter list."""
+    lib = _C.lib()
+    text = open(os.path.join(ROOT, "include", "vdr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name in _C.EXPORTS:
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+        assert m, name
+        params = [p for p in (q.strip() for q in m.group(1).split(",")) if p and p != "void"]
+        fn = getattr(lib, name)
+        if not params:
+            assert fn.argtypes is None or len(fn.argtypes) == 0, name
+        else:
+            assert fn.argtypes is not None and len(fn.argtypes) == len(params), (name, len(params), fn.argtypes and len(fn.argtypes))
