@@ -92,3 +92,27 @@ def test_every_entry_point_has_declared_argument_types():
             assert fn.argtypes is None or len(fn.argtypes) == 0, name
         else:
             assert fn.argtypes is not None and len(fn.argtypes) == len(params), (name, len(params), fn.argtypes and len(fn.argtypes))
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of the C structs (compiled from include/vdr.h with gcc) against the ctypes mirrors in _C.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"vdr_gemm_args": _C.GemmArgs, "vdr_vit_block": _C.VitBlock, "vdr_vit_weights": _C.VitWeights}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "vdr.h")}"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert int(got[f"{cname}.{field}"]) == getattr(cls, field).offset, (cname, field)
