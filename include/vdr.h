@@ -237,6 +237,8 @@ int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_ou
  *             The encoding is evaluated once per distinct coordinate ((h + w + S) rows of 2*(D/6) f64 in the
  *             workspace) and added row-wise: bit-identical to evaluating it per token.
  *   workspace >= vdr_mask_gather_workspace_bytes(S,h,w,D), 16-byte aligned
+ * One cooperative launch (g1_fused_kernel): the mask is read once, tile ballots stay in shared memory between the count and
+ * the rank phase, the scan is a sum over the co-resident blocks' totals, rows are emitted by one warp per OUTPUT row.
  */
 size_t vdr_mask_gather_workspace_bytes(int S, int h, int w, int D);
 int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
@@ -247,6 +249,29 @@ int vdr_mask_gather(const void* feat, int feat_dtype, int64_t ld_feat, int64_t f
                     float* out_tok, int32_t* out_src, int32_t* out_count, int cap,
                     double pe_scale, const double* pe_div, const double* coef_host,
                     void* workspace, size_t workspace_bytes, vdr_stream_t stream);
+
+/* The same gather writing into a slot of a SHARED point-cloud table (the table the ranks assemble with one
+ * all-gather; replaces the reference's per-patient loop + merge, tfds_dense_descriptor.py:421, merge_dataframe_features.py:12-30):
+ * row r of this call lands at table row (*row_offset + r) -- row_offset is a DEVICE scalar (NULL = 0), typically one entry of
+ * the exclusive scan over every patient's count (vdr_mask_count -> counts all-gather -> vdr_exclusive_scan_i64), so the kernel
+ * writes at the rank's offset of the all-gather buffer with no host round trip in between.  table_src has src_cols int32 per
+ * row: 3 = (slice,row,col), 4 = (patient,slice,row,col) with `patient` written by the kernel.  Rows at or beyond table_cap are
+ * not written; out_count (int32[1]) receives this call's count. */
+int vdr_mask_gather_table(const void* feat, int feat_dtype, int64_t ld_feat, int64_t feat_slice_rows,
+                          int64_t feat_row_pitch, int64_t feat_row0,
+                          const uint8_t* mask, int64_t mask_slice_stride, int64_t mask_row_stride, int64_t mask_col_stride,
+                          const int32_t* row_map, const int32_t* col_map,
+                          int S, int h, int w, int D,
+                          float* table_tok, int32_t* table_src, int src_cols, int32_t patient, const int64_t* row_offset,
+                          int64_t table_cap, int32_t* out_count,
+                          double pe_scale, const double* pe_div, const double* coef_host,
+                          void* workspace, size_t workspace_bytes, vdr_stream_t stream);
+/* Number of tokens vdr_mask_gather would select (same mask / index-map arguments), as a device int64 -- the row count every
+ * rank exchanges before any rank emits. */
+int vdr_mask_count(const uint8_t* mask, int64_t mask_slice_stride, int64_t mask_row_stride, int64_t mask_col_stride,
+                   const int32_t* row_map, const int32_t* col_map, int S, int h, int w, int64_t* out_count, vdr_stream_t stream);
+/* offsets[i] = sum(counts[0..i)), i = 0..n (n + 1 values, device): table row offsets of n patients' slots. */
+int vdr_exclusive_scan_i64(const int64_t* counts, int n, int64_t* offsets, vdr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * G2: voxel point cloud.  Replaces: to_pointcloud_df + the caller's mask_box filter

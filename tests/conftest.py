@@ -11,6 +11,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("filterwarnings", "ignore:load_model")     # tests use seeded random backbones on purpose
 
 
 @pytest.fixture(scope="session")

@@ -164,3 +164,79 @@ def test_run_fold_world_size_2(tmp_path):
     assert out[0][0] == out[1][0] and len(out[0][0]) == 2              # same gathered records -> same history on both ranks
     assert out[1][1] is None                                           # rank 1 writes nothing
     assert {"train_metrics_0.json", "test_metrics_0.json", "train_metrics_1.json", "test_metrics_1.json", "model_epoch_0000.pth"} <= set(out[0][1])
+
+
+def _table_worker(rank, world, port, out):
+    """PointCloudTable host logic at world size 2 (gloo, CPU tensors): contiguous patient shards, padded count exchange,
+    offsets, in-place variable-length all-gather == the single-process table, on every rank.  (The device side -- the gather
+    kernel writing at a device-resident offset -- is covered by tests/test_gpu_gather.py::test_g1_count_scan_and_table_slots.)"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vit_deep_radiomics_b200.distributed import PointCloudTable
+    g = torch.Generator().manual_seed(3)
+    P, D = 5, 6                                                   # 5 patients over 2 ranks: shards of 3 and 2 (padded to 3)
+    n_rows = [4, 0, 7, 3, 5]
+    clouds = [torch.randn(n, D, generator=g) for n in n_rows]
+    keys = [torch.stack([torch.full((n,), p), torch.arange(n) % 3, torch.arange(n) // 3, torch.arange(n)], 1).int() for p, n in enumerate(n_rows)]
+    table = PointCloudTable(P, D, cap_rows=sum(n_rows) + 2, device="cpu")
+    for p in table.local_patients():
+        table.count_out(p)[0] = n_rows[p]
+    table.exchange_counts()
+    for p in table.local_patients():                              # what vdr_mask_gather_table does on the device
+        slot = table.slot(p)
+        off = int(slot["row_offset"][0])
+        slot["tokens"][off:off + n_rows[p]] = clouds[p]
+        slot["src"][off:off + n_rows[p]] = keys[p]
+    total = table.all_gather()
+    ok = total == sum(n_rows) and torch.equal(table.tokens[:total], torch.cat(clouds)) and torch.equal(table.src[:total], torch.cat(keys))
+    ok_off = table.offsets.tolist() == ([0, 4, 4, 11, 14, 19, 19] if world == 2 else None)
+    out[rank] = (ok, ok_off, list(table.local_patients()))
+    dist.destroy_process_group()
+
+
+def test_point_cloud_table_world_size_2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_table_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == (True, True, [0, 1, 2]) and out[1] == (True, True, [3, 4]), dict(out)
+
+
+def _bucket_worker(rank, world, port, out):
+    """GradBucket: .grad tensors are views of one flat buffer; all-reduce through it == per-tensor all-reduce, also after
+    ``zero_grad(set_to_none=True)`` detached the views."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vit_deep_radiomics_b200.distributed import grad_bucket, zero_grads
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Linear(4, 2))
+    data = torch.randn(8, 6, generator=torch.Generator().manual_seed(0))
+    ref = [torch.zeros_like(p) for p in model.parameters()]
+    for i in range(8):
+        model.zero_grad()
+        model(data[i]).sum().backward()
+        for r, p in zip(ref, model.parameters()):
+            r += p.grad
+    oks = []
+    for mode in ("views", "detached"):
+        if mode == "views":
+            zero_grads(model)
+            grad_bucket(model).zero()
+        else:
+            model.zero_grad(set_to_none=True)
+        for i in range(rank, 8, world):
+            model(data[i]).sum().backward()
+        allreduce_grads(model)
+        b = grad_bucket(model)
+        oks.append(all(torch.allclose(p.grad, r, atol=1e-6) for p, r in zip(model.parameters(), ref)))
+        oks.append(all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(b.params, b.views)))
+    out[rank] = tuple(oks)
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_world_size_2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bucket_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == (True,) * 4 and out[1] == (True,) * 4, dict(out)

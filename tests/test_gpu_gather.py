@@ -115,3 +115,59 @@ def test_g2_full_size_properties(cuda):
     assert np.all(np.diff(flat) > 0)
     assert np.array_equal(raw.cpu().numpy(), img.reshape(-1)[flat]) and np.array_equal(mk.cpu().numpy().astype(bool), mask.reshape(-1)[flat])
     assert int(mk.sum().item()) == int(mask.sum())                                     # every in-mask voxel is inside the box
+
+
+def test_g1_many_tiles_per_block(cuda):
+    """A candidate grid large enough that one block of the cooperative kernel owns more tiles than it keeps ballots for
+    (kKeep = 16): the recompute path of the rank phase must give the same stable order."""
+    from oracle import gather_np as G
+    from vit_deep_radiomics_b200 import ops
+    rng = np.random.default_rng(21)
+    S, gh, gw, D = 64, 200, 200, 8              # 2.56 M candidates = 1250 tiles of 2048 over <= 592 co-resident blocks... x17+ with a small grid
+    feats = rng.standard_normal((S, gh, gw, D)).astype(np.float32)
+    masks = rng.random((S, gh, gw)) < 0.03
+    t, src, cnt = ops.mask_gather(torch.from_numpy(feats).to(cuda), torch.from_numpy(masks.astype(np.uint8)).to(cuda))
+    n = int(cnt.item())
+    sel = np.moveaxis(masks, 0, -1).reshape(-1)                # (h, w, S) flatten order
+    assert n == int(sel.sum())
+    flat = np.nonzero(sel)[0]
+    s = src[:n].cpu().numpy().astype(np.int64)
+    assert np.array_equal(s[:, 1] * (gw * S) + s[:, 2] * S + s[:, 0], flat)
+    assert np.array_equal(t[:n].cpu().numpy(), np.moveaxis(feats, 0, 2).reshape(-1, D)[flat])
+
+
+def test_g1_count_scan_and_table_slots(cuda):
+    """The sharded-extraction contract: vdr_mask_count == the gather's count; offsets = device exclusive scan; three
+    'patients' gathered into ONE table at device-resident row offsets == the concatenation of their own gathers, with the
+    patient index in column 0 of the 4-column key."""
+    from vit_deep_radiomics_b200 import ops
+    rng = np.random.default_rng(33)
+    D, pats = 48, []
+    for p, (S, gh, gw, HM, WM, dens) in enumerate([(5, 6, 7, 30, 41, 0.4), (3, 9, 4, 27, 16, 0.0), (8, 5, 5, 20, 20, 0.7), (2, 4, 6, 16, 18, 0.2)]):
+        feats = torch.from_numpy(rng.standard_normal((S, gh, gw, D)).astype(np.float32)).to(cuda)
+        mask = torch.from_numpy((rng.random((S, HM, WM)) < dens).astype(np.uint8)).to(cuda)
+        pats.append((feats, mask, dict(res=(0.8, 0.8, 1.0), noise=(0.1 * p, 0.0, -0.2))))
+    counts = torch.zeros(len(pats), dtype=torch.int64, device=cuda)
+    singles = []
+    for p, (f, m, pe) in enumerate(pats):
+        ops.mask_count(m, grid=f.shape[:3], out=counts[p:p + 1])
+        t, s, c = ops.mask_gather(f, m, pe=pe)
+        n = int(c.item())
+        assert int(counts[p].item()) == n
+        singles.append((t[:n].clone(), s[:n].clone()))
+    offsets = ops.exclusive_scan_i64(counts)
+    want_off = np.concatenate([[0], np.cumsum(counts.cpu().numpy())])
+    assert np.array_equal(offsets.cpu().numpy(), want_off) and int(counts[1].item()) == 0      # an empty patient in the middle
+    total = int(want_off[-1])
+    table = dict(tokens=torch.full((total + 5, D), -7.0, device=cuda), src=torch.full((total + 5, 4), -7, dtype=torch.int32, device=cuda))
+    for p in (2, 0, 3, 1):                                                                       # any order: slots are disjoint
+        f, m, pe = pats[p]
+        _, _, c = ops.mask_gather(f, m, pe=pe, table=dict(table, row_offset=offsets[p:p + 1], patient=p))
+        assert int(c.item()) == int(counts[p].item())
+    assert torch.equal(table["tokens"][:total], torch.cat([t for t, _ in singles]))
+    keys = torch.cat([torch.cat([torch.full((s.shape[0], 1), p, dtype=torch.int32, device=cuda), s], 1) for p, (_, s) in enumerate(singles)])
+    assert torch.equal(table["src"][:total], keys)
+    assert (table["tokens"][total:] == -7.0).all() and (table["src"][total:] == -7).all()        # nothing beyond the slots
+    # a large scan (more elements than threads)
+    big = torch.from_numpy(rng.integers(0, 1 << 33, 5000)).to(cuda)
+    assert np.array_equal(ops.exclusive_scan_i64(big).cpu().numpy(), np.concatenate([[0], np.cumsum(big.cpu().numpy())]))

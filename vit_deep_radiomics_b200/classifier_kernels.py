@@ -40,8 +40,15 @@ def _cached(p: torch.Tensor, tag: str, make):
     if hit is not None and hit[0]() is p and hit[1] == p._version and hit[2].device == p.device:
         return hit[2]
     val = make(p.detach())
-    _CACHE[key] = (weakref.ref(p), p._version, val)
+    # the entry dies with its parameter (one model per fold would otherwise leak two bf16 copies of every weight)
+    _CACHE[key] = (weakref.ref(p, lambda _r, k=key: _CACHE.pop(k, None)), p._version, val)
     return val
+
+
+def invalidate_cache() -> None:
+    """Drop every cached bf16 operand copy.  The cache keys on ``Parameter._version``; writes made through ``.data`` (EMA / SWA,
+    manual clamping, ``dist.broadcast(p.data, ...)``) do not bump it -- call this after such an update."""
+    _CACHE.clear()
 
 
 def _bf16(p):      # (out, in) bf16: forward operand

@@ -699,12 +699,12 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   CUtensorMap tm;
   int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * d, (uint64_t)ld_qkv, 128, kHD);
   if (rc != VDR_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceFlags configured;
+  if (!configured.current()) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_fwd)");
-    configured = true;
+    configured.current() = true;
   }
   AttnParams p;
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);

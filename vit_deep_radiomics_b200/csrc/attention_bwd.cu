@@ -273,11 +273,11 @@ extern "C" int vdr_flash_attn_bwd(const void* qkv, int64_t ld_qkv, const void* O
   if (rc != VDR_OK) return rc;
   rc = make_tmap_2d_bf16(&tmDO, dO, (uint64_t)B * N, (uint64_t)d, (uint64_t)ld_o, 128, kBD);
   if (rc != VDR_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceFlags configured;
+  if (!configured.current()) {
     e = cudaFuncSetAttribute(flash_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_bwd)");
-    configured = true;
+    configured.current() = true;
   }
   AttnBwdParams p;
   p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;

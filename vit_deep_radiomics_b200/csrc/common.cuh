@@ -39,6 +39,16 @@ int  make_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64
     if (e__ != cudaSuccess) return ::vdr::cuda_fail(e__, what);        \
   } while (0)
 
+// One flag per CUDA device: cudaFuncSetAttribute & co. are per-device state, a process may drive several devices.
+struct DeviceFlags {
+  bool f[64] = {};
+  bool& current() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    return f[d];
+  }
+};
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ----------------------------------------------------------------------------- device helpers

@@ -572,12 +572,12 @@ template <int BN, int kCtas, bool kRes, int kFold>
 static int launch_gemm_(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR, const GemmParams& p, int grid,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kCtas, kRes>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceFlags configured;
+  if (!configured.current()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kCtas, kRes, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
-    configured = true;
+    configured.current() = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);

@@ -348,11 +348,11 @@ extern "C" int vdr_layernorm_bwd(const void* dy, int64_t lddy, const void* x, in
   if (d <= 256) {
     layernorm_bwd_kernel<1><<<grid, kLnWarps * 32, smem, s>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, dxb, lddx, dgamma, dbeta, rows, d);
   } else {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceFlags configured;
+    if (!configured.current()) {
       cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(layernorm_bwd)");
-      configured = true;
+      configured.current() = true;
     }
     layernorm_bwd_kernel<4><<<grid, kLnWarps * 32, smem, s>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, dxb, lddx, dgamma, dbeta, rows, d);
   }

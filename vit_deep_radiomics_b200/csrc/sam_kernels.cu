@@ -656,11 +656,11 @@ extern "C" int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const voi
   const int N = Sh * Sw;
   dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
   constexpr int kTableSmem = 4 * 2 * kRpTile * (int)sizeof(__nv_bfloat16);      // 73,728 B
-  static bool configured = false;
-  if (!configured) {
+  static DeviceFlags configured;
+  if (!configured.current()) {
     cudaError_t e = cudaFuncSetAttribute(relpos_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableSmem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(relpos_table_kernel)");
-    configured = true;
+    configured.current() = true;
   }
   relpos_table_kernel<<<grid, 256, kTableSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
@@ -688,11 +688,11 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const v
   if (N <= kWinRows && 2 * Sh - 1 + 2 * Sw - 1 <= 64) {
     // small extents (the 14 x 14 windows): two CTAs per (window, head) with everything resident
     const size_t smem_w = (2 * (size_t)kWinRows * kRpPitch + 2 * (size_t)kRpTile) * sizeof(__nv_bfloat16) + (size_t)kWinQ * RP * sizeof(float);
-    static bool configured_w = false;
-    if (!configured_w) {
+    static DeviceFlags configured_w;
+    if (!configured_w.current()) {
       cudaError_t e = cudaFuncSetAttribute(attn_relpos_win_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_win_kernel)");
-      configured_w = true;
+      configured_w.current() = true;
     }
     attn_relpos_win_kernel<false><<<dim3(heads, BW, N > kWinQ ? 2 : 1), kWinThreads, smem_w, reinterpret_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), ld_qkv, static_cast<const __nv_bfloat16*>(rcat_hi_bf16),
@@ -704,11 +704,11 @@ extern "C" int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const v
   }
   const bool row_tiles = Sw == 64 && N % 64 == 0;
   auto kernel = row_tiles ? attn_relpos_kernel<true> : attn_relpos_kernel<false>;
-  static size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[row_tiles]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static DeviceFlags configured[2];
+  if (!configured[row_tiles].current()) {   // opt in to the device maximum once per device: smem varies with the extent
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_kernel)");
-    configured[row_tiles] = smem;
+    configured[row_tiles].current() = true;
   }
   dim3 grid((N + kRpBQ - 1) / kRpBQ, heads, BW);
   kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -740,11 +740,11 @@ extern "C" int vdr_attn_relpos_windows_fwd(const void* qkv_bf16, int64_t ld_qkv,
   const int rp0 = ((ws + 1) & ~1) + ws;
   const int RP = rp0 + (8 - rp0 % 32 + 32) % 32;
   const size_t smem_w = (2 * (size_t)kWinRows * kRpPitch + 2 * (size_t)kRpTile) * sizeof(__nv_bfloat16) + (size_t)kWinQ * RP * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceFlags configured;
+  if (!configured.current()) {
     cudaError_t e = cudaFuncSetAttribute(attn_relpos_win_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_relpos_win_kernel<mapped>)");
-    configured = true;
+    configured.current() = true;
   }
   const uint32_t magic = ws > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)ws - 1) / (uint64_t)ws) : 0u;
   WinMap wm{gh, gw, nwh, nww, qkv_bias};

@@ -41,6 +41,11 @@ def _stream() -> int:
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor (libvdr has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # libvdr launches on the CUDA runtime's current device / torch's current stream of that device: a tensor that lives
+        # elsewhere would be touched by a kernel of the wrong device (callers: torch.cuda.set_device(...) first)
+        raise ValueError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         "call torch.cuda.set_device(tensor.device) before using libvdr ops")
     if t.dtype != dtype:
         raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
     return t
@@ -334,39 +339,11 @@ def _index_map_dev(n_out: int, n_in: int, dev) -> torch.Tensor:
     return _MAP_CACHE[key]
 
 
-def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = None, pe: dict | None = None,
-                grid: tuple | None = None, feat_roi: tuple | None = None, mask_roi: tuple | None = None,
-                mask_layout: str = "shw"):
-    """G1 (reference src/train_models.py:143-182 on device).
-
-    feat     (S, h, w, D) dense descriptors, or the backbone's token matrix (S*slice_rows, D) together
-             with ``grid=(S, gh, gw, slice_rows, first_row)`` (CLS-first layout: slice_rows = gh*gw+1,
-             first_row = 1).  bf16 or f32, CUDA, unit inner stride.
-    mask_u8  uint8 CUDA pixel masks, contiguous: (S, HM, WM) with mask_layout="shw", or the (HM, WM, S) volume
-             mask read in place with mask_layout="hws" (no transpose pass).
-    feat_roi (r0, r1, c0, c1) feature-grid window, mask_roi (y0, y1, x0, x1) pixel window: the
-             extract_roi crops of tfds_dense_descriptor.py:278-279, applied by pointer arithmetic.
-    pe       dict(res=(3,), noise=(3,), scale=0.25): add the 3-D positional encoding / 4 (:178-180).
-    Returns (tokens (cap, D) f32, src (cap, 3) int32 [slice,row,col in ROI coords], count int32[1]),
-    all on the device; rows >= count are unspecified.
-    """
+def _mask_geometry(mask_u8: torch.Tensor, S: int, gh: int, gw: int, feat_roi, mask_roi, mask_layout: str):
+    """Pixel-mask strides, ROI extents and the order-0 resize index maps of train_models.py:151 (cached device tensors)."""
     _req(mask_u8, torch.uint8, "mask")
-    if feat.dtype not in _DT or not feat.is_cuda:
-        raise ValueError("feat must be a bf16 or f32 CUDA tensor")
     if not mask_u8.is_contiguous() or mask_u8.dim() != 3:
         raise ValueError("mask must be a contiguous (S, HM, WM) tensor")
-    if feat.dim() == 4:
-        if not feat.is_contiguous():
-            raise ValueError("dense feat must be contiguous")
-        S, gh, gw, D = feat.shape
-        slice_rows, first_row, ld = gh * gw, 0, D
-    elif feat.dim() == 2 and grid is not None:
-        S, gh, gw, slice_rows, first_row = (int(v) for v in grid)
-        D, ld = feat.shape[1], feat.stride(0)
-        if feat.stride(1) != 1 or feat.shape[0] < S * slice_rows:
-            raise ValueError("token matrix too small / not unit inner stride")
-    else:
-        raise ValueError("feat must be (S,h,w,D) or a token matrix with grid=(S,gh,gw,slice_rows,first_row)")
     if mask_layout == "shw":
         SM, HM, WM = mask_u8.shape
         ms, mr, mc = HM * WM, WM, 1
@@ -382,16 +359,103 @@ def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = 
     h, w, hm, wm = r1 - r0, c1 - c0, y1 - y0, x1 - x0
     if min(h, w, hm, wm) <= 0 or r1 > gh or c1 > gw or y1 > HM or x1 > WM or min(r0, c0, y0, x0) < 0:
         raise ValueError("empty or out-of-range ROI")
+    dev = mask_u8.device
+    return dict(h=h, w=w, hm=hm, wm=wm, r0=r0, c0=c0, ms=ms, mr=mr, mc=mc, mask_ptr=mask_u8.data_ptr() + y0 * mr + x0 * mc,
+                row_map=_index_map_dev(h, hm, dev), col_map=_index_map_dev(w, wm, dev))
+
+
+def mask_count(mask_u8: torch.Tensor, *, grid: tuple, feat_roi: tuple | None = None, mask_roi: tuple | None = None,
+               mask_layout: str = "shw", out: torch.Tensor | None = None) -> torch.Tensor:
+    """Number of tokens ``mask_gather`` would select for the same mask / ROI arguments, as a device int64[1] (vdr_mask_count):
+    the row count the ranks exchange before any of them emits into the shared table."""
+    S, gh, gw = (int(v) for v in grid[:3])
+    geo = _mask_geometry(mask_u8, S, gh, gw, feat_roi, mask_roi, mask_layout)
+    if out is None:
+        out = torch.empty(1, dtype=torch.int64, device=mask_u8.device)
+    _req(out, torch.int64, "out")
+    _C.check(_C.lib().vdr_mask_count(geo["mask_ptr"], geo["ms"], geo["mr"], geo["mc"], geo["row_map"].data_ptr(), geo["col_map"].data_ptr(),
+                                     S, geo["h"], geo["w"], out.data_ptr(), _stream()), "vdr_mask_count")
+    return out
+
+
+def exclusive_scan_i64(counts: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """offsets (n + 1) int64 = exclusive prefix sums of counts (n) int64 on the device (vdr_exclusive_scan_i64)."""
+    _req(counts, torch.int64, "counts")
+    n = counts.numel()
+    if out is None:
+        out = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    _req(out, torch.int64, "out")
+    if not counts.is_contiguous() or not out.is_contiguous() or out.numel() < n + 1:
+        raise ValueError("counts / out must be contiguous and out hold n + 1 values")
+    _C.check(_C.lib().vdr_exclusive_scan_i64(counts.data_ptr(), n, out.data_ptr(), _stream()), "vdr_exclusive_scan_i64")
+    return out
+
+
+_GATHER_WS: dict = {}
+
+
+def _gather_workspace(nbytes: int, dev) -> torch.Tensor:
+    """Scratch of the gather (block totals + PE table), kept per (device, stream): calls on one stream are ordered, so the
+    buffer can be reused without a fresh allocation per call."""
+    key = (str(dev), _stream())
+    ws = _GATHER_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _GATHER_WS[key] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = None, pe: dict | None = None,
+                grid: tuple | None = None, feat_roi: tuple | None = None, mask_roi: tuple | None = None,
+                mask_layout: str = "shw", table: dict | None = None):
+    """G1 (reference src/train_models.py:143-182 on device).
+
+    feat     (S, h, w, D) dense descriptors, or the backbone's token matrix (S*slice_rows, D) together
+             with ``grid=(S, gh, gw, slice_rows, first_row)`` (CLS-first layout: slice_rows = gh*gw+1,
+             first_row = 1).  bf16 or f32, CUDA, unit inner stride.
+    mask_u8  uint8 CUDA pixel masks, contiguous: (S, HM, WM) with mask_layout="shw", or the (HM, WM, S) volume
+             mask read in place with mask_layout="hws" (no transpose pass).
+    feat_roi (r0, r1, c0, c1) feature-grid window, mask_roi (y0, y1, x0, x1) pixel window: the
+             extract_roi crops of tfds_dense_descriptor.py:278-279, applied by pointer arithmetic.
+    pe       dict(res=(3,), noise=(3,), scale=0.25): add the 3-D positional encoding / 4 (:178-180).
+    table    dict(tokens (rows, D) f32, src (rows, 3|4) int32, row_offset int64[1] device view, patient int): write into the
+             slot of a shared table that starts at row ``row_offset`` (device scalar) instead of fresh tensors.
+    Returns (tokens (cap, D) f32, src (cap, 3) int32 [slice,row,col in ROI coords], count int32[1]),
+    all on the device; rows >= count are unspecified.  With ``table`` the first two are the table's tensors.
+    """
+    if feat.dtype not in _DT or not feat.is_cuda:
+        raise ValueError("feat must be a bf16 or f32 CUDA tensor")
+    if feat.dim() == 4:
+        if not feat.is_contiguous():
+            raise ValueError("dense feat must be contiguous")
+        S, gh, gw, D = feat.shape
+        slice_rows, first_row, ld = gh * gw, 0, D
+    elif feat.dim() == 2 and grid is not None:
+        S, gh, gw, slice_rows, first_row = (int(v) for v in grid)
+        D, ld = feat.shape[1], feat.stride(0)
+        if feat.stride(1) != 1 or feat.shape[0] < S * slice_rows:
+            raise ValueError("token matrix too small / not unit inner stride")
+    else:
+        raise ValueError("feat must be (S,h,w,D) or a token matrix with grid=(S,gh,gw,slice_rows,first_row)")
+    geo = _mask_geometry(mask_u8, S, gh, gw, feat_roi, mask_roi, mask_layout)
+    h, w, hm, wm = geo["h"], geo["w"], geo["hm"], geo["wm"]
     dev = feat.device
-    row_map = _index_map_dev(h, hm, dev)
-    col_map = _index_map_dev(w, wm, dev)
-    if cap is None:
-        cap = S * h * w
-    tokens = torch.empty((cap, D), dtype=torch.float32, device=dev)
-    src = torch.empty((cap, 3), dtype=torch.int32, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
+    if table is None:
+        if cap is None:
+            cap = S * h * w
+        tokens = torch.empty((cap, D), dtype=torch.float32, device=dev)
+        src = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+        src_cols, patient, row_off_ptr = 3, 0, None
+    else:
+        tokens, src = _req(table["tokens"], torch.float32, "table tokens"), _req(table["src"], torch.int32, "table src")
+        if tokens.dim() != 2 or tokens.shape[1] != D or not tokens.is_contiguous() or not src.is_contiguous() or src.shape[0] != tokens.shape[0] \
+                or src.shape[1] not in (3, 4):
+            raise ValueError("table: tokens (rows, D) f32 and src (rows, 3|4) int32, both contiguous")
+        cap, src_cols, patient = tokens.shape[0], src.shape[1], int(table.get("patient", 0))
+        ro = table.get("row_offset")
+        row_off_ptr = _req(ro, torch.int64, "row_offset").data_ptr() if ro is not None else None
     ws_bytes = _C.lib().vdr_mask_gather_workspace_bytes(S, h, w, D)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = _gather_workspace(ws_bytes, dev)
     pe_scale, pe_div_ptr, coef = 0.0, None, None
     if pe is not None:
         res, noise = [float(v) for v in pe["res"]], [float(v) for v in pe.get("noise", (0, 0, 0))]
@@ -399,11 +463,11 @@ def mask_gather(feat: torch.Tensor, mask_u8: torch.Tensor, *, cap: int | None = 
         coef = (C.c_double * 11)(float(wm), float(hm), res[0], res[1], res[2], noise[0], noise[1], noise[2], mx, my, mz)
         pe_scale = float(pe.get("scale", 0.25))
         pe_div_ptr = _pe_div(D, dev).data_ptr()
-    _C.check(_C.lib().vdr_mask_gather(feat.data_ptr(), _DT[feat.dtype], ld, slice_rows, gw, first_row + r0 * gw + c0,
-                                      mask_u8.data_ptr() + y0 * mr + x0 * mc, ms, mr, mc,
-                                      row_map.data_ptr(), col_map.data_ptr(), S, h, w, D,
-                                      tokens.data_ptr(), src.data_ptr(), count.data_ptr(), cap,
-                                      pe_scale, pe_div_ptr, coef, ws.data_ptr(), ws_bytes, _stream()),
+    _C.check(_C.lib().vdr_mask_gather_table(feat.data_ptr(), _DT[feat.dtype], ld, slice_rows, gw, first_row + geo["r0"] * gw + geo["c0"],
+                                            geo["mask_ptr"], geo["ms"], geo["mr"], geo["mc"],
+                                            geo["row_map"].data_ptr(), geo["col_map"].data_ptr(), S, h, w, D,
+                                            tokens.data_ptr(), src.data_ptr(), src_cols, patient, row_off_ptr, cap, count.data_ptr(),
+                                            pe_scale, pe_div_ptr, coef, ws.data_ptr(), ws.numel(), _stream()),
              "vdr_mask_gather")
     return tokens, src, count
 

@@ -33,8 +33,14 @@ def load_model(model_name, model_path=None, img_hw=None, device="cuda:0", seed=1
     (segment_anything / DINOv2 / timm key names); without it the weights are seeded random (no checkpoints exist offline)."""
     sd = None
     if model_path is not None:
+        if not os.path.isfile(model_path):
+            raise FileNotFoundError(f"load_model: checkpoint {model_path!r} not found (random weights only on request: model_path=None)")
         sd = torch.load(model_path, map_location="cpu")
         sd = sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+    else:
+        import warnings
+        warnings.warn(f"load_model({model_name!r}): no model_path -- the backbone gets SEEDED RANDOM weights (seed {seed}); "
+                      "descriptors from it are only good for tests and benchmarks", stacklevel=2)
     if model_name in SAM_CONFIGS:
         # load_medsam (:91-107): sam_model_registry['vit_b'](model_path); only model.image_encoder is ever called (:123).
         # prepare_image feeds it 1024 x 1024 (:42); other sizes need a pos_embed of that grid.
@@ -253,6 +259,61 @@ class PointCloudExtractor:
                 out.update(tokens=tokens, src=src, count=count)
             yield out
 
+    # ---- sharded extraction into ONE table (reference: the per-patient loop :421 + merge_dataframe_features.py)
+    def plan_patient(self, mask_dev):
+        """Crop / ROI plan of a device-resident (H, W, S) uint8 mask: the union-mask bounding box is reduced on the device
+        (24-byte read-back), the rest is host integer geometry."""
+        model = self.model
+        H, W, S = mask_dev.shape
+        box = ops.mask_bbox(mask_dev).cpu()
+        cmin, cmax, rmin, rmax, _, _ = (int(v) for v in box)
+        if cmax < cmin:
+            raise ValueError("extract_coords: empty mask")
+        plan = _plan_from_bbox(model, H, W, (rmin, rmax, cmin, cmax))
+        return plan if plan is not None else _plan(model, mask_dev.cpu().numpy())
+
+    def run_table(self, items, table, add_pe=True):
+        """This rank's patients of a sharded extraction, written straight into ``table`` (distributed.PointCloudTable).
+
+        items: list of (patient_index, img (H, W, S) f32, mask (H, W, S) uint8, spatial_res[, noise]) for the patients of
+        ``table.local_patients()``; tensors may be pinned host tensors (uploaded here) or already on the device.
+        1. every local patient's row count from its mask alone (``ops.mask_count``), 2. counts all-gather + device scan
+        (``table.exchange_counts``), 3. per patient backbone + gather at the patient's row offset of the table (the offset is read
+        by the kernel from device memory), 4. one in-place all-gather of the rank's row range (``table.all_gather``).
+        Returns the table's total row count; ``table.tokens[:total]`` / ``table.src[:total]`` then hold every rank's rows in
+        (patient, candidate) order, identical on all ranks."""
+        model, dev = self.model, self.model.device
+        gh, gw = model.grid
+        staged = []
+        for it in items:
+            pid, img_t, mask_t, res = it[:4]
+            noise = it[4] if len(it) > 4 else (0.0, 0.0, 0.0)
+            mask_dev = mask_t if mask_t.is_cuda else mask_t.to(dev, non_blocking=True)
+            plan = self.plan_patient(mask_dev)
+            S = mask_dev.shape[2]
+            geo = dict(grid=(S, gh, gw, model.n_tokens, model.token_offset), feat_roi=plan["feat_roi"],
+                       mask_roi=_shift_roi(plan["mask_roi"], plan["crop"]), mask_layout="hws")
+            ops.mask_count(mask_dev, grid=geo["grid"], feat_roi=geo["feat_roi"], mask_roi=geo["mask_roi"], mask_layout="hws",
+                           out=table.count_out(pid))
+            staged.append((pid, img_t, mask_dev, res, noise, plan, geo))
+        table.exchange_counts()
+        main = torch.cuda.current_stream(dev)
+        nxt = None
+        for i, (pid, img_t, mask_dev, res, noise, plan, geo) in enumerate(staged):
+            img_dev = nxt if nxt is not None else (img_t if img_t.is_cuda else img_t.to(dev, non_blocking=True))
+            nxt = None
+            tok = _forward_volume(model, img_dev, plan)
+            if i + 1 < len(staged) and not staged[i + 1][1].is_cuda:       # next volume crosses PCIe while this one is in the backbone
+                with torch.cuda.stream(self.copy_stream):
+                    nxt = staged[i + 1][1].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.copy_stream)
+            pe = dict(res=res, noise=noise, scale=0.25) if add_pe else None
+            ops.mask_gather(tok, mask_dev, pe=pe, table=table.slot(pid), **geo)
+            if nxt is not None:
+                main.wait_event(ev)
+        return table.all_gather()
+
 
 def _shift_roi(mask_roi, crop):
     """ROI of the cropped mask -> window of the full (H, W, S) mask."""
@@ -398,8 +459,10 @@ def build_arg_parser():
     """Same flags as the reference CLI (tfds_dense_descriptor.py:365-382)."""
     p = argparse.ArgumentParser(description="ViT patch embeddings of the lung_radiomics datasets (B200-native)")
     p.add_argument("-mn", "--model_name", type=str, default="medsam", help="medsam (the reference's default) | dinov2 | vit_s16 | vit_b16 | vit_l14")
-    p.add_argument("-mp", "--model_path", type=str, default=None,
-                   help="state-dict .pth (the reference defaults to models/backbones/medsam/medsam_vit_b.pth); omitted = seeded random weights")
+    p.add_argument("-mp", "--model_path", type=str, default=os.path.join("models", "backbones", "medsam", "medsam_vit_b.pth"),
+                   help="state-dict .pth (same default as the reference, :368-370)")
+    p.add_argument("--random_init", action="store_true",
+                   help="NOT in the reference: run with seeded random backbone weights instead of a checkpoint (tests / benchmarks only)")
     p.add_argument("-d", "--dataset_path", type=str, default=os.path.join("data", "lung_radiomics"))
     p.add_argument("-f", "--feature_folder", type=str, default=os.path.join("data", "features"))
     p.add_argument("-h5", "--hdf5_path", type=str, default=os.path.join("data", "lung_radiomics", "lung_radiomics_datasets_isotropic.hdf5"))
@@ -425,7 +488,11 @@ def main(argv=None):
     ``<feature_folder>/features_masks_<modality>.hdf5``; patients whose parquet exists are skipped (:424)."""
     import pandas as pd
     args = build_arg_parser().parse_args(argv)
-    model = load_model(args.model_name, args.model_path)
+    if args.random_init:
+        print("WARNING: --random_init: features come from an UNTRAINED backbone")
+        model = load_model(args.model_name, None)
+    else:
+        model = load_model(args.model_name, args.model_path)       # a missing checkpoint is an error, never silent random weights
     modalities = ["pet", args.modality]
     meta = pd.read_csv(args.df_path)
     meta["label"] = (meta["egfr"] == "Mutant").astype(int)                               # :398

@@ -351,10 +351,11 @@ def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, gra
     steps every iters_to_accumulate samples and at the last sample (:685-687).  ``grad_sync`` (optional
     callable) is invoked right before each optimizer step: the data-parallel gradient all-reduce.
     Returns (mean loss, list of softmax scores)."""
+    from .distributed import zero_grads
     samples = list(samples)
     iters = min(virtual_batch_size, len(samples))
     model.train()
-    optimizer.zero_grad()
+    zero_grads(model, optimizer)
     total, scores = 0.0, []
     for i, sample in enumerate(samples):
         label = sample[-1]
@@ -371,7 +372,7 @@ def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, gra
             if grad_sync is not None:
                 grad_sync(model)
             optimizer.step()
-            optimizer.zero_grad()
+            zero_grads(model, optimizer)
     return total / max(len(samples), 1), scores
 
 
@@ -408,12 +409,13 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
     are gathered, so every rank returns the whole epoch's records.
     Returns (mean loss, y_true list, y_score list, patient ids)."""
     import torch.distributed as dist
+    from .distributed import zero_grads
     train = optimizer is not None
     order = list(order)
     iters = min(virtual_batch_size, len(order)) if train else max(len(order), 1)
     model.train(train)
     if train:
-        optimizer.zero_grad()
+        zero_grads(model, optimizer)
     total, y_true, y_score, pids = 0.0, [], [], []
     with torch.enable_grad() if train else torch.no_grad():
         for w0 in range(0, len(order), iters):
@@ -431,7 +433,7 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
                 if grad_sync is not None:
                     grad_sync(model)
                 optimizer.step()
-                optimizer.zero_grad()
+                zero_grads(model, optimizer)
     if world > 1:
         parts = [None] * world
         dist.all_gather_object(parts, (total, y_true, y_score, pids))
@@ -457,10 +459,13 @@ def run_fold(cfg, arch, modality, df_train, df_test, label_encoder, hdf5_ct_path
     if rank == 0:
         os.makedirs(save_dir, exist_ok=True)
     cfg_model = cfg["models"][arch]
+    if torch.device(device).type == "cuda":
+        torch.cuda.set_device(device)        # libvdr launches on the current device / its current stream (ops._req checks)
     model = build_model(cfg, arch, modality, modality_a, modality_b, num_classes=2).to(device)
     if world > 1:
-        for p_ in model.parameters():
-            dist.broadcast(p_.data, 0)
+        with torch.no_grad():
+            for p_ in model.parameters():
+                dist.broadcast(p_, 0)        # in place on the parameter itself: bumps its version counter, so the cached bf16 operand copies refresh
         grad_sync = grad_sync or allreduce_grads
     criterion = make_criterion(loss_func, device)
     optimizer, scheduler = make_optimizer(model, cfg, arch)
@@ -507,6 +512,7 @@ def main(argv=None):
     from .distributed import init_distributed
     rank, world = init_distributed()                       # under torchrun: data parallel over the virtual batch
     device = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}" if world > 1 else f"cuda:{args.gpu}"
+    torch.cuda.set_device(device)
     modality_a, modality_b = "pet", ("chest" if "chest" in args.modality else "ct")
     hdf5_pet = os.path.join("..", "data", "features", f"features_masks_{modality_a}.hdf5")
     hdf5_ct = os.path.join("..", "data", "features", f"features_masks_{modality_b}.hdf5")
