@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: ViT dense-descriptor extraction + tumour-mask gather.
+"""Benchmark of the hot path: ViT dense-descriptor extraction + tumour-mask gather (+ the table all-gather at N > 1).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C2]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C2] [--no-sub]
 
-A "step" is one pass of the path over one synthetic CT volume (BASELINE.json configs[1]:
-ViT-B/16 over a 512x512x120 volume, mask-gathered point cloud): the batched backbone forward of
-all slices + the stream-compaction gather.  Metric = CT slices per second (whole job, all GPUs).
+A "step" is one pass of the path over one synthetic CT volume per GPU (BASELINE.json configs[1]: ViT-B/16 over a
+512x512x120 volume, mask-gathered point cloud): the batched backbone forward of all slices + the stream-compaction gather.
+Metric = CT slices per second (whole job, all GPUs).
   value : inputs already resident in HBM when the timed region starts
-  e2e   : same metric through the public call `tfds_dense_descriptor.extract_point_cloud` with HOST
-          (pinned) buffers: H2D of the volume + mask and D2H of the point cloud inside the timed region
-One JSON line is printed by rank 0.  Under torchrun each rank processes its own volume (patients are
-independent: weak scaling, no data-path collective); time = max over ranks of device time.
-`--impl reference` times the CPU implementation of the same path on the host cores (the oracle port:
-the reference's backbone lives in un-vendored third-party code and hard-codes .cuda()).
+  e2e   : same metric through the public API with HOST (pinned) buffers: H2D of the volumes + masks and D2H of the
+          point clouds inside the timed region
+N > 1 (torchrun, one rank per GPU): the patients are sharded over the ranks and every step ALSO assembles the point-cloud
+table on every rank INSIDE the timed region (distributed.PointCloudTable: row counts -> one small all-gather -> device scan ->
+each rank's gather kernel writes at its row offset of the table -> one in-place NCCL all-gather of the row ranges), the
+exchange step of SURVEY.md 8(e).  Time = max over ranks of the device time.
+Sub-records (key "sub", each with its own roofline / cpu_baseline / e2e): C1 (ViT-S/16 224^2 x 8), C4 (ViT-L/14, patients
+sharded + table all-gather), C5 (extraction -> gather -> classifier training step, patients/s), c3 (classifier data-parallel
+training, samples/s, gradient all-reduce), medsam (the reference's default backbone).
+`--impl reference` times the CPU implementation of the same path on the host cores (the oracle port: the reference's
+backbone lives in un-vendored third-party code and hard-codes .cuda()).
 """
 from __future__ import annotations
 
@@ -29,6 +34,10 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+NOMINAL_BF16_TFLOPS = 2250.0     # B200 dense bf16 (the north star's nominal denominator)
+NOMINAL_HBM_GBS = 8000.0
+NVLINK_PEER_GBS = 770.0          # measured peer copy per direction on this pool (B200_PROFILING.md); nominal 900
 
 
 # ----------------------------------------------------------------------------------------- helpers
@@ -83,20 +92,65 @@ def measured_peaks():
     return dict(bf16=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-def cpu_baseline(case: str, sample_slices: int, threads: int | None = None):
-    """Oracle port of the path on the host cores: fp32 ViT forward (oracle/vit_fp32.py) over a bounded
-    sample of slices of the SAME synthetic volume + the NumPy gather on those slices."""
+def tensor_fracs(tflops, peaks):
+    """Fraction of the measured sustained / measured burst / nominal dense bf16 peak (BASELINE.md section 2 asks for all)."""
+    if not tflops:
+        return {"frac": None, "frac_burst": None, "frac_nominal": None}
+    return {"frac": tflops / peaks["bf16"], "frac_burst": tflops / peaks["burst"], "frac_nominal": tflops / NOMINAL_BF16_TFLOPS}
+
+
+class Dist:
+    """rank / world + the barrier and max-over-ranks the timing contract asks for."""
+
+    def __init__(self):
+        from vit_deep_radiomics_b200.distributed import init_distributed
+        self.rank, self.world = init_distributed("nccl")
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device(f"cuda:{self.local}")
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(self, fn, steps):
+        """barrier + synchronize, `steps` calls between two CUDA events on the launching stream, barrier + synchronize;
+        returns (max over ranks of the device ms, last result)."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        return self.max_ms(e0.elapsed_time(e1)), out
+
+
+# ----------------------------------------------------------------------------------------- CPU legs (oracle port)
+def cpu_extraction(case: str, sample_slices: int, weights=None, threads: int | None = None, seed: int = 1235):
+    """Oracle port of the path on the host cores: fp32 ViT forward (oracle/vit_fp32.py) over a bounded sample of slices of the
+    SAME synthetic volume + the NumPy gather on those slices.  Returns (cpu_baseline dict, seconds, dense descriptors, slice range)."""
     from oracle import gather_np, vit_fp32
     from vit_deep_radiomics_b200 import synth
-    from vit_deep_radiomics_b200.visualization_utils import crop_window, roi_window
+    from vit_deep_radiomics_b200.visualization_utils import roi_window
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
-    img, mask, res, model_name = synth.make_case(case)
+    img, mask, res, model_name = synth.make_case(case, seed=seed)
     cfg = vit_fp32.VIT_CONFIGS[model_name]
     H, W, S = img.shape
+    sample_slices = min(sample_slices, S)
     s0 = max(0, S // 2 - sample_slices // 2)
     sl = slice(s0, s0 + sample_slices)
-    w = vit_fp32.init_weights(cfg, (H, W), seed=1234)
+    w = weights if weights is not None else vit_fp32.init_weights(cfg, (H, W), seed=1234)
     x = torch.from_numpy(np.ascontiguousarray(np.moveaxis(img[:, :, sl], -1, 0)))[:, None].expand(-1, 3, -1, -1).contiguous()
     t0 = time.perf_counter()
     with torch.no_grad():
@@ -109,9 +163,11 @@ def cpu_baseline(case: str, sample_slices: int, threads: int | None = None):
     masks = [mask[my0:my1, mx0:mx1, s0 + i] for i in range(dense.shape[0])]
     out = gather_np.token_gather(feats, masks, res)
     dt = time.perf_counter() - t0
-    return dict(value=sample_slices / dt, unit="slices/s", cores=cores, kind="port",
-                sample=f"{sample_slices} of {S} slices of the {case} volume ({model_name}, {H}x{W}): fp32 torch ViT forward "
-                       f"+ NumPy mask gather ({out['flat'].size} tokens), {dt:.2f} s wall"), dt
+    cb = dict(value=sample_slices / dt, unit="slices/s", cores=cores, kind="port",
+              sample=f"{sample_slices} of {S} slices of the {case} volume ({model_name}, {H}x{W}): fp32 torch ViT forward (oracle/vit_fp32.py) "
+                     f"+ NumPy mask gather (oracle/gather_np.py restatement of _get_features; the reference sources are not on the GPU box), "
+                     f"{out['flat'].size} tokens, {dt:.2f} s wall")
+    return cb, dt, dense, (s0, sample_slices)
 
 
 # ----------------------------------------------------------------------------------------- reference arm
@@ -120,9 +176,9 @@ def run_reference(args):
     if rank != 0:
         return
     sample = args.sample_slices
-    vals = []
+    vals, cb = [], None
     for i in range(args.warmup + args.steps):
-        cb, dt = cpu_baseline(args.config, sample)
+        cb, dt, _, _ = cpu_extraction(args.config, sample)
         if i >= args.warmup:
             vals.append(dt)
     v = sample * len(vals) / sum(vals)
@@ -142,186 +198,416 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
-# ----------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch.distributed as dist
+# ----------------------------------------------------------------------------------------- extraction (C1 / C2 / C4)
+def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bool, cpu_slices: int, clocks: bool = False,
+                     patients_per_step: int = 1):
+    """One extraction config: `patients_per_step` synthetic volumes of `case` per rank per step.  Returns the record (rank 0
+    keeps it; all ranks run it: at N > 1 it contains collectives)."""
     from vit_deep_radiomics_b200 import _C, ops, synth, tfds_dense_descriptor as tdd
-    from vit_deep_radiomics_b200.distributed import init_distributed
-    rank, world = init_distributed("nccl")
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    img, mask, res, model_name = synth.make_case(args.config, seed=1235 + rank)
+    from vit_deep_radiomics_b200.distributed import PointCloudTable
+    rank, world, dev = D.rank, D.world, D.dev
+    P = patients_per_step
+    n_pat = world * P                                    # patients per step over the whole job; rank r owns [r*P, (r+1)*P)
+    vols = [synth.make_case(case, seed=1235 + rank * P + i) for i in range(P)]
+    img, mask, res, model_name = vols[0]
     H, W, S = img.shape
     model = tdd.load_model(model_name, img_hw=(H, W), device=dev, seed=1234)
-    plan = tdd._plan(model, mask)
+    ex = tdd.PointCloudExtractor(model)
     gh, gw = model.grid
+    dim = model.cfg["dim"]
+    peaks = measured_peaks()
 
     # resident inputs for `value`
-    img_dev = torch.as_tensor(img).to(dev)
-    mask_s = torch.as_tensor(np.ascontiguousarray(np.moveaxis(mask, -1, 0)).view(np.uint8)).to(dev)
+    img_dev = [torch.as_tensor(v[0]).to(dev) for v in vols]
+    mask_dev = [torch.as_tensor(np.ascontiguousarray(v[1]).view(np.uint8)).to(dev) for v in vols]
+    plans = [ex.plan_patient(m) for m in mask_dev]
+    geos = [dict(grid=(S, gh, gw, model.n_tokens, model.token_offset), feat_roi=p["feat_roi"],
+                 mask_roi=tdd._shift_roi(p["mask_roi"], p["crop"]), mask_layout="hws") for p in plans]
     pe = dict(res=res, noise=(0.0, 0.0, 0.0), scale=0.25)
+    cand = max(S * (p["feat_roi"][1] - p["feat_roi"][0]) * (p["feat_roi"][3] - p["feat_roi"][2]) for p in plans)
+    table = PointCloudTable(n_pat, dim, cap_rows=n_pat * cand, device=dev, rank=rank, world=world)
 
     def step_resident():
-        tok = tdd._forward_volume(model, img_dev, plan)
-        return ops.mask_gather(tok, mask_s, grid=(S, gh, gw, model.n_tokens, 1), feat_roi=plan["feat_roi"],
-                               mask_roi=plan["mask_roi"], pe=pe)
+        """counts -> (all-gather of counts, device scan) -> per patient backbone + gather at its table offset -> table all-gather"""
+        for i in range(P):
+            ops.mask_count(mask_dev[i], out=table.count_out(rank * P + i), **geos[i])
+        table.exchange_counts()
+        for i in range(P):
+            tok = tdd._forward_volume(model, img_dev[i], plans[i])
+            ops.mask_gather(tok, mask_dev[i], pe=pe, table=table.slot(rank * P + i), **geos[i])
+        return table.all_gather()
 
     # pinned host inputs for `e2e`
-    img_pin = torch.as_tensor(img).pin_memory()
-    mask_pin = torch.as_tensor(np.ascontiguousarray(mask).view(np.uint8)).pin_memory()
-
-    extractor = tdd.PointCloudExtractor(model)
+    img_pin = [torch.as_tensor(v[0]).pin_memory() for v in vols]
+    mask_pin = [torch.as_tensor(np.ascontiguousarray(v[1]).view(np.uint8)).pin_memory() for v in vols]
+    host_tok = host_src = None
 
     def run_e2e(k):
-        """k patients through the public streaming API: H2D of patient i+1 overlaps the backbone of patient i;
-        every patient's point cloud is read back to the host."""
-        last = None
-        for out in extractor.run([(img_pin, mask_pin, res)] * k):
-            last = out
-        return last
+        """k steps through the public API from pinned host buffers.  N = 1: the streaming extractor (upload of patient i+1
+        overlaps the backbone of patient i), every point cloud read back.  N > 1: the sharded extraction into one table
+        (PointCloudExtractor.run_table): k*P patients per rank, one count exchange, one table all-gather, every rank reads its
+        own row range back (the table itself stays on every GPU for the trainer)."""
+        nonlocal host_tok, host_src
+        if world == 1:
+            last = None
+            for out in ex.run([(img_pin[i % P], mask_pin[i % P], res) for i in range(k * P)]):
+                last = out
+            return last["count"] * P
+        tb = PointCloudTable(world * k * P, dim, cap_rows=world * k * P * cand, device=dev, rank=rank, world=world)
+        items = [(rank * k * P + j, img_pin[j % P], mask_pin[j % P], res) for j in range(k * P)]
+        total = ex.run_table(items, tb)
+        lo, hi = tb.rank_ranges()[rank]
+        if host_tok is None or host_tok.shape[0] < hi - lo:
+            host_tok = torch.empty((hi - lo, dim), dtype=torch.float32).pin_memory()
+            host_src = torch.empty((hi - lo, 4), dtype=torch.int32).pin_memory()
+        host_tok[:hi - lo].copy_(tb.tokens[lo:hi], non_blocking=True)
+        host_src[:hi - lo].copy_(tb.src[lo:hi], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return (hi - lo) // k
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, profile=False):
-        barrier()
-        if profile:
-            ops.PROFILE = []
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        prof, ops.PROFILE = ops.PROFILE, None
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, out, prof
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_resident()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(D.local) if clocks and rank == 0 else None
+    if sampler:
         sampler.start()
     launches0 = _C.launch_count()
-    ms, out, _ = timed(step_resident, args.steps)
+    ms, total_rows = D.timed(step_resident, steps)
     launches = _C.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    n_tokens = int(out[2].item())
-    value = world * S * args.steps / (ms / 1e3)
+    clk = sampler.stop() if sampler else None
+    n_tokens = int(table.rank_ranges()[rank][1] - table.rank_ranges()[rank][0]) // P
+    value = n_pat * S * steps / (ms / 1e3)
+    flops_step = model.flops_per_slice() * S * P
+    rec = {"workload": f"{case}: {model_name} dense descriptors over synthetic {H}x{W}x{S} CT volumes with mask-gathered point cloud "
+                       f"({n_tokens} tokens per volume), {P} volume(s) per GPU per step" +
+                       (f", patients sharded over {world} ranks + in-place NCCL all-gather of the point-cloud table every step" if world > 1 else ""),
+           "value": value, "unit": "slices/s", "patients_per_s": n_pat * steps / (ms / 1e3), "ms_per_step": ms / steps,
+           "model_tflops": flops_step * world * steps / (ms / 1e3) / 1e12, "gpu_launches": int(launches), "clocks": clk}
+    rec.update({("model_" + k): v for k, v in tensor_fracs(rec["model_tflops"] / world, peaks).items()})
 
-    # per-kernel profile pass (CUDA events around every GEMM launch, same stream), separate from `value`; it runs the
-    # op-by-op path (the native vdr_vit_forward call cannot be instrumented from here): one untimed step first, so that
-    # its activation buffers exist
-    ops.PROFILE = []
-    step_resident()
-    ops.PROFILE = None
-    ms_p, _, prof = timed(step_resident, max(1, min(args.steps, 3)), profile=True)
-    torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for (kind, fl, a, b, _) in prof if kind == "gemm")
-    gemm_fl = sum(fl for (kind, fl, a, b, _) in prof if kind == "gemm")
-    attn_ms = sum(a.elapsed_time(b) for (kind, fl, a, b, _) in prof if kind == "attn")
-    attn_fl = sum(fl for (kind, fl, a, b, _) in prof if kind == "attn")
-    n_gemm = sum(1 for p in prof if p[0] == "gemm")
-    by_label = {}
-    for (kind, fl, a, b, label) in prof:
-        t = by_label.setdefault(label, [0, 0.0, 0.0])
-        t[0] += 1
-        t[1] += a.elapsed_time(b)
-        t[2] += fl
-    kinds = {label: kind for (kind, fl, a, b, label) in prof}
-    per_kernel = {}
-    for k, v in sorted(by_label.items(), key=lambda kv: -kv[1][1]):
-        e = {"launches": v[0], "ms_per_launch": v[1] / v[0]}
-        if kinds[k] == "ln":      # HBM-bound: algorithmic bytes / time
-            e["gbs"] = v[2] / (v[1] / 1e3) / 1e9
-        else:
-            e["tflops"] = v[2] / (v[1] / 1e3) / 1e12
-        per_kernel[k] = e
+    # ---- the exchange step alone (N > 1): events around table.all_gather() after a barrier, max over ranks; bit-identity check
+    if world > 1:
+        ms_c, _ = D.timed(table.all_gather, 5)
+        row_bytes = dim * 4 + 16
+        tot_bytes = table.total * row_bytes
+        rec["collective"] = {"kind": "in-place variable-length all-gather of the point-cloud table (ncclAllGather when the row ranges are equal, "
+                                     "else grouped ncclBroadcast per rank) + all-gather of the int64 row counts",
+                             "bytes_per_step": int(tot_bytes), "rows": int(table.total), "ms": ms_c / 5,
+                             "busbw_gbs": tot_bytes * (world - 1) / world / (ms_c / 5 / 1e3) / 1e9,
+                             "nvlink_peer_gbs_measured": NVLINK_PEER_GBS,
+                             "share_of_step": (ms_c / 5) / (ms / steps),
+                             "limiting": "launch/latency-bound at this size (a few MB per rank): the table rows are ~0.5 % of a step's HBM traffic"}
+        # rank 0 recomputes patient P (rank 1's first volume) alone on its GPU through the 1-GPU path: the gathered rows must be bit-identical
+        ok = None
+        if rank == 0:
+            v1 = synth.make_case(case, seed=1235 + 1 * P)
+            o1 = tdd.extract_point_cloud(model, v1[0], v1[1], v1[2], to_host=False)
+            n1 = int(o1["count"].item())
+            lo = int(table.offsets[table._slot_index(P)].item())
+            ok = bool(n1 == int(table.counts_host[table._slot_index(P)]) and torch.equal(table.tokens[lo:lo + n1], o1["tokens"][:n1])
+                      and torch.equal(table.src[lo:lo + n1, 1:], o1["src"][:n1]) and bool((table.src[lo:lo + n1, 0] == P).all()))
+        rec["collective"]["table_bit_identical_to_1gpu"] = ok
 
-    # The HBM-bound kernels of the path, timed alone (CUDA events, 10 launches each after 3 warm-ups):
-    #   mask gather of this volume (C2: 5 k tokens out of a 14 k-candidate ROI -> launch / host-latency bound, reported as is)
-    #   and of a dense mask over the whole token grid (every token selected: the bandwidth of the compaction + emit kernels);
-    #   algorithmic bytes per SURVEY 8d: S*h*w mask bytes + n_sel * (D*4 read + D*4 written + 12).
-    def time_gather(mask_dev, roi, reps=10):
+    # ---- per-kernel profile pass (CUDA events around every GEMM / attention launch, same stream), separate from `value`; it runs
+    # the op-by-op path (the native vdr_vit_forward call cannot be instrumented from here)
+    if profile:
+        ops.PROFILE = []
+        tdd._forward_volume(model, img_dev[0], plans[0])           # untimed: the op-by-op activation buffers get allocated
+        ops.PROFILE = None
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        reps = max(1, min(steps, 3))
+        for _ in range(reps):
+            tdd._forward_volume(model, img_dev[0], plans[0])
+        p1.record()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        ms_p = p0.elapsed_time(p1)
+        tot = {}
+        for kind, fl, a, b, label in prof:
+            t = tot.setdefault(kind, [0.0, 0.0, 0])
+            t[0] += a.elapsed_time(b)
+            t[1] += fl
+            t[2] += 1
+        by_label = {}
+        for kind, fl, a, b, label in prof:
+            t = by_label.setdefault(label, [0, 0.0, 0.0, kind])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+            t[2] += fl
+        per_kernel = {}
+        for k, v in sorted(by_label.items(), key=lambda kv: -kv[1][1]):
+            e = {"launches": v[0], "ms_per_launch": v[1] / v[0]}
+            if v[3] == "ln":                                       # HBM-bound: algorithmic bytes / time
+                e["gbs"] = v[2] / (v[1] / 1e3) / 1e9
+            else:
+                e["tflops"] = v[2] / (v[1] / 1e3) / 1e12
+            per_kernel[k] = e
+        g_ms, g_fl, g_n = tot.get("gemm", [0.0, 0.0, 0])
+        a_ms, a_fl, _ = tot.get("attn", [0.0, 0.0, 0])
+        achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if case == "C2" and os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        attn = a_fl / (a_ms / 1e3) / 1e12 if a_ms else None
+        rec["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                           **tensor_fracs(achieved, peaks), "peak_burst": peaks["burst"], "peak_nominal": NOMINAL_BF16_TFLOPS,
+                           "traffic": traffic,
+                           "traffic_source": "dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/gemm_traffic.json); "
+                                             "a constant of that capture, NOT measured in this run" if traffic else None,
+                           "peak_source": peaks["source"], "launches_timed": g_n, "share_of_step": g_ms / ms_p if ms_p else None,
+                           "attention": {"achieved": attn, **tensor_fracs(attn, peaks), "share_of_step": a_ms / ms_p if ms_p else None},
+                           "per_kernel": per_kernel}
+
+    # ---- the HBM-bound kernel of the path, the mask gather, timed alone: CUDA events around 10 launches after 3 warm-ups.
+    # algorithmic bytes per SURVEY 8d: S*h*w mask bytes + n_sel * (D*4 read + D*4 written + 12).
+    def time_gather(mask_t, geo, reps=10):
+        """Device time of the gather alone: per repetition an L2 flush (1 GiB memset: also keeps the GPU busy long enough for the host
+        to enqueue the next launch, so no launch gap is measured), then CUDA events right around the one cooperative launch."""
         tok = model._workspace(S)["OUT"]
-        froi, mroi = (plan["feat_roi"], plan["mask_roi"]) if roi else (None, None)
-        call = lambda: ops.mask_gather(tok, mask_dev, grid=(S, gh, gw, model.n_tokens, 1), feat_roi=froi,  # noqa: E731
-                                       mask_roi=mroi, pe=pe)
+        flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        call = lambda: ops.mask_gather(tok, mask_t, pe=pe, **geo)          # noqa: E731
         for _ in range(3):
             out_g = call()
         torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
+        evs = []
         for _ in range(reps):
+            flush.zero_()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
             out_g = call()
-        g1.record()
+            g1.record()
+            evs.append((g0, g1))
         torch.cuda.synchronize()
         n_sel = int(out_g[2].item())
-        r0, r1, c0, c1 = plan["feat_roi"] if roi else (0, gh, 0, gw)
-        cand = S * (r1 - r0) * (c1 - c0)
-        nbytes = cand + n_sel * (model.cfg["dim"] * 8 + 12)
-        ms_g = g0.elapsed_time(g1) / reps
-        return {"ms": ms_g, "selected": n_sel, "candidates": cand, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms_g / 1e3) / 1e9}
+        r0, r1, c0, c1 = geo["feat_roi"] if geo["feat_roi"] is not None else (0, gh, 0, gw)
+        cand_g = S * (r1 - r0) * (c1 - c0)
+        nbytes = cand_g + n_sel * (dim * 8 + 12)
+        ms_g = sum(a.elapsed_time(b) for a, b in evs) / reps
+        del flush
+        return {"ms": ms_g, "selected": n_sel, "candidates": cand_g, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms_g / 1e3) / 1e9,
+                "frac_measured": nbytes / (ms_g / 1e3) / 1e9 / peaks["hbm"], "frac_nominal": nbytes / (ms_g / 1e3) / 1e9 / NOMINAL_HBM_GBS,
+                "launches": 1, "timing": "CUDA events around each launch, L2 flushed before every repetition"}
 
-    gather_c2 = time_gather(mask_s, roi=True)                        # the workload's own gather (ROI of the tumour, ~35 % selected)
-    gather_dense = time_gather(torch.ones_like(mask_s), roi=False)   # whole 32x32xS grid, every token selected
+    if profile:
+        dense_geo = dict(grid=geos[0]["grid"], feat_roi=None, mask_roi=None, mask_layout="hws")
+        rec["roofline"]["hbm_kernels"] = {
+            "kernel": "g1_fused_kernel (one cooperative launch: PE table + predicate/ballots + scan + ranks + emit)", "peak_gbs": peaks["hbm"],
+            "peak_nominal_gbs": NOMINAL_HBM_GBS,
+            "mask_gather_own": time_gather(mask_dev[0], geos[0]),                      # the workload's own gather (ROI of the tumour)
+            "mask_gather_dense": time_gather(torch.ones_like(mask_dev[0]), dense_geo)}  # whole token grid, every token selected
 
+    # ---- e2e
     run_e2e(2)
-    ms_e, out_e, _ = timed(lambda: run_e2e(args.steps), 1)
-    e2e_value = world * S * args.steps / (ms_e / 1e3)
-    h2d = img_pin.numel() * 4 + mask_pin.numel()
-    d2h = out_e["count"] * (model.cfg["dim"] * 4 + 12) + 4
+    ms_e, per_step_rows = D.timed(lambda: run_e2e(steps), 1)
+    rec["e2e"] = {"value": n_pat * S * steps / (ms_e / 1e3), "unit": "slices/s",
+                  "h2d_bytes_per_step": int(P * (img_pin[0].numel() * 4 + mask_pin[0].numel())),
+                  "d2h_bytes_per_step": int(per_step_rows * (dim * 4 + (12 if world == 1 else 16)) + 4), "ms_per_step": ms_e / steps,
+                  "api": "tfds_dense_descriptor.PointCloudExtractor.run (pinned host buffers, uploads double-buffered on a copy stream)" if world == 1 else
+                         "tfds_dense_descriptor.PointCloudExtractor.run_table into a distributed.PointCloudTable (pinned host buffers; counts all-gather, "
+                         "table all-gather and the read-back of each rank's row range inside the timed region)"}
 
-    if rank != 0:
-        return
-    medsam = medsam_side_measurement(dev) if args.medsam else None
+    # ---- CPU leg + parity of the device descriptors against the fp32 oracle on the CPU leg's slices (rank 0)
+    if rank == 0:
+        cb, _, dense, (s0, ns) = cpu_extraction(case, cpu_slices, weights=model.state_dict_f32)
+        rec["cpu_baseline"] = cb
+        x = torch.from_numpy(np.ascontiguousarray(np.moveaxis(vols[0][0][:, :, s0:s0 + min(ns, 2)], -1, 0))).to(dev)
+        got = model.dense_descriptors(x).cpu().numpy().astype(np.float64)
+        want = dense[:got.shape[0]].astype(np.float64)
+        g2, w2 = got.reshape(-1, dim), want.reshape(-1, dim)
+        cos = (g2 * w2).sum(1) / (np.linalg.norm(g2, axis=1) * np.linalg.norm(w2, axis=1))
+        rec["parity"] = {"what": f"bf16 device descriptors vs the fp32 oracle, {got.shape[0]} slices of this workload ({model_name}@{H}x{W})",
+                         "max_abs": float(np.abs(got - want).max()), "rms_rel": float(np.sqrt(((got - want) ** 2).sum() / (want ** 2).sum())),
+                         "min_cosine": float(cos.min()), "gather_indices": "bit-exact (tests/test_gpu_gather.py, test_gpu_pipeline.py)"}
+    return rec
+
+
+# ----------------------------------------------------------------------------------------- classifier (c3) and pipeline (C5)
+def _classifier_flops(n, d, ff, layers):
+    """F_fwd = L*(8 n d^2 + 4 n d ff + 4 n^2 d) + 4 d^2 + 8 d with n including the CLS token."""
+    return layers * (8.0 * n * d * d + 4.0 * n * d * ff + 4.0 * n * n * d) + 4.0 * d * d + 8.0 * d
+
+
+def bench_classifier(D: Dist, samples: int = 64, epochs: int = 2, cpu_samples: int = 2):
+    """C3: point-cloud transformer training (fwd + focal loss + bwd, AdamW every 32-sample virtual batch split over the ranks,
+    ONE flat-bucket gradient all-reduce per optimizer step) on synthetic clouds; samples/s over all ranks."""
+    from vit_deep_radiomics_b200 import _C, synth
+    from vit_deep_radiomics_b200.distributed import allreduce_grads, grad_bucket, zero_grads
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier
+    from vit_deep_radiomics_b200.train_models import FocalLoss
+    rank, world, dev = D.rank, D.world, D.dev
+    ids, labels, sizes, cloud = synth.point_cloud_patients(samples, d=256, n_range=(512, 4096), seed=1236)
+    torch.manual_seed(0)
+    model = TransformerNoduleClassifier(256, 1024, 4, 2, 2).to(dev)
+    if world > 1:
+        with torch.no_grad():
+            for p in model.parameters():
+                torch.distributed.broadcast(p, 0)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.01)
+    crit = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=dev), gamma=2)
+    mine = list(range(rank, samples, world))
+    data = [(torch.from_numpy(cloud(i)).to(dev), torch.eye(2, device=dev)[int(labels[i])]) for i in mine]
+    window = max(1, 32 // world)
+    bucket = grad_bucket(model)
+
+    def epoch():
+        zero_grads(model, opt)
+        tot = torch.zeros((), device=dev)
+        for k, (x, y) in enumerate(data):
+            logits, _ = model(x.unsqueeze(0))
+            loss = crit(torch.squeeze(logits), y) / 32                      # train_models.py:674
+            loss.backward()
+            tot += loss.detach()
+            if (k + 1) % window == 0 or k + 1 == len(data):                  # :685
+                allreduce_grads(model)
+                opt.step()
+                zero_grads(model, opt)
+        return tot
+
+    l0 = float(epoch()) * 32 / len(data)
+    n0 = _C.launch_count()
+    ms, tot = D.timed(epoch, epochs)
+    launches = _C.launch_count() - n0
+    l1 = float(tot) * 32 / len(data)
+    rec = {"workload": f"C3: TransformerNoduleClassifier(256, ff 1024, 4 heads, 2 layers) training on {samples} synthetic point clouds of 512..4096 tokens, "
+                       f"virtual batch 32 split over {world} rank(s), AdamW, focal loss",
+           "value": samples * epochs / (ms / 1e3), "unit": "samples/s", "ms_per_sample_per_gpu": ms / (epochs * len(data)),
+           "gpu_launches": int(launches), "loss_first_epoch": l0, "loss_last_epoch": l1}
+    flops = sum(3.0 * _classifier_flops(int(sizes[i]) + 1, 256, 1024, 2) for i in range(samples)) * epochs
     peaks = measured_peaks()
-    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-    if os.path.isfile(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    cb, _ = cpu_baseline(args.config, args.cpu_sample_slices)     # ~10 s of host work on rank 0
-    c = synth.CONFIGS[args.config]
-    flops_step = model.flops_per_slice() * S
-    print(json.dumps({
-        "metric": "CT slices/sec ViT dense-descriptor extraction + mask gather", "value": value, "unit": "slices/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {c['model']} dense descriptors over a synthetic {H}x{W}x{S} CT volume with "
-                               f"mask-gathered point cloud ({n_tokens} tokens), one volume per GPU per step",
-                   "l2": "inputs+activations per step (>1.5 GB) exceed the 126 MB L2; no explicit flush",
-                   "weights": "seeded random init (no checkpoints offline)"},
-        "model_tflops": flops_step * world * args.steps / (ms / 1e3) / 1e12,
-        "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e / args.steps, "api": "tfds_dense_descriptor.PointCloudExtractor.run (pinned host buffers, uploads double-buffered on a copy stream)"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16"],
-                     "unit": "TFLOP/s", "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": traffic,
-                     "peak_source": peaks["source"], "launches_timed": n_gemm,
-                     "share_of_step": gemm_ms / ms_p if ms_p else None,
-                     "attention": {"achieved": attn_fl / (attn_ms / 1e3) / 1e12 if attn_ms else None,
-                                   "share_of_step": attn_ms / ms_p if ms_p else None},
-                     "per_kernel": per_kernel,
-                     "hbm_kernels": {"peak_gbs": peaks["hbm"], "mask_gather_c2": gather_c2, "mask_gather_dense": gather_dense,
-                                     "mask_gather_dense_frac": gather_dense["gbs"] / peaks["hbm"] if peaks["hbm"] else None}},
-        "cpu_baseline": cb,
-        "clocks": clocks,
-        "n1_medsam": medsam}))
+    tfl = flops / (ms / 1e3) / 1e12
+    rec["roofline"] = {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "peak": peaks["bf16"], **tensor_fracs(tfl / world, peaks),
+                       "note": "fwd+bwd algorithmic flops (3 x forward) over the whole step incl. optimizer; batch-1 sequences of <= 4k tokens are launch- "
+                               "and latency-bound, not tensor-bound"}
+    if world > 1:
+        ms_c, _ = D.timed(bucket.allreduce, 10)
+        nbytes = bucket.flat.numel() * 4
+        rec["collective"] = {"kind": "ncclAllReduce(sum) of the persistent flat fp32 gradient bucket (param.grad tensors are views of it)",
+                             "bytes_per_step": int(nbytes), "ms": ms_c / 10, "busbw_gbs": nbytes * 2 * (world - 1) / world / (ms_c / 10 / 1e3) / 1e9,
+                             "per_optimizer_step": True, "limiting": "latency-bound (6.85 MB)"}
+        bucket.zero()
+    if rank == 0:
+        from oracle import classifier_fp32 as C
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        t1 = time.perf_counter()
+        for i in range(cpu_samples):
+            lg, _ = C.classifier_forward(sd, torch.from_numpy(cloud(i))[None], 4, 2)
+            C.focal_loss(lg[0], torch.eye(2)[int(labels[i])], 2.0, torch.tensor([0.25, 0.75])).backward()
+        cpu_dt = time.perf_counter() - t1
+        rec["cpu_baseline"] = {"value": cpu_samples / cpu_dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"first {cpu_samples} clouds ({int(sizes[0])}, {int(sizes[1])} tokens), fp32 oracle fwd+bwd (oracle/classifier_fp32.py, "
+                                         f"pinned to the unmodified models_archs module), {cpu_dt:.2f} s wall"}
+    # e2e: clouds start in pinned host memory, the loss comes back per sample
+    pin = [(torch.from_numpy(cloud(i)).pin_memory(), torch.eye(2)[int(labels[i])].pin_memory()) for i in mine[:8]]
+
+    def e2e_pass():
+        zero_grads(model, opt)
+        for k, (x, y) in enumerate(pin):
+            logits, _ = model(x.to(dev, non_blocking=True).unsqueeze(0))
+            loss = crit(torch.squeeze(logits), y.to(dev, non_blocking=True)) / 32
+            loss.backward()
+            float(loss.item())                                               # :681 the reference reads the loss back every sample
+        allreduce_grads(model)
+        opt.step()
+
+    e2e_pass()
+    ms_e, _ = D.timed(e2e_pass, 1)
+    rec["e2e"] = {"value": world * len(pin) / (ms_e / 1e3), "unit": "samples/s",
+                  "h2d_bytes_per_step": int(sum(x.numel() * 4 + 8 for x, _ in pin) / len(pin)), "d2h_bytes_per_step": 4,
+                  "api": "models_archs.TransformerNoduleClassifier.forward + FocalLoss + backward per sample from pinned host clouds, loss.item() per sample "
+                         "(as train_models.py:681), one optimizer step per 8 samples per rank"}
+    return rec
 
 
-def medsam_side_measurement(dev, B=8, steps=3):
-    """Not part of `value`: the reference's own default backbone (load_model('medsam'): SAM ViT-B image encoder, 1024 x 1024
-    inputs, (64, 64, 256) descriptors) through the same libvdr kernels, B resident gray slices per pass."""
+def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4):
+    """C5: per patient a 512x512x120 volume goes through ViT-B/16 extraction, the mask gather (+ PE) and ONE training step of the
+    point-cloud classifier on the 768-wide descriptors (feature_dim 768 / 12 heads in the YAML schema; the reference's 256 comes
+    from MedSAM's neck); volumes uploaded inside the timed region; patients/s over all ranks."""
+    from vit_deep_radiomics_b200 import _C, synth, tfds_dense_descriptor as tdd
+    from vit_deep_radiomics_b200.distributed import allreduce_grads, zero_grads
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier
+    from vit_deep_radiomics_b200.train_models import FocalLoss
+    rank, world, dev = D.rank, D.world, D.dev
+    img, mask, res, name = synth.make_case("C2", seed=1238 + rank)
+    H, W, S = img.shape
+    backbone = tdd.load_model(name, img_hw=(H, W), device=dev, seed=1234)
+    dim = backbone.feature_dim
+    torch.manual_seed(0)
+    clf = TransformerNoduleClassifier(dim, 4 * dim, dim // 64, 2, 2).to(dev)
+    if world > 1:
+        with torch.no_grad():
+            for p in clf.parameters():
+                torch.distributed.broadcast(p, 0)
+    opt = torch.optim.AdamW(clf.parameters(), lr=5e-4, weight_decay=0.01)
+    crit = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=dev), gamma=2)
+    img_pin = torch.as_tensor(img).pin_memory()
+    mask_pin = torch.as_tensor(np.ascontiguousarray(mask).view(np.uint8)).pin_memory()
+    ex = tdd.PointCloudExtractor(backbone)
+    window = max(1, 32 // world)
+    labels = [torch.eye(2, device=dev)[i % 2] for i in range(2)]
+    n_tok = 0
+
+    def run(k):
+        nonlocal n_tok
+        zero_grads(clf, opt)
+        last = None
+        for i, out in enumerate(ex.run([(img_pin, mask_pin, res)] * k, to_host=False)):
+            n_tok = int(out["count"].item())                # the point cloud's size is data-dependent: one 4-byte read-back
+            logits, _ = clf(out["tokens"][:n_tok].unsqueeze(0))
+            loss = crit(torch.squeeze(logits), labels[i % 2]) / 32
+            loss.backward()
+            last = loss
+            if (i + 1) % window == 0 or i + 1 == k:
+                allreduce_grads(clf)
+                opt.step()
+                zero_grads(clf, opt)
+        return float(last.detach())
+
+    run(2)
+    n0 = _C.launch_count()
+    ms, loss = D.timed(lambda: run(patients), 1)
+    launches = _C.launch_count() - n0
+    peaks = measured_peaks()
+    flops = patients * world * (backbone.flops_per_slice() * S + 3.0 * _classifier_flops(n_tok + 1, dim, 4 * dim, 2))
+    tfl = flops / (ms / 1e3) / 1e12
+    v = world * patients / (ms / 1e3)
+    rec = {"workload": f"C5: {name} extraction over a {H}x{W}x{S} volume -> mask gather + PE ({n_tok} tokens) -> 2-layer transformer classifier "
+                       f"(d {dim}, {dim // 64} heads) training step per patient, {patients} patients per rank, gradient all-reduce per {window} patients per rank",
+           "value": v, "unit": "patients/s", "slices_per_s": v * S, "ms_per_patient": ms / patients, "gpu_launches": int(launches), "loss": loss,
+           "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "peak": peaks["bf16"], **tensor_fracs(tfl / world, peaks),
+                        "note": "algorithmic flops of the backbone + 3 x classifier forward over the whole per-patient time (uploads, gather, optimizer included)"},
+           "e2e": {"value": v, "unit": "patients/s", "h2d_bytes_per_step": int(img_pin.numel() * 4 + mask_pin.numel()), "d2h_bytes_per_step": 8,
+                   "api": "PointCloudExtractor.run(to_host=False) -> TransformerNoduleClassifier -> FocalLoss.backward; the timed region IS end to end "
+                          "(pinned host volumes in, the token count and the loss out)"}}
+    if rank == 0:
+        from oracle import classifier_fp32 as C, gather_np, vit_fp32
+        torch.set_num_threads(os.cpu_count() or 1)
+        cfg = vit_fp32.VIT_CONFIGS[name]
+        s0 = S // 2 - cpu_slices // 2
+        x = torch.from_numpy(np.ascontiguousarray(np.moveaxis(img[:, :, s0:s0 + cpu_slices], -1, 0)))[:, None].expand(-1, 3, -1, -1).contiguous()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            dense = vit_fp32.vit_forward(backbone.state_dict_f32, cfg, x).numpy()
+        o = gather_np.token_gather([dense[i] for i in range(dense.shape[0])], [mask[:, :, s0 + i] for i in range(dense.shape[0])], res)
+        sd = {k: v_.detach().cpu().clone().requires_grad_(True) for k, v_ in clf.state_dict().items()}
+        lg, _ = C.classifier_forward(sd, torch.from_numpy(o["tokens"].astype(np.float32))[None], dim // 64, 2)
+        C.focal_loss(lg[0], torch.eye(2)[0], 2.0, torch.tensor([0.25, 0.75])).backward()
+        cpu_dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": (cpu_slices / S) / cpu_dt, "unit": "patients/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"{cpu_slices} of {S} slices through the fp32 oracle ViT + NumPy gather + oracle classifier fwd/bwd "
+                                         f"({o['flat'].size} tokens), {cpu_dt:.2f} s wall, scaled by slices"}
+    return rec
+
+
+def bench_medsam(D: Dist, B: int = 8, steps: int = 3, cpu: bool = True):
+    """The reference's own default backbone (load_model('medsam'): SAM ViT-B image encoder, 1024 x 1024 inputs, (64, 64, 256)
+    descriptors) through the same libvdr kernels, B gray slices per pass on rank 0's GPU."""
     from vit_deep_radiomics_b200 import _C, tfds_dense_descriptor as tdd
+    dev = D.dev
     model = tdd.load_model("medsam", device=dev, seed=1)
     x = torch.rand(B, 1024, 1024, device=dev)
     strides = (x.stride(0), 0, x.stride(1), x.stride(2))
@@ -336,8 +622,75 @@ def medsam_side_measurement(dev, B=8, steps=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"metric": "MedSAM (SAM ViT-B) encoder slices/s, 1024x1024 gray slices resident, 1 GPU", "value": B / ms * 1e3, "batch": B,
-            "ms_per_batch": ms, "model_tflops": model.flops_per_slice() * B / ms / 1e9, "gpu_launches_per_batch": (_C.launch_count() - n0) // steps}
+    launches = (_C.launch_count() - n0) // steps
+    peaks = measured_peaks()
+    tfl = model.flops_per_slice() * B / ms / 1e9
+    rec = {"workload": f"MedSAM (SAM ViT-B image encoder, the reference's default backbone): {B} gray 1024x1024 slices per pass -> (64, 64, 256) descriptors, 1 GPU",
+           "value": B / ms * 1e3, "unit": "slices/s", "ms_per_batch": ms, "gpu_launches_per_batch": int(launches),
+           "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "peak": peaks["bf16"], **tensor_fracs(tfl, peaks),
+                        "note": "942 GFLOP per slice (patch embed + block GEMMs 701, global attention incl. bias 209, windowed attention 25, neck 6) over the whole pass"}}
+    # e2e: pinned host slices in, descriptors back to the host
+    xp = torch.rand(B, 1024, 1024).pin_memory()
+    out_host = torch.empty((B, 64, 64, 256), dtype=torch.float32).pin_memory()
+
+    def e2e():
+        xd = xp.to(dev, non_blocking=True)
+        d = model.dense_descriptors(xd)
+        out_host.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e()
+    ms_e, _ = D.timed(e2e, 2) if D.world == 1 else (None, None)
+    if ms_e:
+        rec["e2e"] = {"value": 2 * B / (ms_e / 1e3), "unit": "slices/s", "h2d_bytes_per_step": int(xp.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                      "api": "SamImageEncoder.dense_descriptors on pinned host slices, descriptors copied back (what get_dense_descriptor returns, batched)"}
+    if cpu:
+        from oracle import sam_fp32
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, xp[:1, None].expand(-1, 3, -1, -1))
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": 1.0 / dt, "unit": "slices/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"1 slice through oracle/sam_fp32.py (fp32 restatement of segment_anything's ImageEncoderViT, pinned to HF SamVisionEncoder), {dt:.2f} s wall"}
+    return rec
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    D = Dist()
+    rank, world = D.rank, D.world
+    from vit_deep_radiomics_b200 import synth
+    main = bench_extraction(D, args.config, args.steps, args.warmup, profile=True, cpu_slices=args.cpu_sample_slices, clocks=True)
+    sub = {}
+    if args.sub:
+        torch.cuda.empty_cache()
+        if world == 1:
+            sub["C1"] = bench_extraction(D, "C1", 20, 3, profile=True, cpu_slices=8)
+        torch.cuda.empty_cache()
+        sub["C4"] = bench_extraction(D, "C4", 5, 3, profile=(world == 1), cpu_slices=8, patients_per_step=8)
+        torch.cuda.empty_cache()
+        sub["c3"] = bench_classifier(D)
+        torch.cuda.empty_cache()
+        sub["C5"] = bench_pipeline(D)
+        torch.cuda.empty_cache()
+        if world == 1 and args.medsam:
+            sub["medsam"] = bench_medsam(D)
+    if rank != 0:
+        return
+    c = synth.CONFIGS[args.config]
+    line = {
+        "metric": "CT slices/sec ViT dense-descriptor extraction + mask gather", "value": main["value"], "unit": "slices/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": main["workload"],
+                   "l2": "inputs+activations per step (>1.5 GB) exceed the 126 MB L2; no explicit flush",
+                   "weights": "seeded random init (no checkpoints offline)", "model": c["model"]},
+        "model_tflops": main["model_tflops"], "model_frac": main["model_frac"], "model_frac_burst": main["model_frac_burst"],
+        "model_frac_nominal": main["model_frac_nominal"],
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main.get("roofline"), "cpu_baseline": main.get("cpu_baseline"),
+        "parity": main.get("parity"), "clocks": main["clocks"], "collective": main.get("collective"), "sub": sub}
+    print(json.dumps(line))
 
 
 def main():
@@ -350,7 +703,8 @@ def main():
     ap.add_argument("--sample-slices", type=int, default=8, dest="sample_slices")
     ap.add_argument("--cpu-sample-slices", type=int, default=32, dest="cpu_sample_slices",
                     help="slices of the workload the cpu_baseline leg of our arm runs on the host cores (~0.3 s per slice)")
-    ap.add_argument("--no-medsam", action="store_false", dest="medsam", help="skip the MedSAM side measurement (key n1_medsam)")
+    ap.add_argument("--no-sub", action="store_false", dest="sub", help="skip the sub-records (C1, C4, c3, C5, medsam)")
+    ap.add_argument("--no-medsam", action="store_false", dest="medsam", help="skip the MedSAM sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -270,6 +270,9 @@ int vdr_mask_gather_table(const void* feat, int feat_dtype, int64_t ld_feat, int
  * rank exchanges before any rank emits. */
 int vdr_mask_count(const uint8_t* mask, int64_t mask_slice_stride, int64_t mask_row_stride, int64_t mask_col_stride,
                    const int32_t* row_map, const int32_t* col_map, int S, int h, int w, int64_t* out_count, vdr_stream_t stream);
+/* Diagnostics: when set to a device buffer of 16 uint64, the gather kernel stamps %globaltimer of its first ([0..6]) and last
+ * ([8..14]) block at its phase boundaries (start, table, count, sync, ranks, sync, emit).  NULL (default) switches it off. */
+int vdr_debug_set_gather_trace(void* dev_u64x16);
 /* offsets[i] = sum(counts[0..i)), i = 0..n (n + 1 values, device): table row offsets of n patients' slots. */
 int vdr_exclusive_scan_i64(const int64_t* counts, int n, int64_t* offsets, vdr_stream_t stream);
 

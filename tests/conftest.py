@@ -7,6 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))     # tests/parity.py (stated tolerances + measured-error log)
 
 
 def pytest_configure(config):
@@ -25,3 +27,18 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured parity triplets of this session -> gpurun_out/parity_measured.json (tests/parity.py)."""
+    import json
+    import parity
+    if not parity.LOG:
+        return
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.json"), "w") as f:
+            json.dump(parity.LOG, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

@@ -7,10 +7,12 @@ import numpy as np
 import pytest
 import torch
 
+import parity
+
 pytestmark = pytest.mark.gpu
 
-# |descriptor error| <= ABS_TOL (final-LayerNorm outputs are O(1)), rms relative error <= REL_TOL, cosine >= COS
-ABS_TOL, REL_TOL, COS = 0.12, 0.02, 0.999
+# per config: |descriptor error| (final-LayerNorm outputs are O(1)), rms relative error, min token cosine -- the stated bounds
+# live in tests/parity.py (about twice what a B200 run measured), the measured values go to gpurun_out/parity_measured.json
 
 
 def _oracle_dense(model, imgs_nchw):
@@ -19,13 +21,8 @@ def _oracle_dense(model, imgs_nchw):
         return vit_fp32.vit_forward(model.state_dict_f32, vit_fp32.VIT_CONFIGS[model.model_name], imgs_nchw).numpy()
 
 
-def _check_descriptors(got, want):
-    got, want = got.astype(np.float64), want.astype(np.float64)
-    err = np.abs(got - want).max()
-    rel = np.sqrt(((got - want) ** 2).sum() / (want ** 2).sum())
-    g2, w2 = got.reshape(-1, got.shape[-1]), want.reshape(-1, want.shape[-1])
-    cos = (g2 * w2).sum(1) / (np.linalg.norm(g2, axis=1) * np.linalg.norm(w2, axis=1))
-    assert err <= ABS_TOL and rel <= REL_TOL and cos.min() >= COS, (err, rel, cos.min())
+def _check_descriptors(got, want, key):
+    return parity.check(key, got, want)
 
 
 @pytest.mark.parametrize("name,hw,B", [("vit_t16", (64, 64), 3), ("vit_t16", (48, 80), 2), ("vit_s16", (224, 224), 8)])
@@ -38,7 +35,7 @@ def test_vit_dense_descriptors_vs_oracle(cuda, name, hw, B):
     got = model.dense_descriptors(x.to(cuda)).cpu().numpy()
     want = _oracle_dense(model, x)
     assert got.shape == want.shape == (B, hw[0] // 16, hw[1] // 16, model.cfg["dim"])
-    _check_descriptors(got, want)
+    _check_descriptors(got, want, f"descriptors {name}@{hw[0]}x{hw[1]} B{B}")
 
 
 def test_vit_l14_patch14_k_tail(cuda):
@@ -46,7 +43,7 @@ def test_vit_l14_patch14_k_tail(cuda):
     from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
     model = tdd.load_model("vit_l14", img_hw=(56, 56), device=cuda, seed=5)
     x = torch.rand(2, 3, 56, 56)
-    _check_descriptors(model.dense_descriptors(x.to(cuda)).cpu().numpy(), _oracle_dense(model, x))
+    _check_descriptors(model.dense_descriptors(x.to(cuda)).cpu().numpy(), _oracle_dense(model, x), "descriptors vit_l14@56x56 B2")
 
 
 def test_get_dense_descriptor_single_slice_api(cuda):
@@ -56,7 +53,7 @@ def test_get_dense_descriptor_single_slice_api(cuda):
     f = tdd.get_dense_descriptor(model, img)
     assert f.shape == (4, 4, 128) and f.dtype == np.float32
     want = _oracle_dense(model, torch.from_numpy(np.stack([img] * 3))[None])
-    _check_descriptors(f[None], want)
+    _check_descriptors(f[None], want, "get_dense_descriptor vit_t16@64x64")
 
 
 @pytest.mark.parametrize("case", ["T0", "C1"])
@@ -78,16 +75,52 @@ def test_extract_point_cloud_vs_oracle(cuda, case):
     ref = G.token_gather(feats, masks, res, noise)
     assert out["count"] == ref["flat"].size > 0
     assert np.array_equal(out["src"].numpy(), ref["src"])
-    _check_descriptors(out["tokens"].numpy()[None], ref["tokens"][None])
+    _check_descriptors(out["tokens"].numpy()[None], ref["tokens"][None], f"point-cloud tokens {case}")
     # generate_features API: same shapes / masks as the oracle's, descriptors within tolerance
     fl, ml = tdd.generate_features(model, img, mask)
     assert len(fl) == len(feats) == S
     assert all(a.shape == b.shape for a, b in zip(fl, feats)) and all(np.array_equal(a, b) for a, b in zip(ml, masks))
-    _check_descriptors(np.stack(fl), np.stack(feats))
+    _check_descriptors(np.stack(fl), np.stack(feats), f"generate_features {case}")
     # gathering the device descriptors with the oracle gives the device tokens bit-for-bit (PE aside): the
     # gather itself adds no error
     ref2 = G.token_gather(fl, ml, res, noise)
     assert np.allclose(out["tokens"].numpy(), ref2["tokens"].astype(np.float32), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("case,n_slices", [("C2", 3), ("C4", 3)])
+def test_headline_config_descriptors_and_point_cloud_vs_oracle(cuda, case, n_slices):
+    """FLOAT parity at the benchmarked configurations themselves: ViT-B/16 @ 512x512 (C2, N = 1025 tokens per slice, the bench
+    line's workload) and ViT-L/14 @ 224x224 (C4, 24 layers, K = 588 patch rows) -- the middle slices of the config's own synthetic
+    volume through the batched device path vs oracle/vit_fp32.py in fp32 on the CPU, dense descriptors AND the mask-gathered
+    point cloud (indices bit-exact, tokens within the stated bounds of tests/parity.py).
+    reference: tfds_dense_descriptor.py:110-139 (get_dense_descriptor), train_models.py:143-182 (_get_features)."""
+    from oracle import gather_np as G
+    from vit_deep_radiomics_b200 import synth, tfds_dense_descriptor as tdd
+    img, mask, res, name = synth.make_case(case)
+    H, W, S = img.shape
+    s0 = S // 2 - n_slices // 2
+    img, mask = np.ascontiguousarray(img[:, :, s0:s0 + n_slices]), np.ascontiguousarray(mask[:, :, s0:s0 + n_slices])
+    model = tdd.load_model(name, img_hw=(H, W), device=cuda, seed=1234)
+    x = torch.from_numpy(np.ascontiguousarray(np.moveaxis(img, -1, 0)))[:, None].expand(-1, 3, -1, -1).contiguous()
+    want = _oracle_dense(model, x)
+    got = model.dense_descriptors(x.to(cuda)).cpu().numpy()
+    p = model.cfg["patch"]
+    assert got.shape == want.shape == (n_slices, H // p, W // p, model.cfg["dim"])
+    _check_descriptors(got, want, f"descriptors {name}@{H}x{W} ({case})")
+    # the fused path on the same slices: volume staging (TMA im2col view for C2) -> batched forward -> ROI -> gather
+    out = tdd.extract_point_cloud(model, img, mask, res)
+    order = iter(range(n_slices))
+
+    def oracle_descriptor(img2d):             # the crop window of these configs is the whole slice: reuse the batch computed above
+        k = next(order)
+        assert np.array_equal(img2d, img[:, :, k])
+        return want[k]
+
+    feats, masks = G.generate_features(oracle_descriptor, img, mask)
+    ref = G.token_gather(feats, masks, res)
+    assert out["count"] == ref["flat"].size > 50
+    assert np.array_equal(out["src"].numpy(), ref["src"])
+    _check_descriptors(out["tokens"].numpy(), ref["tokens"], f"point-cloud tokens {name}@{H}x{W} ({case})")
 
 
 def test_c2_full_size_properties(cuda):
@@ -127,10 +160,8 @@ def test_classifier_forward_vs_golden(cuda, golden_dir):
     with torch.no_grad():
         logits, cls = model(torch.tensor(g["x"]).to(cuda))
     assert logits.shape == (1, 2) and cls.shape == (1, d)
-    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < 0.03
-    c, w = cls.cpu().numpy()[0].astype(np.float64), g["cls"][0].astype(np.float64)
-    assert (c * w).sum() / (np.linalg.norm(c) * np.linalg.norm(w)) > 0.999
-    assert np.abs(c - w).max() < 0.06
+    parity.check("classifier logits (golden, small)", logits.cpu().numpy(), g["logits"], dict(abs=0.03, rel=1.0, cos=-1.0))
+    parity.check("classifier CLS (golden, small)", cls.cpu().numpy(), g["cls"], dict(abs=0.06, rel=1.0, cos=0.999))
 
 
 def test_classifier_full_config_vs_oracle(cuda):
@@ -145,8 +176,8 @@ def test_classifier_full_config_vs_oracle(cuda):
     with torch.no_grad():
         logits, cls = model(x.to(cuda))
         want_l, want_c = C.classifier_forward(sd, x, 4, 2)
-    assert (logits.cpu() - want_l).abs().max() < 0.05
-    assert torch.nn.functional.cosine_similarity(cls.cpu(), want_c).item() > 0.999
+    parity.check("classifier logits (d256 ff1024 h4 L2, n=2000)", logits.cpu().numpy(), want_l.numpy(), dict(abs=0.05, rel=1.0, cos=-1.0))
+    parity.check("classifier CLS (d256 ff1024 h4 L2, n=2000)", cls.cpu().numpy(), want_c.numpy(), dict(abs=1.0, rel=1.0, cos=0.999))
 
 
 def test_classifier_backward_vs_golden(cuda, golden_dir):
@@ -175,7 +206,7 @@ def test_classifier_backward_vs_golden(cuda, golden_dir):
         cos = float((got @ want) / (got.norm() * want.norm()))
         rel = float((got - want).norm() / want.norm())
         worst = min(worst, cos)
-        assert cos > 0.99 and rel < 0.12, (name, cos, rel)
+        parity.check("classifier gradients (golden, small)", got.numpy()[None], want.numpy()[None], dict(abs=1e9, rel=0.12, cos=0.99))
     assert worst > 0.99
 
 
@@ -288,9 +319,9 @@ def test_folded_layernorm_forward_matches_layernorm_kernel_path(cuda):
         a2 = folded.forward_volume(vol, crop).clone()
         b = plain.forward_volume(vol, crop).clone()
         assert torch.equal(a, a2)
-        _check_descriptors(a.cpu().numpy(), b.cpu().numpy())
+        _check_descriptors(a.cpu().numpy(), b.cpu().numpy(), f"folded vs unfolded LayerNorm {name}")
         x = torch.from_numpy(rng.random((2, 3) + hw, dtype=np.float32))
-        _check_descriptors(plain.dense_descriptors(x.to(cuda)).cpu().numpy(), _oracle_dense(plain, x))
+        _check_descriptors(plain.dense_descriptors(x.to(cuda)).cpu().numpy(), _oracle_dense(plain, x), f"descriptors unfolded {name}@{hw[0]}")
 
 
 @pytest.mark.parametrize("ch,cw,oh,ow", [(37, 53, 64, 64), (200, 180, 256, 256), (96, 80, 64, 48), (300, 260, 128, 224)])
@@ -337,7 +368,7 @@ def test_generate_features_resizes_crop_to_backbone_input(cuda):
     assert len(feats) == S
     for s in range(S):
         assert feats[s].shape == dense[s, fy0:fy1, fx0:fx1].shape
-        _check_descriptors(feats[s], dense[s, fy0:fy1, fx0:fx1])
+        _check_descriptors(feats[s], dense[s, fy0:fy1, fx0:fx1], "generate_features resized crop")
         assert np.array_equal(masks[s], mask[y0:y1, x0:x1, s][my0:my1, mx0:mx1])
 
 
@@ -413,7 +444,7 @@ def test_bimodal_classifier_vs_golden(cuda, golden_dir, mode):
             continue
         cos = float((got @ want) / (got.norm() * want.norm()))
         rel = float((got - want).norm() / want.norm())
-        assert cos > 0.99 and rel < 0.15, (name, cos, rel)
+        parity.check(f"bimodal gradients (golden, {mode})", got.numpy()[None], want.numpy()[None], dict(abs=1e9, rel=0.15, cos=0.99))
         checked += 1
     assert checked >= 15
 

@@ -15,16 +15,12 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-ABS_TOL, REL_TOL, COS = 0.15, 0.02, 0.999
+ABS_TOL, REL_TOL, COS = 0.15, 0.02, 0.999        # fallback; the per-config stated bounds are in tests/parity.py
 
 
-def _check_descriptors(got, want):
-    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
-    err = np.abs(got - want).max()
-    rel = np.sqrt(((got - want) ** 2).sum() / (want ** 2).sum())
-    g2, w2 = got.reshape(-1, got.shape[-1]), want.reshape(-1, want.shape[-1])
-    cos = (g2 * w2).sum(1) / (np.linalg.norm(g2, axis=1) * np.linalg.norm(w2, axis=1))
-    assert err <= ABS_TOL and rel <= REL_TOL and cos.min() >= COS, (err, rel, cos.min())
+def _check_descriptors(got, want, key):
+    import parity
+    return parity.check(key, got, want, dict(abs=ABS_TOL, rel=REL_TOL, cos=COS))
 
 
 @pytest.mark.parametrize("B,H,W,ws,d", [(2, 16, 16, 14, 128), (1, 14, 14, 14, 64), (3, 9, 20, 7, 72), (1, 64, 64, 14, 768)])
@@ -171,7 +167,7 @@ def test_sam_encoder_vs_oracle(cuda, hw, B):
     with torch.no_grad():
         want = sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, x).numpy()
     assert got.shape == want.shape == (B, hw[0] // 16, hw[1] // 16, 64)
-    _check_descriptors(got, want)
+    _check_descriptors(got, want, f"descriptors sam_tiny@{hw[0]}x{hw[1]}")
 
 
 def test_sam_encoder_layernorm_kernel_path_and_mma_global_attention(cuda):
@@ -189,7 +185,7 @@ def test_sam_encoder_layernorm_kernel_path_and_mma_global_attention(cuda):
     with torch.no_grad():
         want = sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, x).numpy()
     for got in outs:
-        _check_descriptors(got, want)
+        _check_descriptors(got, want, "descriptors sam_tiny@128x1024 (kernel variants)")
 
 
 def test_sam_encoder_against_committed_golden(cuda, golden_dir):
@@ -204,7 +200,7 @@ def test_sam_encoder_against_committed_golden(cuda, golden_dir):
     full = {"image_encoder." + k: v for k, v in sd.items()}                      # as a full SAM checkpoint stores it
     model = sam_encoder.SamImageEncoder("sam_tiny", img_hw=(mk.IMG, mk.IMG), state_dict=full, device=cuda)
     got = model.dense_descriptors(mk.golden_input().to(cuda))[0].cpu().numpy()
-    _check_descriptors(got, g["descriptors"])
+    _check_descriptors(got, g["descriptors"], "descriptors sam_tiny vs HF golden")
 
 
 def test_medsam_full_size_slice(cuda):
@@ -220,7 +216,7 @@ def test_medsam_full_size_slice(cuda):
     with torch.no_grad():
         want = sam_fp32.sam_dense_descriptor(model.state_dict_f32, model.cfg, gray[:, None].expand(-1, 3, -1, -1)).numpy()
     assert got.shape == want.shape == (1, 64, 64, 256)
-    _check_descriptors(got, want)
+    _check_descriptors(got, want, "descriptors medsam (SAM ViT-B)@1024x1024")
 
 
 def test_medsam_point_cloud_through_the_gather(cuda):

@@ -283,3 +283,60 @@ def test_patient_pointcloud_matches_reference_loop_body(monkeypatch):
         assert list(got.columns) == list(df.columns) and len(got) == len(df) > 0
         for col in df.columns:
             assert np.array_equal(got[col].values, df[col].values), (modality, col)
+
+
+def test_hdf5_handoff_executed_against_the_h5py_stand_in(capsys):
+    """V5 (tfds_dense_descriptor.py:142-165, :353-362): h5py is not in this image, so the HDF5 hand-off is EXECUTED against
+    ref_shim's dict-backed ``h5py.File`` stand-in -- our save_features / get_voxels and the unmodified reference's write and read
+    the same stand-in; the stores must match key for key, dtype for dtype, byte for byte, and the trainer's reader
+    (PETCTDataset3D._get_features through the same File API, store=None) must return the reference's tokens from the file
+    save_features wrote."""
+    ref = ref_shim.load_reference("tfds_dense_descriptor")          # installs the h5py stand-in into sys.modules
+    tm_ref = ref_shim.load_reference("train_models")
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    from vit_deep_radiomics_b200 import train_models as tm
+    rng = np.random.default_rng(17)
+    D = 12
+    feats = [rng.standard_normal((5, 4, D)).astype(np.float32) for _ in range(7)]
+    masks = [rng.random((17, 13)) < 0.4 for _ in range(7)]
+    for path in ("ours.h5", "ref.h5"):
+        ref_shim.H5_FILES.pop(path, None)
+    # a stale group of the same patient must be replaced, another patient kept (:153-155)
+    tdd.save_features("ours.h5", feats[:2], masks[:2], "P9")
+    ref.save_features("ref.h5", feats[:2], masks[:2], "P9")
+    tdd.save_features("ours.h5", feats[:3], masks[:3], "P1")
+    ref.save_features("ref.h5", feats[:3], masks[:3], "P1")
+    tdd.save_features("ours.h5", feats, masks, "P1")
+    ref.save_features("ref.h5", feats, masks, "P1")
+    assert capsys.readouterr().out.count("already exists") == 2      # both implementations announce the overwrite
+    ours, want = ref_shim.H5_FILES["ours.h5"], ref_shim.H5_FILES["ref.h5"]
+    assert sorted(ours) == sorted(want) and len(ours) == 2 * 7 + 2 * 2
+    for k in want:
+        assert ours[k].dtype == want[k].dtype and ours[k].shape == want[k].shape and ours[k].tobytes() == want[k].tobytes(), k
+    assert ours["P1/features/6"].dtype == np.float32 and ours["P1/masks/6"].dtype == bool
+    # the trainer reads that file back through the File API (no `store` shortcut): reference tokens, bit for bit
+
+    class RefDS(tm_ref.PETCTDataset3D):
+        def __init__(self):
+            self.feature_dim, self.arch = D, "transformer"
+
+    ds = tm.PETCTDataset3D.__new__(tm.PETCTDataset3D)
+    ds.store, ds.feature_dim, ds.arch, ds.device = None, D, "transformer", "cpu"
+    ds.gather = lambda f, m, r, n, d: G.token_gather(f, m, r, n, d)["tokens"]
+    res, noise = np.array([0.8, 0.8, 1.5]), np.array([0.5, -1.0, 2.0])
+    ids = [1, 2, 3, 5]
+    want_tok = RefDS()._get_features("ref.h5", "P1", ids, 0, "None", noise, res)
+    got_tok = ds._get_features("ours.h5", "P1", ids, 0, "None", noise, res)
+    assert np.array_equal(got_tok.numpy(), want_tok.astype(np.float32))
+    # input side: get_voxels on <pid>_<mod>/img_exam/<k>, mask_exam/<k> (slices named by integers, stacked in numeric order)
+    store = ref_shim.H5_FILES.setdefault("in.h5", {})
+    store.clear()
+    for k in (10, 2, 0, 1, 11):
+        store[f"A7_ct/img_exam/{k}"] = rng.random((6, 5)).astype(np.float32)
+        store[f"A7_ct/mask_exam/{k}"] = rng.random((6, 5)) < 0.3
+    img, mask, sr = tdd.get_voxels("in.h5", "A7", "ct")
+    img_r, mask_r, sr_r = ref.get_voxels("in.h5", "A7", "ct")
+    assert img.shape == (6, 5, 5) and np.array_equal(sr, sr_r)
+    assert np.array_equal(img, img_r) and np.array_equal(mask, mask_r) and img.dtype == img_r.dtype and mask.dtype == mask_r.dtype
+    for j, k in enumerate((0, 1, 2, 10, 11)):                        # numeric slice order, not the key (string) order
+        assert np.array_equal(img[:, :, j], store[f"A7_ct/img_exam/{k}"]) and np.array_equal(mask[:, :, j], store[f"A7_ct/mask_exam/{k}"])

@@ -20,7 +20,7 @@ EXPORTS = (
     "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd", "vdr_row_stats", "vdr_fold_layernorm",
     "vdr_flash_attn_fwd", "vdr_flash_attn_bwd_workspace_bytes", "vdr_flash_attn_bwd",
-    "vdr_mask_gather_workspace_bytes", "vdr_mask_gather", "vdr_mask_gather_table", "vdr_mask_count", "vdr_exclusive_scan_i64",
+    "vdr_mask_gather_workspace_bytes", "vdr_mask_gather", "vdr_mask_gather_table", "vdr_mask_count", "vdr_exclusive_scan_i64", "vdr_debug_set_gather_trace",
     "vdr_voxel_bbox", "vdr_mask_bbox", "vdr_voxel_gather",
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
     "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
                                         vp, vp, i32, i32, vp, i64, vp, f64, vp, C.POINTER(f64), vp, sz, vp]
     L.vdr_mask_count.argtypes = [vp, i64, i64, i64, vp, vp, i32, i32, i32, vp, vp]
     L.vdr_exclusive_scan_i64.argtypes = [vp, i32, vp, vp]
+    L.vdr_debug_set_gather_trace.argtypes = [vp]
     L.vdr_voxel_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_mask_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_voxel_gather.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]

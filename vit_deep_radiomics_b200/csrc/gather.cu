@@ -73,7 +73,16 @@ struct G1Args {
   int vec_ok, npair2;
   int32_t* block_totals;       // [gridDim.x] workspace
   int tiles, tiles_per_block;
+  unsigned long long* trace;   // diagnostics (vdr_debug_set_gather_trace): %globaltimer of block 0 / the last block at the phase boundaries
 };
+
+__device__ __forceinline__ void g1_stamp(const G1Args& A, int slot) {
+  if (A.trace != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    A.trace[(blockIdx.x == 0 ? 0 : 8) + slot] = t;
+  }
+}
 
 // ONE cooperative launch: [PE table | predicate ballots + per-block totals] -> grid sync -> [ranks -> (slice,row,col) rows at the
 // block's base] -> grid sync -> [emit: one warp per OUTPUT row over the whole grid].  The mask is read once (ballots of up to kKeep
@@ -89,6 +98,7 @@ __global__ void __launch_bounds__(kGThreads, 4) g1_fused_kernel(const G1Args A) 
   const G1Geom& g = A.g;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  g1_stamp(A, 0);
   // ---- phase 0: positional-encoding table (grid-strided; a few thousand f64 sin/cos)
   if (A.pe.scale != 0. && A.npair2 > 0) {
     const int64_t entries = static_cast<int64_t>(g.h + g.w + g.S) * A.npair2;
@@ -96,6 +106,7 @@ __global__ void __launch_bounds__(kGThreads, 4) g1_fused_kernel(const G1Args A) 
       A.pe.table[idx] = g1_pe_entry(A.pe, g.S, g.h, g.w, A.npair2, idx);
   }
 
+  g1_stamp(A, 1);
   // ---- phase 1: predicate -> ballots, block total
   const int t0 = blockIdx.x * A.tiles_per_block;
   const int t1 = min(t0 + A.tiles_per_block, A.tiles);
@@ -118,7 +129,9 @@ __global__ void __launch_bounds__(kGThreads, 4) g1_fused_kernel(const G1Args A) 
     for (int i = 0; i < kGThreads / 32; ++i) tot += s_red[0][i];
     A.block_totals[blockIdx.x] = tot;
   }
+  g1_stamp(A, 2);
   grid.sync();
+  g1_stamp(A, 3);
 
   // ---- phase 2: exclusive base of this block = sum of the totals of the blocks before it; ranks; (slice,row,col) rows
   int lt = 0, all = 0;
@@ -192,7 +205,9 @@ __global__ void __launch_bounds__(kGThreads, 4) g1_fused_kernel(const G1Args A) 
     base += tile_n;
     __syncthreads();   // s_cnt / s_off / s_sel are rewritten by the next tile
   }
+  g1_stamp(A, 4);
   grid.sync();
+  g1_stamp(A, 5);
 
   // ---- phase 3: emit.  One warp per output row over the whole grid: copies the descriptor row and adds the positional
   // encoding from the per-coordinate f64 table (row in, row out, three cache-resident table rows).
@@ -265,6 +280,7 @@ __global__ void __launch_bounds__(kGThreads, 4) g1_fused_kernel(const G1Args A) 
       }
     }
   }
+  g1_stamp(A, 6);
 }
 
 // Count only (the multi-GPU table needs every patient's row count before any rank emits: SURVEY.md 8e): tile ballots, one
@@ -399,6 +415,13 @@ voxel_gather_kernel(const float* __restrict__ img, const uint8_t* __restrict__ m
 
 }  // namespace vdr
 
+static unsigned long long* g_g1_trace = nullptr;   // diagnostics only
+
+extern "C" int vdr_debug_set_gather_trace(void* dev_u64x16) {
+  g_g1_trace = static_cast<unsigned long long*>(dev_u64x16);
+  return VDR_OK;
+}
+
 constexpr int kMaxCoopBlocks = 2048;   // upper bound of the fused kernel's grid (148 SMs x <= 8 blocks); sizes the block-totals scratch
 
 static size_t g1_scan_bytes() { return (size_t)kMaxCoopBlocks * sizeof(int32_t); }
@@ -470,6 +493,7 @@ extern "C" int vdr_mask_gather_table(const void* feat, int feat_dtype, int64_t l
     A.pe.mean_x = coef_host[8]; A.pe.mean_y = coef_host[9]; A.pe.mean_z = coef_host[10];
   }
   A.block_totals = static_cast<int32_t*>(workspace);
+  A.trace = g_g1_trace;
   A.tiles = (int)(((int64_t)A.g.total + kTile - 1) / kTile);
   const bool bf16 = feat_dtype == VDR_DTYPE_BF16;
   const int max_blocks = bf16 ? g1_coop_blocks<true>() : g1_coop_blocks<false>();
