@@ -19,5 +19,6 @@ L.vdr_debug_set_attn_trace(None)
 t = buf.cpu().view(16, 16).numpy()
 t0 = int(t[0, 0])
 print("softmax: loop_top s_ready s_loaded math_done o_wait_done p_stored | issuer: top sfree_seen s_next_issued before_pready pready_seen pv_issued (us)")
-for j in range(9):
+print("v6 columns: softmax loop_top s_ready s_loaded math_done p_stored - | issuer: top k_ready o_ready s_issued p_seen v_ready")
+for j in range(16):
     print(j, " ".join(f"{(int(v) - t0) / 1e3:7.2f}" for v in t[j, :6]), "|", " ".join(f"{(int(v) - t0) / 1e3:7.2f}" for v in t[j, 8:14]))

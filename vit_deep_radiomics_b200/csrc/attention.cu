@@ -80,11 +80,11 @@ __device__ __forceinline__ unsigned long long attn_gtime() {
 }
 #define ATT_TRACE(ev)                                                                                              \
   do {                                                                                                             \
-    if (p.trace != nullptr && tid == 32 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 16 + (ev)] = attn_gtime(); \
+    if (p.trace != nullptr && tid == 32 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 60 && j < 16) p.trace[j * 16 + (ev)] = attn_gtime(); \
   } while (0)
 #define ISS_TRACE(ev)                                                                                              \
   do {                                                                                                             \
-    if (p.trace != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && j < 16) p.trace[j * 16 + 8 + (ev)] = attn_gtime(); \
+    if (p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 60 && j < 16) p.trace[j * 16 + 8 + (ev)] = attn_gtime(); \
   } while (0)
 #else
 #define ATT_TRACE(ev) do { } while (0)
@@ -149,10 +149,11 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // eight sibling tensor-core CTAs are streaming at the same time.  8 lanes share a key (16 bytes of the 128-byte K / V
 // row each): a warp-wide load touches 4 rows x 128 contiguous bytes; the 48 lane-groups of the CTA each run an online
 // softmax over the keys dealt to them and the partial states are merged through shared memory.
+template <int kThreads>
 __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, int head, int b, int row0, int nrows) {
-  constexpr int kGroups = kAttnThreads / 8;                        // 48 key groups of 8 lanes: lane `sub` owns 8 of the 64 dims
+  constexpr int kGroups = kThreads / 8;                            // key groups of 8 lanes (48 / 20): lane `sub` owns 8 of the 64 dims
   constexpr int kDepth = 5;                                        // keys in flight per group (cp.async ring)
-  constexpr uint32_t kStageBytes = kAttnThreads * 16 * 2;          // one 16-byte K piece and one V piece per thread
+  constexpr uint32_t kStageBytes = kThreads * 16 * 2;              // one 16-byte K piece and one V piece per thread
   float* s_m = sm;                                                 // [kGroups]
   float* s_l = sm + kGroups;                                       // [kGroups]
   float* s_o = sm + 2 * kGroups;                                   // [kGroups][kHD]
@@ -173,7 +174,7 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
       const __nv_bfloat16* row = base + static_cast<int64_t>(j) * p.ld_qkv;
       const uint32_t dst = ring + static_cast<uint32_t>(step % kDepth) * kStageBytes;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(row + p.d) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kAttnThreads * 16), "l"(row + 2 * p.d) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kThreads * 16), "l"(row + 2 * p.d) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -197,7 +198,7 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
         const uint32_t src = ring + static_cast<uint32_t>(step % kDepth) * kStageBytes;
         uint4 ku, vu;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ku.x), "=r"(ku.y), "=r"(ku.z), "=r"(ku.w) : "r"(src) : "memory");
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vu.x), "=r"(vu.y), "=r"(vu.z), "=r"(vu.w) : "r"(src + kAttnThreads * 16) : "memory");
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vu.x), "=r"(vu.y), "=r"(vu.z), "=r"(vu.w) : "r"(src + kThreads * 16) : "memory");
         const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y), k2 = unpack_bf16x2(ku.z), k3 = unpack_bf16x2(ku.w);
         float sdot = qv[0] * k0.x + qv[1] * k0.y + qv[2] * k1.x + qv[3] * k1.y + qv[4] * k2.x + qv[5] * k2.y + qv[6] * k3.x + qv[7] * k3.y;
         sdot += __shfl_xor_sync(gmask, sdot, 1);   // reduce inside the 8-lane group (groups may skip the last step,
@@ -251,6 +252,8 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
 // its bias is one scalar rel_h[q, kh] per block (prefetched from global memory a block ahead) plus the 64 rel_w[q, kw]
 // of its query row, which are the same for every block and sit in shared memory as fp16 (16 KB per CTA; |rel_w| of a
 // few units -> 1e-3 absolute in the exponent, below the bf16 rounding of P).
+__device__ unsigned int g_attn_sm_ticket[1024];   // experiment (VDR_ATTN_DBG >= 100): alternate start delay per SM slot
+
 template <bool kBias>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
@@ -275,10 +278,15 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
   if (static_cast<int>(blockIdx.x) >= p.q_tiles) {   // the extra CTA of this (image, head): trailing query rows on the CUDA cores
-    if (p.dbg != 1) attn_tail_rows(p, reinterpret_cast<float*>(smem), head, b, p.N - p.tail_rows, p.tail_rows);
+    if (p.dbg != 1) attn_tail_rows<kAttnThreads>(p, reinterpret_cast<float*>(smem), head, b, p.N - p.tail_rows, p.tail_rows);
     return;
   }
   if (p.dbg == 4) return;                             // timing experiments: only the trailing-row CTAs work
+  if (p.dbg >= 100 && tid == 0) {                     // experiment: every other CTA of an SM starts p.dbg ns late (de-phases the co-resident pair)
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (atomicAdd(&g_attn_sm_ticket[smid & 1023], 1u) & 1u) __nanosleep(p.dbg);
+  }
   const int row_base = b * p.N;                       // first token row of this image in the qkv matrix
   const int colQ = head * kHD, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
   // Key blocks: full 128-key blocks on the tensor cores; a ragged last block either runs as a narrow MMA block
@@ -332,8 +340,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     // 8 steps) are dispatched concurrently.
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
-    if (warp == kSoftmaxWarps && lane == 0) {
-      // ---- K tiles + S = Q K^T
+    if (warp == kSoftmaxWarps) {
+      // ---- K tiles + S = Q K^T.  The whole warp runs the loop and waits; the tcgen05 / TMA instructions sit under elect.sync
+      // (exactly one lane, known to the compiler: operands go to uniform registers directly -- under `lane == 0` every
+      // tcgen05.mma was wrapped in an ELECT / BRA.U.ANY waterfall and cost ~0.1 us of issue time, 0.5 us per S block and
+      // 0.85 us per PV block in the round-2 traces)
       auto issue_s = [&](int j) {
         const int t = 2 * j;
         mbar_wait_relaxed(&bar_kv[t & 3], (t >> 2) & 1);
@@ -342,20 +353,24 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         const uint64_t dk = umma_desc_kmajor_sw128(sRing + (t & 3) * kTileBytes);
         // the last key block only computes the (16-column granular) part of S that has keys behind it
         const uint32_t idesc = (j == nkv - 1) ? umma_idesc_bf16(128, ntail) : idesc_s;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
-        umma_commit(bar_s);
+          for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
       };
       mbar_wait_relaxed(bar_q, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
-        ISS_TRACE(0);
+        if (lane == 0) ISS_TRACE(0);
         mbar_wait_relaxed(bar_sfree, j & 1);               // S_j is in registers -> K_j's slot and the S columns are free
         tc_fence_after();
-        ISS_TRACE(1);
+        if (lane == 0) ISS_TRACE(1);
         if (j + 1 < nkv) issue_s(j + 1);
-        if (j + 2 < nkv) issue_tile(2 * j + 4);            // K_{j+2} into K_j's slot
-        ISS_TRACE(2);
+        if (j + 2 < nkv && elect_one()) issue_tile(2 * j + 4);   // K_{j+2} into K_j's slot
+        __syncwarp();
+        if (lane == 0) ISS_TRACE(2);
       }
     } else if (warp == kSoftmaxWarps + 2) {
       // ---- the few trailing keys (folded in by the softmax epilogue): their K and V rows -> shared memory, early
@@ -393,16 +408,17 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         __syncwarp();
       }
       if (lane == 0) mbar_arrive(bar_tail);
-    } else if (warp == kSoftmaxWarps + 1 && lane == 0) {
-      // ---- V tiles + O += P V
+    } else if (warp == kSoftmaxWarps + 1) {
+      // ---- V tiles + O += P V (warp-wide loop, instructions under elect.sync as above)
       for (int j = 0; j < nkv; ++j) {
-        ISS_TRACE(3);
+        if (lane == 0) ISS_TRACE(3);
         mbar_wait_relaxed(bar_pready, j & 1);              // P_j is in TMEM (and O rescaled if the maximum moved)
         tc_fence_after();
-        ISS_TRACE(4);
+        if (lane == 0) ISS_TRACE(4);
         if (j >= 1 && j + 1 < nkv) {                       // V_{j+1} goes into V_{j-1}'s slot: O_{j-1} must be complete.
           mbar_wait_relaxed(bar_o, (j - 1) & 1);           // (waited BEFORE O_j is committed: a parity wait must never
-          issue_tile(2 * j + 3);                           //  be two phases behind its barrier)
+          if (elect_one()) issue_tile(2 * j + 3);          //  be two phases behind its barrier)
+          __syncwarp();
         }
         const int t = 2 * j + 1;
         mbar_wait_relaxed(&bar_kv[t & 3], (t >> 2) & 1);
@@ -410,18 +426,22 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         const uint64_t dv0 = umma_desc_mnmajor_sw128(sRing + (t & 3) * kTileBytes);
         // A = P from TMEM (16 bf16 = 8 columns per K step); O accumulates in TMEM across all key blocks.
         // Each K step covers 16 kv rows x 128 B of the V tile = 2048 B = 128 descriptor address units.
-        if (j < nkv - 1 || ntail == kBKV) {
+        const bool full = (j < nkv - 1 || ntail == kBKV);
+        if (elect_one()) {
+          if (full) {
 #pragma unroll
-          for (int k = 0; k < kBKV / 16; ++k)
-            umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
-        } else {
-          const int ksteps = ntail / 16;
+            for (int k = 0; k < kBKV / 16; ++k)
+              umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          } else {
+            const int ksteps = ntail / 16;
 #pragma unroll 1
-          for (int k = 0; k < ksteps; ++k)
-            umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k)
+              umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(bar_o);
         }
-        umma_commit(bar_o);
-        ISS_TRACE(5);
+        __syncwarp();
+        if (lane == 0) ISS_TRACE(5);
       }
     }
   } else {
@@ -682,6 +702,315 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   }
 }
 
+// ================================================================================================ v6
+// Four light CTAs per SM instead of two heavy ones.  The v5 profile (profiles/r02_attention.md) shows every pipe about half
+// busy -- MUFU 46 %, issue 50 %, tensor 25 % -- because each CTA is a serial latency chain (S ready -> tcgen05.ld -> max ->
+// exp2 -> P store -> PV) and two chains per SM cannot cover each other's gaps.  v6 makes the chain as short and as simple as
+// possible and runs FOUR of them per SM (four independent phases per scheduler):
+//   * 64-key blocks: S = Q K_j^T is 128 x 64 (64 TMEM columns), one softmax THREAD per query row (64 scores in registers, no
+//     exchange of maxima between threads, no pair barrier);
+//   * P_j (bf16 pairs, 32 columns) is written over the first half of the S columns it was computed from; O (64 columns)
+//     accumulates next to it: 128 TMEM columns per CTA = four CTAs per SM;
+//   * 5 warps: 0-3 softmax, 4 = one lane that issues the TMA loads (two K and two V slots of 8 KB) and every MMA;
+//     96 registers per thread (4 x 160 threads x 96 = the register file), 49.5 KB of shared memory.
+// Per block the issuer waits for PV_{j-1} (the S / P columns are free again), issues S_j, waits for the four softmax warps'
+// "P_j stored", issues O += P_j V_j.  Overlap comes from the other three CTAs of the SM.
+
+constexpr int kV6Threads = 160;
+constexpr int kV6BK = 64;                                  // keys per block
+constexpr int kV6KV = kV6BK * kHD * 2;                     // 8 KB: one 64 x 64 bf16 K or V tile
+constexpr int kV6Smem = kTileBytes + 4 * kV6KV + 256;      // Q | K0 K1 | V0 V1 | barriers
+constexpr int kV6TmemCols = 128;                           // S (f32) / P (bf16 pairs in its first 32 columns): [0,64)   O: [64,128)
+
+__global__ void __launch_bounds__(kV6Threads, 4)
+flash_attn_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sQ = base, sK = base + kTileBytes, sV = sK + 2 * kV6KV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBytes + 4 * kV6KV);
+  uint64_t* bar_q = bars;          // Q landed (two 64-row boxes)
+  uint64_t* bar_k = bars + 1;      // [2] K slot landed
+  uint64_t* bar_v = bars + 3;      // [2] V slot landed
+  uint64_t* bar_s = bars + 5;      // S_j complete                      (tcgen05.commit)
+  uint64_t* bar_o = bars + 6;      // O += P_j V_j complete             (tcgen05.commit)
+  uint64_t* bar_p = bars + 7;      // P_j stored, O rescaled            (4 softmax warps arrive)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
+  const int row_base = b * p.N;
+  const int colQ = head * kHD, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
+  // Key blocks: full 64-key blocks on the tensor cores; a ragged last block runs as a narrow MMA block (16-column granularity)
+  // or, when it holds only a few keys (<= 8: the 1025th token of a 32x32-patch image + CLS), is folded into the epilogue on the
+  // CUDA cores instead of costing every CTA one more round trip of the serial chain.
+  const int nkv_all = (p.N + kV6BK - 1) / kV6BK;
+  const int last_keys = p.N - (nkv_all - 1) * kV6BK;             // keys in the last block (1..64)
+  const int tail_keys = (last_keys <= 8 && nkv_all > 1) ? last_keys : 0;
+  const int nkv = tail_keys ? nkv_all - 1 : nkv_all;             // blocks that go through the MMA pipeline
+  const int valid_last = tail_keys ? kV6BK : last_keys;          // keys in the last MMA block
+  const int ntail = (valid_last + 15) & ~15;                     // ... rounded to the MMA's 16-column granularity
+
+  if (tid == 128) {
+    if (base & 1023u) { printf("vdr: attention smem base not 1024-byte aligned\n"); __trap(); }
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_q, 1);
+    mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
+    mbar_init(&bar_v[0], 1); mbar_init(&bar_v[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_p, 4);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar_q, kTileBytes);
+    tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
+    tma_load_2d(&tmQKV, bar_q, smem + kV6KV, colQ, row_base + q0 + 64);
+    const int pre = nkv > 1 ? 2 : 1;
+    for (int j = 0; j < pre; ++j) {
+      mbar_arrive_expect_tx(&bar_k[j], kV6KV);
+      tma_load_2d(&tmQKV, &bar_k[j], smem + kTileBytes + j * kV6KV, colK, row_base + j * kV6BK);
+      mbar_arrive_expect_tx(&bar_v[j], kV6KV);
+      tma_load_2d(&tmQKV, &bar_v[j], smem + kTileBytes + (2 + j) * kV6KV, colV, row_base + j * kV6BK);
+    }
+  }
+  if (warp == 0) tmem_alloc<kV6TmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+
+  if (warp == 4) {
+    // =============================================================== loads + MMA issue
+    // The whole warp runs the loop and waits on the barriers; the tcgen05 / TMA instructions sit under elect.sync, which the
+    // compiler understands as "exactly one lane": their operands go to uniform registers directly.  (Under `lane == 0` it wraps
+    // every tcgen05.mma in an ELECT / BRA.U.ANY waterfall of ~10 dependent instructions -- ~0.1 us per MMA in the v5 traces,
+    // and the issue latency is on this kernel's critical path twice per block.)
+    {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kV6BK, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHD, 0, 1);   // B (= V) is MN-major
+      const uint64_t dq = umma_desc_kmajor_sw128(sQ);
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int slot = j & 1, ph = (j >> 1) & 1;
+        const bool last = j == nkv - 1;
+        if (lane == 0) ISS_TRACE(0);
+        mbar_wait(&bar_k[slot], ph);
+        if (lane == 0) ISS_TRACE(1);
+        if (j > 0) mbar_wait(bar_o, (j - 1) & 1);          // PV_{j-1} complete: the S / P columns and V_{j-1}'s slot are free
+        tc_fence_after();
+        if (lane == 0) ISS_TRACE(2);
+        const uint64_t dk = umma_desc_kmajor_sw128(sK + slot * kV6KV);
+        const uint32_t idesc = last ? umma_idesc_bf16(128, ntail) : idesc_s;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+          umma_commit(bar_s);
+          if (j >= 1 && j + 1 < nkv) {                     // V_{j+1} into V_{j-1}'s slot (PV_{j-1} is complete)
+            const int s1 = (j + 1) & 1;
+            mbar_arrive_expect_tx(&bar_v[s1], kV6KV);
+            tma_load_2d(&tmQKV, &bar_v[s1], smem + kTileBytes + (2 + s1) * kV6KV, colV, row_base + (j + 1) * kV6BK);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ISS_TRACE(3);
+        mbar_wait(bar_p, j & 1);                           // P_j stored (so S_j has been read), O rescaled
+        if (lane == 0) ISS_TRACE(4);
+        mbar_wait(&bar_v[slot], ph);
+        tc_fence_after();
+        if (lane == 0) ISS_TRACE(5);
+        const uint64_t dv = umma_desc_mnmajor_sw128(sV + slot * kV6KV);
+        const int ksteps = last ? ntail / 16 : kV6BK / 16;
+        if (elect_one()) {
+          // A = P from TMEM (16 bf16 = 8 columns per K step); each K step covers 16 kv rows x 128 B of the V tile = 128 address units
+          if (ksteps == kV6BK / 16) {
+#pragma unroll
+            for (int k = 0; k < kV6BK / 16; ++k)
+              umma_ts(tmem_O, tmem_S + k * 8, dv + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          } else {
+#pragma unroll 1
+            for (int k = 0; k < ksteps; ++k)
+              umma_ts(tmem_O, tmem_S + k * 8, dv + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(bar_o);
+          if (j + 2 < nkv) {                               // K_{j+2} into K_j's slot (S_j has been read: bar_p(j))
+            mbar_arrive_expect_tx(&bar_k[slot], kV6KV);
+            tma_load_2d(&tmQKV, &bar_k[slot], smem + kTileBytes + slot * kV6KV, colK, row_base + (j + 2) * kV6BK);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================================================== softmax: thread = query row
+    const int row = warp * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t tS = tmem_S + lane_sel, tO = tmem_O + lane_sel;
+    float m_ref = -INFINITY, l_run = 0.f;
+    const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+    for (int j = 0; j < nkv; ++j) {
+      ATT_TRACE(0);
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      ATT_TRACE(1);
+      uint32_t sr[2][32];
+      tmem_ld_32x32b_x32(tS, sr[0]);
+      tmem_ld_32x32b_x32(tS + 32, sr[1]);
+      tmem_ld_wait();
+      ATT_TRACE(2);
+      if (j == nkv - 1 && valid_last < kV6BK) {   // ragged last block: columns >= valid_last are other tokens / were never written
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid_last) sr[c][i] = 0xff800000u;   // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = max3(mx0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+        mx1 = max3(mx1, __uint_as_float(sr[0][i + 2]), __uint_as_float(sr[0][i + 3]));
+        mx2 = max3(mx2, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+        mx3 = max3(mx3, __uint_as_float(sr[1][i + 2]), __uint_as_float(sr[1][i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+      // lazy rescaling: the reference maximum only moves when exceeded by 2^8; warp-uniform because TMEM accesses are warp-wide
+      const bool moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);
+      float alpha = 1.f;
+      if (moved) {
+        alpha = ex2(m_ref - m_new);
+        m_ref = m_new;
+      }
+      const uint64_t negm2 = pack2(-m_ref, -m_ref);
+      uint64_t lsum2 = 0ull;
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2);
+          float p0, p1;
+          if ((kPolyMask >> ((i >> 1) & 7)) & 1u) {   // a fixed subset of every 8 pairs: FMA-pipe exp2
+            exp2_poly2(x2, p0, p1);
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
+          lsum2 = add2(lsum2, pack2(p0, p1));
+          pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
+        }
+      }
+      float l0, l1;
+      unpack2(lsum2, l0, l1);
+      l_run = l_run * alpha + (l0 + l1);
+      ATT_TRACE(3);
+      if (j > 0 && moved) {   // rare after the first blocks.  PV_{j-1} is complete: S_j was issued behind it
+        const uint64_t alpha2 = pack2(alpha, alpha);
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tO + hlf * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            unpack2(mul2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2), a0, a1);
+            r[i] = __float_as_uint(a0);
+            r[i + 1] = __float_as_uint(a1);
+          }
+          tmem_st_32x32b_x32(tO + hlf * 32, r);
+        }
+      }
+      tmem_st_32x32b_x32(tS, pk);   // P_j over the first 32 of the S columns: the A operand of O += P V
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      ATT_TRACE(4);
+    }
+    mbar_wait(bar_o, (nkv - 1) & 1);
+    tc_fence_after();
+    // ---- epilogue: fold the few trailing keys (if any), normalise this row's 64 output columns and store them (128
+    //      contiguous bytes per thread)
+    const int q = q0 + row;
+    const __nv_bfloat16* ktail = p.qkv + static_cast<int64_t>(row_base + nkv * kV6BK) * p.ld_qkv + colK;
+    const __nv_bfloat16* vtail = ktail + p.d;                  // colV = colK + d
+    __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD;
+    float m_fin = m_ref, l_fin = l_run;
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tO + hlf * 32, r);
+      tmem_ld_wait();
+      float m = m_ref, l = l_run;                              // both halves replay the same (m, l) recurrence: no arrays across the loop
+      for (int t = 0; t < tail_keys; ++t) {
+        // q . k for this thread's query row: Q row from the (swizzled) shared-memory tile, K / V rows straight from global memory
+        // (the same 128 bytes for every thread of the CTA: one L1 line)
+        uint4 ku[8], vu[4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ku[c] = __ldg(reinterpret_cast<const uint4*>(ktail + static_cast<int64_t>(t) * p.ld_qkv) + c);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vu[c] = __ldg(reinterpret_cast<const uint4*>(vtail + static_cast<int64_t>(t) * p.ld_qkv + hlf * 32) + c);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 qu;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qu.x), "=r"(qu.y), "=r"(qu.z), "=r"(qu.w)
+                       : "r"(sQ + row * 128 + ((c ^ (row & 7)) << 4)));
+          const float2 q0v = unpack_bf16x2(qu.x), q1v = unpack_bf16x2(qu.y), q2v = unpack_bf16x2(qu.z), q3v = unpack_bf16x2(qu.w);
+          const float2 a0 = unpack_bf16x2(ku[c].x), a1 = unpack_bf16x2(ku[c].y), a2 = unpack_bf16x2(ku[c].z), a3 = unpack_bf16x2(ku[c].w);
+          d0 = fmaf(q0v.x, a0.x, d0); d1 = fmaf(q0v.y, a0.y, d1);
+          d0 = fmaf(q1v.x, a1.x, d0); d1 = fmaf(q1v.y, a1.y, d1);
+          d0 = fmaf(q2v.x, a2.x, d0); d1 = fmaf(q2v.y, a2.y, d1);
+          d0 = fmaf(q3v.x, a3.x, d0); d1 = fmaf(q3v.y, a3.y, d1);
+        }
+        const float sdot = (d0 + d1) * p.scale_log2;
+        const float m_new = fmaxf(m, sdot);
+        const float a = ex2(m - m_new);
+        const float pp = __bfloat162float(__float2bfloat16_rn(ex2(sdot - m_new)));   // same bf16 rounding of P as the MMA path
+        m = m_new;
+        l = l * a + pp;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float2 v0 = unpack_bf16x2(vu[c].x), v1 = unpack_bf16x2(vu[c].y), v2 = unpack_bf16x2(vu[c].z), v3 = unpack_bf16x2(vu[c].w);
+          r[c * 8 + 0] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 0]), a, pp * v0.x));
+          r[c * 8 + 1] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 1]), a, pp * v0.y));
+          r[c * 8 + 2] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 2]), a, pp * v1.x));
+          r[c * 8 + 3] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 3]), a, pp * v1.y));
+          r[c * 8 + 4] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 4]), a, pp * v2.x));
+          r[c * 8 + 5] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 5]), a, pp * v2.y));
+          r[c * 8 + 6] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 6]), a, pp * v3.x));
+          r[c * 8 + 7] = __float_as_uint(fmaf(__uint_as_float(r[c * 8 + 7]), a, pp * v3.y));
+        }
+      }
+      m_fin = m;
+      l_fin = l;
+      const float inv = 1.f / l;
+      if (q < p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = cvt_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+          w.y = cvt_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+          w.z = cvt_bf16x2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+          w.w = cvt_bf16x2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + hlf * 32 + i) = w;
+        }
+      }
+    }
+    m_ref = m_fin;
+    l_run = l_fin;
+    if (q < p.N && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_run)) * 0.69314718055994531f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kV6TmemCols>(tmem_base);
+  }
+}
+
 }  // namespace vdr
 
 static unsigned long long* g_attn_trace = nullptr;
@@ -696,13 +1025,18 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   VDR_CHECK_ARG(ld_qkv >= 3 * d && ld_qkv % 8 == 0 && ld_out >= d && ld_out % 8 == 0, VDR_EALIGN, "%s: ld_qkv (%lld) / ld_out (%lld) too small or not multiples of 8", who, (long long)ld_qkv, (long long)ld_out);
   VDR_CHECK_ARG(aligned16(qkv) && aligned16(out), VDR_EALIGN, "%s: pointers must be 16-byte aligned", who);
   VDR_CHECK_ARG(B <= 65535 && heads <= 65535, VDR_EINVAL, "%s: B and heads must be <= 65535", who);
+  // v6 (four light CTAs per SM) is faster than v5 when timed alone (N = 1024: 0.596 vs 0.627 ms) but slower inside the
+  // power-capped extraction step (0.904 vs 0.875 ms per layer at N = 1025): v5 stays the default, VDR_ATTN_V6=1 selects v6 for A/B runs
+  static const bool want_v6 = getenv("VDR_ATTN_V6") != nullptr;
+  const bool v6 = rel == nullptr && want_v6;
   CUtensorMap tm;
-  int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * d, (uint64_t)ld_qkv, 128, kHD);
+  int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * d, (uint64_t)ld_qkv, v6 ? kV6BK : 128, kHD);
   if (rc != VDR_OK) return rc;
   static DeviceFlags configured;
   if (!configured.current()) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV6Smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_fwd)");
     configured.current() = true;
   }
@@ -719,14 +1053,20 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   p.rel = rel;
   p.rel_pitch = rel_pitch;
   // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head)
+  // v5: full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head).
+  // v6: its CTAs are a quarter of an SM, so a trailing tile with a single valid row costs less than the CUDA-core CTA did
+  // (measured alone, N = 1025: 0.723 ms with the v5 CUDA-core routine on 160 threads, 0.711 as a tile; a one-warp-per-row
+  // routine with exact two-pass softmax was tried and was far slower, 0.862 ms): every tile goes through the tensor-core path.
   const int tail_rows = N % kBQ;
-  const bool vector_tail = tail_rows > 0 && tail_rows <= 8;
+  const bool vector_tail = !v6 && tail_rows > 0 && tail_rows <= 8;
   p.q_tiles = vector_tail ? N / kBQ : (N + kBQ - 1) / kBQ;
   p.tail_rows = vector_tail ? tail_rows : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.q_tiles + (vector_tail ? 1 : 0), heads, B);
   if (rel != nullptr)
     flash_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, p);
+  else if (v6)
+    flash_attn_fwd_v6_kernel<<<grid, kV6Threads, kV6Smem, s>>>(tm, p);
   else
     flash_attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
   count_launch();

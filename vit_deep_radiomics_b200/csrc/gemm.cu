@@ -156,7 +156,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (warp-wide loop, the TMA / mbarrier instructions under elect.sync: see the MMA issuer below)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -165,6 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          if (elect_one()) {
           if constexpr (kCtas == 2) {
             // both CTAs load their own A rows and their half of W; all bytes are credited to the LEADER's barrier
             const uint32_t lead_bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);
@@ -194,15 +196,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tma_load_2d(&tmW, &full_bar[stage], sa + Cfg::kStageBytesA, kb * BK, n_blk * BN);
           }
-          if (kb == 0) VDR_TRACE(5, it);
+          }
+          __syncwarp();
+          if (kb == 0 && lane == 0) VDR_TRACE(5, it);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        VDR_TRACE(6, it);
+        if (lane == 0) VDR_TRACE(6, it);
       }
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {   // pair: only the leader CTA issues MMAs
+    // The whole warp walks the tiles and waits on the barriers; the tcgen05 instructions sit under elect.sync.  The compiler
+    // knows that branch has exactly one active lane and feeds the instructions from uniform registers directly; under
+    // `lane == 0` it wrapped EVERY tcgen05.mma / commit in an ELECT / BRA.U.ANY waterfall (~19 dependent instructions per MMA,
+    // found in the SASS while profiling the attention kernel): the issue loop was then about as long as the 128 cycles the
+    // pair's tensor cores need per 256 x 256 x 16 step, i.e. the tensor pipe waited for its issuer.
+    if (cta_rank == 0) {   // pair: only the leader CTA issues MMAs
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -212,35 +221,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
-        VDR_TRACE(0, it);
+        if (lane == 0) VDR_TRACE(0, it);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (kb == 0) VDR_TRACE(1, it);
+          if (kb == 0 && lane == 0) VDR_TRACE(1, it);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           // A: +32 bytes per K step inside the 128-byte swizzle row (encoded address units of 16 B); in im2col mode the K
           // steps are the four [128][16] sub-tiles (32-byte rows, SWIZZLE_32B), 4 KB = 256 address units apart
           const uint64_t da = p.a_im2col ? umma_desc_kmajor_sw32(sa) : umma_desc_kmajor_sw128(sa);
           const uint64_t da_step = p.a_im2col ? 256u : 2u;
           const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            if (p.dbg == 1) break;
-            if constexpr (kCtas == 2)
-              umma_ss_2sm(d_tmem, da + da_step * k, db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_ss(d_tmem, da + da_step * k, db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (p.dbg == 1) break;
+              if constexpr (kCtas == 2)
+                umma_ss_2sm(d_tmem, da + da_step * k, db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                umma_ss(d_tmem, da + da_step * k, db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // smem slot free once these MMAs have read it (pair: in both CTAs)
+            if constexpr (kCtas == 2) umma_commit_2sm(&empty_bar[stage], 3);
+            else umma_commit(&empty_bar[stage]);
+            // accumulator complete (pair: wakes the epilogue warps of both CTAs)
+            if (kb == k_blocks - 1) {
+              if constexpr (kCtas == 2) umma_commit_2sm(&tmem_full[acc], 3);
+              else umma_commit(&tmem_full[acc]);
+            }
           }
-          // smem slot free once these MMAs have read it (pair: in both CTAs)
-          if constexpr (kCtas == 2) umma_commit_2sm(&empty_bar[stage], 3);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        // accumulator complete (pair: wakes the epilogue warps of both CTAs)
-        if constexpr (kCtas == 2) umma_commit_2sm(&tmem_full[acc], 3);
-        else umma_commit(&tmem_full[acc]);
-        VDR_TRACE(2, it);
+        if (lane == 0) VDR_TRACE(2, it);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
