@@ -49,6 +49,26 @@ const char* vdr_last_error_string(void);
 uint64_t    vdr_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Dropout of the classifier's train mode (nn.TransformerEncoderLayer(dropout=0.1 | 0.5), MLPLayer(0.1): models_archs.py:51,58,135,
+ * 187-199; active under model.train(), train_models.py:652).  Counter based: element (row r, column c) of dropout site `site` is
+ * KEPT iff the 16-bit lane (c & 7) of Philox4x32-10(counter = (c >> 3, r_lo, r_hi, site), key = (seed_lo, seed_hi)) is >= thr16,
+ * and kept values are multiplied by 65536 / (65536 - thr16): p = thr16 / 65536.  The backward kernels regenerate the masks from
+ * the same (seed, site), nothing is stored.  thr16 == 0 (or a NULL pointer) = no dropout, bit-identical to the p = 0 path.
+ * RNG streams cannot match PyTorch's: parity is statistical (keep rate, 1 / (1 - p) scale) plus exact gradients against fp32
+ * autograd with the mask exported by vdr_dropout_mask. */
+typedef struct {
+  uint64_t seed;
+  uint32_t site;
+  uint32_t thr16;
+} vdr_dropout;
+/* out = x * mask / (1 - p): bf16 (rows, cols) with row pitches ldx / ldo (elements), cols % 8 == 0.  The backward of a dropout
+ * that the forward applied inside a GEMM epilogue. */
+int vdr_dropout_apply(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int cols, const vdr_dropout* drop,
+                      vdr_stream_t stream);
+/* out[r * cols + c] = 1 if element (r, c) of the site is kept: the mask as every kernel of this library computes it. */
+int vdr_dropout_mask(uint8_t* out, int64_t rows, int64_t cols, const vdr_dropout* drop, vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores: C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N] (+ R)).
  * A, W bf16 (K contiguous), fp32 accumulation in TMEM, bias f32 (may be NULL), C bf16 or f32.
  * Replaces: torch.nn.Linear inside the backbone (tfds_dense_descriptor.py:123, K3 in SURVEY 2.4)
@@ -81,6 +101,10 @@ typedef struct {
   const float* ln_stats;  int ln_slots;  float ln_eps;
   const float* ln_colsum;
   float* stats_out;
+  /* EPI_BIAS_RESIDUAL only: C = R + dropout(A W^T + bias), element (m, n) of the site = output element (m, n) -- dropout1 /
+   * dropout2 of nn.TransformerEncoderLayer (the sub-layer output is dropped BEFORE the residual add).  bf16 C, N % 32 == 0,
+   * no row remapping, no folded LayerNorm / statistics (the classifier's shapes).  thr16 == 0 = off. */
+  vdr_dropout drop;
 } vdr_gemm_args;
 
 int vdr_gemm(const vdr_gemm_args* args, vdr_stream_t stream);
@@ -207,9 +231,11 @@ int vdr_cls_concat_layernorm_fwd(const float* X, const float* cls, const float* 
  * nn.TransformerEncoderLayer (models_archs.py:146).
  * qkv bf16 (B*N, 3*d) as written by the QKV GEMM: [q(h,64) | k(h,64) | v(h,64)] per token;
  * out bf16 (B*N, d).  lse (B, h, N) f32 optional (log-sum-exp, for the backward pass).
+ * drop (NULL = none): attention dropout of nn.MultiheadAttention -- the NORMALISED probabilities are dropped before P V (the row
+ * sums keep every key); element (row (b*heads + h)*N + q, column k) of the site.
  */
 int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse,
-                       int B, int N, int heads, float scale, vdr_stream_t stream);
+                       int B, int N, int heads, float scale, const vdr_dropout* drop, vdr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * G1: tumour-mask gather of ViT descriptors into a per-patient point cloud.
@@ -298,9 +324,10 @@ int vdr_voxel_gather(const float* img, const uint8_t* mask, int H, int W, int S,
  * Training-only kernels of the point-cloud classifier (backward of models_archs.py:141-147 as driven by
  * loss.backward() at train_models.py:683).  dgrad / wgrad reuse vdr_gemm on transposed operands.
  */
-/* h = gelu_erf(z), dz = dh * gelu'(z); bf16, n elements (n % 8 == 0). */
-int vdr_gelu_fwd(const void* z, void* h, int64_t n, vdr_stream_t stream);
-int vdr_gelu_bwd(const void* dh, const void* z, void* dz, int64_t n, vdr_stream_t stream);
+/* h = dropout(gelu_erf(z)), dz = dh * mask / (1 - p) * gelu'(z); bf16, n elements (n % 8 == 0).  drop (NULL = none) is the
+ * feed-forward block's inner dropout; with it the n elements are a contiguous (n / cols, cols) matrix, cols % 8 == 0. */
+int vdr_gelu_fwd(const void* z, void* h, int64_t n, int cols, const vdr_dropout* drop, vdr_stream_t stream);
+int vdr_gelu_bwd(const void* dh, const void* z, void* dz, int64_t n, int cols, const vdr_dropout* drop, vdr_stream_t stream);
 /* out (cols, rows; pitch ld_out) = in (rows, cols; pitch ld_in)^T, bf16, through a shared-memory tile. */
 int vdr_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols,
                        vdr_stream_t stream);
@@ -314,7 +341,7 @@ int vdr_colsum_bf16(const void* in, int64_t ld, int rows, int cols, float* out_a
  * workspace >= vdr_flash_attn_bwd_workspace_bytes(B, N, heads), 16-byte aligned. */
 size_t vdr_flash_attn_bwd_workspace_bytes(int B, int N, int heads);
 int vdr_flash_attn_bwd(const void* qkv, int64_t ld_qkv, const void* O, const void* dO, int64_t ld_o, const float* lse,
-                       void* dqkv, int64_t ld_dqkv, int B, int N, int heads, float scale, void* workspace,
+                       void* dqkv, int64_t ld_dqkv, int B, int N, int heads, float scale, const vdr_dropout* drop, void* workspace,
                        size_t workspace_bytes, vdr_stream_t stream);
 /* Attention backward pieces of the earlier, unfused path (scores materialised per head; N <= ~16k tokens in this model):
  *   delta[h][i] = sum_c dO[i][h*64+c] * O[i][h*64+c]
@@ -326,13 +353,14 @@ int vdr_attn_p_ds(const float* S, const float* dP, const float* lse, const float
 int vdr_cls_concat_layernorm_bwd(const void* dY, const float* X, const float* cls, const float* gamma,
                                  const float* mean, const float* rstd, float* dgamma, float* dbeta, float* dcls,
                                  int n, int d, vdr_stream_t stream);
-/* Classification head MLPLayer (models_archs.py:186-200): zc = W1 cls + b1, logits = W2 gelu(zc) + b2, and its
- * backward (accumulates dW1, db1, dW2, db2; writes dcls = W1^T dzc + dcls_in).  Single CTA, f32 weights. */
+/* Classification head MLPLayer (models_archs.py:186-200): zc = W1 cls + b1, logits = drop(W2 drop(gelu(zc)) + b2), and its
+ * backward (accumulates dW1, db1, dW2, db2; writes dcls = W1^T dzc + dcls_in).  f32 weights.  drop (NULL = none): the layer's two
+ * dropouts, hidden units = row 0 of the site, outputs = row 1 (the reference really drops the logits, :198-199). */
 int vdr_cls_head_fwd(const void* cls_bf16, const float* W1, const float* b1, const float* W2, const float* b2,
-                     float* zc, float* logits, int d, int H1, int C, vdr_stream_t stream);
+                     float* zc, float* logits, int d, int H1, int C, const vdr_dropout* drop, vdr_stream_t stream);
 int vdr_cls_head_bwd(const void* cls_bf16, const float* W1, const float* W2, const float* zc, const float* dlogits,
                      const float* dcls_in, float* dW1, float* db1, float* dW2, float* db2, float* dcls,
-                     int d, int H1, int C, vdr_stream_t stream);
+                     int d, int H1, int C, const vdr_dropout* drop, vdr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Bimodal PET+CT classifier pieces (TransformerNoduleBimodalClassifier, models_archs.py:38-124).

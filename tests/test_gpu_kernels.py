@@ -2,6 +2,7 @@
 Tolerances are for bf16 operands / bf16 outputs with fp32 accumulation (bf16 eps = 2^-8 = 3.9e-3)."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -324,3 +325,174 @@ def test_flash_attention_backward_vs_fp32_autograd(cuda, B, N, heads):
         assert err <= 0.02 * w.abs().max().item() + 2e-3, (name, err, w.abs().max().item())
         cos = torch.nn.functional.cosine_similarity(g.flatten(), w.flatten(), dim=0).item()
         assert cos > 0.999, (name, cos)
+
+
+# ----------------------------------------------------------------------------- train-mode dropout (models_archs.py:51,58,135,187-199)
+def _philox4x32_10(c, k):
+    """NumPy Philox4x32-10 (Salmon et al., as curand / torch use it): c (n, 4) uint32 counters, k (2,) key."""
+    c = c.astype(np.uint64).copy()
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], 1)
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c.astype(np.uint32)
+
+
+def _host_mask(rows, cols, seed, site, thr16):
+    """The documented definition (include/vdr.h, vdr_dropout): element (r, c) kept iff the 16-bit lane c & 7 of
+    Philox(counter = (c >> 3, r_lo, r_hi, site), key = seed) >= thr16."""
+    r, c8 = np.meshgrid(np.arange(rows, dtype=np.uint64), np.arange((cols + 7) // 8, dtype=np.uint64), indexing="ij")
+    ctr = np.stack([c8.ravel(), r.ravel() & np.uint64(0xFFFFFFFF), r.ravel() >> np.uint64(32), np.full(r.size, site, np.uint64)], 1)
+    out = _philox4x32_10(ctr, (seed & 0xFFFFFFFF, seed >> 32)).reshape(rows, -1, 4)
+    lanes = np.stack([out[..., 0] & 0xFFFF, out[..., 0] >> 16, out[..., 1] & 0xFFFF, out[..., 1] >> 16,
+                      out[..., 2] & 0xFFFF, out[..., 2] >> 16, out[..., 3] & 0xFFFF, out[..., 3] >> 16], -1).reshape(rows, -1)[:, :cols]
+    return lanes >= thr16
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_dropout_mask_definition_and_statistics(cuda, p):
+    """The device mask == the documented Philox definition (bit for bit), keep rate = 1 - p within binomial noise, kept values
+    scaled by 1 / (1 - p), and p = 0 is the identity."""
+    from vit_deep_radiomics_b200 import ops
+    d = ops.Drop(seed=0x1234567890ABCDEF, site=7, p=p)
+    m = ops.dropout_mask(300, 1000, d, cuda).cpu().numpy().astype(bool)
+    assert np.array_equal(m, _host_mask(300, 1000, d.seed, d.site, d.thr16))
+    keep = m.mean()
+    assert abs(keep - (1 - d.p)) < 4 * np.sqrt(d.p * (1 - d.p) / m.size)
+    assert not np.array_equal(m, ops.dropout_mask(300, 1000, ops.Drop(d.seed, 8, p), cuda).cpu().numpy().astype(bool))   # another site, another mask
+    x = torch.randn(64, 256, device=cuda).bfloat16()
+    y = ops.dropout_apply(x, d).float().cpu().numpy()
+    mk = ops.dropout_mask(64, 256, d, cuda).cpu().numpy().astype(bool)
+    want = np.where(mk, x.float().cpu().numpy() / (1 - d.p), 0.0)
+    assert np.allclose(y, want, rtol=2 ** -7, atol=0) and np.all(y[~mk] == 0)
+    z = torch.randn(32, 64, device=cuda).bfloat16()
+    assert torch.equal(ops.gelu(z), ops.gelu(z, drop=ops.Drop(1, 1, 0.0)))                                                 # p = 0: bit-identical
+
+
+def test_dropout_sites_match_exported_mask(cuda):
+    """Every kernel that applies dropout uses the exported mask: GELU (fwd / bwd), the residual GEMM epilogue, the head."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(0)
+    d = ops.Drop(seed=99, site=3, p=0.3)
+    z = torch.randn(130, 256, device=cuda).bfloat16()
+    mk = ops.dropout_mask(130, 256, d, cuda).bool()
+    sc = 1.0 / (1 - d.p)
+    h, h0 = ops.gelu(z, drop=d).float(), ops.gelu(z).float()
+    assert torch.all(h[~mk] == 0) and torch.allclose(h[mk], h0[mk] * sc, rtol=2 ** -7, atol=1e-6)
+    dh = torch.randn(130, 256, device=cuda).bfloat16()
+    dz, dz0 = ops.gelu_bwd(dh, z, drop=d).float(), ops.gelu_bwd(dh, z).float()
+    assert torch.all(dz[~mk] == 0) and torch.allclose(dz[mk], dz0[mk] * sc, rtol=2 ** -6, atol=1e-6)
+    # C = R + dropout(A W^T + b)
+    a = (torch.randn(130, 64, device=cuda) * 0.5).bfloat16()
+    w = (torch.randn(256, 64, device=cuda) * 0.2).bfloat16()
+    b = torch.randn(256, device=cuda)
+    r = torch.randn(130, 256, device=cuda).bfloat16()
+    got = ops.gemm(a, w, b, epilogue="residual", residual=r, drop=d).float()
+    lin = a.float() @ w.float().t() + b
+    want = r.float() + torch.where(mk, lin * sc, torch.zeros_like(lin))
+    assert (got - want).abs().max() < 0.05
+    plain = ops.gemm(a, w, b, epilogue="residual", residual=r).float()
+    assert torch.equal(ops.gemm(a, w, b, epilogue="residual", residual=r, drop=ops.Drop(5, 5, 0.0)).float(), plain)        # p = 0 path untouched
+    # head: hidden mask = row 0, logit mask = row 1 of the site
+    cls = torch.randn(64, device=cuda).bfloat16()
+    W1, b1, W2, b2 = torch.randn(128, 64, device=cuda) * 0.2, torch.randn(128, device=cuda) * 0.1, torch.randn(2, 128, device=cuda) * 0.2, torch.randn(2, device=cuda)
+    hm = ops.dropout_mask(2, 128, d, cuda).bool()
+    logits, zc = ops.cls_head_fwd(cls, W1, b1, W2, b2, drop=d)
+    hid = torch.nn.functional.gelu(W1 @ cls.float() + b1) * hm[0].float() * sc
+    want_l = (W2 @ hid + b2) * hm[1, :2].float() * sc
+    assert torch.allclose(logits, want_l, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,heads,p", [(200, 2, 0.1), (1025, 1, 0.5), (130, 4, 0.25)])
+def test_flash_attention_dropout_fwd_bwd_vs_fp32_autograd(cuda, N, heads, p):
+    """Attention dropout (nn.MultiheadAttention(dropout=p)): softmax -> mask / (1 - p) -> P V, forward AND the fused backward
+    (which regenerates the mask) against fp32 autograd using the exported mask; lse is the dropout-free normaliser."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(N)
+    d = heads * 64
+    qkv = (torch.randn(N, 3 * d, device=cuda) * 0.7).bfloat16()
+    drop = ops.Drop(seed=4242, site=11, p=p)
+    out, lse = ops.flash_attn(qkv, 1, N, heads, return_lse=True, drop=drop)
+    mk = ops.dropout_mask(heads * N, N, drop, cuda).bool().view(heads, N, N)          # row = (b*heads + h)*N + q
+    x = qkv.float().clone().requires_grad_(True)
+    q, k, v = (x[:, i * d:(i + 1) * d].view(N, heads, 64).transpose(0, 1) for i in range(3))
+    s = q @ k.transpose(1, 2) / 8.0
+    pm = torch.softmax(s, -1) * mk.float() / (1 - drop.p)
+    ref = (pm @ v).transpose(0, 1).reshape(N, d)
+    assert (out.float() - ref).abs().max() < 0.06
+    assert torch.allclose(lse[0], torch.logsumexp(s, -1).detach(), rtol=0, atol=2e-2)
+    do = torch.randn(N, d, device=cuda).bfloat16()
+    ref.backward(do.float())
+    dqkv = ops.flash_attn_bwd(qkv, out, do, lse, 1, N, heads, drop=drop).float()
+    for i, name in enumerate("qkv"):
+        g, w = dqkv[:, i * d:(i + 1) * d].flatten().double(), x.grad[:, i * d:(i + 1) * d].flatten().double()
+        cos = float(g @ w / (g.norm() * w.norm()))
+        assert cos > 0.998, (name, cos)
+    # without dropout the same call is the p = 0 kernel
+    assert torch.equal(ops.flash_attn(qkv, 1, N, heads), ops.flash_attn(qkv, 1, N, heads, drop=ops.Drop(1, 2, 0.0)))
+
+
+def test_classifier_train_mode_dropout_gradients_vs_fp32_autograd(cuda):
+    """TransformerNoduleClassifier in train() with the reference's rates (0.1 / 0.1): the kernels' forward and EVERY parameter
+    gradient against an fp32 autograd restatement of the same network that applies the exported masks at the same sites
+    (attention probabilities, both sub-layer outputs, the feed-forward activation, head hidden units, logits);
+    eval() stays dropout-free and deterministic, train() differs between passes."""
+    from oracle import classifier_fp32 as C
+    from vit_deep_radiomics_b200 import classifier_kernels as ck, ops
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier
+    d, ff, heads, layers, n = 128, 256, 2, 2, 150
+    sd0 = C.init_state_dict(d, ff, 2, layers, seed=21)
+    model = TransformerNoduleClassifier(d, ff, heads, 2, layers)
+    model.load_state_dict(sd0)
+    model = model.to(cuda)
+    x = torch.randn(1, n, d, generator=torch.Generator().manual_seed(3)).to(cuda)
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = model(x)[0], model(x)[0]
+    assert torch.equal(e1, e2)
+    model.train()
+    with torch.no_grad():
+        t1, t2 = model(x)[0], model(x)[0]
+    assert not torch.equal(t1, t2) and not torch.equal(t1, e1)
+    # one pass with a known seed through the autograd Function
+    cfg = ck.DropCfg(seed=777, p=0.1, p_head=0.1)
+    params = model.param_list()
+    logits, cls = ck.ClassifierFunction.apply(x[0], heads, layers, cfg, *params)
+    (logits * torch.tensor([1.0, -2.0], device=cuda)).sum().backward()
+    N = n + 1
+
+    def mask(site_drop, rows, cols):
+        return ops.dropout_mask(rows, cols, site_drop, cuda).float() / (1 - site_drop.p)
+
+    sd = {k: v.detach().clone().to(cuda).requires_grad_(True) for k, v in sd0.items()}
+    y = torch.nn.functional.layer_norm(torch.cat([sd["cls_token"][0], x[0]], 0), (d,), sd["norm.weight"], sd["norm.bias"], 1e-5)
+    for l in range(layers):
+        pre = f"transformer_encoder.layers.{l}."
+        qkv = y @ sd[pre + "self_attn.in_proj_weight"].t() + sd[pre + "self_attn.in_proj_bias"]
+        q, k, v = (qkv[:, i * d:(i + 1) * d].view(N, heads, 64).transpose(0, 1) for i in range(3))
+        pm = torch.softmax(q @ k.transpose(1, 2) / 8.0, -1) * mask(cfg.site(l, 0), heads * N, N).view(heads, N, N)
+        a = (pm @ v).transpose(0, 1).reshape(N, d)
+        t = y + (a @ sd[pre + "self_attn.out_proj.weight"].t() + sd[pre + "self_attn.out_proj.bias"]) * mask(cfg.site(l, 1), N, d)
+        y1 = torch.nn.functional.layer_norm(t, (d,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5)
+        h = torch.nn.functional.gelu(y1 @ sd[pre + "linear1.weight"].t() + sd[pre + "linear1.bias"]) * mask(cfg.site(l, 2), N, ff)
+        u = y1 + (h @ sd[pre + "linear2.weight"].t() + sd[pre + "linear2.bias"]) * mask(cfg.site(l, 3), N, d)
+        y = torch.nn.functional.layer_norm(u, (d,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
+    hm = mask(cfg.head(0), 2, 2 * d)
+    hid = torch.nn.functional.gelu(sd["classifier.dense1.weight"] @ y[0] + sd["classifier.dense1.bias"]) * hm[0]
+    want = (sd["classifier.dense2.weight"] @ hid + sd["classifier.dense2.bias"]) * hm[1, :2]
+    (want * torch.tensor([1.0, -2.0], device=cuda)).sum().backward()
+    assert (logits.detach() - want.detach()).abs().max() < 0.05, (logits, want)
+    worst = 1.0
+    for name, p_ in model.named_parameters():
+        g, w = p_.grad.detach().double().flatten(), sd[name].grad.double().flatten()
+        assert torch.isfinite(g).all(), name
+        if w.norm() < 1e-7:
+            assert g.norm() < 1e-4, name
+            continue
+        cos = float(g @ w / (g.norm() * w.norm()))
+        worst = min(worst, cos)
+        assert cos > 0.99 and float((g - w).norm() / w.norm()) < 0.15, (name, cos)
+    assert worst > 0.99

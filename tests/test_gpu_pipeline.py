@@ -189,7 +189,8 @@ def test_classifier_backward_vs_golden(cuda, golden_dir):
     d, ff, heads, layers = g["cfg"].tolist()
     model = TransformerNoduleClassifier(d, ff, heads, 2, layers)
     model.load_state_dict({k[len("param__"):]: torch.tensor(g[k]) for k in g.files if k.startswith("param__")})
-    model = model.to(cuda).train()
+    from vit_deep_radiomics_b200.models_archs import set_dropout
+    model = set_dropout(model.to(cuda), 0.0, 0.0).train()      # the golden gradients come from the reference in eval() mode (no dropout)
     crit = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=cuda), gamma=2)
     logits, cls = model(torch.tensor(g["x"]).to(cuda))
     loss = crit(torch.squeeze(logits), torch.tensor(g["y"]).to(cuda)[0])
@@ -218,9 +219,10 @@ def test_train_step_accumulation_semantics(cuda):
     from vit_deep_radiomics_b200.train_models import FocalLoss, train_epoch
     torch.manual_seed(0)
     sd0 = C.init_state_dict(64, 128, 2, 1, seed=9)
+    from vit_deep_radiomics_b200.models_archs import set_dropout
     model = TransformerNoduleClassifier(64, 128, 1, 2, 1)
     model.load_state_dict(sd0)
-    model = model.to(cuda)
+    model = set_dropout(model.to(cuda), 0.0, 0.0)              # parity with the dropout-free fp32 oracle
     opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.01)
     gen = torch.Generator().manual_seed(2)
     data = [(torch.randn(int(n), 64, generator=gen), torch.eye(2)[int(c)]) for n, c in [(40, 0), (25, 1), (33, 1), (17, 0), (29, 1)]]
@@ -253,9 +255,10 @@ def test_train_epoch_bimodal_crossmodal_loss_matches_cpu_training(cuda, golden_d
     cfg = [int(v) for v in g["cfg"]]
     d, heads_ct, heads_pet, layers_ct, layers_pet = cfg[0], cfg[3], cfg[4], cfg[5], cfg[6]
     sd0 = {k[len("param__"):]: torch.tensor(g[k]) for k in g.files if k.startswith("param__")}
+    from vit_deep_radiomics_b200.models_archs import set_dropout
     model = TransformerNoduleBimodalClassifier(*cfg)
     model.load_state_dict(sd0)
-    model = model.to(cuda)
+    model = set_dropout(model.to(cuda), 0.0, 0.0)              # parity with the dropout-free fp32 oracle
     opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.01)
     gen = torch.Generator().manual_seed(4)
     data = [(torch.randn(nc, d, generator=gen), torch.randn(np_, d, generator=gen), torch.eye(2)[c])
@@ -388,7 +391,8 @@ def test_c5_extraction_feeds_classifier_training_step(cuda):
     tokens = out["tokens"][:n]
     D = model.cfg["dim"]
     torch.manual_seed(1)
-    clf = TransformerNoduleClassifier(D, 4 * D, D // 64, 2, 2).to(cuda)
+    from vit_deep_radiomics_b200.models_archs import set_dropout
+    clf = set_dropout(TransformerNoduleClassifier(D, 4 * D, D // 64, 2, 2).to(cuda), 0.0, 0.0)   # compared with the dropout-free oracle below
     y = torch.tensor([0.0, 1.0], device=cuda)
     logits, cls = clf(tokens.unsqueeze(0))
     loss = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=cuda), gamma=2)(torch.squeeze(logits), y)
@@ -413,9 +417,10 @@ def test_bimodal_classifier_vs_golden(cuda, golden_dir, mode):
     from vit_deep_radiomics_b200.models_archs import TransformerNoduleBimodalClassifier
     from vit_deep_radiomics_b200.train_models import FocalLoss
     g = np.load(os.path.join(golden_dir, "bimodal_small.npz"))
+    from vit_deep_radiomics_b200.models_archs import set_dropout
     model = TransformerNoduleBimodalClassifier(*[int(v) for v in g["cfg"]])
     model.load_state_dict({k[len("param__"):]: torch.tensor(g[k]) for k in g.files if k.startswith("param__")})
-    model = model.to(cuda).train()
+    model = set_dropout(model.to(cuda), 0.0, 0.0).train()      # the golden gradients come from the reference without dropout
     x_ct = torch.tensor(g["x_ct"]).to(cuda) if mode in ("both", "ct") else None
     x_pet = torch.tensor(g["x_pet"]).to(cuda) if mode in ("both", "pet") else None
     y = torch.tensor(g["y"]).to(cuda)

@@ -271,7 +271,8 @@ def test_medsam_descriptors_feed_the_shipped_classifier_config(cuda):
     tokens = out["tokens"][:n]
     cfg = config_manager.load_conf(project_dir=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     torch.manual_seed(2)
-    clf = tm.build_model(cfg, "transformer", "ct").to(cuda)
+    from vit_deep_radiomics_b200.models_archs import set_dropout
+    clf = set_dropout(tm.build_model(cfg, "transformer", "ct").to(cuda), 0.0, 0.0)   # compared with the dropout-free oracle below
     mcfg = cfg["models"]["transformer"]
     assert mcfg["feature_dim"] == 256
     heads, layers = mcfg["ct"]["num_heads"], mcfg["ct"]["num_layers"]

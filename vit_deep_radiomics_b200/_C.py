@@ -17,7 +17,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 #: every symbol include/vdr.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "vdr_version", "vdr_last_error_string", "vdr_launch_count",
-    "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
+    "vdr_dropout_apply", "vdr_dropout_mask", "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd", "vdr_row_stats", "vdr_fold_layernorm",
     "vdr_flash_attn_fwd", "vdr_flash_attn_bwd_workspace_bytes", "vdr_flash_attn_bwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather", "vdr_mask_gather_table", "vdr_mask_count", "vdr_exclusive_scan_i64", "vdr_debug_set_gather_trace",
@@ -43,6 +43,11 @@ class VitWeights(C.Structure):
                 ("pos", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("blocks", C.POINTER(VitBlock))]
 
 
+class Dropout(C.Structure):
+    """== vdr_dropout (include/vdr.h): counter-based dropout site; thr16 = round(p * 65536), 0 = off"""
+    _fields_ = [("seed", C.c_uint64), ("site", C.c_uint32), ("thr16", C.c_uint32)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("lda", C.c_int64),
@@ -56,6 +61,7 @@ class GemmArgs(C.Structure):
         ("res_mod", C.c_int), ("res_offset", C.c_int),
         ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
         ("stats_out", C.c_void_p),
+        ("drop", Dropout),
     ]
 
 
@@ -100,8 +106,11 @@ def lib() -> C.CDLL:
     L.vdr_patch_embed_gemm.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp, i64, i32, vp]
     L.vdr_flash_attn_bwd_workspace_bytes.argtypes = [i32, i32, i32]
     L.vdr_flash_attn_bwd_workspace_bytes.restype = sz
-    L.vdr_flash_attn_bwd.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, i32, f32, vp, sz, vp]
-    L.vdr_flash_attn_fwd.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, f32, vp]
+    dp = C.POINTER(Dropout)
+    L.vdr_dropout_apply.argtypes = [vp, i64, vp, i64, i64, i32, dp, vp]
+    L.vdr_dropout_mask.argtypes = [vp, i64, i64, dp, vp]
+    L.vdr_flash_attn_bwd.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, i32, f32, dp, vp, sz, vp]
+    L.vdr_flash_attn_fwd.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, f32, dp, vp]
     L.vdr_mask_gather_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.vdr_mask_gather_workspace_bytes.restype = sz
     L.vdr_mask_gather.argtypes = [vp, i32, i64, i64, i64, i64, vp, i64, i64, i64, vp, vp, i32, i32, i32, i32,
@@ -114,15 +123,15 @@ def lib() -> C.CDLL:
     L.vdr_voxel_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_mask_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_voxel_gather.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
-    L.vdr_gelu_fwd.argtypes = [vp, vp, i64, vp]
-    L.vdr_gelu_bwd.argtypes = [vp, vp, vp, i64, vp]
+    L.vdr_gelu_fwd.argtypes = [vp, vp, i64, i32, dp, vp]
+    L.vdr_gelu_bwd.argtypes = [vp, vp, vp, i64, i32, dp, vp]
     L.vdr_transpose_bf16.argtypes = [vp, i64, vp, i64, i32, i32, vp]
     L.vdr_colsum_bf16.argtypes = [vp, i64, i32, i32, vp, vp]
     L.vdr_attn_delta.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.vdr_attn_p_ds.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, f32, vp]
     L.vdr_cls_concat_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
-    L.vdr_cls_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
-    L.vdr_cls_head_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    L.vdr_cls_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, dp, vp]
+    L.vdr_cls_head_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, dp, vp]
     L.vdr_linear_vec_fwd.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     L.vdr_linear_vec_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.vdr_cross_cls_attn_fwd.argtypes = [vp, vp, i64, i32, i32, f32, vp, vp, vp]

@@ -12,7 +12,9 @@ reference: src/models_archs.py:38-124 (TransformerNoduleBimodalClassifier), :174
     z = MLP_proj(cat(a_ct, a_pet)); logits_petct = MLP_petct(z)       returns (logits_petct, z, logits_ct, logits_pet)
 
 With one modality missing the model is the unimodal classifier with that modality's encoder and head (:105-119).
-Dropout (0.5 / 0.1 in the reference's train mode) is not applied, as in the unimodal model.
+Train mode: dropout 0.5 inside both encoders (:51,58) and 0.1 in the four MLPLayers (:66-75), applied inside the kernels as in
+classifier_kernels.py (``drop``: a DropCfg; the two encoders and the four heads use disjoint site ids); the reference's
+nn.MultiheadAttention cross attention has no dropout (:177).
 """
 from __future__ import annotations
 
@@ -26,11 +28,11 @@ from . import ops
 _f32, _bf16, _bf16_t = ck._f32, ck._bf16, ck._bf16_t
 
 
-def _head_fwd(vec_f32, hp):
+def _head_fwd(vec_f32, hp, drop=None):
     """MLPLayer on one vector: returns (out f32, saved)."""
     v16 = vec_f32.to(torch.bfloat16)
-    out, zc = ops.cls_head_fwd(v16, _f32(hp[0]), _f32(hp[1]), _f32(hp[2]), _f32(hp[3]))
-    return out, (v16, zc)
+    out, zc = ops.cls_head_fwd(v16, _f32(hp[0]), _f32(hp[1]), _f32(hp[2]), _f32(hp[3]), drop=drop)
+    return out, (v16, zc, drop)
 
 
 def _cross_fwd(y_q, y_kv, cp, heads):
@@ -68,36 +70,43 @@ def _cross_bwd(da, cp, s, heads, dy_q_row0, dy_kv):
     return [g_in, g_bin, g_o, g_bo], dy_kv
 
 
-def bimodal_forward(x_ct, x_pet, cfg, params, save=False):
+#: site bases of the two encoders / indices of the four heads (ct, pet, projection, petct)
+_BASE_CT, _BASE_PET = 0, 4096
+
+
+def bimodal_forward(x_ct, x_pet, cfg, params, save=False, drop=None):
     """x_* (n, d) f32 CUDA or None.  cfg = dict(heads_ct, heads_pet, layers_ct, layers_pet); params = dict of parameter lists
     (enc_ct, enc_pet, cross_ct, cross_pet, head_ct, head_pet, proj, head_petct).  Returns the reference's 4-tuple (each for batch 1:
     logits (C,), petct_cls (d,), logits_ct (C,), logits_pet (C,)) [, saved]."""
     saved = {}
     y_ct = y_pet = None
     if x_ct is not None:
-        r = ck.encoder_forward(x_ct, cfg["heads_ct"], cfg["layers_ct"], params["enc_ct"], save=save)
+        r = ck.encoder_forward(x_ct, cfg["heads_ct"], cfg["layers_ct"], params["enc_ct"], save=save,
+                               drop=drop.with_base(_BASE_CT) if drop is not None else None)
         y_ct, saved["enc_ct"] = r if save else (r, None)
     if x_pet is not None:
-        r = ck.encoder_forward(x_pet, cfg["heads_pet"], cfg["layers_pet"], params["enc_pet"], save=save)
+        r = ck.encoder_forward(x_pet, cfg["heads_pet"], cfg["layers_pet"], params["enc_pet"], save=save,
+                               drop=drop.with_base(_BASE_PET) if drop is not None else None)
         y_pet, saved["enc_pet"] = r if save else (r, None)
+    hd = (lambda i: drop.head(i)) if drop is not None else (lambda i: None)
     if y_ct is not None and y_pet is not None:
         a_ct, saved["cross_ct"] = _cross_fwd(y_ct, y_pet, params["cross_ct"], cfg["heads_ct"])
         a_pet, saved["cross_pet"] = _cross_fwd(y_pet, y_ct, params["cross_pet"], cfg["heads_ct"])   # the reference builds both with num_heads_ct (:70-71)
-        logits_ct, saved["h_ct"] = _head_fwd(a_ct, params["head_ct"])
-        logits_pet, saved["h_pet"] = _head_fwd(a_pet, params["head_pet"])
+        logits_ct, saved["h_ct"] = _head_fwd(a_ct, params["head_ct"], hd(0))
+        logits_pet, saved["h_pet"] = _head_fwd(a_pet, params["head_pet"], hd(1))
         cat = torch.cat([a_ct, a_pet])
-        z, saved["h_proj"] = _head_fwd(cat, params["proj"])
-        logits, saved["h_petct"] = _head_fwd(z, params["head_petct"])
+        z, saved["h_proj"] = _head_fwd(cat, params["proj"], hd(2))
+        logits, saved["h_petct"] = _head_fwd(z, params["head_petct"], hd(3))
         out = (logits, z, logits_ct, logits_pet)
         saved["mode"] = "both"
     elif y_ct is not None:
         cls = y_ct[0].float()
-        logits_ct, saved["h_ct"] = _head_fwd(cls, params["head_ct"])
+        logits_ct, saved["h_ct"] = _head_fwd(cls, params["head_ct"], hd(0))
         out = (logits_ct, cls, logits_ct, logits_ct)
         saved["mode"] = "ct"
     else:
         cls = y_pet[0].float()
-        logits_pet, saved["h_pet"] = _head_fwd(cls, params["head_pet"])
+        logits_pet, saved["h_pet"] = _head_fwd(cls, params["head_pet"], hd(1))
         out = (logits_pet, cls, logits_pet, logits_pet)
         saved["mode"] = "pet"
     return out + ((saved,) if save else ())
@@ -119,8 +128,8 @@ def bimodal_backward(cfg, params, saved, d_logits, d_z, d_logits_ct, d_logits_pe
         key_e, key_h, heads, layers = ("enc_ct", "head_ct", cfg["heads_ct"], cfg["layers_ct"]) if mode == "ct" else \
                                       ("enc_pet", "head_pet", cfg["heads_pet"], cfg["layers_pet"])
         dl = add(add(d_logits, d_logits_ct), d_logits_pet)            # the three logits outputs are the same tensor (:105-119)
-        v16, zc = saved["h_ct" if mode == "ct" else "h_pet"]
-        g[key_h], dvec = ck.head_backward(v16, params[key_h], zc, dl, d_z)
+        v16, zc, hdrop = saved["h_ct" if mode == "ct" else "h_pet"]
+        g[key_h], dvec = ck.head_backward(v16, params[key_h], zc, dl, d_z, drop=hdrop)
         enc_saved = saved[key_e]
         n, d = enc_saved["x"].shape
         dy = torch.zeros((n + 1, d), dtype=torch.bfloat16, device=dvec.device)
@@ -129,14 +138,14 @@ def bimodal_backward(cfg, params, saved, d_logits, d_z, d_logits_ct, d_logits_pe
         return g
 
     d = saved["cross_ct"]["xq"].numel()
-    v16, zc = saved["h_petct"]
-    g["head_petct"], dz = ck.head_backward(v16, params["head_petct"], zc, d_logits, d_z)
-    v16, zc = saved["h_proj"]
-    g["proj"], dcat = ck.head_backward(v16, params["proj"], zc, dz, None)      # an MLPLayer whose output gradient is a vector: same kernel, C = d
-    v16, zc = saved["h_ct"]
-    g["head_ct"], da_ct = ck.head_backward(v16, params["head_ct"], zc, d_logits_ct, dcat[:d].contiguous())
-    v16, zc = saved["h_pet"]
-    g["head_pet"], da_pet = ck.head_backward(v16, params["head_pet"], zc, d_logits_pet, dcat[d:].contiguous())
+    v16, zc, hdrop = saved["h_petct"]
+    g["head_petct"], dz = ck.head_backward(v16, params["head_petct"], zc, d_logits, d_z, drop=hdrop)
+    v16, zc, hdrop = saved["h_proj"]
+    g["proj"], dcat = ck.head_backward(v16, params["proj"], zc, dz, None, drop=hdrop)      # an MLPLayer whose output gradient is a vector: same kernel, C = d
+    v16, zc, hdrop = saved["h_ct"]
+    g["head_ct"], da_ct = ck.head_backward(v16, params["head_ct"], zc, d_logits_ct, dcat[:d].contiguous(), drop=hdrop)
+    v16, zc, hdrop = saved["h_pet"]
+    g["head_pet"], da_pet = ck.head_backward(v16, params["head_pet"], zc, d_logits_pet, dcat[d:].contiguous(), drop=hdrop)
     dev = da_ct.device
     row0_ct = torch.zeros(d, dtype=torch.float32, device=dev)
     row0_pet = torch.zeros(d, dtype=torch.float32, device=dev)
@@ -156,12 +165,12 @@ class BimodalFunction(torch.autograd.Function):
     """(logits_petct, petct_cls, logits_ct, logits_pet) = f(x_ct, x_pet, params...) with a hand-written backward over libvdr kernels."""
 
     @staticmethod
-    def forward(ctx, x_ct, x_pet, cfg, sizes, *flat):
+    def forward(ctx, x_ct, x_pet, cfg, sizes, drop, *flat):
         params, i = {}, 0
         for k, n in zip(GROUPS, sizes):
             params[k] = list(flat[i:i + n])
             i += n
-        out = bimodal_forward(x_ct, x_pet, cfg, params, save=True)
+        out = bimodal_forward(x_ct, x_pet, cfg, params, save=True, drop=drop)
         ctx.saved, ctx.params, ctx.cfg, ctx.sizes = out[4], params, cfg, sizes
         return out[0], out[1], out[2], out[3]
 
@@ -172,4 +181,4 @@ class BimodalFunction(torch.autograd.Function):
         flat = []
         for k, n in zip(GROUPS, ctx.sizes):
             flat += list(g[k]) if g[k] is not None else [None] * n
-        return (None, None, None, None) + tuple(flat)
+        return (None, None, None, None, None) + tuple(flat)

@@ -15,6 +15,12 @@ src/models_archs.py:130-147):
                 y   = LN2(u)
     cls = y[0];  logits = W_d2 gelu(W_d1 cls + b_d1) + b_d2        fused head kernel (fp32)
 
+Train mode (``drop``): the reference's dropouts -- nn.TransformerEncoderLayer(dropout=p) has four per layer (attention
+probabilities, the two sub-layer outputs before their residual adds, the activation inside the feed-forward block) and MLPLayer
+two (hidden units, and the logits themselves) -- are applied inside the kernels from a counter-based generator
+(include/vdr.h, vdr_dropout): site = base + 4 * layer + {0: attention P, 1: after out_proj, 2: after GELU, 3: after linear2};
+the backward regenerates every mask from (seed, site).
+
 Backward: dgrad / wgrad are the same tcgen05 GEMM on transposed operands (transpose kernel), bias
 grads are column sums, LayerNorm / GELU have their own backward kernels, and the attention backward
 recomputes P from the saved log-sum-exp with the score matrices materialised per head
@@ -63,10 +69,32 @@ def _f32(p):
     return p.detach().contiguous()
 
 
-def encoder_forward(x, num_heads, num_layers, enc_params, save=False):
+class DropCfg:
+    """Dropout of one forward pass: ``seed`` (fresh per pass), rate ``p`` of the encoder layers, rate ``p_head`` of the MLPLayer
+    heads, ``base`` = first site id of an encoder (two encoders of the bimodal model must not share sites)."""
+
+    def __init__(self, seed: int, p: float, p_head: float, base: int = 0):
+        self.seed, self.p, self.p_head, self.base = int(seed), float(p), float(p_head), int(base)
+
+    def site(self, layer: int, k: int):
+        return ops.Drop(self.seed, self.base + 4 * layer + k, self.p) if self.p > 0 else None
+
+    def head(self, idx: int = 0):
+        return ops.Drop(self.seed, 1_000_000 + idx, self.p_head) if self.p_head > 0 else None
+
+    def with_base(self, base: int):
+        return DropCfg(self.seed, self.p, self.p_head, base)
+
+
+def new_seed() -> int:
+    """A fresh 62-bit dropout seed from torch's default generator (so torch.manual_seed makes a run reproducible)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def encoder_forward(x, num_heads, num_layers, enc_params, save=False, drop: DropCfg | None = None):
     """CLS-concat + LayerNorm + `num_layers` post-norm encoder layers.  x (n, d) f32 CUDA; enc_params = [cls_token, norm.weight,
     norm.bias] + 12 tensors per layer (PARAM_ORDER of models_archs.param_list).  Returns y (n + 1, d) bf16 (row 0 = CLS)
-    [, saved activations]."""
+    [, saved activations].  ``drop``: train-mode dropout (see the module docstring)."""
     n, d = x.shape
     N = n + 1
     it = iter(enc_params)
@@ -80,22 +108,26 @@ def encoder_forward(x, num_heads, num_layers, enc_params, save=False):
     else:
         y = ops.cls_concat_layernorm(x, cls_vec, _f32(norm_w), _f32(norm_b), 1e-5)
     layers = []
-    for _ in range(num_layers):
+    dsite = (lambda l, k: drop.site(l, k)) if drop is not None else (lambda l, k: None)
+    for l in range(num_layers):
         (w_in, b_in, w_o, b_o, n1w, n1b, w1, b1, w2, b2, n2w, n2b) = (next(it) for _ in range(12))
         qkv = ops.gemm(y, _bf16(w_in), _f32(b_in))
         if save:
-            a, lse = ops.flash_attn(qkv, 1, N, num_heads, return_lse=True)
+            a, lse = ops.flash_attn(qkv, 1, N, num_heads, return_lse=True, drop=dsite(l, 0))
         else:
-            a, lse = ops.flash_attn(qkv, 1, N, num_heads), None
-        t = ops.gemm(a, _bf16(w_o), _f32(b_o), epilogue="residual", residual=y)
-        if save:
-            y1, mu1, rs1 = ops.layernorm(t, _f32(n1w), _f32(n1b), 1e-5, save_stats=True)
+            a, lse = ops.flash_attn(qkv, 1, N, num_heads, drop=dsite(l, 0)), None
+        t = ops.gemm(a, _bf16(w_o), _f32(b_o), epilogue="residual", residual=y, drop=dsite(l, 1))
+        if save or dsite(l, 2) is not None:
+            if save:
+                y1, mu1, rs1 = ops.layernorm(t, _f32(n1w), _f32(n1b), 1e-5, save_stats=True)
+            else:
+                y1 = ops.layernorm(t, _f32(n1w), _f32(n1b), 1e-5)
             z = ops.gemm(y1, _bf16(w1), _f32(b1))                      # pre-activation kept for GELU'
-            h = ops.gelu(z)
+            h = ops.gelu(z, drop=dsite(l, 2))
         else:
             y1 = ops.layernorm(t, _f32(n1w), _f32(n1b), 1e-5)
             h = ops.gemm(y1, _bf16(w1), _f32(b1), epilogue="gelu")
-        u = ops.gemm(h, _bf16(w2), _f32(b2), epilogue="residual", residual=y1)
+        u = ops.gemm(h, _bf16(w2), _f32(b2), epilogue="residual", residual=y1, drop=dsite(l, 3))
         if save:
             y2, mu2, rs2 = ops.layernorm(u, _f32(n2w), _f32(n2b), 1e-5, save_stats=True)
             layers.append(dict(y_in=y, qkv=qkv, a=a, lse=lse, t=t, mu1=mu1, rs1=rs1, y1=y1, z=z, h=h, u=u,
@@ -104,20 +136,21 @@ def encoder_forward(x, num_heads, num_layers, enc_params, save=False):
             y2 = ops.layernorm(u, _f32(n2w), _f32(n2b), 1e-5)
         y = y2
     if save:
-        saved.update(layers=layers, x=x)
+        saved.update(layers=layers, x=x, drop=drop)
         return y, saved
     return y
 
 
-def classifier_forward(x, num_heads, num_layers, params, save=False):
+def classifier_forward(x, num_heads, num_layers, params, save=False, drop: DropCfg | None = None):
     """x (n, d) f32 CUDA.  Returns (logits (C,) f32, cls (d,) f32[, saved activations])."""
-    enc = encoder_forward(x, num_heads, num_layers, params[:-4], save=save)
+    enc = encoder_forward(x, num_heads, num_layers, params[:-4], save=save, drop=drop)
     y, saved = enc if save else (enc, None)
     wd1, bd1, wd2, bd2 = params[-4:]
-    logits, zc = ops.cls_head_fwd(y[0], _f32(wd1), _f32(bd1), _f32(wd2), _f32(bd2))
+    hdrop = drop.head(0) if drop is not None else None
+    logits, zc = ops.cls_head_fwd(y[0], _f32(wd1), _f32(bd1), _f32(wd2), _f32(bd2), drop=hdrop)
     cls = y[0].float()
     if save:
-        saved.update(y_last=y, zc=zc)
+        saved.update(y_last=y, zc=zc, head_drop=hdrop)
         return logits, cls, saved
     return logits, cls
 
@@ -126,10 +159,12 @@ def classifier_forward(x, num_heads, num_layers, params, save=False):
 FUSED_ATTENTION_BACKWARD = True
 
 
-def attention_backward(qkv, a, da, lse, heads):
-    """dqkv (N, 3d) bf16 from da (N, d)."""
+def attention_backward(qkv, a, da, lse, heads, drop=None):
+    """dqkv (N, 3d) bf16 from da (N, d); ``drop`` = the forward's attention-dropout site (its mask is regenerated)."""
     if FUSED_ATTENTION_BACKWARD:
-        return ops.flash_attn_bwd(qkv, a, da.contiguous(), lse, 1, qkv.shape[0], heads)
+        return ops.flash_attn_bwd(qkv, a, da.contiguous(), lse, 1, qkv.shape[0], heads, drop=drop)
+    if drop is not None:
+        raise NotImplementedError("attention dropout needs the fused backward (FUSED_ATTENTION_BACKWARD)")
     return attention_backward_materialised(qkv, a, da, lse, heads)
 
 
@@ -169,24 +204,28 @@ def encoder_backward(num_heads, num_layers, enc_params, saved, dy):
         g[i] = torch.zeros(enc_params[i].shape, dtype=torch.float32, device=dev)
         return g[i]
 
+    drop = saved.get("drop")
+    dsite = (lambda l, k: drop.site(l, k)) if drop is not None else (lambda l, k: None)
     for l in reversed(range(num_layers)):
         base = 3 + 12 * l
         (w_in, b_in, w_o, b_o, n1w, n1b, w1, b1, w2, b2, n2w, n2b) = enc_params[base:base + 12]
         s = saved["layers"][l]
         du = ops.layernorm_bwd(dy, s["u"], _f32(n2w), s["mu2"], s["rs2"], zeros_like_param(base + 10), zeros_like_param(base + 11))
-        ops.colsum_accum(du, zeros_like_param(base + 9))
-        du_t = ops.transpose(du)
-        g[base + 8] = ops.gemm(du_t, ops.transpose(s["h"]), out_dtype=torch.float32)          # dW2 = du^T h
-        dh = ops.gemm(du, _bf16_t(w2))                                                         # dh = du W2
-        dz = ops.gelu_bwd(dh, s["z"])
+        # u = y1 + dropout2(h W2^T + b2): the branch sees the masked gradient, the residual path the plain one
+        g2 = ops.dropout_apply(du, dsite(l, 3)) if dsite(l, 3) is not None else du
+        ops.colsum_accum(g2, zeros_like_param(base + 9))
+        g[base + 8] = ops.gemm(ops.transpose(g2), ops.transpose(s["h"]), out_dtype=torch.float32)    # dW2 = g2^T h  (h = dropped activation)
+        dh = ops.gemm(g2, _bf16_t(w2))                                                         # dh = g2 W2
+        dz = ops.gelu_bwd(dh, s["z"], drop=dsite(l, 2))
         ops.colsum_accum(dz, zeros_like_param(base + 7))
         g[base + 6] = ops.gemm(ops.transpose(dz), ops.transpose(s["y1"]), out_dtype=torch.float32)   # dW1 = dz^T y1
         dy1 = ops.gemm(dz, _bf16_t(w1), epilogue="residual", residual=du)                      # + residual branch
         dt = ops.layernorm_bwd(dy1, s["t"], _f32(n1w), s["mu1"], s["rs1"], zeros_like_param(base + 4), zeros_like_param(base + 5))
-        ops.colsum_accum(dt, zeros_like_param(base + 3))
-        g[base + 2] = ops.gemm(ops.transpose(dt), ops.transpose(s["a"]), out_dtype=torch.float32)    # dWo = dt^T a
-        da = ops.gemm(dt, _bf16_t(w_o))
-        dqkv = attention_backward(s["qkv"], s["a"], da, s["lse"], num_heads)
+        g1 = ops.dropout_apply(dt, dsite(l, 1)) if dsite(l, 1) is not None else dt             # t = y + dropout1(a Wo^T + bo)
+        ops.colsum_accum(g1, zeros_like_param(base + 3))
+        g[base + 2] = ops.gemm(ops.transpose(g1), ops.transpose(s["a"]), out_dtype=torch.float32)    # dWo = g1^T a
+        da = ops.gemm(g1, _bf16_t(w_o))
+        dqkv = attention_backward(s["qkv"], s["a"], da, s["lse"], num_heads, drop=dsite(l, 0))
         ops.colsum_accum(dqkv, zeros_like_param(base + 1))
         g[base] = ops.gemm(ops.transpose(dqkv), ops.transpose(s["y_in"]), out_dtype=torch.float32)   # dWin = dqkv^T y
         dy = ops.gemm(dqkv, _bf16_t(w_in), epilogue="residual", residual=dt)
@@ -200,14 +239,14 @@ def encoder_backward(num_heads, num_layers, enc_params, saved, dy):
     return g
 
 
-def head_backward(y_cls_bf16, head_params, zc, d_logits, d_cls_in):
-    """MLPLayer head backward: returns (grads of [W1, b1, W2, b2], d(input vector) f32)."""
+def head_backward(y_cls_bf16, head_params, zc, d_logits, d_cls_in, drop=None):
+    """MLPLayer head backward: returns (grads of [W1, b1, W2, b2], d(input vector) f32).  ``drop`` = the forward's dropout site."""
     wd1, bd1, wd2, bd2 = head_params
     dev = wd1.device
     gs = [torch.zeros(p.shape, dtype=torch.float32, device=dev) for p in head_params]
     dlog = d_logits.detach().float().contiguous() if d_logits is not None else torch.zeros(wd2.shape[0], device=dev)
     dcls_in = d_cls_in.detach().float().contiguous() if d_cls_in is not None else None
-    dvec = ops.cls_head_bwd(y_cls_bf16, _f32(wd1), _f32(wd2), zc, dlog, dcls_in, gs[0], gs[1], gs[2], gs[3])
+    dvec = ops.cls_head_bwd(y_cls_bf16, _f32(wd1), _f32(wd2), zc, dlog, dcls_in, gs[0], gs[1], gs[2], gs[3], drop=drop)
     return gs, dvec
 
 
@@ -216,7 +255,7 @@ def classifier_backward(num_heads, num_layers, params, saved, d_logits, d_cls):
     dev = params[0].device
     n, d = saved["x"].shape
     y_last = saved["y_last"]
-    g_head, dcls = head_backward(y_last[0], params[-4:], saved["zc"], d_logits, d_cls)
+    g_head, dcls = head_backward(y_last[0], params[-4:], saved["zc"], d_logits, d_cls, drop=saved.get("head_drop"))
     dy = torch.zeros((n + 1, d), dtype=torch.bfloat16, device=dev)          # only the CLS row carries gradient
     dy[0] = dcls.to(torch.bfloat16)
     return encoder_backward(num_heads, num_layers, params[:-4], saved, dy) + g_head
@@ -226,8 +265,8 @@ class ClassifierFunction(torch.autograd.Function):
     """logits, cls = f(x, params...) with a hand-written backward over libvdr kernels."""
 
     @staticmethod
-    def forward(ctx, x, num_heads, num_layers, *params):
-        logits, cls, saved = classifier_forward(x, num_heads, num_layers, params, save=True)
+    def forward(ctx, x, num_heads, num_layers, drop, *params):
+        logits, cls, saved = classifier_forward(x, num_heads, num_layers, params, save=True, drop=drop)
         ctx.saved = saved
         ctx.params = params
         ctx.num_heads, ctx.num_layers = num_heads, num_layers
@@ -237,4 +276,4 @@ class ClassifierFunction(torch.autograd.Function):
     def backward(ctx, d_logits, d_cls):
         grads = classifier_backward(ctx.num_heads, ctx.num_layers, ctx.params, ctx.saved, d_logits, d_cls)
         ctx.saved = None
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)

@@ -61,6 +61,7 @@ struct AttnParams {
   int64_t ld_out;
   int B, N, heads, d;
   float scale_log2;
+  int no_key_fold;             // 1: a ragged last key block always runs as a narrow MMA block (never folded in the epilogue)
   int dbg;                     // timing experiments only (VDR_ATTN_DBG): 1 = tail CTAs exit at once, 2 = skip the trailing-key fold
   int q_tiles, tail_rows;      // full 128-row query tiles (tensor cores) / trailing rows handled by the extra CUDA-core CTA
   unsigned long long* trace;   // debug (VDR_ATTN_TRACE builds only): per-iteration timestamps of CTA (0,0,0)
@@ -68,6 +69,7 @@ struct AttnParams {
   // rel[(b*heads + head)*N + q][kh] + rel[...][Sh + kw] for key (kh, kw), already multiplied by log2(e)  (vdr_relpos_tables)
   const float* rel;
   int rel_pitch;               // Sh + 64
+  DropSpec drop;               // kDrop instantiation only: attention dropout (thr16 == 0: off)
 };
 constexpr int kBiasPitch = 136;                          // bytes per query row of the rel_w terms in shared memory: 64 halfs + 8 pad
 constexpr int kAttnSmemBias = kAttnSmem + 128 * kBiasPitch;
@@ -254,7 +256,7 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
 // few units -> 1e-3 absolute in the exponent, below the bf16 rounding of P).
 __device__ unsigned int g_attn_sm_ticket[1024];   // experiment (VDR_ATTN_DBG >= 100): alternate start delay per SM slot
 
-template <bool kBias>
+template <bool kBias, bool kDrop = false>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -294,7 +296,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   // + CLS), is folded into the epilogue on the CUDA cores instead of costing every CTA one more pipeline round trip.
   const int nkv_all = (p.N + kBKV - 1) / kBKV;
   const int last_keys = p.N - (nkv_all - 1) * kBKV;              // keys in the last block (1..128)
-  const int tail_keys = (last_keys <= 8 && nkv_all > 1) ? last_keys : 0;
+  const int tail_keys = (last_keys <= 8 && nkv_all > 1 && !p.no_key_fold) ? last_keys : 0;
   const int nkv = tail_keys ? nkv_all - 1 : nkv_all;             // blocks that go through the MMA pipeline
   const int valid_last = tail_keys ? kBKV : last_keys;           // keys in the last MMA block
   const int ntail = (valid_last + 15) & ~15;                     // ... rounded to the MMA's 16-column granularity
@@ -514,12 +516,26 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
           uint32_t r[16], w[8];
           tmem_ld_32x32b_x16(tmem_S + lane_sel + c, r);
           tmem_ld_wait();
+          uint4 db[2];
+          if (kDrop) {
+            const uint64_t drow = (static_cast<uint64_t>(b) * p.heads + head) * p.N + q0 + row;
+            const uint32_t c8 = static_cast<uint32_t>((j * kBKV + c) >> 3);
+            db[0] = drop_bits8(p.drop, drow, c8);
+            db[1] = drop_bits8(p.drop, drow, c8 + 1);
+          }
+          const float dsc = kDrop ? drop_scale(p.drop) : 1.f;
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             const float p0 = (c + i < valid_last) ? ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_ref)) : 0.f;
             const float p1 = (c + i + 1 < valid_last) ? ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_ref)) : 0.f;
-            lsum += p0 + p1;
-            w[i >> 1] = cvt_bf16x2(p0, p1);
+            lsum += p0 + p1;                                  // the normaliser keeps every key: dropout follows the softmax
+            if (kDrop) {
+              const float k0 = drop_lane16(db[i >> 3], i & 7) >= p.drop.thr16 ? dsc : 0.f;
+              const float k1 = drop_lane16(db[i >> 3], (i & 7) + 1) >= p.drop.thr16 ? dsc : 0.f;
+              w[i >> 1] = cvt_bf16x2(p0 * k0, p1 * k1);
+            } else {
+              w[i >> 1] = cvt_bf16x2(p0, p1);
+            }
           }
           tmem_st_32x32b_x8(tmem_P + lane_sel + (c >> 1), w);
         }
@@ -590,6 +606,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         const uint64_t negm2 = pack2(-m_ref, -m_ref);
         uint64_t lsum2 = 0ull;
         uint32_t pk[32];
+        uint4 dbits = make_uint4(0, 0, 0, 0);
+        const uint64_t drop_row = (static_cast<uint64_t>(b) * p.heads + head) * p.N + q0 + row;
+        const float dsc = kDrop ? drop_scale(p.drop) : 1.f;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -605,8 +624,16 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
               p0 = ex2(x0);
               p1 = ex2(x1);
             }
-            lsum2 = add2(lsum2, pack2(p0, p1));
-            pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
+            lsum2 = add2(lsum2, pack2(p0, p1));                  // the normaliser keeps every key: dropout follows the softmax
+            if (kDrop) {
+              if ((i & 7) == 0)                                  // eight consecutive key columns per Philox call
+                dbits = drop_bits8(p.drop, drop_row, static_cast<uint32_t>((j * kBKV + half * 64 + c * 32 + i) >> 3));
+              const float k0 = drop_lane16(dbits, i & 7) >= p.drop.thr16 ? dsc : 0.f;
+              const float k1 = drop_lane16(dbits, (i & 7) + 1) >= p.drop.thr16 ? dsc : 0.f;
+              pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0 * k0, p1 * k1);
+            } else {
+              pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
+            }
           }
         }
         float l0, l1;
@@ -1017,7 +1044,7 @@ static unsigned long long* g_attn_trace = nullptr;
 extern "C" void vdr_debug_set_attn_trace(void* device_buf) { g_attn_trace = static_cast<unsigned long long*>(device_buf); }
 
 static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, const float* rel, int rel_pitch, void* out, int64_t ld_out,
-                             float* lse, int B, int N, int heads, float scale, vdr_stream_t stream) {
+                             float* lse, int B, int N, int heads, float scale, const vdr_dropout* drop, vdr_stream_t stream) {
   using namespace vdr;
   VDR_CHECK_ARG(qkv && out, VDR_EINVAL, "%s: null pointer", who);
   VDR_CHECK_ARG(B > 0 && N > 0 && heads > 0, VDR_EINVAL, "%s: bad shape B=%d N=%d heads=%d", who, B, N, heads);
@@ -1028,7 +1055,9 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   // v6 (four light CTAs per SM) is faster than v5 when timed alone (N = 1024: 0.596 vs 0.627 ms) but slower inside the
   // power-capped extraction step (0.904 vs 0.875 ms per layer at N = 1025): v5 stays the default, VDR_ATTN_V6=1 selects v6 for A/B runs
   static const bool want_v6 = getenv("VDR_ATTN_V6") != nullptr;
-  const bool v6 = rel == nullptr && want_v6;
+  const bool dropout = drop != nullptr && drop->thr16 != 0;
+  VDR_CHECK_ARG(!dropout || (rel == nullptr && drop->thr16 < 65536u), VDR_EINVAL, "%s: attention dropout needs thr16 < 65536 and no rel-pos bias", who);
+  const bool v6 = rel == nullptr && want_v6 && !dropout;
   CUtensorMap tm;
   int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * d, (uint64_t)ld_qkv, v6 ? kV6BK : 128, kHD);
   if (rc != VDR_OK) return rc;
@@ -1037,6 +1066,7 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
     cudaError_t e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV6Smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_fwd)");
     configured.current() = true;
   }
@@ -1052,19 +1082,25 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   p.dbg = getenv("VDR_ATTN_DBG") ? atoi(getenv("VDR_ATTN_DBG")) : 0;
   p.rel = rel;
   p.rel_pitch = rel_pitch;
+  p.drop = DropSpec{0ull, 0u, 0u};
+  if (dropout) p.drop = DropSpec{drop->seed, drop->site, drop->thr16};
   // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head)
   // v5: full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head).
   // v6: its CTAs are a quarter of an SM, so a trailing tile with a single valid row costs less than the CUDA-core CTA did
   // (measured alone, N = 1025: 0.723 ms with the v5 CUDA-core routine on 160 threads, 0.711 as a tile; a one-warp-per-row
   // routine with exact two-pass softmax was tried and was far slower, 0.862 ms): every tile goes through the tensor-core path.
   const int tail_rows = N % kBQ;
-  const bool vector_tail = !v6 && tail_rows > 0 && tail_rows <= 8;
+  // (with dropout every row and key goes through the two tensor-core softmax paths, the only ones that apply the mask)
+  const bool vector_tail = !v6 && !dropout && tail_rows > 0 && tail_rows <= 8;
+  p.no_key_fold = dropout ? 1 : 0;
   p.q_tiles = vector_tail ? N / kBQ : (N + kBQ - 1) / kBQ;
   p.tail_rows = vector_tail ? tail_rows : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.q_tiles + (vector_tail ? 1 : 0), heads, B);
   if (rel != nullptr)
     flash_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, p);
+  else if (dropout)
+    flash_attn_fwd_kernel<false, true><<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
   else if (v6)
     flash_attn_fwd_v6_kernel<<<grid, kV6Threads, kV6Smem, s>>>(tm, p);
   else
@@ -1075,8 +1111,8 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
 }
 
 extern "C" int vdr_flash_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B,
-                                  int N, int heads, float scale, vdr_stream_t stream) {
-  return launch_flash_attn("vdr_flash_attn_fwd", qkv, ld_qkv, nullptr, 0, out, ld_out, lse, B, N, heads, scale, stream);
+                                  int N, int heads, float scale, const vdr_dropout* drop, vdr_stream_t stream) {
+  return launch_flash_attn("vdr_flash_attn_fwd", qkv, ld_qkv, nullptr, 0, out, ld_out, lse, B, N, heads, scale, drop, stream);
 }
 
 extern "C" int vdr_flash_attn_relpos_fwd(const void* qkv, int64_t ld_qkv, const float* rel_log2, void* out, int64_t ld_out, int B, int Sh,
@@ -1084,5 +1120,5 @@ extern "C" int vdr_flash_attn_relpos_fwd(const void* qkv, int64_t ld_qkv, const 
   using namespace vdr;
   VDR_CHECK_ARG(rel_log2 != nullptr && aligned16(rel_log2), VDR_EINVAL, "vdr_flash_attn_relpos_fwd: rel table must be a 16-byte aligned device pointer");
   VDR_CHECK_ARG(Sh > 0 && Sh % 4 == 0 && Sh <= 1020, VDR_EINVAL, "vdr_flash_attn_relpos_fwd: the token grid must be Sh x 64 with Sh a multiple of 4 (Sh = %d)", Sh);
-  return launch_flash_attn("vdr_flash_attn_relpos_fwd", qkv, ld_qkv, rel_log2, Sh + 64, out, ld_out, nullptr, B, Sh * 64, heads, scale, stream);
+  return launch_flash_attn("vdr_flash_attn_relpos_fwd", qkv, ld_qkv, rel_log2, Sh + 64, out, ld_out, nullptr, B, Sh * 64, heads, scale, nullptr, stream);
 }

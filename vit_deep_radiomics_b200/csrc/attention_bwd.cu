@@ -28,6 +28,7 @@ struct AttnBwdParams {
   int64_t ld_dqkv;
   int B, N, heads, d;
   float scale, scale_log2;
+  DropSpec drop;         // attention dropout of the forward (thr16 == 0: none); the mask is regenerated here
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -95,7 +96,9 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
   if (warp == 4) {
-    if (lane == 0) {
+    // the whole warp runs the loop and waits; TMA / tcgen05 instructions under elect.sync (one lane, operands straight to uniform
+    // registers: under `lane == 0` each of the 32 MMAs of a block was wrapped in an ELECT / BRA.U.ANY waterfall)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // S, dP: A, B K-major
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 1, 1);      // dV, dK: A MN-major (P^T / dS^T), B MN-major (dO / Q)
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);      // dQ: A = dS K-major, B = K_j MN-major
@@ -105,7 +108,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         mbar_wait(&bar_ld[buf], (i >> 1) & 1);
         if (i > 0) mbar_wait(bar_free, (i - 1) & 1);       // block i - 1 is done: S / dP columns, P / dS tiles, its Q / dO buffer are free
         tc_fence_after();
-        if (i + 1 < nq) {   // prefetch the next query block into the buffer block i - 1 used
+        if (i + 1 < nq && elect_one()) {   // prefetch the next query block into the buffer block i - 1 used
           mbar_arrive_expect_tx(&bar_ld[buf ^ 1], 2 * kTile);
           tma_load_2d(&tmQKV, &bar_ld[buf ^ 1], smem + (2 + (buf ^ 1)) * kTile, colQ, row_base + (i + 1) * kBT);
           tma_load_2d(&tmDO, &bar_ld[buf ^ 1], smem + (4 + (buf ^ 1)) * kTile, head * kBD, row_base + (i + 1) * kBT);
@@ -113,27 +116,34 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const uint32_t q_t = sQ + buf * kTile, do_t = sDO + buf * kTile;
         const uint64_t dq = umma_desc_kmajor_sw128(q_t), dk = umma_desc_kmajor_sw128(sK);
         const uint64_t ddo = umma_desc_kmajor_sw128(do_t), dv = umma_desc_kmajor_sw128(sV);
+        __syncwarp();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBD / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < kBD / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < kBD / 16; ++k) umma_ss(tDP, ddo + 2 * k, dv + 2 * k, idesc_s, k != 0);
-        umma_commit(bar_sdp);
+          for (int k = 0; k < kBD / 16; ++k) umma_ss(tDP, ddo + 2 * k, dv + 2 * k, idesc_s, k != 0);
+          umma_commit(bar_sdp);
+        }
+        __syncwarp();
         mbar_wait(bar_pds, i & 1);
         tc_fence_after();
         // K dimension = the 128 query rows of the block: 8 steps of 16 rows (2048 B = 128 address units per step in every tile)
         const uint64_t a_p = umma_desc_mn_sw128(sP, kTile), a_ds = umma_desc_mn_sw128(sDS, kTile);
         const uint64_t b_do = umma_desc_mn_sw128(do_t, kTile), b_q = umma_desc_mn_sw128(q_t, kTile);
-#pragma unroll
-        for (int k = 0; k < kBT / 16; ++k) umma_ss(tDV, a_p + 128 * k, b_do + 128 * k, idesc_g, (i | k) != 0);
-#pragma unroll
-        for (int k = 0; k < kBT / 16; ++k) umma_ss(tDK, a_ds + 128 * k, b_q + 128 * k, idesc_g, (i | k) != 0);
         // dQ_i = dS K_j: K dimension = the 128 keys: dS K-major as two [128][64] sub-tiles, K_j MN-major (16 key rows per step)
         const uint64_t a_dsk0 = umma_desc_kmajor_sw128(sDS), a_dsk1 = umma_desc_kmajor_sw128(sDS + kTile);
         const uint64_t b_k = umma_desc_mn_sw128(sK, kTile);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBT / 16; ++k)
-          umma_ss(tDQ, (k < 4 ? a_dsk0 + 2 * k : a_dsk1 + 2 * (k - 4)), b_k + 128 * k, idesc_q, k != 0);
-        umma_commit(bar_grad);
+          for (int k = 0; k < kBT / 16; ++k) umma_ss(tDV, a_p + 128 * k, b_do + 128 * k, idesc_g, (i | k) != 0);
+#pragma unroll
+          for (int k = 0; k < kBT / 16; ++k) umma_ss(tDK, a_ds + 128 * k, b_q + 128 * k, idesc_g, (i | k) != 0);
+#pragma unroll
+          for (int k = 0; k < kBT / 16; ++k)
+            umma_ss(tDQ, (k < 4 ? a_dsk0 + 2 * k : a_dsk1 + 2 * (k - 4)), b_k + 128 * k, idesc_q, k != 0);
+          umma_commit(bar_grad);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -154,13 +164,25 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tmem_ld_32x32b_x32(tDP + lane_sel + c * 32, dp);
         tmem_ld_wait();
         uint32_t pw[16], dw[16];
+        // forward: O = (P (.) M) V with M = mask / (1 - p)  =>  dV = (P (.) M)^T dO,  dP = M (.) (dO V^T),  dS = P (.) (dP - delta) * scale
+        // (delta = rowsum(dO (.) O) already contains the mask)
+        const bool dropping = p.drop.thr16 != 0;
+        const uint64_t drow = (static_cast<uint64_t>(b) * p.heads + head) * p.N + q;
+        const float dsc = dropping ? drop_scale(p.drop) : 1.f;
+        uint4 dbits = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const bool ok0 = q_ok && (kv0 + c * 32 + e) < p.N, ok1 = q_ok && (kv0 + c * 32 + e + 1) < p.N;
           const float p0 = ok0 ? ex2f(fmaf(__uint_as_float(s[e]), p.scale_log2, nlse)) : 0.f;
           const float p1 = ok1 ? ex2f(fmaf(__uint_as_float(s[e + 1]), p.scale_log2, nlse)) : 0.f;
-          const float d0 = p0 * (__uint_as_float(dp[e]) - dlt) * p.scale, d1 = p1 * (__uint_as_float(dp[e + 1]) - dlt) * p.scale;
-          pw[e >> 1] = pack_bf16x2(p0, p1);
+          float k0 = 1.f, k1 = 1.f;
+          if (dropping) {
+            if ((e & 7) == 0) dbits = drop_bits8(p.drop, drow, static_cast<uint32_t>((kv0 + c * 32 + e) >> 3));
+            k0 = drop_lane16(dbits, e & 7) >= p.drop.thr16 ? dsc : 0.f;
+            k1 = drop_lane16(dbits, (e & 7) + 1) >= p.drop.thr16 ? dsc : 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dp[e]) * k0 - dlt) * p.scale, d1 = p1 * (__uint_as_float(dp[e + 1]) * k1 - dlt) * p.scale;
+          pw[e >> 1] = pack_bf16x2(p0 * k0, p1 * k1);
           dw[e >> 1] = pack_bf16x2(d0, d1);
         }
         // row tid of sub-tile (c >> 1), 16-byte chunks (c & 1) * 4 .. + 3, SWIZZLE_128B
@@ -250,7 +272,7 @@ extern "C" size_t vdr_flash_attn_bwd_workspace_bytes(int B, int N, int heads) {
 }
 
 extern "C" int vdr_flash_attn_bwd(const void* qkv, int64_t ld_qkv, const void* O, const void* dO, int64_t ld_o, const float* lse,
-                                  void* dqkv, int64_t ld_dqkv, int B, int N, int heads, float scale, void* workspace,
+                                  void* dqkv, int64_t ld_dqkv, int B, int N, int heads, float scale, const vdr_dropout* drop, void* workspace,
                                   size_t workspace_bytes, vdr_stream_t stream) {
   using namespace vdr;
   VDR_CHECK_ARG(qkv && O && dO && lse && dqkv && workspace, VDR_EINVAL, "vdr_flash_attn_bwd: null pointer");
@@ -284,6 +306,11 @@ extern "C" int vdr_flash_attn_bwd(const void* qkv, int64_t ld_qkv, const void* O
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld_dqkv = ld_dqkv;
   p.B = B; p.N = N; p.heads = heads; p.d = d;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.drop = DropSpec{0ull, 0u, 0u};
+  if (drop != nullptr && drop->thr16 != 0) {
+    VDR_CHECK_ARG(drop->thr16 < 65536u, VDR_EINVAL, "vdr_flash_attn_bwd: dropout threshold must be < 65536");
+    p.drop = DropSpec{drop->seed, drop->site, drop->thr16};
+  }
   dim3 grid((N + kBT - 1) / kBT, heads, B);
   flash_attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, s>>>(tmQKV, tmDO, p);
   count_launch();

@@ -512,6 +512,43 @@ __device__ __forceinline__ void gelu_sig2_x16(uint64_t (&x2)[16]) {
   }
 }
 
+// ---- dropout (train mode of the point-cloud classifier: nn.TransformerEncoderLayer(dropout=p), MLPLayer, models_archs.py:51,58,135,187-199)
+// Counter-based, so the backward kernels REGENERATE the masks instead of storing them.  Element (row r, column c) of dropout site
+// `site` is kept iff the 16-bit lane (c & 7) of Philox4x32-10(counter = (c >> 3, r_lo, r_hi, site), key = seed) is >= thr16;
+// kept values are multiplied by 65536 / (65536 - thr16), i.e. p = thr16 / 65536 (0.1 -> 6554, 0.5 -> 32768).  thr16 == 0 = no dropout.
+struct DropSpec {
+  unsigned long long seed;
+  uint32_t site;
+  uint32_t thr16;
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// the eight 16-bit lanes of columns [c8 * 8, c8 * 8 + 8) of row `row`
+__device__ __forceinline__ uint4 drop_bits8(const DropSpec& d, uint64_t row, uint32_t c8) {
+  return philox4x32_10(make_uint4(c8, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), d.site),
+                       make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
+}
+__device__ __forceinline__ uint32_t drop_lane16(const uint4& bits, int lane8) {
+  const uint32_t w = lane8 < 2 ? bits.x : lane8 < 4 ? bits.y : lane8 < 6 ? bits.z : bits.w;
+  return (lane8 & 1) ? (w >> 16) : (w & 0xffffu);
+}
+__device__ __forceinline__ float drop_scale(const DropSpec& d) { return 65536.f / static_cast<float>(65536u - d.thr16); }
+// multiplier (0 or scale) of a single element; for vectors and other low-rate sites
+__device__ __forceinline__ float drop_factor(const DropSpec& d, uint64_t row, uint32_t col) {
+  if (d.thr16 == 0) return 1.f;
+  const uint4 bits = drop_bits8(d, row, col >> 3);
+  return drop_lane16(bits, static_cast<int>(col & 7)) >= d.thr16 ? drop_scale(d) : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

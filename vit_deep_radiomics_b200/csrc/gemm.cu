@@ -59,6 +59,7 @@ struct GemmParams {
   int64_t out_rows;            // rows of the output matrix (TMA clipping bound)
   unsigned long long* trace;   // debug: per-tile timestamps of CTA 0 (nullptr = off)
   int dbg;                     // debug: 1 = skip MMAs, 2 = skip TMA loads (timing experiments only; results are garbage)
+  DropSpec drop;               // generic instantiations, residual epilogue: C = R + dropout(A W^T + bias)  (thr16 == 0: off)
 };
 
 // kCtas = 2: a CTA pair (cluster of two SMs, cta_group::2) computes a 256 x BN tile: each CTA stages its own 128 rows
@@ -355,7 +356,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                        ? *reinterpret_cast<const uint4*>(Rb + res_row_c[i] * p.ldr + n + cchk * 8) : make_uint4(0, 0, 0, 0);
       };
       auto tma_res_load = [&](int c) {                // 32 rows x 32 columns of R -> rbuf (rows / columns past the edge arrive as zeros)
-        if (lane == 0) {
+        if (elect_one()) {        // = lane 0 of the converged warp; elect.sync lets the TMA operands go straight to uniform registers
           mbar_arrive_expect_tx(&res_bar[ew], 2048);
           tma_load_2d_addr(&tmR, &res_bar[ew], rbuf, nw0 + c, static_cast<int>(res_row_w));
         }
@@ -458,6 +459,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             gelu_sig2_x16(v2);
 #endif
           } else if (epi_sel == VDR_EPI_BIAS_RESIDUAL) {
+            if (kFold < 0 && p.drop.thr16 != 0) {
+              // dropout1 / dropout2 of nn.TransformerEncoderLayer: the sub-layer output is dropped before the residual add.
+              // This thread holds columns n0 .. n0 + 31 of output row m: four Philox calls of eight 16-bit lanes each.
+              const float dsc = drop_scale(p.drop);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 bits = drop_bits8(p.drop, static_cast<uint64_t>(m), static_cast<uint32_t>((n0 >> 3) + g));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float k0 = drop_lane16(bits, 2 * k) >= p.drop.thr16 ? dsc : 0.f;
+                  const float k1 = drop_lane16(bits, 2 * k + 1) >= p.drop.thr16 ? dsc : 0.f;
+                  v2[g * 4 + k] = mul2(v2[g * 4 + k], pack2(k0, k1));
+                }
+              }
+            }
             if (res_bf16) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -515,7 +531,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw(lane, g)), "r"(o[g].x), "r"(o[g].y), "r"(o[g].z), "r"(o[g].w) : "memory");
             fence_proxy_async_smem();                  // generic-proxy writes -> visible to the TMA (async proxy)
             __syncwarp();
-            if (lane == 0 && warp_ok) {
+            if (warp_ok && elect_one()) {   // the elected lane is lane 0, the thread whose bulk groups tma_store_wait_read tracks
               tma_store_2d(&tmC, stg, n0, static_cast<int>(out_row_w));   // rows >= out_rows and columns >= N are clipped
               tma_store_commit();
             }
@@ -617,7 +633,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUt
                        cudaStream_t stream) {
   if constexpr (BN == 256 && kCtas == 2) {   // the hot configuration: one instantiation per epilogue / folded-LayerNorm role
     const int fold = (p.ln_stats != nullptr ? 1 : 0) | (p.stats_out != nullptr ? 2 : 0);
-    const bool spec = p.tma_out >= 1 && p.c_dtype == VDR_DTYPE_BF16 && p.N % BN == 0 && p.trace == nullptr;
+    const bool spec = p.tma_out >= 1 && p.c_dtype == VDR_DTYPE_BF16 && p.N % BN == 0 && p.trace == nullptr && p.drop.thr16 == 0;
     if (p.tma_out >= 2) {   // bf16 residual through TMA
       if (spec && fold == 0) return launch_gemm_<BN, kCtas, true, (VDR_EPI_BIAS_RESIDUAL << 2) | 0>(tmA, tmW, tmC, tmR, p, grid, stream);
       if (spec && fold == 2) return launch_gemm_<BN, kCtas, true, (VDR_EPI_BIAS_RESIDUAL << 2) | 2>(tmA, tmW, tmC, tmR, p, grid, stream);
@@ -676,6 +692,11 @@ static int gemm_impl(const vdr_gemm_args* a, const Im2colSpec* ic, vdr_stream_t 
     VDR_CHECK_ARG((reinterpret_cast<uintptr_t>(a->stats_out) & 7) == 0, VDR_EALIGN, "vdr_gemm: stats_out must be 8-byte aligned");
   }
 
+  if (a->drop.thr16 != 0) {
+    VDR_CHECK_ARG(a->drop.thr16 < 65536u && a->epilogue == VDR_EPI_BIAS_RESIDUAL && a->c_dtype == VDR_DTYPE_BF16 && a->N % 32 == 0 && a->out_group == 0 &&
+                  a->ln_stats == nullptr && a->stats_out == nullptr && !ic, VDR_EINVAL,
+                  "vdr_gemm: dropout needs thr16 < 65536, the residual epilogue, a bf16 C, N %% 32 == 0 (N = %d), no row remapping and no folded LayerNorm", a->N);
+  }
   const int sms = num_sms();
   const int m_tiles = (a->M + BM - 1) / BM;
   auto tiles = [&](int bn) { return m_tiles * ((a->N + bn - 1) / bn); };
@@ -714,6 +735,7 @@ static int gemm_impl(const vdr_gemm_args* a, const Im2colSpec* ic, vdr_stream_t 
   p.stats_out = reinterpret_cast<float2*>(a->stats_out);
   p.trace = g_trace;
   p.dbg = getenv("VDR_GEMM_DBG") ? atoi(getenv("VDR_GEMM_DBG")) : 0;
+  p.drop = DropSpec{a->drop.seed, a->drop.site, a->drop.thr16};
   p.a_im2col = ic ? 1 : 0;
   p.ic_patch = p.ic_gw = p.ic_np = p.ic_chan = p.ic_kb_per_chan = 1;
   if (ic) {

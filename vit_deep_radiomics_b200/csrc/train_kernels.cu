@@ -11,30 +11,79 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ h, int64_t n8) {
+// eight consecutive columns (one 16-byte vector) of dropout site `d`: multipliers 0 / scale (all 1 when thr16 == 0).
+// i = index of the 8-column vector in a contiguous (rows, cols) matrix with cols % 8 == 0
+__device__ __forceinline__ void drop8(const DropSpec& d, int64_t i, int cols8, float (&f)[8]) {
+  if (d.thr16 == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 1.f;
+    return;
+  }
+  const uint4 bits = drop_bits8(d, static_cast<uint64_t>(i / cols8), static_cast<uint32_t>(i % cols8));
+  const float sc = drop_scale(d);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = drop_lane16(bits, k) >= d.thr16 ? sc : 0.f;
+}
+
+// h = dropout(gelu(z)): the feed-forward block's inner dropout (nn.TransformerEncoderLayer._ff_block) fused into the activation
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ h, int64_t n8,
+                                                       int cols8, DropSpec drop) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 v = reinterpret_cast<const uint4*>(z)[i];
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float m[8];
+    drop8(drop, i, cols8, m);
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = unpack_bf16x2(w[k]);
-      o[k] = pack_bf16x2(gelu_erf(f.x), gelu_erf(f.y));
+      o[k] = pack_bf16x2(gelu_erf(f.x) * m[2 * k], gelu_erf(f.y) * m[2 * k + 1]);
     }
     reinterpret_cast<uint4*>(h)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
+// out = x * mask / (1 - p) (bf16 matrix, contiguous columns, row pitches ld): the backward of a dropout that the forward applied
+// inside a GEMM epilogue (sub-layer outputs before the residual add)
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
+                                                            int64_t ldo, int64_t rows, int cols8, DropSpec drop) {
+  const int64_t n8 = rows * cols8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols8;
+    const int c8 = static_cast<int>(i % cols8);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + r * ldx + c8 * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float m[8];
+    drop8(drop, i, cols8, m);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      o[k] = pack_bf16x2(f.x * m[2 * k], f.y * m[2 * k + 1]);
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// the mask itself (1 = kept), for tests and for reference computations that must use the device's masks
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ out, int64_t rows, int64_t cols, DropSpec drop) {
+  const int64_t n = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = drop_factor(drop, static_cast<uint64_t>(i / cols), static_cast<uint32_t>(i % cols)) != 0.f;
+}
+
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ z,
-                                                       __nv_bfloat16* __restrict__ dz, int64_t n8) {
+                                                       __nv_bfloat16* __restrict__ dz, int64_t n8, int cols8, DropSpec drop) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 a = reinterpret_cast<const uint4*>(dh)[i], b = reinterpret_cast<const uint4*>(z)[i];
     const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+    float m[8];
+    drop8(drop, i, cols8, m);                       // the mask of the forward, regenerated
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 g = unpack_bf16x2(wa[k]), x = unpack_bf16x2(wb[k]);
-      o[k] = pack_bf16x2(g.x * gelu_grad(x.x), g.y * gelu_grad(x.y));
+      o[k] = pack_bf16x2(g.x * m[2 * k] * gelu_grad(x.x), g.y * m[2 * k + 1] * gelu_grad(x.y));
     }
     reinterpret_cast<uint4*>(dz)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -172,41 +221,44 @@ cls_head_hidden_kernel(const __nv_bfloat16* __restrict__ cls, const float* __res
 
 __global__ void __launch_bounds__(256)
 cls_head_out_kernel(const float* __restrict__ zc, const float* __restrict__ W2, const float* __restrict__ b2,
-                    float* __restrict__ logits, int H1, int C) {
+                    float* __restrict__ logits, int H1, int C, DropSpec drop) {
+  // MLPLayer (:193-199): dense1 -> GELU -> dropout -> dense2 -> dropout (the second one on the outputs themselves);
+  // hidden mask = row 0 of the site, output mask = row 1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int k = warp; k < C; k += nw) {
     float acc = 0.f;
-    for (int j = lane; j < H1; j += 32) acc = fmaf(W2[static_cast<int64_t>(k) * H1 + j], gelu_erf(zc[j]), acc);
+    for (int j = lane; j < H1; j += 32) acc = fmaf(W2[static_cast<int64_t>(k) * H1 + j], gelu_erf(zc[j]) * drop_factor(drop, 0, j), acc);
     acc = warp_sum(acc);
-    if (lane == 0) logits[k] = acc + b2[k];
+    if (lane == 0) logits[k] = (acc + b2[k]) * drop_factor(drop, 1, k);
   }
 }
 
 // Backward.  Gradients are ACCUMULATED into dW1, db1, dW2, db2; dcls (d) = W1^T dzc + dcls_in.
 __global__ void __launch_bounds__(256)
 cls_head_bwd_init_kernel(const float* __restrict__ dlogits, const float* __restrict__ dcls_in, float* __restrict__ db2,
-                         float* __restrict__ dcls, int d, int C) {
+                         float* __restrict__ dcls, int d, int C, DropSpec drop) {
   for (int c = threadIdx.x; c < d; c += blockDim.x) dcls[c] = dcls_in ? dcls_in[c] : 0.f;
-  if (static_cast<int>(threadIdx.x) < C) db2[threadIdx.x] += dlogits[threadIdx.x];
+  if (static_cast<int>(threadIdx.x) < C) db2[threadIdx.x] += dlogits[threadIdx.x] * drop_factor(drop, 1, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(kHeadWarps * 32)
 cls_head_bwd_rows_kernel(const __nv_bfloat16* __restrict__ cls, const float* __restrict__ W1, const float* __restrict__ W2,
                          const float* __restrict__ zc, const float* __restrict__ dlogits, float* __restrict__ dW1,
-                         float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ dcls, int d, int H1, int C) {
+                         float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ dcls, int d, int H1, int C, DropSpec drop) {
   extern __shared__ float s_dcls[];   // [d] this CTA's partial W1^T dzc
   for (int c = threadIdx.x; c < d; c += blockDim.x) s_dcls[c] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, j = blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
   if (j < H1) {
-    const float z = zc[j], h = gelu_erf(z);
+    const float mh = drop_factor(drop, 0, j);                 // hidden-unit mask of the forward, regenerated
+    const float z = zc[j], h = gelu_erf(z) * mh;
     float dh = 0.f;
     for (int k = 0; k < C; ++k) {
-      const float dl = dlogits[k];
+      const float dl = dlogits[k] * drop_factor(drop, 1, k);  // gradient behind the output dropout
       dh = fmaf(W2[static_cast<int64_t>(k) * H1 + j], dl, dh);
       if (lane == 0) dW2[static_cast<int64_t>(k) * H1 + j] += dl * h;
     }
-    const float dz = dh * gelu_grad(z);
+    const float dz = dh * mh * gelu_grad(z);
     if (lane == 0) db1[j] += dz;
     for (int c = lane; c < d; c += 32) {
       const int64_t e = static_cast<int64_t>(j) * d + c;
@@ -376,20 +428,35 @@ static int ew_grid(int64_t n) {
 using namespace vdr;
 #define S_(stream) reinterpret_cast<cudaStream_t>(stream)
 
-extern "C" int vdr_gelu_fwd(const void* z, void* h, int64_t n, vdr_stream_t stream) {
+static int check_drop(const char* who, const vdr_dropout* d, int64_t n, int cols) {
+  VDR_CHECK_ARG(d == nullptr || d->thr16 < 65536u, VDR_EINVAL, "%s: dropout threshold must be < 65536 (p < 1)", who);
+  VDR_CHECK_ARG(d == nullptr || d->thr16 == 0 || (cols > 0 && cols % 8 == 0 && n % cols == 0), VDR_EINVAL,
+                "%s: dropout needs the matrix width (cols %% 8 == 0, n %% cols == 0), got cols = %d", who, cols);
+  return VDR_OK;
+}
+static vdr::DropSpec drop_spec(const vdr_dropout* d) {
+  vdr::DropSpec s{0ull, 0u, 0u};
+  if (d != nullptr) { s.seed = d->seed; s.site = d->site; s.thr16 = d->thr16; }
+  return s;
+}
+
+extern "C" int vdr_gelu_fwd(const void* z, void* h, int64_t n, int cols, const vdr_dropout* drop, vdr_stream_t stream) {
   VDR_CHECK_ARG(z && h && n > 0 && n % 8 == 0, VDR_EINVAL, "vdr_gelu_fwd: null pointer or n %% 8 != 0");
   VDR_CHECK_ARG(aligned16(z) && aligned16(h), VDR_EALIGN, "vdr_gelu_fwd: pointers must be 16-byte aligned");
-  gelu_fwd_kernel<<<ew_grid(n / 8), 256, 0, S_(stream)>>>(static_cast<const __nv_bfloat16*>(z), static_cast<__nv_bfloat16*>(h), n / 8);
+  if (int rc = check_drop("vdr_gelu_fwd", drop, n, cols)) return rc;
+  gelu_fwd_kernel<<<ew_grid(n / 8), 256, 0, S_(stream)>>>(static_cast<const __nv_bfloat16*>(z), static_cast<__nv_bfloat16*>(h), n / 8,
+                                                          cols > 0 ? cols / 8 : 1, drop_spec(drop));
   count_launch();
   VDR_CHECK_LAUNCH("gelu_fwd_kernel");
   return VDR_OK;
 }
 
-extern "C" int vdr_gelu_bwd(const void* dh, const void* z, void* dz, int64_t n, vdr_stream_t stream) {
+extern "C" int vdr_gelu_bwd(const void* dh, const void* z, void* dz, int64_t n, int cols, const vdr_dropout* drop, vdr_stream_t stream) {
   VDR_CHECK_ARG(dh && z && dz && n > 0 && n % 8 == 0, VDR_EINVAL, "vdr_gelu_bwd: null pointer or n %% 8 != 0");
   VDR_CHECK_ARG(aligned16(dh) && aligned16(z) && aligned16(dz), VDR_EALIGN, "vdr_gelu_bwd: pointers must be 16-byte aligned");
+  if (int rc = check_drop("vdr_gelu_bwd", drop, n, cols)) return rc;
   gelu_bwd_kernel<<<ew_grid(n / 8), 256, 0, S_(stream)>>>(static_cast<const __nv_bfloat16*>(dh), static_cast<const __nv_bfloat16*>(z),
-                                                          static_cast<__nv_bfloat16*>(dz), n / 8);
+                                                          static_cast<__nv_bfloat16*>(dz), n / 8, cols > 0 ? cols / 8 : 1, drop_spec(drop));
   count_launch();
   VDR_CHECK_LAUNCH("gelu_bwd_kernel");
   return VDR_OK;
@@ -449,12 +516,35 @@ extern "C" int vdr_cls_concat_layernorm_bwd(const void* dY, const float* X, cons
   return VDR_OK;
 }
 
+extern "C" int vdr_dropout_apply(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int cols, const vdr_dropout* drop,
+                                 vdr_stream_t stream) {
+  VDR_CHECK_ARG(x && out && drop && rows > 0 && cols > 0 && cols % 8 == 0, VDR_EINVAL, "vdr_dropout_apply: null pointer or cols %% 8 != 0");
+  VDR_CHECK_ARG(aligned16(x) && aligned16(out) && ldx % 8 == 0 && ldo % 8 == 0 && ldx >= cols && ldo >= cols, VDR_EALIGN,
+                "vdr_dropout_apply: pointers must be 16-byte aligned, pitches multiples of 8 and >= cols");
+  VDR_CHECK_ARG(drop->thr16 < 65536u, VDR_EINVAL, "vdr_dropout_apply: dropout threshold must be < 65536");
+  dropout_apply_kernel<<<ew_grid(rows * (cols / 8)), 256, 0, S_(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out),
+                                                                            ldo, rows, cols / 8, drop_spec(drop));
+  count_launch();
+  VDR_CHECK_LAUNCH("dropout_apply_kernel");
+  return VDR_OK;
+}
+
+extern "C" int vdr_dropout_mask(uint8_t* out, int64_t rows, int64_t cols, const vdr_dropout* drop, vdr_stream_t stream) {
+  VDR_CHECK_ARG(out && drop && rows > 0 && cols > 0 && cols < (1ll << 35), VDR_EINVAL, "vdr_dropout_mask: bad arguments");
+  VDR_CHECK_ARG(drop->thr16 < 65536u, VDR_EINVAL, "vdr_dropout_mask: dropout threshold must be < 65536");
+  dropout_mask_kernel<<<ew_grid(rows * cols), 256, 0, S_(stream)>>>(out, rows, cols, drop_spec(drop));
+  count_launch();
+  VDR_CHECK_LAUNCH("dropout_mask_kernel");
+  return VDR_OK;
+}
+
 extern "C" int vdr_cls_head_fwd(const void* cls_bf16, const float* W1, const float* b1, const float* W2, const float* b2,
-                                float* zc, float* logits, int d, int H1, int C, vdr_stream_t stream) {
+                                float* zc, float* logits, int d, int H1, int C, const vdr_dropout* drop, vdr_stream_t stream) {
   VDR_CHECK_ARG(cls_bf16 && W1 && b1 && W2 && b2 && zc && logits, VDR_EINVAL, "vdr_cls_head_fwd: null pointer");
   VDR_CHECK_ARG(d > 0 && H1 > 0 && C > 0, VDR_EINVAL, "vdr_cls_head_fwd: bad shape");
+  VDR_CHECK_ARG(drop == nullptr || drop->thr16 < 65536u, VDR_EINVAL, "vdr_cls_head_fwd: dropout threshold must be < 65536");
   cls_head_hidden_kernel<<<(H1 + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, 0, S_(stream)>>>(static_cast<const __nv_bfloat16*>(cls_bf16), W1, b1, zc, d, H1);
-  cls_head_out_kernel<<<1, 256, 0, S_(stream)>>>(zc, W2, b2, logits, H1, C);
+  cls_head_out_kernel<<<1, 256, 0, S_(stream)>>>(zc, W2, b2, logits, H1, C, drop_spec(drop));
   count_launch(2);
   VDR_CHECK_LAUNCH("cls_head_fwd kernels");
   return VDR_OK;
@@ -462,12 +552,13 @@ extern "C" int vdr_cls_head_fwd(const void* cls_bf16, const float* W1, const flo
 
 extern "C" int vdr_cls_head_bwd(const void* cls_bf16, const float* W1, const float* W2, const float* zc, const float* dlogits,
                                 const float* dcls_in, float* dW1, float* db1, float* dW2, float* db2, float* dcls, int d,
-                                int H1, int C, vdr_stream_t stream) {
+                                int H1, int C, const vdr_dropout* drop, vdr_stream_t stream) {
   VDR_CHECK_ARG(cls_bf16 && W1 && W2 && zc && dlogits && dW1 && db1 && dW2 && db2 && dcls, VDR_EINVAL, "vdr_cls_head_bwd: null pointer");
   VDR_CHECK_ARG(d > 0 && H1 > 0 && C > 0 && C <= 256 && (size_t)d * 4 <= 48 * 1024, VDR_EINVAL, "vdr_cls_head_bwd: bad shape");
-  cls_head_bwd_init_kernel<<<1, 256, 0, S_(stream)>>>(dlogits, dcls_in, db2, dcls, d, C);
+  VDR_CHECK_ARG(drop == nullptr || drop->thr16 < 65536u, VDR_EINVAL, "vdr_cls_head_bwd: dropout threshold must be < 65536");
+  cls_head_bwd_init_kernel<<<1, 256, 0, S_(stream)>>>(dlogits, dcls_in, db2, dcls, d, C, drop_spec(drop));
   cls_head_bwd_rows_kernel<<<(H1 + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, d * sizeof(float), S_(stream)>>>(
-      static_cast<const __nv_bfloat16*>(cls_bf16), W1, W2, zc, dlogits, dW1, db1, dW2, dcls, d, H1, C);
+      static_cast<const __nv_bfloat16*>(cls_bf16), W1, W2, zc, dlogits, dW1, db1, dW2, dcls, d, H1, C, drop_spec(drop));
   count_launch(2);
   VDR_CHECK_LAUNCH("cls_head_bwd kernels");
   return VDR_OK;

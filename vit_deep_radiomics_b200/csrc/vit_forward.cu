@@ -124,7 +124,7 @@ extern "C" int vdr_vit_forward(const vdr_vit_weights* w, const void* images_bf16
     for (int l = 0; l < w->depth; ++l) {
       const vdr_vit_block& b = w->blocks[l];
       if ((rc = gemm(X, d, b.qkv_wf, b.qkv_bf, 3 * d, d, VDR_EPI_BIAS, nullptr, QKV, l == 0 ? 1 : slots, b.qkv_cs)) != VDR_OK) return rc;
-      if ((rc = vdr_flash_attn_fwd(QKV, 3 * d, Y, d, nullptr, B, N, w->heads, scale, stream)) != VDR_OK) return rc;
+      if ((rc = vdr_flash_attn_fwd(QKV, 3 * d, Y, d, nullptr, B, N, w->heads, scale, nullptr, stream)) != VDR_OK) return rc;
       if ((rc = gemm(Y, d, b.proj_w, b.proj_b, d, d, VDR_EPI_BIAS_RESIDUAL, X, X, 0, nullptr, true)) != VDR_OK) return rc;
       if ((rc = gemm(X, d, b.fc1_wf, b.fc1_bf, 4 * d, d, VDR_EPI_BIAS_GELU, nullptr, Hb, slots, b.fc1_cs)) != VDR_OK) return rc;
       if ((rc = gemm(Hb, 4 * d, b.fc2_w, b.fc2_b, d, 4 * d, VDR_EPI_BIAS_RESIDUAL, X, X, 0, nullptr, l + 1 < w->depth)) != VDR_OK) return rc;
@@ -135,7 +135,7 @@ extern "C" int vdr_vit_forward(const vdr_vit_weights* w, const void* images_bf16
     const vdr_vit_block& b = w->blocks[l];
     if ((rc = vdr_layernorm_fwd(X, d, b.n1w, b.n1b, Y, d, VDR_DTYPE_BF16, nullptr, nullptr, M, d, eps, stream)) != VDR_OK) return rc;
     if ((rc = gemm(Y, d, b.qkv_w, b.qkv_b, 3 * d, d, VDR_EPI_BIAS, nullptr, QKV)) != VDR_OK) return rc;
-    if ((rc = vdr_flash_attn_fwd(QKV, 3 * d, Y, d, nullptr, B, N, w->heads, scale, stream)) != VDR_OK) return rc;
+    if ((rc = vdr_flash_attn_fwd(QKV, 3 * d, Y, d, nullptr, B, N, w->heads, scale, nullptr, stream)) != VDR_OK) return rc;
     if ((rc = gemm(Y, d, b.proj_w, b.proj_b, d, d, VDR_EPI_BIAS_RESIDUAL, X, X)) != VDR_OK) return rc;
     if ((rc = vdr_layernorm_fwd(X, d, b.n2w, b.n2b, Y, d, VDR_DTYPE_BF16, nullptr, nullptr, M, d, eps, stream)) != VDR_OK) return rc;
     if ((rc = gemm(Y, d, b.fc1_w, b.fc1_b, 4 * d, d, VDR_EPI_BIAS_GELU, nullptr, Hb)) != VDR_OK) return rc;

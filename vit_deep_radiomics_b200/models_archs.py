@@ -9,7 +9,9 @@ reference (``save_checkpoint`` / ``load_checkpoint`` keep its file naming, :14-3
 The arithmetic does not go through torch.nn: parameters are only *stored* in torch modules.
 Forward and backward run in libvdr.so (CLS-concat+LayerNorm kernel, tcgen05 GEMMs with fused
 bias/GELU/residual epilogues, fused attention, LayerNorm) -- see ``classifier_kernels.py``.
-Deviation: dropout (0.1 in the reference's train mode) is not applied (p = 0).
+Train mode applies the reference's dropouts (encoder layers 0.1 / 0.5, MLPLayer 0.1, :51,58,135,187-199) inside the kernels from a
+counter-based generator seeded per forward pass from torch's default generator; RNG streams differ from PyTorch's by
+construction, so parity with the reference is exact in ``eval()`` and statistical in ``train()``.
 """
 from __future__ import annotations
 
@@ -43,6 +45,21 @@ def load_checkpoint(model, save_dir, epoch):
     return load(model, os.path.join(save_dir, f"model_epoch_{str(epoch).zfill(4)}.pth"))
 
 
+def set_dropout(model: nn.Module, p_encoder: float | None = None, p_head: float | None = None) -> nn.Module:
+    """Change the dropout rates of a classifier built by this module (the reference hard-codes 0.1 / 0.5 in its constructors):
+    ``p_encoder`` for every nn.TransformerEncoderLayer (its sub-layer dropouts and the attention probabilities), ``p_head`` for every
+    MLPLayer.  ``set_dropout(model, 0.0, 0.0)`` makes ``train()`` deterministic -- what the parity tests against the fp32 oracle and
+    the reference's gradients use ("dropout 0 for parity runs")."""
+    for m in model.modules():
+        if p_encoder is not None and isinstance(m, nn.TransformerEncoderLayer):
+            for name in ("dropout", "dropout1", "dropout2"):
+                getattr(m, name).p = float(p_encoder)
+            m.self_attn.dropout = float(p_encoder)
+        if p_head is not None and isinstance(m, MLPLayer):
+            m.dropout_rate = float(p_head)
+    return model
+
+
 class MLPLayer(nn.Module):
     """Parameter container for the reference's MLPLayer (:186-200): dense1 -> GELU -> dense2."""
 
@@ -72,6 +89,17 @@ class TransformerNoduleClassifier(nn.Module):
         self.input_dim, self.dim_feedforward = input_dim, dim_feedforward
         self.num_heads, self.num_layers, self.num_classes = num_heads, num_layers, num_classes
 
+    def _drop_cfg(self):
+        """Dropout of this forward pass: active in train mode (model.train(), train_models.py:652) with the rates the modules were
+        built with (0.1 in every encoder sub-layer and on the attention probabilities, :135; 0.1 in the head, :139,187)."""
+        if not self.training:
+            return None
+        p_enc = float(self.transformer_encoder.layers[0].dropout.p)
+        p_head = float(self.classifier.dropout_rate)
+        if p_enc <= 0 and p_head <= 0:
+            return None
+        return ck.DropCfg(ck.new_seed(), p_enc, p_head)
+
     def param_list(self):
         """Parameters in the fixed order the kernels expect (see classifier_kernels.PARAM_ORDER)."""
         ps = [self.cls_token, self.norm.weight, self.norm.bias]
@@ -94,10 +122,11 @@ class TransformerNoduleClassifier(nn.Module):
         train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         logits, cls = [], []
         for b in range(x.shape[0]):
+            drop = self._drop_cfg()
             if train:
-                lg, c = ck.ClassifierFunction.apply(x[b], self.num_heads, self.num_layers, *params)
+                lg, c = ck.ClassifierFunction.apply(x[b], self.num_heads, self.num_layers, drop, *params)
             else:
-                lg, c = ck.classifier_forward(x[b], self.num_heads, self.num_layers, params)
+                lg, c = ck.classifier_forward(x[b], self.num_heads, self.num_layers, params, drop=drop)
             logits.append(lg)
             cls.append(c)
         return torch.stack(logits, 0), torch.stack(cls, 0)
@@ -177,10 +206,15 @@ class TransformerNoduleBimodalClassifier(nn.Module):
         for b in range(B):
             xc = x_ct[b] if x_ct is not None else None
             xp = x_pet[b] if x_pet is not None else None
+            drop = None
+            if self.training:   # 0.5 in both encoders (:51,58), 0.1 in the four MLPLayers (:66-75)
+                p_enc, p_head = float(self.transformer_encoder_ct.layers[0].dropout.p), float(self.classifier_ct.dropout_rate)
+                if p_enc > 0 or p_head > 0:
+                    drop = ck.DropCfg(ck.new_seed(), p_enc, p_head)
             if train:
-                r = bk.BimodalFunction.apply(xc, xp, self.cfg, sizes, *flat)
+                r = bk.BimodalFunction.apply(xc, xp, self.cfg, sizes, drop, *flat)
             else:
-                r = bk.bimodal_forward(xc, xp, self.cfg, groups)
+                r = bk.bimodal_forward(xc, xp, self.cfg, groups, drop=drop)
             for o, v in zip(outs, r):
                 o.append(v)
         return tuple(torch.stack(o, 0) for o in outs)

@@ -51,11 +51,53 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+class Drop:
+    """One dropout site of a training step (include/vdr.h, vdr_dropout): ``seed`` per forward pass, ``site`` per dropout
+    module, ``p`` the module's rate.  The kernels regenerate the mask from (seed, site); nothing is stored."""
+    __slots__ = ("seed", "site", "thr16")
+
+    def __init__(self, seed: int, site: int, p: float):
+        if not 0.0 <= p < 1.0:
+            raise ValueError(f"dropout probability has to be in [0, 1), got {p}")
+        self.seed, self.site = int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF
+        self.thr16 = min(65535, int(round(p * 65536)))
+
+    @property
+    def p(self) -> float:
+        return self.thr16 / 65536.0
+
+    def c(self):
+        return _C.Dropout(self.seed, self.site, self.thr16)
+
+
+def _dp(drop):
+    """ctypes argument for an optional Drop (None / p = 0 -> NULL)."""
+    return C.byref(drop.c()) if drop is not None and drop.thr16 else None
+
+
+def dropout_mask(rows: int, cols: int, drop: Drop, device) -> torch.Tensor:
+    """(rows, cols) uint8, 1 = kept: the mask exactly as the kernels compute it (tests, reference computations)."""
+    out = torch.empty((rows, cols), dtype=torch.uint8, device=device)
+    _C.check(_C.lib().vdr_dropout_mask(out.data_ptr(), rows, cols, C.byref(drop.c()), _stream()), "vdr_dropout_mask")
+    return out
+
+
+def dropout_apply(x: torch.Tensor, drop: Drop) -> torch.Tensor:
+    """x * mask / (1 - p) for a bf16 matrix (the backward of a dropout applied inside a GEMM epilogue)."""
+    _req(x, torch.bfloat16, "x")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be 2-D with unit inner stride")
+    out = torch.empty((x.shape[0], x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    _C.check(_C.lib().vdr_dropout_apply(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
+                                        C.byref(drop.c()), _stream()), "vdr_dropout_apply")
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, epilogue: str = "bias",
          residual: torch.Tensor | None = None, out: torch.Tensor | None = None, out_dtype=torch.bfloat16,
          k: int | None = None, out_rows: int | None = None, out_group=(0, 0, 0), res_mod=(0, 0),
          ln_stats: torch.Tensor | None = None, ln_colsum: torch.Tensor | None = None, ln_eps: float = 1e-6,
-         stats_out: torch.Tensor | None = None) -> torch.Tensor:
+         stats_out: torch.Tensor | None = None, drop: "Drop | None" = None) -> torch.Tensor:
     """out = epi(a @ w.T + bias [+ residual]) on tcgen05.  a (M, K[ld]) bf16, w (N, K[ld]) bf16.
 
     Folded LayerNorm (include/vdr.h, vdr_gemm_args): ``ln_stats`` (slots, M, 2) f32 row statistics of ``a`` + ``ln_colsum`` (N)
@@ -98,6 +140,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
         if not stats_out.is_contiguous() or stats_out.numel() < (N // 64) * M * 2:
             raise ValueError("stats_out must be a contiguous f32 buffer of at least (N/64, M, 2)")
         args.stats_out = stats_out.data_ptr()
+    if drop is not None and drop.thr16:      # residual epilogue: out = residual + dropout(a @ w.T + bias)
+        args.drop = drop.c()
     with _Prof("gemm", 2.0 * M * N * K, f"gemm M{M} N{N} K{K} {epilogue}"):
         _C.check(_C.lib().vdr_gemm(C.byref(args), _stream()), "vdr_gemm")
     return out
@@ -265,8 +309,8 @@ def cls_concat_layernorm(x: torch.Tensor, cls: torch.Tensor, gamma, beta, eps: f
 
 
 def flash_attn(qkv: torch.Tensor, B: int, N: int, heads: int, scale: float | None = None,
-               out: torch.Tensor | None = None, return_lse: bool = False):
-    """qkv (B*N, 3*heads*64) bf16 -> out (B*N, heads*64) bf16."""
+               out: torch.Tensor | None = None, return_lse: bool = False, drop: "Drop | None" = None):
+    """qkv (B*N, 3*heads*64) bf16 -> out (B*N, heads*64) bf16.  ``drop``: attention dropout on the normalised probabilities."""
     _req(qkv, torch.bfloat16, "qkv")
     d = heads * 64
     if qkv.shape != (B * N, 3 * d):
@@ -278,7 +322,7 @@ def flash_attn(qkv: torch.Tensor, B: int, N: int, heads: int, scale: float | Non
     lse = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if return_lse else None
     with _Prof("attn", 4.0 * B * heads * N * N * 64, f"attn B{B} N{N} h{heads}"):
         _C.check(_C.lib().vdr_flash_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0),
-                                             lse.data_ptr() if return_lse else None, B, N, heads, float(scale),
+                                             lse.data_ptr() if return_lse else None, B, N, heads, float(scale), _dp(drop),
                                              _stream()), "vdr_flash_attn_fwd")
     return (out, lse) if return_lse else out
 
@@ -508,16 +552,21 @@ def voxel_gather(img: torch.Tensor, mask_u8: torch.Tensor, bbox: torch.Tensor, c
 
 
 # ----------------------------------------------------------------------------- training-only kernels
-def gelu(z: torch.Tensor) -> torch.Tensor:
+def gelu(z: torch.Tensor, drop: "Drop | None" = None) -> torch.Tensor:
+    """dropout(gelu(z)) for a contiguous bf16 matrix (the feed-forward block's inner dropout fused into the activation)."""
     _req(z, torch.bfloat16, "z")
+    if not z.is_contiguous():
+        raise ValueError("z must be contiguous")
     h = torch.empty_like(z)
-    _C.check(_C.lib().vdr_gelu_fwd(z.data_ptr(), h.data_ptr(), z.numel(), _stream()), "vdr_gelu_fwd")
+    _C.check(_C.lib().vdr_gelu_fwd(z.data_ptr(), h.data_ptr(), z.numel(), z.shape[-1], _dp(drop), _stream()), "vdr_gelu_fwd")
     return h
 
 
-def gelu_bwd(dh: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+def gelu_bwd(dh: torch.Tensor, z: torch.Tensor, drop: "Drop | None" = None) -> torch.Tensor:
+    if not (z.is_contiguous() and dh.is_contiguous()):
+        raise ValueError("dh and z must be contiguous")
     dz = torch.empty_like(z)
-    _C.check(_C.lib().vdr_gelu_bwd(dh.data_ptr(), z.data_ptr(), dz.data_ptr(), z.numel(), _stream()), "vdr_gelu_bwd")
+    _C.check(_C.lib().vdr_gelu_bwd(dh.data_ptr(), z.data_ptr(), dz.data_ptr(), z.numel(), z.shape[-1], _dp(drop), _stream()), "vdr_gelu_bwd")
     return dz
 
 
@@ -541,7 +590,7 @@ def colsum_accum(x: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def flash_attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Tensor, B: int, N: int, heads: int,
-                   scale: float | None = None) -> torch.Tensor:
+                   scale: float | None = None, drop: "Drop | None" = None) -> torch.Tensor:
     """dqkv (B*N, 3d) bf16 from the forward's packed qkv, output o, upstream gradient do (all bf16) and lse (B, heads, N) f32."""
     _req(qkv, torch.bfloat16, "qkv"), _req(o, torch.bfloat16, "o"), _req(do, torch.bfloat16, "do"), _req(lse, torch.float32, "lse")
     d = heads * 64
@@ -554,7 +603,7 @@ def flash_attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: to
     ws = torch.empty(need, dtype=torch.uint8, device=qkv.device)
     with _Prof("attn_bwd", 10.0 * B * heads * N * N * 64, f"attn-bwd B{B} N{N} h{heads}"):
         _C.check(_C.lib().vdr_flash_attn_bwd(qkv.data_ptr(), qkv.stride(0), o.data_ptr(), do.data_ptr(), o.stride(0), lse.data_ptr(),
-                                             dqkv.data_ptr(), dqkv.stride(0), B, N, heads, float(scale), ws.data_ptr(), need, _stream()),
+                                             dqkv.data_ptr(), dqkv.stride(0), B, N, heads, float(scale), _dp(drop), ws.data_ptr(), need, _stream()),
                  "vdr_flash_attn_bwd")
     return dqkv
 
@@ -584,21 +633,21 @@ def cls_concat_layernorm_bwd(dY, X, cls, gamma, mean, rstd, dgamma, dbeta, dcls)
              "vdr_cls_concat_layernorm_bwd")
 
 
-def cls_head_fwd(cls_bf16, W1, b1, W2, b2):
+def cls_head_fwd(cls_bf16, W1, b1, W2, b2, drop: "Drop | None" = None):
     d, H1, Cn = cls_bf16.numel(), W1.shape[0], W2.shape[0]
     zc = torch.empty(H1, dtype=torch.float32, device=W1.device)
     logits = torch.empty(Cn, dtype=torch.float32, device=W1.device)
     _C.check(_C.lib().vdr_cls_head_fwd(cls_bf16.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
-                                       zc.data_ptr(), logits.data_ptr(), d, H1, Cn, _stream()), "vdr_cls_head_fwd")
+                                       zc.data_ptr(), logits.data_ptr(), d, H1, Cn, _dp(drop), _stream()), "vdr_cls_head_fwd")
     return logits, zc
 
 
-def cls_head_bwd(cls_bf16, W1, W2, zc, dlogits, dcls_in, dW1, db1, dW2, db2):
+def cls_head_bwd(cls_bf16, W1, W2, zc, dlogits, dcls_in, dW1, db1, dW2, db2, drop: "Drop | None" = None):
     d, H1, Cn = cls_bf16.numel(), W1.shape[0], W2.shape[0]
     dcls = torch.empty(d, dtype=torch.float32, device=W1.device)
     _C.check(_C.lib().vdr_cls_head_bwd(cls_bf16.data_ptr(), W1.data_ptr(), W2.data_ptr(), zc.data_ptr(), dlogits.data_ptr(),
                                        dcls_in.data_ptr() if dcls_in is not None else None, dW1.data_ptr(), db1.data_ptr(),
-                                       dW2.data_ptr(), db2.data_ptr(), dcls.data_ptr(), d, H1, Cn, _stream()),
+                                       dW2.data_ptr(), db2.data_ptr(), dcls.data_ptr(), d, H1, Cn, _dp(drop), _stream()),
              "vdr_cls_head_bwd")
     return dcls
 
