@@ -303,6 +303,27 @@ int vdr_debug_set_gather_trace(void* dev_u64x16);
 int vdr_exclusive_scan_i64(const int64_t* counts, int n, int64_t* offsets, vdr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * V4 / N2: the offline augmentation of the extraction loop on the device.
+ * Replaces: flip_image (tfds_dense_descriptor.py:306-325) and rotate_image (:328-350: scipy.ndimage.rotate(x, angle, axes=(0, 1),
+ * reshape=False, mode='nearest'), cubic spline; np.clip(image, 0, 1); mask > 0), applied to whole volumes 12 times per patient
+ * (:463-466).  The rotation restates scipy's algorithm operation for operation in IEEE double (12-pixel edge padding, cubic
+ * prefilter with its 'reflect' initialisers, unmapped coordinates, clamped taps, 16-term sum): the results are bit-identical to
+ * scipy 1.18 -- masks AND float32 images (tests/test_gpu_augment.py; the reference's bool mask is the interpolated value cast to
+ * unsigned char, i.e. |t| >= 1, which depends on the last bit of t inside the mask).
+ *   src / dst  (H, W, planes) volumes, plane index fastest (np.dstack layout; planes = slices x channels)
+ *   src_kind   0: f32 image -> f32 image clipped to [0, 1];  1: bool mask (u8 storage) -> u8 mask;  2: uint8 mask -> u8 mask
+ *   flip       0 none, 1 'horizontal' (columns reversed), 2 'vertical' (rows reversed); applied before the rotation as in :463-466
+ *   rotate     0: flip only (masks are re-binarised);  1: rotate with xform_host (HOST, f64[6]) = {m00, m01, m10, m11, off0, off1}
+ *              = scipy's rot_matrix [[c, s], [-s, c]] (special.cosdg / sindg) and offset = in_center - rot_matrix @ out_center;
+ *              z_n_rows = pow(z, H + 24), z_n_cols = pow(z, W + 24) with z = -0x1.126145e9ecd56p-2 (libm pow on the host)
+ *   workspace  >= vdr_rotate_workspace_bytes(H, W, planes) (the padded f64 planes), 8-byte aligned; unused when rotate == 0
+ */
+size_t vdr_rotate_workspace_bytes(int H, int W, int planes);
+int vdr_flip_rotate_volume(const void* src, int src_kind, void* dst, int H, int W, int planes, int flip, int rotate,
+                           const double* xform_host, double z_n_rows, double z_n_cols, void* workspace, size_t workspace_bytes,
+                           vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * G2: voxel point cloud.  Replaces: to_pointcloud_df + the caller's mask_box filter
  * (create_pointcloud_dataframe.py:15-31,78).
  *   img f32 (H,W,S), mask u8 (H,W,S).  Pass 1 reduces the index-space bounding box of mask>0

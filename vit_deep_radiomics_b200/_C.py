@@ -21,7 +21,7 @@ EXPORTS = (
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd", "vdr_row_stats", "vdr_fold_layernorm",
     "vdr_flash_attn_fwd", "vdr_flash_attn_bwd_workspace_bytes", "vdr_flash_attn_bwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather", "vdr_mask_gather_table", "vdr_mask_count", "vdr_exclusive_scan_i64", "vdr_debug_set_gather_trace",
-    "vdr_voxel_bbox", "vdr_mask_bbox", "vdr_voxel_gather",
+    "vdr_voxel_bbox", "vdr_mask_bbox", "vdr_voxel_gather", "vdr_rotate_workspace_bytes", "vdr_flip_rotate_volume",
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
     "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
     "vdr_linear_vec_fwd", "vdr_linear_vec_bwd", "vdr_cross_cls_attn_fwd", "vdr_cross_cls_attn_bwd",
@@ -120,6 +120,9 @@ def lib() -> C.CDLL:
     L.vdr_mask_count.argtypes = [vp, i64, i64, i64, vp, vp, i32, i32, i32, vp, vp]
     L.vdr_exclusive_scan_i64.argtypes = [vp, i32, vp, vp]
     L.vdr_debug_set_gather_trace.argtypes = [vp]
+    L.vdr_rotate_workspace_bytes.argtypes = [i32, i32, i32]
+    L.vdr_rotate_workspace_bytes.restype = sz
+    L.vdr_flip_rotate_volume.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, C.POINTER(f64), f64, f64, vp, sz, vp]
     L.vdr_voxel_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_mask_bbox.argtypes = [vp, i32, i32, i32, vp, vp]
     L.vdr_voxel_gather.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
@@ -146,7 +149,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         if name not in ("vdr_version", "vdr_last_error_string", "vdr_launch_count",
                         "vdr_mask_gather_workspace_bytes", "vdr_vit_forward_workspace_bytes",
-                        "vdr_volume_to_slices_resized_workspace_bytes", "vdr_flash_attn_bwd_workspace_bytes"):
+                        "vdr_volume_to_slices_resized_workspace_bytes", "vdr_flash_attn_bwd_workspace_bytes", "vdr_rotate_workspace_bytes"):
             fn.restype = i32
     _lib = L
     return L

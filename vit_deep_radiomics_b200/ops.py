@@ -327,6 +327,58 @@ def flash_attn(qkv: torch.Tensor, B: int, N: int, heads: int, scale: float | Non
     return (out, lse) if return_lse else out
 
 
+# ----------------------------------------------------------------------------- offline augmentation (flip / rotate) on the device
+ROT_POLE = float.fromhex("-0x1.126145e9ecd56p-2")      # the cubic-spline pole as folded into scipy's binary (include/vdr.h)
+_FLIPS = {None: 0, "None": 0, "horizontal": 1, "vertical": 2}
+
+
+def rotation_xform(shape_hw, angle):
+    """(m00, m01, m10, m11, off0, off1) exactly as scipy.ndimage.rotate computes them for reshape=False (same NumPy / scipy.special
+    calls, so the same doubles)."""
+    from scipy import special
+    c, s = special.cosdg(angle), special.sindg(angle)
+    rot = np.array([[c, s], [-s, c]])
+    plane = np.asarray(shape_hw)
+    offset = (plane - 1) / 2 - rot @ ((plane - 1) / 2)
+    return (C.c_double * 6)(rot[0, 0], rot[0, 1], rot[1, 0], rot[1, 1], offset[0], offset[1])
+
+
+_ROT_WS: dict = {}
+
+
+def flip_rotate_volume(vol: torch.Tensor, flip=None, angle=0, *, kind: str = "image", out: torch.Tensor | None = None) -> torch.Tensor:
+    """flip_image + rotate_image of the reference's augmentation loop (tfds_dense_descriptor.py:306-350, :463-466) for a whole
+    device-resident volume: (H, W, S[, C]) contiguous; kind "image" (f32 -> f32 clipped to [0, 1]), "mask_bool" (a NumPy bool mask
+    uploaded as uint8) or "mask_u8" (a uint8 mask; scipy rounds instead of truncating there).  Bit-identical to the host functions."""
+    kinds = {"image": (0, torch.float32), "mask_bool": (1, torch.uint8), "mask_u8": (2, torch.uint8)}
+    if kind not in kinds:
+        raise ValueError(f"kind must be one of {sorted(kinds)}")
+    code, dt = kinds[kind]
+    _req(vol, dt, "vol")
+    if vol.dim() not in (3, 4) or not vol.is_contiguous():
+        raise ValueError("vol must be a contiguous (H, W, S) or (H, W, S, C) tensor")
+    if flip not in _FLIPS:
+        raise ValueError(f"flip must be None, 'horizontal' or 'vertical', got {flip!r}")
+    H, W = vol.shape[0], vol.shape[1]
+    planes = vol.numel() // (H * W)
+    if out is None:
+        out = torch.empty_like(vol)
+    rotate = int(angle) % 360 != 0
+    xf, zr, zc, ws, need = None, 0.0, 0.0, None, 0
+    if rotate:
+        xf = rotation_xform((H, W), angle)
+        zr, zc = math.pow(ROT_POLE, H + 24), math.pow(ROT_POLE, W + 24)
+        need = _C.lib().vdr_rotate_workspace_bytes(H, W, planes)
+        key = (str(vol.device), _stream())
+        ws = _ROT_WS.get(key)
+        if ws is None or ws.numel() < need:
+            ws = _ROT_WS[key] = torch.empty(need, dtype=torch.uint8, device=vol.device)
+    _C.check(_C.lib().vdr_flip_rotate_volume(vol.data_ptr(), code, out.data_ptr(), H, W, planes, _FLIPS[flip], 1 if rotate else 0, xf, zr, zc,
+                                             ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, _stream()),
+             "vdr_flip_rotate_volume")
+    return out
+
+
 # ----------------------------------------------------------------------------- gathers
 def nearest_index_map(n_out: int, n_in: int) -> np.ndarray:
     """Order-0 resize source indices (skimage.transform.resize(order=0) semantics used at

@@ -173,6 +173,28 @@ def generate_features(model, img_3d, mask_3d, tqdm_text="", display=False, max_b
     return features_list, mask_list
 
 
+_BUILTIN_GENERATE_FEATURES = generate_features
+
+
+def generate_features_device(model, img_dev, mask_dev, max_batch=None):
+    """``generate_features`` for a volume that already lives on the device ((H, W, S) f32 image, (H, W, S) uint8 mask): the
+    union-mask bounding box comes from a device reduction (24-byte read-back), the ROI crops of the descriptors and of the masks
+    are read back as the reference returns them (lists of per-slice arrays)."""
+    ex = getattr(model, "_extractor", None)
+    if ex is None:
+        ex = model._extractor = PointCloudExtractor(model)
+    plan = ex.plan_patient(mask_dev)
+    tok = _forward_volume(model, img_dev, plan, max_batch)
+    S, d, off = img_dev.shape[2], model.feature_dim, model.token_offset
+    gh, gw = model.grid
+    fy0, fy1, fx0, fx1 = plan["feat_roi"]
+    feats = tok.view(S, model.n_tokens, d)[:, off:, :].reshape(S, gh, gw, d)[:, fy0:fy1, fx0:fx1, :].cpu().numpy()
+    y0, y1, x0, x1 = plan["crop"]
+    my0, my1, mx0, mx1 = plan["mask_roi"]
+    mask_c = mask_dev[y0 + my0:y0 + my1, x0 + mx0:x0 + mx1].cpu().numpy() > 0
+    return [feats[s] for s in range(S)], [np.ascontiguousarray(mask_c[:, :, s]) for s in range(S)]
+
+
 def _as_pinned_pair(img_3d, mask_3d):
     img_t = img_3d if isinstance(img_3d, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(img_3d, dtype=np.float32))
     if isinstance(mask_3d, torch.Tensor):
@@ -385,7 +407,7 @@ def normalize_volume(img_raw, modality, model_name):
 
 
 def extract_patient_features(model, img_raw, mask_raw, patient_id, label, dataset_name, modality, spatial_res, tqdm_text=None,
-                             generate=None):
+                             generate=None, device_augment=None):
     """One patient of the reference's extraction loop (tfds_dense_descriptor.py:452-488): every (flip, angle) of the offline
     augmentation grid goes through ``generate_features`` (all slices of a volume as one backbone batch here), the per-slice
     feature maps / masks are concatenated and described by the metadata table the trainer reads.
@@ -399,12 +421,32 @@ def extract_patient_features(model, img_raw, mask_raw, patient_id, label, datase
     gen = generate or generate_features
     rows = {"slice": [], "angle": [], "flip": []}
     all_features, all_masks = [], []
+    img_raw, mask_raw = np.asarray(img_raw), np.asarray(mask_raw)
+    # The 12 whole-volume copies (3 flips x 4 angles, :463-466) are made ON THE DEVICE from one upload of the raw volume when the
+    # inputs have the dtypes the kernels restate scipy for (float32 gray volume; bool or uint8 mask): csrc/augment.cu is
+    # bit-identical to flip_image + rotate_image.  Other dtypes (a float64 volume keeps float64 through scipy) and custom
+    # `generate` callbacks take the reference's own host functions.
+    builtin = generate is None and generate_features is _BUILTIN_GENERATE_FEATURES      # (a patched module attribute is a custom callback too)
+    on_device = device_augment if device_augment is not None else builtin
+    on_device = on_device and builtin and img_raw.dtype == np.float32 and img_raw.ndim == 3 and mask_raw.dtype in (np.bool_, np.uint8)
+    if device_augment and not on_device:
+        raise ValueError("device_augment needs a float32 (H, W, S) volume, a bool / uint8 mask and the built-in generate_features")
+    if on_device:
+        img_dev = torch.as_tensor(np.ascontiguousarray(img_raw)).to(model.device)
+        mask_kind = "mask_bool" if mask_raw.dtype == np.bool_ else "mask_u8"
+        mask_dev = torch.as_tensor(np.ascontiguousarray(mask_raw).view(np.uint8)).to(model.device)
     for flip_type in AUG_FLIPS:
-        image_flip, mask_flip = flip_image(img_raw, mask_raw, flip_type)
+        if not on_device:
+            image_flip, mask_flip = flip_image(img_raw, mask_raw, flip_type)
         for angle in AUG_ANGLES:
-            image, mask = rotate_image(image_flip, mask_flip, angle)
-            features, features_mask = gen(model=model, img_3d=image, mask_3d=mask,
-                                          tqdm_text=tqdm_text or f"{modality} {patient_id}", display=False)
+            if on_device:
+                image = ops.flip_rotate_volume(img_dev, flip_type, angle, kind="image")
+                mask = ops.flip_rotate_volume(mask_dev, flip_type, angle, kind=mask_kind)
+                features, features_mask = generate_features_device(model, image, mask)
+            else:
+                image, mask = rotate_image(image_flip, mask_flip, angle)
+                features, features_mask = gen(model=model, img_3d=image, mask_3d=mask,
+                                              tqdm_text=tqdm_text or f"{modality} {patient_id}", display=False)
             all_masks += features_mask
             all_features += features
             rows["angle"] += [angle] * len(features)
