@@ -567,7 +567,8 @@ def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4):
                 zero_grads(clf, opt)
         return float(last.detach())
 
-    run(2)
+    for _ in range(3):                                      # the first passes pay the caching allocator's growth (every workspace size is new) and
+        run(patients)                                       # the clock ramp: measured 57 -> 32 ms per patient between the first and the third pass
     n0 = _C.launch_count()
     ms, loss = D.timed(lambda: run(patients), 1)
     launches = _C.launch_count() - n0

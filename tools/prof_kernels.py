@@ -57,7 +57,7 @@ if which in ("gather", "all"):
     tok = torch.randn(S * (gh * gw + 1), d, device=dev)
     m = torch.as_tensor(np.ascontiguousarray(np.moveaxis(mask, -1, 0)).view(np.uint8)).to(dev)
     pe = dict(res=res, noise=(0.0, 0.0, 0.0), scale=0.25)
-    for _ in range(3):   # two warm rounds (16 g1_* launches), then the captured round (-s 16 -c 8)
+    for _ in range(3):   # two warm rounds (4 g1_fused launches), then the captured round (-s 4 -c 2): C2's own mask, then a dense one
         for mm in (m, torch.ones_like(m)):
             ops.mask_gather(tok, mm, grid=(S, gh, gw, gh * gw + 1, 1), pe=pe)
         torch.cuda.synchronize()
