@@ -657,6 +657,66 @@ def bench_medsam(D: Dist, B: int = 8, steps: int = 3, cpu: bool = True):
     return rec
 
 
+def bench_augment(D: Dist, host_slices: int = 6):
+    """V4 / N2: one patient of the reference's offline extraction loop (tfds_dense_descriptor.py:452-488: 3 flips x 4 angles of the
+    whole volume, each through generate_features) -- the 12 volume copies made on the device (csrc/augment.cu, bit-identical to
+    scipy.ndimage.rotate) against the reference's host flip_image + rotate_image, timed on a slab of the same volume."""
+    from vit_deep_radiomics_b200 import _C, ops, synth, tfds_dense_descriptor as tdd
+    dev = D.dev
+    img, mask, res, name = synth.make_case("C2", seed=1240)
+    H, W, S = img.shape
+    model = tdd.load_model(name, img_hw=(H, W), device=dev, seed=1234)
+
+    def patient():
+        df, feats, masks = tdd.extract_patient_features(model, img, mask, "p0", 1, "synthetic_dataset", "CT", res, device_augment=True)
+        return len(feats)
+
+    patient()
+    torch.cuda.synchronize()
+    n0 = _C.launch_count()
+    t0 = time.perf_counter()
+    n_maps = patient()
+    torch.cuda.synchronize()
+    dt_dev = time.perf_counter() - t0
+    launches = _C.launch_count() - n0
+    # the 24 whole-volume transforms alone (image + mask per (flip, angle)), device time
+    img_d = torch.as_tensor(img).to(dev)
+    mask_d = torch.as_tensor(np.ascontiguousarray(mask).view(np.uint8)).to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for flip in tdd.AUG_FLIPS:
+        for angle in tdd.AUG_ANGLES:
+            ops.flip_rotate_volume(img_d, flip, angle, kind="image")
+            ops.flip_rotate_volume(mask_d, flip, angle, kind="mask_bool")
+    e1.record()
+    torch.cuda.synchronize()
+    ms_aug = e0.elapsed_time(e1)
+    voxels = H * W * S
+    rec = {"workload": f"offline augmentation loop of one patient: {len(tdd.AUG_FLIPS)} flips x {len(tdd.AUG_ANGLES)} angles of a {H}x{W}x{S} volume + mask on the device "
+                       f"(cubic-spline rotation bit-identical to scipy), each copy through {name} + ROI read-back ({n_maps} feature maps)",
+           "value": 1.0 / dt_dev, "unit": "patients/s", "s_per_patient": dt_dev, "gpu_launches": int(launches),
+           "augmentation_ms": ms_aug, "augmentation_share": ms_aug / 1e3 / dt_dev,
+           "roofline": {"bound": "hbm", "kernel": "rot_prefilter_kernel + rot_interp_kernel (+ flip_copy_kernel)",
+                        "achieved": 12 * voxels * (4 + 4 + 1 + 1) / (ms_aug / 1e3) / 1e9, "unit": "GB/s", "peak": measured_peaks()["hbm"],
+                        "frac": 12 * voxels * 10 / (ms_aug / 1e3) / 1e9 / measured_peaks()["hbm"],
+                        "note": "algorithmic bytes = volume in + out (f32) and mask in + out (u8) per (flip, angle); the rotation itself is f64 arithmetic "
+                                "(prefilter planes in a padded f64 workspace), so the fraction is an upper bound on what the memory system sees"},
+           "e2e": {"value": 1.0 / dt_dev, "unit": "patients/s", "h2d_bytes_per_step": int(voxels * 5), "d2h_bytes_per_step": None,
+                   "api": "tfds_dense_descriptor.extract_patient_features(..., device_augment=True): NumPy volume in, metadata table + per-slice feature maps / masks out (wall clock)"}}
+    if D.rank == 0:
+        sub_i, sub_m = np.ascontiguousarray(img[:, :, :host_slices]), np.ascontiguousarray(mask[:, :, :host_slices])
+        t0 = time.perf_counter()
+        fi, fm = tdd.flip_image(sub_i, sub_m, "horizontal")
+        tdd.rotate_image(fi, fm, 45)
+        dt = time.perf_counter() - t0
+        host_aug = dt * (S / host_slices) * 9 + 0.0            # 9 of the 12 copies are rotated (angle != 0)
+        host_total = host_aug + (dt_dev - ms_aug / 1e3)         # the backbone / read-back part is the same on both paths
+        rec["cpu_baseline"] = {"value": 1.0 / host_total, "unit": "patients/s", "cores": 1, "kind": "port",
+                               "sample": f"flip_image + rotate_image (the reference's scipy.ndimage.rotate calls, one thread as scipy runs them) on a {host_slices}-slice slab, "
+                                         f"{dt:.2f} s, scaled to {S} slices x 9 rotated copies = {host_aug:.1f} s per patient, plus the device path's backbone time"}
+    return rec
+
+
 # ----------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     D = Dist()
@@ -677,6 +737,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
         if world == 1 and args.medsam:
             sub["medsam"] = bench_medsam(D)
+        torch.cuda.empty_cache()
+        if world == 1:
+            sub["augment"] = bench_augment(D)
     if rank != 0:
         return
     c = synth.CONFIGS[args.config]
@@ -704,7 +767,7 @@ def main():
     ap.add_argument("--sample-slices", type=int, default=8, dest="sample_slices")
     ap.add_argument("--cpu-sample-slices", type=int, default=32, dest="cpu_sample_slices",
                     help="slices of the workload the cpu_baseline leg of our arm runs on the host cores (~0.3 s per slice)")
-    ap.add_argument("--no-sub", action="store_false", dest="sub", help="skip the sub-records (C1, C4, c3, C5, medsam)")
+    ap.add_argument("--no-sub", action="store_false", dest="sub", help="skip the sub-records (C1, C4, c3, C5, medsam, augment)")
     ap.add_argument("--no-medsam", action="store_false", dest="medsam", help="skip the MedSAM sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
