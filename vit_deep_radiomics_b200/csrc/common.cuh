@@ -39,6 +39,10 @@ int  make_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64
     if (e__ != cudaSuccess) return ::vdr::cuda_fail(e__, what);        \
   } while (0)
 
+// sam_window_tc.cu: 14 x 14 windows with decomposed rel-pos bias on tcgen05
+int  launch_attn_win14_tc(const void* qkv, int64_t ld_qkv, const float* qkv_bias, const void* rcat_hi, const void* rcat_lo, void* out,
+                          int64_t ld_out, int B, int gh, int gw, int heads, float scale, cudaStream_t s);
+
 // One flag per CUDA device: cudaFuncSetAttribute & co. are per-device state, a process may drive several devices.
 struct DeviceFlags {
   bool f[64] = {};

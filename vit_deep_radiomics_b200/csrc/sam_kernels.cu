@@ -737,6 +737,11 @@ extern "C" int vdr_attn_relpos_windows_fwd(const void* qkv_bf16, int64_t ld_qkv,
   const int nwh = (gh + ws - 1) / ws, nww = (gw + ws - 1) / ws;
   const int64_t BW = (int64_t)B * nwh * nww;
   VDR_CHECK_ARG(BW <= 65535, VDR_EINVAL, "vdr_attn_relpos_windows_fwd: %lld windows exceed the grid limit (65535): split the batch", (long long)BW);
+  // SAM's own window size: the tcgen05 kernel (sam_window_tc.cu); VDR_SAM_WIN_MMA_SYNC=1 keeps the mma.sync kernel below for A/B runs
+  static const bool legacy = getenv("VDR_SAM_WIN_MMA_SYNC") != nullptr;
+  if (ws == 14 && !legacy)
+    return launch_attn_win14_tc(qkv_bf16, ld_qkv, qkv_bias, rcat_hi_bf16, rcat_lo_bf16, out_bf16, ld_out, B, gh, gw, heads, scale,
+                                reinterpret_cast<cudaStream_t>(stream));
   const int rp0 = ((ws + 1) & ~1) + ws;
   const int RP = rp0 + (8 - rp0 % 32 + 32) % 32;
   const size_t smem_w = (2 * (size_t)kWinRows * kRpPitch + 2 * (size_t)kRpTile) * sizeof(__nv_bfloat16) + (size_t)kWinQ * RP * sizeof(float);
