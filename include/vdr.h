@@ -53,13 +53,15 @@ uint64_t    vdr_launch_count(void);
  * 187-199; active under model.train(), train_models.py:652).  Counter based: element (row r, column c) of dropout site `site` is
  * KEPT iff the 16-bit lane (c & 7) of Philox4x32-10(counter = (c >> 3, r_lo, r_hi, site), key = (seed_lo, seed_hi)) is >= thr16,
  * and kept values are multiplied by 65536 / (65536 - thr16): p = thr16 / 65536.  The backward kernels regenerate the masks from
- * the same (seed, site), nothing is stored.  thr16 == 0 (or a NULL pointer) = no dropout, bit-identical to the p = 0 path.
+ * the same (seed + *seed_offset, site), nothing is stored.  thr16 == 0 (or a NULL pointer) = no dropout, bit-identical to the p = 0 path.
  * RNG streams cannot match PyTorch's: parity is statistical (keep rate, 1 / (1 - p) scale) plus exact gradients against fp32
  * autograd with the mask exported by vdr_dropout_mask. */
 typedef struct {
   uint64_t seed;
   uint32_t site;
   uint32_t thr16;
+  const uint64_t* seed_offset;   /* optional DEVICE scalar added to `seed` by the kernels (NULL = 0): a training step captured in a
+                                    CUDA graph bumps it on the device, so every replay draws fresh masks from a fixed launch */
 } vdr_dropout;
 /* out = x * mask / (1 - p): bf16 (rows, cols) with row pitches ldx / ldo (elements), cols % 8 == 0.  The backward of a dropout
  * that the forward applied inside a GEMM epilogue. */
@@ -426,6 +428,11 @@ int vdr_relpos_tables(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_
                       int Sh, int Sw, int heads, float out_scale, vdr_stream_t stream);
 int vdr_flash_attn_relpos_fwd(const void* qkv, int64_t ld_qkv, const float* rel_log2, void* out, int64_t ld_out, int B, int Sh,
                               int heads, float scale, vdr_stream_t stream);
+/* vdr_flash_attn_relpos_fwd without the table: the kernel computes its rows' bias terms itself (Q [R_hi ; R_lo]^T on the tensor cores
+ * into TMEM before the first key block).  Token grids of Sh x 64, Sh % 4 == 0, Sh <= 64; rcat_* = the split [rel_pos_h ; rel_pos_w]
+ * tables ((2*Sh-1) + 127 rows of 64).  Replaces vdr_relpos_tables + vdr_flash_attn_relpos_fwd for SAM's global-attention blocks. */
+int vdr_flash_attn_relpos_fused_fwd(const void* qkv, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, void* out,
+                                    int64_t ld_out, int B, int Sh, int heads, float scale, vdr_stream_t stream);
 int vdr_attn_relpos_fwd(const void* qkv_bf16, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, void* out_bf16,
                         int64_t ld_out, int BW, int Sh, int Sw, int heads, float scale, vdr_stream_t stream);
 /* Windowed attention straight on the un-partitioned token rows of B images of gh x gw tokens (window_partition, the attention

@@ -79,7 +79,7 @@ def test_attn_relpos_vs_fp32(cuda, BW, Sh, Sw, heads):
 @pytest.mark.parametrize("BW,Sh,heads", [(1, 64, 2), (2, 64, 12), (3, 4, 1), (1, 8, 3)])
 def test_flash_attn_relpos_tcgen05_vs_fp32(cuda, BW, Sh, heads):
     """The tcgen05 flash kernel with the bias (token grids of Sh x 64): against fp32 and against the mma.sync kernel."""
-    from vit_deep_radiomics_b200 import ops
+    from vit_deep_radiomics_b200 import _C, ops
     Sw = 64
     g = torch.Generator().manual_seed(77 + BW + Sh)
     N, d = Sh * Sw, heads * 64
@@ -95,6 +95,15 @@ def test_flash_attn_relpos_tcgen05_vs_fp32(cuda, BW, Sh, heads):
     cos = F.cosine_similarity(got.reshape(-1, 64), want.reshape(-1, 64), dim=1).min()
     assert err < 2e-2 and cos > 0.9995, (float(err), float(cos))
     assert (got - ref2).abs().max() < 2e-2
+    # the same kernel computing its own bias terms (no table, one launch): what the encoder runs
+    n0 = _C.launch_count()
+    fused = ops.attn_relpos(qkv.to(cuda), BW, Sh, Sw, heads, hi, lo, kernel="fused").cpu().float()
+    assert _C.launch_count() - n0 == 1
+    assert torch.isfinite(fused).all()
+    err = (fused - want).abs().max()
+    cos = F.cosine_similarity(fused.reshape(-1, 64), want.reshape(-1, 64), dim=1).min()
+    assert err < 2e-2 and cos > 0.9995, (float(err), float(cos))
+    assert (fused - got).abs().max() < 1e-2            # table in f32 vs terms straight from the accumulator: fp16 rounding of rel_w either way
     with pytest.raises(ValueError):      # Sh = 2: not a multiple of 4 -> the tcgen05 variant refuses, it never falls back silently
         hi2, lo2 = ops.relpos_split(torch.zeros(3, 64, device=cuda), torch.zeros(127, 64, device=cuda))
         ops.attn_relpos(qkv.to(cuda)[:128], 1, 2, Sw, heads, hi2, lo2, kernel="tcgen05")

@@ -25,7 +25,7 @@ EXPORTS = (
     "vdr_gelu_fwd", "vdr_gelu_bwd", "vdr_transpose_bf16", "vdr_colsum_bf16", "vdr_attn_delta", "vdr_attn_p_ds",
     "vdr_cls_concat_layernorm_bwd", "vdr_cls_head_fwd", "vdr_cls_head_bwd",
     "vdr_linear_vec_fwd", "vdr_linear_vec_bwd", "vdr_cross_cls_attn_fwd", "vdr_cross_cls_attn_bwd",
-    "vdr_window_rows", "vdr_relpos_tables", "vdr_attn_relpos_fwd", "vdr_flash_attn_relpos_fwd", "vdr_attn_relpos_windows_fwd", "vdr_im2col3x3_tokens",
+    "vdr_window_rows", "vdr_relpos_tables", "vdr_attn_relpos_fwd", "vdr_flash_attn_relpos_fwd", "vdr_flash_attn_relpos_fused_fwd", "vdr_attn_relpos_windows_fwd", "vdr_im2col3x3_tokens",
 )
 
 
@@ -45,7 +45,7 @@ class VitWeights(C.Structure):
 
 class Dropout(C.Structure):
     """== vdr_dropout (include/vdr.h): counter-based dropout site; thr16 = round(p * 65536), 0 = off"""
-    _fields_ = [("seed", C.c_uint64), ("site", C.c_uint32), ("thr16", C.c_uint32)]
+    _fields_ = [("seed", C.c_uint64), ("site", C.c_uint32), ("thr16", C.c_uint32), ("seed_offset", C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
@@ -142,6 +142,7 @@ def lib() -> C.CDLL:
     L.vdr_window_rows.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     L.vdr_relpos_tables.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, f32, vp]
     L.vdr_flash_attn_relpos_fwd.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, f32, vp]
+    L.vdr_flash_attn_relpos_fused_fwd.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, f32, vp]
     L.vdr_attn_relpos_fwd.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp]
     L.vdr_attn_relpos_windows_fwd.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp]
     L.vdr_im2col3x3_tokens.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp]

@@ -73,17 +73,18 @@ class DropCfg:
     """Dropout of one forward pass: ``seed`` (fresh per pass), rate ``p`` of the encoder layers, rate ``p_head`` of the MLPLayer
     heads, ``base`` = first site id of an encoder (two encoders of the bimodal model must not share sites)."""
 
-    def __init__(self, seed: int, p: float, p_head: float, base: int = 0):
+    def __init__(self, seed: int, p: float, p_head: float, base: int = 0, seed_offset: torch.Tensor | None = None):
         self.seed, self.p, self.p_head, self.base = int(seed), float(p), float(p_head), int(base)
+        self.seed_offset = seed_offset          # device scalar added to the seed by the kernels (CUDA-graph replays; ops.Drop)
 
     def site(self, layer: int, k: int):
-        return ops.Drop(self.seed, self.base + 4 * layer + k, self.p) if self.p > 0 else None
+        return ops.Drop(self.seed, self.base + 4 * layer + k, self.p, self.seed_offset) if self.p > 0 else None
 
     def head(self, idx: int = 0):
-        return ops.Drop(self.seed, 1_000_000 + idx, self.p_head) if self.p_head > 0 else None
+        return ops.Drop(self.seed, 1_000_000 + idx, self.p_head, self.seed_offset) if self.p_head > 0 else None
 
     def with_base(self, base: int):
-        return DropCfg(self.seed, self.p, self.p_head, base)
+        return DropCfg(self.seed, self.p, self.p_head, base, self.seed_offset)
 
 
 def new_seed() -> int:

@@ -256,9 +256,15 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
 // few units -> 1e-3 absolute in the exponent, below the bf16 rounding of P).
 __device__ unsigned int g_attn_sm_ticket[1024];   // experiment (VDR_ATTN_DBG >= 100): alternate start delay per SM slot
 
-template <bool kBias, bool kDrop = false>
+// kFused (with kBias): the bias terms are not read from a table in HBM but computed by the CTA itself before its first key
+// block -- T = Q [R_hi ; R_lo]^T on the tensor cores into the (still unused) TMEM columns: q . rel_pos_h[i] for the 64-row
+// windows of rel_pos_h that belong to the tile's two grid rows (columns 0..63 / 64..127) and q . rel_pos_w[i] for all 127
+// offsets (columns 128..255); the R tiles borrow the K / V ring.  Each softmax thread keeps its row's 64 rel_h terms in a local
+// array (one load per key block, a block ahead) and scatters its half of the rel_w terms into the fp16 tile in shared memory.
+template <bool kBias, bool kDrop = false, bool kFused = false>
 __global__ void __launch_bounds__(kAttnThreads, 2)
-flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmRhi,
+                      const __grid_constant__ CUtensorMap tmRlo, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   // layout: Q | ring0..3 | barriers | max exchange [2 buffers][2 halves][128] | sum exchange [2 halves][128]
@@ -271,7 +277,10 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
   uint64_t* bar_sfree = bars + 7;    // S_j is in registers               (8 softmax warps arrive)
   uint64_t* bar_pready = bars + 8;   // P_j is in TMEM, O rescaled        (8 softmax warps arrive)
   uint64_t* bar_tail = bars + 9;     // trailing keys' K / V rows are in shared memory (warp 10 arrives)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_r = bars + 10;       // kFused: the rel-pos table tiles landed (in the K / V ring)
+  uint64_t* bar_t = bars + 11;       // kFused: T = Q R^T complete
+  uint64_t* bar_tread = bars + 12;   // kFused: T is in registers / shared memory (8 softmax warps arrive): its columns become S, O, P
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
   float* s_max = reinterpret_cast<float*>(smem + 5 * kTileBytes + 256);   // [2][2][128]
   float* s_sum = s_max + 2 * 2 * 128;                                      // [2][128]
   uint4* s_tail = reinterpret_cast<uint4*>(s_sum + 2 * 128);               // [tail_keys][K row (8 x 16 B) | V row (8 x 16 B)]
@@ -318,14 +327,32 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     mbar_init(bar_sfree, kSoftmaxWarps);
     mbar_init(bar_pready, kSoftmaxWarps);
     mbar_init(bar_tail, 1);
+    mbar_init(bar_r, 1);
+    mbar_init(bar_t, 1);
+    mbar_init(bar_tread, kSoftmaxWarps);
     fence_barrier_init();
     mbar_arrive_expect_tx(bar_q, kTileBytes);
     tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
-    issue_tile(0);
-    issue_tile(1);
-    if (nkv > 1) {
-      issue_tile(2);
-      issue_tile(3);
+    if (kFused) {
+      // ring slot 0: rel_pos_h rows [qh, qh + 64) for the tile's first grid row (hi | lo), slot 1: the same for qh + 1,
+      // slots 2 / 3: rel_pos_w (127 rows -> 128) hi / lo.  rel_h[q, kh] = q . rel_pos_h[qh - kh + Sh - 1] = T[Sh - 1 - kh].
+      const int qh = q0 >> 6, rw0 = 2 * (p.N >> 6) - 1;
+      mbar_arrive_expect_tx(bar_r, 4 * kTileBytes);
+      tma_load_2d(&tmRhi, bar_r, smem + kTileBytes, 0, qh);
+      tma_load_2d(&tmRlo, bar_r, smem + kTileBytes + 8192, 0, qh);
+      tma_load_2d(&tmRhi, bar_r, smem + 2 * kTileBytes, 0, qh + 1);
+      tma_load_2d(&tmRlo, bar_r, smem + 2 * kTileBytes + 8192, 0, qh + 1);
+      tma_load_2d(&tmRhi, bar_r, smem + 3 * kTileBytes, 0, rw0);
+      tma_load_2d(&tmRhi, bar_r, smem + 3 * kTileBytes + 8192, 0, rw0 + 64);
+      tma_load_2d(&tmRlo, bar_r, smem + 4 * kTileBytes, 0, rw0);
+      tma_load_2d(&tmRlo, bar_r, smem + 4 * kTileBytes + 8192, 0, rw0 + 64);
+    } else {
+      issue_tile(0);
+      issue_tile(1);
+      if (nkv > 1) {
+        issue_tile(2);
+        issue_tile(3);
+      }
     }
   }
   if (warp == 0) tmem_alloc<kAttnTmemCols>(tmem_ptr);
@@ -363,6 +390,39 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
         __syncwarp();
       };
       mbar_wait_relaxed(bar_q, 0);
+      if (kFused) {
+        mbar_wait_relaxed(bar_r, 0);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dq = umma_desc_kmajor_sw128(sQ);
+          constexpr uint32_t id64 = umma_idesc_bf16(128, 64), id128 = umma_idesc_bf16(128, 128);
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {        // hi, then lo into the same accumulators
+            const uint64_t da = umma_desc_kmajor_sw128(sRing + part * 8192), db = umma_desc_kmajor_sw128(sRing + kTileBytes + part * 8192);
+            const uint64_t dw = umma_desc_kmajor_sw128(sRing + (2 + part) * kTileBytes);
+#pragma unroll
+            for (int k = 0; k < kHD / 16; ++k) {
+              umma_ss(tmem_base, dq + 2 * k, da + 2 * k, id64, (part | k) != 0);
+              umma_ss(tmem_base + 64, dq + 2 * k, db + 2 * k, id64, (part | k) != 0);
+              umma_ss(tmem_base + 128, dq + 2 * k, dw + 2 * k, id128, (part | k) != 0);
+            }
+          }
+          umma_commit(bar_t);
+        }
+        __syncwarp();
+        mbar_wait_relaxed(bar_t, 0);                       // the ring is free again: start the K / V stream
+        if (elect_one()) {
+          issue_tile(0);
+          issue_tile(1);
+          if (nkv > 1) {
+            issue_tile(2);
+            issue_tile(3);
+          }
+        }
+        __syncwarp();
+        mbar_wait_relaxed(bar_tread, 0);                   // every softmax warp has taken its terms out of T
+        tc_fence_after();
+      }
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         if (lane == 0) ISS_TRACE(0);
@@ -460,7 +520,38 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     const unsigned char* bw_row = smem + kAttnSmem + row * kBiasPitch;     // kBias: this query row's 64 rel_w terms (fp16)
     const float* rel_row = nullptr;
     float bh_next = 0.f;
-    if (kBias) {
+    float rh_loc[64];                                                      // kFused: this row's rel_h terms (log2 domain), index Sh - 1 - kh
+    const int Sh = p.N >> 6;
+    if (kFused) {
+      mbar_wait(bar_t, 0);
+      tc_fence_after();
+      const int qw = row & 63;
+      unsigned char* brow = smem + kAttnSmem + row * kBiasPitch;
+      uint32_t u[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32b_x32(tmem_base + lane_sel + (row & 64) + 32 * c, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rh_loc[32 * c + i] = __uint_as_float(u[i]) * 1.4426950408889634f;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32b_x32(tmem_base + lane_sel + 128 + half * 64 + 32 * c, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {                                     // rel_w[q, kw] = q . rel_pos_w[qw - kw + 63] = T_w[qw + 63 - kw]
+          const int jj = qw + 63 - (half * 64 + 32 * c + i);
+          if (static_cast<unsigned>(jj) < 64u)
+            *reinterpret_cast<__half*>(brow + 2 * jj) = __float2half_rn(__uint_as_float(u[i]) * 1.4426950408889634f);
+        }
+      }
+      tc_fence_before();
+      pair_bar_sync(quarter);                                              // both halves of the row are written, both have read T
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tread);
+      bh_next = rh_loc[Sh - 1 - half];
+    } else if (kBias) {
       rel_row = p.rel + (static_cast<int64_t>(b * p.heads + head) * p.N + q0 + row) * p.rel_pitch;
       const float4* src = reinterpret_cast<const float4*>(rel_row + (p.rel_pitch - 64) + half * 32);   // this thread converts 32 of the 64
       uint2* dst = reinterpret_cast<uint2*>(smem + kAttnSmem + row * kBiasPitch + half * 64);
@@ -477,7 +568,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParam
     for (int j = 0; j < nkv; ++j) {
       ATT_TRACE(0);
       const float bh_cur = bh_next;
-      if (kBias && j + 1 < nkv) bh_next = __ldg(rel_row + 2 * (j + 1) + half);
+      if (kFused) {
+        if (j + 1 < nkv) bh_next = rh_loc[Sh - 1 - (2 * (j + 1) + half)];
+      } else if (kBias && j + 1 < nkv) {
+        bh_next = __ldg(rel_row + 2 * (j + 1) + half);
+      }
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       ATT_TRACE(1);
@@ -1044,7 +1139,8 @@ static unsigned long long* g_attn_trace = nullptr;
 extern "C" void vdr_debug_set_attn_trace(void* device_buf) { g_attn_trace = static_cast<unsigned long long*>(device_buf); }
 
 static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, const float* rel, int rel_pitch, void* out, int64_t ld_out,
-                             float* lse, int B, int N, int heads, float scale, const vdr_dropout* drop, vdr_stream_t stream) {
+                             float* lse, int B, int N, int heads, float scale, const vdr_dropout* drop, vdr_stream_t stream,
+                             const void* rcat_hi = nullptr, const void* rcat_lo = nullptr) {
   using namespace vdr;
   VDR_CHECK_ARG(qkv && out, VDR_EINVAL, "%s: null pointer", who);
   VDR_CHECK_ARG(B > 0 && N > 0 && heads > 0, VDR_EINVAL, "%s: bad shape B=%d N=%d heads=%d", who, B, N, heads);
@@ -1057,16 +1153,26 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   static const bool want_v6 = getenv("VDR_ATTN_V6") != nullptr;
   const bool dropout = drop != nullptr && drop->thr16 != 0;
   VDR_CHECK_ARG(!dropout || (rel == nullptr && drop->thr16 < 65536u), VDR_EINVAL, "%s: attention dropout needs thr16 < 65536 and no rel-pos bias", who);
-  const bool v6 = rel == nullptr && want_v6 && !dropout;
-  CUtensorMap tm;
+  const bool fused = rcat_hi != nullptr;
+  const bool v6 = rel == nullptr && want_v6 && !dropout && !fused;
+  CUtensorMap tm, tm_rhi, tm_rlo;
   int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * d, (uint64_t)ld_qkv, v6 ? kV6BK : 128, kHD);
   if (rc != VDR_OK) return rc;
+  tm_rhi = tm;
+  tm_rlo = tm;
+  if (fused) {   // [rel_pos_h (2 Sh - 1) ; rel_pos_w (127)] x 64, 64-row boxes
+    const uint64_t rows = 2ull * (N / 64) - 1 + 127;
+    rc = make_tmap_2d_bf16(&tm_rhi, rcat_hi, rows, 64, 64, 64, 64);
+    if (rc == VDR_OK) rc = make_tmap_2d_bf16(&tm_rlo, rcat_lo, rows, 64, 64, 64, 64);
+    if (rc != VDR_OK) return rc;
+  }
   static DeviceFlags configured;
   if (!configured.current()) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV6Smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_fwd)");
     configured.current() = true;
   }
@@ -1082,8 +1188,8 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   p.dbg = getenv("VDR_ATTN_DBG") ? atoi(getenv("VDR_ATTN_DBG")) : 0;
   p.rel = rel;
   p.rel_pitch = rel_pitch;
-  p.drop = DropSpec{0ull, 0u, 0u};
-  if (dropout) p.drop = DropSpec{drop->seed, drop->site, drop->thr16};
+  p.drop = DropSpec{0ull, 0u, 0u, nullptr};
+  if (dropout) p.drop = DropSpec{drop->seed, drop->site, drop->thr16, reinterpret_cast<const unsigned long long*>(drop->seed_offset)};
   // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head)
   // v5: full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head).
   // v6: its CTAs are a quarter of an SM, so a trailing tile with a single valid row costs less than the CUDA-core CTA did
@@ -1097,14 +1203,16 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   p.tail_rows = vector_tail ? tail_rows : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.q_tiles + (vector_tail ? 1 : 0), heads, B);
-  if (rel != nullptr)
-    flash_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, p);
+  if (fused)
+    flash_attn_fwd_kernel<true, false, true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, tm_rhi, tm_rlo, p);
+  else if (rel != nullptr)
+    flash_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, tm_rhi, tm_rlo, p);
   else if (dropout)
-    flash_attn_fwd_kernel<false, true><<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
+    flash_attn_fwd_kernel<false, true><<<grid, kAttnThreads, kAttnSmem, s>>>(tm, tm_rhi, tm_rlo, p);
   else if (v6)
     flash_attn_fwd_v6_kernel<<<grid, kV6Threads, kV6Smem, s>>>(tm, p);
   else
-    flash_attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmem, s>>>(tm, p);
+    flash_attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmem, s>>>(tm, tm_rhi, tm_rlo, p);
   count_launch();
   VDR_CHECK_LAUNCH("flash_attn_fwd_kernel");
   return VDR_OK;
@@ -1121,4 +1229,17 @@ extern "C" int vdr_flash_attn_relpos_fwd(const void* qkv, int64_t ld_qkv, const 
   VDR_CHECK_ARG(rel_log2 != nullptr && aligned16(rel_log2), VDR_EINVAL, "vdr_flash_attn_relpos_fwd: rel table must be a 16-byte aligned device pointer");
   VDR_CHECK_ARG(Sh > 0 && Sh % 4 == 0 && Sh <= 1020, VDR_EINVAL, "vdr_flash_attn_relpos_fwd: the token grid must be Sh x 64 with Sh a multiple of 4 (Sh = %d)", Sh);
   return launch_flash_attn("vdr_flash_attn_relpos_fwd", qkv, ld_qkv, rel_log2, Sh + 64, out, ld_out, nullptr, B, Sh * 64, heads, scale, nullptr, stream);
+}
+
+// The same with the bias terms computed by the kernel itself from the split tables (no table in HBM, no vdr_relpos_tables
+// launch): rcat_hi / rcat_lo = [rel_pos_h (2 Sh - 1, 64) ; rel_pos_w (127, 64)] as bf16 hi + lo parts.
+extern "C" int vdr_flash_attn_relpos_fused_fwd(const void* qkv, int64_t ld_qkv, const void* rcat_hi_bf16, const void* rcat_lo_bf16, void* out,
+                                               int64_t ld_out, int B, int Sh, int heads, float scale, vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(rcat_hi_bf16 != nullptr && rcat_lo_bf16 != nullptr && aligned16(rcat_hi_bf16) && aligned16(rcat_lo_bf16), VDR_EINVAL,
+                "vdr_flash_attn_relpos_fused_fwd: the split tables must be 16-byte aligned device pointers");
+  VDR_CHECK_ARG(Sh > 0 && Sh % 4 == 0 && Sh <= 64, VDR_EINVAL,
+                "vdr_flash_attn_relpos_fused_fwd: the token grid must be Sh x 64 with Sh a multiple of 4, Sh <= 64 (Sh = %d)", Sh);
+  return launch_flash_attn("vdr_flash_attn_relpos_fused_fwd", qkv, ld_qkv, nullptr, 0, out, ld_out, nullptr, B, Sh * 64, heads, scale, nullptr, stream,
+                           rcat_hi_bf16, rcat_lo_bf16);
 }

@@ -306,10 +306,10 @@ extern "C" int vdr_flash_attn_bwd(const void* qkv, int64_t ld_qkv, const void* O
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld_dqkv = ld_dqkv;
   p.B = B; p.N = N; p.heads = heads; p.d = d;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  p.drop = DropSpec{0ull, 0u, 0u};
+  p.drop = DropSpec{0ull, 0u, 0u, nullptr};
   if (drop != nullptr && drop->thr16 != 0) {
     VDR_CHECK_ARG(drop->thr16 < 65536u, VDR_EINVAL, "vdr_flash_attn_bwd: dropout threshold must be < 65536");
-    p.drop = DropSpec{drop->seed, drop->site, drop->thr16};
+    p.drop = DropSpec{drop->seed, drop->site, drop->thr16, reinterpret_cast<const unsigned long long*>(drop->seed_offset)};
   }
   dim3 grid((N + kBT - 1) / kBT, heads, B);
   flash_attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, s>>>(tmQKV, tmDO, p);

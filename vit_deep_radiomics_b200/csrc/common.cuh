@@ -524,6 +524,7 @@ struct DropSpec {
   unsigned long long seed;
   uint32_t site;
   uint32_t thr16;
+  const unsigned long long* seed_offset;   // device scalar added to the seed (nullptr = 0): see vdr_dropout
 };
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -538,8 +539,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 // the eight 16-bit lanes of columns [c8 * 8, c8 * 8 + 8) of row `row`
 __device__ __forceinline__ uint4 drop_bits8(const DropSpec& d, uint64_t row, uint32_t c8) {
+  const unsigned long long seed = d.seed + (d.seed_offset != nullptr ? __ldg(d.seed_offset) : 0ull);
   return philox4x32_10(make_uint4(c8, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), d.site),
-                       make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
+                       make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
 }
 __device__ __forceinline__ uint32_t drop_lane16(const uint4& bits, int lane8) {
   const uint32_t w = lane8 < 2 ? bits.x : lane8 < 4 ? bits.y : lane8 < 6 ? bits.z : bits.w;

@@ -735,7 +735,7 @@ static int gemm_impl(const vdr_gemm_args* a, const Im2colSpec* ic, vdr_stream_t 
   p.stats_out = reinterpret_cast<float2*>(a->stats_out);
   p.trace = g_trace;
   p.dbg = getenv("VDR_GEMM_DBG") ? atoi(getenv("VDR_GEMM_DBG")) : 0;
-  p.drop = DropSpec{a->drop.seed, a->drop.site, a->drop.thr16};
+  p.drop = DropSpec{a->drop.seed, a->drop.site, a->drop.thr16, reinterpret_cast<const unsigned long long*>(a->drop.seed_offset)};
   p.a_im2col = ic ? 1 : 0;
   p.ic_patch = p.ic_gw = p.ic_np = p.ic_chan = p.ic_kb_per_chan = 1;
   if (ic) {

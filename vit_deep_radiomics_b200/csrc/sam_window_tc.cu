@@ -128,7 +128,7 @@ attn_win14_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* bar_fix = bars + 8;    // pad tokens overwritten (128 arrivals)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int half = blockIdx.x, head = blockIdx.y;
   const int win = blockIdx.z;
   const int wx = win % p.nww, wy = (win / p.nww) % p.nwh, b = win / (p.nww * p.nwh);

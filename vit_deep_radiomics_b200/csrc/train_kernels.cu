@@ -435,8 +435,8 @@ static int check_drop(const char* who, const vdr_dropout* d, int64_t n, int cols
   return VDR_OK;
 }
 static vdr::DropSpec drop_spec(const vdr_dropout* d) {
-  vdr::DropSpec s{0ull, 0u, 0u};
-  if (d != nullptr) { s.seed = d->seed; s.site = d->site; s.thr16 = d->thr16; }
+  vdr::DropSpec s{0ull, 0u, 0u, nullptr};
+  if (d != nullptr) { s.seed = d->seed; s.site = d->site; s.thr16 = d->thr16; s.seed_offset = reinterpret_cast<const unsigned long long*>(d->seed_offset); }
   return s;
 }
 

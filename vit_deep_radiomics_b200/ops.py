@@ -54,20 +54,24 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 class Drop:
     """One dropout site of a training step (include/vdr.h, vdr_dropout): ``seed`` per forward pass, ``site`` per dropout
     module, ``p`` the module's rate.  The kernels regenerate the mask from (seed, site); nothing is stored."""
-    __slots__ = ("seed", "site", "thr16")
+    __slots__ = ("seed", "site", "thr16", "seed_offset")
 
-    def __init__(self, seed: int, site: int, p: float):
+    def __init__(self, seed: int, site: int, p: float, seed_offset: torch.Tensor | None = None):
         if not 0.0 <= p < 1.0:
             raise ValueError(f"dropout probability has to be in [0, 1), got {p}")
         self.seed, self.site = int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF
         self.thr16 = min(65535, int(round(p * 65536)))
+        # optional one-element int64 CUDA tensor the kernels add to the seed (a CUDA-graph replay bumps it on the device)
+        if seed_offset is not None and (not seed_offset.is_cuda or seed_offset.dtype != torch.int64 or seed_offset.numel() != 1):
+            raise ValueError("seed_offset must be a one-element int64 CUDA tensor")
+        self.seed_offset = seed_offset
 
     @property
     def p(self) -> float:
         return self.thr16 / 65536.0
 
     def c(self):
-        return _C.Dropout(self.seed, self.site, self.thr16)
+        return _C.Dropout(self.seed, self.site, self.thr16, self.seed_offset.data_ptr() if self.seed_offset is not None else None)
 
 
 def _dp(drop):
@@ -811,16 +815,22 @@ def attn_relpos(qkv: torch.Tensor, BW: int, Sh: int, Sw: int, heads: int, rcat_h
     """Attention with SAM's decomposed relative-position bias over BW images/windows of Sh x Sw tokens.
     qkv (BW*Sh*Sw, 3*heads*64) bf16; (rcat_hi, rcat_lo) = relpos_split(rel_pos_h (2*Sh-1, 64), rel_pos_w (2*Sw-1, 64))
     -> out (BW*Sh*Sw, heads*64) bf16.
-    kernel: "tcgen05" = bias table (vdr_relpos_tables, log2 domain; `rel` = optional f32 scratch of BW*heads*N*(Sh+Sw)) +
-    the tcgen05 flash kernel with bias (token grids of Sh x 64, Sh % 4 == 0: the global-attention blocks); "mma" = the one-launch
-    mma.sync kernel that builds the bias on chip (any extent: the 14 x 14 windows); "auto" picks tcgen05 where it applies."""
+    kernel: "fused" = the tcgen05 flash kernel computing its own bias terms (one launch, no table; token grids of Sh x 64,
+    Sh % 4 == 0, Sh <= 64: the global-attention blocks); "tcgen05" = bias table (vdr_relpos_tables, log2 domain; `rel` = optional
+    f32 scratch of BW*heads*N*(Sh+Sw)) + the same kernel reading it; "mma" = the one-launch mma.sync kernel that builds the bias on
+    chip (any extent); "auto" picks "fused" where it applies."""
     N, d = _check_relpos_args(qkv, BW, Sh, Sw, heads, rcat_hi, rcat_lo)
     if scale is None:
         scale = 1.0 / math.sqrt(64)
     if out is None:
         out = torch.empty((BW * N, d), dtype=torch.bfloat16, device=qkv.device)
     if kernel == "auto":
-        kernel = "tcgen05" if (Sw == 64 and Sh % 4 == 0) else "mma"
+        kernel = "fused" if (Sw == 64 and Sh % 4 == 0 and Sh <= 64) else ("tcgen05" if (Sw == 64 and Sh % 4 == 0) else "mma")
+    if kernel == "fused":
+        with _Prof("attn", 4.0 * BW * heads * N * N * 64 + 2.0 * BW * heads * N * 256 * 64 * 2, f"attn+relpos fused BW{BW} N{N} h{heads}"):
+            _C.check(_C.lib().vdr_flash_attn_relpos_fused_fwd(qkv.data_ptr(), qkv.stride(0), rcat_hi.data_ptr(), rcat_lo.data_ptr(), out.data_ptr(),
+                                                              out.stride(0), BW, Sh, heads, float(scale), _stream()), "vdr_flash_attn_relpos_fused_fwd")
+        return out
     if kernel == "tcgen05":
         table = relpos_tables(qkv, BW, Sh, Sw, heads, rcat_hi, rcat_lo, out_scale=LOG2E, out=rel)
         with _Prof("attn", 4.0 * BW * heads * N * N * 64, f"attn+relpos tcgen05 BW{BW} N{N} h{heads}"):

@@ -186,7 +186,7 @@ class SamImageEncoder:
                       OUT=torch.empty(B * N, oc, dtype=torch.float32, device=dev))
             if not in_place:                                         # window_partition / unpartition copies of the explicit path
                 ws.update(YW=torch.empty(B * NW, d, dtype=bf, device=dev), OW=torch.empty(B * NW, d, dtype=bf, device=dev))
-            if gw == 64 and gh % 4 == 0 and self.global_attn_kernel != "mma":       # bias table of the tcgen05 global attention
+            if gw == 64 and gh % 4 == 0 and self.global_attn_kernel == "tcgen05":   # bias table of the table-reading tcgen05 kernel (A/B)
                 ws["REL"] = torch.empty(B * cfg["heads"] * N * (gh + gw), dtype=torch.float32, device=dev)
             self._ws = {B: ws}
         return ws
@@ -197,7 +197,8 @@ class SamImageEncoder:
     #: windowed blocks read their windows in place (vdr_attn_relpos_windows_fwd); False = window_partition / unpartition copies
     windows_in_place = True
 
-    #: "auto" (tcgen05 flash kernel with bias where the token grid is Sh x 64, else mma.sync) | "mma" (A/B timing, parity tests)
+    #: "auto" (tcgen05 flash kernel computing its own bias terms where the token grid is Sh x 64, else mma.sync) | "tcgen05" (the same
+    #: kernel reading a bias table from vdr_relpos_tables) | "mma" (A/B timing, parity tests)
     global_attn_kernel = "auto"
 
     # -- forward -----------------------------------------------------------------------------
