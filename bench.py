@@ -452,22 +452,23 @@ def bench_classifier(D: Dist, samples: int = 64, epochs: int = 2, cpu_samples: i
     data = [(torch.from_numpy(cloud(i)).to(dev), torch.eye(2, device=dev)[int(labels[i])]) for i in mine]
     window = max(1, 32 // world)
     bucket = grad_bucket(model)
+    from vit_deep_radiomics_b200.graph_step import graphed_step
+    step = graphed_step(model, crit)          # forward + loss + backward of a sample as one CUDA graph per cloud length
 
     def epoch():
         zero_grads(model, opt)
         tot = torch.zeros((), device=dev)
         for k, (x, y) in enumerate(data):
-            logits, _ = model(x.unsqueeze(0))
-            loss = crit(torch.squeeze(logits), y) / 32                      # train_models.py:674
-            loss.backward()
-            tot += loss.detach()
+            loss, _ = step(x, y, 1.0 / 32)                                   # loss / iters_to_accumulate, train_models.py:674
+            tot += loss
             if (k + 1) % window == 0 or k + 1 == len(data):                  # :685
                 allreduce_grads(model)
                 opt.step()
                 zero_grads(model, opt)
         return tot
 
-    l0 = float(epoch()) * 32 / len(data)
+    l0 = float(epoch()) * 32 / len(data)      # first visit of every length: eager
+    epoch()                                    # second visit: captured; from here on every sample is one graph launch
     n0 = _C.launch_count()
     ms, tot = D.timed(epoch, epochs)
     launches = _C.launch_count() - n0
@@ -475,7 +476,9 @@ def bench_classifier(D: Dist, samples: int = 64, epochs: int = 2, cpu_samples: i
     rec = {"workload": f"C3: TransformerNoduleClassifier(256, ff 1024, 4 heads, 2 layers) training on {samples} synthetic point clouds of 512..4096 tokens, "
                        f"virtual batch 32 split over {world} rank(s), AdamW, focal loss",
            "value": samples * epochs / (ms / 1e3), "unit": "samples/s", "ms_per_sample_per_gpu": ms / (epochs * len(data)),
-           "gpu_launches": int(launches), "loss_first_epoch": l0, "loss_last_epoch": l1}
+           "gpu_launches": int(launches), "loss_first_epoch": l0, "loss_last_epoch": l1,
+           "cuda_graphs": {"lengths_captured": len(step.graphs), "replays": step.replays, "eager_steps": step.eager, "pool_bytes": int(step.bytes),
+                           "note": "gpu_launches counts the library's launch calls; replayed graphs run the captured kernels without them"}}
     flops = sum(3.0 * _classifier_flops(int(sizes[i]) + 1, 256, 1024, 2) for i in range(samples)) * epochs
     peaks = measured_peaks()
     tfl = flops / (ms / 1e3) / 1e12
@@ -507,9 +510,7 @@ def bench_classifier(D: Dist, samples: int = 64, epochs: int = 2, cpu_samples: i
     def e2e_pass():
         zero_grads(model, opt)
         for k, (x, y) in enumerate(pin):
-            logits, _ = model(x.to(dev, non_blocking=True).unsqueeze(0))
-            loss = crit(torch.squeeze(logits), y.to(dev, non_blocking=True)) / 32
-            loss.backward()
+            loss, _ = step(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), 1.0 / 32)
             float(loss.item())                                               # :681 the reference reads the loss back every sample
         allreduce_grads(model)
         opt.step()
@@ -518,7 +519,7 @@ def bench_classifier(D: Dist, samples: int = 64, epochs: int = 2, cpu_samples: i
     ms_e, _ = D.timed(e2e_pass, 1)
     rec["e2e"] = {"value": world * len(pin) / (ms_e / 1e3), "unit": "samples/s",
                   "h2d_bytes_per_step": int(sum(x.numel() * 4 + 8 for x, _ in pin) / len(pin)), "d2h_bytes_per_step": 4,
-                  "api": "models_archs.TransformerNoduleClassifier.forward + FocalLoss + backward per sample from pinned host clouds, loss.item() per sample "
+                  "api": "graph_step.GraphedTrainStep (= train_models.train_epoch(cuda_graphs=True): TransformerNoduleClassifier.forward + FocalLoss + backward) per sample from pinned host clouds, loss.item() per sample "
                          "(as train_models.py:681), one optimizer step per 8 samples per rank"}
     return rec
 
@@ -551,16 +552,16 @@ def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4):
     labels = [torch.eye(2, device=dev)[i % 2] for i in range(2)]
     n_tok = 0
 
+    from vit_deep_radiomics_b200.graph_step import graphed_step
+    step = graphed_step(clf, crit)
+
     def run(k):
         nonlocal n_tok
         zero_grads(clf, opt)
         last = None
         for i, out in enumerate(ex.run([(img_pin, mask_pin, res)] * k, to_host=False)):
             n_tok = int(out["count"].item())                # the point cloud's size is data-dependent: one 4-byte read-back
-            logits, _ = clf(out["tokens"][:n_tok].unsqueeze(0))
-            loss = crit(torch.squeeze(logits), labels[i % 2]) / 32
-            loss.backward()
-            last = loss
+            last, _ = step(out["tokens"][:n_tok], labels[i % 2], 1.0 / 32)
             if (i + 1) % window == 0 or i + 1 == k:
                 allreduce_grads(clf)
                 opt.step()

@@ -245,6 +245,56 @@ def test_train_step_accumulation_semantics(cuda):
         assert (v.cpu() - sd[k].detach()).abs().max() < 3e-3, k     # 3 AdamW steps of lr 5e-4: updates ~1.5e-3
 
 
+def test_cuda_graph_training_step_equals_eager_step(cuda):
+    """graph_step.GraphedTrainStep: three epochs of the accumulation loop with the per-length CUDA graphs (first visit eager, second
+    visit captured + replayed, third visit replayed; weights change in between) give the weights of the eager loop (to the last bits) --
+    without dropout, and with train-mode dropout when the eager model draws from the same (seed, counter) sequence."""
+    from vit_deep_radiomics_b200 import classifier_kernels as ck
+    from vit_deep_radiomics_b200.graph_step import graphed_step
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleClassifier, set_dropout
+    from vit_deep_radiomics_b200.train_models import FocalLoss, train_epoch
+    gen = torch.Generator().manual_seed(5)
+    data = [(torch.randn(int(n), 128, generator=gen).to(cuda), torch.eye(2)[int(c)].to(cuda)) for n, c in [(200, 0), (77, 1), (200, 1), (131, 0), (77, 0)]]
+    crit = FocalLoss(alpha=torch.tensor([0.25, 0.75], device=cuda), gamma=2)
+    for p_drop in (0.0, 0.1):
+        out = []
+        for graphs in (False, True):
+            torch.manual_seed(1)
+            model = set_dropout(TransformerNoduleClassifier(128, 256, 2, 2, 2).to(cuda), p_drop, p_drop)
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01)
+            if p_drop > 0:
+                # one seed sequence for both runs: seed = base + (number of samples stepped so far), the graph's device counter
+                step = graphed_step(model, crit)
+                step.base_seed = 1234
+                if not graphs:
+                    k = [0]
+
+                    def override(m=model, k=k):
+                        k[0] += 1
+                        return ck.DropCfg(1234 + k[0], *m._drop_rates())
+                    model._drop_override = override
+                else:
+                    # eager visits inside the graphed loop must consume the counter as the captured ones do
+                    def eager(x, label, inv, s=step, m=model):
+                        s.seed_offset.add_(1)
+                        m._drop_override = lambda: ck.DropCfg(s.base_seed, *m._drop_rates(), seed_offset=s.seed_offset)
+                        try:
+                            return type(s)._eager(s, x, label, inv)
+                        finally:
+                            m._drop_override = None
+                    step._eager = eager
+            losses = [train_epoch(model, data, crit, opt, virtual_batch_size=2, cuda_graphs=graphs)[0] for _ in range(3)]
+            if graphs:
+                st = graphed_step(model, crit)
+                assert st.replays >= 9 and len(st.graphs) == 3, (st.replays, st.eager, len(st.graphs))
+            out.append((losses, {k_: v.clone() for k_, v in model.state_dict().items()}))
+        (l0, w0), (l1, w1) = out
+        # same kernels in the same order; the backward's float atomics (dq, LayerNorm column sums) make two runs differ in the last bits
+        assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-5, (p_drop, l0, l1)
+        for k_ in w0:
+            assert (w0[k_] - w1[k_]).abs().max() < 2e-5, (p_drop, k_, float((w0[k_] - w1[k_]).abs().max()))
+
+
 def test_train_epoch_bimodal_crossmodal_loss_matches_cpu_training(cuda, golden_dir):
     """The reference's bimodal loop (train_models.py:656-688 with loss_func 'crossmodal'): model(ct, pet) -> CrossModalFocalLoss on
     outputs[0], [2], [3] / iters, optimizer steps as in the unimodal loop -- against the fp32 oracle trained the same way on CPU."""

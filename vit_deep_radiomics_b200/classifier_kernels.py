@@ -43,12 +43,28 @@ def _cached(p: torch.Tensor, tag: str, make):
     key = (id(p), tag)
     hit = _CACHE.get(key)
     # the weak reference guards against id() reuse after a model has been freed
-    if hit is not None and hit[0]() is p and hit[1] == p._version and hit[2].device == p.device:
-        return hit[2]
+    if hit is not None and hit[0]() is p and hit[2].device == p.device:
+        if hit[1] == p._version:
+            return hit[2]
+        # the parameter was updated: refresh the copy IN PLACE -- a captured CUDA graph (graph_step.GraphedTrainStep) holds its address
+        val = make(p.detach())
+        if val.shape == hit[2].shape and val.dtype == hit[2].dtype:
+            hit[2].copy_(val)
+            _CACHE[key] = (hit[0], p._version, hit[2], make)
+            return hit[2]
     val = make(p.detach())
     # the entry dies with its parameter (one model per fold would otherwise leak two bf16 copies of every weight)
-    _CACHE[key] = (weakref.ref(p, lambda _r, k=key: _CACHE.pop(k, None)), p._version, val)
+    _CACHE[key] = (weakref.ref(p, lambda _r, k=key: _CACHE.pop(k, None)), p._version, val, make)
     return val
+
+
+def refresh_cache() -> None:
+    """Bring every cached operand copy up to date (in place).  The eager path does this lazily inside the forward; a replayed
+    CUDA graph runs no Python, so graph_step calls it before every replay (one pass over ~50 entries)."""
+    for key, hit in list(_CACHE.items()):
+        p = hit[0]()
+        if p is not None and hit[1] != p._version:
+            _cached(p, key[1], hit[3])
 
 
 def invalidate_cache() -> None:

@@ -94,11 +94,16 @@ class TransformerNoduleClassifier(nn.Module):
         built with (0.1 in every encoder sub-layer and on the attention probabilities, :135; 0.1 in the head, :139,187)."""
         if not self.training:
             return None
-        p_enc = float(self.transformer_encoder.layers[0].dropout.p)
-        p_head = float(self.classifier.dropout_rate)
+        p_enc, p_head = self._drop_rates()
         if p_enc <= 0 and p_head <= 0:
             return None
+        override = self.__dict__.get("_drop_override")        # graph_step: seed taken from a device counter during capture
+        if override is not None:
+            return override()
         return ck.DropCfg(ck.new_seed(), p_enc, p_head)
+
+    def _drop_rates(self):
+        return float(self.transformer_encoder.layers[0].dropout.p), float(self.classifier.dropout_rate)
 
     def param_list(self):
         """Parameters in the fixed order the kernels expect (see classifier_kernels.PARAM_ORDER)."""

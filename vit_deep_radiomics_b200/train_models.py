@@ -341,7 +341,7 @@ def make_optimizer(model, cfg, arch="transformer"):
     return opt, sched
 
 
-def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, grad_sync=None):
+def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, grad_sync=None, cuda_graphs=False):
     """One pass of the reference's accumulation loop (train_models.py:652-688).
 
     samples: iterable of (tokens (n, d) f32 CUDA, one-hot label (C,) f32 CUDA); for the bimodal model
@@ -350,22 +350,31 @@ def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, gra
     Loss is divided by iters_to_accumulate = min(virtual_batch, len(samples)) (:655,674); the optimizer
     steps every iters_to_accumulate samples and at the last sample (:685-687).  ``grad_sync`` (optional
     callable) is invoked right before each optimizer step: the data-parallel gradient all-reduce.
+    ``cuda_graphs``: unimodal model only -- forward + loss + backward of a sample run as one CUDA graph per token count
+    (graph_step.GraphedTrainStep: captured the second time a length is seen, same kernels in the same order as the eager step).
     Returns (mean loss, list of softmax scores)."""
     from .distributed import zero_grads
     samples = list(samples)
     iters = min(virtual_batch_size, len(samples))
     model.train()
+    step = None
+    if cuda_graphs and isinstance(model, TransformerNoduleClassifier) and not isinstance(criterion, CrossModalFocalLoss):
+        from .graph_step import graphed_step
+        step = graphed_step(model, criterion)
     zero_grads(model, optimizer)
     total, scores = 0.0, []
     for i, sample in enumerate(samples):
         label = sample[-1]
-        outputs = model(*(t.unsqueeze(0) for t in sample[:-1]))
-        logits = outputs[0]
-        if isinstance(criterion, CrossModalFocalLoss):
-            loss = criterion(torch.squeeze(logits), torch.squeeze(outputs[2]), torch.squeeze(outputs[3]), label) / iters
+        if step is not None:
+            loss, logits = step(sample[0], label, 1.0 / iters)
         else:
-            loss = criterion(torch.squeeze(logits), label) / iters
-        loss.backward()
+            outputs = model(*(t.unsqueeze(0) for t in sample[:-1]))
+            logits = outputs[0]
+            if isinstance(criterion, CrossModalFocalLoss):
+                loss = criterion(torch.squeeze(logits), torch.squeeze(outputs[2]), torch.squeeze(outputs[3]), label) / iters
+            else:
+                loss = criterion(torch.squeeze(logits), label) / iters
+            loss.backward()
         total += float(loss.item()) * iters
         scores.append(torch.softmax(logits.detach(), dim=1)[0].cpu().numpy())
         if (i + 1) % iters == 0 or (i + 1) == len(samples):
@@ -397,7 +406,7 @@ def _item_loss(criterion, outputs, label):
 
 
 def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None, virtual_batch_size=32, grad_sync=None,
-              rank=0, world=1):
+              rank=0, world=1, cuda_graphs=False):
     """One pass over ``dataset`` in ``order`` (batch size 1, as the reference's loaders, :639-640).  With ``optimizer`` it is
     the training loop (:648-688: loss / iters_to_accumulate, step every iters_to_accumulate items and at the last one),
     without it the evaluation loop (:689-718, no gradients).
@@ -407,6 +416,8 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
     scale (:674), so ``grad_sync`` (``distributed.allreduce_grads``: one sum over the ranks) right before each optimizer step
     yields the single-process gradients.  ``order`` must be the same list on every rank.  Labels / scores / ids / the loss
     are gathered, so every rank returns the whole epoch's records.
+    ``cuda_graphs`` (training pass of a unimodal model): each sample's forward + loss + backward replays a CUDA graph kept per token
+    count (graph_step.GraphedTrainStep); lengths seen for the first time run eagerly.
     Returns (mean loss, y_true list, y_score list, patient ids)."""
     import torch.distributed as dist
     from .distributed import zero_grads
@@ -417,17 +428,28 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
     if train:
         zero_grads(model, optimizer)
     total, y_true, y_score, pids = 0.0, [], [], []
+    step = None
+    if (train and cuda_graphs and modality not in ("petct", "petchest") and isinstance(model, TransformerNoduleClassifier)
+            and not isinstance(criterion, CrossModalFocalLoss)):
+        from .graph_step import graphed_step
+        step = graphed_step(model, criterion)
     with torch.enable_grad() if train else torch.no_grad():
         for w0 in range(0, len(order), iters):
             for idx in order[w0:w0 + iters][rank::world]:
-                outputs, label, pid = _forward_item(model, dataset[int(idx)], modality, device)
-                loss = _item_loss(criterion, outputs, label) / (iters if train else 1)
+                if step is not None:
+                    ct, pet, onehot, pid = dataset[int(idx)]
+                    label = torch.squeeze(torch.as_tensor(onehot)).to(device)
+                    loss, logits = step((pet if modality == "pet" else ct).to(device), label, 1.0 / iters)
+                    outputs = (logits,)
+                else:
+                    outputs, label, pid = _forward_item(model, dataset[int(idx)], modality, device)
+                    loss = _item_loss(criterion, outputs, label) / (iters if train else 1)
                 yt, ys = get_y_true_and_pred(y_true=label, y_pred=outputs[0], cpu=True)
                 y_true.append(yt)
                 y_score.append(ys)
                 pids.append(np.array([pid]))
                 total += float(loss.item()) * (iters if train else 1)           # :681, :716
-                if train:
+                if train and step is None:
                     loss.backward()
             if train:
                 if grad_sync is not None:
@@ -444,7 +466,7 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
 
 def run_fold(cfg, arch, modality, df_train, df_test, label_encoder, hdf5_ct_path, hdf5_pet_path, save_dir, kfold,
              loss_func="focal", device="cuda:0", modality_a="pet", modality_b="ct", store=None, num_epochs=None, grad_sync=None,
-             gather=None, rank=0, world=1):
+             gather=None, rank=0, world=1, cuda_graphs=False):
     """One fold of the reference's training script (train_models.py:562-810): model / criterion / AdamW + cosine schedule from
     the YAML, train and test datasets (augmentation on / off), per epoch a shuffled training pass, an evaluation pass, the
     scheduler step, the patient-weighted reports written to ``<split>_metrics_<epoch>.json``, a checkpoint when the target
@@ -479,7 +501,7 @@ def run_fold(cfg, arch, modality, df_train, df_test, label_encoder, hdf5_ct_path
         if world > 1:
             dist.broadcast_object_list(order, 0)
         tr_loss, yt, ys, pid = run_epoch(model, train_ds, order[0], criterion, modality, device, optimizer,
-                                         cfg_model["virtual_batch_size"], grad_sync, rank, world)
+                                         cfg_model["virtual_batch_size"], grad_sync, rank, world, cuda_graphs=cuda_graphs)
         te_loss, yt2, ys2, pid2 = run_epoch(model, test_ds, range(len(test_ds)), criterion, modality, device, rank=rank, world=world)
         scheduler.step()
         train_report = split_report(yt, ys, pid, tr_loss, kfold, epoch, "train")
@@ -531,7 +553,8 @@ def main(argv=None):
         df_test = df[df["patient_id"].isin(split["test"])].reset_index(drop=True)
         save_dir = os.path.join(models_dir, args.modality, f"kfold_{kfold}")
         histories[kfold] = run_fold(cfg, args.arch, args.modality, df_train, df_test, encoder, hdf5_ct, hdf5_pet, save_dir, kfold,
-                                    loss_func=args.loss, device=device, modality_a=modality_a, modality_b=modality_b, rank=rank, world=world)
+                                    loss_func=args.loss, device=device, modality_a=modality_a, modality_b=modality_b, rank=rank, world=world,
+                                    cuda_graphs=getattr(args, "cuda_graphs", False))
     return histories
 
 
@@ -545,6 +568,8 @@ def build_arg_parser():
     p.add_argument("-gpu", "--gpu", type=int, default=0)
     p.add_argument("-l", "--loss", type=str, default="focal")
     p.add_argument("-e", "--experiment", type=str, default="petct")
+    # not in the reference: replay each training sample as a CUDA graph per cloud length (unimodal models; graph_step.py)
+    p.add_argument("--cuda_graphs", action="store_true")
     return p
 
 
