@@ -51,7 +51,7 @@ class GraphedTrainStep:
                  scale=torch.ones((), dtype=torch.float32, device=dev))
         ck.refresh_cache()
         grad_bucket(self.model).attach()
-        before = torch.cuda.memory_allocated(dev)
+        before = torch.cuda.memory_reserved(dev)               # the graph's private pool is reserved, not 'allocated', once capture ends
         g = torch.cuda.CUDAGraph()
         model = self.model
         model._drop_override = lambda: ck.DropCfg(self.base_seed, *model._drop_rates(), seed_offset=self.seed_offset)
@@ -65,7 +65,7 @@ class GraphedTrainStep:
         finally:
             model._drop_override = None
         e["graph"] = g
-        e["bytes"] = max(0, torch.cuda.memory_allocated(dev) - before)
+        e["bytes"] = max(0, torch.cuda.memory_reserved(dev) - before)
         self.bytes += e["bytes"]
         self.graphs[n] = e
         while self.bytes > self.max_bytes and len(self.graphs) > 1:
