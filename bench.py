@@ -227,15 +227,13 @@ def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bo
     cand = max(S * (p["feat_roi"][1] - p["feat_roi"][0]) * (p["feat_roi"][3] - p["feat_roi"][2]) for p in plans)
     table = PointCloudTable(n_pat, dim, cap_rows=n_pat * cand, device=dev, rank=rank, world=world)
 
+    staged = ex.stage_table([(rank * P + i, img_dev[i], mask_dev[i], res) for i in range(P)], table, count=False)   # plans: once
+
     def step_resident():
-        """counts -> (all-gather of counts, device scan) -> per patient backbone + gather at its table offset -> table all-gather"""
-        for i in range(P):
-            ops.mask_count(mask_dev[i], out=table.count_out(rank * P + i), **geos[i])
-        table.exchange_counts()
-        for i in range(P):
-            tok = tdd._forward_volume(model, img_dev[i], plans[i])
-            ops.mask_gather(tok, mask_dev[i], pe=pe, table=table.slot(rank * P + i), **geos[i])
-        return table.all_gather()
+        """counts -> (all-gather of counts, device scan) -> backbone (patients that fit share a batch) + per-patient gather at its
+        table offset -> table all-gather: PointCloudExtractor.count_table + emit_table, the steps of run_table after planning"""
+        ex.count_table(staged, table)
+        return ex.emit_table(staged, table)
 
     # pinned host inputs for `e2e`
     img_pin = [torch.as_tensor(v[0]).pin_memory() for v in vols]
@@ -244,11 +242,11 @@ def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bo
 
     def run_e2e(k):
         """k steps through the public API from pinned host buffers.  N = 1: the streaming extractor (upload of patient i+1
-        overlaps the backbone of patient i), every point cloud read back.  N > 1: the sharded extraction into one table
+        overlaps the backbone of patient i), every point cloud read back.  N > 1 (or several small patients per step): the extraction into one table
         (PointCloudExtractor.run_table): k*P patients per rank, one count exchange, one table all-gather, every rank reads its
         own row range back (the table itself stays on every GPU for the trainer)."""
         nonlocal host_tok, host_src
-        if world == 1:
+        if world == 1 and P == 1:
             last = None
             for out in ex.run([(img_pin[i % P], mask_pin[i % P], res) for i in range(k * P)]):
                 last = out
@@ -310,8 +308,13 @@ def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bo
     # ---- per-kernel profile pass (CUDA events around every GEMM / attention launch, same stream), separate from `value`; it runs
     # the op-by-op path (the native vdr_vit_forward call cannot be instrumented from here)
     if profile:
+        def prof_forward():      # the backbone batch exactly as a step issues it (several small patients share one batch)
+            if P > 1:
+                return model.forward_volumes([(img_dev[i], plans[i]["crop"]) for i in range(P)])
+            return tdd._forward_volume(model, img_dev[0], plans[0])
+
         ops.PROFILE = []
-        tdd._forward_volume(model, img_dev[0], plans[0])           # untimed: the op-by-op activation buffers get allocated
+        prof_forward()                                              # untimed: the op-by-op activation buffers get allocated
         ops.PROFILE = None
         torch.cuda.synchronize()
         ops.PROFILE = []
@@ -319,7 +322,7 @@ def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bo
         p0.record()
         reps = max(1, min(steps, 3))
         for _ in range(reps):
-            tdd._forward_volume(model, img_dev[0], plans[0])
+            prof_forward()
         p1.record()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
@@ -405,8 +408,8 @@ def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bo
     ms_e, per_step_rows = D.timed(lambda: run_e2e(steps), 1)
     rec["e2e"] = {"value": n_pat * S * steps / (ms_e / 1e3), "unit": "slices/s",
                   "h2d_bytes_per_step": int(P * (img_pin[0].numel() * 4 + mask_pin[0].numel())),
-                  "d2h_bytes_per_step": int(per_step_rows * (dim * 4 + (12 if world == 1 else 16)) + 4), "ms_per_step": ms_e / steps,
-                  "api": "tfds_dense_descriptor.PointCloudExtractor.run (pinned host buffers, uploads double-buffered on a copy stream)" if world == 1 else
+                  "d2h_bytes_per_step": int(per_step_rows * (dim * 4 + (12 if (world == 1 and P == 1) else 16)) + 4), "ms_per_step": ms_e / steps,
+                  "api": "tfds_dense_descriptor.PointCloudExtractor.run (pinned host buffers, uploads double-buffered on a copy stream)" if (world == 1 and P == 1) else
                          "tfds_dense_descriptor.PointCloudExtractor.run_table into a distributed.PointCloudTable (pinned host buffers; counts all-gather, "
                          "table all-gather and the read-back of each rank's row range inside the timed region)"}
 

@@ -556,3 +556,24 @@ def test_run_fold_trains_the_shipped_classifier_config(cuda, tmp_path):
     assert saved and saved[0] == "model_epoch_0000.pth"          # epoch 0: target == the fold's mean
     sd = torch.load(tmp_path / saved[-1], map_location="cpu")
     assert "cls_token" in sd and sd["cls_token"].shape[-1] == D
+
+
+def test_run_table_batches_small_patients_bit_identically(cuda):
+    """PointCloudExtractor.run_table: several small patients share one backbone batch (forward_volumes); the table must be bit for
+    bit what the one-patient-per-forward path writes (same kernels per row: the GEMM tiles never mix rows of different images)."""
+    from vit_deep_radiomics_b200 import synth, tfds_dense_descriptor as tdd
+    from vit_deep_radiomics_b200.distributed import PointCloudTable
+    vols = [synth.make_case("C1", seed=50 + i) for i in range(3)]
+    img, mask, res, name = vols[0]
+    model = tdd.load_model(name, img_hw=img.shape[:2], device=cuda, seed=3)
+    ex = tdd.PointCloudExtractor(model)
+    items = [(i, torch.as_tensor(v[0]).to(cuda), torch.as_tensor(np.ascontiguousarray(v[1]).view(np.uint8)).to(cuda), v[2]) for i, v in enumerate(vols)]
+    cap = 3 * img.shape[2] * model.grid[0] * model.grid[1]
+    tables = []
+    for max_rows in (0, 131072):
+        tb = PointCloudTable(3, model.cfg["dim"], cap_rows=cap, device=cuda, rank=0, world=1)
+        total = ex.run_table(items, tb, max_rows_per_batch=max_rows)
+        tables.append((total, tb.tokens[:total].clone(), tb.src[:total].clone()))
+    assert tables[0][0] == tables[1][0] and tables[0][0] > 30
+    assert torch.equal(tables[0][2], tables[1][2])
+    assert torch.equal(tables[0][1], tables[1][1])

@@ -294,7 +294,7 @@ class PointCloudExtractor:
         plan = _plan_from_bbox(model, H, W, (rmin, rmax, cmin, cmax))
         return plan if plan is not None else _plan(model, mask_dev.cpu().numpy())
 
-    def run_table(self, items, table, add_pe=True):
+    def run_table(self, items, table, add_pe=True, max_rows_per_batch=131072):
         """This rank's patients of a sharded extraction, written straight into ``table`` (distributed.PointCloudTable).
 
         items: list of (patient_index, img (H, W, S) f32, mask (H, W, S) uint8, spatial_res[, noise]) for the patients of
@@ -304,6 +304,11 @@ class PointCloudExtractor:
         by the kernel from device memory), 4. one in-place all-gather of the rank's row range (``table.all_gather``).
         Returns the table's total row count; ``table.tokens[:total]`` / ``table.src[:total]`` then hold every rank's rows in
         (patient, candidate) order, identical on all ranks."""
+        return self.emit_table(self.stage_table(items, table), table, add_pe=add_pe, max_rows_per_batch=max_rows_per_batch)
+
+    def stage_table(self, items, table, count=True):
+        """Step 1 of run_table: per patient the crop / ROI plan (24-byte read-back of the mask's bounding box) and, with
+        ``count``, its row count into the table's count vector.  Returns the staged list ``emit_table`` takes."""
         model, dev = self.model, self.model.device
         gh, gw = model.grid
         staged = []
@@ -315,25 +320,71 @@ class PointCloudExtractor:
             S = mask_dev.shape[2]
             geo = dict(grid=(S, gh, gw, model.n_tokens, model.token_offset), feat_roi=plan["feat_roi"],
                        mask_roi=_shift_roi(plan["mask_roi"], plan["crop"]), mask_layout="hws")
-            ops.mask_count(mask_dev, grid=geo["grid"], feat_roi=geo["feat_roi"], mask_roi=geo["mask_roi"], mask_layout="hws",
-                           out=table.count_out(pid))
             staged.append((pid, img_t, mask_dev, res, noise, plan, geo))
+        if count:
+            self.count_table(staged, table)
+        return staged
+
+    def count_table(self, staged, table):
+        """Row counts of planned patients into the table's count vector (every step over the same patients starts here)."""
+        for pid, _, mask_dev, _, _, _, geo in staged:
+            ops.mask_count(mask_dev, out=table.count_out(pid), **geo)
+
+    def emit_table(self, staged, table, add_pe=True, max_rows_per_batch=131072):
+        """Steps 2-4 of run_table for patients staged by ``stage_table``."""
+        model, dev = self.model, self.model.device
         table.exchange_counts()
         main = torch.cuda.current_stream(dev)
-        nxt = None
-        for i, (pid, img_t, mask_dev, res, noise, plan, geo) in enumerate(staged):
-            img_dev = nxt if nxt is not None else (img_t if img_t.is_cuda else img_t.to(dev, non_blocking=True))
-            nxt = None
-            tok = _forward_volume(model, img_dev, plan)
-            if i + 1 < len(staged) and not staged[i + 1][1].is_cuda:       # next volume crosses PCIe while this one is in the backbone
-                with torch.cuda.stream(self.copy_stream):
-                    nxt = staged[i + 1][1].to(dev, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self.copy_stream)
-            pe = dict(res=res, noise=noise, scale=0.25) if add_pe else None
-            ops.mask_gather(tok, mask_dev, pe=pe, table=table.slot(pid), **geo)
-            if nxt is not None:
+        # consecutive patients share one backbone batch while their token rows stay below what one 512 x 512 x 120 volume has
+        # (small volumes do not fill the GPU on their own); the gather then runs per patient on its rows of the token matrix
+        batchable = hasattr(model, "forward_volumes") and all(st[1].dim() == 3 for st in staged)
+        groups, rows = [], 0
+        for i, st in enumerate(staged):
+            r = int(st[2].shape[2]) * model.n_tokens
+            if groups and batchable and rows + r <= max_rows_per_batch:
+                groups[-1].append(i)
+                rows += r
+            else:
+                groups.append([i])
+                rows = r
+
+        def fetch(idx, stream_ctx):
+            out = {}
+            for i in idx:
+                t = staged[i][1]
+                if t.is_cuda:
+                    out[i] = t
+                else:
+                    with stream_ctx():
+                        out[i] = t.to(dev, non_blocking=True)
+            return out
+
+        import contextlib
+        cur = fetch(groups[0], contextlib.nullcontext) if groups else {}
+        for gi, grp in enumerate(groups):
+            vols = [(cur[i] if cur[i].is_contiguous() else cur[i].contiguous(), staged[i][5]["crop"]) for i in grp]
+            if len(vols) > 1:
+                tok = model.forward_volumes(vols)
+            else:
+                tok = _forward_volume(model, vols[0][0], staged[grp[0]][5])
+            nxt, ev = None, None
+            if gi + 1 < len(groups) and any(not staged[i][1].is_cuda for i in groups[gi + 1]):
+                # the next batch's volumes cross PCIe while this one is in the backbone
+                nxt = fetch(groups[gi + 1], lambda: torch.cuda.stream(self.copy_stream))
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            elif gi + 1 < len(groups):
+                nxt = fetch(groups[gi + 1], contextlib.nullcontext)
+            r0 = 0
+            for i in grp:
+                pid, _, mask_dev, res, noise, plan, geo = staged[i]
+                r1 = r0 + int(mask_dev.shape[2]) * model.n_tokens
+                pe = dict(res=res, noise=noise, scale=0.25) if add_pe else None
+                ops.mask_gather(tok[r0:r1], mask_dev, pe=pe, table=table.slot(pid), **geo)
+                r0 = r1
+            if ev is not None:
                 main.wait_event(ev)
+            cur = nxt
         return table.all_gather()
 
 

@@ -163,6 +163,27 @@ class ViTBackbone:
         ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=self._op_buffers(S)["A"])
         return self._encode(S)
 
+    def forward_volumes(self, vols) -> torch.Tensor:
+        """Several patients in ONE backbone batch: vols = [(vol (H, W, S_i) f32 CUDA, crop), ...]; their slices are staged one
+        after the other and go through the encoder together (small volumes -- 16 slices of 224 x 224 -- do not fill the GPU on their
+        own).  Returns the (sum(S_i) * N, d) f32 token matrix, patient i's rows behind patient i - 1's."""
+        if len(vols) == 1:
+            return self.forward_volume(*vols[0])
+        S = sum(int(v.shape[2]) for v, _ in vols)
+        ws = self._workspace(S)
+        if "SL" not in ws:
+            ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
+        s0 = 0
+        for vol, crop in vols:
+            ops.volume_to_slices(vol, crop, out=ws["SL"][s0:s0 + vol.shape[2]], out_hw=self.img_hw)
+            s0 += int(vol.shape[2])
+        if ops.PROFILE is None and self.use_native_forward:
+            return self._encode_native(S, ws["SL"])
+        if ops.patch_embed_supported(self.img_hw[0], self.img_hw[1], self.cfg["patch"]):
+            return self._encode(S, images=ws["SL"])
+        ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=self._op_buffers(S)["A"])
+        return self._encode(S)
+
     def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
         """src: f32 CUDA storage holding B images of self.img_hw addressed by element `strides`
         (batch, channel, row, col).  Returns the final-LayerNorm token matrix (B*N, d) f32
