@@ -409,7 +409,7 @@ def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bo
     rec["e2e"] = {"value": n_pat * S * steps / (ms_e / 1e3), "unit": "slices/s",
                   "h2d_bytes_per_step": int(P * (img_pin[0].numel() * 4 + mask_pin[0].numel())),
                   "d2h_bytes_per_step": int(per_step_rows * (dim * 4 + (12 if (world == 1 and P == 1) else 16)) + 4), "ms_per_step": ms_e / steps,
-                  "api": "tfds_dense_descriptor.PointCloudExtractor.run (pinned host buffers, uploads double-buffered on a copy stream)" if (world == 1 and P == 1) else
+                  "api": "tfds_dense_descriptor.PointCloudExtractor.run (pinned host buffers, uploads double-buffered on a copy stream, each point cloud read back on a third stream while the next patient is in the backbone)" if (world == 1 and P == 1) else
                          "tfds_dense_descriptor.PointCloudExtractor.run_table into a distributed.PointCloudTable (pinned host buffers; counts all-gather, "
                          "table all-gather and the read-back of each rank's row range inside the timed region)"}
 

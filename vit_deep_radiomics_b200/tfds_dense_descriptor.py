@@ -260,12 +260,17 @@ class PointCloudExtractor:
         return plan, tokens, src, count
 
     def run(self, items, add_pe=True, to_host=True):
-        """items: iterable of (img_3d, mask_3d, spatial_res[, noise]); yields one result dict per patient."""
+        """items: iterable of (img_3d, mask_3d, spatial_res[, noise]); yields one result dict per patient.
+
+        ``to_host``: the point cloud of patient i is read back (row count first, then exactly that many rows, on a copy stream
+        into pinned staging) AFTER the backbone of patient i + 1 has been enqueued, so the read-back and the host's wait for it
+        never leave the GPU idle; results are yielded in order, one patient behind the launches."""
         it = iter(items)
         nxt = next(it, None)
         slot = 0
         if nxt is not None:
             self._upload(slot, *_as_pinned_pair(nxt[0], nxt[1]))
+        pending = None
         while nxt is not None:
             cur, cur_slot = nxt, slot
             plan, tokens, src, count = self._compute(cur_slot, cur[2], cur[3] if len(cur) > 3 else (0.0, 0.0, 0.0), add_pe)
@@ -273,13 +278,40 @@ class PointCloudExtractor:
             slot ^= 1
             if nxt is not None:                                   # overlaps with the backbone of `cur`
                 self._upload(slot, *_as_pinned_pair(nxt[0], nxt[1]))
-            out = dict(plan=plan)
-            if to_host:
-                n = int(count.item())                             # D2H sync: the step's result
-                out.update(tokens=tokens[:n].cpu(), src=src[:n].cpu(), count=n)
-            else:
-                out.update(tokens=tokens, src=src, count=count)
-            yield out
+            if not to_host:
+                yield dict(plan=plan, tokens=tokens, src=src, count=count)
+                continue
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.model.device))
+            if pending is not None:
+                yield self._read_back(*pending)
+            pending = (plan, tokens, src, count, done)
+        if pending is not None:
+            yield self._read_back(*pending)
+
+    def _read_back(self, plan, tokens, src, count, done):
+        """D2H of one patient's point cloud on the read-back stream: 4-byte count, then count rows of tokens / source triplets."""
+        if not hasattr(self, "d2h_stream"):
+            self.d2h_stream = torch.cuda.Stream(device=self.model.device)
+            self._n_host = torch.empty(1, dtype=torch.int32).pin_memory()
+            self._stage = {}
+        st = self.d2h_stream
+        with torch.cuda.stream(st):
+            st.wait_event(done)
+            self._n_host.copy_(count, non_blocking=True)
+            st.synchronize()
+            n = int(self._n_host[0])
+            key = (tokens.shape[1], src.shape[1])
+            buf = self._stage.get(key)
+            if buf is None or buf[0].shape[0] < n:
+                rows = max(n, tokens.shape[0] // 2)
+                buf = self._stage[key] = (torch.empty((rows, tokens.shape[1]), dtype=torch.float32).pin_memory(),
+                                          torch.empty((rows, src.shape[1]), dtype=torch.int32).pin_memory())
+            buf[0][:n].copy_(tokens[:n], non_blocking=True)
+            buf[1][:n].copy_(src[:n], non_blocking=True)
+            st.synchronize()
+        # (tokens / src were allocated on the main stream and are referenced until here: the allocator cannot hand them out earlier)
+        return dict(plan=plan, tokens=buf[0][:n].clone(), src=buf[1][:n].clone(), count=n)
 
     # ---- sharded extraction into ONE table (SURVEY.md 8e; reference: the per-patient loop :421 + merge_dataframe_features.py)
     def plan_patient(self, mask_dev):
