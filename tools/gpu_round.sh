@@ -15,13 +15,14 @@ timeout 600 python bench.py --steps 1 --warmup 3 --no-sub > $O/plain_bench.log 2
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 160 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-sub > $O/ncu_launches.log 2>&1
 echo "ncu launches rc=$?" | tee -a $O/status.txt
-for k in gemm attn ln gather; do
+for k in gemm attn ln gather sam; do
   pat=$k; skip=0; cnt=12
   case $k in
     gemm) pat='regex:gemm_tcgen05'; skip=8; cnt=4;;
     attn) pat='regex:flash_attn'; skip=2; cnt=1;;
     ln) pat='regex:layernorm'; skip=2; cnt=1;;
     gather) pat='regex:g1_fused'; skip=4; cnt=2;;
+    sam) pat='regex:flash_attn|attn_win14'; skip=2; cnt=2;;
   esac
   timeout 300 python tools/prof_kernels.py $k > $O/plain_$k.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k "$pat" -s $skip -c $cnt -f -o $O/${TAG}_prof_$k \

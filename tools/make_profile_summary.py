@@ -84,7 +84,8 @@ if rows:
                    dram_bytes_per_launch=sum(p["dram_bytes"] for p in per) / len(per),
                    note="mean over the four per-layer GEMM shapes of config C2 (each launched 12x per step); dram__bytes_read.sum + dram__bytes_write.sum",
                    per_shape=per), open(os.path.join(DST, "gemm_traffic.json"), "w"), indent=1)
-for kind, title in (("attn", "Flash attention B=120 N=1025 heads=12"), ("ln", "LayerNorm 123000x768 bf16"), ("gather", "Mask gather (C2 ellipsoid mask, then a dense mask)")):
+for kind, title in (("attn", "Flash attention B=120 N=1025 heads=12"), ("ln", "LayerNorm 123000x768 bf16"), ("gather", "Mask gather (C2 ellipsoid mask, then a dense mask)"),
+                    ("sam", "MedSAM attention, 4 images of 64x64 tokens, 12 heads: global block (fused rel-pos flash kernel), then a windowed block (tcgen05 14x14 windows)")):
     hdr, units, rows = raw(kind)
     for r in rows:
         md += [f"## {title}", "", table(hdr, units, r), ""]

@@ -63,9 +63,9 @@ if which in ("gather", "all"):
         torch.cuda.synchronize()
 print("done")
 if which in ("sam",):
-    # MedSAM attention with rel-pos bias, 4 images of 64 x 64 tokens, 12 heads: the global block (bias table kernel + tcgen05 flash
-    # kernel with bias) and a windowed block read in place (100 windows of 14 x 14, mma.sync resident-key kernel).
-    # One warm round (3 launches), then the round ncu captures:  ncu -k regex:'relpos|flash_attn' -s 3 -c 3
+    # MedSAM attention with rel-pos bias, 4 images of 64 x 64 tokens, 12 heads: the global block (tcgen05 flash kernel computing
+    # its own bias terms) and a windowed block read in place (100 windows of 14 x 14, tcgen05 one-shot kernel).
+    # One warm round (2 launches), then the round ncu captures:  ncu -k regex:'flash_attn|attn_win14' -s 2 -c 2
     B, S = 4, 64
     qkv = torch.randn(B * S * S, 3 * d, device=dev).bfloat16()
     bias = torch.randn(3 * d, device=dev) * 0.1
