@@ -103,7 +103,7 @@ def test_flash_attn_relpos_tcgen05_vs_fp32(cuda, BW, Sh, heads):
     err = (fused - want).abs().max()
     cos = F.cosine_similarity(fused.reshape(-1, 64), want.reshape(-1, 64), dim=1).min()
     assert err < 2e-2 and cos > 0.9995, (float(err), float(cos))
-    assert (fused - got).abs().max() < 1e-2            # table in f32 vs terms straight from the accumulator: fp16 rounding of rel_w either way
+    assert (fused - got).abs().max() < 2e-2            # one bf16 ulp of an output of magnitude 2..4: rel_w is fp16 in both, added by the MMA here
     with pytest.raises(ValueError):      # Sh = 2: not a multiple of 4 -> the tcgen05 variant refuses, it never falls back silently
         hi2, lo2 = ops.relpos_split(torch.zeros(3, 64, device=cuda), torch.zeros(127, 64, device=cuda))
         ops.attn_relpos(qkv.to(cuda)[:128], 1, 2, Sw, heads, hi2, lo2, kernel="tcgen05")

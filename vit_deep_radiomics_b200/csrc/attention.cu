@@ -53,6 +53,11 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) 
   return d;
 }
 
+// instruction descriptor for fp16 x fp16 -> f32 (the rel_w accumulate): A / B format fields 0
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 struct AttnParams {
   const __nv_bfloat16* qkv;
   int64_t ld_qkv;
@@ -73,6 +78,10 @@ struct AttnParams {
 };
 constexpr int kBiasPitch = 136;                          // bytes per query row of the rel_w terms in shared memory: 64 halfs + 8 pad
 constexpr int kAttnSmemBias = kAttnSmem + 128 * kBiasPitch;
+// kFused: the rel_w terms live in an fp16 UMMA operand tile (128 rows x 64, 1024-byte aligned; it takes the place of the trailing-key
+// scratch, which N % 128 == 0 never needs) next to a 64 x 64 fp16 identity tile: S += Qw I^T adds them on the tensor cores
+constexpr int kFusedQwOff = 86016, kFusedIdOff = kFusedQwOff + kTileBytes, kAttnSmemFused = kFusedIdOff + 8192;
+static_assert(kFusedQwOff >= 5 * kTileBytes + 256 + 3 * 2 * 128 * 4 && kFusedQwOff % 1024 == 0, "fused rel-pos tiles overlap the barriers / exchange buffers");
 
 #ifdef VDR_ATTN_TRACE
 __device__ __forceinline__ unsigned long long attn_gtime() {
@@ -385,6 +394,15 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+          if (kFused) {   // + rel_w[q, kw] / scale for both grid rows of the block: S[:, 0:64] += Qw I^T, S[:, 64:128] += Qw I^T
+            const uint64_t dqw = umma_desc_kmajor_sw128(base + kFusedQwOff), did = umma_desc_kmajor_sw128(base + kFusedIdOff);
+            constexpr uint32_t idw = umma_idesc_f16(128, 64);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_ss(tmem_S, dqw + 2 * k, did + 2 * k, idw, 1u);
+              umma_ss(tmem_S + 64, dqw + 2 * k, did + 2 * k, idw, 1u);
+            }
+          }
           umma_commit(bar_s);
         }
         __syncwarp();
@@ -526,7 +544,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       mbar_wait(bar_t, 0);
       tc_fence_after();
       const int qw = row & 63;
-      unsigned char* brow = smem + kAttnSmem + row * kBiasPitch;
+      unsigned char* qw_tile = smem + kFusedQwOff;
+      const float inv_scale = 1.4426950408889634f / p.scale_log2;
       uint32_t u[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -542,10 +561,25 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; ++i) {                                     // rel_w[q, kw] = q . rel_pos_w[qw - kw + 63] = T_w[qw + 63 - kw]
           const int jj = qw + 63 - (half * 64 + 32 * c + i);
-          if (static_cast<unsigned>(jj) < 64u)
-            *reinterpret_cast<__half*>(brow + 2 * jj) = __float2half_rn(__uint_as_float(u[i]) * 1.4426950408889634f);
+          if (static_cast<unsigned>(jj) < 64u)     // element jj of row `row` of the 128-byte-swizzled K-major tile
+            *reinterpret_cast<__half*>(qw_tile + row * 128 + (((jj >> 3) ^ (row & 7)) << 4) + 2 * (jj & 7)) = __float2half_rn(__uint_as_float(u[i]) * inv_scale);
         }
       }
+      {   // the identity tile: 64 rows x 8 sixteen-byte chunks, two chunks per softmax thread
+        const int t0 = warp * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int idx = t0 + 256 * k, r = idx >> 3, cch = idx & 7;
+          uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+          if ((r >> 3) == cch) {
+            const uint32_t one = (r & 1) ? 0x3C000000u : 0x00003C00u;      // fp16 1.0 in the element's half of its word
+            const int word = (r & 7) >> 1;
+            w0 = word == 0 ? one : 0u; w1 = word == 1 ? one : 0u; w2 = word == 2 ? one : 0u; w3 = word == 3 ? one : 0u;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + kFusedIdOff + r * 128 + ((cch ^ (r & 7)) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        }
+      }
+      fence_proxy_async_smem();
       tc_fence_before();
       pair_bar_sync(quarter);                                              // both halves of the row are written, both have read T
       __syncwarp();
@@ -662,7 +696,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfree);
         ATT_TRACE(2);
-        if (kBias) {   // scores -> log2 domain with the bias added: v = S * scale + (rel_h + rel_w)
+        if (kBias && !kFused) {   // scores -> log2 domain with the bias added: v = S * scale + (rel_h + rel_w)
           const uint64_t bh2 = pack2(bh_cur, bh_cur);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -689,16 +723,19 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           mx3 = max3(mx3, __uint_as_float(sr[1][i + 2]), __uint_as_float(sr[1][i + 3]));
         }
         float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // kFused: the scores already hold rel_w / scale (added by the MMA); rel_h of this half's grid row is one scalar per row --
+        // the two half-row threads have DIFFERENT rel_h terms, so they exchange the maximum with the term added (log2 domain)
+        if (kFused) mx = fmaf(mx, p.scale_log2, bh_cur);
         xmax[half * 128 + row] = mx;
         pair_bar_sync(quarter);
         mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]);
-        const float m_new = fmaxf(m_ref, kBias ? mx : mx * p.scale_log2);
+        const float m_new = fmaxf(m_ref, (kBias || kFused) ? mx : mx * p.scale_log2);
         moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);   // warp-uniform (TMEM accesses are warp-wide) and, since both
         if (moved) {                                             //  half-row warps see the same row maxima, CTA-pair-uniform
           alpha = ex2(m_ref - m_new);
           m_ref = m_new;
         }
-        const uint64_t negm2 = pack2(-m_ref, -m_ref);
+        const uint64_t negm2 = kFused ? pack2(bh_cur - m_ref, bh_cur - m_ref) : pack2(-m_ref, -m_ref);
         uint64_t lsum2 = 0ull;
         uint32_t pk[32];
         uint4 dbits = make_uint4(0, 0, 0, 0);
@@ -709,7 +746,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint64_t s2 = pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
-            const uint64_t x2 = kBias ? add2(s2, negm2) : fma2(s2, scale2, negm2);
+            const uint64_t x2 = (kBias && !kFused) ? add2(s2, negm2) : fma2(s2, scale2, negm2);
             float p0, p1;
             if ((kPolyMask >> ((i >> 1) & 7)) & 1u) {   // a fixed subset of every 8 pairs: FMA-pipe exp2
               exp2_poly2(x2, p0, p1);
@@ -1172,7 +1209,7 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV6Smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBias);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemFused);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_fwd)");
     configured.current() = true;
   }
@@ -1204,7 +1241,7 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.q_tiles + (vector_tail ? 1 : 0), heads, B);
   if (fused)
-    flash_attn_fwd_kernel<true, false, true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, tm_rhi, tm_rlo, p);
+    flash_attn_fwd_kernel<true, false, true><<<grid, kAttnThreads, kAttnSmemFused, s>>>(tm, tm_rhi, tm_rlo, p);
   else if (rel != nullptr)
     flash_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBias, s>>>(tm, tm_rhi, tm_rlo, p);
   else if (dropout)
