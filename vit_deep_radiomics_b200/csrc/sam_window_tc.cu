@@ -9,7 +9,8 @@
 //            (dim, x, y, image): positions beyond the image arrive as zeros and are overwritten with bf16(qkv bias) -- the
 //            reference pads AFTER norm1, so a pad token is exactly "q = k = v = bias" and takes part in the softmax.
 //   T        = Q [R_hi ; R_lo]^T   (128 x 64 x 64, twice, one accumulator): q . rel_pos_h[i], q . rel_pos_w[i] for all 27 + 27
-//            relative offsets; a query thread picks its 14 + 14 terms (a barrel shift by its own (qh, qw) over registers).
+//            relative offsets (the R tiles borrow the E tile's space); a query thread picks its 14 + 14 terms (a barrel shift by its
+//            own (qh, qw) over registers).
 //   S'       = [Q | E] [K | onehot]^T  (128 x 208 x 128): the bias is folded INTO the score MMA.  E holds the query row's
 //            28 bias terms / scale as bf16 hi + lo parts (fp32-class accuracy) and a constant 1; the matching 64 extra K columns
 //            are one-hot in (kh, kw) (a constant tile, the same for every window) and -30000 in the constant's column for the
@@ -120,7 +121,7 @@ attn_win14_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* bar_ld = bars;         // Q, K, V landed
   uint64_t* bar_r = bars + 1;      // R_hi, R_lo landed
   uint64_t* bar_t = bars + 2;      // T complete
-  uint64_t* bar_kx = bars + 3;     // the constant key columns landed (over R_hi / R_lo)
+  uint64_t* bar_kx = bars + 3;     // the constant key columns landed
   uint64_t* bar_qx = bars + 4;     // E written, fix-ups done (128 arrivals)
   uint64_t* bar_s = bars + 5;      // S' complete
   uint64_t* bar_p = bars + 6;      // P stored (128 arrivals)
@@ -150,8 +151,10 @@ attn_win14_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_arrive_expect_tx(bar_ld, kW14Half * 128 + 2 * kW14N * 128);
     tma_load_4d(&tmQ, bar_ld, sQm, head * 64, x0, y0 + 7 * half, b);
     mbar_arrive_expect_tx(bar_r, 2 * 64 * 128);
-    tma_load_2d_addr(&tmRhi, bar_r, sKx, 0, 0);
-    tma_load_2d_addr(&tmRlo, bar_r, sKx + 8192, 0, 0);
+    tma_load_2d_addr(&tmRhi, bar_r, sQx, 0, 0);            // R_hi / R_lo borrow the E tile's space: E is written only after T is complete
+    tma_load_2d_addr(&tmRlo, bar_r, sQx + 8192, 0, 0);
+    mbar_arrive_expect_tx(bar_kx, kW14Tile208);
+    tma_load_2d_addr(&tmKx, bar_kx, sKx, 0, 0);
     tma_load_4d(&tmKV, bar_ld, sKm, d + head * 64, x0, y0, b);
     tma_load_4d(&tmKV, bar_ld, sV, 2 * d + head * 64, x0, y0, b);
   }
@@ -178,18 +181,12 @@ attn_win14_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_wait(bar_r, 0);
     tc_fence_after();
     if (elect_one()) {
-      const uint64_t dq = umma_desc_kmajor_sw128(sQm), dh = umma_desc_kmajor_sw128(sKx), dl = umma_desc_kmajor_sw128(sKx + 8192);
+      const uint64_t dq = umma_desc_kmajor_sw128(sQm), dh = umma_desc_kmajor_sw128(sQx), dl = umma_desc_kmajor_sw128(sQx + 8192);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_ss(tmem_S, dq + 2 * k, dh + 2 * k, idesc_t, k != 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_ss(tmem_S, dq + 2 * k, dl + 2 * k, idesc_t, 1u);
       umma_commit(bar_t);
-    }
-    __syncwarp();
-    mbar_wait(bar_t, 0);                     // R_hi / R_lo consumed: their space takes the constant key columns
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bar_kx, kW14Tile208);
-      tma_load_2d_addr(&tmKx, bar_kx, sKx, 0, 0);
     }
     __syncwarp();
     mbar_wait(bar_kx, 0);
