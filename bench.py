@@ -774,10 +774,14 @@ def main():
     ap.add_argument("--no-sub", action="store_false", dest="sub", help="skip the sub-records (C1, C4, c3, C5, medsam, augment)")
     ap.add_argument("--no-medsam", action="store_false", dest="medsam", help="skip the MedSAM sub-record")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
