@@ -731,7 +731,7 @@ def run_ours(args):
     if args.sub:
         torch.cuda.empty_cache()
         if world == 1:
-            sub["C1"] = bench_extraction(D, "C1", 20, 3, profile=True, cpu_slices=8)
+            sub["C1"] = bench_extraction(D, "C1", 20, 3, profile=True, cpu_slices=8, patients_per_step=16)   # 16 x 8 slices share a backbone batch
         torch.cuda.empty_cache()
         sub["C4"] = bench_extraction(D, "C4", 5, 3, profile=(world == 1), cpu_slices=8, patients_per_step=8)
         torch.cuda.empty_cache()

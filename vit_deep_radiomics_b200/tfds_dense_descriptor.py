@@ -344,11 +344,23 @@ class PointCloudExtractor:
         model, dev = self.model, self.model.device
         gh, gw = model.grid
         staged = []
-        for it in items:
-            pid, img_t, mask_t, res = it[:4]
+        items = list(items)
+        # every mask's bounding box first (uploads + reductions enqueued back to back), then ONE read-back for all patients
+        masks = [it[2] if it[2].is_cuda else it[2].to(dev, non_blocking=True) for it in items]
+        boxes = torch.empty((max(len(items), 1), 6), dtype=torch.int32, device=dev)
+        for i, m in enumerate(masks):
+            ops.mask_bbox(m, out=boxes[i])
+        boxes_host = boxes.cpu()
+        for i, it in enumerate(items):
+            pid, img_t, _, res = it[:4]
             noise = it[4] if len(it) > 4 else (0.0, 0.0, 0.0)
-            mask_dev = mask_t if mask_t.is_cuda else mask_t.to(dev, non_blocking=True)
-            plan = self.plan_patient(mask_dev)
+            mask_dev = masks[i]
+            cmin, cmax, rmin, rmax, _, _ = (int(v) for v in boxes_host[i])
+            if cmax < cmin:
+                raise ValueError("extract_coords: empty mask")
+            plan = _plan_from_bbox(model, mask_dev.shape[0], mask_dev.shape[1], (rmin, rmax, cmin, cmax))
+            if plan is None:
+                plan = _plan(model, mask_dev.cpu().numpy())
             S = mask_dev.shape[2]
             geo = dict(grid=(S, gh, gw, model.n_tokens, model.token_offset), feat_roi=plan["feat_roi"],
                        mask_roi=_shift_roi(plan["mask_roi"], plan["crop"]), mask_layout="hws")
