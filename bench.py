@@ -527,7 +527,7 @@ def bench_classifier(D: Dist, samples: int = 64, epochs: int = 2, cpu_samples: i
     return rec
 
 
-def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4):
+def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4, model: str | None = None):
     """C5: per patient a 512x512x120 volume goes through ViT-B/16 extraction, the mask gather (+ PE) and ONE training step of the
     point-cloud classifier on the 768-wide descriptors (feature_dim 768 / 12 heads in the YAML schema; the reference's 256 comes
     from MedSAM's neck); volumes uploaded inside the timed region; patients/s over all ranks."""
@@ -538,7 +538,9 @@ def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4):
     rank, world, dev = D.rank, D.world, D.dev
     img, mask, res, name = synth.make_case("C2", seed=1238 + rank)
     H, W, S = img.shape
-    backbone = tdd.load_model(name, img_hw=(H, W), device=dev, seed=1234)
+    if model is not None:     # e.g. "medsam": the reference's DEFAULT pipeline -- SAM ViT-B encoder on the crop window resized to 1024^2
+        name = model          # (on the device) -> 256-wide descriptors -> the classifier exactly as conf/parameters_models.yaml configures it
+    backbone = tdd.load_model(name, img_hw=None if model is not None else (H, W), device=dev, seed=1234)
     dim = backbone.feature_dim
     torch.manual_seed(0)
     clf = TransformerNoduleClassifier(dim, 4 * dim, dim // 64, 2, 2).to(dev)
@@ -580,7 +582,7 @@ def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4):
     flops = patients * world * (backbone.flops_per_slice() * S + 3.0 * _classifier_flops(n_tok + 1, dim, 4 * dim, 2))
     tfl = flops / (ms / 1e3) / 1e12
     v = world * patients / (ms / 1e3)
-    rec = {"workload": f"C5: {name} extraction over a {H}x{W}x{S} volume -> mask gather + PE ({n_tok} tokens) -> 2-layer transformer classifier "
+    rec = {"workload": f"C5: {name} extraction over a {H}x{W}x{S} volume{' (crop window resized to 1024x1024 on the device)' if model is not None else ''} -> mask gather + PE ({n_tok} tokens) -> 2-layer transformer classifier "
                        f"(d {dim}, {dim // 64} heads) training step per patient, {patients} patients per rank, gradient all-reduce per {window} patients per rank",
            "value": v, "unit": "patients/s", "slices_per_s": v * S, "ms_per_patient": ms / patients, "gpu_launches": int(launches), "loss": loss,
            "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "peak": peaks["bf16"], **tensor_fracs(tfl / world, peaks),
@@ -588,7 +590,17 @@ def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4):
            "e2e": {"value": v, "unit": "patients/s", "h2d_bytes_per_step": int(img_pin.numel() * 4 + mask_pin.numel()), "d2h_bytes_per_step": 8,
                    "api": "PointCloudExtractor.run(to_host=False) -> TransformerNoduleClassifier -> FocalLoss.backward; the timed region IS end to end "
                           "(pinned host volumes in, the token count and the loss out)"}}
-    if rank == 0:
+    if rank == 0 and model is not None:
+        from oracle import sam_fp32
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            sam_fp32.sam_dense_descriptor(backbone.state_dict_f32, backbone.cfg, torch.rand(1, 3, 1024, 1024))
+        cpu_dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": (1.0 / S) / cpu_dt, "unit": "patients/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"1 of {S} slices through oracle/sam_fp32.py at 1024x1024 (the encoder alone: resize, gather and classifier step are "
+                                         f"< 2 % of the host time), {cpu_dt:.2f} s wall, scaled by slices"}
+    elif rank == 0:
         from oracle import classifier_fp32 as C, gather_np, vit_fp32
         torch.set_num_threads(os.cpu_count() or 1)
         cfg = vit_fp32.VIT_CONFIGS[name]
@@ -738,6 +750,9 @@ def run_ours(args):
         sub["c3"] = bench_classifier(D)
         torch.cuda.empty_cache()
         sub["C5"] = bench_pipeline(D)
+        torch.cuda.empty_cache()
+        if args.medsam:
+            sub["C5_medsam"] = bench_pipeline(D, patients=2, model="medsam")      # the reference's default backbone + shipped classifier config
         torch.cuda.empty_cache()
         if world == 1 and args.medsam:
             sub["medsam"] = bench_medsam(D)
