@@ -181,7 +181,8 @@ def test_gemm_argument_errors(cuda):
         ops.gemm(a[:, 1:], torch.zeros(16, 63, device=cuda, dtype=torch.bfloat16))   # misaligned / ld % 8
 
 
-@pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (2, 197, 6), (1, 1025, 2), (3, 300, 4), (1, 7, 1), (2, 257, 16)])
+@pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (2, 197, 6), (1, 1025, 2), (3, 300, 4), (1, 7, 1), (2, 257, 16),
+                                         (2, 136, 3), (2, 1030, 2), (3, 645, 2), (2, 2, 1), (5, 1025, 12)])   # 8 / 6 / 5 / 2 trailing rows: the mma.sync tail CTA
 def test_flash_attention(cuda, B, N, heads):
     from vit_deep_radiomics_b200 import ops
     torch.manual_seed(B * 1000 + N)

@@ -253,6 +253,162 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
   }
 }
 
+// ---- the same trailing rows with warp-level MMAs (the v5 grid's default).  The CUDA-core routine above spends ~18 k warp
+// instructions per trailing row (8 lanes per key: unpack, shuffles, two exponentials per key and lane) -- as many issue slots as a
+// whole 128-row tensor-core tile, taken from the MUFU-bound tile CTA that shares the SM.  Here one lane of warp 8 streams the
+// head's K / V through the tile CTAs' own TMA ring (same tensor map, same 128 x 64 SWIZZLE_128B tiles, L2 hits on the lines the
+// siblings stream) and warps 0-7 each own 16 keys of every 128-key tile:
+//   S^T chunk : m16n8k16, A = the trailing query rows (row g of the fragment = trailing row g, rows 8-15 zero), B = K via ldmatrix
+//   softmax   : plain online softmax per (warp, row); the accumulator fragment of S IS the A fragment of P (FlashAttention-2's layout identity)
+//   O chunk   : A = P (bf16), B = V via ldmatrix.trans
+// ~2.6 k warp instructions per (image, head) for up to 8 trailing rows; the 8 per-warp states are merged through shared memory.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+// D[rows 0-7] += A[rows 0-7] B  (rows 8-15 of A are zero: their accumulators are neither fed nor kept)
+__device__ __forceinline__ void mma_16816_top(float& c0, float& c1, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  [[maybe_unused]] float d2, d3;
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %10, %10};"
+               : "+f"(c0), "+f"(c1), "=f"(d2), "=f"(d3) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1), "f"(0.f));
+  (void)d2;
+  (void)d3;
+}
+constexpr int kTailEmptyBar = 16;   // bars[16..19]: ring slot consumed (8 warps arrive); the tile CTAs use bars[0..13]
+
+__device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const AttnParams& p, uint8_t* smem, int head, int b, int row0, int nrows) {
+  const uint32_t base = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
+  uint64_t* full = bars + 1;                                              // [4] ring slot landed (the tile CTAs' bar_kv)
+  uint64_t* empty = bars + kTailEmptyBar;                                 // [4]
+  float* s_m = reinterpret_cast<float*>(smem + 5 * kTileBytes + 256);     // [8 warps][8 rows]
+  float* s_l = s_m + 64;
+  float* s_o = reinterpret_cast<float*>(smem);                            // the (unused) Q slot: [8 warps][8 rows][64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nblk = (p.N + kBKV - 1) / kBKV;
+  const int row_base = b * p.N, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    // ---- producer: K_0 V_0 K_1 V_1 ... through the four ring slots
+    for (int tt = 0; tt < 2 * nblk; ++tt) {
+      const int slot = tt & 3;
+      if (tt >= 4) mbar_wait_relaxed(&empty[slot], ((tt >> 2) - 1) & 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[slot], kTileBytes);
+        tma_load_2d(tm, &full[slot], smem + kTileBytes * (1 + slot), (tt & 1) ? colV : colK, row_base + (tt >> 1) * kBKV);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 8) {
+    // A fragments of the trailing rows: row g of the fragment = trailing row min(g, nrows - 1) (duplicates are never stored)
+    uint32_t qa[4][2];
+    {
+      const __nv_bfloat16* qrow = p.qkv + static_cast<int64_t>(row_base + row0 + min(g, nrows - 1)) * p.ld_qkv + head * kHD + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(qrow + 16 * ks));
+        qa[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 8));
+      }
+    }
+    float oc[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) oc[nt][0] = oc[nt][1] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const int mi = lane >> 3, r8 = lane & 7;
+    for (int j = 0; j < nblk; ++j) {
+      const int key0 = j * kBKV + warp * 16;
+      const bool active = key0 < p.N;                                     // warp-uniform
+      const int tk = 2 * j, tv = 2 * j + 1;
+      mbar_wait_relaxed(&full[tk & 3], (tk >> 2) & 1);
+      uint32_t pa0 = 0u, pa2 = 0u;
+      if (active) {
+        const uint32_t kt = base + kTileBytes * (1 + (tk & 3));
+        float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        const int r = warp * 16 + (mi >> 1) * 8 + r8;                     // matrices 0/1: keys 0-7, matrices 2/3: keys 8-15
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b00, b01, b10, b11;
+          ldsm_x4(kt + r * 128 + (((2 * ks + (mi & 1)) ^ (r & 7)) << 4), b00, b01, b10, b11);
+          mma_16816_top(s[0][0], s[0][1], qa[ks][0], qa[ks][1], b00, b01);
+          mma_16816_top(s[1][0], s[1][1], qa[ks][0], qa[ks][1], b10, b11);
+        }
+        float x[2][2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) x[nt][e] = (key0 + 8 * nt + 2 * t + e < p.N) ? s[nt][e] * p.scale_log2 : -INFINITY;
+        float mx = fmaxf(fmaxf(x[0][0], x[0][1]), fmaxf(x[1][0], x[1][1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));             // the chunk holds at least one key: finite
+        const float m_new = fmaxf(m, mx);
+        const float alpha = ex2(m - m_new);
+        m = m_new;
+        const float p00 = ex2(x[0][0] - m), p01 = ex2(x[0][1] - m), p10 = ex2(x[1][0] - m), p11 = ex2(x[1][1] - m);
+        l = l * alpha + ((p00 + p01) + (p10 + p11));
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          oc[nt][0] *= alpha;
+          oc[nt][1] *= alpha;
+        }
+        pa0 = cvt_bf16x2(p00, p01);
+        pa2 = cvt_bf16x2(p10, p11);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[tk & 3]);
+      mbar_wait_relaxed(&full[tv & 3], (tv >> 2) & 1);
+      if (active) {
+        const uint32_t vt = base + kTileBytes * (1 + (tv & 3));
+        const int r = warp * 16 + (mi & 1) * 8 + r8;                      // matrices 0/2: keys 0-7, matrices 1/3: keys 8-15
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {                                  // 16 output dims per ldmatrix
+          uint32_t v0, v1, v2, v3;
+          ldsm_x4_trans(vt + r * 128 + (((2 * np + (mi >> 1)) ^ (r & 7)) << 4), v0, v1, v2, v3);
+          mma_16816_top(oc[2 * np][0], oc[2 * np][1], pa0, pa2, v0, v1);
+          mma_16816_top(oc[2 * np + 1][0], oc[2 * np + 1][1], pa0, pa2, v2, v3);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[tv & 3]);
+    }
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    if (t == 0) {
+      s_m[warp * 8 + g] = m;
+      s_l[warp * 8 + g] = l;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      *reinterpret_cast<float2*>(s_o + (warp * 8 + g) * kHD + 8 * nt + 2 * t) = make_float2(oc[nt][0], oc[nt][1]);
+  }
+  __syncthreads();
+  // merge the eight per-warp states: thread (row, dim)
+  for (int i = tid; i < nrows * kHD; i += kAttnThreads) {
+    const int rr = i >> 6, dd = i & 63;
+    float mt = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mt = fmaxf(mt, s_m[w * 8 + rr]);
+    float lt = 0.f, acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float f = ex2(s_m[w * 8 + rr] - mt);                          // a warp without keys: m = -inf -> 0
+      lt = fmaf(s_l[w * 8 + rr], f, lt);
+      acc = fmaf(s_o[(w * 8 + rr) * kHD + dd], f, acc);
+    }
+    const int q = row0 + rr;
+    p.out[(static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD + dd] = __float2bfloat16_rn(acc / lt);
+    if (dd == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mt + log2f(lt)) * 0.69314718055994531f;
+  }
+}
+
 // Pipeline per 128-key block j (no CTA-wide barrier in the loop):
 //   issuers: wait S_j consumed -> prefetch K_{j+2}, issue S_{j+1};  wait P_j ready -> issue O += P_j V_j
 //   softmax: wait S_j -> registers -> signal "consumed" -> max (exchanged between the two half-row threads) ->
@@ -298,7 +454,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
   if (static_cast<int>(blockIdx.x) >= p.q_tiles) {   // the extra CTA of this (image, head): trailing query rows on the CUDA cores
-    if (p.dbg != 1) attn_tail_rows<kAttnThreads>(p, reinterpret_cast<float*>(smem), head, b, p.N - p.tail_rows, p.tail_rows);
+    if (p.dbg == 5) attn_tail_rows<kAttnThreads>(p, reinterpret_cast<float*>(smem), head, b, p.N - p.tail_rows, p.tail_rows);   // A/B: the CUDA-core routine
+    else if (p.dbg != 1) attn_tail_rows_mma(&tmQKV, p, smem, head, b, p.N - p.tail_rows, p.tail_rows);
     return;
   }
   if (p.dbg == 4) return;                             // timing experiments: only the trailing-row CTAs work
@@ -599,7 +756,22 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       pair_bar_sync(quarter);                                              // the other half-row warp wrote the other 32
     }
 
-    for (int j = 0; j < nkv; ++j) {
+    // A ragged last query tile (N = 1025: one valid row): warps whose 32 rows are all beyond N only keep the barriers moving --
+    // no TMEM reads, no exponentials, no P (their rows of P / O are never stored and do not touch other rows of the MMAs)
+    const bool idle_rows = !kBias && q0 + quarter * 32 >= p.N;
+    if (idle_rows) {
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait_relaxed(bar_s, j & 1);
+        if (j > 0) mbar_wait_relaxed(bar_o, (j - 1) & 1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_sfree);
+          mbar_arrive(bar_pready);
+        }
+      }
+    }
+    for (int j = 0; j < (idle_rows ? 0 : nkv); ++j) {
       ATT_TRACE(0);
       const float bh_cur = bh_next;
       if (kFused) {
@@ -801,7 +973,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     }
     mbar_wait(bar_o, (nkv - 1) & 1);
     tc_fence_after();
-
+    if (!idle_rows) {
     // ---- epilogue: this thread's 32 columns of O (TMEM) -> registers, fold the few trailing keys (if any),
     //      combine the two half-row sums, normalise, store
     const int q = q0 + row;
@@ -852,6 +1024,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       }
       if (half == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
     }
+    }   // !idle_rows
   }
   tc_fence_before();
   __syncthreads();
@@ -1234,7 +1407,8 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   // routine with exact two-pass softmax was tried and was far slower, 0.862 ms): every tile goes through the tensor-core path.
   const int tail_rows = N % kBQ;
   // (with dropout every row and key goes through the two tensor-core softmax paths, the only ones that apply the mask)
-  const bool vector_tail = !v6 && !dropout && tail_rows > 0 && tail_rows <= 8;
+  static const bool tail_tile = getenv("VDR_ATTN_TAIL_TILE") != nullptr;   // experiment: the trailing rows as a (mostly idle) ninth tile
+  const bool vector_tail = !v6 && !dropout && !tail_tile && tail_rows > 0 && tail_rows <= 8;
   p.no_key_fold = dropout ? 1 : 0;
   p.q_tiles = vector_tail ? N / kBQ : (N + kBQ - 1) / kBQ;
   p.tail_rows = vector_tail ? tail_rows : 0;
