@@ -93,12 +93,17 @@ __device__ __forceinline__ unsigned long long attn_gtime() {
   do {                                                                                                             \
     if (p.trace != nullptr && tid == 32 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 60 && j < 16) p.trace[j * 16 + (ev)] = attn_gtime(); \
   } while (0)
+#define ATT_TRACE_AT(row, ev)                                                                                      \
+  do {                                                                                                             \
+    if (p.trace != nullptr && threadIdx.x == 32 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 60) p.trace[(row) * 16 + (ev)] = attn_gtime(); \
+  } while (0)
 #define ISS_TRACE(ev)                                                                                              \
   do {                                                                                                             \
     if (p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 60 && j < 16) p.trace[j * 16 + 8 + (ev)] = attn_gtime(); \
   } while (0)
 #else
 #define ATT_TRACE(ev) do { } while (0)
+#define ATT_TRACE_AT(row, ev) do { } while (0)
 #define ISS_TRACE(ev) do { } while (0)
 #endif
 
@@ -419,6 +424,11 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
 // its bias is one scalar rel_h[q, kh] per block (prefetched from global memory a block ahead) plus the 64 rel_w[q, kw]
 // of its query row, which are the same for every block and sit in shared memory as fp16 (16 KB per CTA; |rel_w| of a
 // few units -> 1e-3 absolute in the exponent, below the bf16 rounding of P).
+__device__ __forceinline__ unsigned long long attn_gtime_always() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ unsigned int g_attn_sm_ticket[1024];   // experiment (VDR_ATTN_DBG >= 100): alternate start delay per SM slot
 
 // kFused (with kBias): the bias terms are not read from a table in HBM but computed by the CTA itself before its first key
@@ -1343,6 +1353,474 @@ flash_attn_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPa
   }
 }
 
+// ================================================================================================ v7: persistent tiles
+// The v5 timeline of one CTA (tools/attn_trace.py, B 120 / N 1024 / 12 heads, alone): 17.3 us of life for eight key blocks that
+// take 1.5 us each in the steady state -- 0.6 us of set-up (barriers, TMEM allocation), 1.0 us until Q / K_0 have arrived, a slow
+// first block, 0.8 us for the last PV to drain, 1.1 us of epilogue and the CTA exit / relaunch.  v7 runs the SAME per-block
+// pipeline (same warp roles, same TMEM columns, same softmax arithmetic as the plain v5 instantiation) but one resident CTA walks
+// over query tiles w = blockIdx.x, + gridDim.x, ...; every counter of the block pipeline (ring slot, barrier phase) simply keeps
+// running across the tile boundary, so the K / V tiles, the Q tile (double-buffered) and S_0 of the next tile are in flight while
+// the softmax warps finish the current one; TMEM and the barriers are set up once.
+//   O is safe across the boundary without a new barrier: PV_0 of the next tile is issued after "P_0 stored", which every softmax
+//   warp signals only after its epilogue has read the previous O out of TMEM.
+//   Q buffer (it & 1) is refilled with tile it + 2 after "S_last in registers" of tile it; the trailing-key warp's read of that
+//   buffer is ordered before it because the softmax warps wait for its "tail ready" before they signal that block.
+// The few trailing query rows (N mod 128 <= 8) run as a second, small kernel (flash_attn_tail_kernel: the mma.sync routine above).
+#ifdef VDR_ATTN_TRACE
+#define V7_TRACE(ev)                                                                                               \
+  do {                                                                                                             \
+    if (p.trace != nullptr && (threadIdx.x & 31) == 0 && blockIdx.x == 100 && g >= 16 && g < 32) p.trace[(g - 16) * 16 + (ev)] = attn_gtime(); \
+  } while (0)
+#else
+#define V7_TRACE(ev) do { } while (0)
+#endif
+constexpr int kV7Smem = 6 * kTileBytes /*Q0, Q1, 4 ring slots*/ + 256 + 3 * 2 * 128 * 4 + 8 * 2 * 128 + 8 * 128 * 4;
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+flash_attn_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sRing = base + 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);
+  uint64_t* bar_q = bars;            // [2] Q buffer landed
+  uint64_t* bar_kv = bars + 2;       // [4] ring slot landed
+  uint64_t* bar_s = bars + 6;        // S_g complete
+  uint64_t* bar_o = bars + 7;        // O += P_g V_g complete
+  uint64_t* bar_sfree = bars + 8;    // S_g in registers (8 warps)
+  uint64_t* bar_pready = bars + 9;   // P_g in TMEM (8 warps)
+  uint64_t* bar_tail = bars + 10;    // trailing keys' rows + scores of tile it ready (warp 10)
+  uint64_t* bar_tailfree = bars + 11;   // ... consumed by the epilogue of tile it (8 warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  float* s_max = reinterpret_cast<float*>(smem + 6 * kTileBytes + 256);   // [2][2][128]
+  float* s_sum = s_max + 2 * 2 * 128;                                      // [2][128]
+  uint4* s_tail = reinterpret_cast<uint4*>(s_sum + 2 * 128);               // [tail_keys][K row | V row]
+  float* s_dot = reinterpret_cast<float*>(s_tail + 8 * 16);                // [tail_keys][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = p.B * p.heads * p.q_tiles;
+  const int my_tiles = (static_cast<int>(blockIdx.x) < total) ? (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+  const int nkv_all = (p.N + kBKV - 1) / kBKV;
+  const int last_keys = p.N - (nkv_all - 1) * kBKV;
+  const int tail_keys = (last_keys <= 8 && nkv_all > 1 && !p.no_key_fold) ? last_keys : 0;
+  const int nkv = tail_keys ? nkv_all - 1 : nkv_all;
+  const int valid_last = tail_keys ? kBKV : last_keys;
+  const int ntail = (valid_last + 15) & ~15;
+  const int G_total = my_tiles * nkv;                  // key blocks this CTA walks through
+
+  auto tile_coords = [&](int it, int& b, int& head, int& x) {
+    const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+    x = w % p.q_tiles;
+    const int bh = w / p.q_tiles;
+    head = bh % p.heads;
+    b = bh / p.heads;
+  };
+  auto issue_tile = [&](int T) {   // ring tile T: even = K of global block T/2, odd = its V
+    const int G = T >> 1, it = G / nkv, j = G - it * nkv;
+    int b, head, x;
+    tile_coords(it, b, head, x);
+    const int slot = T & 3;
+    mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
+    tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (2 + slot), ((T & 1) ? 2 * p.d : p.d) + head * kHD, b * p.N + j * kBKV);
+  };
+  auto issue_q = [&](int it) {
+    int b, head, x;
+    tile_coords(it, b, head, x);
+    mbar_arrive_expect_tx(&bar_q[it & 1], kTileBytes);
+    tma_load_2d(&tmQKV, &bar_q[it & 1], smem + kTileBytes * (it & 1), head * kHD, b * p.N + x * kBQ);
+  };
+  if (tid == kSoftmaxWarps * 32) {
+    if (base & 1023u) { printf("vdr: attention smem base not 1024-byte aligned\n"); __trap(); }
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(&bar_q[0], 1);
+    mbar_init(&bar_q[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_kv[i], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_sfree, kSoftmaxWarps);
+    mbar_init(bar_pready, kSoftmaxWarps);
+    mbar_init(bar_tail, 1);
+    mbar_init(bar_tailfree, kSoftmaxWarps);
+    fence_barrier_init();
+    if (my_tiles > 0) issue_q(0);
+    for (int T = 0; T < 4 && T < 2 * G_total; ++T) issue_tile(T);
+    if (my_tiles > 1) issue_q(1);
+  }
+  if (warp == 0) tmem_alloc<kAttnTmemCols>(tmem_ptr);
+  if (p.dbg >= 100 && tid == 0) {   // experiment: the second CTA of an SM starts p.dbg ns late (the two resident CTAs would otherwise run in lockstep)
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (atomicAdd(&g_attn_sm_ticket[smid & 1023], 1u) & 1u) {
+      const unsigned long long t0 = attn_gtime_always();
+      while (attn_gtime_always() - t0 < static_cast<unsigned long long>(p.dbg)) __nanosleep(200);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
+
+  if (warp >= kSoftmaxWarps) {
+    // =============================================================== issuer warpgroup
+    reg_dec<32>();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+    if (warp == kSoftmaxWarps) {
+      // ---- K tiles, Q tiles + S = Q K^T
+      auto issue_s = [&](int g, int it, int j) {
+        if (j == 0) mbar_wait_relaxed(&bar_q[it & 1], (it >> 1) & 1);
+        const int T = 2 * g;
+        mbar_wait_relaxed(&bar_kv[T & 3], (T >> 2) & 1);
+        tc_fence_after();
+        { --g; V7_TRACE(15); ++g; }
+        const uint64_t dq = umma_desc_kmajor_sw128(base + (it & 1) * kTileBytes);
+        const uint64_t dk = umma_desc_kmajor_sw128(sRing + (T & 3) * kTileBytes);
+        const uint32_t idesc = (j == nkv - 1) ? umma_idesc_bf16(128, ntail) : idesc_s;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
+      };
+      if (G_total > 0) issue_s(0, 0, 0);
+      int it = 0, j = 0;
+      for (int g = 0; g < G_total; ++g) {
+        V7_TRACE(8);
+        mbar_wait_relaxed(bar_sfree, g & 1);               // S_g in registers: its S columns, K_g's slot (and, at j = nkv - 1, the Q buffer) are free
+        tc_fence_after();
+        V7_TRACE(9);
+        const bool last = (j == nkv - 1);
+        if (last && it + 2 < my_tiles && elect_one()) issue_q(it + 2);
+        __syncwarp();
+        const int jn = last ? 0 : j + 1, itn = last ? it + 1 : it;
+        if (g + 1 < G_total) issue_s(g + 1, itn, jn);
+        V7_TRACE(10);
+        if (g + 2 < G_total && elect_one()) issue_tile(2 * g + 4);
+        __syncwarp();
+        it = itn;
+        j = jn;
+      }
+    } else if (warp == kSoftmaxWarps + 2) {
+      // ---- the few trailing keys of every tile: K / V rows -> shared memory, q . k for the 128 query rows
+      if (tail_keys > 0) {
+        for (int it = 0; it < my_tiles; ++it) {
+          int b, head, x;
+          tile_coords(it, b, head, x);
+          if (it > 0) mbar_wait_relaxed(bar_tailfree, (it - 1) & 1);
+          const int colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
+          for (int i = lane; i < tail_keys * 16; i += 32) {
+            const int t = i >> 4, c = i & 15;
+            const __nv_bfloat16* krow = p.qkv + static_cast<int64_t>(b * p.N + nkv * kBKV + t) * p.ld_qkv;
+            s_tail[i] = __ldg(reinterpret_cast<const uint4*>(krow + (c < 8 ? colK : colV)) + (c & 7));
+          }
+          __syncwarp();
+          mbar_wait_relaxed(&bar_q[it & 1], (it >> 1) & 1);
+          const uint32_t sQ = base + (it & 1) * kTileBytes;
+          for (int t = 0; t < tail_keys; ++t) {
+            for (int i = 0; i < 4; ++i) {
+              const int r = lane + 32 * i;
+              float acc = 0.f;
+#pragma unroll 2
+              for (int c = 0; c < 8; ++c) {
+                uint4 qu;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qu.x), "=r"(qu.y), "=r"(qu.z), "=r"(qu.w)
+                             : "r"(sQ + r * 128 + ((c ^ (r & 7)) << 4)));
+                const uint4 u = s_tail[t * 16 + c];
+                const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+                const float2 q0v = unpack_bf16x2(qu.x), q1v = unpack_bf16x2(qu.y), q2v = unpack_bf16x2(qu.z), q3v = unpack_bf16x2(qu.w);
+                acc = fmaf(q0v.x, a0.x, acc); acc = fmaf(q0v.y, a0.y, acc);
+                acc = fmaf(q1v.x, a1.x, acc); acc = fmaf(q1v.y, a1.y, acc);
+                acc = fmaf(q2v.x, a2.x, acc); acc = fmaf(q2v.y, a2.y, acc);
+                acc = fmaf(q3v.x, a3.x, acc); acc = fmaf(q3v.y, a3.y, acc);
+              }
+              s_dot[t * 128 + r] = acc;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tail);
+        }
+      }
+    } else if (warp == kSoftmaxWarps + 1) {
+      // ---- V tiles + O += P V
+      int j = 0;
+      for (int g = 0; g < G_total; ++g) {
+        V7_TRACE(11);
+        mbar_wait_relaxed(bar_pready, g & 1);
+        tc_fence_after();
+        V7_TRACE(12);
+        if (g >= 1 && g + 1 < G_total) {                   // V_{g+1} into V_{g-1}'s slot
+          mbar_wait_relaxed(bar_o, (g - 1) & 1);
+          if (elect_one()) issue_tile(2 * g + 3);
+          __syncwarp();
+        }
+        const int T = 2 * g + 1;
+        mbar_wait_relaxed(&bar_kv[T & 3], (T >> 2) & 1);
+        tc_fence_after();
+        V7_TRACE(14);
+        const uint64_t dv0 = umma_desc_mnmajor_sw128(sRing + (T & 3) * kTileBytes);
+        const bool full = (j < nkv - 1 || ntail == kBKV);
+        if (elect_one()) {
+          if (full) {
+#pragma unroll
+            for (int k = 0; k < kBKV / 16; ++k)
+              umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          } else {
+            const int ksteps = ntail / 16;
+#pragma unroll 1
+            for (int k = 0; k < ksteps; ++k)
+              umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(bar_o);
+        }
+        __syncwarp();
+        V7_TRACE(13);
+        j = (j == nkv - 1) ? 0 : j + 1;
+      }
+    }
+  } else {
+    // =============================================================== softmax warpgroups
+    reg_inc<104>();
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_S + lane_sel + half * 64;
+    const uint32_t tP = tmem_P + lane_sel + half * 32;
+    const uint32_t tO = tmem_O + lane_sel + half * 32;
+    const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+    int g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      int b, head, x;
+      tile_coords(it, b, head, x);
+      const int q0 = x * kBQ;
+      const int row_base = b * p.N;
+      float m_ref = -INFINITY, l_run = 0.f;
+      const bool idle_rows = q0 + quarter * 32 >= p.N;   // ragged last query tile: these 32 rows do not exist
+      for (int j = 0; j < nkv; ++j, ++g) {
+        if (warp == 1) V7_TRACE(0);
+        mbar_wait(bar_s, g & 1);
+        tc_fence_after();
+        if (warp == 1) V7_TRACE(1);
+        if (tail_keys && j == nkv - 1) mbar_wait(bar_tail, it & 1);   // orders the trailing-key warp's Q reads before the Q refill (see above)
+        float alpha = 1.f;
+        bool moved = false;
+        float lsum;
+        float* xmax = s_max + (g & 1) * 256;
+        const bool narrow = (j == nkv - 1 && ntail < kBKV);
+        if (idle_rows) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sfree);
+          if (j > 0) mbar_wait(bar_o, (g - 1) & 1);
+        } else if (narrow) {
+          const int c_lo = half * 64, c_hi = min(ntail, c_lo + 64);
+          float mx = -INFINITY;
+          for (int c = c_lo; c < c_hi; c += 16) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_S + lane_sel + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c + i < valid_last) ? __uint_as_float(r[i]) : -INFINITY);
+          }
+          xmax[half * 128 + row] = mx;
+          pair_bar_sync(quarter);
+          mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]);
+          const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+          moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);
+          if (moved) {
+            alpha = ex2(m_ref - m_new);
+            m_ref = m_new;
+          }
+          lsum = 0.f;
+          if (j > 0) {
+            mbar_wait(bar_o, (g - 1) & 1);
+            tc_fence_after();
+          }
+          for (int c = c_lo; c < c_hi; c += 16) {
+            uint32_t r[16], w[8];
+            tmem_ld_32x32b_x16(tmem_S + lane_sel + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = (c + i < valid_last) ? ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_ref)) : 0.f;
+              const float p1 = (c + i + 1 < valid_last) ? ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_ref)) : 0.f;
+              lsum += p0 + p1;
+              w[i >> 1] = cvt_bf16x2(p0, p1);
+            }
+            tmem_st_32x32b_x8(tmem_P + lane_sel + (c >> 1), w);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sfree);
+          l_run = l_run * alpha + lsum;
+          if (j > 0 && moved) {
+            const uint64_t alpha2 = pack2(alpha, alpha);
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tO, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float a0, a1;
+              unpack2(mul2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2), a0, a1);
+              r[i] = __float_as_uint(a0);
+              r[i + 1] = __float_as_uint(a1);
+            }
+            tmem_st_32x32b_x32(tO, r);
+          }
+        } else {
+          uint32_t sr[2][32];
+          tmem_ld_32x32b_x32(tS, sr[0]);
+          tmem_ld_32x32b_x32(tS + 32, sr[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sfree);
+          if (warp == 1) V7_TRACE(2);
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = max3(mx0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+            mx1 = max3(mx1, __uint_as_float(sr[0][i + 2]), __uint_as_float(sr[0][i + 3]));
+            mx2 = max3(mx2, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+            mx3 = max3(mx3, __uint_as_float(sr[1][i + 2]), __uint_as_float(sr[1][i + 3]));
+          }
+          float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          xmax[half * 128 + row] = mx;
+          pair_bar_sync(quarter);
+          mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]);
+          const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+          moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);
+          if (moved) {
+            alpha = ex2(m_ref - m_new);
+            m_ref = m_new;
+          }
+          const uint64_t negm2 = pack2(-m_ref, -m_ref);
+          uint64_t lsum2 = 0ull;
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), scale2, negm2);
+              float p0, p1;
+              if ((kPolyMask >> ((i >> 1) & 7)) & 1u) {
+                exp2_poly2(x2, p0, p1);
+              } else {
+                float x0, x1;
+                unpack2(x2, x0, x1);
+                p0 = ex2(x0);
+                p1 = ex2(x1);
+              }
+              lsum2 = add2(lsum2, pack2(p0, p1));
+              pk[c * 16 + (i >> 1)] = cvt_bf16x2(p0, p1);
+            }
+          }
+          float l0, l1;
+          unpack2(lsum2, l0, l1);
+          l_run = l_run * alpha + (l0 + l1);
+          if (warp == 1) V7_TRACE(3);
+          if (j > 0) {
+            mbar_wait(bar_o, (g - 1) & 1);
+            tc_fence_after();
+            if (moved) {
+              const uint64_t alpha2 = pack2(alpha, alpha);
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(tO, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                float a0, a1;
+                unpack2(mul2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2), a0, a1);
+                r[i] = __float_as_uint(a0);
+                r[i + 1] = __float_as_uint(a1);
+              }
+              tmem_st_32x32b_x32(tO, r);
+            }
+          }
+          if (warp == 1) V7_TRACE(4);
+          tmem_st_32x32b_x32(tP, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pready);
+        if (warp == 1) V7_TRACE(5);
+      }
+      mbar_wait(bar_o, (g - 1) & 1);
+      tc_fence_after();
+      { --g; if (warp == 1) V7_TRACE(6); ++g; }
+      // ---- epilogue of this tile (the next tile's S_0 is already on its way)
+      if (!idle_rows) {
+        const int q = q0 + row;
+        float o[32];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tO, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
+        }
+        tc_fence_before();
+        if (tail_keys && p.dbg != 2) {
+          for (int t = 0; t < tail_keys; ++t) {
+            const float sdot = s_dot[t * 128 + row] * p.scale_log2;
+            const float m_new = fmaxf(m_ref, sdot);
+            const float a = ex2(m_ref - m_new);
+            const float pj = __bfloat162float(__float2bfloat16_rn(ex2(sdot - m_new)));
+            m_ref = m_new;
+            l_run = l_run * a + (half == 0 ? pj : 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 u = s_tail[t * 16 + 8 + half * 4 + c];
+              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              o[c * 8 + 0] = fmaf(o[c * 8 + 0], a, pj * a0.x); o[c * 8 + 1] = fmaf(o[c * 8 + 1], a, pj * a0.y);
+              o[c * 8 + 2] = fmaf(o[c * 8 + 2], a, pj * a1.x); o[c * 8 + 3] = fmaf(o[c * 8 + 3], a, pj * a1.y);
+              o[c * 8 + 4] = fmaf(o[c * 8 + 4], a, pj * a2.x); o[c * 8 + 5] = fmaf(o[c * 8 + 5], a, pj * a2.y);
+              o[c * 8 + 6] = fmaf(o[c * 8 + 6], a, pj * a3.x); o[c * 8 + 7] = fmaf(o[c * 8 + 7], a, pj * a3.y);
+            }
+          }
+        }
+        s_sum[half * 128 + row] = l_run;
+        pair_bar_sync(quarter);
+        const float l_tot = l_run + s_sum[(half ^ 1) * 128 + row];
+        const float inv = 1.f / l_tot;
+        if (q < p.N) {
+          __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD + half * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = cvt_bf16x2(o[i] * inv, o[i + 1] * inv);
+            w.y = cvt_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
+            w.z = cvt_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
+            w.w = cvt_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+            *reinterpret_cast<uint4*>(op + i) = w;
+          }
+          if (half == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
+        }
+      }
+      { --g; if (warp == 1) V7_TRACE(7); ++g; }
+      if (tail_keys) {   // the trailing-key scratch may be rewritten for the next tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tailfree);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kAttnTmemCols>(tmem_base);
+  }
+}
+
+// The trailing query rows of every (image, head) for the v7 grid: one CTA each (attn_tail_rows_mma)
+__global__ void __launch_bounds__(kAttnThreads, 2)
+flash_attn_tail_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  attn_tail_rows_mma(&tmQKV, p, smem, blockIdx.x, blockIdx.y, p.N - p.tail_rows, p.tail_rows);
+}
+constexpr int kTailSmem = 5 * kTileBytes + 256 + 1024;
+
 }  // namespace vdr
 
 static unsigned long long* g_attn_trace = nullptr;
@@ -1383,6 +1861,8 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV6Smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemFused);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_fwd_v7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV7Smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_fwd)");
     configured.current() = true;
   }
@@ -1413,6 +1893,27 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   p.q_tiles = vector_tail ? N / kBQ : (N + kBQ - 1) / kBQ;
   p.tail_rows = vector_tail ? tail_rows : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // v7 (persistent tiles; experiment, VDR_ATTN_V7=1): measured slower than the one-tile-per-CTA grid (0.672 vs 0.605 ms at N = 1024)
+  static const bool want_v7 = getenv("VDR_ATTN_V7") != nullptr;
+  if (!fused && rel == nullptr && !dropout && !v6 && want_v7) {
+    const int total = B * heads * p.q_tiles;
+    if (total > 0) {
+      int dev = 0, sms = 0;
+      cudaError_t e = cudaGetDevice(&dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(SM count)");
+      const int ctas = total < 2 * sms ? total : 2 * sms;
+      flash_attn_fwd_v7_kernel<<<ctas, kAttnThreads, kV7Smem, s>>>(tm, p);
+      count_launch();
+      VDR_CHECK_LAUNCH("flash_attn_fwd_v7_kernel");
+    }
+    if (vector_tail) {
+      flash_attn_tail_kernel<<<dim3(heads, B), kAttnThreads, kTailSmem, s>>>(tm, p);
+      count_launch();
+      VDR_CHECK_LAUNCH("flash_attn_tail_kernel");
+    }
+    return VDR_OK;
+  }
   dim3 grid(p.q_tiles + (vector_tail ? 1 : 0), heads, B);
   if (fused)
     flash_attn_fwd_kernel<true, false, true><<<grid, kAttnThreads, kAttnSmemFused, s>>>(tm, tm_rhi, tm_rlo, p);
