@@ -540,6 +540,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 
   if (warp >= kSoftmaxWarps) {
     // =============================================================== issuer warpgroup
+    // (32 is all the CTA's register pool leaves: 8 x 104 + 4 x 32 warps = the 960 warp-registers of a launch at 80 per thread;
+    //  setmaxnreg.inc of the softmax warpgroups never returns if the issuer warps keep more -- tried with 48)
     reg_dec<32>();
     // Two issuing threads so that the two dependent MMA chains of a block (S_{j+1} = Q K^T: 4 steps, O += P V:
     // 8 steps) are dispatched concurrently.
@@ -550,9 +552,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       // (exactly one lane, known to the compiler: operands go to uniform registers directly -- under `lane == 0` every
       // tcgen05.mma was wrapped in an ELECT / BRA.U.ANY waterfall and cost ~0.1 us of issue time, 0.5 us per S block and
       // 0.85 us per PV block in the round-2 traces)
-      auto issue_s = [&](int j) {
+      auto wait_k = [&](int j) { mbar_wait_relaxed(&bar_kv[(2 * j) & 3], ((2 * j) >> 2) & 1); };
+      auto issue_s = [&](int j) {    // (K_j has landed: wait_k(j) precedes the wait for the S columns)
         const int t = 2 * j;
-        mbar_wait_relaxed(&bar_kv[t & 3], (t >> 2) & 1);
         tc_fence_after();
         const uint64_t dq = umma_desc_kmajor_sw128(sQ);
         const uint64_t dk = umma_desc_kmajor_sw128(sRing + (t & 3) * kTileBytes);
@@ -608,9 +610,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         mbar_wait_relaxed(bar_tread, 0);                   // every softmax warp has taken its terms out of T
         tc_fence_after();
       }
+      wait_k(0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         if (lane == 0) ISS_TRACE(0);
+        if (j + 1 < nkv) wait_k(j + 1);                    // (long since landed: keeps the path from "S_j consumed" to the MMAs short)
         mbar_wait_relaxed(bar_sfree, j & 1);               // S_j is in registers -> K_j's slot and the S columns are free
         tc_fence_after();
         if (lane == 0) ISS_TRACE(1);
@@ -659,17 +663,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       // ---- V tiles + O += P V (warp-wide loop, instructions under elect.sync as above)
       for (int j = 0; j < nkv; ++j) {
         if (lane == 0) ISS_TRACE(3);
+        const int t = 2 * j + 1;
+        mbar_wait_relaxed(&bar_kv[t & 3], (t >> 2) & 1);   // V_j (landed long before P_j is ready)
         mbar_wait_relaxed(bar_pready, j & 1);              // P_j is in TMEM (and O rescaled if the maximum moved)
         tc_fence_after();
         if (lane == 0) ISS_TRACE(4);
-        if (j >= 1 && j + 1 < nkv) {                       // V_{j+1} goes into V_{j-1}'s slot: O_{j-1} must be complete.
-          mbar_wait_relaxed(bar_o, (j - 1) & 1);           // (waited BEFORE O_j is committed: a parity wait must never
-          if (elect_one()) issue_tile(2 * j + 3);          //  be two phases behind its barrier)
-          __syncwarp();
-        }
-        const int t = 2 * j + 1;
-        mbar_wait_relaxed(&bar_kv[t & 3], (t >> 2) & 1);
-        tc_fence_after();
         const uint64_t dv0 = umma_desc_mnmajor_sw128(sRing + (t & 3) * kTileBytes);
         // A = P from TMEM (16 bf16 = 8 columns per K step); O accumulates in TMEM across all key blocks.
         // Each K step covers 16 kv rows x 128 B of the V tile = 2048 B = 128 descriptor address units.
@@ -689,6 +687,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         }
         __syncwarp();
         if (lane == 0) ISS_TRACE(5);
+        if (j + 2 < nkv) {                                 // V_{j+2} into V_j's slot as soon as O_j is complete: this warp has nothing else
+          mbar_wait_relaxed(bar_o, j & 1);                 //  to do until P_{j+1} is ready, most of a block period later
+          if (elect_one()) issue_tile(2 * j + 5);
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -871,9 +874,34 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       } else {
         // this thread's 64 score columns -> registers, then hand the S columns back
         uint32_t sr[2][32];
+#if defined(VDR_X_FULLMAX)
+        float omx = -INFINITY;   // experiment: the maximum of the OTHER half's 64 scores, reduced by this thread itself (no exchange)
+        if (!kBias && !kFused) {
+          uint32_t t0[32], t1[32];
+          tmem_ld_32x32b_x32(tS + 64 - half * 128, t0);
+          tmem_ld_32x32b_x32(tS + 96 - half * 128, t1);
+          tmem_ld_32x32b_x32(tS, sr[0]);
+          tmem_ld_32x32b_x32(tS + 32, sr[1]);
+          tmem_ld_wait();
+          float n0 = -INFINITY, n1 = -INFINITY, n2 = -INFINITY, n3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            n0 = max3(n0, __uint_as_float(t0[i]), __uint_as_float(t0[i + 1]));
+            n1 = max3(n1, __uint_as_float(t0[i + 2]), __uint_as_float(t0[i + 3]));
+            n2 = max3(n2, __uint_as_float(t1[i]), __uint_as_float(t1[i + 1]));
+            n3 = max3(n3, __uint_as_float(t1[i + 2]), __uint_as_float(t1[i + 3]));
+          }
+          omx = fmaxf(fmaxf(n0, n1), fmaxf(n2, n3));
+        } else {
+          tmem_ld_32x32b_x32(tS, sr[0]);
+          tmem_ld_32x32b_x32(tS + 32, sr[1]);
+          tmem_ld_wait();
+        }
+#else
         tmem_ld_32x32b_x32(tS, sr[0]);
         tmem_ld_32x32b_x32(tS + 32, sr[1]);
         tmem_ld_wait();
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfree);
@@ -908,9 +936,19 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         // kFused: the scores already hold rel_w / scale (added by the MMA); rel_h of this half's grid row is one scalar per row --
         // the two half-row threads have DIFFERENT rel_h terms, so they exchange the maximum with the term added (log2 domain)
         if (kFused) mx = fmaf(mx, p.scale_log2, bh_cur);
+#if defined(VDR_X_FULLMAX)
+        if (!kBias && !kFused) {
+          mx = fmaxf(mx, omx);
+        } else
+#endif
+#if defined(VDR_X_NOEXCH)
+        if (kBias)
+#endif
+        {
         xmax[half * 128 + row] = mx;
         pair_bar_sync(quarter);
         mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]);
+        }
         const float m_new = fmaxf(m_ref, (kBias || kFused) ? mx : mx * p.scale_log2);
         moved = __any_sync(0xffffffffu, m_new - m_ref > 8.0f);   // warp-uniform (TMEM accesses are warp-wide) and, since both
         if (moved) {                                             //  half-row warps see the same row maxima, CTA-pair-uniform
@@ -930,6 +968,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             const uint64_t s2 = pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
             const uint64_t x2 = (kBias && !kFused) ? add2(s2, negm2) : fma2(s2, scale2, negm2);
             float p0, p1;
+#if defined(VDR_X_NOMATH)
+            if (true) {
+              unpack2(x2, p0, p1);
+            } else
+#endif
             if ((kPolyMask >> ((i >> 1) & 7)) & 1u) {   // a fixed subset of every 8 pairs: FMA-pipe exp2
               exp2_poly2(x2, p0, p1);
             } else {
