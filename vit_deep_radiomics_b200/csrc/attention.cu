@@ -86,7 +86,11 @@ static_assert(kFusedQwOff >= 5 * kTileBytes + 256 + 3 * 2 * 128 * 4 && kFusedQwO
 #ifdef VDR_ATTN_TRACE
 __device__ __forceinline__ unsigned long long attn_gtime() {
   unsigned long long t;
+#ifdef VDR_ATTN_TRACE_CLOCK   // SM cycles (1-cycle resolution; %globaltimer ticks every 32 ns): all stamps of a CTA come from one SM
+  asm volatile("mov.u64 %0, %clock64;" : "=l"(t));
+#else
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+#endif
   return t;
 }
 #define ATT_TRACE(ev)                                                                                              \
@@ -488,8 +492,15 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 
   auto issue_tile = [&](int t) {   // ring tile t: even = K block t/2 (slots 0/2), odd = V block t/2 (slots 1/3)
     const int slot = t & 3;
+#if defined(VDR_X_NOLOAD)
+    mbar_arrive(&bar_kv[slot]);        // experiment: no K / V traffic at all (the MMAs read whatever the slot holds)
+#elif defined(VDR_X_SAMELOAD)
+    mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);   // experiment: every CTA streams the same two tiles (L2 hits only)
+    tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? 2 * p.d : p.d, 0);
+#else
     mbar_arrive_expect_tx(&bar_kv[slot], kTileBytes);
     tma_load_2d(&tmQKV, &bar_kv[slot], smem + kTileBytes * (1 + slot), (t & 1) ? colV : colK, row_base + (t >> 1) * kBKV);
+#endif
   };
   if (tid == kSoftmaxWarps * 32) {
     // one thread initialises the barriers and immediately starts the first loads (Q, K0, V0, K1, V1), so that their
@@ -562,7 +573,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const uint32_t idesc = (j == nkv - 1) ? umma_idesc_bf16(128, ntail) : idesc_s;
         if (elect_one()) {
 #pragma unroll
+#if !defined(VDR_X_NOMMA)
           for (int k = 0; k < kHD / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+#endif
           if (kFused) {   // + rel_w[q, kw] / scale for both grid rows of the block: S[:, 0:64] += Qw I^T, S[:, 64:128] += Qw I^T
             const uint64_t dqw = umma_desc_kmajor_sw128(base + kFusedQwOff), did = umma_desc_kmajor_sw128(base + kFusedIdOff);
             constexpr uint32_t idw = umma_idesc_f16(128, 64);
@@ -673,11 +686,15 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         // Each K step covers 16 kv rows x 128 B of the V tile = 2048 B = 128 descriptor address units.
         const bool full = (j < nkv - 1 || ntail == kBKV);
         if (elect_one()) {
+#if defined(VDR_X_NOMMA)
+          if (false) {
+#else
           if (full) {
+#endif
 #pragma unroll
             for (int k = 0; k < kBKV / 16; ++k)
               umma_ts(tmem_O, tmem_P + k * 8, dv0 + static_cast<uint64_t>(k * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
-          } else {
+          } else if (!full) {
             const int ksteps = ntail / 16;
 #pragma unroll 1
             for (int k = 0; k < ksteps; ++k)
@@ -923,6 +940,20 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             }
           }
         }
+#if defined(VDR_X_NOSOFTMAX)
+        if (!kBias && !kFused && !kDrop) {   // experiment: the pipeline skeleton alone (S -> registers -> P without any arithmetic)
+          if (j > 0) {
+            mbar_wait(bar_o, (j - 1) & 1);
+            tc_fence_after();
+          }
+          tmem_st_32x32b_x32(tP, sr[0]);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_pready);
+          continue;
+        }
+#endif
         // block maximum of this half row (four independent chains), exchanged with the other half-row thread
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
