@@ -139,6 +139,15 @@ size_t vdr_volume_to_slices_resized_workspace_bytes(int S, int ch, int cw, int O
 int vdr_volume_to_slices_resized(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH, int OW,
                                  void* slices_bf16, void* workspace, size_t workspace_bytes, vdr_stream_t stream);
 
+/* The same staging (plain crop when OH x OW == ch x cw, else the resize above) into a CELL-PADDED layout: every cell_in x cell_in patch of
+ * the (OH, OW) slice lands in the top-left corner of a cell_out x cell_out cell of a (S, OH / cell_in * cell_out, OW / cell_in * cell_out)
+ * bf16 image whose other pixels the caller has zeroed once.  A 14-pixel patch grid (ViT-L/14, DINOv2; reference
+ * src/tfds_dense_descriptor.py:70-88,110-139) becomes a 16-pixel one that vdr_patch_embed_gemm's TMA im2col view addresses; the patch
+ * weights get zero columns at the pad positions. */
+int vdr_volume_to_slices_cells(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH, int OW,
+                               int cell_in, int cell_out, void* slices_bf16, void* workspace, size_t workspace_bytes,
+                               vdr_stream_t stream);
+
 /* Patch embedding as ONE TMA-fed im2col GEMM (K1: Conv2d(3, d, p, p) + position embedding of the backbone the reference
  * calls at tfds_dense_descriptor.py:123): the A operand is never materialised -- a 5-D tensor map (ix, iy, px, py, image)
  * over the bf16 pictures delivers each 128-patch x 64-k tile of the im2col matrix straight into the swizzled shared-memory

@@ -577,3 +577,58 @@ def test_run_table_batches_small_patients_bit_identically(cuda):
     assert tables[0][0] == tables[1][0] and tables[0][0] > 30
     assert torch.equal(tables[0][2], tables[1][2])
     assert torch.equal(tables[0][1], tables[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("crop,out_hw", [((3, 59, 5, 61), (56, 56)), ((0, 70, 2, 100), (56, 84))])
+def test_cell_padded_staging_layout(cuda, crop, out_hw):
+    """vdr_volume_to_slices_cells: the pixels of the plain staging (same crop / resize), each 14 x 14 patch in the corner of a 16 x 16
+    cell; every other pixel of the zeroed buffer stays zero."""
+    from vit_deep_radiomics_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    vol = torch.rand(72, 104, 5, generator=g).to(cuda)
+    plain = ops.volume_to_slices(vol, crop, out_hw=out_hw)
+    cells = ops.volume_to_slices(vol, crop, out_hw=out_hw, cells=(14, 16))
+    S, OH, OW = plain.shape
+    assert tuple(cells.shape) == (S, OH // 14 * 16, OW // 14 * 16)
+    c = cells.view(S, OH // 14, 16, OW // 14, 16)
+    assert torch.equal(c[:, :, :14, :, :14].reshape(S, OH, OW), plain)
+    assert float(c[:, :, 14:, :, :].float().abs().max()) == 0.0 and float(c[:, :, :, :, 14:].float().abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_vit_l14_cell_padded_tma_patch_embed(cuda, monkeypatch):
+    """ViT-L/14 at 224 x 224 (config C4): the cell-padded TMA im2col patch embedding (14-pixel patches in 16-pixel cells, zero weight
+    columns at the pads) against the materialised-im2col path of the same weights -- same bf16 products, another accumulation order."""
+    from vit_deep_radiomics_b200 import tfds_dense_descriptor as tdd
+    g = torch.Generator().manual_seed(3)
+    vol = torch.rand(230, 240, 3, generator=g).to(cuda)
+    crop = (2, 226, 9, 233)
+    model = tdd.load_model("vit_l14", img_hw=(224, 224), device=cuda, seed=5)
+    assert model.cell == (14, 16) and model.stage_hw == (256, 256) and model.pe_patch == 16
+    a = model.forward_volume(vol, crop).clone()
+    model.use_native_forward = False                      # the op-by-op path reads the same cell-padded slices
+    b = model.forward_volume(vol, crop).clone()
+    monkeypatch.setenv("VDR_NO_CELL_PAD", "1")
+    ref_model = tdd.load_model("vit_l14", img_hw=(224, 224), device=cuda, seed=5)
+    assert ref_model.cell is None
+    r = ref_model.forward_volume(vol, crop)
+    assert torch.equal(a, b)
+    # the patch embedding itself: same bf16 products, fp32 accumulation in another order -> at most a bf16 ulp of the embedded tokens
+    from vit_deep_radiomics_b200 import ops
+    S, N, d = 3, model.n_tokens, model.cfg["dim"]
+    sl_cell = ops.volume_to_slices(vol, crop, out_hw=(224, 224), cells=(14, 16))
+    sl = ops.volume_to_slices(vol, crop, out_hw=(224, 224))
+    x_cell = torch.zeros(S * N, d, dtype=torch.bfloat16, device=cuda)
+    x_ref = torch.zeros_like(x_cell)
+    ops.patch_embed(sl_cell, model.w["pe_w_tma"], model.w["pe_b"], model.w["pos"], 16, out=x_cell)
+    A = ops.im2col_gray_bf16(sl, 14)
+    ops.gemm(A, ref_model.w["pe_w"], ref_model.w["pe_b"], epilogue="residual", residual=ref_model.w["pos"], out=x_ref, k=ref_model.K,
+             out_group=(N - 1, N, 1), res_mod=(N - 1, 1))
+    dx = float((x_cell.float() - x_ref.float()).abs().max())
+    print("cell-padded TMA patch embedding vs materialised im2col GEMM: max abs %.3g (tokens of magnitude %.2f)" % (dx, float(x_ref.float().abs().max())))
+    assert dx <= 2.0 ** -7 * max(1.0, float(x_ref.float().abs().max())), dx
+    # ... and after 24 layers the two paths differ by what that last-bit difference grows to (the size of the bf16-vs-fp32 parity error)
+    err = float((a - r).abs().max()), float((a - r).norm() / r.norm())
+    print("cell-padded vs materialised path, descriptors (vit_l14@224): max abs %.3g, rms rel %.3g" % err)
+    assert err[0] < parity.BOUNDS["descriptors vit_l14@224x224 (C4)"]["abs"] and err[1] < parity.BOUNDS["descriptors vit_l14@224x224 (C4)"]["rel"], err

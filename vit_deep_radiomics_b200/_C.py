@@ -17,7 +17,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 #: every symbol include/vdr.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "vdr_version", "vdr_last_error_string", "vdr_launch_count",
-    "vdr_dropout_apply", "vdr_dropout_mask", "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
+    "vdr_dropout_apply", "vdr_dropout_mask", "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_volume_to_slices_cells", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd", "vdr_row_stats", "vdr_fold_layernorm",
     "vdr_flash_attn_fwd", "vdr_flash_attn_bwd_workspace_bytes", "vdr_flash_attn_bwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather", "vdr_mask_gather_table", "vdr_mask_count", "vdr_exclusive_scan_i64", "vdr_debug_set_gather_trace",
@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.vdr_volume_to_slices_resized_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.vdr_volume_to_slices_resized_workspace_bytes.restype = sz
     L.vdr_volume_to_slices_resized.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+    L.vdr_volume_to_slices_cells.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
     L.vdr_patch_embed_supported.argtypes = [i32, i32, i32]
     L.vdr_patch_embed_gemm.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp, i64, i32, vp]
     L.vdr_flash_attn_bwd_workspace_bytes.argtypes = [i32, i32, i32]

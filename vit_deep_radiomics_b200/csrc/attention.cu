@@ -954,6 +954,12 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           continue;
         }
 #endif
+#if defined(VDR_X_NOMAX)   // experiment (UNSAFE: no overflow guard): the reference maximum is the one of block 0, later blocks skip max / exchange / vote
+        const bool do_max = (j == 0) || kBias || kFused || kDrop;
+#else
+        constexpr bool do_max = true;
+#endif
+        if (do_max) {
         // block maximum of this half row (four independent chains), exchanged with the other half-row thread
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -985,6 +991,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         if (moved) {                                             //  half-row warps see the same row maxima, CTA-pair-uniform
           alpha = ex2(m_ref - m_new);
           m_ref = m_new;
+        }
         }
         const uint64_t negm2 = kFused ? pack2(bh_cur - m_ref, bh_cur - m_ref) : pack2(-m_ref, -m_ref);
         uint64_t lsum2 = 0ull;

@@ -41,12 +41,26 @@ im2col_patches_kernel(const float* __restrict__ src, int64_t sb, int64_t sc, int
   }
 }
 
+// Destination layout of the staged slices.  Plain: (S, OH, OW).  Cell-padded (cin < cout): every cin x cin patch of the slice sits in
+// the top-left corner of a cout x cout cell of a (S, OH / cin * cout, OW / cin * cout) image whose other pixels stay zero -- a 14-pixel
+// patch grid becomes a 16-pixel one, which the TMA im2col view of the patch embedding can address (32-byte box rows; the weights get
+// zero columns at the pad positions), vdr_volume_to_slices_cells.
+struct CellMap {
+  int cin, cout;   // 0, 0: plain
+  __device__ __forceinline__ int64_t index(int s, int y, int x, int OH, int OW) const {
+    if (cin == 0) return (static_cast<int64_t>(s) * OH + y) * OW + x;
+    const int Y = y / cin * cout + y % cin, X = x / cin * cout + x % cin;
+    const int OHp = OH / cin * cout, OWp = OW / cin * cout;
+    return (static_cast<int64_t>(s) * OHp + Y) * OWp + X;
+  }
+};
+
 // (H, W, S) f32 volume (slice index fastest, as np.dstack lays it out) -> (S, ch, cw) bf16 slices of
 // the crop window, through a 32x33 smem tile so that both the reads (along S) and the writes (along x)
 // are coalesced.  prepare_image's float32 cast becomes the bf16 operand cast here.
 __global__ void __launch_bounds__(256)
 volume_to_slices_kernel(const float* __restrict__ src, int W_full, int S, int y0, int x0, int ch, int cw,
-                        __nv_bfloat16* __restrict__ dst) {
+                        __nv_bfloat16* __restrict__ dst, CellMap cm) {
   __shared__ float tile[32][33];
   const int y = blockIdx.y;
   const int xb = blockIdx.x * 32, sb = blockIdx.z * 32;
@@ -60,7 +74,7 @@ volume_to_slices_kernel(const float* __restrict__ src, int W_full, int S, int y0
 #pragma unroll
   for (int j = threadIdx.y; j < 32; j += 8) {          // j: s within tile, threadIdx.x: x within tile
     const int sidx = sb + j, x = xb + threadIdx.x;
-    if (sidx < S && x < cw) dst[(static_cast<int64_t>(sidx) * ch + y) * cw + x] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    if (sidx < S && x < cw) dst[cm.index(sidx, y, x, ch, cw)] = __float2bfloat16_rn(tile[threadIdx.x][j]);
   }
 }
 
@@ -112,7 +126,7 @@ gauss_pass_kernel(const float* __restrict__ src, int64_t src_row_pitch, int64_t 
 // volume_to_slices_kernel (reads coalesced along s, writes along x).
 __global__ void __launch_bounds__(256)
 resize_to_slices_kernel(const float* __restrict__ src, int64_t src_row_pitch, int64_t src_col_pitch, int rows, int cols, int S,
-                        int OH, int OW, float sy, float sx, __nv_bfloat16* __restrict__ dst) {
+                        int OH, int OW, float sy, float sx, __nv_bfloat16* __restrict__ dst, CellMap cm) {
   __shared__ float tile[32][33];
   const int Y = blockIdx.y;
   const int xb = blockIdx.x * 32, sb = blockIdx.z * 32;
@@ -140,7 +154,7 @@ resize_to_slices_kernel(const float* __restrict__ src, int64_t src_row_pitch, in
 #pragma unroll
   for (int j = threadIdx.y; j < 32; j += 8) {          // j: s within tile, threadIdx.x: X within tile
     const int sidx = sb + j, X = xb + threadIdx.x;
-    if (sidx < S && X < OW) dst[(static_cast<int64_t>(sidx) * OH + Y) * OW + X] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    if (sidx < S && X < OW) dst[cm.index(sidx, Y, X, OH, OW)] = __float2bfloat16_rn(tile[threadIdx.x][j]);
   }
 }
 
@@ -218,19 +232,24 @@ extern "C" int vdr_im2col_patches(const float* src, int64_t sb, int64_t sc, int6
   return VDR_OK;
 }
 
-extern "C" int vdr_volume_to_slices(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw,
-                                    void* slices_bf16, vdr_stream_t stream) {
+static int volume_to_slices_impl(const char* who, const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, void* slices_bf16,
+                                 vdr::CellMap cm, vdr_stream_t stream) {
   using namespace vdr;
-  VDR_CHECK_ARG(vol && slices_bf16, VDR_EINVAL, "vdr_volume_to_slices: null pointer");
+  VDR_CHECK_ARG(vol && slices_bf16, VDR_EINVAL, "%s: null pointer", who);
   VDR_CHECK_ARG(H > 0 && W > 0 && S > 0 && ch > 0 && cw > 0 && y0 >= 0 && x0 >= 0 && y0 + ch <= H && x0 + cw <= W, VDR_EINVAL,
-                "vdr_volume_to_slices: crop window (%d:%d, %d:%d) outside the %dx%d volume", y0, y0 + ch, x0, x0 + cw, H, W);
-  VDR_CHECK_ARG(ch <= 65535 && (S + 31) / 32 <= 65535, VDR_EINVAL, "vdr_volume_to_slices: volume too large for the launch grid");
+                "%s: crop window (%d:%d, %d:%d) outside the %dx%d volume", who, y0, y0 + ch, x0, x0 + cw, H, W);
+  VDR_CHECK_ARG(ch <= 65535 && (S + 31) / 32 <= 65535, VDR_EINVAL, "%s: volume too large for the launch grid", who);
   dim3 grid((cw + 31) / 32, ch, (S + 31) / 32), block(32, 8);
   volume_to_slices_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      vol, W, S, y0, x0, ch, cw, static_cast<__nv_bfloat16*>(slices_bf16));
+      vol, W, S, y0, x0, ch, cw, static_cast<__nv_bfloat16*>(slices_bf16), cm);
   count_launch();
   VDR_CHECK_LAUNCH("volume_to_slices_kernel");
   return VDR_OK;
+}
+
+extern "C" int vdr_volume_to_slices(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw,
+                                    void* slices_bf16, vdr_stream_t stream) {
+  return volume_to_slices_impl("vdr_volume_to_slices", vol, H, W, S, y0, x0, ch, cw, slices_bf16, vdr::CellMap{0, 0}, stream);
 }
 
 static void resize_sigmas(int ch, int cw, int OH, int OW, float* sig_y, float* sig_x) {
@@ -249,13 +268,13 @@ extern "C" size_t vdr_volume_to_slices_resized_workspace_bytes(int S, int ch, in
   return static_cast<size_t>(passes) * ch * cw * S * sizeof(float);
 }
 
-extern "C" int vdr_volume_to_slices_resized(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH,
-                                            int OW, void* slices_bf16, void* workspace, size_t workspace_bytes,
-                                            vdr_stream_t stream) {
+static int volume_to_slices_resized_impl(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH, int OW,
+                                         void* slices_bf16, void* workspace, size_t workspace_bytes, vdr::CellMap cm,
+                                         vdr_stream_t stream) {
   using namespace vdr;
   VDR_CHECK_ARG(vol && slices_bf16, VDR_EINVAL, "vdr_volume_to_slices_resized: null pointer");
   VDR_CHECK_ARG(H > 0 && W > 0 && S > 0 && ch > 0 && cw > 0 && y0 >= 0 && x0 >= 0 && y0 + ch <= H && x0 + cw <= W, VDR_EINVAL,
-                "vdr_volume_to_slices_resized: crop window (%d:%d, %d:%d) outside the %dx%d volume", y0, y0 + ch, x0, x0 + cw, H, W);
+                "vdr_volume_to_slices_resized / _cells: crop window (%d:%d, %d:%d) outside the %dx%d volume", y0, y0 + ch, x0, x0 + cw, H, W);
   VDR_CHECK_ARG(OH > 0 && OW > 0 && OH <= 65535 && (S + 31) / 32 <= 65535, VDR_EINVAL, "vdr_volume_to_slices_resized: bad output size %dx%d", OH, OW);
   const size_t need = vdr_volume_to_slices_resized_workspace_bytes(S, ch, cw, OH, OW);
   VDR_CHECK_ARG(need == 0 || (workspace && workspace_bytes >= need), VDR_EWORKSPACE,
@@ -287,10 +306,30 @@ extern "C" int vdr_volume_to_slices_resized(const float* vol, int H, int W, int 
   }
   dim3 grid((OW + 31) / 32, OH, (S + 31) / 32), block(32, 8);
   resize_to_slices_kernel<<<grid, block, 0, s>>>(src, row_pitch, col_pitch, ch, cw, S, OH, OW, static_cast<float>(ch) / OH,
-                                                static_cast<float>(cw) / OW, static_cast<__nv_bfloat16*>(slices_bf16));
+                                                static_cast<float>(cw) / OW, static_cast<__nv_bfloat16*>(slices_bf16), cm);
   count_launch();
   VDR_CHECK_LAUNCH("resize_to_slices_kernel");
   return VDR_OK;
+}
+
+extern "C" int vdr_volume_to_slices_resized(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH,
+                                            int OW, void* slices_bf16, void* workspace, size_t workspace_bytes,
+                                            vdr_stream_t stream) {
+  return volume_to_slices_resized_impl(vol, H, W, S, y0, x0, ch, cw, OH, OW, slices_bf16, workspace, workspace_bytes, vdr::CellMap{0, 0}, stream);
+}
+
+// The same staging into the CELL-PADDED layout (see CellMap): output pixel (y, x) of the (OH, OW) slice goes to
+// (y / cell_in * cell_out + y % cell_in, x / cell_in * cell_out + x % cell_in) of a (S, OH / cell_in * cell_out, OW / cell_in * cell_out)
+// image; the caller zeroes that buffer once (the pad pixels are never written).  OH x OW == ch x cw: no resize, workspace unused.
+extern "C" int vdr_volume_to_slices_cells(const float* vol, int H, int W, int S, int y0, int x0, int ch, int cw, int OH, int OW,
+                                          int cell_in, int cell_out, void* slices_bf16, void* workspace, size_t workspace_bytes,
+                                          vdr_stream_t stream) {
+  using namespace vdr;
+  VDR_CHECK_ARG(cell_in > 0 && cell_out >= cell_in && OH > 0 && OW > 0 && OH % cell_in == 0 && OW % cell_in == 0, VDR_EINVAL,
+                "vdr_volume_to_slices_cells: %dx%d slices do not tile into %d-pixel cells (cell_out %d)", OH, OW, cell_in, cell_out);
+  const CellMap cm{cell_in, cell_out};
+  if (OH == ch && OW == cw) return volume_to_slices_impl("vdr_volume_to_slices_cells", vol, H, W, S, y0, x0, ch, cw, slices_bf16, cm, stream);
+  return volume_to_slices_resized_impl(vol, H, W, S, y0, x0, ch, cw, OH, OW, slices_bf16, workspace, workspace_bytes, cm, stream);
 }
 
 extern "C" int vdr_im2col_gray_bf16(const void* slices_bf16, int B, int H, int W, int patch, void* A_bf16,

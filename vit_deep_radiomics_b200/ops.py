@@ -191,20 +191,36 @@ def im2col_patches(src: torch.Tensor, strides, B: int, H: int, W: int, patch: in
     return out
 
 
-def volume_to_slices(vol: torch.Tensor, crop, out: torch.Tensor | None = None, out_hw=None) -> torch.Tensor:
+def volume_to_slices(vol: torch.Tensor, crop, out: torch.Tensor | None = None, out_hw=None, cells=None) -> torch.Tensor:
     """(H, W, S) f32 volume -> (S, ch, cw) bf16 slices of the crop window (y0, y1, x0, x1); with ``out_hw`` different
     from the window size the slices are resized as prepare_image does (tfds_dense_descriptor.py:40-44: skimage resize =
-    Gaussian anti-aliasing when shrinking + order-1 resampling, mirrored borders)."""
+    Gaussian anti-aliasing when shrinking + order-1 resampling, mirrored borders).
+    ``cells = (cell_in, cell_out)``: the slices are written in the cell-padded layout of vdr_volume_to_slices_cells
+    ((S, OH / cell_in * cell_out, OW / cell_in * cell_out); ``out`` must have been zeroed once: the pad pixels are never written)."""
     _req(vol, torch.float32, "vol")
     if vol.dim() != 3 or not vol.is_contiguous():
         raise ValueError("vol must be a contiguous (H, W, S) tensor")
     H, W, S = vol.shape
     y0, y1, x0, x1 = (int(v) for v in crop)
-    if out_hw is not None and tuple(int(v) for v in out_hw) != (y1 - y0, x1 - x0):
-        OH, OW = (int(v) for v in out_hw)
+    OH, OW = (int(v) for v in out_hw) if out_hw is not None else (y1 - y0, x1 - x0)
+    resized = (OH, OW) != (y1 - y0, x1 - x0)
+    need = _C.lib().vdr_volume_to_slices_resized_workspace_bytes(S, y1 - y0, x1 - x0, OH, OW) if resized else 0
+    if cells is not None:
+        cin, cout = (int(v) for v in cells)
+        if OH % cin or OW % cin or cout < cin:
+            raise ValueError(f"{OH}x{OW} slices do not tile into {cin}-pixel cells")
+        shape = (S, OH // cin * cout, OW // cin * cout)
+        if out is None:
+            out = torch.zeros(shape, dtype=torch.bfloat16, device=vol.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.bfloat16 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous bf16 tensor of shape {shape}")
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=vol.device)
+        _C.check(_C.lib().vdr_volume_to_slices_cells(vol.data_ptr(), H, W, S, y0, x0, y1 - y0, x1 - x0, OH, OW, cin, cout, out.data_ptr(),
+                                                     ws.data_ptr(), need, _stream()), "vdr_volume_to_slices_cells")
+        return out
+    if resized:
         if out is None:
             out = torch.empty((S, OH, OW), dtype=torch.bfloat16, device=vol.device)
-        need = _C.lib().vdr_volume_to_slices_resized_workspace_bytes(S, y1 - y0, x1 - x0, OH, OW)
         ws = torch.empty(max(need, 16), dtype=torch.uint8, device=vol.device)
         _C.check(_C.lib().vdr_volume_to_slices_resized(vol.data_ptr(), H, W, S, y0, x0, y1 - y0, x1 - x0, OH, OW, out.data_ptr(),
                                                        ws.data_ptr(), need, _stream()), "vdr_volume_to_slices_resized")

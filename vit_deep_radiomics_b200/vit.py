@@ -79,6 +79,15 @@ class ViTBackbone:
         self.device = torch.device(device)
         self.state_dict_f32 = state_dict if state_dict is not None else init_vit_state_dict(self.cfg, self.img_hw, seed)
         self._ws: dict = {}
+        # Patch sizes below 16 (ViT-L/14, DINOv2): the slices are staged CELL-PADDED -- every p x p patch in the corner of a 16 x 16 cell
+        # of a zeroed (gh*16, gw*16) image (vdr_volume_to_slices_cells) -- and the patch weights get zero columns at the pad positions, so
+        # the patch embedding is the same TMA im2col GEMM as for 16-pixel patches (a 14-pixel box row is 28 bytes, not a TMA box).
+        self.cell = None
+        if (p < 16 and not ops.patch_embed_supported(self.img_hw[0], self.img_hw[1], p) and os.environ.get("VDR_NO_CELL_PAD") is None
+                and ops.patch_embed_supported(self.grid[0] * 16, self.grid[1] * 16, 16)):
+            self.cell = (p, 16)
+        self.pe_patch = 16 if self.cell else p
+        self.stage_hw = (self.grid[0] * 16, self.grid[1] * 16) if self.cell else self.img_hw
         self.prepare()
 
     # -- weights -----------------------------------------------------------------------------
@@ -92,7 +101,12 @@ class ViTBackbone:
         w_pe[:, :K] = sd["patch_embed.weight"].reshape(d, K).to(dev).bfloat16()
         f32 = lambda k: sd[k].to(dev, torch.float32).contiguous()   # noqa: E731
         bf = lambda k: sd[k].to(dev).bfloat16().contiguous()        # noqa: E731
-        self.w = dict(pe_w=w_pe, pe_b=f32("patch_embed.bias"), cls=f32("cls_token").reshape(d),
+        w_pe_tma = w_pe
+        if self.cell:   # [d, 3, p, p] -> [d, 3, 16, 16] with zeros behind every patch row / below every patch
+            w4 = torch.zeros(d, 3, 16, 16, dtype=torch.bfloat16, device=dev)
+            w4[:, :, :p, :p] = sd["patch_embed.weight"].to(dev).bfloat16()
+            w_pe_tma = w4.reshape(d, 3 * 256).contiguous()
+        self.w = dict(pe_w=w_pe, pe_w_tma=w_pe_tma, pe_b=f32("patch_embed.bias"), cls=f32("cls_token").reshape(d),
                       pos=f32("pos_embed").reshape(self.n_tokens, d),
                       norm_w=f32("norm.weight"), norm_b=f32("norm.bias"), blocks=[])
         for i in range(self.cfg["depth"]):
@@ -121,8 +135,8 @@ class ViTBackbone:
                     setattr(blocks[i], name, blk[name].data_ptr())
         w = self.w
         self._native_blocks = blocks          # keeps the array alive
-        self._native = _C.VitWeights(d, self.cfg["depth"], self.cfg["heads"], p, self.img_hw[0], self.img_hw[1], 1e-6,
-                                     w["pe_w"].data_ptr(), w["pe_w"].stride(0), w["pe_b"].data_ptr(), w["cls"].data_ptr(),
+        self._native = _C.VitWeights(d, self.cfg["depth"], self.cfg["heads"], self.pe_patch, self.stage_hw[0], self.stage_hw[1], 1e-6,
+                                     w["pe_w_tma"].data_ptr(), w["pe_w_tma"].stride(0), w["pe_b"].data_ptr(), w["cls"].data_ptr(),
                                      w["pos"].data_ptr(), w["norm_w"].data_ptr(), w["norm_b"].data_ptr(),
                                      C.cast(blocks, C.POINTER(_C.VitBlock)))
 
@@ -153,15 +167,10 @@ class ViTBackbone:
         (S*N, d) f32 token matrix."""
         S = vol.shape[2]
         ws = self._workspace(S)
-        if "SL" not in ws:
-            ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
-        ops.volume_to_slices(vol, crop, out=ws["SL"], out_hw=self.img_hw)
-        if ops.PROFILE is None and self.use_native_forward:
-            return self._encode_native(S, ws["SL"])          # one C call enqueues the whole forward (same kernels, same order)
-        if ops.patch_embed_supported(self.img_hw[0], self.img_hw[1], self.cfg["patch"]):
-            return self._encode(S, images=ws["SL"])          # patch embedding reads the slices through a TMA im2col view
-        ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=self._op_buffers(S)["A"])
-        return self._encode(S)
+        if "SL" not in ws:   # (zeroed once: the pad pixels of the cell-padded layout are never written)
+            ws["SL"] = torch.zeros((S,) + self.stage_hw, dtype=torch.bfloat16, device=self.device)
+        ops.volume_to_slices(vol, crop, out=ws["SL"], out_hw=self.img_hw, cells=self.cell)
+        return self._encode_slices(S, ws["SL"])
 
     def forward_volumes(self, vols) -> torch.Tensor:
         """Several patients in ONE backbone batch: vols = [(vol (H, W, S_i) f32 CUDA, crop), ...]; their slices are staged one
@@ -172,16 +181,21 @@ class ViTBackbone:
         S = sum(int(v.shape[2]) for v, _ in vols)
         ws = self._workspace(S)
         if "SL" not in ws:
-            ws["SL"] = torch.empty((S,) + self.img_hw, dtype=torch.bfloat16, device=self.device)
+            ws["SL"] = torch.zeros((S,) + self.stage_hw, dtype=torch.bfloat16, device=self.device)
         s0 = 0
         for vol, crop in vols:
-            ops.volume_to_slices(vol, crop, out=ws["SL"][s0:s0 + vol.shape[2]], out_hw=self.img_hw)
+            ops.volume_to_slices(vol, crop, out=ws["SL"][s0:s0 + vol.shape[2]], out_hw=self.img_hw, cells=self.cell)
             s0 += int(vol.shape[2])
+        return self._encode_slices(S, ws["SL"])
+
+    def _encode_slices(self, S: int, slices: torch.Tensor) -> torch.Tensor:
+        """The staged (S,) + stage_hw bf16 slices through the encoder: the native forward, else the op-by-op path with the TMA im2col view,
+        else (geometries the view cannot address) the materialised im2col matrix."""
         if ops.PROFILE is None and self.use_native_forward:
-            return self._encode_native(S, ws["SL"])
-        if ops.patch_embed_supported(self.img_hw[0], self.img_hw[1], self.cfg["patch"]):
-            return self._encode(S, images=ws["SL"])
-        ops.im2col_gray_bf16(ws["SL"], self.cfg["patch"], out=self._op_buffers(S)["A"])
+            return self._encode_native(S, slices)            # one C call enqueues the whole forward (same kernels, same order)
+        if ops.patch_embed_supported(self.stage_hw[0], self.stage_hw[1], self.pe_patch):
+            return self._encode(S, images=slices)            # patch embedding reads the slices through a TMA im2col view
+        ops.im2col_gray_bf16(slices, self.cfg["patch"], out=self._op_buffers(S)["A"])
         return self._encode(S)
 
     def forward_tokens(self, src: torch.Tensor, strides, B: int) -> torch.Tensor:
@@ -200,7 +214,7 @@ class ViTBackbone:
         ws = self._op_buffers(B)
         # patch embedding GEMM: bias + pos-embed fused, rows written behind each image's CLS row
         if images is not None:
-            ops.patch_embed(images, w["pe_w"], w["pe_b"], w["pos"], cfg["patch"], out=ws["X"])
+            ops.patch_embed(images, w["pe_w_tma"], w["pe_b"], w["pos"], self.pe_patch, out=ws["X"])
         else:
             ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=ws["X"], k=self.K,
                      out_group=(Np, N, 1), res_mod=(Np, 1))
