@@ -62,3 +62,28 @@ def test_extract_patient_features_device_augmentation_equals_host_loop(cuda):
         assert a.shape == b.shape and np.array_equal(a, b)
     for a, b in zip(f_h, f_d):
         assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_pipelined_augmentation_equals_copy_by_copy_device_loop(cuda):
+    """The pipelined device loop (masks + plans first, ROI read-backs on a copy stream behind the next backbone) returns what the
+    copy-by-copy device calls return, and its arrays are caller-owned: a second patient does not overwrite the first one's."""
+    from vit_deep_radiomics_b200 import ops, synth, tfds_dense_descriptor as tdd
+    img, mask, res, name = synth.make_case("C1")
+    model = tdd.load_model(name, img_hw=img.shape[:2], device=cuda, seed=11)
+    img_d = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(cuda)
+    mask_d = torch.from_numpy(np.ascontiguousarray(mask).view(np.uint8)).to(cuda)
+    grid = [(f, a) for f in tdd.AUG_FLIPS for a in tdd.AUG_ANGLES]
+    got = tdd._augmented_features_device(model, img_d, mask_d, "mask_bool", grid)
+    keep = [(np.array(f[0]), np.array(m[0])) for f, m in got]
+    again = tdd._augmented_features_device(model, torch.flip(img_d, dims=(2,)).contiguous(), mask_d, "mask_bool", grid)
+    assert len(got) == len(again) == 12
+    for k, (flip, angle) in enumerate(grid):
+        i = ops.flip_rotate_volume(img_d, flip, angle, kind="image")
+        m = ops.flip_rotate_volume(mask_d, flip, angle, kind="mask_bool")
+        want_f, want_m = tdd.generate_features_device(model, i, m)
+        assert len(want_f) == len(got[k][0]) == img.shape[2]
+        for a, b in zip(want_f, got[k][0]):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        for a, b in zip(want_m, got[k][1]):
+            assert a.dtype == b.dtype == np.bool_ and np.array_equal(a, b)
+        assert np.array_equal(keep[k][0], got[k][0][0]) and np.array_equal(keep[k][1], got[k][1][0])

@@ -195,6 +195,130 @@ def generate_features_device(model, img_dev, mask_dev, max_batch=None):
     return [feats[s] for s in range(S)], [np.ascontiguousarray(mask_c[:, :, s]) for s in range(S)]
 
 
+class _RoiReadback:
+    """Read-back ring of the augmentation loop: the ROI crop of every augmented copy (descriptors (S, h_f, w_f, D) f32 and pixel
+    masks (h_m, w_m, S) u8) is packed on the main stream into a device slot, copied into pinned staging on a copy stream and
+    turned into caller-owned NumPy arrays by one worker thread, while the main stream is already in the backbone of the next
+    copy.  Results come back in submission order from ``finish``."""
+
+    def __init__(self, device, slots):
+        import queue
+        import threading
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = slots                      # persistent across patients (pinned staging is expensive to allocate)
+        for slot in slots:
+            slot.setdefault("cap_f", 0), slot.setdefault("cap_m", 0)
+            slot["idle"] = threading.Semaphore(1)
+        self.jobs = queue.Queue()
+        self.results = []
+        self.error = None
+        self.n = 0
+        self.worker = threading.Thread(target=self._drain, daemon=True)
+        self.worker.start()
+
+    def _drain(self):
+        while True:
+            job = self.jobs.get()
+            if job is None:
+                return
+            slot, copied, fshape, mshape = job
+            try:
+                copied.synchronize()                                        # (releases the GIL)
+                nf, nm = int(np.prod(fshape)), int(np.prod(mshape))
+                feats = np.array(slot["pin_f"][:nf].numpy().reshape(fshape))      # caller-owned copies: the staging is reused
+                masks = np.array(slot["pin_m"][:nm].numpy().reshape(mshape))
+                self.results.append((feats, masks))
+            except BaseException as e:   # surfaced by finish()
+                self.error = e
+                self.results.append(None)
+            finally:
+                slot["idle"].release()
+
+    def submit(self, feat_view, mask_view):
+        """feat_view / mask_view: (strided) device views, valid on the current stream until the next backbone launch."""
+        slot = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        slot["idle"].acquire()                                              # the worker has emptied this slot's staging
+        nf, nm = feat_view.numel(), mask_view.numel()
+        if slot["cap_f"] < nf:
+            slot.update(cap_f=nf, dev_f=torch.empty(nf, dtype=torch.float32, device=self.device),
+                        pin_f=torch.empty(nf, dtype=torch.float32).pin_memory())
+        if slot["cap_m"] < nm:
+            slot.update(cap_m=nm, dev_m=torch.empty(nm, dtype=torch.uint8, device=self.device),
+                        pin_m=torch.empty(nm, dtype=torch.uint8).pin_memory())
+        main = torch.cuda.current_stream(self.device)
+        # (the slot's previous D2H was synchronised by the worker before it released the slot: dev_f / dev_m are free)
+        slot["dev_f"][:nf].view(feat_view.shape).copy_(feat_view)
+        slot["dev_m"][:nm].view(mask_view.shape).copy_(mask_view)
+        packed = torch.cuda.Event()
+        packed.record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(packed)
+            slot["pin_f"][:nf].copy_(slot["dev_f"][:nf], non_blocking=True)
+            slot["pin_m"][:nm].copy_(slot["dev_m"][:nm], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.stream)
+        self.jobs.put((slot, copied, tuple(feat_view.shape), tuple(mask_view.shape)))
+
+    def finish(self):
+        self.jobs.put(None)
+        self.worker.join()
+        if self.error is not None:
+            raise self.error
+        return self.results
+
+
+def _augmented_features_device(model, img_dev, mask_dev, mask_kind, grid):
+    """The augmentation grid of one patient on the device, pipelined: ``grid`` = [(flip, angle), ...].
+    1. every augmented MASK first (cheap) and all their union bounding boxes in ONE read-back -> the crop / ROI plans;
+    2. per copy: image flip / rotation -> batched backbone -> ROI crops handed to the read-back ring (`_RoiReadback`).
+    Per copy the same values as ``generate_features_device`` (same kernels, same plans); only the order of the waits differs.
+    Returns [(features_list, mask_list)] per grid entry."""
+    ex = getattr(model, "_extractor", None)
+    if ex is None:
+        ex = model._extractor = PointCloudExtractor(model)
+    H, W, S = mask_dev.shape
+    boxes = torch.empty((len(grid), 6), dtype=torch.int32, device=model.device)
+    masks = []
+    for k, (flip_type, angle) in enumerate(grid):
+        m = ops.flip_rotate_volume(mask_dev, flip_type, angle, kind=mask_kind)
+        ops.mask_bbox(m, out=boxes[k])
+        masks.append(m)
+    boxes_h = boxes.cpu().numpy()
+    plans = []
+    for k in range(len(grid)):
+        cmin, cmax, rmin, rmax = (int(v) for v in boxes_h[k, :4])
+        if cmax < cmin:
+            raise ValueError("extract_coords: empty mask")
+        plan = _plan_from_bbox(model, H, W, (rmin, rmax, cmin, cmax))
+        plans.append(plan if plan is not None else _plan(model, masks[k].cpu().numpy()))
+    if not hasattr(ex, "roi_slots"):
+        ex.roi_slots = [dict() for _ in range(3)]
+    ring = _RoiReadback(model.device, ex.roi_slots)
+    d, off = model.feature_dim, model.token_offset
+    gh, gw = model.grid
+    image = None
+    try:
+        for k, (flip_type, angle) in enumerate(grid):
+            plan = plans[k]
+            image = ops.flip_rotate_volume(img_dev, flip_type, angle, kind="image", out=image)
+            tok = _forward_volume(model, image, plan)
+            fy0, fy1, fx0, fx1 = plan["feat_roi"]
+            y0, y1, x0, x1 = plan["crop"]
+            my0, my1, mx0, mx1 = plan["mask_roi"]
+            ring.submit(tok.view(S, model.n_tokens, d)[:, off:, :].reshape(S, gh, gw, d)[:, fy0:fy1, fx0:fx1, :],
+                        masks[k][y0 + my0:y0 + my1, x0 + mx0:x0 + mx1])
+            masks[k] = None
+    finally:
+        results = ring.finish()
+    out = []
+    for feats, mask_c in results:
+        mask_c = mask_c > 0
+        out.append(([feats[s] for s in range(S)], [np.ascontiguousarray(mask_c[:, :, s]) for s in range(S)]))
+    return out
+
+
 def _as_pinned_pair(img_3d, mask_3d):
     img_t = img_3d if isinstance(img_3d, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(img_3d, dtype=np.float32))
     if isinstance(mask_3d, torch.Tensor):
@@ -530,14 +654,15 @@ def extract_patient_features(model, img_raw, mask_raw, patient_id, label, datase
         img_dev = torch.as_tensor(np.ascontiguousarray(img_raw)).to(model.device)
         mask_kind = "mask_bool" if mask_raw.dtype == np.bool_ else "mask_u8"
         mask_dev = torch.as_tensor(np.ascontiguousarray(mask_raw).view(np.uint8)).to(model.device)
+        # all 12 copies through the pipelined device loop (ROI read-backs overlap the next copy's backbone)
+        aug_grid = [(f, a) for f in AUG_FLIPS for a in AUG_ANGLES]
+        device_results = iter(_augmented_features_device(model, img_dev, mask_dev, mask_kind, aug_grid))
     for flip_type in AUG_FLIPS:
         if not on_device:
             image_flip, mask_flip = flip_image(img_raw, mask_raw, flip_type)
         for angle in AUG_ANGLES:
             if on_device:
-                image = ops.flip_rotate_volume(img_dev, flip_type, angle, kind="image")
-                mask = ops.flip_rotate_volume(mask_dev, flip_type, angle, kind=mask_kind)
-                features, features_mask = generate_features_device(model, image, mask)
+                features, features_mask = next(device_results)
             else:
                 image, mask = rotate_image(image_flip, mask_flip, angle)
                 features, features_mask = gen(model=model, img_3d=image, mask_3d=mask,
