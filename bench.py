@@ -417,12 +417,16 @@ def bench_extraction(D: Dist, case: str, steps: int, warmup: int, *, profile: bo
     if rank == 0:
         cb, _, dense, (s0, ns) = cpu_extraction(case, cpu_slices, weights=model.state_dict_f32)
         rec["cpu_baseline"] = cb
-        x = torch.from_numpy(np.ascontiguousarray(np.moveaxis(vols[0][0][:, :, s0:s0 + min(ns, 2)], -1, 0))).to(dev)
-        got = model.dense_descriptors(x).cpu().numpy().astype(np.float64)
+        # (through forward_volume = the timed path: slice staging -> TMA im2col patch embedding on channel-summed weights -> native forward)
+        k = min(ns, 2)
+        sub_vol = torch.from_numpy(np.ascontiguousarray(np.asarray(vols[0][0][:, :, s0:s0 + k], dtype=np.float32))).to(dev)
+        gh_, gw_ = model.grid
+        tok = model.forward_volume(sub_vol, (0, H, 0, W))
+        got = tok.view(k, model.n_tokens, dim)[:, model.token_offset:, :].reshape(k, gh_, gw_, dim).cpu().numpy().astype(np.float64)
         want = dense[:got.shape[0]].astype(np.float64)
         g2, w2 = got.reshape(-1, dim), want.reshape(-1, dim)
         cos = (g2 * w2).sum(1) / (np.linalg.norm(g2, axis=1) * np.linalg.norm(w2, axis=1))
-        rec["parity"] = {"what": f"bf16 device descriptors vs the fp32 oracle, {got.shape[0]} slices of this workload ({model_name}@{H}x{W})",
+        rec["parity"] = {"what": f"bf16 device descriptors (forward_volume, the timed path) vs the fp32 oracle, {got.shape[0]} slices of this workload ({model_name}@{H}x{W})",
                          "max_abs": float(np.abs(got - want).max()), "rms_rel": float(np.sqrt(((got - want) ** 2).sum() / (want ** 2).sum())),
                          "min_cosine": float(cos.min()), "gather_indices": "bit-exact (tests/test_gpu_gather.py, test_gpu_pipeline.py)"}
     return rec

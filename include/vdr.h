@@ -160,6 +160,14 @@ int vdr_patch_embed_supported(int H, int W, int patch);
 int vdr_patch_embed_gemm(const void* images_bf16, int B, int C, int H, int W, int patch, const void* Wpe_bf16,
                          int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d,
                          vdr_stream_t stream);
+/* The same for gray pictures (B, H, W) against CHANNEL-SUMMED weights Wsum (d, p*p) = Wpe[:, 0] + Wpe[:, 1] + Wpe[:, 2] (summed in
+ * f32, rounded to bf16 once): gray2rgb (:41) feeds one picture to all three input channels, so the convolution is
+ * patch . (W_r + W_g + W_b) -- K = p*p, a third of the MMA work and one read of the picture instead of three.
+ * token_offset = rows in front of every image's patch tokens in X and pos: 1 (the CLS row of a ViT) or 0 (SAM's image encoder,
+ * `model.image_encoder` of load_medsam, tfds_dense_descriptor.py:91-107). */
+int vdr_patch_embed_gemm_gray(const void* images_bf16, int B, int H, int W, int patch, const void* Wsum_bf16,
+                              int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d,
+                              int token_offset, vdr_stream_t stream);
 
 /* CLS rows of the token matrix: X[b*N + 0, :] = cls[:] + pos[0, :]   (f32 params -> bf16 tokens) */
 int vdr_write_cls_rows(const float* cls, const float* pos0, void* X_bf16, int B, int N, int d,
@@ -197,6 +205,7 @@ typedef struct {
   const float* pos;                           /* (N, dim) */
   const float *norm_w, *norm_b;
   const vdr_vit_block* blocks;
+  const void* pe_w_gray; int64_t pe_gray_ldw; /* optional: channel-summed patch weights (dim, patch^2), used for C = 1 pictures */
 } vdr_vit_weights;
 
 size_t vdr_vit_forward_workspace_bytes(const vdr_vit_weights* weights, int B);
@@ -453,6 +462,50 @@ int vdr_attn_relpos_windows_fwd(const void* qkv_bf16, int64_t ld_qkv, const floa
                                 float scale, vdr_stream_t stream);
 int vdr_im2col3x3_tokens(const void* X_bf16, int64_t ldx, void* A_bf16, int64_t lda, int B, int H, int W, int C,
                          vdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SAM's image encoder as one call (the reference's DEFAULT backbone: load_medsam + `model.image_encoder(img_tensor)`,
+ * src/tfds_dense_descriptor.py:91-107,123; segment_anything ImageEncoderViT: patch_embed, pos_embed, blocks[i].{norm1, attn.qkv,
+ * attn.proj, attn.rel_pos_h / rel_pos_w, norm2, mlp.lin1, mlp.lin2}, neck): every kernel enqueued on `stream`, no host
+ * synchronisation, no allocation.
+ *   blocks      HOST array of `depth` entries.  The LayerNorms are folded into the GEMMs that consume them: qkv_wf / qkv_bf / qkv_cs
+ *               and fc1_wf / fc1_bf / fc1_cs from vdr_fold_layernorm are REQUIRED; qkv_b is the unfolded qkv bias (what a window's
+ *               pad token projects to).  rel_hi / rel_lo = the split [rel_pos_h ; rel_pos_w] tables of the block's extent
+ *               (window x window, or the whole token grid when window == 0 = a global-attention block).
+ *   images_bf16 (B, H, W) gray slices (gray2rgb :41 is folded into the channel-summed patch weights pe_w_gray when the geometry
+ *               tiles into TMA im2col boxes, else the slices are expanded in the workspace), or NULL with
+ *   im2col_bf16 (B*N, 3*patch^2) the materialised patch matrix (k = (c, iy, ix)) of RGB pictures (vdr_im2col_patches)
+ *   descriptors (B*N, out_chans) f32 with row pitch ld_out, N = (H/patch)*(W/patch) tokens in (row, col) order: the
+ *               (64, 64, 256) map get_dense_descriptor returns per slice (:124-126), for B slices
+ *   workspace   >= vdr_sam_forward_workspace_bytes(weights, B), 256-byte aligned
+ */
+typedef struct {
+  const void* qkv_wf; const float* qkv_bf; const float* qkv_cs;   /* norm1 folded into attn.qkv: (3*dim, dim) bf16, bias', column sums */
+  const float* qkv_b;                                              /* the unfolded qkv bias (3*dim) */
+  const void* proj_w; const float* proj_b;                         /* (dim, dim) */
+  const void* fc1_wf; const float* fc1_bf; const float* fc1_cs;   /* norm2 folded into mlp.lin1: (4*dim, dim) */
+  const void* fc2_w;  const float* fc2_b;                          /* (dim, 4*dim) */
+  const void* rel_hi; const void* rel_lo;                          /* bf16 hi / lo parts of [rel_pos_h ; rel_pos_w] */
+  int window;                                                      /* 0 = global attention */
+} vdr_sam_block;
+
+typedef struct {
+  int dim, depth, heads, patch, H, W, out_chans;
+  float eps;                                  /* LayerNorm epsilon (<= 0: 1e-6) */
+  const void* pe_w; int64_t pe_ldw;           /* (dim, 3*patch^2) bf16, k = (c, iy, ix) */
+  const void* pe_w_gray; int64_t pe_gray_ldw; /* optional: channel-summed (dim, patch^2) for gray slices (vdr_patch_embed_gemm_gray) */
+  const float* pe_b;
+  const float* pos;                           /* (N, dim) */
+  const void* neck0;                          /* (out_chans, dim) bf16: 1x1 conv */
+  const float *neck1_w, *neck1_b;             /* LayerNorm2d */
+  const void* neck2;                          /* (out_chans, 9*out_chans) bf16: 3x3 conv weight permuted to (out, ky, kx, in) */
+  const float *neck3_w, *neck3_b;
+  const vdr_sam_block* blocks;
+} vdr_sam_weights;
+
+size_t vdr_sam_forward_workspace_bytes(const vdr_sam_weights* weights, int B);
+int vdr_sam_forward(const vdr_sam_weights* weights, const void* images_bf16, const void* im2col_bf16, int B, float* descriptors,
+                    int64_t ld_out, void* workspace, size_t workspace_bytes, vdr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -100,7 +100,8 @@ def test_struct_layouts_match_the_header(tmp_path):
     import subprocess
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
-    pairs = {"vdr_gemm_args": _C.GemmArgs, "vdr_vit_block": _C.VitBlock, "vdr_vit_weights": _C.VitWeights, "vdr_dropout": _C.Dropout}
+    pairs = {"vdr_gemm_args": _C.GemmArgs, "vdr_vit_block": _C.VitBlock, "vdr_vit_weights": _C.VitWeights, "vdr_dropout": _C.Dropout,
+             "vdr_sam_block": _C.SamBlock, "vdr_sam_weights": _C.SamWeights}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "vdr.h")}"', "int main(void) {"]
     for cname, cls in pairs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -182,7 +182,7 @@ def test_gemm_argument_errors(cuda):
 
 
 @pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (2, 197, 6), (1, 1025, 2), (3, 300, 4), (1, 7, 1), (2, 257, 16),
-                                         (2, 136, 3), (2, 1030, 2), (3, 645, 2), (2, 2, 1), (5, 1025, 12)])   # 8 / 6 / 5 / 2 trailing rows: the mma.sync tail CTA
+                                         (2, 136, 3), (2, 1030, 2), (3, 645, 2), (2, 2, 1), (5, 1025, 12), (2, 250, 2), (3, 1273, 1)])   # 8 / 6 / 5 / 2 trailing rows: the mma.sync tail CTA
 def test_flash_attention(cuda, B, N, heads):
     from vit_deep_radiomics_b200 import ops
     torch.manual_seed(B * 1000 + N)
@@ -291,6 +291,36 @@ def test_patch_embed_tma_im2col_matches_materialised_path(cuda, B, C, H, W, d):
     want = a32 @ w_pe.float().t() + bias + pos[1:].repeat(B, 1)
     got = x.view(B, N, d)[:, 1:].reshape(B * Np, d).float()
     assert (got - want).abs().max() <= 0.02 * want.abs().max()
+
+
+@pytest.mark.parametrize("B,H,W,d", [(3, 512, 512, 768), (2, 256, 256, 384)])
+def test_patch_embed_gray_channel_summed_weights(cuda, B, H, W, d):
+    """vdr_patch_embed_gemm_gray: gray pictures against W_r + W_g + W_b (K = p*p) == the exact fp32 patch embedding of the
+    gray2rgb picture within the rounding of the summed bf16 weights, and agrees with the 3-channel TMA path."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(5)
+    p = 16
+    imgs = torch.rand((B, H, W), device=cuda).bfloat16()
+    gh, gw = H // p, W // p
+    Np, N = gh * gw, gh * gw + 1
+    w4 = torch.randn(d, 3, p, p, device=cuda) * 0.05
+    w_sum = w4.sum(dim=1).reshape(d, p * p).bfloat16().contiguous()
+    bias, pos = torch.randn(d, device=cuda), torch.randn(N, d, device=cuda)
+    x = torch.full((B * N, d), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.patch_embed(imgs, w_sum, bias, pos, p, out=x, channel_summed=True)
+    assert torch.all(x.view(B, N, d)[:, 0] == 7.0)
+    a32 = imgs.float().reshape(B, gh, p, gw, p).permute(0, 1, 3, 2, 4).reshape(B * Np, p * p)
+    got = x.view(B, N, d)[:, 1:].reshape(B * Np, d).float()
+    want_sum = a32 @ w_sum.float().t() + bias + pos[1:].repeat(B, 1)          # same bf16 operands: only the output rounding differs
+    assert (got - want_sum).abs().max() <= 0.006 * want_sum.abs().max()
+    want = a32 @ w4.sum(dim=1).reshape(d, -1).t() + bias + pos[1:].repeat(B, 1)   # exact weights
+    assert (got - want).abs().max() <= 0.02 * want.abs().max()
+    x3 = torch.full((B * N, d), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.patch_embed(imgs, w4.reshape(d, -1).bfloat16().contiguous(), bias, pos, p, out=x3)
+    got3 = x3.view(B, N, d)[:, 1:].reshape(B * Np, d).float()
+    assert (got - got3).abs().max() <= 0.02 * want.abs().max()
+    with pytest.raises(ValueError):
+        ops.patch_embed(imgs[:, None].expand(-1, 3, -1, -1).contiguous(), w_sum, bias, pos, p, out=x, channel_summed=True)
 
 
 def test_patch_embed_unsupported_geometry_is_rejected(cuda):

@@ -324,3 +324,31 @@ def test_dinov2_patch_embed_mode(cuda, hw, B):
     want = sam_fp32.dinov2_patch_embed(model.state_dict_f32, x)
     assert got.shape == want.shape == (B, hw[0] // 14, hw[1] // 14, 384)
     assert torch.allclose(got, want, atol=6e-3, rtol=1e-2), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize("hw,B", [((256, 256), 2), ((224, 224), 1), ((128, 1024), 1)])
+def test_sam_native_forward_equals_op_by_op(cuda, hw, B):
+    """vdr_sam_forward (the whole encoder as one C call) enqueues the same kernels in the same order as the op-by-op path:
+    bit-identical descriptors from a materialised im2col matrix (RGB pictures); gray slices of a volume go through the TMA im2col
+    patch embedding on channel-summed weights where the geometry allows it (another rounding of the same sum: tolerance)."""
+    from vit_deep_radiomics_b200 import _C, sam_encoder
+    model = sam_encoder.SamImageEncoder("sam_tiny", img_hw=hw, device=cuda, seed=31)
+    x = torch.rand(B, 3, *hw, generator=torch.Generator().manual_seed(6)).to(cuda)
+    assert model._native_struct() is not None
+    n0 = _C.launch_count()
+    native = model.dense_descriptors(x).clone()
+    n_native = _C.launch_count() - n0
+    model.use_native_forward = False
+    assert model._native_struct() is None
+    eager = model.dense_descriptors(x).clone()
+    assert n_native > 0 and torch.equal(native, eager)
+    # a gray volume: (H, W, S) f32, full-window crop
+    vol = torch.rand(hw[0], hw[1], 3, generator=torch.Generator().manual_seed(7)).to(cuda)
+    eager_v = model.forward_volume(vol, (0, hw[0], 0, hw[1])).clone()
+    model.use_native_forward = True
+    native_v = model.forward_volume(vol, (0, hw[0], 0, hw[1])).clone()
+    assert native_v.shape == eager_v.shape == (3 * model.n_tokens, model.feature_dim)
+    err = (native_v - eager_v).abs().max().item()
+    assert err <= 0.05, err                                     # O(1) LayerNorm outputs; bf16 patch weights summed vs summed products
+    cos = torch.nn.functional.cosine_similarity(native_v, eager_v, dim=1).min().item()
+    assert cos >= 0.9995, cos

@@ -17,7 +17,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 #: every symbol include/vdr.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "vdr_version", "vdr_last_error_string", "vdr_launch_count",
-    "vdr_dropout_apply", "vdr_dropout_mask", "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_volume_to_slices_cells", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
+    "vdr_dropout_apply", "vdr_dropout_mask", "vdr_gemm", "vdr_vit_forward_workspace_bytes", "vdr_vit_forward", "vdr_sam_forward_workspace_bytes", "vdr_sam_forward", "vdr_patch_embed_supported", "vdr_patch_embed_gemm", "vdr_patch_embed_gemm_gray", "vdr_im2col_patches", "vdr_volume_to_slices", "vdr_volume_to_slices_resized_workspace_bytes", "vdr_volume_to_slices_resized", "vdr_volume_to_slices_cells", "vdr_im2col_gray_bf16", "vdr_write_cls_rows",
     "vdr_layernorm_fwd", "vdr_layernorm_bwd", "vdr_cls_concat_layernorm_fwd", "vdr_row_stats", "vdr_fold_layernorm",
     "vdr_flash_attn_fwd", "vdr_flash_attn_bwd_workspace_bytes", "vdr_flash_attn_bwd",
     "vdr_mask_gather_workspace_bytes", "vdr_mask_gather", "vdr_mask_gather_table", "vdr_mask_count", "vdr_exclusive_scan_i64", "vdr_debug_set_gather_trace",
@@ -40,7 +40,23 @@ class VitWeights(C.Structure):
     """== vdr_vit_weights (include/vdr.h)"""
     _fields_ = [("dim", C.c_int), ("depth", C.c_int), ("heads", C.c_int), ("patch", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("eps", C.c_float), ("pe_w", C.c_void_p), ("pe_ldw", C.c_int64), ("pe_b", C.c_void_p), ("cls", C.c_void_p),
-                ("pos", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("blocks", C.POINTER(VitBlock))]
+                ("pos", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("blocks", C.POINTER(VitBlock)),
+                ("pe_w_gray", C.c_void_p), ("pe_gray_ldw", C.c_int64)]
+
+
+class SamBlock(C.Structure):
+    """== vdr_sam_block (include/vdr.h)"""
+    _fields_ = [(n, C.c_void_p) for n in ("qkv_wf", "qkv_bf", "qkv_cs", "qkv_b", "proj_w", "proj_b", "fc1_wf", "fc1_bf", "fc1_cs",
+                                          "fc2_w", "fc2_b", "rel_hi", "rel_lo")] + [("window", C.c_int)]
+
+
+class SamWeights(C.Structure):
+    """== vdr_sam_weights (include/vdr.h)"""
+    _fields_ = [("dim", C.c_int), ("depth", C.c_int), ("heads", C.c_int), ("patch", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("out_chans", C.c_int), ("eps", C.c_float), ("pe_w", C.c_void_p), ("pe_ldw", C.c_int64), ("pe_w_gray", C.c_void_p),
+                ("pe_gray_ldw", C.c_int64), ("pe_b", C.c_void_p), ("pos", C.c_void_p), ("neck0", C.c_void_p), ("neck1_w", C.c_void_p),
+                ("neck1_b", C.c_void_p), ("neck2", C.c_void_p), ("neck3_w", C.c_void_p), ("neck3_b", C.c_void_p),
+                ("blocks", C.POINTER(SamBlock))]
 
 
 class Dropout(C.Structure):
@@ -99,12 +115,16 @@ def lib() -> C.CDLL:
     L.vdr_vit_forward_workspace_bytes.argtypes = [C.POINTER(VitWeights), i32]
     L.vdr_vit_forward_workspace_bytes.restype = sz
     L.vdr_vit_forward.argtypes = [C.POINTER(VitWeights), vp, i32, i32, vp, i64, vp, sz, vp]
+    L.vdr_sam_forward_workspace_bytes.argtypes = [C.POINTER(SamWeights), i32]
+    L.vdr_sam_forward_workspace_bytes.restype = sz
+    L.vdr_sam_forward.argtypes = [C.POINTER(SamWeights), vp, vp, i32, vp, i64, vp, sz, vp]
     L.vdr_volume_to_slices_resized_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.vdr_volume_to_slices_resized_workspace_bytes.restype = sz
     L.vdr_volume_to_slices_resized.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
     L.vdr_volume_to_slices_cells.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
     L.vdr_patch_embed_supported.argtypes = [i32, i32, i32]
     L.vdr_patch_embed_gemm.argtypes = [vp, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp, i64, i32, vp]
+    L.vdr_patch_embed_gemm_gray.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp, vp, vp, i64, i32, i32, vp]
     L.vdr_flash_attn_bwd_workspace_bytes.argtypes = [i32, i32, i32]
     L.vdr_flash_attn_bwd_workspace_bytes.restype = sz
     dp = C.POINTER(Dropout)
@@ -150,7 +170,7 @@ def lib() -> C.CDLL:
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("vdr_version", "vdr_last_error_string", "vdr_launch_count",
-                        "vdr_mask_gather_workspace_bytes", "vdr_vit_forward_workspace_bytes",
+                        "vdr_mask_gather_workspace_bytes", "vdr_vit_forward_workspace_bytes", "vdr_sam_forward_workspace_bytes",
                         "vdr_volume_to_slices_resized_workspace_bytes", "vdr_flash_attn_bwd_workspace_bytes", "vdr_rotate_workspace_bytes"):
             fn.restype = i32
     _lib = L

@@ -788,17 +788,16 @@ extern "C" int vdr_patch_embed_supported(int H, int W, int patch) {
   return (patch == 16 && W % 8 == 0 && gw <= 128 && 128 % gw == 0 && np % 128 == 0) ? 1 : 0;
 }
 
-extern "C" int vdr_patch_embed_gemm(const void* images_bf16, int B, int C, int H, int W, int patch, const void* Wpe_bf16,
-                                    int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d,
-                                    vdr_stream_t stream) {
+static int patch_embed_impl(const char* who, const void* images_bf16, int B, int C, int wchan, int lead, int H, int W, int patch, const void* Wpe_bf16,
+                            int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d, vdr_stream_t stream) {
   using namespace vdr;
-  VDR_CHECK_ARG(images_bf16 && Wpe_bf16 && pos && X_bf16, VDR_EINVAL, "vdr_patch_embed_gemm: null pointer");
-  VDR_CHECK_ARG(B > 0 && (C == 1 || C == 3) && d > 0, VDR_EINVAL, "vdr_patch_embed_gemm: bad shape B=%d C=%d d=%d", B, C, d);
+  VDR_CHECK_ARG(images_bf16 && Wpe_bf16 && pos && X_bf16, VDR_EINVAL, "%s: null pointer", who);
+  VDR_CHECK_ARG(B > 0 && (C == 1 || C == 3) && d > 0 && lead >= 0, VDR_EINVAL, "%s: bad shape B=%d C=%d d=%d token_offset=%d", who, B, C, d, lead);
   VDR_CHECK_ARG(vdr_patch_embed_supported(H, W, patch), VDR_EINVAL,
-                "vdr_patch_embed_gemm: %dx%d images with %d-pixel patches do not tile into TMA im2col boxes (use vdr_im2col_* + vdr_gemm)", H, W, patch);
-  VDR_CHECK_ARG(aligned16(images_bf16), VDR_EALIGN, "vdr_patch_embed_gemm: images must be 16-byte aligned");
+                "%s: %dx%d images with %d-pixel patches do not tile into TMA im2col boxes (use vdr_im2col_* + vdr_gemm)", who, H, W, patch);
+  VDR_CHECK_ARG(aligned16(images_bf16), VDR_EALIGN, "%s: images must be 16-byte aligned", who);
   const int np = (H / patch) * (W / patch);
-  VDR_CHECK_ARG((int64_t)B * np < 0x7fffffffLL, VDR_EINVAL, "vdr_patch_embed_gemm: too many patches");
+  VDR_CHECK_ARG((int64_t)B * np < 0x7fffffffLL, VDR_EINVAL, "%s: too many patches", who);
   vdr_gemm_args a;
   memset(&a, 0, sizeof(a));
   a.A = nullptr; a.lda = 0;
@@ -806,10 +805,25 @@ extern "C" int vdr_patch_embed_gemm(const void* images_bf16, int B, int C, int H
   a.bias = bias;
   a.R = pos; a.ldr = d; a.r_dtype = VDR_DTYPE_F32;
   a.C = X_bf16; a.ldc = ldx; a.c_dtype = VDR_DTYPE_BF16;
-  a.M = B * np; a.N = d; a.K = 3 * patch * patch;
+  a.M = B * np; a.N = d; a.K = wchan * patch * patch;                 // wchan = channel planes of the WEIGHTS (1: channel-summed)
   a.epilogue = VDR_EPI_BIAS_RESIDUAL;
-  a.out_group = np; a.out_group_stride = np + 1; a.out_offset = 1;   // patch tokens behind each image's CLS row
-  a.res_mod = np; a.res_offset = 1;                                   // + pos_embed[1 + patch index]
+  if (lead > 0) { a.out_group = np; a.out_group_stride = np + lead; a.out_offset = lead; }   // patch tokens behind each image's CLS row
+  a.res_mod = np; a.res_offset = lead;                                // + pos_embed[lead + patch index]
   const Im2colSpec ic{images_bf16, B, C, H, W, patch};
   return gemm_impl(&a, &ic, stream);
+}
+
+extern "C" int vdr_patch_embed_gemm(const void* images_bf16, int B, int C, int H, int W, int patch, const void* Wpe_bf16,
+                                    int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d,
+                                    vdr_stream_t stream) {
+  return patch_embed_impl("vdr_patch_embed_gemm", images_bf16, B, C, 3, 1, H, W, patch, Wpe_bf16, ldw, bias, pos, X_bf16, ldx, d, stream);
+}
+
+// Gray pictures against CHANNEL-SUMMED weights: gray2rgb feeds the same picture to the three input channels, so
+// sum_c patch . W_c = patch . (W_r + W_g + W_b) -- K = p*p instead of 3*p*p, the picture is read once instead of three times.
+// token_offset: rows in front of every image's patch tokens in X and pos (1 = the CLS row of a ViT, 0 = SAM's encoder).
+extern "C" int vdr_patch_embed_gemm_gray(const void* images_bf16, int B, int H, int W, int patch, const void* Wsum_bf16,
+                                         int64_t ldw, const float* bias, const float* pos, void* X_bf16, int64_t ldx, int d,
+                                         int token_offset, vdr_stream_t stream) {
+  return patch_embed_impl("vdr_patch_embed_gemm_gray", images_bf16, B, 1, 1, token_offset, H, W, patch, Wsum_bf16, ldw, bias, pos, X_bf16, ldx, d, stream);
 }

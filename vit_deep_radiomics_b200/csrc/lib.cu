@@ -106,7 +106,7 @@ int make_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_
 
 extern "C" {
 
-int vdr_version(void) { return 100; }
+int vdr_version(void) { return 101; }
 
 const char* vdr_last_error_string(void) { return vdr::g_err; }
 

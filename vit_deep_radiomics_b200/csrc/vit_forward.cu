@@ -80,7 +80,10 @@ extern "C" int vdr_vit_forward(const vdr_vit_weights* w, const void* images_bf16
 
   // ---- patch embedding (+ bias + position embedding), rows written behind each image's CLS row
   if (pl.tma_patch_embed) {
-    rc = vdr_patch_embed_gemm(images_bf16, B, C, w->H, w->W, w->patch, w->pe_w, w->pe_ldw, w->pe_b, w->pos, X, d, d, stream);
+    if (C == 1 && w->pe_w_gray)   // gray slices: channel-summed weights, K = patch^2
+      rc = vdr_patch_embed_gemm_gray(images_bf16, B, w->H, w->W, w->patch, w->pe_w_gray, w->pe_gray_ldw, w->pe_b, w->pos, X, d, d, 1, stream);
+    else
+      rc = vdr_patch_embed_gemm(images_bf16, B, C, w->H, w->W, w->patch, w->pe_w, w->pe_ldw, w->pe_b, w->pos, X, d, d, stream);
     if (rc != VDR_OK) return rc;
   } else {
     VDR_CHECK_ARG(C == 1, VDR_EINVAL, "vdr_vit_forward: RGB input needs a geometry the TMA im2col view supports (or vdr_im2col_patches + vdr_gemm)");

@@ -259,7 +259,7 @@ def patch_embed_supported(H: int, W: int, patch: int) -> bool:
 
 
 def patch_embed(images: torch.Tensor, w_pe: torch.Tensor, bias: torch.Tensor, pos: torch.Tensor, patch: int,
-                out: torch.Tensor) -> torch.Tensor:
+                out: torch.Tensor, channel_summed: bool = False, token_offset: int = 1) -> torch.Tensor:
     """Patch embedding + position embedding as one TMA-fed im2col GEMM (no materialised im2col matrix).
     images (B, H, W) [gray, reused for the 3 input channels] or (B, 3, H, W), bf16 contiguous; w_pe (d, >= 3*p*p) bf16
     (k = (c, iy, ix)); bias (d) f32; pos (N, d) f32 with N = patches + 1; out (B*N, d) bf16: rows b*N + 1.. are written."""
@@ -270,9 +270,20 @@ def patch_embed(images: torch.Tensor, w_pe: torch.Tensor, bias: torch.Tensor, po
     B, C = images.shape[0], (1 if images.dim() == 3 else 3)
     H, W = images.shape[-2:]
     d = w_pe.shape[0]
-    N = (H // patch) * (W // patch) + 1
+    N = (H // patch) * (W // patch) + token_offset
     if pos.shape != (N, d) or not pos.is_contiguous() or out.shape != (B * N, d) or out.stride(1) != 1:
         raise ValueError(f"pos must be ({N}, {d}) and out ({B * N}, {d})")
+    if token_offset != 1 and not channel_summed:
+        raise ValueError("token_offset other than 1 needs channel_summed weights (vdr_patch_embed_gemm_gray)")
+    if channel_summed:
+        # gray pictures against w_pe = W_r + W_g + W_b (d, p*p): K = p*p (vdr_patch_embed_gemm_gray)
+        if C != 1 or w_pe.shape[1] < patch * patch:
+            raise ValueError("channel_summed weights need gray (B, H, W) pictures and w_pe (d, >= p*p)")
+        with _Prof("gemm", 2.0 * B * (N - token_offset) * d * patch * patch, f"patch-embed gemm (TMA im2col, gray: channel-summed weights) M{B * (N - token_offset)} N{d} K{patch * patch}"):
+            _C.check(_C.lib().vdr_patch_embed_gemm_gray(images.data_ptr(), B, H, W, patch, w_pe.data_ptr(), w_pe.stride(0),
+                                                        bias.data_ptr(), pos.data_ptr(), out.data_ptr(), out.stride(0), d, int(token_offset), _stream()),
+                     "vdr_patch_embed_gemm_gray")
+        return out
     with _Prof("gemm", 2.0 * B * (N - 1) * d * 3 * patch * patch, f"patch-embed gemm (TMA im2col) M{B * (N - 1)} N{d} K{3 * patch * patch}"):
         _C.check(_C.lib().vdr_patch_embed_gemm(images.data_ptr(), B, C, H, W, patch, w_pe.data_ptr(), w_pe.stride(0),
                                                bias.data_ptr(), pos.data_ptr(), out.data_ptr(), out.stride(0), d, _stream()),

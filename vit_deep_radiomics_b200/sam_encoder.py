@@ -16,11 +16,12 @@ partition, attention and unpartition in one launch).  There is no CPU path: ever
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import _C, ops
 
 SAM_CONFIGS = {
     "medsam": dict(dim=768, depth=12, heads=12, global_attn=(2, 5, 8, 11), window=14, out_chans=256, patch=16),
@@ -138,7 +139,10 @@ class SamImageEncoder:
         f32 = lambda k: sd[k].to(dev, torch.float32).contiguous()   # noqa: E731
         bf = lambda k: sd[k].to(dev).bfloat16().contiguous()        # noqa: E731
         self.K = 3 * p * p
+        self.__dict__.pop("_native", None)
         self.w = dict(pe_w=sd["patch_embed.proj.weight"].reshape(d, self.K).to(dev).bfloat16().contiguous(),
+                      # gray slices (gray2rgb, :41): sum_c x . W_c = x . (W_r + W_g + W_b) -- K = p*p for the TMA im2col patch embedding
+                      pe_w_gray=sd["patch_embed.proj.weight"].to(dev, torch.float32).sum(dim=1).reshape(d, p * p).bfloat16().contiguous(),
                       pe_b=f32("patch_embed.proj.bias"), pos=f32("pos_embed").reshape(gh * gw, d), blocks=[],
                       neck0=sd["neck.0.weight"].reshape(oc, d).to(dev).bfloat16().contiguous(),
                       neck1_w=f32("neck.1.weight"), neck1_b=f32("neck.1.bias"),
@@ -166,6 +170,57 @@ class SamImageEncoder:
             for blk in self.w["blocks"]:
                 blk["fc1_wf"], blk["fc1_bf"], blk["fc1_cs"] = ops.fold_layernorm(blk["fc1_w"], blk["fc1_b"], blk["n2w"], blk["n2b"])
                 blk["qkv_wf"], blk["qkv_bf"], blk["qkv_cs"] = ops.fold_layernorm(blk["qkv_w"], blk["qkv_b"], blk["n1w"], blk["n1b"])
+
+    def _native_struct(self):
+        """The weights as a vdr_sam_weights struct (one C call per forward, vdr_sam_forward); None for configurations the native
+        forward does not cover (unfolded LayerNorms, explicit window copies, the table-reading global kernel)."""
+        import ctypes as C
+        cfg, w = self.cfg, self.w
+        win = cfg["window"]
+        # (the switches below are class attributes that tests / A/B runs flip on an instance: evaluated on every call)
+        if not (self.use_native_forward and "fc1_wf" in w["blocks"][0] and self.windows_in_place and win * win <= 208
+                and self.global_attn_kernel == "auto"):
+            return None
+        gh, gw = self.grid
+        if not (gw == 64 and gh % 4 == 0 and gh <= 64) and (gw == 64 and gh % 4 == 0):
+            return None                                       # "auto" would pick the bias-table kernel here (needs the REL scratch)
+        nat = self.__dict__.get("_native")
+        if nat is not None:
+            return nat
+        blocks = (_C.SamBlock * cfg["depth"])()
+        for i, blk in enumerate(w["blocks"]):
+            for name in ("qkv_wf", "qkv_bf", "qkv_cs", "qkv_b", "proj_w", "proj_b", "fc1_wf", "fc1_bf", "fc1_cs", "fc2_w", "fc2_b", "rel_hi", "rel_lo"):
+                setattr(blocks[i], name, blk[name].data_ptr())
+            blocks[i].window = int(blk["window"])
+        self._native_blocks = blocks                          # keeps the array alive
+        self._native = _C.SamWeights(cfg["dim"], cfg["depth"], cfg["heads"], cfg["patch"], self.img_hw[0], self.img_hw[1], cfg["out_chans"], 1e-6,
+                                     w["pe_w"].data_ptr(), w["pe_w"].stride(0), w["pe_w_gray"].data_ptr(), w["pe_w_gray"].stride(0),
+                                     w["pe_b"].data_ptr(), w["pos"].data_ptr(), w["neck0"].data_ptr(), w["neck1_w"].data_ptr(),
+                                     w["neck1_b"].data_ptr(), w["neck2"].data_ptr(), w["neck3_w"].data_ptr(), w["neck3_b"].data_ptr(),
+                                     C.cast(blocks, C.POINTER(_C.SamBlock)))
+        return self._native
+
+    #: the whole encoder as one C call (vdr_sam_forward) where it applies; False = the op-by-op path (profiling, A/B)
+    use_native_forward = os.environ.get("VDR_SAM_OP_BY_OP") is None
+
+    def _encode_native(self, B: int, images: torch.Tensor | None, im2col: torch.Tensor | None, out: torch.Tensor | None) -> torch.Tensor:
+        import ctypes as C
+        nat = self._native_struct()
+        nb = self.__dict__.setdefault("_native_ws", {})
+        need = _C.lib().vdr_sam_forward_workspace_bytes(C.byref(nat), B)
+        if need == 0:
+            _C.check(1, "vdr_sam_forward_workspace_bytes")
+        buf = nb.get("buf")
+        if buf is None or buf.numel() < need:
+            buf = nb["buf"] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if out is None:
+            out = nb.get(("out", B))
+            if out is None:
+                out = nb[("out", B)] = torch.empty(B * self.n_tokens, self.feature_dim, dtype=torch.float32, device=self.device)
+        _C.check(_C.lib().vdr_sam_forward(C.byref(nat), images.data_ptr() if images is not None else None,
+                                          im2col.data_ptr() if im2col is not None else None, B, out.data_ptr(), out.stride(0),
+                                          buf.data_ptr(), buf.numel(), ops._stream()), "vdr_sam_forward")
+        return out
 
     def _buffers(self, B: int) -> dict:
         ws = self._ws.get(B)
@@ -208,6 +263,15 @@ class SamImageEncoder:
         """src: f32 CUDA storage of B images addressed by element strides (batch, channel, row, col); channel stride 0 =
         gray2rgb.  Returns the neck output as a token matrix (B*gh*gw, out_chans) f32, tokens in (row, col) order."""
         H, W = self.img_hw
+        if ops.PROFILE is None and self._native_struct() is not None:
+            nb = self.__dict__.setdefault("_native_ws", {})
+            A = nb.get(("A", B))
+            if A is None:
+                for k in [k for k in nb if isinstance(k, tuple) and k[0] == "A"]:
+                    del nb[k]
+                A = nb[("A", B)] = torch.empty(B * self.n_tokens, self.K, dtype=torch.bfloat16, device=self.device)
+            ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"], out=A)
+            return self._encode_native(B, None, A, None)
         ws = self._buffers(B)
         ops.im2col_patches(src, strides, B, H, W, self.cfg["patch"], out=ws["A"])
         return self._encode(B)
@@ -223,8 +287,12 @@ class SamImageEncoder:
                                   OUT=torch.empty(S * self.n_tokens, self.feature_dim, dtype=torch.float32, device=self.device))
         ops.volume_to_slices(vol, crop, out=vb["SL"], out_hw=self.img_hw)      # all slices staged (and resized) by one kernel
         N = self.n_tokens
+        native = ops.PROFILE is None and self._native_struct() is not None
         for s0 in range(0, S, Bc):                                             # encoder batches of `volume_batch` slices
             b = min(Bc, S - s0)
+            if native:                                                         # one C call per batch: gray slices -> descriptors
+                self._encode_native(b, vb["SL"][s0:s0 + b], None, vb["OUT"][s0 * N:(s0 + b) * N])
+                continue
             ws = self._buffers(b)
             ops.im2col_gray_bf16(vb["SL"][s0:s0 + b], self.cfg["patch"], out=ws["A"])
             self._encode(b, out=vb["OUT"][s0 * N:(s0 + b) * N])

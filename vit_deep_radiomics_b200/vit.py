@@ -106,7 +106,15 @@ class ViTBackbone:
             w4 = torch.zeros(d, 3, 16, 16, dtype=torch.bfloat16, device=dev)
             w4[:, :, :p, :p] = sd["patch_embed.weight"].to(dev).bfloat16()
             w_pe_tma = w4.reshape(d, 3 * 256).contiguous()
-        self.w = dict(pe_w=w_pe, pe_w_tma=w_pe_tma, pe_b=f32("patch_embed.bias"), cls=f32("cls_token").reshape(d),
+        # gray slices (gray2rgb feeds one picture to the three input channels): sum_c x . W_c = x . (W_r + W_g + W_b), summed in f32 and
+        # rounded to bf16 once -> K = p*p for the TMA im2col GEMM (vdr_patch_embed_gemm_gray), in the cell layout when cell-padded
+        w_sum = sd["patch_embed.weight"].to(dev, torch.float32).sum(dim=1)                     # (d, p, p)
+        if self.cell:
+            w_g = torch.zeros(d, 16, 16, dtype=torch.float32, device=dev)
+            w_g[:, :p, :p] = w_sum
+            w_sum = w_g
+        w_pe_gray = w_sum.reshape(d, -1).bfloat16().contiguous()
+        self.w = dict(pe_w=w_pe, pe_w_tma=w_pe_tma, pe_w_gray=w_pe_gray, pe_b=f32("patch_embed.bias"), cls=f32("cls_token").reshape(d),
                       pos=f32("pos_embed").reshape(self.n_tokens, d),
                       norm_w=f32("norm.weight"), norm_b=f32("norm.bias"), blocks=[])
         for i in range(self.cfg["depth"]):
@@ -138,7 +146,8 @@ class ViTBackbone:
         self._native = _C.VitWeights(d, self.cfg["depth"], self.cfg["heads"], self.pe_patch, self.stage_hw[0], self.stage_hw[1], 1e-6,
                                      w["pe_w_tma"].data_ptr(), w["pe_w_tma"].stride(0), w["pe_b"].data_ptr(), w["cls"].data_ptr(),
                                      w["pos"].data_ptr(), w["norm_w"].data_ptr(), w["norm_b"].data_ptr(),
-                                     C.cast(blocks, C.POINTER(_C.VitBlock)))
+                                     C.cast(blocks, C.POINTER(_C.VitBlock)),
+                                     w["pe_w_gray"].data_ptr() if self.gray_fold else None, w["pe_w_gray"].stride(0))
 
     def _workspace(self, B: int) -> dict:
         ws = self._ws.get(B)
@@ -213,7 +222,9 @@ class ViTBackbone:
         d, heads, N, Np = cfg["dim"], cfg["heads"], self.n_tokens, self.n_patches
         ws = self._op_buffers(B)
         # patch embedding GEMM: bias + pos-embed fused, rows written behind each image's CLS row
-        if images is not None:
+        if images is not None and images.dim() == 3 and self.gray_fold:
+            ops.patch_embed(images, w["pe_w_gray"], w["pe_b"], w["pos"], self.pe_patch, out=ws["X"], channel_summed=True)
+        elif images is not None:
             ops.patch_embed(images, w["pe_w_tma"], w["pe_b"], w["pos"], self.pe_patch, out=ws["X"])
         else:
             ops.gemm(ws["A"], w["pe_w"], w["pe_b"], epilogue="residual", residual=w["pos"], out=ws["X"], k=self.K,
@@ -250,6 +261,7 @@ class ViTBackbone:
 
     #: fold norm1 / norm2 into the qkv / fc1 GEMMs (set False before prepare() for the LayerNorm-kernel path)
     fold_layernorm = os.environ.get("VDR_NO_LN_FOLD") is None     # the env switch exists for A/B timing only
+    gray_fold = os.environ.get("VDR_NO_GRAY_FOLD") is None        # channel-summed patch weights for gray slices (A/B switch)
 
     #: route forward_volume through vdr_vit_forward (per-kernel profiling, ops.PROFILE, always uses the op-by-op path)
     use_native_forward = True
