@@ -265,6 +265,16 @@ class SamImageEncoder:
         H, W = self.img_hw
         if ops.PROFILE is None and self._native_struct() is not None:
             nb = self.__dict__.setdefault("_native_ws", {})
+            if (src.dim() == 3 and strides[1] == 0 and src.is_contiguous() and tuple(src.shape) == (B, H, W)
+                    and ops.patch_embed_supported(H, W, self.cfg["patch"])):
+                # gray pictures: bf16 slices straight into the TMA im2col patch embedding (channel-summed weights), no patch matrix
+                sl = nb.get(("SL", B))
+                if sl is None:
+                    for k in [k for k in nb if isinstance(k, tuple) and k[0] in ("SL", "A")]:
+                        del nb[k]
+                    sl = nb[("SL", B)] = torch.empty((B, H, W), dtype=torch.bfloat16, device=self.device)
+                sl.copy_(src)
+                return self._encode_native(B, sl, None, None)
             A = nb.get(("A", B))
             if A is None:
                 for k in [k for k in nb if isinstance(k, tuple) and k[0] == "A"]:
