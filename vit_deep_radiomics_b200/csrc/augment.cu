@@ -51,32 +51,63 @@ __global__ void __launch_bounds__(128) rot_prefilter_kernel(const T* __restrict_
   double* c = P + (axis == 0 ? static_cast<int64_t>(o) * g.NP : static_cast<int64_t>(o) * g.WP * g.NP) + p;
   const double z = kRotPole;
   const double gain = __dmul_rn(__dsub_rn(1.0, __ddiv_rn(1.0, z)), __dsub_rn(1.0, z));
-  // gain, and (first axis) the padded source read
-  for (int i = 0; i < n; ++i) {
-    const double v = kFirst ? (axis == 0 ? rot_src(src, g, i, o, p) : rot_src(src, g, o, i, p)) : c[i * stride];
-    c[i * stride] = __dmul_rn(v, gain);
-  }
-  // causal initialisation (_init_causal_reflect)
-  const double c0 = c[0];
-  double acc = __dadd_rn(__dmul_rn(c[(n - 1) * stride], z_n), c0);
+  // Element i of the line after scipy's gain pass: the (flipped, edge-padded) source sample (first axis) or what the first axis left in
+  // P (second axis), times the gain.  Evaluated on the fly wherever it is needed -- the same product, so the same double -- instead of
+  // a read-modify-write sweep of its own.  The lines are latency-bound recurrences (64 k threads, one dependent chain each): the loads
+  // of kB consecutive elements are issued together, ahead of the arithmetic that consumes them and of the stores of the batch (the
+  // compiler cannot hoist a load of c[] above a store to c[] itself).
+  auto raw = [&](int i) -> double { return kFirst ? (axis == 0 ? rot_src(src, g, i, o, p) : rot_src(src, g, o, i, p)) : c[i * stride]; };
+  constexpr int kB = 8;
+  // causal initialisation (_init_causal_reflect): c0 + z^n c[n-1] + sum_i z^i (c[i] + z^n c[n-1-i]), terms added in index order
+  const double c0 = __dmul_rn(raw(0), gain);
+  double acc = __dadd_rn(__dmul_rn(__dmul_rn(raw(n - 1), gain), z_n), c0);
   double z_i = z;
-  for (int i = 1; i < n; ++i) {
-    const double t = __dmul_rn(__dadd_rn(__dmul_rn(c[(n - 1 - i) * stride], z_n), c[i * stride]), z_i);
-    z_i = __dmul_rn(z_i, z);
-    acc = __dadd_rn(acc, t);
+  for (int i0 = 1; i0 < n; i0 += kB) {
+    double a[kB], r[kB];
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+      const int i = min(i0 + k, n - 1);
+      a[k] = raw(i);
+      r[k] = raw(n - 1 - i);
+    }
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+      if (i0 + k < n) {
+        const double t = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(r[k], gain), z_n), __dmul_rn(a[k], gain)), z_i);
+        z_i = __dmul_rn(z_i, z);
+        acc = __dadd_rn(acc, t);
+      }
+    }
   }
   double prev = __dadd_rn(__ddiv_rn(__dmul_rn(z, acc), __dsub_rn(1.0, __dmul_rn(z_n, z_n))), c0);
   c[0] = prev;
-  for (int i = 1; i < n; ++i) {
-    prev = __dadd_rn(__dmul_rn(prev, z), c[i * stride]);
-    c[i * stride] = prev;
+  // causal: c[i] = c[i-1] z + c[i]
+  for (int i0 = 1; i0 < n; i0 += kB) {
+    double a[kB];
+#pragma unroll
+    for (int k = 0; k < kB; ++k) a[k] = raw(min(i0 + k, n - 1));
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+      if (i0 + k < n) {
+        prev = __dadd_rn(__dmul_rn(prev, z), __dmul_rn(a[k], gain));
+        c[(i0 + k) * stride] = prev;
+      }
+    }
   }
-  // anticausal
+  // anticausal: c[n-1] *= z / (z - 1); c[i] = z (c[i+1] - c[i])
   prev = __dmul_rn(__ddiv_rn(z, __dsub_rn(z, 1.0)), prev);
   c[(n - 1) * stride] = prev;
-  for (int i = n - 2; i >= 0; --i) {
-    prev = __dmul_rn(__dsub_rn(prev, c[i * stride]), z);
-    c[i * stride] = prev;
+  for (int i0 = n - 2; i0 >= 0; i0 -= kB) {
+    double a[kB];
+#pragma unroll
+    for (int k = 0; k < kB; ++k) a[k] = c[max(i0 - k, 0) * stride];
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+      if (i0 - k >= 0) {
+        prev = __dmul_rn(__dsub_rn(prev, a[k]), z);
+        c[(i0 - k) * stride] = prev;
+      }
+    }
   }
 }
 
