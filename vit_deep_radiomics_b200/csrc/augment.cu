@@ -126,12 +126,15 @@ __device__ __forceinline__ void rot_weights(double cc, int& start, double (&w)[4
 }
 
 // kOut: 0 = f32 image clipped to [0, 1]; 1 = mask from a bool input; 2 = mask from a uint8 input
+// One warp per output pixel (i, j), lanes over the planes: the input coordinate, the two sets of cubic weights (six f64 divisions) and the
+// clamped tap indices depend on the pixel only and are evaluated once per warp instead of once per element; every tap is then one coalesced
+// 256-byte read of 32 consecutive planes.
 template <int kOut>
 __global__ void __launch_bounds__(256) rot_interp_kernel(const double* __restrict__ P, RotGeom g, RotXform x, void* __restrict__ out) {
-  const int64_t total = static_cast<int64_t>(g.H) * g.W * g.NP;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int p = static_cast<int>(e % g.NP);
-    const int64_t rc = e / g.NP;
+  const int lane = threadIdx.x & 31;
+  const int64_t pixels = static_cast<int64_t>(g.H) * g.W;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5, nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t rc = warp0; rc < pixels; rc += nwarps) {
     const int j = static_cast<int>(rc % g.W), i = static_cast<int>(rc / g.W);
     const double di = static_cast<double>(i), dj = static_cast<double>(j);
     const double cc0 = __dadd_rn(__dadd_rn(__dadd_rn(x.off0, __dmul_rn(di, x.m00)), __dmul_rn(dj, x.m01)), static_cast<double>(kRotPad));
@@ -140,24 +143,32 @@ __global__ void __launch_bounds__(256) rot_interp_kernel(const double* __restric
     double w0[4], w1[4];
     rot_weights(cc0, s0, w0);
     rot_weights(cc1, s1, w1);
-    double t = 0.0;
+    int64_t row[4];
+    int col[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      const int ia = min(max(s0 + a, 0), g.HP - 1);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int ib = min(max(s1 + b, 0), g.WP - 1);
-        const double c = P[(static_cast<int64_t>(ia) * g.WP + ib) * g.NP + p];
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(c, w0[a]), w1[b]));
-      }
+      row[a] = static_cast<int64_t>(min(max(s0 + a, 0), g.HP - 1)) * g.WP;
+      col[a] = min(max(s1 + a, 0), g.WP - 1);
     }
-    if (kOut == 0) {
-      const float v = __double2float_rn(t);
-      static_cast<float*>(out)[e] = fminf(fmaxf(v, 0.f), 1.f);                         // np.clip(image_rot, 0, 1)
-    } else if (kOut == 1) {
-      static_cast<uint8_t*>(out)[e] = (t >= 1.0 || t <= -1.0) ? 1 : 0;                 // (npy_bool)t, then > 0
-    } else {
-      static_cast<uint8_t*>(out)[e] = (t > 0.0 && __dadd_rn(t, 0.5) >= 1.0) ? 1 : 0;   // round-half-up to uint8, then > 0
+    for (int p = lane; p < g.NP; p += 32) {
+      double t = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double c = P[(row[a] + col[b]) * g.NP + p];
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(c, w0[a]), w1[b]));
+        }
+      }
+      const int64_t e = rc * g.NP + p;
+      if (kOut == 0) {
+        const float v = __double2float_rn(t);
+        static_cast<float*>(out)[e] = fminf(fmaxf(v, 0.f), 1.f);                         // np.clip(image_rot, 0, 1)
+      } else if (kOut == 1) {
+        static_cast<uint8_t*>(out)[e] = (t >= 1.0 || t <= -1.0) ? 1 : 0;                 // (npy_bool)t, then > 0
+      } else {
+        static_cast<uint8_t*>(out)[e] = (t > 0.0 && __dadd_rn(t, 0.5) >= 1.0) ? 1 : 0;   // round-half-up to uint8, then > 0
+      }
     }
   }
 }
@@ -224,9 +235,10 @@ extern "C" int vdr_flip_rotate_volume(const void* src, int src_kind, void* dst, 
   rot_prefilter_kernel<float, false><<<(unsigned)((lines1 + 127) / 128), 128, 0, s>>>(nullptr, P, g, 1, z_n_cols);
   VDR_CHECK_LAUNCH("rot_prefilter_kernel (axis 1)");
   const RotXform x{xform_host[0], xform_host[1], xform_host[2], xform_host[3], xform_host[4], xform_host[5]};
-  if (src_kind == 0) rot_interp_kernel<0><<<rot_grid(total, 256), 256, 0, s>>>(P, g, x, dst);
-  else if (src_kind == 1) rot_interp_kernel<1><<<rot_grid(total, 256), 256, 0, s>>>(P, g, x, dst);
-  else rot_interp_kernel<2><<<rot_grid(total, 256), 256, 0, s>>>(P, g, x, dst);
+  const int igrid = rot_grid((int64_t)H * W * 32, 256);              // one warp per pixel
+  if (src_kind == 0) rot_interp_kernel<0><<<igrid, 256, 0, s>>>(P, g, x, dst);
+  else if (src_kind == 1) rot_interp_kernel<1><<<igrid, 256, 0, s>>>(P, g, x, dst);
+  else rot_interp_kernel<2><<<igrid, 256, 0, s>>>(P, g, x, dst);
   count_launch(3);
   VDR_CHECK_LAUNCH("rot_interp_kernel");
   return VDR_OK;
