@@ -196,6 +196,34 @@ def test_flash_attention(cuda, B, N, heads):
     _close(lse, torch.logsumexp(s, -1), 5e-4)
 
 
+@pytest.mark.parametrize("N,late_gain,nats", [(1025, 5.0, 35), (1025, 16.0, 120), (645, 16.0, 120), (384, 16.0, 120)])
+def test_flash_attention_maximum_free_blocks_guard(cuda, N, late_gain, nats):
+    """The plain kernel takes its reference maximum from key block 0 only.  Later keys whose scores sit tens of nats above it give
+    P >> 1 (no overflow: same result as the exact softmax); hundreds of nats above it overflow exp2, the row sums flag it and the
+    CTA recomputes its tile exactly (attn_tail_rows) -- outputs and lse must equal the fp32 softmax either way."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(N + int(late_gain * 10))
+    B, heads = 2, 2
+    d = heads * 64
+    qkv = torch.randn(B * N, 3 * d, device=cuda)
+    x = qkv.view(B, N, 3, heads, 64)
+    x[:, :, 0] = x[:, :, 0].abs() * 0.5 + 2.0                   # queries: all components in [2, ~4]
+    x[:, :, 1] = x[:, :, 1].abs() * 0.1 + 0.5                   # keys: positive, so q . k grows with the key's gain
+    x[:, 200:, 1] *= late_gain                                   # keys beyond block 0 (and a part of block 1) are scaled
+    if N > 600:
+        x[0, 600:, 1] = x[0, 600:, 1] / late_gain                # image 0: only blocks 1 .. 4 carry the large keys
+    qkv = qkv.bfloat16()
+    q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / math.sqrt(64)
+    gap = (s[..., 128:].amax(-1) - s[..., :128].amax(-1))        # nats above (below) the block-0 maximum, per row
+    assert gap.max().item() > nats
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, d)
+    out, lse = ops.flash_attn(qkv, B, N, heads, return_lse=True)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    _close(out, ref, 8e-3)
+    _close(lse, torch.logsumexp(s, -1), 5e-4)
+
+
 @pytest.mark.parametrize("rows,d", [(1000, 256), (1025, 768), (333, 384), (77, 1024), (50, 2048), (3, 8)])
 def test_layernorm_fwd_bwd(cuda, rows, d):
     from vit_deep_radiomics_b200 import ops

@@ -169,8 +169,13 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // eight sibling tensor-core CTAs are streaming at the same time.  8 lanes share a key (16 bytes of the 128-byte K / V
 // row each): a warp-wide load touches 4 rows x 128 contiguous bytes; the 48 lane-groups of the CTA each run an online
 // softmax over the keys dealt to them and the partial states are merged through shared memory.
-template <int kThreads>
+// kBar == 0: called by the whole CTA (__syncthreads); kBar > 0: called by threads 0 .. kThreads - 1 only (named barrier kBar).
+template <int kThreads, int kBar = 0>
 __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, int head, int b, int row0, int nrows) {
+  auto sync = [] {
+    if (kBar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(kBar), "n"(kThreads) : "memory");
+  };
   constexpr int kGroups = kThreads / 8;                            // key groups of 8 lanes (48 / 20): lane `sub` owns 8 of the 64 dims
   constexpr int kDepth = 5;                                        // keys in flight per group (cp.async ring)
   constexpr uint32_t kStageBytes = kThreads * 16 * 2;              // one 16-byte K piece and one V piece per thread
@@ -239,7 +244,7 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     // merge the 48 partial softmax states: global maximum first, then every group rescales its own (l, o) before the sums
     if (sub == 0) s_m[grp] = m;
-    __syncthreads();
+    sync();
     float mt = -INFINITY;
 #pragma unroll 8
     for (int g = 0; g < kGroups; ++g) mt = fmaxf(mt, s_m[g]);
@@ -247,7 +252,7 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
     if (sub == 0) s_l[grp] = l * f;
 #pragma unroll
     for (int d = 0; d < 8; ++d) s_o[grp * kHD + sub * 8 + d] = o[d] * f;
-    __syncthreads();
+    sync();
     if (tid < kHD) {
       float lt = 0.f, acc = 0.f;
 #pragma unroll 8
@@ -258,7 +263,7 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
       p.out[(static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD + tid] = __float2bfloat16_rn(acc / lt);
       if (tid == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mt + log2f(lt)) * 0.69314718055994531f;
     }
-    __syncthreads();
+    sync();
   }
 }
 
@@ -517,6 +522,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     mbar_init(bar_r, 1);
     mbar_init(bar_t, 1);
     mbar_init(bar_tread, kSoftmaxWarps);
+    reinterpret_cast<volatile uint32_t*>(bars)[32] = 0u;   // "a row sum went out of range" (maximum-free blocks), byte 128 of the barrier block
     fence_barrier_init();
     mbar_arrive_expect_tx(bar_q, kTileBytes);
     tma_load_2d(&tmQKV, bar_q, smem, colQ, row_base + q0);
@@ -954,15 +960,14 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           continue;
         }
 #endif
-#if defined(VDR_X_NOMAX)   // experiment (UNSAFE: no overflow guard): the reference maximum is the one of block 0, later blocks skip max / exchange / vote
-        // Measured: 0.598 -> 0.560 ms at N = 1024.  A guarded form (row-sum vote per block, the two half-row warps exchange the bit,
-        // the block is redone from the scores still in registers when a sum reaches 2^64) keeps the 64 scores live next to the 32
-        // packed P registers: 96 + state > the 104 registers of a softmax thread, ptxas spills 16 STL.64 + 32 LDL per block and the
-        // gain is gone.  Without the scores the redo cannot repair an exponential that already overflowed, so the exact maximum stays.
+        // Maximum-free blocks (plain kernel): the reference maximum m_ref is the row maximum of block 0; later blocks skip the 44 max
+        // instructions, the exchange between the two half-row threads and the vote (0.598 -> 0.560 ms at N = 1024).  P = exp2(s - m_ref)
+        // may then exceed 1, which is harmless while nothing overflows: P is bf16 with the fp32 exponent range, O and the row sums are
+        // fp32 and are normalised by the same sum at the end.  The epilogue checks every row's sum (finite and < 2^100); a CTA with a
+        // row out of range -- a score more than ~88 nats above its row's block-0 maximum -- recomputes its tile exactly on the CUDA
+        // cores (attn_tail_rows) before it exits.  A guard per block (redo from the scores in registers) was measured first: keeping the
+        // 64 scores live next to the 32 packed P registers spills 16 STL.64 + 32 LDL per block and costs what the maximum did.
         const bool do_max = (j == 0) || kBias || kFused || kDrop;
-#else
-        constexpr bool do_max = true;
-#endif
         if (do_max) {
         // block maximum of this half row (four independent chains), exchanged with the other half-row thread
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -1068,6 +1073,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     }
     mbar_wait(bar_o, (nkv - 1) & 1);
     tc_fence_after();
+    bool bad_row = false;
     if (!idle_rows) {
     // ---- epilogue: this thread's 32 columns of O (TMEM) -> registers, fold the few trailing keys (if any),
     //      combine the two half-row sums, normalise, store
@@ -1106,6 +1112,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     pair_bar_sync(quarter);
     const float l_tot = l_run + s_sum[(half ^ 1) * 128 + row];
     const float inv = 1.f / l_tot;
+    bad_row = q < p.N && !(l_tot < 0x1p100f);          // (also NaN / +inf: an exponential of a maximum-free block overflowed)
     if (q < p.N) {
       __nv_bfloat16* op = p.out + static_cast<int64_t>(row_base + q) * p.ld_out + head * kHD + half * 32;
 #pragma unroll
@@ -1120,6 +1127,15 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       if (half == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
     }
     }   // !idle_rows
+    if (!kBias && !kFused && !kDrop) {
+      // Maximum-free blocks: a row sum out of range means P overflowed somewhere in this tile.  The eight softmax warps agree through
+      // shared memory and recompute the tile's rows exactly on the CUDA cores (K / V straight from global memory; every TMA load and
+      // MMA of this CTA has completed, its shared memory is free).  Never taken for scores within ~88 nats of a row's block-0 maximum.
+      volatile uint32_t* s_flag = reinterpret_cast<volatile uint32_t*>(bars) + 32;
+      if (__any_sync(0xffffffffu, bad_row) && lane == 0) *s_flag = 1u;
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (*s_flag != 0u) attn_tail_rows<kSoftmaxWarps * 32, 5>(p, reinterpret_cast<float*>(smem), head, b, q0, min(kBQ, p.N - q0));
+    }
   }
   tc_fence_before();
   __syncthreads();
