@@ -224,6 +224,27 @@ def test_flash_attention_maximum_free_blocks_guard(cuda, N, late_gain, nats):
     _close(lse, torch.logsumexp(s, -1), 5e-4)
 
 
+@pytest.mark.parametrize("hot_key", [130, 131, 138, 129, 600, 1024])
+def test_flash_attention_single_hot_key_beyond_block0(cuda, hot_key):
+    """One key with a score hundreds of nats above everything else, sitting in a column that takes the polynomial exp2 (130, 131, 138),
+    a MUFU column (129), a later block or the trailing key (1024): a maximum-free block must not turn it into a wrapped exponent."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(hot_key)
+    B, N, heads = 1, 1025, 1
+    qkv = torch.randn(B * N, 3 * 64, device=cuda)
+    qkv[:, :64] = qkv[:, :64].abs() + 1.0                       # queries positive
+    qkv[:, 64:128] *= 0.1
+    qkv[hot_key, 64:128] = 24.0                                  # q . k / 8 ~ 64 * 1.8 * 24 / 8 = 350 nats
+    qkv = qkv.bfloat16()
+    q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / math.sqrt(64)
+    assert (s[..., hot_key] - s[..., :128].amax(-1)).min().item() > 150
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, 64)
+    out, lse = ops.flash_attn(qkv, B, N, heads, return_lse=True)
+    _close(out, ref, 8e-3)
+    _close(lse, torch.logsumexp(s, -1), 5e-4)
+
+
 @pytest.mark.parametrize("rows,d", [(1000, 256), (1025, 768), (333, 384), (77, 1024), (50, 2048), (3, 8)])
 def test_layernorm_fwd_bwd(cuda, rows, d):
     from vit_deep_radiomics_b200 import ops

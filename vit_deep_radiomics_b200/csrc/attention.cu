@@ -22,7 +22,7 @@
 #include "common.cuh"
 
 #ifndef VDR_ATTN_POLY_MASK
-#define VDR_ATTN_POLY_MASK 0x02u   // 1 pair of every 8: measured in the pipeline (power-capped) 0/8 0.874, 1/8 0.759, 2/8 0.799, 3/8 0.812, 4/8 0.887 ms
+#define VDR_ATTN_POLY_MASK 0x22u   // 2 pairs of every 8.  With maximum-free blocks (N = 1024 alone): 0/8 0.585, 1/8 0.562, 2/8 0.540, 3/8 0.554, 4/8 0.605 ms; bench.py on one box: 1/8 4,336-4,373, 2/8 4,344-4,401, 3/8 4,298-4,316, 4/8 4,191-4,214 slices/s (round 1, with the maximum in every block: 1/8 was the optimum)
 #endif
 
 namespace vdr {
@@ -128,7 +128,10 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
 __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
   float x0, x1;
   unpack2(x2, x0, x1);
-  x2 = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  // clamped on both sides: below, 2^x underflows cleanly; above (maximum-free blocks: x is not bounded by the running maximum any
+  // more), the exponent-field addition at the end would wrap into the sign bit -- at 128 the result is >= 2^127 or not finite,
+  // either of which trips the epilogue's row-sum check
+  x2 = pack2(fminf(fmaxf(x0, -125.f), 128.f), fminf(fmaxf(x1, -125.f), 128.f));
   const uint64_t magic2 = pack2(12582912.f, 12582912.f);           // 1.5 * 2^23: t = x + magic rounds x to an integer
   const uint64_t t2 = add2(x2, magic2);
   const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
