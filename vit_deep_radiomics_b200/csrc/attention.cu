@@ -298,8 +298,10 @@ constexpr int kTailEmptyBar = 16;   // bars[16..19]: ring slot consumed (8 warps
 __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const AttnParams& p, uint8_t* smem, int head, int b, int row0, int nrows) {
   const uint32_t base = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
-  uint64_t* full = bars + 1;                                              // [4] ring slot landed (the tile CTAs' bar_kv)
-  uint64_t* empty = bars + kTailEmptyBar;                                 // [4]
+  // Two ring stages of (K_j, V_j): one barrier pair per key block (both tiles of a block are waited for and released together --
+  // the CTA's lifetime is its hand-shakes, and it holds half an SM while it lives)
+  uint64_t* full = bars + 1;                                              // [2] stage landed (K and V tile: 32 KB)
+  uint64_t* empty = bars + kTailEmptyBar;                                 // [2]
   float* s_m = reinterpret_cast<float*>(smem + 5 * kTileBytes + 256);     // [8 warps][8 rows]
   float* s_l = s_m + 64;
   float* s_o = reinterpret_cast<float*>(smem);                            // the (unused) Q slot: [8 warps][8 rows][64]
@@ -307,7 +309,7 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
   const int nblk = (p.N + kBKV - 1) / kBKV;
   const int row_base = b * p.N, colK = p.d + head * kHD, colV = 2 * p.d + head * kHD;
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 8);
     }
@@ -315,13 +317,14 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
   }
   __syncthreads();
   if (warp == 8) {
-    // ---- producer: K_0 V_0 K_1 V_1 ... through the four ring slots
-    for (int tt = 0; tt < 2 * nblk; ++tt) {
-      const int slot = tt & 3;
-      if (tt >= 4) mbar_wait_relaxed(&empty[slot], ((tt >> 2) - 1) & 1);
+    // ---- producer: (K_0, V_0), (K_1, V_1), ... through two stages of two ring slots each
+    for (int jj = 0; jj < nblk; ++jj) {
+      const int st = jj & 1;
+      if (jj >= 2) mbar_wait_relaxed(&empty[st], ((jj >> 1) - 1) & 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[slot], kTileBytes);
-        tma_load_2d(tm, &full[slot], smem + kTileBytes * (1 + slot), (tt & 1) ? colV : colK, row_base + (tt >> 1) * kBKV);
+        mbar_arrive_expect_tx(&full[st], 2 * kTileBytes);
+        tma_load_2d(tm, &full[st], smem + kTileBytes * (1 + 2 * st), colK, row_base + jj * kBKV);
+        tma_load_2d(tm, &full[st], smem + kTileBytes * (2 + 2 * st), colV, row_base + jj * kBKV);
       }
       __syncwarp();
     }
@@ -344,11 +347,11 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
     for (int j = 0; j < nblk; ++j) {
       const int key0 = j * kBKV + warp * 16;
       const bool active = key0 < p.N;                                     // warp-uniform
-      const int tk = 2 * j, tv = 2 * j + 1;
-      mbar_wait_relaxed(&full[tk & 3], (tk >> 2) & 1);
+      const int st = j & 1;
+      mbar_wait_relaxed(&full[st], (j >> 1) & 1);
       uint32_t pa0 = 0u, pa2 = 0u;
       if (active) {
-        const uint32_t kt = base + kTileBytes * (1 + (tk & 3));
+        const uint32_t kt = base + kTileBytes * (1 + 2 * st);
         float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
         const int r = warp * 16 + (mi >> 1) * 8 + r8;                     // matrices 0/1: keys 0-7, matrices 2/3: keys 8-15
 #pragma unroll
@@ -379,11 +382,8 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
         pa0 = cvt_bf16x2(p00, p01);
         pa2 = cvt_bf16x2(p10, p11);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[tk & 3]);
-      mbar_wait_relaxed(&full[tv & 3], (tv >> 2) & 1);
       if (active) {
-        const uint32_t vt = base + kTileBytes * (1 + (tv & 3));
+        const uint32_t vt = base + kTileBytes * (2 + 2 * st);
         const int r = warp * 16 + (mi & 1) * 8 + r8;                      // matrices 0/2: keys 0-7, matrices 1/3: keys 8-15
 #pragma unroll
         for (int np = 0; np < 4; ++np) {                                  // 16 output dims per ldmatrix
@@ -394,7 +394,7 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[tv & 3]);
+      if (lane == 0) mbar_arrive(&empty[st]);
     }
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
