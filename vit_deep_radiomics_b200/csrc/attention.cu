@@ -297,6 +297,15 @@ constexpr int kTailEmptyBar = 16;   // bars[16..19]: ring slot consumed (8 warps
 
 __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const AttnParams& p, uint8_t* smem, int head, int b, int row0, int nrows) {
   const uint32_t base = smem_u32(smem);
+#ifdef VDR_ATTN_TRACE   // timeline of one trailing-row CTA (tools/attn_trace_tail.py): row = key block (15 = CTA-level stamps), warp 0 / producer
+#define TAIL_TRACE(row, ev)                                                                                        \
+  do {                                                                                                             \
+    if (p.trace != nullptr && (threadIdx.x & 31) == 0 && blockIdx.y == 5 && blockIdx.z == 60 && (row) < 16) p.trace[256 + (row) * 16 + (ev)] = attn_gtime(); \
+  } while (0)
+#else
+#define TAIL_TRACE(row, ev) do { } while (0)
+#endif
+  if (threadIdx.x == 0) TAIL_TRACE(15, 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
   // Two ring stages of (K_j, V_j): one barrier pair per key block (both tiles of a block are waited for and released together --
   // the CTA's lifetime is its hand-shakes, and it holds half an SM while it lives)
@@ -316,11 +325,13 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
     fence_barrier_init();
   }
   __syncthreads();
+  if (threadIdx.x == 0) TAIL_TRACE(15, 1);
   if (warp == 8) {
     // ---- producer: (K_0, V_0), (K_1, V_1), ... through two stages of two ring slots each
     for (int jj = 0; jj < nblk; ++jj) {
       const int st = jj & 1;
       if (jj >= 2) mbar_wait_relaxed(&empty[st], ((jj >> 1) - 1) & 1);
+      TAIL_TRACE(jj, 8);
       if (elect_one()) {
         mbar_arrive_expect_tx(&full[st], 2 * kTileBytes);
         tma_load_2d(tm, &full[st], smem + kTileBytes * (1 + 2 * st), colK, row_base + jj * kBKV);
@@ -348,7 +359,9 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
       const int key0 = j * kBKV + warp * 16;
       const bool active = key0 < p.N;                                     // warp-uniform
       const int st = j & 1;
+      if (warp == 0) TAIL_TRACE(j, 0);
       mbar_wait_relaxed(&full[st], (j >> 1) & 1);
+      if (warp == 0) TAIL_TRACE(j, 1);
       uint32_t pa0 = 0u, pa2 = 0u;
       if (active) {
         const uint32_t kt = base + kTileBytes * (1 + 2 * st);
@@ -382,6 +395,7 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
         pa0 = cvt_bf16x2(p00, p01);
         pa2 = cvt_bf16x2(p10, p11);
       }
+      if (warp == 0) TAIL_TRACE(j, 2);
       if (active) {
         const uint32_t vt = base + kTileBytes * (2 + 2 * st);
         const int r = warp * 16 + (mi & 1) * 8 + r8;                      // matrices 0/2: keys 0-7, matrices 1/3: keys 8-15
@@ -395,7 +409,9 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
+      if (warp == 0) TAIL_TRACE(j, 3);
     }
+    if (warp == 0) TAIL_TRACE(15, 2);
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
     if (t == 0) {
@@ -407,6 +423,7 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
       *reinterpret_cast<float2*>(s_o + (warp * 8 + g) * kHD + 8 * nt + 2 * t) = make_float2(oc[nt][0], oc[nt][1]);
   }
   __syncthreads();
+  if (threadIdx.x == 0) TAIL_TRACE(15, 3);
   // merge the eight per-warp states: thread (row, dim)
   for (int i = tid; i < nrows * kHD; i += kAttnThreads) {
     const int rr = i >> 6, dd = i & 63;
@@ -424,6 +441,8 @@ __device__ __forceinline__ void attn_tail_rows_mma(const CUtensorMap* tm, const 
     p.out[(static_cast<int64_t>(b) * p.N + q) * p.ld_out + head * kHD + dd] = __float2bfloat16_rn(acc / lt);
     if (dd == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (mt + log2f(lt)) * 0.69314718055994531f;
   }
+  if (threadIdx.x == 0) TAIL_TRACE(15, 4);
+#undef TAIL_TRACE
 }
 
 // Pipeline per 128-key block j (no CTA-wide barrier in the loop):
