@@ -77,6 +77,32 @@ def test_sam_entry_points_validate_arguments_without_a_gpu():
                         torch.zeros(14, 64, dtype=torch.bfloat16))
 
 
+def test_sam_forward_and_gray_patch_embedding_validate_arguments_without_a_gpu():
+    """vdr_sam_forward / vdr_patch_embed_gemm_gray reject bad arguments before any CUDA call; the workspace query needs no GPU."""
+    lib = _C.lib()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.addressof(buf)
+    p += (-p) % 256
+    blocks = (_C.SamBlock * 2)()
+    w = _C.SamWeights(128, 2, 2, 16, 256, 256, 64, 1e-6, p, 768, p, 256, p, p, p, p, p, p, p, p, ctypes.cast(blocks, ctypes.POINTER(_C.SamBlock)))
+    need = lib.vdr_sam_forward_workspace_bytes(ctypes.byref(w), 2)
+    rows = 2 * 256
+    assert need >= rows * 128 * 2 * (1 + 1 + 3 + 4)                      # X, Y, QKV, MLP hidden (bf16) at least
+    assert lib.vdr_sam_forward(None, p, None, 1, p, 64, p, 1 << 30, None) == -1 and b"null weights" in lib.vdr_last_error_string()
+    assert lib.vdr_sam_forward(ctypes.byref(w), p, p, 1, p, 64, p, 1 << 30, None) == -1           # both input forms at once
+    assert b"either gray slices" in lib.vdr_last_error_string()
+    assert lib.vdr_sam_forward(ctypes.byref(w), p, None, 1, p, 64, p, 16, None) != 0              # workspace too small
+    assert b"workspace too small" in lib.vdr_last_error_string()
+    assert lib.vdr_sam_forward(ctypes.byref(w), p, None, 1, p, 64, p, 1 << 30, None) == -1        # blocks without folded weights / tables
+    assert b"folded-LayerNorm" in lib.vdr_last_error_string()
+    bad = _C.SamWeights(100, 2, 2, 16, 256, 256, 64, 1e-6, p, 768, p, 256, p, p, p, p, p, p, p, p, ctypes.cast(blocks, ctypes.POINTER(_C.SamBlock)))
+    assert lib.vdr_sam_forward_workspace_bytes(ctypes.byref(bad), 1) == 0                         # dim != heads x 64
+    assert lib.vdr_patch_embed_gemm_gray(None, 1, 256, 256, 16, p, 256, p, p, p, 128, 128, 0, None) == -1
+    assert lib.vdr_patch_embed_gemm_gray(p, 1, 224, 224, 16, p, 256, p, p, p, 128, 128, 1, None) == -1   # 14-wide grid: no TMA im2col box
+    assert b"do not tile" in lib.vdr_last_error_string()
+    assert lib.vdr_patch_embed_gemm_gray(p, 1, 256, 256, 16, p, 256, p, p, p, 128, 128, -1, None) == -1  # negative token offset
+
+
 def test_every_entry_point_has_declared_argument_types():
     """A ctypes function without argtypes would pass 64-bit device pointers as C ints: every exported function that takes
     arguments declares them, and their count matches the header's parameter list."""
