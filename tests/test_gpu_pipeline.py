@@ -333,6 +333,46 @@ def test_train_epoch_bimodal_crossmodal_loss_matches_cpu_training(cuda, golden_d
         assert (v.cpu() - sd[k].detach()).abs().max() < 3e-3, k     # 2 AdamW steps of lr 5e-4
 
 
+def test_cuda_graph_training_step_bimodal_equals_eager_step(cuda, golden_dir):
+    """graph_step.GraphedTrainStep for the bimodal model: one graph per (CT count, PET count) pair, CrossModalFocalLoss on
+    outputs[0], [2], [3]; three epochs (eager visit, capture, replay -- weights change in between) give the eager loop's losses and
+    weights (float atomics in the backward: last bits)."""
+    from vit_deep_radiomics_b200.graph_step import graphed_step
+    from vit_deep_radiomics_b200.models_archs import TransformerNoduleBimodalClassifier, set_dropout
+    from vit_deep_radiomics_b200.train_models import make_criterion, train_epoch
+    g = np.load(os.path.join(golden_dir, "bimodal_small.npz"))
+    cfg = [int(v) for v in g["cfg"]]
+    d = cfg[0]
+    sd0 = {k[len("param__"):]: torch.tensor(g[k]) for k in g.files if k.startswith("param__")}
+    gen = torch.Generator().manual_seed(9)
+    data = [(torch.randn(nc, d, generator=gen).to(cuda), torch.randn(np_, d, generator=gen).to(cuda), torch.eye(2)[c].to(cuda))
+            for nc, np_, c in [(30, 12, 0), (21, 40, 1), (30, 12, 1), (26, 26, 0)]]
+    crit = make_criterion("crossmodal", cuda)
+    out = []
+    for graphs in (False, True):
+        model = TransformerNoduleBimodalClassifier(*cfg)
+        model.load_state_dict(sd0)
+        model = set_dropout(model.to(cuda), 0.0, 0.0)
+        # (plain SGD: Adam's normalisation turns the float-atomics noise of mathematically-zero gradients -- key biases -- into lr-sized steps)
+        opt = torch.optim.SGD(model.parameters(), lr=0.01)     # (the eager loop itself repeats to ~1e-5 in the loss at lr 0.05: atomics noise grows with the step size)
+        losses = [train_epoch(model, data, crit, opt, virtual_batch_size=3, cuda_graphs=graphs)[0] for _ in range(3)]
+        if graphs:
+            st = graphed_step(model, crit)
+            assert len(st.graphs) == 3 and st.replays >= 7, (st.replays, st.eager, len(st.graphs))   # (30, 12) is seen twice per epoch
+        out.append((losses, {k_: v.clone() for k_, v in model.state_dict().items()}))
+    (l0, w0), (l1, w1) = out
+    assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-5, (l0, l1)
+    for k_ in w0:
+        assert (w0[k_] - w1[k_]).abs().max().item() < 2e-5, k_
+    # train-mode dropout inside a captured bimodal step: replays draw fresh masks (device seed counter), losses stay finite
+    model = TransformerNoduleBimodalClassifier(*cfg)
+    model.load_state_dict(sd0)
+    model = model.to(cuda)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.01)
+    ls = [train_epoch(model, data, crit, opt, virtual_batch_size=3, cuda_graphs=True)[0] for _ in range(4)]
+    assert all(np.isfinite(v) for v in ls) and len(set(round(v, 6) for v in ls)) > 1
+
+
 def test_native_vit_forward_equals_op_by_op_path(cuda):
     """vdr_vit_forward (one C call) enqueues the same kernels in the same order as the Python op-by-op path: identical tokens."""
     from vit_deep_radiomics_b200 import synth, tfds_dense_descriptor as tdd

@@ -198,6 +198,9 @@ class TransformerNoduleBimodalClassifier(nn.Module):
                     head_ct=_mlp_params(self.classifier_ct), head_pet=_mlp_params(self.classifier_pet),
                     proj=_mlp_params(self.projection_petct), head_petct=_mlp_params(self.classifier_petct))
 
+    def _drop_rates(self):
+        return float(self.transformer_encoder_ct.layers[0].dropout.p), float(self.classifier_ct.dropout_rate)
+
     def forward(self, x_ct=None, x_pet=None):
         """x_* (batch, seq_len, feature_dim) f32 CUDA or None (at least one).  Batches are looped (the reference runs batch 1)."""
         if x_ct is None and x_pet is None:
@@ -213,9 +216,10 @@ class TransformerNoduleBimodalClassifier(nn.Module):
             xp = x_pet[b] if x_pet is not None else None
             drop = None
             if self.training:   # 0.5 in both encoders (:51,58), 0.1 in the four MLPLayers (:66-75)
-                p_enc, p_head = float(self.transformer_encoder_ct.layers[0].dropout.p), float(self.classifier_ct.dropout_rate)
+                p_enc, p_head = self._drop_rates()
                 if p_enc > 0 or p_head > 0:
-                    drop = ck.DropCfg(ck.new_seed(), p_enc, p_head)
+                    override = self.__dict__.get("_drop_override")    # graph_step: seed taken from a device counter during capture
+                    drop = override() if override is not None else ck.DropCfg(ck.new_seed(), p_enc, p_head)
             if train:
                 r = bk.BimodalFunction.apply(xc, xp, self.cfg, sizes, drop, *flat)
             else:

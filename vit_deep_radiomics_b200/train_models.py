@@ -350,15 +350,16 @@ def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, gra
     Loss is divided by iters_to_accumulate = min(virtual_batch, len(samples)) (:655,674); the optimizer
     steps every iters_to_accumulate samples and at the last sample (:685-687).  ``grad_sync`` (optional
     callable) is invoked right before each optimizer step: the data-parallel gradient all-reduce.
-    ``cuda_graphs``: unimodal model only -- forward + loss + backward of a sample run as one CUDA graph per token count
-    (graph_step.GraphedTrainStep: captured the second time a length is seen, same kernels in the same order as the eager step).
+    ``cuda_graphs``: forward + loss + backward of a sample run as one CUDA graph per token count (per (CT, PET) pair of counts for
+    the bimodal model; graph_step.GraphedTrainStep: captured the second time a length is seen, same kernels in the same order as
+    the eager step).
     Returns (mean loss, list of softmax scores)."""
     from .distributed import zero_grads
     samples = list(samples)
     iters = min(virtual_batch_size, len(samples))
     model.train()
     step = None
-    if cuda_graphs and isinstance(model, TransformerNoduleClassifier) and not isinstance(criterion, CrossModalFocalLoss):
+    if cuda_graphs and isinstance(model, (TransformerNoduleClassifier, TransformerNoduleBimodalClassifier)):
         from .graph_step import graphed_step
         step = graphed_step(model, criterion)
     zero_grads(model, optimizer)
@@ -366,7 +367,7 @@ def train_epoch(model, samples, criterion, optimizer, virtual_batch_size=32, gra
     for i, sample in enumerate(samples):
         label = sample[-1]
         if step is not None:
-            loss, logits = step(sample[0], label, 1.0 / iters)
+            loss, logits = step(sample[0] if len(sample) == 2 else tuple(sample[:-1]), label, 1.0 / iters)
         else:
             outputs = model(*(t.unsqueeze(0) for t in sample[:-1]))
             logits = outputs[0]
@@ -416,8 +417,8 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
     scale (:674), so ``grad_sync`` (``distributed.allreduce_grads``: one sum over the ranks) right before each optimizer step
     yields the single-process gradients.  ``order`` must be the same list on every rank.  Labels / scores / ids / the loss
     are gathered, so every rank returns the whole epoch's records.
-    ``cuda_graphs`` (training pass of a unimodal model): each sample's forward + loss + backward replays a CUDA graph kept per token
-    count (graph_step.GraphedTrainStep); lengths seen for the first time run eagerly.
+    ``cuda_graphs`` (training pass): each sample's forward + loss + backward replays a CUDA graph kept per token
+    count (per pair of counts for the two clouds of the bimodal model) (graph_step.GraphedTrainStep); lengths seen for the first time run eagerly.
     Returns (mean loss, y_true list, y_score list, patient ids)."""
     import torch.distributed as dist
     from .distributed import zero_grads
@@ -429,8 +430,7 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
         zero_grads(model, optimizer)
     total, y_true, y_score, pids = 0.0, [], [], []
     step = None
-    if (train and cuda_graphs and modality not in ("petct", "petchest") and isinstance(model, TransformerNoduleClassifier)
-            and not isinstance(criterion, CrossModalFocalLoss)):
+    if train and cuda_graphs and isinstance(model, (TransformerNoduleClassifier, TransformerNoduleBimodalClassifier)):
         from .graph_step import graphed_step
         step = graphed_step(model, criterion)
     with torch.enable_grad() if train else torch.no_grad():
@@ -439,7 +439,10 @@ def run_epoch(model, dataset, order, criterion, modality, device, optimizer=None
                 if step is not None:
                     ct, pet, onehot, pid = dataset[int(idx)]
                     label = torch.squeeze(torch.as_tensor(onehot)).to(device)
-                    loss, logits = step((pet if modality == "pet" else ct).to(device), label, 1.0 / iters)
+                    if modality in ("petct", "petchest"):
+                        loss, logits = step((ct.to(device), pet.to(device)), label, 1.0 / iters)
+                    else:
+                        loss, logits = step((pet if modality == "pet" else ct).to(device), label, 1.0 / iters)
                     outputs = (logits,)
                 else:
                     outputs, label, pid = _forward_item(model, dataset[int(idx)], modality, device)
