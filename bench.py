@@ -531,6 +531,94 @@ def bench_classifier(D: Dist, samples: int = 64, epochs: int = 2, cpu_samples: i
     return rec
 
 
+def bench_classifier_bimodal(D: Dist, samples: int = 32, epochs: int = 2):
+    """N4: the PET/CT bimodal classifier exactly as conf/parameters_models.yaml builds it for 'petct' (two encoders,
+    CLS-query cross attention both ways, three heads; CrossModalFocalLoss), one training sample = one CUDA graph per (CT, PET) pair
+    of token counts.  Single GPU; samples/s with the optimizer step of a 32-sample virtual batch inside the timed region."""
+    from oracle import classifier_fp32 as C
+    from vit_deep_radiomics_b200 import _C, config_manager, train_models as tm
+    from vit_deep_radiomics_b200.distributed import zero_grads
+    from vit_deep_radiomics_b200.graph_step import graphed_step
+    dev = D.dev
+    cfg = config_manager.load_conf(project_dir=os.path.dirname(os.path.abspath(__file__)))
+    cm = cfg["models"]["transformer"]
+    d = cm["feature_dim"]
+    gen = torch.Generator().manual_seed(1239)
+    n_ct = torch.randint(512, 4096, (samples,), generator=gen)
+    n_pet = torch.randint(64, 1024, (samples,), generator=gen)
+    host = [(torch.randn(int(a), d, generator=gen), torch.randn(int(b), d, generator=gen), torch.eye(2)[i % 2]) for i, (a, b) in enumerate(zip(n_ct, n_pet))]
+    data = [tuple(t.to(dev) for t in smp) for smp in host]
+    torch.manual_seed(0)
+    model = tm.build_model(cfg, "transformer", "petct").to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    crit = tm.make_criterion("crossmodal", dev)
+    step = graphed_step(model, crit)
+    model.train()
+
+    def epoch():
+        zero_grads(model, opt)
+        tot = torch.zeros((), device=dev)
+        for k, (xc, xp, y) in enumerate(data):
+            loss, _ = step((xc, xp), y, 1.0 / 32)
+            tot += loss
+            if (k + 1) % 32 == 0 or k + 1 == len(data):
+                opt.step()
+                zero_grads(model, opt)
+        return tot
+
+    epoch()                                     # first visit of every pair of lengths: eager
+    epoch()                                     # second visit: captured
+    n0 = _C.launch_count()
+    ms, _ = D.timed(epoch, epochs)
+    launches = _C.launch_count() - n0
+    tm.train_epoch(model, data[:8], crit, opt, virtual_batch_size=32, cuda_graphs=False)      # (warm: per-shape kernel attributes of the eager path)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tm.train_epoch(model, data[:8], crit, opt, virtual_batch_size=32, cuda_graphs=False)
+    torch.cuda.synchronize()
+    eager_ms = (time.perf_counter() - t0) / 8 * 1e3
+    rec = {"workload": f"N4: TransformerNoduleBimodalClassifier ('petct' of conf/parameters_models.yaml, feature_dim {d}) training on {samples} synthetic "
+                       "(CT 512..4096, PET 64..1024 token) cloud pairs, virtual batch 32, AdamW, CrossModalFocalLoss",
+           "value": samples * epochs / (ms / 1e3), "unit": "samples/s", "ms_per_sample": ms / (epochs * samples), "gpu_launches": int(launches),
+           "op_by_op_ms_per_sample": eager_ms,
+           "cuda_graphs": {"pairs_captured": len(step.graphs), "replays": step.replays, "eager_steps": step.eager, "pool_bytes": int(step.bytes)}}
+    ct_c, pet_c = cm["ct"], cm["pet"]
+    ff_ct, ff_pet = int(d * ct_c["mlp_ratio"]), int(d * pet_c["mlp_ratio"])
+    flops = sum(3.0 * (_classifier_flops(int(a) + 1, d, ff_ct, ct_c["num_layers"]) + _classifier_flops(int(b) + 1, d, ff_pet, pet_c["num_layers"]))
+                for a, b in zip(n_ct, n_pet)) * epochs
+    peaks = measured_peaks()
+    tfl = flops / (ms / 1e3) / 1e12
+    rec["roofline"] = {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "peak": peaks["bf16"], **tensor_fracs(tfl, peaks),
+                       "note": "fwd+bwd algorithmic flops of the two encoders (3 x forward); batch-1 sequences: launch- and latency-bound"}
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    crit_c = tm.CrossModalFocalLoss(alpha=torch.tensor([0.25, 0.75]), gamma_unimodal=2.0, gamma_bimodal=1.0, beta=0.6)
+    t1 = time.perf_counter()
+    xc, xp, y = host[0]
+    lg, _, lc, lp = C.bimodal_forward(sd, xc[None], xp[None], ct_c["num_heads"], pet_c["num_heads"], ct_c["num_layers"], pet_c["num_layers"])
+    crit_c(lg[0], lc[0], lp[0], y).backward()
+    cpu_dt = time.perf_counter() - t1
+    rec["cpu_baseline"] = {"value": 1.0 / cpu_dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                           "sample": f"first cloud pair ({int(n_ct[0])}, {int(n_pet[0])} tokens), fp32 oracle fwd+bwd (oracle/classifier_fp32.bimodal_forward, "
+                                     f"pinned to the unmodified models_archs module), {cpu_dt:.2f} s wall"}
+    # e2e: cloud pairs start in pinned host memory, the loss comes back per sample
+    pin = [tuple(t.pin_memory() for t in smp) for smp in host[:8]]
+
+    def e2e_pass():
+        zero_grads(model, opt)
+        for xc_, xp_, y_ in pin:
+            loss, _ = step((xc_.to(dev, non_blocking=True), xp_.to(dev, non_blocking=True)), y_.to(dev, non_blocking=True), 1.0 / 32)
+            float(loss.item())
+        opt.step()
+
+    e2e_pass()
+    ms_e, _ = D.timed(e2e_pass, 2)
+    rec["e2e"] = {"value": len(pin) * 2 / (ms_e / 1e3), "unit": "samples/s",
+                  "h2d_bytes_per_step": int(sum(a.numel() + b.numel() for a, b, _ in pin) * 4 // len(pin)), "d2h_bytes_per_step": 4,
+                  "api": "graph_step.GraphedTrainStep((x_ct, x_pet), label) = train_models.train_epoch(cuda_graphs=True) for the bimodal model, pinned host clouds"}
+    return rec
+
+
 def bench_pipeline(D: Dist, patients: int = 4, cpu_slices: int = 4, model: str | None = None):
     """C5: per patient a 512x512x120 volume goes through ViT-B/16 extraction, the mask gather (+ PE) and ONE training step of the
     point-cloud classifier on the 768-wide descriptors (feature_dim 768 / 12 heads in the YAML schema; the reference's 256 comes
@@ -752,6 +840,9 @@ def run_ours(args):
         sub["C4"] = bench_extraction(D, "C4", 5, 3, profile=(world == 1), cpu_slices=8, patients_per_step=8)
         torch.cuda.empty_cache()
         sub["c3"] = bench_classifier(D)
+        torch.cuda.empty_cache()
+        if world == 1:
+            sub["c3_bimodal"] = bench_classifier_bimodal(D)
         torch.cuda.empty_cache()
         sub["C5"] = bench_pipeline(D)
         torch.cuda.empty_cache()
