@@ -352,3 +352,33 @@ def test_sam_native_forward_equals_op_by_op(cuda, hw, B):
     assert err <= 0.05, err                                     # O(1) LayerNorm outputs; bf16 patch weights summed vs summed products
     cos = torch.nn.functional.cosine_similarity(native_v, eager_v, dim=1).min().item()
     assert cos >= 0.9995, cos
+
+
+@pytest.mark.parametrize("gain,nats", [(4.0, 30), (14.0, 120)])
+def test_fused_relpos_attention_maximum_free_blocks_guard(cuda, gain, nats):
+    """The fused global-attention kernel takes its reference maximum from key block 0 (two rows of the token grid) and runs the later
+    blocks without a maximum.  Keys further down whose scores sit tens of nats above it (large P, no overflow) or > 88 nats above it
+    (exp2 overflows: the row sums flag the tile and the CTA recomputes it exactly, bias included, on the CUDA cores) must give the
+    fp32 softmax either way."""
+    from vit_deep_radiomics_b200 import ops
+    g = torch.Generator().manual_seed(int(gain))
+    BW, Sh, Sw, heads = 1, 8, 64, 2
+    N, d = Sh * Sw, heads * 64
+    qkv = torch.randn(BW * N, 3 * d, generator=g)
+    x = qkv.view(BW, N, 3, heads, 64)
+    x[:, :, 0] = x[:, :, 0].abs() * 0.5 + 2.0
+    x[:, :, 1] = x[:, :, 1].abs() * 0.1 + 0.5
+    x[:, 200:330, 1] *= gain                                    # rows 3 .. 5 of the grid: key blocks 1 and 2
+    qkv = qkv.bfloat16()
+    rel_h = torch.randn(2 * Sh - 1, 64, generator=g) * 0.1
+    rel_w = torch.randn(2 * Sw - 1, 64, generator=g) * 0.1
+    want, _ = _attn_reference(qkv, BW, Sh, Sw, heads, rel_h, rel_w)
+    q, k, _ = qkv.float().reshape(BW, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0
+    assert (s[..., 128:].amax(-1) - s[..., :128].amax(-1)).max().item() > nats
+    hi, lo = ops.relpos_split(rel_h.to(cuda), rel_w.to(cuda))
+    fused = ops.attn_relpos(qkv.to(cuda), BW, Sh, Sw, heads, hi, lo, kernel="fused").cpu().float()
+    assert torch.isfinite(fused).all()
+    err = (fused - want).abs().max()
+    cos = F.cosine_similarity(fused.reshape(-1, 64), want.reshape(-1, 64), dim=1).min()
+    assert err < 2e-2 * max(1.0, float(want.abs().max()) / 3.0) and cos > 0.9995, (float(err), float(cos))

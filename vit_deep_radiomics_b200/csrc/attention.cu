@@ -74,6 +74,9 @@ struct AttnParams {
   // rel[(b*heads + head)*N + q][kh] + rel[...][Sh + kw] for key (kh, kw), already multiplied by log2(e)  (vdr_relpos_tables)
   const float* rel;
   int rel_pitch;               // Sh + 64
+  // kFused instantiation: the split [rel_pos_h (2 Sh - 1) ; rel_pos_w (127)] x 64 tables as plain pointers (the kernel reads them through
+  // TMA; the exact CUDA-core recomputation of a tile whose maximum-free blocks overflowed reads them directly)
+  const __nv_bfloat16 *rcat_hi, *rcat_lo;
   DropSpec drop;               // kDrop instantiation only: attention dropout (thr16 == 0: off)
 };
 constexpr int kBiasPitch = 136;                          // bytes per query row of the rel_w terms in shared memory: 64 halfs + 8 pad
@@ -173,7 +176,8 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // row each): a warp-wide load touches 4 rows x 128 contiguous bytes; the 48 lane-groups of the CTA each run an online
 // softmax over the keys dealt to them and the partial states are merged through shared memory.
 // kBar == 0: called by the whole CTA (__syncthreads); kBar > 0: called by threads 0 .. kThreads - 1 only (named barrier kBar).
-template <int kThreads, int kBar = 0>
+// kRel: + the decomposed relative-position bias of a token grid of Sh x 64 (SAM's global-attention blocks), from p.rcat_hi / p.rcat_lo.
+template <int kThreads, int kBar = 0, bool kRel = false>
 __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, int head, int b, int row0, int nrows) {
   auto sync = [] {
     if (kBar == 0) __syncthreads();
@@ -217,6 +221,10 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
       qv[0] = a0.x * p.scale_log2; qv[1] = a0.y * p.scale_log2; qv[2] = a1.x * p.scale_log2; qv[3] = a1.y * p.scale_log2;
       qv[4] = a2.x * p.scale_log2; qv[5] = a2.y * p.scale_log2; qv[6] = a3.x * p.scale_log2; qv[7] = a3.y * p.scale_log2;
     }
+    float qb[8];                                                     // kRel: the unscaled query (x log2 e) against the table rows
+#pragma unroll
+    for (int d = 0; d < 8; ++d) qb[d] = kRel ? qv[d] * (1.4426950408889634f / p.scale_log2) : 0.f;
+    const int Sh = p.N >> 6, qh = q >> 6, qw = q & 63;
 #pragma unroll
     for (int d = 0; d < 8; ++d) o[d] = 0.f;
     float m = -INFINITY, l = 0.f;
@@ -229,6 +237,19 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vu.x), "=r"(vu.y), "=r"(vu.z), "=r"(vu.w) : "r"(src + kThreads * 16) : "memory");
         const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y), k2 = unpack_bf16x2(ku.z), k3 = unpack_bf16x2(ku.w);
         float sdot = qv[0] * k0.x + qv[1] * k0.y + qv[2] * k1.x + qv[3] * k1.y + qv[4] * k2.x + qv[5] * k2.y + qv[6] * k3.x + qv[7] * k3.y;
+        if (kRel) {   // rel_h[q, kh] = q . rel_pos_h[qh - kh + Sh - 1], rel_w[q, kw] = q . rel_pos_w[qw - kw + 63]: this lane's 8 dims of both
+          const int j = grp + step * kGroups, kh = j >> 6, kw = j & 63;
+          const int rows[2] = {qh - kh + Sh - 1, 2 * Sh - 1 + qw - kw + 63};
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p.rcat_hi + static_cast<int64_t>(rows[r]) * kHD + sub * 8));
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p.rcat_lo + static_cast<int64_t>(rows[r]) * kHD + sub * 8));
+            const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y), h2 = unpack_bf16x2(hi.z), h3 = unpack_bf16x2(hi.w);
+            const float2 l0 = unpack_bf16x2(lo.x), l1 = unpack_bf16x2(lo.y), l2 = unpack_bf16x2(lo.z), l3 = unpack_bf16x2(lo.w);
+            sdot += qb[0] * (h0.x + l0.x) + qb[1] * (h0.y + l0.y) + qb[2] * (h1.x + l1.x) + qb[3] * (h1.y + l1.y) +
+                    qb[4] * (h2.x + l2.x) + qb[5] * (h2.y + l2.y) + qb[6] * (h3.x + l3.x) + qb[7] * (h3.y + l3.y);
+          }
+        }
         sdot += __shfl_xor_sync(gmask, sdot, 1);   // reduce inside the 8-lane group (groups may skip the last step,
         sdot += __shfl_xor_sync(gmask, sdot, 2);   //  so the mask names only this group)
         sdot += __shfl_xor_sync(gmask, sdot, 4);
@@ -989,7 +1010,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         // row out of range -- a score more than ~88 nats above its row's block-0 maximum -- recomputes its tile exactly on the CUDA
         // cores (attn_tail_rows) before it exits.  A guard per block (redo from the scores in registers) was measured first: keeping the
         // 64 scores live next to the 32 packed P registers spills 16 STL.64 + 32 LDL per block and costs what the maximum did.
-        const bool do_max = (j == 0) || kBias || kFused || kDrop;
+        const bool do_max = (j == 0) || (kBias && !kFused) || kDrop;   // (plain and fused instantiations run maximum-free blocks)
         if (do_max) {
         // block maximum of this half row (four independent chains), exchanged with the other half-row thread
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -1149,14 +1170,14 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       if (half == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
     }
     }   // !idle_rows
-    if (!kBias && !kFused && !kDrop) {
+    if ((!kBias || kFused) && !kDrop) {
       // Maximum-free blocks: a row sum out of range means P overflowed somewhere in this tile.  The eight softmax warps agree through
       // shared memory and recompute the tile's rows exactly on the CUDA cores (K / V straight from global memory; every TMA load and
       // MMA of this CTA has completed, its shared memory is free).  Never taken for scores within ~88 nats of a row's block-0 maximum.
       volatile uint32_t* s_flag = reinterpret_cast<volatile uint32_t*>(bars) + 32;
       if (__any_sync(0xffffffffu, bad_row) && lane == 0) *s_flag = 1u;
       asm volatile("bar.sync 5, 256;" ::: "memory");
-      if (*s_flag != 0u) attn_tail_rows<kSoftmaxWarps * 32, 5>(p, reinterpret_cast<float*>(smem), head, b, q0, min(kBQ, p.N - q0));
+      if (*s_flag != 0u) attn_tail_rows<kSoftmaxWarps * 32, 5, kFused>(p, reinterpret_cast<float*>(smem), head, b, q0, min(kBQ, p.N - q0));
     }
   }
   tc_fence_before();
@@ -2001,6 +2022,8 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   p.dbg = getenv("VDR_ATTN_DBG") ? atoi(getenv("VDR_ATTN_DBG")) : 0;
   p.rel = rel;
   p.rel_pitch = rel_pitch;
+  p.rcat_hi = static_cast<const __nv_bfloat16*>(rcat_hi);
+  p.rcat_lo = static_cast<const __nv_bfloat16*>(rcat_lo);
   p.drop = DropSpec{0ull, 0u, 0u, nullptr};
   if (dropout) p.drop = DropSpec{drop->seed, drop->site, drop->thr16, reinterpret_cast<const unsigned long long*>(drop->seed_offset)};
   // full 128-row query tiles on the tensor cores; a short tail of rows (<= 8) on one extra CUDA-core CTA per (image, head)
