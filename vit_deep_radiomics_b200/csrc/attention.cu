@@ -1983,10 +1983,17 @@ static int launch_flash_attn(const char* who, const void* qkv, int64_t ld_qkv, c
   // v6 (four light CTAs per SM) is faster than v5 when timed alone (N = 1024: 0.596 vs 0.627 ms) but slower inside the
   // power-capped extraction step (0.904 vs 0.875 ms per layer at N = 1025): v5 stays the default, VDR_ATTN_V6=1 selects v6 for A/B runs
   static const bool want_v6 = getenv("VDR_ATTN_V6") != nullptr;
+  static const bool want_v5 = getenv("VDR_ATTN_V5") != nullptr;   // A/B: never pick v6 by shape
   const bool dropout = drop != nullptr && drop->thr16 != 0;
   VDR_CHECK_ARG(!dropout || (rel == nullptr && drop->thr16 < 65536u), VDR_EINVAL, "%s: attention dropout needs thr16 < 65536 and no rel-pos bias", who);
   const bool fused = rcat_hi != nullptr;
-  const bool v6 = rel == nullptr && want_v6 && !dropout && !fused;
+  // Short sequences with a few trailing rows (N = 257 = 2 * 128 + 1 of ViT-L/14 @224): a third of the v5 grid would be trailing-row CTAs
+  // and the tile CTAs are all prologue; v6's light CTAs take every tile through the tensor cores.  Measured, B 120 / 12 heads alone:
+  // N = 257 0.114 (v5) vs 0.104 ms (v6); inside the C4 step 0.201 vs 0.177 ms per launch, 6,140-6,300 vs 6,510-6,520 slices/s.
+  // N = 513 is a tie, N = 1025 goes to v5 (above).
+  const int tail_pre = N % kBQ;
+  const bool short_tail = tail_pre >= 1 && tail_pre <= 8 && N > kBQ && N < 512 && !want_v5;
+  const bool v6 = rel == nullptr && (want_v6 || short_tail) && !dropout && !fused;
   CUtensorMap tm, tm_rhi, tm_rlo;
   int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * d, (uint64_t)ld_qkv, v6 ? kV6BK : 128, kHD);
   if (rc != VDR_OK) return rc;
