@@ -253,7 +253,7 @@ int vdr_cls_concat_layernorm_fwd(const float* X, const float* cls, const float* 
  * out bf16 (B*N, d).  lse (B, h, N) f32 optional (log-sum-exp, for the backward pass).
  * drop (NULL = none): attention dropout of nn.MultiheadAttention -- the NORMALISED probabilities are dropped before P V (the row
  * sums keep every key); element (row (b*heads + h)*N + q, column k) of the site.
- * Numerics: exact softmax for any finite input.  Without dropout the kernel takes the reference maximum of a row from its first
+ * Numerics: exact softmax for any finite input.  The kernel takes the reference maximum of a row from its first
  * 128-key block and runs the later blocks maximum-free; a tile in which a later score exceeds that maximum by more than ~88 nats
  * (exp2 would overflow) is detected from its row sums and recomputed exactly before the kernel returns -- slower for such tiles,
  * never wrong.  The same holds for vdr_flash_attn_relpos_fused_fwd below.

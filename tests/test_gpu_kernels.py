@@ -515,6 +515,32 @@ def test_flash_attention_dropout_fwd_bwd_vs_fp32_autograd(cuda, N, heads, p):
     assert torch.equal(ops.flash_attn(qkv, 1, N, heads), ops.flash_attn(qkv, 1, N, heads, drop=ops.Drop(1, 2, 0.0)))
 
 
+@pytest.mark.parametrize("gain,nats", [(5.0, 35), (16.0, 120)])
+def test_flash_attention_dropout_maximum_free_blocks_guard(cuda, gain, nats):
+    """The dropout instantiation runs maximum-free key blocks as well: late keys tens of nats above the block-0 maximum (large P) and
+    hundreds of nats above it (overflow -> the tile is recomputed exactly, dropout mask included) against fp32 with the exported mask."""
+    from vit_deep_radiomics_b200 import ops
+    torch.manual_seed(int(gain))
+    N, heads = 700, 2
+    d = heads * 64
+    qkv = torch.randn(N, 3 * d, device=cuda)
+    x = qkv.view(N, 3, heads, 64)
+    x[:, 0] = x[:, 0].abs() * 0.5 + 2.0
+    x[:, 1] = x[:, 1].abs() * 0.1 + 0.5
+    x[200:520, 1] *= gain
+    qkv = qkv.bfloat16()
+    drop = ops.Drop(seed=99, site=3, p=0.25)
+    out, lse = ops.flash_attn(qkv, 1, N, heads, return_lse=True, drop=drop)
+    mk = ops.dropout_mask(heads * N, N, drop, cuda).bool().view(heads, N, N)
+    q, k, v = (qkv.float()[:, i * d:(i + 1) * d].view(N, heads, 64).transpose(0, 1) for i in range(3))
+    s = q @ k.transpose(1, 2) / 8.0
+    assert (s[..., 128:].amax(-1) - s[..., :128].amax(-1)).max().item() > nats
+    ref = ((torch.softmax(s, -1) * mk.float() / (1 - drop.p)) @ v).transpose(0, 1).reshape(N, d)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max() < 0.06 * max(1.0, float(ref.abs().max()) / 3.0)
+    assert torch.allclose(lse[0], torch.logsumexp(s, -1), rtol=2e-4, atol=2e-2)
+
+
 def test_classifier_train_mode_dropout_gradients_vs_fp32_autograd(cuda):
     """TransformerNoduleClassifier in train() with the reference's rates (0.1 / 0.1): the kernels' forward and EVERY parameter
     gradient against an fp32 autograd restatement of the same network that applies the exported masks at the same sites

@@ -177,7 +177,8 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // softmax over the keys dealt to them and the partial states are merged through shared memory.
 // kBar == 0: called by the whole CTA (__syncthreads); kBar > 0: called by threads 0 .. kThreads - 1 only (named barrier kBar).
 // kRel: + the decomposed relative-position bias of a token grid of Sh x 64 (SAM's global-attention blocks), from p.rcat_hi / p.rcat_lo.
-template <int kThreads, int kBar = 0, bool kRel = false>
+// kDropT: attention dropout (p.drop) on the normalised probabilities, as the tensor-core paths apply it.
+template <int kThreads, int kBar = 0, bool kRel = false, bool kDropT = false>
 __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, int head, int b, int row0, int nrows) {
   auto sync = [] {
     if (kBar == 0) __syncthreads();
@@ -254,9 +255,12 @@ __device__ __forceinline__ void attn_tail_rows(const AttnParams& p, float* sm, i
         sdot += __shfl_xor_sync(gmask, sdot, 2);   //  so the mask names only this group)
         sdot += __shfl_xor_sync(gmask, sdot, 4);
         const float m_new = fmaxf(m, sdot);
-        const float a = ex2(m - m_new), pj = ex2(sdot - m_new);
+        const float a = ex2(m - m_new);
+        float pj = ex2(sdot - m_new);
         m = m_new;
-        l = l * a + pj;
+        l = l * a + pj;                                               // the normaliser keeps every key: dropout follows the softmax
+        if (kDropT)
+          pj *= drop_factor(p.drop, (static_cast<uint64_t>(b) * p.heads + head) * p.N + q, static_cast<uint32_t>(grp + step * kGroups));
         const float2 v0 = unpack_bf16x2(vu.x), v1 = unpack_bf16x2(vu.y), v2 = unpack_bf16x2(vu.z), v3 = unpack_bf16x2(vu.w);
         o[0] = fmaf(o[0], a, pj * v0.x); o[1] = fmaf(o[1], a, pj * v0.y); o[2] = fmaf(o[2], a, pj * v1.x); o[3] = fmaf(o[3], a, pj * v1.y);
         o[4] = fmaf(o[4], a, pj * v2.x); o[5] = fmaf(o[5], a, pj * v2.y); o[6] = fmaf(o[6], a, pj * v3.x); o[7] = fmaf(o[7], a, pj * v3.y);
@@ -1010,7 +1014,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         // row out of range -- a score more than ~88 nats above its row's block-0 maximum -- recomputes its tile exactly on the CUDA
         // cores (attn_tail_rows) before it exits.  A guard per block (redo from the scores in registers) was measured first: keeping the
         // 64 scores live next to the 32 packed P registers spills 16 STL.64 + 32 LDL per block and costs what the maximum did.
-        const bool do_max = (j == 0) || (kBias && !kFused) || kDrop;   // (plain and fused instantiations run maximum-free blocks)
+        const bool do_max = (j == 0) || (kBias && !kFused);   // (the plain, dropout and fused instantiations run maximum-free blocks)
         if (do_max) {
         // block maximum of this half row (four independent chains), exchanged with the other half-row thread
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -1170,14 +1174,14 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       if (half == 0 && p.lse) p.lse[(static_cast<int64_t>(b) * p.heads + head) * p.N + q] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
     }
     }   // !idle_rows
-    if ((!kBias || kFused) && !kDrop) {
+    if (!kBias || kFused) {
       // Maximum-free blocks: a row sum out of range means P overflowed somewhere in this tile.  The eight softmax warps agree through
       // shared memory and recompute the tile's rows exactly on the CUDA cores (K / V straight from global memory; every TMA load and
       // MMA of this CTA has completed, its shared memory is free).  Never taken for scores within ~88 nats of a row's block-0 maximum.
       volatile uint32_t* s_flag = reinterpret_cast<volatile uint32_t*>(bars) + 32;
       if (__any_sync(0xffffffffu, bad_row) && lane == 0) *s_flag = 1u;
       asm volatile("bar.sync 5, 256;" ::: "memory");
-      if (*s_flag != 0u) attn_tail_rows<kSoftmaxWarps * 32, 5, kFused>(p, reinterpret_cast<float*>(smem), head, b, q0, min(kBQ, p.N - q0));
+      if (*s_flag != 0u) attn_tail_rows<kSoftmaxWarps * 32, 5, kFused, kDrop>(p, reinterpret_cast<float*>(smem), head, b, q0, min(kBQ, p.N - q0));
     }
   }
   tc_fence_before();
