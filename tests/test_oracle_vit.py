@@ -40,3 +40,29 @@ def test_vit_oracle_matches_hf():
         dense, tok = vit_fp32.vit_forward(w, cfg, x, return_tokens=True)
     assert torch.allclose(tok, want, atol=2e-5, rtol=1e-4)
     assert dense.shape == (2, 4, 4, 128) and torch.equal(dense.reshape(2, 16, 128), tok[:, 1:])
+
+
+def test_gray2rgb_patch_embedding_equals_channel_summed_weights():
+    """The identity behind vdr_patch_embed_gemm_gray (include/vdr.h): a gray slice fed to the three input channels (gray2rgb,
+    reference tfds_dense_descriptor.py:41) through Conv2d(3, d, p, p) == the same slice through the weights summed over the input
+    channels -- in f64 exactly, in f32 to rounding; and the oracle's whole forward agrees when its patch weights are replaced by
+    (W_r + W_g + W_b) / 3 in every channel."""
+    import torch.nn.functional as F
+    cfg = vit_fp32.VIT_CONFIGS["vit_t16"] if "vit_t16" in vit_fp32.VIT_CONFIGS else next(iter(vit_fp32.VIT_CONFIGS.values()))
+    hw = (64, 64)
+    w = vit_fp32.init_weights(cfg, hw, seed=5)
+    g = torch.rand(2, 1, *hw, generator=torch.Generator().manual_seed(1))
+    x3 = g.expand(-1, 3, -1, -1).contiguous()
+    W, b, p = w["patch_embed.weight"], w["patch_embed.bias"], cfg["patch"]
+    a = F.conv2d(x3.double(), W.double(), b.double(), stride=p)
+    c = F.conv2d(g.double(), W.double().sum(dim=1, keepdim=True), b.double(), stride=p)
+    assert torch.allclose(a, c, rtol=0, atol=1e-12)
+    a32 = F.conv2d(x3, W, b, stride=p)
+    c32 = F.conv2d(g, W.sum(dim=1, keepdim=True), b, stride=p)
+    assert (a32 - c32).abs().max() < 1e-5
+    w2 = dict(w)
+    w2["patch_embed.weight"] = (W.sum(dim=1, keepdim=True) / 3).expand(-1, 3, -1, -1).contiguous()
+    with torch.no_grad():
+        d0 = vit_fp32.vit_forward(w, cfg, x3)
+        d1 = vit_fp32.vit_forward(w2, cfg, x3)
+    assert (d0 - d1).abs().max() < 1e-4
