@@ -143,3 +143,36 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for field, _ in cls._fields_:
             assert int(got[f"{cname}.{field}"]) == getattr(cls, field).offset, (cname, field)
+
+
+def test_hot_kernels_are_tcgen05_tma_code():
+    """Static check of the shipped library (no GPU): it holds sm_100a SASS only, and the kernels of the hot path issue tcgen05.mma
+    (UTCHMMA) fed by TMA (UTMALDG) with TMEM read-back (LDTM) -- a build that lost them (wrong arch, a mma.sync rewrite) fails here
+    before it reaches the GPU box.  tools/sass_report.py prints the full per-kernel table (profiles/r02_sass_report.md)."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import sass_report
+    finally:
+        sys.path.pop(0)
+    lib = os.path.join(ROOT, "vit_deep_radiomics_b200", "lib", "libvdr.so")
+    archs = set(re.findall(r"arch = (sm_\w+)", subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+                           + subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout))
+    assert archs == {"sm_100a"}, archs
+    per_kernel = sass_report.mnemonic_counts(lib)
+    by_name = {}
+    for name, c in per_kernel.items():
+        by_name.setdefault(name.split("<")[0], []).append(c)
+    for kernel in ("vdr::gemm_tcgen05_kernel", "vdr::flash_attn_fwd_kernel", "vdr::flash_attn_fwd_v6_kernel", "vdr::flash_attn_bwd_kernel",
+                   "vdr::attn_win14_tc_kernel"):
+        assert kernel in by_name, f"{kernel} missing from libvdr.so"
+        for c in by_name[kernel]:
+            assert c["UTCHMMA"] > 0 and c["UTMALDG"] > 0 and c["LDTM"] > 0, (kernel, dict(c))
+    assert any(c["2CTA"] > 0 for c in by_name["vdr::gemm_tcgen05_kernel"])          # CTA pairs (cta_group::2) in the GEMM
+    assert all(c["HMMA"] == 0 for c in by_name["vdr::gemm_tcgen05_kernel"] + by_name["vdr::attn_win14_tc_kernel"])
+    for kernel in ("vdr::g1_fused_kernel", "vdr::layernorm_fwd_kernel", "vdr::rot_interp_kernel"):
+        assert kernel in by_name
