@@ -3,7 +3,9 @@ logit, plus CLS-token cosine >= 0.999 in BF16 versus the reference FP32").
 
 Every check records its measured triplet (max |err|, rms relative error, min row cosine); a `-m gpu` session writes them to
 ``gpurun_out/parity_measured.json``.  BOUNDS holds, per key, about twice the value measured on a B200 (round 2;
-``tests/golden/parity_measured_r02.json`` keeps that run's numbers); keys without an entry fall back to DEFAULT."""
+``tests/golden/parity_measured_r02.json`` keeps the numbers of the last full `-m gpu` run of the round, on the final kernels; where two
+runs of the round differed -- the attention kernels changed between them -- a bound is twice the larger value); keys without an entry
+fall back to DEFAULT."""
 import numpy as np
 
 DEFAULT = dict(abs=0.12, rel=0.02, cos=0.999)
@@ -12,17 +14,17 @@ BOUNDS: dict = {
     "bimodal gradients (golden, both)": dict(abs=0.00023, rel=0.024, cos=0.99987),
     "bimodal gradients (golden, ct)": dict(abs=0.0024, rel=0.047, cos=0.99948),
     "bimodal gradients (golden, pet)": dict(abs=0.0038, rel=0.039, cos=0.99966),
-    "classifier CLS (d256 ff1024 h4 L2, n=2000)": dict(abs=0.031, rel=0.011, cos=0.99997),
+    "classifier CLS (d256 ff1024 h4 L2, n=2000)": dict(abs=0.045, rel=0.011, cos=0.99997),
     "classifier CLS (golden, small)": dict(abs=0.025, rel=0.009, cos=0.99998),
     "classifier gradients (golden, small)": dict(abs=0.0015, rel=0.02, cos=0.99992),
-    "classifier logits (d256 ff1024 h4 L2, n=2000)": dict(abs=0.011, rel=0.0092, cos=0.99998),
+    "classifier logits (d256 ff1024 h4 L2, n=2000)": dict(abs=0.012, rel=0.013, cos=0.99998),
     "classifier logits (golden, small)": dict(abs=0.0021, rel=0.0061, cos=0.99999),
     "descriptors medsam (SAM ViT-B)@1024x1024": dict(abs=0.12, rel=0.023, cos=0.99982),
-    "descriptors sam_tiny vs HF golden": dict(abs=0.061, rel=0.014, cos=0.99992),
+    "descriptors sam_tiny vs HF golden": dict(abs=0.063, rel=0.014, cos=0.99991),
     "descriptors sam_tiny@128x1024 (kernel variants)": dict(abs=0.062, rel=0.013, cos=0.99991),
     "descriptors sam_tiny@192x320": dict(abs=0.06, rel=0.014, cos=0.99990),
-    "descriptors sam_tiny@224x224": dict(abs=0.052, rel=0.013, cos=0.99993),
-    "descriptors sam_tiny@256x256": dict(abs=0.057, rel=0.013, cos=0.99992),
+    "descriptors sam_tiny@224x224": dict(abs=0.06, rel=0.013, cos=0.99992),
+    "descriptors sam_tiny@256x256": dict(abs=0.061, rel=0.013, cos=0.99992),
     "descriptors unfolded vit_s16@256": dict(abs=0.14, rel=0.019, cos=0.99988),
     "descriptors unfolded vit_t16@64": dict(abs=0.052, rel=0.009, cos=0.99996),
     "descriptors vit_b16@512x512 (C2)": dict(abs=0.15, rel=0.019, cos=0.99989),          # the bench line's workload
@@ -37,7 +39,7 @@ BOUNDS: dict = {
     "generate_features T0": dict(abs=0.055, rel=0.0094, cos=0.99997),
     "generate_features resized crop": dict(abs=0.04, rel=0.0095, cos=0.99997),
     "get_dense_descriptor vit_t16@64x64": dict(abs=0.052, rel=0.0091, cos=0.99997),
-    "point-cloud tokens C1": dict(abs=0.11, rel=0.018, cos=0.99990),
+    "point-cloud tokens C1": dict(abs=0.13, rel=0.018, cos=0.99990),
     "point-cloud tokens T0": dict(abs=0.052, rel=0.009, cos=0.99997),
     "point-cloud tokens vit_b16@512x512 (C2)": dict(abs=0.13, rel=0.019, cos=0.99990),
     "point-cloud tokens vit_l14@224x224 (C4)": dict(abs=0.24, rel=0.026, cos=0.99980),
