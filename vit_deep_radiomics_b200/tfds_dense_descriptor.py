@@ -347,12 +347,15 @@ class PointCloudExtractor:
     def _upload(self, slot, img_t, mask_t):
         dev = self.model.device
         b = self.slots[slot]
-        if b.get("shape") != tuple(img_t.shape):
-            b.update(shape=tuple(img_t.shape), img=torch.empty(img_t.shape, dtype=torch.float32, device=dev),
-                     mask=torch.empty(mask_t.shape, dtype=torch.uint8, device=dev),
-                     bbox=torch.empty(6, dtype=torch.int32, device=dev),
-                     bbox_host=torch.empty(6, dtype=torch.int32).pin_memory(), ev=torch.cuda.Event(), ev_box=torch.cuda.Event())
         with torch.cuda.stream(self.copy_stream):
+            if b.get("shape") != tuple(img_t.shape):
+                # allocated in the COPY stream's pool: a block of the main stream's pool may have been freed by Python while kernels
+                # that use it are still queued there (the previous patient's point cloud with to_host=False), and the copies below
+                # would overwrite it without waiting for them.  Real datasets change shape with every patient.
+                b.update(shape=tuple(img_t.shape), img=torch.empty(img_t.shape, dtype=torch.float32, device=dev),
+                         mask=torch.empty(mask_t.shape, dtype=torch.uint8, device=dev),
+                         bbox=torch.empty(6, dtype=torch.int32, device=dev),
+                         bbox_host=torch.empty(6, dtype=torch.int32).pin_memory(), ev=torch.cuda.Event(), ev_box=torch.cuda.Event())
             if "free" in b:
                 self.copy_stream.wait_event(b["free"])          # the previous user of this slot has been consumed
             b["mask"].copy_(mask_t, non_blocking=True)
@@ -529,15 +532,22 @@ class PointCloudExtractor:
 
         import contextlib
         cur = fetch(groups[0], contextlib.nullcontext) if groups else {}
+        fwd_prev = fwd_cur = None          # main-stream events behind the forward of the previous / this group
         for gi, grp in enumerate(groups):
             vols = [(cur[i] if cur[i].is_contiguous() else cur[i].contiguous(), staged[i][5]["crop"]) for i in grp]
             if len(vols) > 1:
                 tok = model.forward_volumes(vols)
             else:
                 tok = _forward_volume(model, vols[0][0], staged[grp[0]][5])
+            fwd_prev, fwd_cur = fwd_cur, torch.cuda.Event()
+            fwd_cur.record(main)
             nxt, ev = None, None
             if gi + 1 < len(groups) and any(not staged[i][1].is_cuda for i in groups[gi + 1]):
-                # the next batch's volumes cross PCIe while this one is in the backbone
+                # the next batch's volumes cross PCIe while this one is in the backbone.  Their buffers come from the copy stream's
+                # pool, which hands out the previous group's volumes again as soon as Python dropped them -- while the host runs
+                # several groups ahead of the GPU: the copies must not start before that group's forward has read them.
+                if fwd_prev is not None:
+                    self.copy_stream.wait_event(fwd_prev)
                 nxt = fetch(groups[gi + 1], lambda: torch.cuda.stream(self.copy_stream))
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
@@ -553,6 +563,8 @@ class PointCloudExtractor:
             if ev is not None:
                 main.wait_event(ev)
             cur = nxt
+        if fwd_cur is not None:
+            self.copy_stream.wait_event(fwd_cur)    # the last volumes go back to the copy stream's pool when this returns
         return table.all_gather()
 
 
