@@ -532,15 +532,17 @@ class PointCloudExtractor:
 
         import contextlib
         cur = fetch(groups[0], contextlib.nullcontext) if groups else {}
-        fwd_prev = fwd_cur = None          # main-stream events behind the forward of the previous / this group
+        host_side = any(not st[1].is_cuda for st in staged)
+        fwd_prev = fwd_cur = None          # main-stream events behind the forward of the previous / this group (host-side volumes only)
         for gi, grp in enumerate(groups):
             vols = [(cur[i] if cur[i].is_contiguous() else cur[i].contiguous(), staged[i][5]["crop"]) for i in grp]
             if len(vols) > 1:
                 tok = model.forward_volumes(vols)
             else:
                 tok = _forward_volume(model, vols[0][0], staged[grp[0]][5])
-            fwd_prev, fwd_cur = fwd_cur, torch.cuda.Event()
-            fwd_cur.record(main)
+            if host_side:
+                fwd_prev, fwd_cur = fwd_cur, torch.cuda.Event()
+                fwd_cur.record(main)
             nxt, ev = None, None
             if gi + 1 < len(groups) and any(not staged[i][1].is_cuda for i in groups[gi + 1]):
                 # the next batch's volumes cross PCIe while this one is in the backbone.  Their buffers come from the copy stream's
