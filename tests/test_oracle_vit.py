@@ -5,13 +5,14 @@ import torch
 from oracle import vit_fp32
 
 
-def test_vit_oracle_matches_hf():
+@pytest.mark.parametrize("patch,H,W", [(16, 64, 64), (14, 56, 84), (16, 48, 80)])
+def test_vit_oracle_matches_hf(patch, H, W):
+    """patch 16 square (C1 / C2 geometry), patch 14 and non-square grids (C4's ViT-L/14 geometry; crops resized to other inputs)."""
     tr = pytest.importorskip("transformers")
-    cfg = dict(dim=128, depth=2, heads=2, patch=16)
-    H = W = 64
+    cfg = dict(dim=128, depth=2, heads=2, patch=patch)
     w = vit_fp32.init_weights(cfg, (H, W), seed=3)
     hf_cfg = tr.ViTConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
-                          image_size=H, patch_size=16, hidden_act="gelu", layer_norm_eps=1e-6, qkv_bias=True,
+                          image_size=(H, W), patch_size=patch, hidden_act="gelu", layer_norm_eps=1e-6, qkv_bias=True,
                           hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     m = tr.ViTModel(hf_cfg, add_pooling_layer=False).eval()
     sd = m.state_dict()
@@ -39,7 +40,8 @@ def test_vit_oracle_matches_hf():
         want = m(pixel_values=x).last_hidden_state
         dense, tok = vit_fp32.vit_forward(w, cfg, x, return_tokens=True)
     assert torch.allclose(tok, want, atol=2e-5, rtol=1e-4)
-    assert dense.shape == (2, 4, 4, 128) and torch.equal(dense.reshape(2, 16, 128), tok[:, 1:])
+    gh, gw = H // patch, W // patch
+    assert dense.shape == (2, gh, gw, 128) and torch.equal(dense.reshape(2, gh * gw, 128), tok[:, 1:])
 
 
 def test_gray2rgb_patch_embedding_equals_channel_summed_weights():
