@@ -176,3 +176,38 @@ def test_hot_kernels_are_tcgen05_tma_code():
     assert all(c["HMMA"] == 0 for c in by_name["vdr::gemm_tcgen05_kernel"] + by_name["vdr::attn_win14_tc_kernel"])
     for kernel in ("vdr::g1_fused_kernel", "vdr::layernorm_fwd_kernel", "vdr::rot_interp_kernel"):
         assert kernel in by_name
+
+
+def test_integration_guide_stub_binds_the_shipped_library():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer (section 2, first code block) is executed as written: every
+    symbol it binds exists, and its struct mirrors have the layout of the package's own binding."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if b.startswith("import ctypes, torch"))
+    cwd = os.getcwd()
+    os.chdir(ROOT)                                   # the stub loads the library by its repo-relative path
+    try:
+        ns: dict = {}
+        exec(compile(stub, "INTEGRATION.md section 2", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    for name in ("check", "layernorm", "linear_gelu", "image_encoder"):
+        assert callable(ns[name]), name
+    sam = next(b for b in blocks if "class SamBlock" in b)                        # second block: only its struct mirrors are executable
+    exec(compile(re.search(r"class SamBlock.*?\n(?=lib\.vdr_sam_forward_workspace_bytes)", sam, flags=re.S).group(0), "INTEGRATION.md 2a", "exec"), ns)
+    for name in ("Dropout", "GemmArgs", "VitBlock", "VitWeights", "SamBlock", "SamWeights"):
+        doc, own = ns[name], getattr(_C, name)
+        assert ctypes.sizeof(doc) == ctypes.sizeof(own), name
+        assert [(f[0], ctypes.sizeof(f[1])) for f in doc._fields_] == [(f[0], ctypes.sizeof(f[1])) for f in own._fields_], name
+    own_lib, bound = _C.lib(), 0
+    for name in _C.EXPORTS:                                                       # every prototype the stub declares == the package's
+        doc_args = getattr(ns["lib"], name).argtypes
+        if doc_args is not None:
+            own_args = getattr(own_lib, name).argtypes
+            assert [ctypes.sizeof(t) for t in doc_args] == [ctypes.sizeof(t) for t in own_args], name
+            bound += 1
+    assert bound >= 3
+    with pytest.raises(ValueError):
+        ns["check"](-1, "x")
+    with pytest.raises(RuntimeError):
+        ns["check"](700, "x")
