@@ -183,6 +183,7 @@ def test_integration_guide_stub_binds_the_shipped_library():
     symbol it binds exists, and its struct mirrors have the layout of the package's own binding."""
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    exec(compile(blocks[0].replace("/path/to/this/repo", ROOT), "INTEGRATION.md section 1", "exec"), {})   # the module-level imports exist
     stub = next(b for b in blocks if b.startswith("import ctypes, torch"))
     cwd = os.getcwd()
     os.chdir(ROOT)                                   # the stub loads the library by its repo-relative path
