@@ -54,3 +54,35 @@ def test_files_named_in_the_docs_exist():
             assert os.path.exists(os.path.join(ROOT, path)), (doc, path)
         for path in sorted(set(re.findall(r"`(csrc/[A-Za-z0-9_]+\.cuh?)`", text))):
             assert os.path.exists(os.path.join(ROOT, "vit_deep_radiomics_b200", path)), (doc, path)
+
+
+def test_reference_citations_are_in_range():
+    """Every `file.py:line[-line]` citation of a reference source (header, oracle, package docstrings, kernels, documents) names a
+    file of the reference with at least that many lines.  Needs /root/reference (this container only)."""
+    import pytest
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    n_lines = {}
+    for r, _, files in os.walk(ref):
+        if ".git" in r:
+            continue
+        for f in files:
+            if f.endswith((".py", ".yaml", ".sh")):
+                n = sum(1 for _ in open(os.path.join(r, f), errors="ignore"))
+                n_lines[f] = max(n, n_lines.get(f, 0))
+    sources = (glob.glob(os.path.join(ROOT, "vit_deep_radiomics_b200", "*.py")) + glob.glob(os.path.join(ROOT, "oracle", "*.py"))
+               + glob.glob(os.path.join(ROOT, "vit_deep_radiomics_b200", "csrc", "*.cu*"))
+               + [os.path.join(ROOT, f) for f in ("include/vdr.h", "DESIGN.md", "INTEGRATION.md")])
+    checked = 0
+    for s in sources:
+        for m in re.finditer(r"\b([a-z_]+\.(?:py|yaml|sh)):(\d+(?:-\d+)?(?:,\d+(?:-\d+)?)*)", open(s).read()):
+            f = m.group(1)
+            if f not in n_lines:
+                continue
+            for span in m.group(2).split(","):
+                lo, _, hi = span.partition("-")
+                lo, hi = int(lo), int(hi or lo)
+                assert 1 <= lo <= hi <= n_lines[f], (os.path.basename(s), m.group(0), n_lines[f])
+                checked += 1
+    assert checked > 150
