@@ -212,3 +212,46 @@ def test_integration_guide_stub_binds_the_shipped_library():
         ns["check"](-1, "x")
     with pytest.raises(RuntimeError):
         ns["check"](700, "x")
+
+
+def test_argument_and_return_kinds_match_the_header():
+    """Per parameter: pointer / integer width / float width of the ctypes prototype == the header's C type (an int64_t bound as
+    c_int, or a double as c_float, still 'works' in registers and corrupts on the stack); size_t / 64-bit returns are not truncated."""
+    lib = _C.lib()
+    text = open(os.path.join(ROOT, "include", "vdr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    scalar = {"int": ("int", 4), "int32_t": ("int", 4), "uint32_t": ("int", 4), "unsigned": ("int", 4), "int64_t": ("int", 8),
+              "uint64_t": ("int", 8), "size_t": ("int", 8), "float": ("flt", 4), "double": ("flt", 8)}
+
+    def c_kind(param):
+        if "*" in param or "vdr_stream_t" in param:
+            return ("ptr", 8)
+        toks = param.replace("const", "").split()
+        return scalar[" ".join(toks[:-1]) if len(toks) > 1 else toks[0]]
+
+    def py_kind(t):
+        if t is ctypes.c_float:
+            return ("flt", 4)
+        if t is ctypes.c_double:
+            return ("flt", 8)
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, (ctypes._Pointer, ctypes.Array))):
+            return ("ptr", 8)
+        return ("int", ctypes.sizeof(t))
+
+    for name in _C.EXPORTS:
+        m = re.search(r"([A-Za-z_0-9\* ]+?)\s*\b" + name + r"\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+        assert m, name
+        fn = getattr(lib, name)
+        params = [p for p in (q.strip() for q in m.group(2).split(",")) if p and p != "void"]
+        for i, (p, t) in enumerate(zip(params, fn.argtypes or [])):
+            assert c_kind(p) == py_kind(t), (name, i, p, t)
+        ret = m.group(1).strip().split("\n")[-1].strip()
+        if ret == "int":
+            assert fn.restype is ctypes.c_int, name
+        elif ret in ("size_t", "uint64_t", "int64_t"):
+            assert fn.restype is not None and ctypes.sizeof(fn.restype) == 8, name
+        elif ret == "const char*":
+            assert fn.restype is ctypes.c_char_p, name
+        else:
+            assert ret == "void", (name, ret)
