@@ -86,3 +86,26 @@ def test_reference_citations_are_in_range():
                 assert 1 <= lo <= hi <= n_lines[f], (os.path.basename(s), m.group(0), n_lines[f])
                 checked += 1
     assert checked > 150
+
+
+def test_parity_bounds_are_about_twice_the_measured_error():
+    """tests/parity.py states every float bound as ~2x what the last full B200 run measured (tests/golden/parity_measured_r02.json):
+    each bound must hold that run with margin (>= 1.5x) without being loose (<= 3x; cosine bounds are rounded to five decimals,
+    so they are only checked where 1 - cos is above that rounding)."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import parity
+    finally:
+        sys.path.pop(0)
+    measured = json.load(open(os.path.join(ROOT, "tests", "golden", "parity_measured_r02.json")))
+    assert set(measured) == set(parity.BOUNDS)            # every measured check has its own stated bound, and vice versa
+    for key, b in parity.BOUNDS.items():
+        m = measured[key]
+        for what in ("abs", "rel"):
+            assert 1.5 <= b[what] / m[what] <= 3.0, (key, what, b[what], m[what])
+        if 1.0 - m["cos"] > 5e-6:
+            assert 1.5 <= (1.0 - b["cos"]) / (1.0 - m["cos"]) <= 4.0, (key, b["cos"], m["cos"])
+        else:
+            assert b["cos"] >= 0.9999
