@@ -166,7 +166,7 @@ def test_run_fold_world_size_2(tmp_path):
     assert {"train_metrics_0.json", "test_metrics_0.json", "train_metrics_1.json", "test_metrics_1.json", "model_epoch_0000.pth"} <= set(out[0][1])
 
 
-def _table_worker(rank, world, port, out):
+def _table_worker(rank, world, port, out, n_rows=(4, 0, 7, 3, 5)):
     """PointCloudTable host logic at world size 2 (gloo, CPU tensors): contiguous patient shards, padded count exchange,
     offsets, in-place variable-length all-gather == the single-process table, on every rank.  (The device side -- the gather
     kernel writing at a device-resident offset -- is covered by tests/test_gpu_gather.py::test_g1_count_scan_and_table_slots.)"""
@@ -175,7 +175,7 @@ def _table_worker(rank, world, port, out):
     from vit_deep_radiomics_b200.distributed import PointCloudTable
     g = torch.Generator().manual_seed(3)
     P, D = 5, 6                                                   # 5 patients over 2 ranks: shards of 3 and 2 (padded to 3)
-    n_rows = [4, 0, 7, 3, 5]
+    n_rows = list(n_rows)
     clouds = [torch.randn(n, D, generator=g) for n in n_rows]
     keys = [torch.stack([torch.full((n,), p), torch.arange(n) % 3, torch.arange(n) // 3, torch.arange(n)], 1).int() for p, n in enumerate(n_rows)]
     table = PointCloudTable(P, D, cap_rows=sum(n_rows) + 2, device="cpu")
@@ -189,7 +189,9 @@ def _table_worker(rank, world, port, out):
         slot["src"][off:off + n_rows[p]] = keys[p]
     total = table.all_gather()
     ok = total == sum(n_rows) and torch.equal(table.tokens[:total], torch.cat(clouds)) and torch.equal(table.src[:total], torch.cat(keys))
-    ok_off = table.offsets.tolist() == ([0, 4, 4, 11, 14, 19, 19] if world == 2 else None)
+    # padded, rank-major count vector: rank 0 = patients 0..2, rank 1 = patients 3, 4 + one pad slot
+    padded = n_rows[:3] + n_rows[3:] + [0]
+    ok_off = table.offsets.tolist() == [0] + [sum(padded[:i + 1]) for i in range(6)]
     out[rank] = (ok, ok_off, list(table.local_patients()))
     dist.destroy_process_group()
 
@@ -199,6 +201,16 @@ def test_point_cloud_table_world_size_2():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_table_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == (True, True, [0, 1, 2]) and out[1] == (True, True, [3, 4]), dict(out)
+
+
+def test_point_cloud_table_rank_without_rows():
+    """A rank whose patients select nothing (every mask empty inside its ROI) contributes an empty range: the exchange skips it
+    and both ranks still end with the single-process table."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_table_worker, args=(world, _free_port(), out, (4, 2, 7, 0, 0)), nprocs=world, join=True)
     assert out[0] == (True, True, [0, 1, 2]) and out[1] == (True, True, [3, 4]), dict(out)
 
 
