@@ -109,3 +109,10 @@ def test_parity_bounds_are_about_twice_the_measured_error():
             assert 1.5 <= (1.0 - b["cos"]) / (1.0 - m["cos"]) <= 4.0, (key, b["cos"], m["cos"])
         else:
             assert b["cos"] >= 0.9999
+
+
+def test_entry_point_count_in_design_matches_the_header():
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vdr.h")).read(), flags=re.S)
+    n = len(set(re.findall(r"\b(vdr_[a-z0-9_]+)\s*\(", header)))
+    m = re.search(r"`include/vdr.h`, (\d+) entry points", open(os.path.join(ROOT, "DESIGN.md")).read())
+    assert m and int(m.group(1)) == n, (m and m.group(1), n)
